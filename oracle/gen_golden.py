@@ -1,0 +1,305 @@
+"""oracle/gen_golden.py — TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.npz by running the reference's OWN modules, imported unchanged from
+/root/reference behind oracle/ref_stubs.py, on small seeded inputs.  Run in the authoring container
+(where /root/reference is mounted); the resulting vectors are committed so that the GPU box — where
+the reference does not exist — can still check the oracle port (and through it the CUDA path).
+
+    python -m oracle.gen_golden            # writes tests/golden/
+"""
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from . import ref_stubs as rs
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+@contextlib.contextmanager
+def cuda_as_cpu():
+    """The reference hard-codes device='cuda' (attentive_modules.py:199, class_embedding.py:13,
+    roi_heads.py:927).  Redirect those `.to('cuda')` calls to CPU without touching the sources."""
+    orig = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        if isinstance(k.get("device"), str) and k["device"].startswith("cuda"):
+            k["device"] = "cpu"
+        return orig(self, *a, **k)
+
+    torch.Tensor.to = to
+    try:
+        yield
+    finally:
+        torch.Tensor.to = orig
+
+
+def sd_to_np(sd, prefix=""):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def synth_proposals(n, h, w, gen, n_obj=4):
+    """70 % RPN-like boxes + 30 % jittered copies of object boxes."""
+    def rand_boxes(m):
+        cx = torch.rand(m, generator=gen) * w
+        cy = torch.rand(m, generator=gen) * h
+        side = torch.exp(torch.rand(m, generator=gen) * (np.log(min(h, w)) - np.log(16.0)) + np.log(16.0))
+        asp = torch.exp((torch.rand(m, generator=gen) * 2 - 1) * np.log(3.0))
+        bw, bh = side * torch.sqrt(asp), side / torch.sqrt(asp)
+        b = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+        b[:, 0::2] = b[:, 0::2].clamp(0, w)
+        b[:, 1::2] = b[:, 1::2].clamp(0, h)
+        return b
+    n_j = int(0.3 * n)
+    objs = rand_boxes(n_obj)
+    j = objs[torch.randint(0, n_obj, (n_j,), generator=gen)] + torch.randn(n_j, 4, generator=gen) * 8.0
+    j[:, 0::2] = j[:, 0::2].clamp(0, w)
+    j[:, 1::2] = j[:, 1::2].clamp(0, h)
+    b = torch.cat([rand_boxes(n - n_j), j], 0)
+    # keep boxes non-degenerate (RPN removes empty boxes)
+    b[:, 2] = torch.maximum(b[:, 2], b[:, 0] + 1.0).clamp(max=w)
+    b[:, 3] = torch.maximum(b[:, 3], b[:, 1] + 1.0).clamp(max=h)
+    b[:, 0] = torch.minimum(b[:, 0], b[:, 2] - 1.0).clamp(min=0)
+    b[:, 1] = torch.minimum(b[:, 1], b[:, 3] - 1.0).clamp(min=0)
+    return b, objs
+
+
+def gen_gdl():
+    gdl = rs.load("defrcn.modeling.meta_arch.gdl")
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(2, 6, 5, 7)).requires_grad_(True)
+    aff = gdl.AffineLayer(6, bias=True)
+    with torch.no_grad():
+        aff.weight.copy_(torch.randn(1, 6, 1, 1))
+        aff.bias.copy_(torch.randn(1, 6, 1, 1))
+    lam = 0.001
+    y = aff(gdl.decouple_layer(x, lam))
+    g = torch.randn_like(y)
+    y.backward(g)
+    np.savez_compressed(os.path.join(OUT, "gdl.npz"), x=x.detach().numpy(), w=aff.weight.detach().numpy(),
+                        b=aff.bias.detach().numpy(), lam=np.float32(lam), y=y.detach().numpy(),
+                        g=g.numpy(), gx=x.grad.numpy(), gw=aff.weight.grad.numpy(), gb=aff.bias.grad.numpy())
+
+
+def gen_fast_rcnn_inference():
+    fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
+    gen = torch.Generator().manual_seed(11)
+    out = {}
+    for tag, (R, K, h, w, peaked, ties) in {
+        "voc": (300, 20, 600, 800, 0.3, False),
+        "coco": (200, 80, 480, 640, 0.5, False),
+        "ties": (128, 5, 300, 400, 0.6, True),
+        "empty": (16, 20, 600, 800, 0.0, False),
+    }.items():
+        props, _ = synth_proposals(R, h, w, gen)
+        logits = torch.randn(R, K + 1, generator=gen)
+        logits[:, K] += 4.0 if peaked > 0 else 12.0
+        npk = int(peaked * R)
+        if npk:
+            cls = torch.randint(0, K, (npk,), generator=gen)
+            logits[torch.arange(npk), cls] += 8.0
+        if ties:  # exactly duplicated rows: equal scores and identical boxes
+            logits[R // 2:] = logits[:R - R // 2]
+            props[R // 2:] = props[:R - R // 2]
+        deltas = torch.randn(R, 4 * K, generator=gen) * 0.5
+        if ties:
+            deltas[R // 2:] = deltas[:R - R // 2]
+        inst = rs.Instances((h, w))
+        inst.proposal_boxes = rs.Boxes(props.clone())
+        o = fr.FastRCNNOutputs(rs.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), logits, deltas, [inst], 0.0)
+        boxes = o.predict_boxes()[0]
+        probs = o.predict_probs()[0]
+        res, roi_inds = fr.fast_rcnn_inference_single_image(boxes.clone(), probs, (h, w), 0.05, 0.5, 100)
+        ncand = int((probs[:, :-1] > 0.05).sum())
+        out.update({
+            tag + "_props": props.numpy(), tag + "_logits": logits.numpy(), tag + "_deltas": deltas.numpy(),
+            tag + "_hw": np.array([h, w], np.int64), tag + "_pred_boxes_all": boxes.numpy(),
+            tag + "_probs": probs.numpy(), tag + "_ncand": np.int64(ncand),
+            tag + "_boxes": res.pred_boxes.tensor.numpy(), tag + "_scores": res.scores.numpy(),
+            tag + "_classes": res.pred_classes.numpy(), tag + "_roi_inds": roi_inds.numpy(),
+        })
+    np.savez_compressed(os.path.join(OUT, "fast_rcnn_inference.npz"), **out)
+
+
+def gen_losses():
+    fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
+    gen = torch.Generator().manual_seed(5)
+    R, K, h, w = 96, 15, 600, 800
+    props, objs = synth_proposals(R, h, w, gen)
+    gt_classes = torch.randint(0, K + 1, (R,), generator=gen)
+    gt_classes[R // 3:] = K
+    gt_boxes = props + torch.randn(R, 4, generator=gen) * 4
+    gt_boxes[:, 2:] = torch.maximum(gt_boxes[:, 2:], gt_boxes[:, :2] + 2)
+    logits = torch.randn(R, K + 1, generator=gen)
+    deltas = torch.randn(R, 4 * K, generator=gen) * 0.1
+    inst = rs.Instances((h, w))
+    inst.proposal_boxes = rs.Boxes(props)
+    inst.gt_boxes = rs.Boxes(gt_boxes)
+    inst.gt_classes = gt_classes
+    o = fr.FastRCNNOutputs(rs.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), logits, deltas, [inst], 0.0)
+    L = o.losses()
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), props=props.numpy(), gt_boxes=gt_boxes.numpy(),
+                        gt_classes=gt_classes.numpy(), logits=logits.numpy(), deltas=deltas.numpy(),
+                        loss_cls=L["loss_cls"].numpy(), loss_box_reg=L["loss_box_reg"].numpy(),
+                        cls_accuracy=np.float64(rs.get_event_storage().scalars["fast_rcnn/cls_accuracy"]))
+
+
+def gen_attention(d_model=32, R=40, K=20, tag="attention_small"):
+    rs.install(class_embed_fn=lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg))
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    am.get_class_embed = lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg)
+    cfg = rs.default_cfg(num_classes=K, addition="clip")
+    torch.manual_seed(0)
+    with cuda_as_cpu():
+        att = am.SematicProposalAttention(d_model, cfg=cfg).eval()
+        x = torch.relu(torch.randn(R, d_model, generator=torch.Generator().manual_seed(3)))
+        with torch.no_grad():
+            attn, out = att(x)
+    d = sd_to_np(att.state_dict(), "attention.")
+    d.update(x=x.numpy(), embed=att.embed.numpy(), bg_feature=att.bg_feature.numpy(),
+             sim2stext=out["sim2stext"].numpy(), text_feat=out["text_feat"].numpy(), attn=attn[0].numpy())
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), **d)
+
+
+def gen_head_tiny():
+    """Whole SematicRes5ROIHeads / SematicRes5ROIHeadsCrossOutput eval forward on a shrunken config
+    (res4 channels 16 -> res5 32) so the weights fit in a fixture."""
+    emb = lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg)
+    rs.install(class_embed_fn=emb)
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    am.get_class_embed = emb
+    rh = rs.load("defrcn.modeling.roi_heads.roi_heads")
+    for head, layer, tag in (("SematicRes5ROIHeads", "FastRCNNOutputLayers", "head_tiny"),
+                             ("SematicRes5ROIHeadsCrossOutput", "FastRCNNAttentionOutputLayers", "head_tiny_cross")):
+        K = 20
+        cfg = rs.default_cfg(num_classes=K, addition="clip", output_layer=layer, roi_head=head)
+        cfg.MODEL.RESNETS.RES2_OUT_CHANNELS = 4      # res5 out = 32, in = 16
+        cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 1        # bottleneck = 8
+        torch.manual_seed(1)
+        with cuda_as_cpu():
+            m = rh.build_roi_heads(cfg, {"res4": rs.ShapeSpec(channels=16, stride=16)}).eval()
+            with torch.no_grad():
+                # make the classifier outputs non-trivial (reference init std=0.01/0.001 gives ~uniform probs)
+                m.box_predictor.cls_score.weight.mul_(60.0)
+                m.box_predictor.bbox_pred.weight.mul_(100.0)
+                for blk in m.res5:
+                    for c in (blk.conv1, blk.conv2, blk.conv3, blk.shortcut):
+                        if c is not None:
+                            c.norm.weight.copy_(torch.rand_like(c.norm.weight) + 0.5)
+                            c.norm.bias.copy_(torch.randn_like(c.norm.bias) * 0.1)
+                            c.norm.running_mean.copy_(torch.randn_like(c.norm.running_mean) * 0.1)
+                            c.norm.running_var.copy_(torch.rand_like(c.norm.running_var) + 0.5)
+            gen = torch.Generator().manual_seed(21)
+            sizes = [(320, 400), (304, 464)]
+            Hf, Wf = 20, 29
+            feat = torch.relu(torch.randn(2, 16, Hf, Wf, generator=gen))
+            props = []
+            for (h, w) in sizes:
+                b, _ = synth_proposals(48, h, w, gen)
+                inst = rs.Instances((h, w))
+                inst.proposal_boxes = rs.Boxes(b)
+                inst.objectness_logits = torch.zeros(len(b))
+                props.append(inst)
+            with torch.no_grad():
+                res, _ = m(None, {"res4": feat}, props, None)
+                pooled = m.pooler([feat], [p.proposal_boxes for p in props])
+                fp = m.res5(pooled).mean(dim=[2, 3])
+                att_out, _ = m.forward_att(fp)
+        d = sd_to_np(m.state_dict())
+        d.update(feat=feat.numpy(), embed=m.attention.embed.numpy(), bg_feature=m.attention.bg_feature.numpy(),
+                 pooled=pooled.numpy(), feature_pooled=fp.numpy(), logits=att_out["pred_logits"].numpy(),
+                 deltas=att_out["pred_bbox"].numpy(), sim2stext=att_out["sim2stext"].numpy())
+        for i, (p, r) in enumerate(zip(props, res)):
+            d["props%d" % i] = p.proposal_boxes.tensor.numpy()
+            d["hw%d" % i] = np.array(p.image_size, np.int64)
+            d["det_boxes%d" % i] = r.pred_boxes.tensor.numpy()
+            d["det_scores%d" % i] = r.scores.numpy()
+            d["det_classes%d" % i] = r.pred_classes.numpy()
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **d)
+
+
+def gen_pcb():
+    """Runs PrototypicalCalibrationBlock.execute_calibration / extract_roi_features unchanged, with the
+    ImageNet CNN replaced by a fixed random conv feature (the CNN itself is out of scope)."""
+    rs.install()
+    sys.modules.setdefault("defrcn.dataloader", types.ModuleType("defrcn.dataloader"))
+    sys.modules["defrcn.dataloader"].build_detection_test_loader = None
+    archs = types.ModuleType("defrcn.evaluation.archs")
+    archs.resnet101 = None
+    sys.modules["defrcn.evaluation.archs"] = archs
+
+    def from_tensors(tensors, size_divisibility=0):
+        return rs.ImageList(torch.stack(tensors), [t.shape[-2:] for t in tensors])
+    rs.ImageList.from_tensors = staticmethod(from_tensors)
+    cl = rs.load("defrcn.evaluation.calibration_layer")
+    gen = torch.Generator().manual_seed(9)
+    h, w, D, K, n = 416, 608, 48, 20, 60
+    conv_feature = torch.relu(torch.randn(1, 64, h // 32, w // 32, generator=gen))
+
+    class FakeNet:
+        fc = torch.nn.Linear(64, D)
+
+        def __call__(self, x):
+            return None, conv_feature
+    torch.manual_seed(4)
+    net = FakeNet()
+    pcb = object.__new__(cl.PrototypicalCalibrationBlock)
+    pcb.cfg = rs.default_cfg()
+    pcb.device = torch.device("cpu")
+    pcb.alpha = 0.5
+    pcb.imagenet_model = net
+    pcb.roi_pooler = rs.ROIPooler(output_size=(1, 1), scales=(1 / 32,), sampling_ratio=(0), pooler_type="ROIAlignV2")
+    protos = torch.randn(K, D, generator=gen)
+    pcb.prototypes = {c: protos[c:c + 1] for c in range(K)}
+    pcb.exclude_cls = list(range(0, 15))
+    boxes, _ = synth_proposals(n, h, w, gen)
+    scores = torch.sort(torch.rand(n, generator=gen) * 1.02, descending=True).values
+    scores[-7:] = scores[-7:] * 0.04           # a tail below PCB_LOWER
+    classes = torch.randint(0, K, (n,), generator=gen)
+    inst = rs.Instances((h, w))
+    inst.pred_boxes = rs.Boxes(boxes.clone())
+    inst.scores = scores.clone()
+    inst.pred_classes = classes
+    img = np.zeros((h, w, 3), np.uint8)
+    cl.cv2.imread = lambda fn: img
+    with torch.no_grad():
+        feats = pcb.extract_roi_features(img, [inst.pred_boxes])
+        dts = pcb.execute_calibration([{"file_name": "x"}], [{"instances": inst}])
+    np.savez_compressed(os.path.join(OUT, "pcb.npz"), conv_feature=conv_feature.numpy(), boxes=boxes.numpy(),
+                        scores_in=scores.numpy(), classes=classes.numpy(), protos=protos.numpy(),
+                        fc_w=net.fc.weight.detach().numpy(), fc_b=net.fc.bias.detach().numpy(),
+                        feats_all=feats.numpy(), scores_out=dts[0]["instances"].scores.numpy(),
+                        exclude=np.array(pcb.exclude_cls, np.int64), alpha=np.float32(0.5))
+
+
+def gen_known_answer():
+    """test.py:80-92 fixture: CE(pred_logits.pt, gt_classes.pt)."""
+    pl = torch.load(os.path.join(rs.REFERENCE_ROOT, "pred_logits.pt"), map_location="cpu").detach()
+    gt = torch.load(os.path.join(rs.REFERENCE_ROOT, "gt_classes.pt"), map_location="cpu")
+    ce = torch.nn.functional.cross_entropy(pl.float(), gt.long())
+    np.savez_compressed(os.path.join(OUT, "known_answer_ce.npz"), ce=np.float64(ce.item()),
+                        shape=np.array(pl.shape), n_bg=np.int64((gt == pl.shape[1] - 1).sum()),
+                        logits_head=pl[:64].float().numpy(), gt_head=gt[:64].numpy())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)  # deterministic summation order in the CPU kernels
+    gen_gdl()
+    gen_fast_rcnn_inference()
+    gen_losses()
+    gen_attention()
+    gen_head_tiny()
+    gen_pcb()
+    gen_known_answer()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""Oracle port vs golden vectors produced by the reference's own modules (oracle/gen_golden.py)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def params(g, strip=""):
+    return {k[len(strip):] if strip and k.startswith(strip) else k: T(g[k]) for k in g.files}
+
+
+def test_gdl_affine(golden):
+    g = golden("gdl")
+    y = O.affine_fwd(T(g["x"]), T(g["w"]), T(g["b"]))
+    assert torch.equal(y, T(g["y"]))
+    gx, gw, gb = O.gdl_affine_bwd(T(g["g"]), T(g["x"]), T(g["w"]), float(g["lam"]))
+    assert torch.allclose(gx, T(g["gx"]), rtol=1e-6, atol=1e-9)
+    assert torch.allclose(gw, T(g["gw"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gb, T(g["gb"]), rtol=1e-5, atol=1e-6)
+
+
+def test_fast_rcnn_inference(golden):
+    g = golden("fast_rcnn_inference")
+    for tag in ("voc", "coco", "ties", "empty"):
+        h, w = g[tag + "_hw"]
+        # decode: C restatement and torch restatement vs reference Box2BoxTransform
+        for impl in ("c", "torch"):
+            b = O.apply_deltas(g[tag + "_deltas"], g[tag + "_props"], impl=impl)
+            assert torch.allclose(b, T(g[tag + "_pred_boxes_all"]), rtol=1e-5, atol=1e-3), (tag, impl)
+        # post-processing is bit-exact given the reference's own decoded boxes / probabilities
+        r = O.fast_rcnn_inference_single_image(g[tag + "_pred_boxes_all"], g[tag + "_probs"], (h, w), 0.05, 0.5, 100)
+        assert r["n_candidates"] == int(g[tag + "_ncand"]), tag
+        assert torch.equal(r["classes"], T(g[tag + "_classes"])), tag
+        assert torch.equal(r["roi_inds"], T(g[tag + "_roi_inds"])), tag
+        assert torch.equal(r["scores"], T(g[tag + "_scores"])), tag
+        assert torch.equal(r["boxes"], T(g[tag + "_boxes"])), tag
+    assert int(g["empty_ncand"]) == 0 and len(g["empty_scores"]) == 0
+    assert len(g["ties_scores"]) > 0
+
+
+def test_losses(golden):
+    g = golden("losses")
+    from oracle import ref_stubs as rs
+    K = g["logits"].shape[1] - 1
+    loss_cls = F.cross_entropy(T(g["logits"]), T(g["gt_classes"]))
+    assert abs(float(loss_cls) - float(g["loss_cls"])) < 1e-6
+    tgt = rs.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).get_deltas(T(g["props"]), T(g["gt_boxes"]))
+    fg = torch.nonzero((T(g["gt_classes"]) >= 0) & (T(g["gt_classes"]) < K)).squeeze(1)
+    cols = 4 * T(g["gt_classes"])[fg][:, None] + torch.arange(4)
+    l1 = (T(g["deltas"])[fg[:, None], cols] - tgt[fg]).abs().sum() / len(g["gt_classes"])
+    assert abs(float(l1) - float(g["loss_box_reg"])) < 1e-5
+
+
+def test_attention_small(golden):
+    g = golden("attention_small")
+    p = params(g)
+    text = torch.cat([T(g["embed"]), T(g["bg_feature"])], 0)
+    assert torch.equal(text, T(g["text_feat"]))
+    sim, attn = O.sematic_proposal_attention(T(g["x"]), text, p)
+    assert attn.shape == (g["x"].shape[0], text.shape[0] + 1)
+    assert torch.allclose(attn, T(g["attn"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sim, T(g["sim2stext"]), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(attn.sum(1), torch.ones(attn.shape[0]), atol=1e-5)
+
+
+def _head(golden, tag, cross):
+    g = golden(tag)
+    p = params(g)
+    text = torch.cat([T(g["embed"]), T(g["bg_feature"])], 0)
+    props = [T(g["props0"]), T(g["props1"])]
+    shapes = [tuple(g["hw0"]), tuple(g["hw1"])]
+    for impl in ("c", "torchvision"):
+        dets, mid = O.head_forward(T(g["feat"]), props, shapes, text, p, cross_output=cross, roi_impl=impl)
+        assert torch.allclose(mid["pooled"], T(g["pooled"]), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(mid["feature_pooled"], T(g["feature_pooled"]), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(mid["sim2stext"], T(g["sim2stext"]), rtol=1e-3, atol=1e-4)
+        assert torch.allclose(mid["logits"], T(g["logits"]), rtol=1e-3, atol=1e-4)
+        assert torch.allclose(mid["deltas"], T(g["deltas"]), rtol=1e-3, atol=1e-4)
+        for i, d in enumerate(dets):
+            assert len(g["det_scores%d" % i]) > 0
+            assert torch.equal(d["classes"], T(g["det_classes%d" % i]))
+            assert torch.allclose(d["scores"], T(g["det_scores%d" % i]), rtol=1e-4, atol=1e-6)
+            assert torch.allclose(d["boxes"], T(g["det_boxes%d" % i]), rtol=1e-4, atol=1e-2)
+
+
+def test_head_tiny(golden):
+    _head(golden, "head_tiny", False)
+
+
+def test_head_tiny_cross(golden):
+    _head(golden, "head_tiny_cross", True)
+
+
+def test_pcb(golden):
+    g = golden("pcb")
+    # Q1: ROIAlign 1x1 @ 1/32 adaptive + fc
+    rois = O.boxes_to_rois([T(g["boxes"])])
+    pooled = O.roi_align_fwd(g["conv_feature"], rois, 1, 1.0 / 32, 0, True)
+    feats = F.linear(pooled.flatten(1), T(g["fc_w"]), T(g["fc_b"]))
+    assert torch.allclose(feats, T(g["feats_all"]), rtol=1e-4, atol=1e-5)
+    # Q2: calibration over ileft..iright
+    s_in = T(g["scores_in"])
+    ileft, iright = int((s_in > 1.0).sum()), int((s_in > 0.05).sum())
+    assert 0 < ileft < iright < len(s_in)
+    out = O.pcb_calibrate(s_in, T(g["feats_all"])[ileft:iright], T(g["protos"]), g["classes"], 0.5,
+                          set(g["exclude"].tolist()))
+    assert torch.allclose(out, T(g["scores_out"]), rtol=1e-5, atol=1e-6)
+    assert not torch.equal(out, s_in)
+
+
+def test_known_answer_ce(golden):
+    g = golden("known_answer_ce")
+    assert abs(float(g["ce"]) - 2.764926910) < 1e-6          # SURVEY.md §4 / BASELINE.md
+    assert tuple(g["shape"]) == (2048, 16) and int(g["n_bg"]) == 1697

@@ -1,0 +1,77 @@
+"""Pin the C restatement against the third-party CPU ops the reference actually calls
+(torchvision roi_align / nms — installed 0.26, same algorithms as the pinned 0.8.1)."""
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+from oracle import oracle as O
+from oracle.gen_golden import synth_proposals
+
+
+@pytest.mark.parametrize("N,C,H,W,R,P,scale,sr,aligned", [
+    (2, 8, 38, 50, 64, 7, 1 / 16, 0, True),
+    (1, 4, 19, 25, 33, 1, 1 / 32, 0, True),      # PCB pooling
+    (1, 3, 20, 20, 20, 7, 1 / 16, 2, True),
+    (1, 3, 20, 20, 20, 7, 1 / 16, 0, False),
+    (3, 5, 13, 17, 40, 14, 1 / 8, 0, True),
+])
+def test_roi_align_fwd_bwd_vs_torchvision(N, C, H, W, R, P, scale, sr, aligned):
+    gen = torch.Generator().manual_seed(N * 100 + R)
+    x = torch.relu(torch.randn(N, C, H, W, generator=gen))
+    boxes = []
+    for n in range(N):
+        b, _ = synth_proposals(R // N + (1 if n < R % N else 0), int(H / scale), int(W / scale), gen)
+        boxes.append(b)
+    rois = O.boxes_to_rois(boxes)
+    # edge cases: box hanging outside the map, zero-size box, whole image
+    rois[0, 1:] = torch.tensor([-40.0, -30.0, 20.0, 25.0])
+    rois[1, 1:] = torch.tensor([10.0, 10.0, 10.0, 10.0])
+    rois[2, 1:] = torch.tensor([0.0, 0.0, W / scale + 50, H / scale + 50])
+    ours = O.roi_align_fwd(x, rois, P, scale, sr, aligned, impl="c")
+    xt = x.clone().requires_grad_(True)
+    ref = torchvision.ops.roi_align(xt, rois, (P, P), scale, sr, aligned)
+    assert torch.allclose(ours, ref.detach(), rtol=1e-6, atol=1e-6)
+    g = torch.randn(ref.shape, generator=gen)
+    ref.backward(g)
+    gin = O.roi_align_bwd(g, rois, x.shape, scale, sr, aligned)
+    assert torch.allclose(gin, xt.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,seed", [(0, 0), (1, 1), (257, 2), (3000, 3)])
+def test_nms_vs_torchvision(n, seed):
+    gen = torch.Generator().manual_seed(seed)
+    boxes, _ = synth_proposals(max(n, 4), 600, 800, gen, n_obj=6)
+    boxes = boxes[:n]
+    scores = torch.rand(n, generator=gen)
+    if n > 10:
+        scores[5:10] = scores[0]            # ties: stable order expected
+    keep = O.nms(boxes, scores, 0.5)
+    ref = torchvision.ops.nms(boxes, scores, 0.5)
+    assert torch.equal(keep, ref)
+
+
+def test_batched_nms_trick_vs_torchvision_nms():
+    gen = torch.Generator().manual_seed(7)
+    n = 2500
+    boxes, _ = synth_proposals(n, 600, 800, gen, n_obj=8)
+    scores = torch.rand(n, generator=gen)
+    idxs = torch.randint(0, 20, (n,), generator=gen)
+    keep = O.batched_nms(boxes, scores, idxs, 0.5)
+    off = idxs.to(boxes) * (boxes.max() + torch.tensor(1).to(boxes))
+    ref = torchvision.ops.nms(boxes + off[:, None], scores, 0.5)
+    assert torch.equal(keep, ref)
+    # and the result is a valid per-class NMS: no two kept boxes of one class overlap > thr
+    kb, kc = boxes[keep], idxs[keep]
+    iou = torchvision.ops.box_iou(kb, kb)
+    same = kc[:, None] == kc[None, :]
+    iou.fill_diagonal_(0)
+    assert float((iou * same).max()) <= 0.5 + 1e-4
+
+
+def test_voc_ap_sanity():
+    gts = {0: np.array([[10, 10, 50, 50.0]]), 1: np.array([[20, 20, 80, 90.0], [100, 100, 150, 160.0]])}
+    dets = [(0, 0.9, 11, 9, 50, 51), (1, 0.8, 21, 22, 79, 88), (1, 0.7, 0, 0, 10, 10), (1, 0.6, 101, 99, 149, 161)]
+    ap = O.voc_eval_class(dets, gts)
+    assert 0.8 < ap <= 1.0
+    assert O.voc_eval_class([], gts) == 0.0
