@@ -1,0 +1,81 @@
+"""ctypes binding of the C-ABI library (include/b200roi.h).
+
+There is deliberately no fallback: if `_C/libb200roi.so` is missing the import raises, and every
+entry point raises `B200Error` on a non-zero status.  Build with
+`python -m fewshotobjectdetection_imporove_via_text_feature_b200._build` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libb200roi.so")
+
+F32, BF16 = 0, 1
+NCHW, NHWC = 0, 1
+
+c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/b200roi.h declaration by declaration
+SIGNATURES = {
+    "b200_abi_version": (c_int, []),
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_gdl_affine_fwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
+    "b200_gdl_affine_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
+    "b200_gdl_affine_bwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_fwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "b200_roi_align_fwd": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_bwd_workspace_bytes": (c_size_t, [c_int] * 10),
+    "b200_roi_align_bwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_void_p]),
+    "b200_batched_nms_workspace_bytes": (c_size_t, [c_int] * 3),
+    "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
+    "b200_gather_detections": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 4 + [c_void_p]),
+    "b200_pcb_cosine_blend": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float] * 3 + [c_void_p]),
+    "b200_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int] + [c_int] * 4 + [c_void_p]),
+    "b200_text_attention": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
+    "b200_cast_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+# kernels launched per entry point (upper bound for the optional layout-conversion launches is counted where it
+# happens); used by bench.py to report `gpu_launches`
+KERNELS_PER_CALL = {
+    "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2,
+    "b200_softmax_decode_compact": 1, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
+    "b200_gemm_bf16": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1,
+}
+LAUNCHES = 0
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "b200roi: %s is missing — build it with `python -m fewshotobjectdetection_imporove_via_text_feature_b200._build`; "
+                "there is no CPU / PyTorch fallback for this path" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point and raise on failure."""
+    global LAUNCHES
+    L = lib()
+    rc = getattr(L, name)(*args)
+    LAUNCHES += KERNELS_PER_CALL.get(name, 0)
+    if rc != 0:
+        raise B200Error("%s failed (%d): %s" % (name, rc, L.b200_last_error().decode("utf-8", "replace")))
+    return rc

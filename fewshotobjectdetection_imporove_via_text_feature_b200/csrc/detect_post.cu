@@ -1,0 +1,548 @@
+// D1 + D2 + D3: fast_rcnn_inference on the device, no host synchronisation.
+//   reference: defrcn/modeling/roi_heads/fast_rcnn.py:46-134 (+ :306-334 predict_boxes / predict_probs),
+//   third-party arithmetic: detectron2 0.3 Box2BoxTransform.apply_deltas, Boxes.clip, layers.batched_nms,
+//   torchvision 0.8.1 ops.nms (coordinate-offset trick).
+//
+// Kernels
+//   softmax_decode_compact_kernel : one CTA per image.  Softmax over K+1 logits (warp per row), score
+//       threshold, ORDERED compaction (row-major == torch.nonzero order, via ballot prefix + block scan),
+//       box decode + clip fused into the compaction: only surviving (roi,class) pairs are decoded.
+//   nms_prepare_kernel            : one CTA per image.  max coordinate (for the offset trick), class
+//       histogram, stable counting sort of candidates by class.
+//   nms_class_kernel              : one CTA per (class, image).  shared-memory bitonic sort by
+//       (score desc, index asc); 64-box diagonal blocks resolved with an IoU bitmask, then a parallel
+//       sweep of the survivors over the remaining boxes with a shared-memory `removed` bitmap.
+//   nms_finalize_kernel           : one CTA per image.  Merge per-class survivors by (score desc, idx asc),
+//       emit the first max_keep.
+// All comparisons that decide membership (score > thresh, iou > thresh) use round-to-nearest fp32 ops in
+// the reference's order with FMA contraction disabled, so keep indices and counts are bit-exact.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), detectron2 _DEFAULT_SCALE_CLAMP
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp /*[33]*/, int* total) {
+  // blockDim.x == 1024.  returns exclusive prefix of v over threads; *total = block sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  const int res = s_warp[warp] + inc - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+
+// probabilities of one row, lanes strided over classes; returns this lane's values for classes
+// lane, lane+32, ... in p[] (at most kMaxChunks chunks -> K+1 <= 32*kMaxChunks)
+constexpr int kMaxChunks = 8;
+
+__device__ __forceinline__ void row_probs(const float* __restrict__ row, int ncol, int input_is_prob, int lane,
+                                          float* p) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kMaxChunks; ++j) {
+    const int k = lane + 32 * j;
+    p[j] = k < ncol ? __ldg(row + k) : -INFINITY;
+    mx = fmaxf(mx, p[j]);
+  }
+  if (input_is_prob) return;
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxChunks; ++j) {
+    const int k = lane + 32 * j;
+    p[j] = k < ncol ? expf(p[j] - mx) : 0.f;
+    s += p[j];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int j = 0; j < kMaxChunks; ++j) p[j] = __fdiv_rn(p[j], s);
+}
+
+__device__ __forceinline__ float4 decode_clip(const float* __restrict__ d, float4 pb, float wx, float wy, float ww,
+                                              float wh, float img_h, float img_w) {
+  // Box2BoxTransform.apply_deltas, op for op (separate roundings), then Boxes.clip
+  const float widths = __fsub_rn(pb.z, pb.x), heights = __fsub_rn(pb.w, pb.y);
+  const float ctr_x = __fadd_rn(pb.x, __fmul_rn(0.5f, widths)), ctr_y = __fadd_rn(pb.y, __fmul_rn(0.5f, heights));
+  const float dx = __fdiv_rn(d[0], wx), dy = __fdiv_rn(d[1], wy);
+  const float dw = fminf(__fdiv_rn(d[2], ww), kScaleClamp), dh = fminf(__fdiv_rn(d[3], wh), kScaleClamp);
+  const float pcx = __fadd_rn(__fmul_rn(dx, widths), ctr_x), pcy = __fadd_rn(__fmul_rn(dy, heights), ctr_y);
+  const float pw = __fmul_rn(expf(dw), widths), ph = __fmul_rn(expf(dh), heights);
+  float4 o;
+  o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw)); o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+  o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw)); o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+  o.x = fminf(fmaxf(o.x, 0.f), img_w); o.y = fminf(fmaxf(o.y, 0.f), img_h);
+  o.z = fminf(fmaxf(o.z, 0.f), img_w); o.w = fminf(fmaxf(o.w, 0.f), img_h);
+  return o;
+}
+
+constexpr int kRowTile = 1024;  // rows handled per block iteration (== threads: one scan element each)
+
+__global__ void __launch_bounds__(1024)
+softmax_decode_compact_kernel(const float* __restrict__ scores_in, int input_is_prob, const float* __restrict__ deltas,
+                              const float* __restrict__ proposals, const int32_t* __restrict__ roi_offsets,
+                              const float* __restrict__ image_hw, int K, int cls_agnostic, float wx, float wy,
+                              float ww, float wh, float thresh, float* __restrict__ probs_out,
+                              float* __restrict__ cand_boxes, float* __restrict__ cand_scores,
+                              int32_t* __restrict__ cand_roi, int32_t* __restrict__ cand_cls,
+                              int32_t* __restrict__ cand_count) {
+  __shared__ int s_cnt[kRowTile];
+  __shared__ int s_base[kRowTile];
+  __shared__ int s_warp[33];
+  const int img = blockIdx.x;
+  const int r0 = roi_offsets[img], r1 = roi_offsets[img + 1];
+  const float img_h = image_hw[2 * img], img_w = image_hw[2 * img + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncol = K + 1;
+  const size_t out0 = (size_t)r0 * K;  // this image's candidate segment
+  int running = 0;
+
+  for (int t0 = r0; t0 < r1; t0 += kRowTile) {
+    const int nrows = min(kRowTile, r1 - t0);
+    // phase A: probabilities + per-row candidate counts (warp per row)
+    for (int lr = warp; lr < nrows; lr += 32) {
+      const int r = t0 + lr;
+      float p[kMaxChunks];
+      row_probs(scores_in + (size_t)r * ncol, ncol, input_is_prob, lane, p);
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < kMaxChunks; ++j) {
+        const int k = lane + 32 * j;
+        if (probs_out && k < ncol) probs_out[(size_t)r * ncol + k] = p[j];
+        cnt += __popc(__ballot_sync(0xffffffffu, k < K && p[j] > thresh));
+      }
+      if (lane == 0) s_cnt[lr] = cnt;
+    }
+    __syncthreads();
+    // phase B: exclusive scan of the row counts
+    int total;
+    const int mine = (int)threadIdx.x < nrows ? s_cnt[threadIdx.x] : 0;
+    const int ex = block_exclusive_scan_1024(mine, s_warp, &total);
+    s_base[threadIdx.x] = running + ex;
+    __syncthreads();
+    // phase C: ordered write, decode fused
+    for (int lr = warp; lr < nrows; lr += 32) {
+      if (s_cnt[lr] == 0) continue;
+      const int r = t0 + lr;
+      float p[kMaxChunks];
+      row_probs(scores_in + (size_t)r * ncol, ncol, input_is_prob, lane, p);
+      const float4 pb = *reinterpret_cast<const float4*>(proposals + 4 * (size_t)r);
+      int pos = s_base[lr];
+#pragma unroll
+      for (int j = 0; j < kMaxChunks; ++j) {
+        const int k = lane + 32 * j;
+        const bool pass = k < K && p[j] > thresh;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+          const size_t o = out0 + pos + __popc(m & ((1u << lane) - 1u));
+          const float* d = deltas + (cls_agnostic ? (size_t)r * 4 : ((size_t)r * K + k) * 4);
+          const float4 bx = decode_clip(d, pb, wx, wy, ww, wh, img_h, img_w);
+          *reinterpret_cast<float4*>(cand_boxes + 4 * o) = bx;
+          cand_scores[o] = p[j];
+          cand_roi[o] = r - r0;
+          cand_cls[o] = k;
+        }
+        pos += __popc(m);
+      }
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cand_count[img] = running;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t desc_key(float s) {
+  // monotone map float -> uint32 such that larger float => SMALLER key (ascending sort == descending score)
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  // torchvision nms kernel: inter / (areaA + areaB - inter) > thr, widths clamped at 0
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+}
+
+// block-wide bitonic sort (ascending) of n2 (power of two) 64-bit keys in shared or global memory
+__device__ void bitonic_sort_u64(unsigned long long* keys, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int i = ((t / j) * (j << 1)) + (t % j);
+        const int l = i + j;
+        const bool asc = (i & k) == 0;
+        const unsigned long long a = keys[i], b = keys[l];
+        if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct NmsWorkspace {
+  float* max1;                 // (N)   boxes.max()+1 per segment (0 when the >=40000 path applies)
+  int32_t* class_start;        // (N, num_classes+1)
+  int32_t* order;              // (total_capacity) candidate indices grouped by class (segment-relative)
+  unsigned long long* kept;    // (total_capacity) survivor keys, ~0 = suppressed
+  unsigned long long* scratch; // (total_capacity rounded up to pow2 per use) global sort fallback
+};
+
+constexpr int kPrepThreads = 1024;
+constexpr int kMaxClasses = 1024;
+
+__global__ void __launch_bounds__(kPrepThreads)
+nms_prepare_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ classes,
+                   const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ seg_count, int num_classes,
+                   float* __restrict__ max1, int32_t* __restrict__ class_start, int32_t* __restrict__ order) {
+  extern __shared__ int s_dyn[];          // hist[num_classes] | cursor[num_classes] | wcnt[32][num_classes]
+  int* s_hist = s_dyn;
+  int* s_cursor = s_dyn + num_classes;
+  int* s_wcnt = s_dyn + 2 * num_classes;
+  __shared__ float s_red[32];
+  const int img = blockIdx.x;
+  const int base = seg_offsets[img], n = seg_count[img];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* bx = boxes + 4 * (size_t)base;
+  const int32_t* cl = classes + base;
+
+  for (int c = threadIdx.x; c < num_classes; c += blockDim.x) s_hist[c] = 0;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) mx = fmaxf(mx, bx[i]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[cl[i]], 1);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    mx = warp_max(s_red[lane]);
+    // detectron2 0.3 batched_nms: coordinate trick only below 40000 boxes
+    if (lane == 0) max1[img] = (n > 0 && n < 40000) ? __fadd_rn(mx, 1.0f) : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < num_classes; ++c) {
+      class_start[(size_t)img * (num_classes + 1) + c] = acc;
+      s_cursor[c] = acc;
+      acc += s_hist[c];
+    }
+    class_start[(size_t)img * (num_classes + 1) + num_classes] = acc;
+  }
+  __syncthreads();
+  // stable placement, 1024 candidates per round
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    for (int k = threadIdx.x; k < 32 * num_classes; k += blockDim.x) s_wcnt[k] = 0;
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    const bool valid = i < n;
+    const int c = valid ? cl[i] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wcnt[warp * num_classes + c] = __popc(peers);
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < num_classes; cc += blockDim.x) {
+      int run = s_cursor[cc];
+      for (int w = 0; w < 32; ++w) {
+        const int t = s_wcnt[w * num_classes + cc];
+        s_wcnt[w * num_classes + cc] = run;
+        run += t;
+      }
+      s_cursor[cc] = run;
+    }
+    __syncthreads();
+    if (valid) order[base + s_wcnt[warp * num_classes + c] + rank] = i;
+    __syncthreads();
+  }
+}
+
+constexpr int kNmsThreads = 256;
+constexpr int kNmsSmemBoxes = 4096;  // per (class, image) handled fully in shared memory; larger -> global path
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                 const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
+                 const float* __restrict__ max1, const int32_t* __restrict__ class_start,
+                 const int32_t* __restrict__ order, unsigned long long* __restrict__ kept,
+                 unsigned long long* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_keep64;
+  const int c = blockIdx.x, img = blockIdx.y;
+  const int base = seg_offsets[img];
+  const int cs = class_start[(size_t)img * (num_classes + 1) + c];
+  const int m = class_start[(size_t)img * (num_classes + 1) + c + 1] - cs;
+  if (m == 0) return;
+  const float off = __fmul_rn((float)c, max1[img]);
+  const int32_t* ord = order + base + cs;
+  unsigned long long* kept_out = kept + base + cs;
+
+  if (m == 1) {
+    if (threadIdx.x == 0) kept_out[0] = ((unsigned long long)desc_key(scores[base + ord[0]]) << 32) | (uint32_t)ord[0];
+    return;
+  }
+  const int m2 = next_pow2(m);
+  const bool in_smem = m <= kNmsSmemBoxes;
+  unsigned long long* gslice = scratch + 4 * (size_t)(base + cs);  // 4*m u64 per class slice (host sizes scratch 4x)
+  unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(s_raw) : gslice;
+  float4* sbox = reinterpret_cast<float4*>(s_raw + (size_t)kNmsSmemBoxes * 8);
+  uint32_t* removed = reinterpret_cast<uint32_t*>(s_raw + (size_t)kNmsSmemBoxes * 24);
+
+  // (score desc, position-in-class asc); positions are ascending candidate index (stable counting sort)
+  for (int p = threadIdx.x; p < m2; p += blockDim.x)
+    keys[p] = p < m ? (((unsigned long long)desc_key(scores[base + ord[p]]) << 32) | (uint32_t)p) : ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(keys, m2);
+
+  auto load_box = [&](int j) -> float4 {
+    const int cand = ord[(int)(keys[j] & 0xffffffffu)];
+    float4 b = *reinterpret_cast<const float4*>(boxes + 4 * (size_t)(base + cand));
+    b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+    return b;
+  };
+  if (in_smem) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) sbox[j] = load_box(j);
+    for (int j = threadIdx.x; j < (m + 31) / 32; j += blockDim.x) removed[j] = 0u;
+  } else {
+    // global path: `removed` bitmap lives in the upper half of this class's scratch slice
+    removed = reinterpret_cast<uint32_t*>(gslice + 2 * (size_t)m);
+    for (int j = threadIdx.x; j < (m + 31) / 32; j += blockDim.x) removed[j] = 0u;
+  }
+  __syncthreads();
+  auto get_box = [&](int j) -> float4 { return in_smem ? sbox[j] : load_box(j); };
+
+  for (int b0 = 0; b0 < m; b0 += 64) {
+    const int nb = min(64, m - b0);
+    // diagonal 64x64 block: row t = boxes later in the block that box t suppresses
+    if ((int)threadIdx.x < 64) {
+      unsigned long long row = 0ull;
+      if ((int)threadIdx.x < nb) {
+        const float4 a = get_box(b0 + threadIdx.x);
+        for (int j = threadIdx.x + 1; j < nb; ++j)
+          if (iou_gt(a, get_box(b0 + j), thr)) row |= 1ull << j;
+      }
+      s_diag[threadIdx.x] = row;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long dead = (unsigned long long)removed[b0 >> 5] |
+                                ((b0 + 32 < m) ? ((unsigned long long)removed[(b0 >> 5) + 1] << 32) : 0ull);
+      unsigned long long keep = 0ull;
+      for (int t = 0; t < nb; ++t)
+        if (!((dead >> t) & 1ull)) { keep |= 1ull << t; dead |= s_diag[t]; }
+      s_keep64 = keep;
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keep64;
+    // survivors of this block: emit, then sweep every later box against them
+    if ((int)threadIdx.x < nb) {
+      const int j = b0 + threadIdx.x;
+      const uint32_t cand = (uint32_t)ord[(int)(keys[j] & 0xffffffffu)];
+      kept_out[j] = ((keep >> threadIdx.x) & 1ull) ? ((keys[j] & 0xffffffff00000000ull) | cand) : ~0ull;
+    }
+    if (keep != 0ull) {
+      for (int j = b0 + 64 + threadIdx.x; j < m; j += blockDim.x) {
+        if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
+        const float4 bj = get_box(j);
+        unsigned long long kk = keep;
+        bool dead = false;
+        while (kk && !dead) {
+          const int t = __ffsll((long long)kk) - 1;
+          kk &= kk - 1;
+          dead = iou_gt(get_box(b0 + t), bj, thr);
+        }
+        if (dead) atomicOr(&removed[j >> 5], 1u << (j & 31));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kFinalSmemKeys = 4096;
+
+__global__ void __launch_bounds__(1024)
+nms_finalize_kernel(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ seg_count,
+                    unsigned long long* __restrict__ kept, unsigned long long* __restrict__ scratch, int max_keep,
+                    int32_t* __restrict__ keep, int32_t* __restrict__ keep_count) {
+  __shared__ unsigned long long s_keys[kFinalSmemKeys];
+  __shared__ int s_n;
+  const int img = blockIdx.x;
+  const int base = seg_offsets[img], n = seg_count[img];
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // count survivors
+  int local = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) local += kept[base + i] != ~0ull;
+  local = (int)warp_sum((float)local);  // n < 2^24 so exact in fp32
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_n, local);
+  __syncthreads();
+  const int nk = s_n;
+  __syncthreads();
+  unsigned long long* keys = nk <= kFinalSmemKeys ? s_keys : scratch + 4 * (size_t)base;
+  const int n2 = next_pow2(max(nk, 1));
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  // compaction order is irrelevant: keys are unique and get sorted next
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long k = kept[base + i];
+    if (k != ~0ull) keys[atomicAdd(&s_n, 1)] = k;
+  }
+  for (int i = nk + threadIdx.x; i < n2; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(keys, n2);
+  const int out_n = max_keep >= 0 ? min(nk, max_keep) : nk;
+  for (int i = threadIdx.x; i < out_n; i += blockDim.x) keep[(size_t)img * max(max_keep, 0) + i] = (int32_t)(keys[i] & 0xffffffffu);
+  if (threadIdx.x == 0) keep_count[img] = out_n;
+}
+
+__global__ void gather_detections_kernel(const float* __restrict__ cand_boxes, const float* __restrict__ cand_scores,
+                                         const int32_t* __restrict__ cand_roi, const int32_t* __restrict__ cand_cls,
+                                         const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ keep,
+                                         const int32_t* __restrict__ keep_count, int max_keep,
+                                         float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                         int64_t* __restrict__ out_classes, int64_t* __restrict__ out_roi) {
+  const int img = blockIdx.x;
+  const int nk = keep_count[img], base = seg_offsets[img];
+  for (int i = threadIdx.x; i < max_keep; i += blockDim.x) {
+    const size_t o = (size_t)img * max_keep + i;
+    if (i < nk) {
+      const int j = base + keep[o];
+      *reinterpret_cast<float4*>(out_boxes + 4 * o) = *reinterpret_cast<const float4*>(cand_boxes + 4 * (size_t)j);
+      out_scores[o] = cand_scores[j];
+      out_classes[o] = cand_cls[j];
+      out_roi[o] = cand_roi[j];
+    } else {
+      *reinterpret_cast<float4*>(out_boxes + 4 * o) = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_scores[o] = 0.f;
+      out_classes[o] = -1;
+      out_roi[o] = -1;
+    }
+  }
+}
+
+static NmsWorkspace carve(void* ws, int N, int total_capacity, int num_classes) {
+  NmsWorkspace w;
+  unsigned char* p = (unsigned char*)ws;
+  w.kept = (unsigned long long*)p;    p += align_up((size_t)total_capacity * 8, 256);
+  w.scratch = (unsigned long long*)p; p += align_up((size_t)total_capacity * 8 * 4, 256);
+  w.order = (int32_t*)p;              p += align_up((size_t)total_capacity * 4, 256);
+  w.class_start = (int32_t*)p;        p += align_up((size_t)N * (num_classes + 1) * 4, 256);
+  w.max1 = (float*)p;
+  return w;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_softmax_decode_compact(const float* scores_in, int input_is_prob, const float* deltas,
+                                           const float* proposals, const int32_t* roi_offsets, const float* image_hw,
+                                           int N, int R, int K, int cls_agnostic, float wx, float wy, float ww,
+                                           float wh, float score_thresh, float* probs_out, float* cand_boxes,
+                                           float* cand_scores, int32_t* cand_roi, int32_t* cand_cls,
+                                           int32_t* cand_count, b200_stream_t stream) {
+  B200_CHECK_ARG(N >= 0 && R >= 0 && K > 0, "softmax_decode_compact: bad shape");
+  if (K + 1 > 32 * kMaxChunks) {
+    set_error("softmax_decode_compact: K+1=%d exceeds %d", K + 1, 32 * kMaxChunks);
+    return B200_ERR_UNSUPPORTED;
+  }
+  B200_CHECK_ARG(roi_offsets && image_hw && cand_count, "softmax_decode_compact: null index tensors");
+  B200_CHECK_ARG(R == 0 || (scores_in && deltas && proposals && cand_boxes && cand_scores && cand_roi && cand_cls),
+                 "softmax_decode_compact: null tensor");
+  if (N == 0) return B200_OK;
+  softmax_decode_compact_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(
+      scores_in, input_is_prob, deltas, proposals, roi_offsets, image_hw, K, cls_agnostic, wx, wy, ww, wh,
+      score_thresh, probs_out, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count);
+  B200_CUDA_LAUNCH_CHECK("softmax_decode_compact");
+  return B200_OK;
+}
+
+extern "C" size_t b200_batched_nms_workspace_bytes(int N, int total_capacity, int num_classes) {
+  return align_up((size_t)total_capacity * 8, 256) + align_up((size_t)total_capacity * 32, 256) +
+         align_up((size_t)total_capacity * 4, 256) + align_up((size_t)N * (num_classes + 1) * 4, 256) +
+         align_up((size_t)N * 4, 256);
+}
+
+extern "C" int b200_batched_nms(const float* boxes, const float* scores, const int32_t* classes,
+                                const int32_t* seg_offsets, const int32_t* seg_count, int N, int total_capacity,
+                                int num_classes, float iou_thresh, int max_keep, int32_t* keep, int32_t* keep_count,
+                                void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(N >= 0 && total_capacity >= 0 && num_classes > 0 && num_classes <= kMaxClasses, "batched_nms: bad shape");
+  B200_CHECK_ARG(max_keep >= 0, "batched_nms: max_keep must be >= 0 (pass the capacity for 'all')");
+  B200_CHECK_ARG(seg_offsets && seg_count && keep_count && (keep || max_keep == 0), "batched_nms: null tensor");
+  if (N == 0) return B200_OK;
+  if (!workspace || workspace_bytes < b200_batched_nms_workspace_bytes(N, total_capacity, num_classes)) {
+    set_error("batched_nms: workspace too small");
+    return B200_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NmsWorkspace w = carve(workspace, N, total_capacity, num_classes);
+  const size_t prep_smem = (size_t)(2 + 32) * num_classes * sizeof(int);
+  if (prep_smem > 48 * 1024)
+    B200_CUDA_CALL(cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+  nms_prepare_kernel<<<N, kPrepThreads, prep_smem, st>>>(boxes, classes, seg_offsets, seg_count, num_classes, w.max1,
+                                                        w.class_start, w.order);
+  B200_CUDA_LAUNCH_CHECK("nms_prepare");
+  // keys (8 B) + shifted boxes (16 B) + removed bitmap
+  const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_CALL(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
+    attr_set = true;
+  }
+  // `scratch` gives every class slice 4x its length: 2x for pow2 padding of the keys, 2x for the bitmap.
+  // slices are addressed at (base+cs)*4 to keep them disjoint.
+  nms_class_kernel<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(
+      boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1, w.class_start, w.order, w.kept, w.scratch);
+  B200_CUDA_LAUNCH_CHECK("nms_class");
+  nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
+  B200_CUDA_LAUNCH_CHECK("nms_finalize");
+  return B200_OK;
+}
+
+extern "C" int b200_gather_detections(const float* cand_boxes, const float* cand_scores, const int32_t* cand_roi,
+                                      const int32_t* cand_cls, const int32_t* seg_offsets, const int32_t* keep,
+                                      const int32_t* keep_count, int N, int max_keep, float* out_boxes,
+                                      float* out_scores, int64_t* out_classes, int64_t* out_roi_inds,
+                                      b200_stream_t stream) {
+  B200_CHECK_ARG(N >= 0 && max_keep >= 0, "gather_detections: bad shape");
+  if (N == 0 || max_keep == 0) return B200_OK;
+  gather_detections_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(cand_boxes, cand_scores, cand_roi, cand_cls, seg_offsets,
+                                                               keep, keep_count, max_keep, out_boxes, out_scores,
+                                                               out_classes, out_roi_inds);
+  B200_CUDA_LAUNCH_CHECK("gather_detections");
+  return B200_OK;
+}

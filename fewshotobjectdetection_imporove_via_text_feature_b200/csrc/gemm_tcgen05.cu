@@ -1,0 +1,343 @@
+// bf16 tensor-core GEMM for the text-fusion chain (A1, A4, A5, C1, C1'), hand-written for sm_100a:
+//   D[M,N] = act(A[M,K] . B[N,K]^T + bias[N])          A, B bf16 K-contiguous ("K-major"), fp32 accumulate
+// Reference ops replaced: nn.Linear at defrcn/modeling/roi_heads/attentive_modules.py:124 (w_q),
+// :166-175 (linear1/2/3), :72 (FFN linear1/2), fast_rcnn.py:407,415 (bbox_pred, cls_score),
+// roi_heads.py:1157-1159 (output_projection and the product with the text prototypes).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of A (128 x 64) and B (BN x 64) bf16 into a
+//               STAGES-deep ring of 128B-swizzled shared-memory tiles, completion on `full` mbarriers;
+//   warp 1      allocates TMEM (BN fp32 columns x 128 lanes), then one elected lane issues
+//               tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage and releases the stage
+//               with tcgen05.commit -> `empty` mbarrier; a final commit signals `acc_full`;
+//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (each warp owns its TMEM lane quarter = 32 output rows),
+//               bias + optional ReLU in registers, fp32 and/or bf16 stores (16 B vectors, row-contiguous).
+// OOB handling is TMA's: boxes hanging over M, N or K are zero-filled, stores are masked.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (reported as a CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int crd0, int crd1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128B swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address       bits [0,14)
+  d |= (uint64_t)0 << 16;                               // leading byte offset bits [16,30) (unused: swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset  bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const float* __restrict__ bias, float* __restrict__ d_f32, __nv_bfloat16* __restrict__ d_bf16,
+                         int ldd, __nv_bfloat16* __restrict__ d2, int ldd2, int M, int N, int K, int relu) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + S * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* acc_bar = empty_bar + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tiles + S * Cfg::kStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64) s_bias[i] = (bias && n0 + i < N) ? bias[n0 + i] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        unsigned char* sa = tiles + s * Cfg::kStageBytes;
+        unsigned char* sb = sa + kBM * kBK * 2;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        tma_load_2d(sa, &map_a, &full_bar[s], kb * kBK, m0);
+        tma_load_2d(sb, &map_b, &full_bar[s], kb * kBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (kb / S) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(tiles + s * Cfg::kStageBytes);
+        const uint32_t sb = sa + kBM * kBK * 2;
+        const uint64_t adesc = make_smem_desc_sw128(sa), bdesc = make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte descriptor units
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);                    // stage reusable once these MMAs have read it
+        if (kb == num_kb - 1) umma_commit(acc_bar);    // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(acc_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = __uint_as_float(r[i]) + s_bias[c0 + i];
+        if (relu) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (row < M) {
+        const int col = n0 + c0;
+        const bool full = col + 32 <= N;
+        if (d_f32) {
+          float* dst = d_f32 + (size_t)row * ldd + col;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = v[i];
+          }
+        }
+        if (d_bf16) {
+          __nv_bfloat16* dst = d_bf16 + (size_t)row * ldd + col;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+              w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+              reinterpret_cast<uint4*>(dst)[i] = w;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+        if (d2) {
+          __nv_bfloat16* dst = d2 + (size_t)row * ldd2 + col;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+              w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+              reinterpret_cast<uint4*>(dst)[i] = w;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows][cols] with leading dimension ld (elements); box = box_rows x 64 cols
+static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("gemm_bf16: cuTensorMapEncodeTiled unavailable"); return B200_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d)", (int)r); return B200_ERR_CUDA; }
+  return B200_OK;
+}
+
+template <int BN>
+static int launch_gemm(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd, int out_dtype,
+                       void* D2, int ldd2, int M, int N, int K, int relu, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, lda, kBM);
+  if (rc != B200_OK) return rc;
+  rc = make_map(&mb, B, N, K, ldb, BN);
+  if (rc != B200_OK) return rc;
+  auto kern = gemm_bf16_tcgen05_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, kBM));
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ma, mb, bias, out_dtype == B200_F32 ? (float*)D : nullptr,
+                                                            out_dtype == B200_BF16 ? (__nv_bfloat16*)D : nullptr, ldd,
+                                                            (__nv_bfloat16*)D2, ldd2, M, N, K, relu);
+  B200_CUDA_LAUNCH_CHECK("gemm_bf16");
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
+                              int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, b200_stream_t stream) {
+  B200_CHECK_ARG(A && B && (D || D2), "gemm_bf16: null tensor");
+  B200_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_bf16: bad shape");
+  B200_CHECK_ARG((out_dtype | 1) == 1, "gemm_bf16: bad out_dtype");
+  if (K % 8 || lda % 8 || ldb % 8 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
+    set_error("gemm_bf16: K, lda, ldb must be multiples of 8 and A, B 16-byte aligned (TMA)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (M == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mt = ceil_div(M, kBM);
+  // widest tile that still gives ~one CTA per SM; narrow N gets the narrowest tile that covers it
+  int bn;
+  if (N <= 32) bn = 32;
+  else if (N <= 64) bn = 64;
+  else if (mt * ceil_div(N, 256) >= 120) bn = 256;
+  else if (mt * ceil_div(N, 128) >= 100 || N <= 128) bn = 128;
+  else bn = 64;
+  switch (bn) {
+    case 32: return launch_gemm<32>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
+    case 64: return launch_gemm<64>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
+    case 128: return launch_gemm<128>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
+    default: return launch_gemm<256>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
+  }
+}

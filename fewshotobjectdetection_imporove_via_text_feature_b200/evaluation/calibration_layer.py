@@ -1,0 +1,106 @@
+"""Prototypical Calibration Block (PCB), B200-native.
+
+Mirror of defrcn/evaluation/calibration_layer.py:17-139.  The reference re-reads the image with cv2, runs an
+ImageNet ResNet-101, pools 1x1 ROI features, and then loops over detections in Python calling sklearn's
+cosine_similarity on the CPU (one `.cpu().numpy()` per detection).  Here the pooling is the ROIAlign kernel
+(1x1 @ 1/32, adaptive sampling) and the cosine + blend is one kernel over all detections of the image
+(csrc/fusion_elem.cu::pcb_cosine_blend_kernel); scores are updated in place and — like the reference — are not
+re-sorted.  The ImageNet CNN itself is outside the hot path: any callable
+`feature_extractor(image_bgr_uint8_hwc) -> (1,C,H/32,W/32)` plus an `fc` module can be plugged in.
+"""
+import torch
+
+from .. import ops
+from ..modeling.poolers import ROIPooler
+from ..structures import Boxes
+
+COCO_BASE_EXCLUDE = [7, 9, 10, 11, 12, 13, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38,
+                     40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 59, 61, 63, 64, 65, 66, 67, 68, 69,
+                     70, 71, 72, 73, 74, 75, 76, 77, 78, 79]
+
+
+class PrototypicalCalibrationBlock:
+    def __init__(self, cfg, feature_extractor=None, fc=None, prototypes=None, image_reader=None):
+        self.cfg = cfg
+        self.device = torch.device(cfg.MODEL.DEVICE)
+        self.alpha = cfg.TEST.PCB_ALPHA
+        self.feature_extractor, self.fc, self.image_reader = feature_extractor, fc, image_reader
+        self.roi_pooler = ROIPooler(output_size=(1, 1), scales=(1 / 32,), sampling_ratio=0, pooler_type="ROIAlignV2")
+        self.exclude_cls = self.clsid_filter()
+        self.prototypes = {}
+        self._proto_mat = self._exclude_mask = None
+        if prototypes is not None:
+            self.set_prototypes(prototypes)
+
+    # -- prototypes -----------------------------------------------------------------------------------
+    def set_prototypes(self, prototypes):
+        """prototypes: {class_id: (1,D) tensor} (the reference's dict) or a dense (K,D) tensor."""
+        if isinstance(prototypes, dict):
+            self.prototypes = prototypes
+            K = max(prototypes) + 1
+            D = next(iter(prototypes.values())).shape[-1]
+            mat = torch.zeros(K, D)
+            missing = torch.ones(K, dtype=torch.uint8)
+            for c, p in prototypes.items():
+                mat[c] = p.reshape(-1).float().cpu()
+                missing[c] = 0
+        else:
+            mat = prototypes.float().cpu()
+            self.prototypes = {c: mat[c:c + 1] for c in range(mat.shape[0])}
+            missing = torch.zeros(mat.shape[0], dtype=torch.uint8)
+        for c in self.exclude_cls:
+            if c < missing.numel():
+                missing[c] = 1
+        self._proto_mat = mat.to(self.device)
+        self._exclude_mask = missing.to(self.device)
+
+    def build_prototypes(self, support):
+        """support: iterable of (image, Boxes, gt_classes).  Class prototype = mean ROI feature (:44-82)."""
+        feats, labels = [], []
+        for img, boxes, gt in support:
+            feats.append(self.extract_roi_features(img, [boxes]).float().cpu())
+            labels.append(gt.cpu())
+        feats, labels = torch.cat(feats), torch.cat(labels)
+        protos = {int(c): feats[labels == c].mean(dim=0, keepdim=True) for c in labels.unique().tolist()}
+        self.set_prototypes(protos)
+        return protos
+
+    # -- features -------------------------------------------------------------------------------------
+    def extract_roi_features(self, img, boxes):
+        """img: HxWx3 BGR uint8 (numpy or tensor) or a precomputed (1,C,h,w) conv feature."""
+        if torch.is_tensor(img) and img.dim() == 4:
+            conv_feature = img.to(self.device)
+        else:
+            conv_feature = self.feature_extractor(img)
+        boxes = [b if isinstance(b, Boxes) or hasattr(b, "tensor") else Boxes(b) for b in boxes]
+        boxes = [Boxes(b.tensor.to(self.device)) for b in boxes]
+        pooled = self.roi_pooler([conv_feature.float()], boxes).flatten(1)
+        return self.fc(pooled) if self.fc is not None else pooled
+
+    # -- calibration ----------------------------------------------------------------------------------
+    def execute_calibration(self, inputs, dts):
+        inst = dts[0]["instances"]
+        n = len(inst)
+        if n == 0:
+            return dts
+        img = inputs[0].get("conv_feature") if isinstance(inputs[0], dict) else None
+        if img is None:
+            img = self.image_reader(inputs[0]["file_name"])
+        # features for every detection; the kernel applies the [ileft, iright) score window itself, on the device
+        feats = self.extract_roi_features(img, [inst.pred_boxes])
+        scores = inst.scores if inst.scores.is_contiguous() else inst.scores.contiguous()
+        ops.pcb_cosine_blend_(scores, feats, self._proto_mat, inst.pred_classes, self._exclude_mask, self.alpha,
+                              self.cfg.TEST.PCB_LOWER, self.cfg.TEST.PCB_UPPER)
+        if scores is not inst.scores:
+            inst.scores.copy_(scores)
+        return dts
+
+    def clsid_filter(self):
+        dsname = self.cfg.DATASETS.TEST[0]
+        if "test_all" in dsname:
+            if "coco" in dsname:
+                return list(COCO_BASE_EXCLUDE)
+            if "voc" in dsname:
+                return list(range(0, 15))
+            raise NotImplementedError
+        return []

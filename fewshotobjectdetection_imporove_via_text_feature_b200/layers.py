@@ -1,0 +1,224 @@
+"""Host-side building blocks around the hot path (torch plumbing, no custom arithmetic):
+the detectron2-v0.3 pieces the ROI head instantiates — FrozenBN bottleneck stage (res5, cuDNN),
+Box2BoxTransform, Matcher, label sub-sampling, event storage.  Names and semantics follow detectron2 so
+checkpoints (`roi_heads.res5.{0,1,2}.conv1.norm.weight`, ...) load unchanged."""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .structures import Boxes, Instances
+
+try:  # pragma: no cover
+    from detectron2.utils.events import get_event_storage
+except Exception:  # noqa: BLE001
+    class _Storage:
+        def __init__(self):
+            self.scalars = {}
+
+        def put_scalar(self, name, value, smoothing_hint=True):
+            self.scalars[name] = float(value)
+
+    _STORAGE = _Storage()
+
+    def get_event_storage():
+        return _STORAGE
+
+
+def cat(tensors, dim=0):
+    return tensors[0] if len(tensors) == 1 else torch.cat(tensors, dim)
+
+
+def nonzero_tuple(x):
+    return (x.unsqueeze(0) if x.dim() == 0 else x).nonzero().unbind(1)
+
+
+class FrozenBatchNorm2d(nn.Module):
+    _version = 3
+
+    def __init__(self, num_features, eps=1e-5):
+        super().__init__()
+        self.num_features, self.eps = num_features, eps
+        self.register_buffer("weight", torch.ones(num_features))
+        self.register_buffer("bias", torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features) - eps)
+
+    def scale_bias(self):
+        scale = self.weight * (self.running_var + self.eps).rsqrt()
+        return scale, self.bias - self.running_mean * scale
+
+    def forward(self, x):
+        s, b = self.scale_bias()
+        return x * s.reshape(1, -1, 1, 1).to(x.dtype) + b.reshape(1, -1, 1, 1).to(x.dtype)
+
+
+def get_norm(norm, channels):
+    if not norm:
+        return None
+    return {"FrozenBN": FrozenBatchNorm2d, "BN": nn.BatchNorm2d}[norm](channels)
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d with an optional `norm` child and activation (detectron2.layers.Conv2d)."""
+
+    def __init__(self, *a, norm=None, activation=None, **k):
+        super().__init__(*a, **k)
+        self.norm, self.activation = norm, activation
+
+    def forward(self, x):
+        x = F.conv2d(x, self.weight.to(x.dtype), None if self.bias is None else self.bias.to(x.dtype), self.stride,
+                     self.padding, self.dilation, self.groups)
+        if self.norm is not None:
+            x = self.norm(x)
+        return x if self.activation is None else self.activation(x)
+
+    def folded(self, dtype, channels_last):
+        """(weight, bias) with a FrozenBN child folded in; used by the inference fast path."""
+        w, b = self.weight.detach().float(), None if self.bias is None else self.bias.detach().float()
+        if isinstance(self.norm, FrozenBatchNorm2d):
+            s, sh = self.norm.scale_bias()
+            w = w * s.reshape(-1, 1, 1, 1)
+            b = sh if b is None else b * s + sh
+        w = w.to(dtype)
+        if channels_last:
+            w = w.contiguous(memory_format=torch.channels_last)
+        return w, None if b is None else b.to(dtype)
+
+
+class BottleneckBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, *, bottleneck_channels, stride=1, num_groups=1, norm="BN",
+                 stride_in_1x1=False, dilation=1):
+        super().__init__()
+        self.in_channels, self.out_channels, self.stride = in_channels, out_channels, stride
+        self.shortcut = None
+        if in_channels != out_channels:
+            self.shortcut = Conv2d(in_channels, out_channels, kernel_size=1, stride=stride, bias=False,
+                                   norm=get_norm(norm, out_channels))
+        s1, s3 = (stride, 1) if stride_in_1x1 else (1, stride)
+        self.conv1 = Conv2d(in_channels, bottleneck_channels, kernel_size=1, stride=s1, bias=False,
+                            norm=get_norm(norm, bottleneck_channels))
+        self.conv2 = Conv2d(bottleneck_channels, bottleneck_channels, kernel_size=3, stride=s3, padding=dilation,
+                            bias=False, groups=num_groups, dilation=dilation, norm=get_norm(norm, bottleneck_channels))
+        self.conv3 = Conv2d(bottleneck_channels, out_channels, kernel_size=1, bias=False, norm=get_norm(norm, out_channels))
+        for m in (self.conv1, self.conv2, self.conv3, self.shortcut):
+            if m is not None:
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self._fold_key, self._fold = None, None
+
+    def forward(self, x):
+        out = F.relu_(self.conv1(x))
+        out = F.relu_(self.conv2(out))
+        out = self.conv3(out)
+        sc = x if self.shortcut is None else self.shortcut(x)
+        out += sc
+        return F.relu_(out)
+
+    def forward_folded(self, x):
+        """Eval-only: FrozenBN folded into the conv weights, cached per (dtype, layout, parameter versions)."""
+        convs = [self.conv1, self.conv2, self.conv3, self.shortcut]
+        cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+        key = (x.dtype, cl, x.device) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs if c is not None)
+        if key != self._fold_key:
+            self._fold = [None if c is None else c.folded(x.dtype, cl) for c in convs]
+            self._fold_key = key
+        (w1, b1), (w2, b2), (w3, b3), sc = self._fold
+        out = F.relu_(F.conv2d(x, w1, b1, self.conv1.stride))
+        out = F.relu_(F.conv2d(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups))
+        out = F.conv2d(out, w3, b3)
+        out += x if sc is None else F.conv2d(x, sc[0], sc[1], self.shortcut.stride)
+        return F.relu_(out)
+
+
+def make_stage(block_class, num_blocks, first_stride, *, in_channels, out_channels, **kwargs):
+    blocks = []
+    for i in range(num_blocks):
+        blocks.append(block_class(in_channels=in_channels, out_channels=out_channels,
+                                  stride=first_stride if i == 0 else 1, **kwargs))
+        in_channels = out_channels
+    return blocks
+
+
+_SCALE_CLAMP = math.log(1000.0 / 16)
+
+
+class Box2BoxTransform:
+    """(dx,dy,dw,dh) parameterisation.  `apply_deltas` here is the torch form used on the training path and in
+    tests; inference decodes inside the compaction kernel (csrc/detect_post.cu)."""
+
+    def __init__(self, weights, scale_clamp=_SCALE_CLAMP):
+        self.weights, self.scale_clamp = tuple(weights), scale_clamp
+
+    def get_deltas(self, src, dst):
+        sw, sh = src[:, 2] - src[:, 0], src[:, 3] - src[:, 1]
+        sx, sy = src[:, 0] + 0.5 * sw, src[:, 1] + 0.5 * sh
+        tw, th = dst[:, 2] - dst[:, 0], dst[:, 3] - dst[:, 1]
+        tx, ty = dst[:, 0] + 0.5 * tw, dst[:, 1] + 0.5 * th
+        wx, wy, ww, wh = self.weights
+        return torch.stack((wx * (tx - sx) / sw, wy * (ty - sy) / sh, ww * torch.log(tw / sw), wh * torch.log(th / sh)), dim=1)
+
+    def apply_deltas(self, deltas, boxes):
+        boxes = boxes.to(deltas.dtype)
+        w, h = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+        cx, cy = boxes[:, 0] + 0.5 * w, boxes[:, 1] + 0.5 * h
+        wx, wy, ww, wh = self.weights
+        dx, dy = deltas[:, 0::4] / wx, deltas[:, 1::4] / wy
+        dw = torch.clamp(deltas[:, 2::4] / ww, max=self.scale_clamp)
+        dh = torch.clamp(deltas[:, 3::4] / wh, max=self.scale_clamp)
+        pcx, pcy = dx * w[:, None] + cx[:, None], dy * h[:, None] + cy[:, None]
+        pw, ph = torch.exp(dw) * w[:, None], torch.exp(dh) * h[:, None]
+        out = torch.zeros_like(deltas)
+        out[:, 0::4], out[:, 1::4] = pcx - 0.5 * pw, pcy - 0.5 * ph
+        out[:, 2::4], out[:, 3::4] = pcx + 0.5 * pw, pcy + 0.5 * ph
+        return out
+
+
+class Matcher:
+    """argmax-IoU assignment with thresholded labels (detectron2.modeling.matcher.Matcher, no low-quality path)."""
+
+    def __init__(self, thresholds, labels, allow_low_quality_matches=False):
+        assert not allow_low_quality_matches, "ROI heads never enable low-quality matches"
+        self.thresholds = [-float("inf")] + list(thresholds) + [float("inf")]
+        self.labels = list(labels)
+
+    def __call__(self, iou):  # iou: (M gt, N proposals)
+        if iou.numel() == 0:
+            return (iou.new_zeros((iou.size(1),), dtype=torch.int64),
+                    iou.new_full((iou.size(1),), self.labels[0], dtype=torch.int8))
+        vals, idx = iou.max(dim=0)
+        lab = idx.new_full(idx.size(), 1, dtype=torch.int8)
+        for l, lo, hi in zip(self.labels, self.thresholds[:-1], self.thresholds[1:]):
+            lab[(vals >= lo) & (vals < hi)] = l
+        return idx, lab
+
+
+def subsample_labels(labels, num_samples, positive_fraction, bg_label):
+    pos = nonzero_tuple((labels != -1) & (labels != bg_label))[0]
+    neg = nonzero_tuple(labels == bg_label)[0]
+    n_pos = min(pos.numel(), int(num_samples * positive_fraction))
+    n_neg = min(neg.numel(), num_samples - n_pos)
+    p1 = torch.randperm(pos.numel(), device=pos.device)[:n_pos]
+    p2 = torch.randperm(neg.numel(), device=neg.device)[:n_neg]
+    return pos[p1], neg[p2]
+
+
+def add_ground_truth_to_proposals(gt_boxes, proposals):
+    out = []
+    logit = math.log((1.0 - 1e-10) / (1 - (1.0 - 1e-10)))
+    for gt, p in zip(gt_boxes, proposals):
+        g = Instances(p.image_size)
+        g.proposal_boxes = gt
+        g.objectness_logits = logit * torch.ones(len(gt), device=gt.tensor.device)
+        out.append(Instances.cat([p, g]))
+    return out
+
+
+def smooth_l1_loss(input, target, beta, reduction="none"):
+    n = torch.abs(input - target)
+    loss = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+    if reduction == "sum":
+        return loss.sum()
+    if reduction == "mean":
+        return loss.mean() if loss.numel() > 0 else 0.0 * loss.sum()
+    return loss

@@ -1,0 +1,272 @@
+"""ROI heads, B200-native, behind Detectron2's ROI_HEADS_REGISTRY / `forward(images, features, proposals, targets)`.
+
+API mirror of defrcn/modeling/roi_heads/roi_heads.py: `ROI_HEADS_REGISTRY`, `build_roi_heads` (:27-45),
+`ROIHeads` (:78-277), `Res5ROIHeads` (:280-386), `SematicRes5ROIHeads` (:921-1149),
+`SematicRes5ROIHeadsCrossOutput` (:1150-1171).  State-dict names match (`res5.*`, `box_predictor.*`,
+`attention.*`, `output_projection.*`, `sematic_projection.*`, `projection_matrix`).
+
+Hot path in eval mode: ROIAlign kernel (channels-last gather) -> res5 (cuDNN, FrozenBN folded, bf16 channels-last)
+-> spatial mean -> tcgen05 text-fusion chain -> predictor GEMMs -> fused softmax/decode/threshold/NMS kernels.
+"""
+import logging
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ... import ops
+from ...config import b200_opt
+from ...layers import (BottleneckBlock, Box2BoxTransform, Matcher, add_ground_truth_to_proposals, cat,
+                       get_event_storage, make_stage, nonzero_tuple, subsample_labels)
+from ...structures import Boxes, Instances, Registry, ShapeSpec, pairwise_iou
+from ..poolers import ROIPooler
+from .attentive_modules import SEMANTIC_DIM, SematicProposalAttention
+from .fast_rcnn import ROI_HEADS_OUTPUT_REGISTRY, FastRCNNOutputs
+
+ROI_HEADS_REGISTRY = Registry("ROI_HEADS")
+logger = logging.getLogger(__name__)
+
+
+def build_roi_heads(cfg, input_shape):
+    return ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME)(cfg, input_shape)
+
+
+def select_foreground_proposals(proposals, bg_label):
+    fg, masks = [], []
+    for p in proposals:
+        m = (p.gt_classes != -1) & (p.gt_classes != bg_label)
+        fg.append(p[m.nonzero().squeeze(1)])
+        masks.append(m)
+    return fg, masks
+
+
+class ROIHeads(nn.Module):
+    """Per-region computation base: proposal matching / sampling shared by all heads."""
+
+    def __init__(self, cfg, input_shape: Dict[str, ShapeSpec]):
+        super().__init__()
+        rh, bh = cfg.MODEL.ROI_HEADS, cfg.MODEL.ROI_BOX_HEAD
+        self.batch_size_per_image = rh.BATCH_SIZE_PER_IMAGE
+        self.positive_sample_fraction = rh.POSITIVE_FRACTION
+        self.test_score_thresh = rh.SCORE_THRESH_TEST
+        self.test_nms_thresh = rh.NMS_THRESH_TEST
+        self.test_detections_per_img = cfg.TEST.DETECTIONS_PER_IMAGE
+        self.in_features = rh.IN_FEATURES
+        self.num_classes = rh.NUM_CLASSES
+        self.proposal_append_gt = rh.PROPOSAL_APPEND_GT
+        self.feature_strides = {k: v.stride for k, v in input_shape.items()}
+        self.feature_channels = {k: v.channels for k, v in input_shape.items()}
+        self.cls_agnostic_bbox_reg = bh.CLS_AGNOSTIC_BBOX_REG
+        self.smooth_l1_beta = bh.SMOOTH_L1_BETA
+        self.proposal_matcher = Matcher(rh.IOU_THRESHOLDS, rh.IOU_LABELS, allow_low_quality_matches=False)
+        self.box2box_transform = Box2BoxTransform(weights=bh.BBOX_REG_WEIGHTS)
+
+    def _assign_labels(self, matched_idxs, matched_labels, gt_classes):
+        if gt_classes.numel() > 0:
+            gt_classes = gt_classes[matched_idxs]
+            gt_classes[matched_labels == 0] = self.num_classes   # unmatched -> background
+            gt_classes[matched_labels == -1] = -1                # ignore
+        else:
+            gt_classes = torch.zeros_like(matched_idxs) + self.num_classes
+        return gt_classes
+
+    def _sample_proposals(self, matched_idxs, matched_labels, gt_classes):
+        gt_classes = self._assign_labels(matched_idxs, matched_labels, gt_classes)
+        fg, bg = subsample_labels(gt_classes, self.batch_size_per_image, self.positive_sample_fraction, self.num_classes)
+        idx = torch.cat([fg, bg], dim=0)
+        return idx, gt_classes[idx]
+
+    @torch.no_grad()
+    def label_and_sample_proposals(self, proposals, targets):
+        if self.proposal_append_gt:
+            proposals = add_ground_truth_to_proposals([t.gt_boxes for t in targets], proposals)
+        out, n_fg, n_bg = [], [], []
+        for p, t in zip(proposals, targets):
+            has_gt = len(t) > 0
+            idxs, labels = self.proposal_matcher(pairwise_iou(t.gt_boxes, p.proposal_boxes))
+            sampled, gt_classes = self._sample_proposals(idxs, labels, t.gt_classes)
+            p = p[sampled]
+            p.gt_classes = gt_classes
+            if has_gt:
+                src = idxs[sampled]
+                for name, value in t.get_fields().items():
+                    if name.startswith("gt_") and not p.has(name):
+                        p.set(name, value[src])
+            else:
+                p.gt_boxes = Boxes(t.gt_boxes.tensor.new_zeros((len(sampled), 4)))
+            n_bg.append((gt_classes == self.num_classes).sum().item())
+            n_fg.append(gt_classes.numel() - n_bg[-1])
+            out.append(p)
+        st = get_event_storage()
+        st.put_scalar("roi_head/num_fg_samples", np.mean(n_fg))
+        st.put_scalar("roi_head/num_bg_samples", np.mean(n_bg))
+        return out
+
+    def forward(self, images, features, proposals, targets=None):
+        raise NotImplementedError()
+
+
+@ROI_HEADS_REGISTRY.register()
+class Res5ROIHeads(ROIHeads):
+    """C4 head: shared ROIAlign + res5, then the predictor (plain DeFRCN baseline, no text)."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape)
+        assert len(self.in_features) == 1
+        bh = cfg.MODEL.ROI_BOX_HEAD
+        assert not cfg.MODEL.KEYPOINT_ON
+        self.channels_last = bool(b200_opt(cfg, "CHANNELS_LAST", True))
+        self.res5_dtype = getattr(torch, b200_opt(cfg, "RES5_DTYPE", "bfloat16"))
+        self.pooler = ROIPooler(output_size=bh.POOLER_RESOLUTION, scales=(1.0 / self.feature_strides[self.in_features[0]],),
+                                sampling_ratio=bh.POOLER_SAMPLING_RATIO, pooler_type=bh.POOLER_TYPE,
+                                channels_last_out=self.channels_last)
+        self.res5, self.out_channels = self._build_res5_block(cfg)
+        self.output_layer = cfg.MODEL.ROI_HEADS.OUTPUT_LAYER
+        self.box_predictor = ROI_HEADS_OUTPUT_REGISTRY.get(self.output_layer)(
+            cfg, self.out_channels, self.num_classes, self.cls_agnostic_bbox_reg)
+
+    def _build_res5_block(self, cfg):
+        r = cfg.MODEL.RESNETS
+        out_channels = r.RES2_OUT_CHANNELS * 8
+        assert not r.DEFORM_ON_PER_STAGE[-1], "Deformable conv is not supported in the res5 head."
+        blocks = make_stage(BottleneckBlock, 3, first_stride=2, in_channels=out_channels // 2,
+                            bottleneck_channels=r.NUM_GROUPS * r.WIDTH_PER_GROUP * 8, out_channels=out_channels,
+                            num_groups=r.NUM_GROUPS, norm=r.NORM, stride_in_1x1=r.STRIDE_IN_1X1)
+        return nn.Sequential(*blocks), out_channels
+
+    def _res5_forward(self, x):
+        """res5 stays on cuDNN.  Unless its weights are being trained, FrozenBN is folded into
+        the convolutions and the stage runs in `res5_dtype` channels-last; gradients still flow to `x`."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.res5.parameters()):
+            return self.res5(x)
+        y = x.to(self.res5_dtype)
+        for blk in self.res5:
+            y = blk.forward_folded(y)
+        return y
+
+    def _shared_roi_transform(self, features, boxes):
+        return self._res5_forward(self.pooler(features, boxes))
+
+    def _pooled(self, features, proposals):
+        box_features = self._shared_roi_transform([features[f] for f in self.in_features],
+                                                  [x.proposal_boxes for x in proposals])
+        return box_features.mean(dim=[2, 3], dtype=torch.float32)
+
+    def forward(self, images, features, proposals, targets=None):
+        del images
+        if self.training:
+            proposals = self.label_and_sample_proposals(proposals, targets)
+        del targets
+        feature_pooled = self._pooled(features, proposals)
+        logits, deltas = self.box_predictor(feature_pooled)
+        outputs = FastRCNNOutputs(self.box2box_transform, logits, deltas, proposals, self.smooth_l1_beta)
+        if self.training:
+            return [], outputs.losses()
+        pred, _ = outputs.inference(self.test_score_thresh, self.test_nms_thresh, self.test_detections_per_img)
+        return pred, {}
+
+
+@ROI_HEADS_REGISTRY.register()
+class SematicRes5ROIHeads(Res5ROIHeads):
+    """C4 head whose classifier sees the ROI feature after cross-attention over class-name text embeddings."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape)
+        self.__init_LV_model__(self.out_channels, cfg)
+        self.box_predictor = ROI_HEADS_OUTPUT_REGISTRY.get(self.output_layer)(
+            cfg, self.out_channels, self.num_classes, self.cls_agnostic_bbox_reg)
+
+    def __init_LV_model__(self, input_size, cfg):
+        self.addition_model = cfg.MODEL.ADDITION.NAME
+        self.semantic_dim = SEMANTIC_DIM[self.addition_model]
+        self.attention = SematicProposalAttention(input_size, cfg=cfg, is_multi=False)
+        if cfg.MODEL.ADDITION.FREEZEATTENTION:
+            for p in self.attention.parameters():
+                p.requires_grad = False
+        self.output_projection = nn.Linear(input_size, self.semantic_dim)
+        self.sematic_projection = nn.Linear(self.semantic_dim, input_size)
+        self.projection_matrix = nn.Parameter(torch.randn(self.semantic_dim, input_size) * 1e-8)
+
+    @torch.no_grad()
+    def label_proposals(self, proposals, targets):
+        """Attach GT labels to *all* proposals without sampling (test-with-GT mode).  Faithful to the reference,
+        including its quirk: labels come out ordered [foreground..., background...] while the proposals keep
+        their original order (roi_heads.py:1008-1028)."""
+        out = []
+        for p, t in zip(proposals, targets):
+            idxs, labels = self.proposal_matcher(pairwise_iou(t.gt_boxes, p.proposal_boxes))
+            gt_classes = self._assign_labels(idxs, labels, t.gt_classes)
+            pos = nonzero_tuple((gt_classes != -1) & (gt_classes != self.num_classes))[0]
+            neg = nonzero_tuple(gt_classes == self.num_classes)[0]
+            order = torch.cat([pos, neg], dim=0)
+            p.gt_classes = gt_classes[order]
+            if len(t) > 0:
+                src = idxs[order]
+                for name, value in t.get_fields().items():
+                    if name.startswith("gt_") and not p.has(name):
+                        p.set(name, value[src])
+            out.append(p)
+        return out
+
+    def cal_CE_att(self, output_att, gt_classes):
+        a = F.relu(self.output_projection(output_att["sim2stext"]))
+        score = F.softmax(torch.matmul(a, output_att["text_feat"].transpose(0, 1)), dim=1)
+        return {"loss_attentive": F.cross_entropy(score, gt_classes, reduction="mean")}
+
+    def forward_att(self, feature_pooled, gt_classes=0):
+        attn, output_att = self.attention(feature_pooled)
+        loss_att = {}
+        if self.training:
+            # CE over the attention *probabilities* (K+2 columns) — reference behaviour, roi_heads.py:1079-1081
+            loss_att["loss_attentive"] = F.cross_entropy(attn[0], gt_classes, reduction="mean")
+        logits, deltas = self.box_predictor(feature_pooled, output_att["sim2stext"],
+                                            output_att.get("x_bf16"), output_att.get("sim2stext_bf16"))
+        output_att["pred_logits"], output_att["pred_bbox"] = logits, deltas
+        return output_att, loss_att
+
+    def forward(self, images, features, proposals, targets=None):
+        del images
+        test_with_gt = (not self.training) and bool(targets)
+        gt_classes = 0
+        if self.training:
+            proposals = self.label_and_sample_proposals(proposals, targets)
+            gt_classes = cat([p.gt_classes for p in proposals], dim=0)
+        elif test_with_gt:
+            proposals = self.label_proposals(proposals, targets)
+        feature_pooled = self._pooled(features, proposals)
+        att_output, att_loss = self.forward_att(feature_pooled, gt_classes)
+        outputs = FastRCNNOutputs(self.box2box_transform, att_output["pred_logits"], att_output["pred_bbox"], proposals,
+                                  self.smooth_l1_beta)
+        if self.training:
+            losses = dict(outputs.losses())
+            losses.update(att_loss)
+            return [], losses
+        pred, _ = outputs.inference(self.test_score_thresh, self.test_nms_thresh, self.test_detections_per_img)
+        return pred, {}
+
+
+@ROI_HEADS_REGISTRY.register()
+class SematicRes5ROIHeadsCrossOutput(SematicRes5ROIHeads):
+    """Logits are dot products of the projected fused feature with the text prototypes (roi_heads.py:1154-1171);
+    used with OUTPUT_LAYER = FastRCNNAttentionOutputLayers."""
+
+    def forward_att(self, feature_pooled, gt_classes=0):
+        if self.training and torch.is_grad_enabled():
+            _, output_att = self.attention(feature_pooled)
+            a = F.relu(self.output_projection(output_att["sim2stext"]))
+            score = torch.matmul(a, output_att["text_feat"].transpose(0, 1))
+            xb = None
+        else:
+            extra = {"output_projection.weight": self.output_projection.weight, "output_projection.bias": self.output_projection.bias}
+            _, output_att = self.attention(feature_pooled, extra=extra)
+            w = output_att["fused_w"]
+            a = ops.gemm_bf16(output_att["sim2stext_bf16"], w["extra.output_projection.weight"],
+                              w["extra.output_projection.bias"], relu=True, out_dtype=torch.bfloat16)
+            tb = output_att["text_feat"].to(torch.bfloat16).contiguous()
+            score = ops.gemm_bf16(a, tb)
+            xb = output_att.get("x_bf16")
+        logits, deltas = self.box_predictor(feature_pooled, score, xb, None)
+        output_att["pred_logits"], output_att["pred_bbox"] = logits, deltas
+        return output_att, {}

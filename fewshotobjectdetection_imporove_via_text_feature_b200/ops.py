@@ -1,0 +1,388 @@
+"""Torch-facing operators over the C-ABI kernels.
+
+PyTorch is plumbing here: device memory (caching allocator), the current CUDA stream, and autograd glue.
+All arithmetic on the ROI-head hot path is done by the kernels in csrc/ through `_lib.call`.
+Reference call sites are cited per op.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, NCHW, NHWC
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.B200Error("b200roi ops run on CUDA tensors only (got %s); there is no CPU fallback" % t.device)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.B200Error("unsupported dtype %s (float32 | bfloat16)" % t.dtype)
+
+
+def _layout4(t):
+    """(layout flag, tensor usable as-is) for a 4-d tensor: NCHW-contiguous or channels_last."""
+    if t.is_contiguous():
+        return NCHW, t
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return NHWC, t
+    return NCHW, t.contiguous()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _empty4(N, C, H, W, dtype, device, channels_last):
+    return torch.empty((N, C, H, W), dtype=dtype, device=device,
+                       memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+
+
+# ---------------------------------------------------------------------------------------------------
+# G1 + G2  (defrcn/modeling/meta_arch/gdl.py:6-38, rcnn.py:94-97)
+# ---------------------------------------------------------------------------------------------------
+class _GDLAffine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, lam, out_dtype, channels_last_out):
+        _require_cuda(x, weight, bias)
+        in_layout, x = _layout4(x)
+        N, C, H, W = x.shape
+        out_dtype = out_dtype or x.dtype
+        y = _empty4(N, C, H, W, out_dtype, x.device, channels_last_out)
+        w = None if weight is None else weight.detach().reshape(-1).float().contiguous()
+        b = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+        _lib.call("b200_gdl_affine_fwd", x.data_ptr(), _ptr(w), _ptr(b), y.data_ptr(), N, C, H, W, _dt(x), in_layout,
+                  _dt(y), NHWC if channels_last_out else NCHW, _stream())
+        ctx.save_for_backward(x, w)
+        ctx.meta = (lam, in_layout, channels_last_out, weight is not None, bias is not None,
+                    None if weight is None else weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        lam, in_layout, cl_out, has_w, has_b, wshape = ctx.meta
+        N, C, H, W = x.shape
+        want_cl = cl_out
+        gy = gy.contiguous(memory_format=torch.channels_last) if want_cl else gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _empty4(N, C, H, W, x.dtype, x.device, in_layout == NHWC)
+        if has_w and ctx.needs_input_grad[1]:
+            gw = torch.empty(C, dtype=torch.float32, device=x.device)
+        if has_b and ctx.needs_input_grad[2]:
+            gb = torch.empty(C, dtype=torch.float32, device=x.device)
+        nbytes = _lib.lib().b200_gdl_affine_bwd_workspace_bytes(N, C, H, W)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.call("b200_gdl_affine_bwd", gy.data_ptr(), x.data_ptr(), _ptr(w), float(lam), _ptr(gx), _ptr(gw), _ptr(gb),
+                  N, C, H, W, _dt(x), in_layout, _dt(gy), NHWC if want_cl else NCHW, ws.data_ptr(), nbytes, _stream())
+        if gw is not None:
+            gw = gw.reshape(wshape)
+        if gb is not None:
+            gb = gb.reshape(wshape)
+        return gx, gw, gb, None, None, None
+
+
+def gdl_scale(g, lam):
+    """GDL backward on its own: g * lambda (same kernel, weight == NULL)."""
+    _require_cuda(g)
+    layout, g = _layout4(g)
+    N, C, H, W = g.shape
+    out = _empty4(N, C, H, W, g.dtype, g.device, layout == NHWC)
+    _lib.call("b200_gdl_affine_bwd", g.data_ptr(), 0, 0, float(lam), out.data_ptr(), 0, 0, N, C, H, W, _dt(g), layout,
+              _dt(g), layout, 0, 0, _stream())
+    return out
+
+
+def gdl_affine(x, weight=None, bias=None, lam=1.0, out_dtype=None, channels_last_out=False):
+    """affine(decouple_layer(x, lam)): y = x*w + b forward, grad_x = g*w*lam backward, in one pass each.
+    Optionally emits channels_last and/or bf16 so ROIAlign gathers without a re-layout."""
+    return _GDLAffine.apply(x, weight, bias, lam, out_dtype, channels_last_out)
+
+
+# ---------------------------------------------------------------------------------------------------
+# P1 / P1b  (roi_heads.py:300-305,339-340 -> detectron2 ROIPooler -> torchvision.ops.roi_align)
+# ---------------------------------------------------------------------------------------------------
+class _ROIAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, rois, roi_batch_offsets, output_size, spatial_scale, sampling_ratio, aligned,
+                channels_last_out):
+        _require_cuda(feat, rois)
+        in_layout, feat = _layout4(feat)
+        rois = rois.detach().float().contiguous()
+        N, C, H, W = feat.shape
+        R = rois.shape[0]
+        PH, PW = output_size
+        out = _empty4(R, C, PH, PW, feat.dtype, feat.device, channels_last_out)
+        nbytes = _lib.lib().b200_roi_align_fwd_workspace_bytes(N, C, H, W, _dt(feat), in_layout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device) if nbytes else None
+        _lib.call("b200_roi_align_fwd", feat.data_ptr(), rois.data_ptr(), out.data_ptr(), N, C, H, W, R, PH, PW,
+                  float(spatial_scale), int(sampling_ratio), int(bool(aligned)), _dt(feat), in_layout,
+                  NHWC if channels_last_out else NCHW, _ptr(ws), nbytes, _stream())
+        ctx.save_for_backward(rois, roi_batch_offsets)
+        ctx.meta = (feat.shape, feat.dtype, in_layout, output_size, spatial_scale, sampling_ratio, aligned,
+                    channels_last_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, offs = ctx.saved_tensors
+        shape, dtype, in_layout, (PH, PW), scale, sr, aligned, cl_out = ctx.meta
+        if offs is None:
+            raise _lib.B200Error("roi_align backward needs roi_batch_offsets (ROIs grouped by image)")
+        N, C, H, W = shape
+        R = rois.shape[0]
+        g = g.contiguous(memory_format=torch.channels_last) if cl_out else g.contiguous()
+        gin = _empty4(N, C, H, W, dtype, g.device, in_layout == NHWC)
+        g_layout = NHWC if cl_out else NCHW
+        nbytes = _lib.lib().b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, PH, PW, _dt(g), in_layout, g_layout)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+        _lib.call("b200_roi_align_bwd", g.data_ptr(), rois.data_ptr(), offs.data_ptr(), gin.data_ptr(), N, C, H, W, R,
+                  PH, PW, float(scale), int(sr), int(bool(aligned)), _dt(g), g_layout, in_layout, ws.data_ptr(), nbytes,
+                  _stream())
+        return gin, None, None, None, None, None, None, None
+
+
+def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=True, channels_last_out=False,
+              roi_batch_offsets=None):
+    """torchvision.ops.roi_align semantics.  feat (N,C,H,W) NCHW or channels_last, fp32|bf16; rois (R,5).
+    roi_batch_offsets: int32 (N+1) prefix of per-image ROI counts — required for backward."""
+    if isinstance(output_size, int):
+        output_size = (output_size, output_size)
+    return _ROIAlign.apply(feat, rois, roi_batch_offsets, tuple(output_size), spatial_scale, sampling_ratio, aligned,
+                           channels_last_out)
+
+
+def boxes_to_rois(box_tensors):
+    """detectron2 convert_boxes_to_pooler_format: list[(Ri,4)] -> (rois (R,5), int32 offsets (N+1))."""
+    dev = box_tensors[0].device
+    counts = [int(b.shape[0]) for b in box_tensors]
+    offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32)
+    idx = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.float32), torch.tensor(counts)).to(dev, non_blocking=True)
+    rois = torch.cat([idx[:, None], torch.cat(box_tensors, 0).float()], dim=1)
+    return rois, offs.to(dev, non_blocking=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# D1..D3  (fast_rcnn.py:46-134, :306-334)
+# ---------------------------------------------------------------------------------------------------
+def softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, weights=(10.0, 10.0, 5.0, 5.0),
+                           input_is_prob=False, want_probs=True):
+    """Returns dict(probs, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count, seg_offsets)."""
+    _require_cuda(scores, deltas, proposals)
+    scores, deltas, proposals = scores.float().contiguous(), deltas.float().contiguous(), proposals.float().contiguous()
+    R, K = scores.shape[0], scores.shape[1] - 1
+    N = roi_offsets.numel() - 1
+    agnostic = deltas.shape[1] == 4 and K != 1
+    dev = scores.device
+    probs = torch.empty_like(scores) if want_probs else None
+    cap = max(R * K, 1)
+    cb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    cs = torch.empty(cap, dtype=torch.float32, device=dev)
+    cr = torch.empty(cap, dtype=torch.int32, device=dev)
+    cc = torch.empty(cap, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+    _lib.call("b200_softmax_decode_compact", scores.data_ptr(), int(input_is_prob), deltas.data_ptr(), proposals.data_ptr(),
+              roi_offsets.data_ptr(), image_hw.data_ptr(), N, R, K, int(agnostic), *map(float, weights),
+              float(score_thresh), _ptr(probs), cb.data_ptr(), cs.data_ptr(), cr.data_ptr(), cc.data_ptr(),
+              cnt.data_ptr(), _stream())
+    return dict(probs=probs, cand_boxes=cb, cand_scores=cs, cand_roi=cr, cand_cls=cc, cand_count=cnt[:N],
+                seg_offsets=(roi_offsets * K).to(torch.int32), capacity=cap)
+
+
+def batched_nms_segments(boxes, scores, classes, seg_offsets, seg_count, num_classes, iou_thresh, max_keep):
+    """Device-side batched NMS over N segments; returns (keep (N,max_keep) int32 segment-relative, keep_count (N))."""
+    _require_cuda(boxes, scores, classes)
+    N = seg_count.numel()
+    cap = boxes.shape[0]
+    dev = boxes.device
+    keep = torch.empty((max(N, 1), max(max_keep, 1)), dtype=torch.int32, device=dev)
+    kc = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+    nbytes = _lib.lib().b200_batched_nms_workspace_bytes(N, cap, num_classes)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.call("b200_batched_nms", boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), seg_offsets.data_ptr(),
+              seg_count.data_ptr(), N, cap, num_classes, float(iou_thresh), int(max_keep), keep.data_ptr(), kc.data_ptr(),
+              ws.data_ptr(), nbytes, _stream())
+    return keep[:N, :max_keep], kc[:N]
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """Drop-in for detectron2.layers.batched_nms (fast_rcnn.py:125): returns int64 keep indices sorted by score.
+    The variable-length result forces one device->host read of the count."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    dev = boxes.device
+    boxes, scores = boxes.float().contiguous(), scores.float().contiguous()
+    cls = idxs.to(torch.int32).contiguous()
+    num_classes = int(cls.max().item()) + 1
+    so = torch.zeros(1, dtype=torch.int32, device=dev)
+    sc = torch.full((1,), n, dtype=torch.int32, device=dev)
+    keep, kc = batched_nms_segments(boxes, scores, cls, so, sc, num_classes, iou_threshold, n)
+    return keep[0, :int(kc.item())].to(torch.int64)
+
+
+def fast_rcnn_inference_device(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, nms_thresh, topk,
+                               weights=(10.0, 10.0, 5.0, 5.0), input_is_prob=False, want_probs=False):
+    """Whole post-processing on the device, no host synchronisation.  Returns padded tensors:
+    boxes (N,topk,4), scores (N,topk), classes (N,topk) int64, roi_inds (N,topk) int64, counts (N) int32,
+    n_candidates (N) int32."""
+    c = softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, weights, input_is_prob,
+                               want_probs)
+    N = roi_offsets.numel() - 1
+    K = scores.shape[1] - 1
+    dev = scores.device
+    topk = int(topk) if topk >= 0 else c["capacity"]
+    keep, kc = batched_nms_segments(c["cand_boxes"], c["cand_scores"], c["cand_cls"], c["seg_offsets"], c["cand_count"],
+                                    K, nms_thresh, topk)
+    keep = keep.contiguous()
+    ob = torch.empty((N, topk, 4), dtype=torch.float32, device=dev)
+    os_ = torch.empty((N, topk), dtype=torch.float32, device=dev)
+    oc = torch.empty((N, topk), dtype=torch.int64, device=dev)
+    orr = torch.empty((N, topk), dtype=torch.int64, device=dev)
+    _lib.call("b200_gather_detections", c["cand_boxes"].data_ptr(), c["cand_scores"].data_ptr(), c["cand_roi"].data_ptr(),
+              c["cand_cls"].data_ptr(), c["seg_offsets"].data_ptr(), keep.data_ptr(), kc.data_ptr(), N, topk,
+              ob.data_ptr(), os_.data_ptr(), oc.data_ptr(), orr.data_ptr(), _stream())
+    return dict(boxes=ob, scores=os_, classes=oc, roi_inds=orr, counts=kc, n_candidates=c["cand_count"], probs=c["probs"],
+                keep=keep, cand=c)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Q2  (calibration_layer.py:110-123)
+# ---------------------------------------------------------------------------------------------------
+def pcb_cosine_blend_(scores, feats, prototypes, classes, exclude_mask, alpha, lower, upper):
+    """In-place PCB score calibration; scores (n) sorted descending, feats (n,D), prototypes (K,D),
+    classes (n) int64, exclude_mask (K) uint8 or None."""
+    _require_cuda(scores, feats, prototypes, classes)
+    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    feats, prototypes = feats.float().contiguous(), prototypes.float().contiguous()
+    classes = classes.to(torch.int64).contiguous()
+    n, D = feats.shape
+    K = prototypes.shape[0]
+    _lib.call("b200_pcb_cosine_blend", scores.data_ptr(), feats.data_ptr(), prototypes.data_ptr(), classes.data_ptr(),
+              _ptr(exclude_mask), n, D, K, float(alpha), float(lower), float(upper), _stream())
+    return scores
+
+
+# ---------------------------------------------------------------------------------------------------
+# text fusion chain (attentive_modules.py:114-177,262-294; fast_rcnn.py:403-417,462-476)
+# ---------------------------------------------------------------------------------------------------
+def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, out2=None):
+    """out[M,N] = act(a[M,K] @ b[N,K]^T + bias).  a, b bf16 with unit inner stride (row stride free)."""
+    _require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    _lib.call("b200_gemm_bf16", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
+              out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu), _stream())
+    return out
+
+
+def text_attention(q, x, kp, vp, p1, p2):
+    """softmax(q Kp^T / sqrt(d)) Vp and the gate operands P1 = O*x, P2 = x-O (bf16, written into p1/p2)."""
+    R, d = q.shape
+    L = kp.shape[0]
+    attn = torch.empty((R, L), dtype=torch.float32, device=q.device)
+    assert p1.stride(0) == p2.stride(0) and p1.stride(1) == 1
+    _lib.call("b200_text_attention", q.data_ptr(), x.data_ptr(), _dt(x), kp.data_ptr(), vp.data_ptr(), attn.data_ptr(),
+              p1.data_ptr(), p2.data_ptr(), p1.stride(0), R, d, L, _stream())
+    return attn
+
+
+def residual_layernorm(y, y2, gamma, beta, eps=1e-5, relu=False, want_f32=True, want_bf16=True):
+    R, d = y.shape
+    of = torch.empty((R, d), dtype=torch.float32, device=y.device) if want_f32 else None
+    ob = torch.empty((R, d), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    _lib.call("b200_residual_layernorm", y.data_ptr(), _ptr(y2), gamma.data_ptr(), beta.data_ptr(), float(eps), int(relu),
+              _ptr(of), _ptr(ob), R, d, _stream())
+    return of, ob
+
+
+def cast_bf16_into(src, dst):
+    """fp32 (rows, cols) -> bf16 view `dst` (rows, cols) with arbitrary row stride."""
+    rows, cols = src.shape
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.stride(1) == 1 and dst.stride(1) == 1
+    _lib.call("b200_cast_bf16", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream())
+    return dst
+
+
+class TextFusionWeights:
+    """bf16 copies of the attention / predictor weights laid out for the GEMM kernel, plus the projected text
+    keys/values.  Rebuilt whenever the parameters' versions change (constant at inference — the reference
+    recomputes the text-side projections every forward, attentive_modules.py:274-277)."""
+
+    def __init__(self):
+        self.key = None
+        self.w = {}
+
+    @staticmethod
+    def _version(params):
+        return tuple((p.data_ptr(), p._version) for p in params)
+
+    def refresh(self, named, text_feat):
+        params = [named[k] for k in sorted(named)] + [text_feat]
+        key = self._version(params)
+        if key == self.key:
+            return self.w
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        w = {}
+        for name in ("w_q.weight", "linear1.0.weight", "linear2.0.weight", "linear3.weight", "ffn.linear1.weight",
+                     "ffn.linear2.weight"):
+            w[name] = bf(named["attention." + name])
+        for name in ("linear1.0.bias", "linear2.0.bias", "linear3.bias", "ffn.linear1.bias", "ffn.linear2.bias",
+                     "ffn.norm3.weight", "ffn.norm3.bias"):
+            w[name] = f32(named["attention." + name])
+        # text side: tiny (K+1 rows); plain torch ops, cached
+        T = text_feat.detach().float()
+        kt = torch.relu(torch.nn.functional.linear(T, named["key_projection.weight"].detach().float(), named["key_projection.bias"].detach().float()))
+        vt = torch.relu(torch.nn.functional.linear(T, named["value_projection.weight"].detach().float(), named["value_projection.bias"].detach().float()))
+        kp = torch.nn.functional.linear(kt, named["attention.w_k.weight"].detach().float())
+        vp = torch.nn.functional.linear(vt, named["attention.w_v.weight"].detach().float())
+        w["kp"] = torch.cat([kp, named["attention.dummy"].detach().float().reshape(1, -1)], 0).contiguous()
+        w["vp"] = torch.cat([vp, torch.zeros(1, vp.shape[1], device=vp.device)], 0).contiguous()
+        for k in named:
+            if k.startswith("extra."):
+                t = named[k]
+                w[k] = bf(t) if (t.dim() == 2) else f32(t)
+        self.key, self.w = key, w
+        return w
+
+
+def text_fusion_forward(x, w):
+    """A1..A6 on the device.  x (R,d) fp32.  Returns (sim2stext fp32 (R,d), sim2stext bf16, attn (R,K+2),
+    x_bf16 view (R,d) with row stride 2d)."""
+    _require_cuda(x)
+    x = x.float().contiguous()
+    R, d = x.shape
+    dev = x.device
+    h = d // 2
+    xcat = torch.empty((R, 2 * d), dtype=torch.bfloat16, device=dev)      # [o1 | o2 | x]  (attentive_modules.py:172-174)
+    xb = cast_bf16_into(x, xcat[:, d:])
+    q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)
+    p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+    p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+    attn = text_attention(q, x, w["kp"], w["vp"], p1, p2)
+    gemm_bf16(p1, w["linear1.0.weight"], w["linear1.0.bias"], relu=True, out=xcat[:, :h])
+    gemm_bf16(p2, w["linear2.0.weight"], w["linear2.0.bias"], relu=True, out=xcat[:, h:d])
+    yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+    y = gemm_bf16(xcat, w["linear3.weight"], w["linear3.bias"], out2=yb)
+    hdn = gemm_bf16(yb, w["ffn.linear1.weight"], w["ffn.linear1.bias"], relu=True, out_dtype=torch.bfloat16)
+    y2 = gemm_bf16(hdn, w["ffn.linear2.weight"], w["ffn.linear2.bias"])
+    z, zb = residual_layernorm(y, y2, w["ffn.norm3.weight"], w["ffn.norm3.bias"], 1e-5, relu=True)
+    return z, zb, attn, xb

@@ -1,0 +1,167 @@
+/*
+ * b200roi.h — C ABI of the B200-native (sm_100a) ROI-head hot path.
+ *
+ * Drop-in boundary for the DeFRCN text-fused ROI head of
+ * hoangpnhat/FewShotObjectDetection_imporove_via_text_feature.  The reference is pure Python and binds
+ * no native code of its own; each entry point below replaces the third-party / ATen call the reference
+ * makes at the cited file:line (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; no allocation happens inside the library:
+ *     the caller passes outputs and (where needed) a workspace sized by the matching *_workspace_bytes();
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream, and
+ *     keeps no global state;
+ *   - return value: B200_OK or a negative B200_ERR_*; never throws.  b200_last_error() returns a
+ *     thread-local description of the last failure on the calling thread;
+ *   - dtype: B200_F32 | B200_BF16 (storage type of the feature maps / activations; accumulation is fp32);
+ *   - layout: B200_NCHW (torch contiguous) | B200_NHWC (torch channels_last) for 4-d tensors.
+ */
+#ifndef B200ROI_H_
+#define B200ROI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+enum { B200_OK = 0, B200_ERR_INVALID = -1, B200_ERR_CUDA = -2, B200_ERR_WORKSPACE = -3, B200_ERR_UNSUPPORTED = -4 };
+enum { B200_F32 = 0, B200_BF16 = 1 };
+enum { B200_NCHW = 0, B200_NHWC = 1 };
+
+B200_API int b200_abi_version(void);
+B200_API const char* b200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * G1 + G2  Gradient Decoupled Layer + AffineLayer
+ *   replaces defrcn/modeling/meta_arch/gdl.py:6-38 as called at defrcn/modeling/meta_arch/rcnn.py:94-97
+ *   fwd:  y = x * weight[c] + bias[c]           (GDL is the identity in forward)
+ *   bwd:  grad_x = grad_y * weight[c] * lambda  (GDL scales by lambda: cfg.MODEL.ROI_HEADS.BACKWARD_SCALE)
+ *         grad_w[c] = sum_{n,h,w} grad_y * x ;  grad_b[c] = sum_{n,h,w} grad_y   (deterministic two-pass)
+ *   x / grad_x use (in_dtype, in_layout); y / grad_y use (out_dtype, out_layout).  weight==NULL means
+ *   identity scale (pure layout / dtype conversion), bias may be NULL.
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_gdl_affine_fwd(const void* x, const float* weight, const float* bias, void* y, int N, int C, int H,
+                        int W, int in_dtype, int in_layout, int out_dtype, int out_layout, b200_stream_t stream);
+B200_API size_t b200_gdl_affine_bwd_workspace_bytes(int N, int C, int H, int W);
+B200_API int b200_gdl_affine_bwd(const void* grad_y, const void* x, const float* weight, float lambda, void* grad_x,
+                        float* grad_w, float* grad_b, int N, int C, int H, int W, int in_dtype, int in_layout,
+                        int out_dtype, int out_layout, void* workspace, size_t workspace_bytes,
+                        b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * P1 / P1b / Q1  ROIAlign (detectron2 ROIPooler "ROIAlignV2" -> torchvision.ops.roi_align)
+ *   replaces the call at defrcn/modeling/roi_heads/roi_heads.py:300-305,339-340 and
+ *   defrcn/evaluation/calibration_layer.py:27,100.
+ *   feat (N,C,H,W) in (dtype,in_layout); rois (R,5) fp32 [batch_idx,x1,y1,x2,y2] in image coordinates;
+ *   out (R,C,PH,PW) in (dtype,out_layout).  sampling_ratio<=0 is the adaptive ceil(roi/pooled) grid.
+ *   The workspace holds an NHWC copy of the map when in_layout==NCHW (0 bytes otherwise).
+ *   bwd is atomic-free and deterministic: grad_feat is fully overwritten (no pre-zeroing needed).
+ * ------------------------------------------------------------------------------------------------- */
+B200_API size_t b200_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int dtype, int in_layout);
+B200_API int b200_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R,
+                       int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                       int dtype, int in_layout, int out_layout, void* workspace, size_t workspace_bytes,
+                       b200_stream_t stream);
+B200_API size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
+                                          int dtype, int grad_in_layout, int grad_out_layout);
+B200_API int b200_roi_align_bwd(const void* grad_out, const float* rois, const int32_t* roi_batch_offsets,
+                       void* grad_feat, int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
+                       float spatial_scale, int sampling_ratio, int aligned, int dtype, int grad_out_layout,
+                       int grad_in_layout, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * D1 + D2 + D3 (front)  softmax, Box2BoxTransform.apply_deltas, Boxes.clip, score threshold, ordered
+ * compaction.  Replaces defrcn/modeling/roi_heads/fast_rcnn.py:306-334 and :104-122.
+ *   scores_in (R,K+1): logits (input_is_prob=0, softmax applied) or probabilities (input_is_prob=1);
+ *   deltas (R,4K) or (R,4) when cls_agnostic; proposals (R,4); roi_offsets (N+1) int32 prefix of the
+ *   per-image ROI counts (device); image_hw (N,2) fp32 (h,w) (device).
+ *   probs_out (R,K+1) may be NULL.  Candidates of image i are written, in torch.nonzero() order
+ *   (roi-major, class-minor), at [roi_offsets[i]*K, roi_offsets[i]*K + cand_count[i]) of
+ *   cand_boxes (R*K,4) / cand_scores / cand_roi (index within the image) / cand_cls.
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_softmax_decode_compact(const float* scores_in, int input_is_prob, const float* deltas,
+                                const float* proposals, const int32_t* roi_offsets, const float* image_hw,
+                                int N, int R, int K, int cls_agnostic, float wx, float wy, float ww, float wh,
+                                float score_thresh, float* probs_out, float* cand_boxes, float* cand_scores,
+                                int32_t* cand_roi, int32_t* cand_cls, int32_t* cand_count,
+                                b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * D3 (back)  per-class NMS == detectron2.layers.batched_nms (torchvision coordinate-offset trick) followed
+ * by keep[:topk].  Replaces defrcn/modeling/roi_heads/fast_rcnn.py:125-128.
+ *   Segment i (one image) holds seg_count[i] boxes starting at seg_offsets[i] (device arrays; offsets are
+ *   the capacities' prefix so segments may be sparse).  keep (N,max_keep) receives indices relative to the
+ *   segment start, ordered by descending score (ties: ascending index); keep_count (N).
+ *   Bit-exact against the reference path for segments below 40000 boxes (above that detectron2 0.3
+ *   switches to an un-offset per-class loop, which this kernel follows as well).
+ * ------------------------------------------------------------------------------------------------- */
+B200_API size_t b200_batched_nms_workspace_bytes(int N, int total_capacity, int num_classes);
+B200_API int b200_batched_nms(const float* boxes, const float* scores, const int32_t* classes,
+                     const int32_t* seg_offsets, const int32_t* seg_count, int N, int total_capacity,
+                     int num_classes, float iou_thresh, int max_keep, int32_t* keep, int32_t* keep_count,
+                     void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
+/* gather kept candidates into padded detection tensors: boxes (N,max_keep,4), scores (N,max_keep),
+ * classes / roi_inds (N,max_keep) int64 — fast_rcnn.py:128-134 */
+B200_API int b200_gather_detections(const float* cand_boxes, const float* cand_scores, const int32_t* cand_roi,
+                           const int32_t* cand_cls, const int32_t* seg_offsets, const int32_t* keep,
+                           const int32_t* keep_count, int N, int max_keep, float* out_boxes,
+                           float* out_scores, int64_t* out_classes, int64_t* out_roi_inds,
+                           b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Q2  PCB cosine calibration.  Replaces defrcn/evaluation/calibration_layer.py:110-123 (per-detection
+ * sklearn cosine_similarity on the CPU).  scores (n) sorted descending, updated in place for detections
+ * ileft <= i < iright where ileft = #(score > upper), iright = #(score > lower), unless
+ * exclude[class]!=0:  s = alpha*s + (1-alpha)*cos(feats[i], prototypes[class]).
+ * feats (n,D) holds features for ALL n detections (row i <-> detection i).
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_pcb_cosine_blend(float* scores, const float* feats, const float* prototypes, const int64_t* classes,
+                          const uint8_t* exclude, int n, int D, int K, float alpha, float lower, float upper,
+                          b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A1..A6, C1, C1'  text-fusion chain on tcgen05 tensor cores.
+ * b200_gemm_bf16: D[M,N] = act(A[M,K] * B[N,K]^T + bias[N])   A,B bf16 row-major (K contiguous), fp32
+ *   accumulation in TMEM, TMA-fed 128B-swizzled smem tiles.  Replaces the nn.Linear calls at
+ *   defrcn/modeling/roi_heads/attentive_modules.py:124,166-175,72 and fast_rcnn.py:407,415.
+ *   M,N arbitrary (TMA clips); K % 8 == 0; lda/ldb/ldd in elements, multiples of 8.
+ *   out_dtype B200_F32|B200_BF16; relu: 0/1.  d2/ldd2 (optional, may be NULL): a second bf16 copy of the
+ *   result, used to feed the next GEMM while the fp32 copy is returned to the caller.
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
+                   int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, b200_stream_t stream);
+
+/* A3 + A4 prologue: S = Q Kp^T / sqrt(d), softmax over the K+2 keys, O = attn Vp, then the two gate
+ * operands P1 = O*x and P2 = x - O written as bf16 (attentive_modules.py:45-55,166,170).
+ *   q (R,d) bf16; x (R,d) fp32 or bf16 (x_dtype); kp,vp (L,d) fp32 (L = K+2, dummy key last, its value 0);
+ *   attn_out (R,L) fp32; p1,p2 (R, ldp) bf16. */
+B200_API int b200_text_attention(const void* q, const void* x, int x_dtype, const float* kp, const float* vp,
+                        float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L,
+                        b200_stream_t stream);
+
+/* A5 tail + A6: out = relu?(LayerNorm(y + y2) * gamma + beta); out_f32 and/or out_bf16 may be NULL
+ * (attentive_modules.py:73-74,285). */
+B200_API int b200_residual_layernorm(const float* y, const float* y2, const float* gamma, const float* beta, float eps,
+                            int relu, float* out_f32, void* out_bf16, int R, int d, b200_stream_t stream);
+
+/* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
+ * in place, without a torch.cat) */
+B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,
+                   b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ROI_H_ */

@@ -1,0 +1,146 @@
+"""Decode / threshold compaction / per-class NMS kernels vs the oracle and the reference golden vectors.
+Bar (north_star): NMS keep indices and compaction counts bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from oracle.gen_golden import synth_proposals
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _run(logits_or_probs, deltas, props, hw, is_prob, topk=100):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    R = logits_or_probs.shape[0]
+    offs = torch.tensor([0, R], dtype=torch.int32, device="cuda")
+    ihw = torch.tensor([[float(hw[0]), float(hw[1])]], device="cuda")
+    return ops.fast_rcnn_inference_device(logits_or_probs.cuda(), deltas.cuda(), props.cuda(), offs, ihw, 0.05, 0.5, topk,
+                                          input_is_prob=is_prob, want_probs=True)
+
+
+@pytest.mark.parametrize("tag", ["voc", "coco", "ties", "empty"])
+def test_golden_fused_path(golden, tag):
+    g = golden("fast_rcnn_inference")
+    hw = g[tag + "_hw"]
+    # (1) probabilities in: the candidate list must be exactly the reference's nonzero() list
+    out = _run(T(g[tag + "_probs"]), T(g[tag + "_deltas"]), T(g[tag + "_props"]), hw, True)
+    n = int(out["n_candidates"][0])
+    assert n == int(g[tag + "_ncand"])
+    ref_idx = (T(g[tag + "_probs"])[:, :-1] > 0.05).nonzero()
+    c = out["cand"]
+    assert torch.equal(c["cand_roi"][:n].cpu().long(), ref_idx[:, 0])
+    assert torch.equal(c["cand_cls"][:n].cpu().long(), ref_idx[:, 1])
+    assert torch.equal(c["cand_scores"][:n].cpu(), T(g[tag + "_probs"])[:, :-1][T(g[tag + "_probs"])[:, :-1] > 0.05])
+    # decoded + clipped candidate boxes vs the reference's Box2BoxTransform (expf ulp differences allowed)
+    refb = T(g[tag + "_pred_boxes_all"]).reshape(len(g[tag + "_props"]), -1, 4).clone()
+    refb[..., 0::2] = refb[..., 0::2].clamp(0, float(hw[1]))
+    refb[..., 1::2] = refb[..., 1::2].clamp(0, float(hw[0]))
+    if n:
+        torch.testing.assert_close(c["cand_boxes"][:n].cpu(), refb[ref_idx[:, 0], ref_idx[:, 1]], rtol=1e-5, atol=2e-3)
+    # (2) NMS is bit-exact on the kernel's own candidates
+    keep_ref = O.batched_nms(c["cand_boxes"][:n].cpu(), c["cand_scores"][:n].cpu(), c["cand_cls"][:n].cpu().long(), 0.5)[:100]
+    k = int(out["counts"][0])
+    assert k == len(keep_ref)
+    assert torch.equal(out["keep"][0, :k].cpu().long(), keep_ref)
+    # (3) and the final detections equal the reference's (same classes / rois; scores exact; boxes to ulp)
+    assert k == len(g[tag + "_scores"])
+    assert torch.equal(out["classes"][0, :k].cpu(), T(g[tag + "_classes"]))
+    assert torch.equal(out["roi_inds"][0, :k].cpu(), T(g[tag + "_roi_inds"]))
+    assert torch.equal(out["scores"][0, :k].cpu(), T(g[tag + "_scores"]))
+    if k:
+        torch.testing.assert_close(out["boxes"][0, :k].cpu(), T(g[tag + "_boxes"]), rtol=1e-5, atol=2e-3)
+    # (4) logits in: softmax within 1e-6 of torch's
+    out2 = _run(T(g[tag + "_logits"]), T(g[tag + "_deltas"]), T(g[tag + "_props"]), hw, False)
+    torch.testing.assert_close(out2["probs"].cpu(), T(g[tag + "_probs"]), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["voc", "coco", "ties", "empty"])
+def test_golden_single_image_entry(golden, tag):
+    """Reference-signature entry on the reference's own decoded boxes / probabilities: bit-exact everything."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling import roi_heads as RH
+    g = golden("fast_rcnn_inference")
+    res, roi = RH.fast_rcnn_inference_single_image(T(g[tag + "_pred_boxes_all"]).cuda(), T(g[tag + "_probs"]).cuda(),
+                                                   tuple(int(v) for v in g[tag + "_hw"]), 0.05, 0.5, 100)
+    assert torch.equal(res.pred_classes.cpu(), T(g[tag + "_classes"]))
+    assert torch.equal(roi.cpu(), T(g[tag + "_roi_inds"]))
+    assert torch.equal(res.scores.cpu(), T(g[tag + "_scores"]))
+    assert torch.equal(res.pred_boxes.tensor.cpu(), T(g[tag + "_boxes"]))
+
+
+@pytest.mark.parametrize("n,ncls,seed", [(1, 1, 0), (2, 1, 1), (257, 5, 2), (3000, 20, 3), (9000, 80, 4), (6000, 1, 5)])
+def test_batched_nms_vs_oracle(n, ncls, seed):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(seed)
+    boxes, _ = synth_proposals(max(n, 8), 600, 800, gen, n_obj=6)
+    boxes = boxes[:n].contiguous()
+    scores = torch.rand(n, generator=gen)
+    if n > 40:
+        scores[5:25] = scores[0]                 # ties -> ascending-index order
+        boxes[30:40] = boxes[20:30]              # identical boxes
+    idxs = torch.randint(0, ncls, (n,), generator=gen)
+    ref = O.batched_nms(boxes, scores, idxs, 0.5)
+    keep = ops.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.5)
+    assert torch.equal(keep.cpu(), ref)
+
+
+def test_batched_nms_empty_and_multi_segment():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    assert ops.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), 0.5).numel() == 0
+    gen = torch.Generator().manual_seed(3)
+    segs, refs = [], []
+    caps = [700, 0, 1300, 64]
+    for n in caps:
+        b, _ = synth_proposals(max(n, 8), 480, 640, gen)
+        b = b[:n]
+        s, c = torch.rand(n, generator=gen), torch.randint(0, 20, (n,), generator=gen)
+        segs.append((b, s, c))
+        refs.append(O.batched_nms(b, s, c, 0.5)[:100])
+    pad = 50                                       # sparse segments: capacity > count
+    offs, boxes, scores, cls = [0], [], [], []
+    for b, s, c in segs:
+        boxes += [b, torch.zeros(pad, 4)]
+        scores += [s, torch.zeros(pad)]
+        cls += [c, torch.zeros(pad, dtype=torch.int64)]
+        offs.append(offs[-1] + len(b) + pad)
+    keep, kc = ops.batched_nms_segments(torch.cat(boxes).cuda(), torch.cat(scores).cuda(), torch.cat(cls).to(torch.int32).cuda(),
+                                        torch.tensor(offs[:-1], dtype=torch.int32).cuda(),
+                                        torch.tensor(caps, dtype=torch.int32).cuda(), 20, 0.5, 100)
+    for i, r in enumerate(refs):
+        assert int(kc[i]) == len(r)
+        assert torch.equal(keep[i, :len(r)].cpu().long(), r)
+
+
+def test_multi_image_full_size():
+    """BASELINE shape: 4 images x 512 proposals, K=20.  Per-image results equal the single-image oracle on the
+    kernel's own probabilities/candidates; idempotence: NMS of the kept set keeps everything."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    N, R, K = 4, 512, 20
+    props = torch.cat([synth_proposals(R, 600, 800, gen)[0] for _ in range(N)])
+    logits = torch.randn(N * R, K + 1, generator=gen)
+    logits[:, K] += 3.0
+    pk = torch.randint(0, N * R, (N * R // 3,), generator=gen)
+    logits[pk, torch.randint(0, K, (len(pk),), generator=gen)] += 7.0
+    deltas = torch.randn(N * R, 4 * K, generator=gen) * 0.5
+    offs = torch.arange(0, N + 1, dtype=torch.int32) * R
+    hw = torch.tensor([[600.0, 800.0]] * N)
+    out = ops.fast_rcnn_inference_device(logits.cuda(), deltas.cuda(), props.cuda(), offs.cuda(), hw.cuda(), 0.05, 0.5, 100,
+                                         want_probs=True)
+    probs = out["probs"].cpu()
+    c = out["cand"]
+    for i in range(N):
+        n = int(out["n_candidates"][i])
+        assert n == int((probs[i * R:(i + 1) * R, :K] > 0.05).sum())
+        s0 = i * R * K
+        cb, cs, cc = c["cand_boxes"][s0:s0 + n].cpu(), c["cand_scores"][s0:s0 + n].cpu(), c["cand_cls"][s0:s0 + n].cpu().long()
+        ref = O.batched_nms(cb, cs, cc, 0.5)[:100]
+        k = int(out["counts"][i])
+        assert k == len(ref) and torch.equal(out["keep"][i, :k].cpu().long(), ref)
+        assert bool((out["scores"][i, :k - 1] >= out["scores"][i, 1:k]).all())          # sorted
+        again = ops.batched_nms(out["boxes"][i, :k], out["scores"][i, :k], out["classes"][i, :k], 0.5)
+        assert torch.equal(again.cpu(), torch.arange(k))                                 # idempotent

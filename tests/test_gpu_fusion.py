@@ -1,0 +1,132 @@
+"""Text-fusion chain kernels (tcgen05 GEMM, attention core, LayerNorm) vs fp32 torch / the oracle.
+Tolerance: GEMM against fp32 math on the same bf16-rounded operands 1e-3 (accumulation order only);
+whole chain against the fp32 oracle 2e-2 relative (north_star bf16 bar)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 2048), (300, 21, 2048), (129, 80, 2048), (1000, 2048, 4096),
+                                   (128, 64, 72), (1, 32, 64), (77, 1024, 16), (640, 512, 2048), (4096, 2048, 1024)])
+@pytest.mark.parametrize("relu,use_bias", [(False, True), (True, False)])
+def test_gemm_bf16(M, N, K, relu, use_bias):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=gen) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K, generator=gen) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=gen) if use_bias else None
+    ref = a.double() @ b.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    out = ops.gemm_bf16(a.cuda(), b.cuda(), None if bias is None else bias.cuda(), relu=relu)
+    assert out.dtype == torch.float32 and out.shape == (M, N)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-3, atol=1e-3)
+    outb = ops.gemm_bf16(a.cuda(), b.cuda(), None if bias is None else bias.cuda(), relu=relu, out_dtype=torch.bfloat16)
+    torch.testing.assert_close(outb.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_strided_and_second_output():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    M, N, K = 200, 1024, 2048
+    big = (torch.randn(M, 2 * K, generator=gen) * 0.5).to(torch.bfloat16).cuda()
+    a = big[:, K:]                                        # row stride 2K, like the concat buffer
+    b = (torch.randn(N, K, generator=gen) * 0.05).to(torch.bfloat16).cuda()
+    dst = torch.zeros(M, 4 * N, dtype=torch.bfloat16, device="cuda")
+    d2 = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm_bf16(a, b, out=dst[:, N:2 * N])
+    ref = (a.double() @ b.double().t()).cpu()
+    torch.testing.assert_close(dst[:, N:2 * N].cpu().double(), ref, rtol=1e-2, atol=1e-2)
+    assert float(dst[:, :N].abs().max()) == 0 and float(dst[:, 2 * N:].abs().max()) == 0   # no stray writes
+    f32 = ops.gemm_bf16(a, b, out2=d2)
+    torch.testing.assert_close(f32.cpu().double(), ref, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(d2.float(), f32.to(torch.bfloat16).float(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("R,d,L", [(512, 2048, 22), (37, 2048, 82), (600, 64, 7), (1500, 2048, 22)])
+def test_text_attention(R, d, L):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(R)
+    q = (torch.randn(R, d, generator=gen)).to(torch.bfloat16)
+    x = torch.relu(torch.randn(R, d, generator=gen))
+    kp, vp = torch.randn(L, d, generator=gen), torch.randn(L, d, generator=gen)
+    vp[-1] = 0
+    s = (q.float() @ kp.t()) / np.sqrt(d)
+    attn = F.softmax(s, dim=1)
+    o = attn @ vp
+    p1 = torch.empty(R, d, dtype=torch.bfloat16, device="cuda")
+    p2 = torch.empty(R, d, dtype=torch.bfloat16, device="cuda")
+    got = ops.text_attention(q.cuda(), x.cuda(), kp.cuda(), vp.cuda(), p1, p2)
+    torch.testing.assert_close(got.cpu(), attn, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(p1.float().cpu(), o * x, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(p2.float().cpu(), x - o, rtol=1e-2, atol=1e-2)
+
+
+def test_residual_layernorm():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    R, d = 333, 2048
+    y, y2 = torch.randn(R, d, generator=gen), torch.randn(R, d, generator=gen) * 3
+    g, b = torch.randn(d, generator=gen), torch.randn(d, generator=gen)
+    ref = F.relu(F.layer_norm(y + y2, (d,), g, b, 1e-5))
+    f, h = ops.residual_layernorm(y.cuda(), y2.cuda(), g.cuda(), b.cuda(), 1e-5, relu=True)
+    torch.testing.assert_close(f.cpu(), ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(h.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+def _build_attention(K, d, seed=0):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.attentive_modules import SematicProposalAttention
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
+    cfg.MODEL.ADDITION.NAME = "clip"
+    torch.manual_seed(seed)
+    m = SematicProposalAttention(d, cfg=cfg, bg_generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():   # reference init (std 0.02) gives near-uniform attention; sharpen it so the test bites
+        m.attention.w_q.weight.mul_(6.0)
+        m.attention.w_k.weight.mul_(6.0)
+        m.key_projection.weight.mul_(3.0)
+    return m.eval()
+
+
+@pytest.mark.parametrize("R,K", [(512, 20), (200, 80)])
+def test_chain_vs_oracle(R, K):
+    d = 2048
+    m = _build_attention(K, d)
+    x = torch.relu(torch.randn(R, d, generator=torch.Generator().manual_seed(2)))
+    p = {"attention." + k: v.detach() for k, v in m.state_dict().items()}
+    text = torch.cat([m.embed, m.bg_feature], 0)
+    sim_ref, attn_ref = O.sematic_proposal_attention(x, text, p)
+    m = m.cuda()
+    with torch.no_grad():
+        attn, out = m(x.cuda())
+    assert attn.shape == (1, R, K + 2)
+    torch.testing.assert_close(attn[0].sum(1).cpu(), torch.ones(R), rtol=1e-4, atol=1e-4)
+    assert rel_err(attn[0].cpu(), attn_ref) < 2e-2
+    assert rel_err(out["sim2stext"].cpu(), sim_ref) < 2e-2
+    assert float((out["sim2stext"].cpu() - sim_ref).abs().max()) < 2e-2 * float(sim_ref.abs().max()) * 4
+
+
+def test_chain_golden_small(golden):
+    """d_model = 32 golden produced by the reference's own SematicProposalAttention."""
+    g = golden("attention_small")
+    m = _build_attention(20, 32)
+    sd = {k[len("attention."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("attention.")}
+    m.load_state_dict(sd)
+    m.embed, m.bg_feature = torch.from_numpy(g["embed"]), torch.from_numpy(g["bg_feature"])
+    m = m.cuda()
+    with torch.no_grad():
+        attn, out = m(torch.from_numpy(g["x"]).cuda())
+    assert rel_err(attn[0].cpu(), torch.from_numpy(g["attn"])) < 2e-2
+    assert rel_err(out["sim2stext"].cpu(), torch.from_numpy(g["sim2stext"])) < 2e-2

@@ -1,0 +1,118 @@
+"""ROIAlign CUDA kernels (through the C-ABI) vs the CPU oracle.  Tolerance: 1e-5 abs+rel in fp32 (north_star),
+2e-2 relative in bf16."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+from oracle.gen_golden import synth_proposals
+
+
+def _inputs(N, C, H, W, R, scale, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.relu(torch.randn(N, C, H, W, generator=gen))
+    boxes = [synth_proposals(R // N + (1 if n < R % N else 0), int(H / scale), int(W / scale), gen)[0] for n in range(N)]
+    rois = O.boxes_to_rois(boxes)
+    if R >= 3:  # edge cases: hanging outside the map, zero-size, larger than the map
+        rois[0, 1:] = torch.tensor([-40.0, -30.0, 20.0, 25.0])
+        rois[1, 1:] = torch.tensor([10.0, 10.0, 10.0, 10.0])
+        rois[2, 1:] = torch.tensor([0.0, 0.0, W / scale + 50, H / scale + 50])
+    offs = torch.tensor([0] + list(torch.tensor([len(b) for b in boxes]).cumsum(0).tolist()), dtype=torch.int32)
+    return x, rois, offs
+
+
+@pytest.mark.parametrize("N,C,H,W,R,P,scale,sr,aligned", [
+    (2, 32, 38, 50, 96, 7, 1 / 16, 0, True),
+    (1, 64, 19, 25, 40, 1, 1 / 32, 0, True),       # PCB pooling
+    (1, 16, 20, 20, 24, 7, 1 / 16, 2, True),
+    (1, 16, 20, 20, 24, 7, 1 / 16, 0, False),
+    (3, 132, 13, 17, 45, 14, 1 / 8, 0, True),       # channel count not a multiple of the chunk
+])
+@pytest.mark.parametrize("cl_in,cl_out", [(False, False), (True, True), (False, True), (True, False)])
+def test_fwd_fp32(N, C, H, W, R, P, scale, sr, aligned, cl_in, cl_out):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    x, rois, _ = _inputs(N, C, H, W, R, scale, 7)
+    ref = O.roi_align_fwd(x, rois, P, scale, sr, aligned, impl="c")
+    xd = x.cuda()
+    if cl_in:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    out = ops.roi_align(xd, rois.cuda(), P, scale, sr, aligned, channels_last_out=cl_out)
+    assert out.shape == ref.shape
+    assert out.is_contiguous(memory_format=torch.channels_last if cl_out else torch.contiguous_format)
+    torch.testing.assert_close(out.cpu().contiguous(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_fwd_bf16():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    x, rois, _ = _inputs(2, 64, 38, 50, 80, 1 / 16, 3)
+    xb = x.to(torch.bfloat16)
+    ref = O.roi_align_fwd(xb.float(), rois, 7, 1 / 16, 0, True)
+    for cl in (False, True):
+        xd = xb.cuda().contiguous(memory_format=torch.channels_last) if cl else xb.cuda()
+        out = ops.roi_align(xd, rois.cuda(), 7, 1 / 16, 0, True, channels_last_out=cl)
+        assert out.dtype == torch.bfloat16
+        torch.testing.assert_close(out.float().cpu().contiguous(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_bwd_fp32(cl):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    N, C, H, W, R, scale = 2, 32, 24, 31, 70, 1 / 16
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 11)
+    g = torch.randn(R, C, 7, 7, generator=torch.Generator().manual_seed(1))
+    ref = O.roi_align_bwd(g, rois, x.shape, scale, 0, True)
+    xd = x.cuda()
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd.requires_grad_(True)
+    out = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=cl, roi_batch_offsets=offs.cuda())
+    out.backward(g.cuda())
+    torch.testing.assert_close(xd.grad.cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
+    # atomic-free: bitwise reproducible
+    xd.grad = None
+    out2 = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=cl, roi_batch_offsets=offs.cuda())
+    out2.backward(g.cuda())
+    g1 = xd.grad.clone()
+    xd.grad = None
+    out3 = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=cl, roi_batch_offsets=offs.cuda())
+    out3.backward(g.cuda())
+    assert torch.equal(g1, xd.grad)
+
+
+def test_full_size_properties():
+    """BASELINE size (R=512, C=1024, 38x50): size-independent properties instead of a slow CPU pass."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    N, C, H, W, R = 1, 1024, 38, 50, 512
+    x, rois, offs = _inputs(N, C, H, W, R, 1 / 16, 5)
+    y = torch.relu(torch.randn(N, C, H, W, generator=torch.Generator().manual_seed(9)))
+    xd, yd, rd = x.cuda(), y.cuda(), rois.cuda()
+    a = ops.roi_align(xd, rd, 7, 1 / 16)
+    b = ops.roi_align(yd, rd, 7, 1 / 16)
+    ab = ops.roi_align(2.0 * xd - 0.5 * yd, rd, 7, 1 / 16)
+    torch.testing.assert_close(ab, 2.0 * a - 0.5 * b, rtol=1e-4, atol=1e-4)           # linearity
+    cl = ops.roi_align(xd.contiguous(memory_format=torch.channels_last), rd, 7, 1 / 16, channels_last_out=True)
+    assert torch.equal(cl.contiguous(), a)                                              # layout independence, bitwise
+    const = ops.roi_align(torch.full_like(xd, 3.0), rd[3:], 7, 1 / 16)                  # in-image boxes of a constant map
+    torch.testing.assert_close(const, torch.full_like(const, 3.0), rtol=1e-5, atol=1e-5)
+    # a CPU spot check on a channel slice
+    ref = O.roi_align_fwd(x[:, :8], rois[:64], 7, 1 / 16, 0, True)
+    torch.testing.assert_close(a[:64, :8].cpu(), ref, rtol=1e-5, atol=1e-5)
+    # adjointness <roi_align(x), g> == <x, roi_align_bwd(g)>
+    g = torch.randn_like(a)
+    xg = xd.clone().requires_grad_(True)
+    out = ops.roi_align(xg, rd, 7, 1 / 16, roi_batch_offsets=offs.cuda())
+    out.backward(g)
+    lhs, rhs = (out.detach().double() * g.double()).sum(), (xd.double() * xg.grad.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-4 * abs(float(lhs))
+
+
+def test_empty_and_errors():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+    x = torch.zeros(1, 8, 5, 5, device="cuda")
+    out = ops.roi_align(x, torch.zeros(0, 5, device="cuda"), 7, 1 / 16)
+    assert out.shape == (0, 8, 7, 7)
+    with pytest.raises(_lib.B200Error):
+        ops.roi_align(torch.zeros(1, 6, 5, 5, device="cuda"), torch.zeros(1, 5, device="cuda"), 7, 1 / 16)  # C % 4
+    with pytest.raises(_lib.B200Error):
+        ops.roi_align(torch.zeros(1, 8, 5, 5), torch.zeros(1, 5), 7, 1 / 16)                                 # CPU tensor
