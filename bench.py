@@ -226,6 +226,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         l0 = _lib.LAUNCHES
+        ops.KERNEL_EVENTS["roi_align_fwd"] = []
         for i in range(args.steps):
             flush.fill_(i & 0xff)
             out = step(feat_d, boxes_d, evs[i])
@@ -235,6 +236,10 @@ def main():
             bdist.all_gather_detections(out["counts"], dets, B * world)
         torch.cuda.synchronize()
         launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
+        roi_ms = float(np.mean([a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["roi_align_fwd"]]))
+        ops.KERNEL_EVENTS.clear()
+        n_cand = out["n_candidates"].float().mean().item()
+        n_det = out["counts"].float().mean().item()
         sampler.stop_flag = True
         if world > 1:
             dist.barrier()
@@ -277,7 +282,7 @@ def main():
         R = B * P
         e = 2
         roi_bytes = B * C4 * HF * WF * e + R * 20 + R * C4 * 49 * e
-        roi_gbs = roi_bytes / (stage_ms[1] * 1e-3) / 1e9
+        roi_gbs = roi_bytes / (roi_ms * 1e-3) / 1e9
         flops_fusion = R * (2 * (2048 ** 2 + 2 * 2048 * 1024 + 4096 * 2048 + 2 * 2048 * 1024) + 4 * 2048 * (K + 2) + 2 * 2048 * (5 * K + 1))
         line = {
             "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -292,12 +297,13 @@ def main():
             "roofline": {"kernel": "roi_align_fwd_nhwc_kernel<bf16> (rank 0)", "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": stage_ms[1]},
+                         "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
+                         "timing": "CUDA events recorded around the launch on the launching stream, mean over the timed steps"},
             "stage_ms": dict(zip(stage_names, stage_ms)),
             "kernels_only_images_per_sec": B / ((sum(stage_ms) - stage_ms[2]) * 1e-3),
             "fusion_chain": {"tflops": flops_fusion / (stage_ms[3] * 1e-3) / 1e12, "peak_tflops": peaks.get("bf16_tflops_sustained"),
                              "note": "whole text-fusion stage incl. attention core / LayerNorm / casts, not a single GEMM"},
-            "nms_us_per_image": 1e3 * stage_ms[4] / B,
+            "nms_us_per_image": 1e3 * stage_ms[4] / B, "candidates_per_image": n_cand, "detections_per_image": n_det,
         }
         if not args.no_cpu_baseline:
             try:

@@ -32,7 +32,7 @@ SIGNATURES = {
     "b200_gather_detections": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 4 + [c_void_p]),
     "b200_pcb_cosine_blend": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float] * 3 + [c_void_p]),
     "b200_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int] + [c_int] * 4 + [c_void_p]),
-    "b200_text_attention": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
     "b200_cast_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

@@ -52,31 +52,17 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp /*[3
   return res;
 }
 
-// probabilities of one row, lanes strided over classes; returns this lane's values for classes
-// lane, lane+32, ... in p[] (at most kMaxChunks chunks -> K+1 <= 32*kMaxChunks)
-constexpr int kMaxChunks = 8;
-
-__device__ __forceinline__ void row_probs(const float* __restrict__ row, int ncol, int input_is_prob, int lane,
-                                          float* p) {
+// softmax statistics of one row (sequential over the K+1 columns: a thread owns a row)
+__device__ __forceinline__ void row_stats(const float* __restrict__ row, int ncol, float* mx_out, float* sum_out) {
   float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < kMaxChunks; ++j) {
-    const int k = lane + 32 * j;
-    p[j] = k < ncol ? __ldg(row + k) : -INFINITY;
-    mx = fmaxf(mx, p[j]);
-  }
-  if (input_is_prob) return;
-  mx = warp_max(mx);
+  for (int k = 0; k < ncol; ++k) mx = fmaxf(mx, __ldg(row + k));
   float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < kMaxChunks; ++j) {
-    const int k = lane + 32 * j;
-    p[j] = k < ncol ? expf(p[j] - mx) : 0.f;
-    s += p[j];
-  }
-  s = warp_sum(s);
-#pragma unroll
-  for (int j = 0; j < kMaxChunks; ++j) p[j] = __fdiv_rn(p[j], s);
+  for (int k = 0; k < ncol; ++k) s += expf(__ldg(row + k) - mx);
+  *mx_out = mx; *sum_out = s;
+}
+__device__ __forceinline__ float row_prob(const float* __restrict__ row, int k, int input_is_prob, float mx, float sum) {
+  const float x = __ldg(row + k);
+  return input_is_prob ? x : __fdiv_rn(expf(x - mx), sum);
 }
 
 __device__ __forceinline__ float4 decode_clip(const float* __restrict__ d, float4 pb, float wx, float wy, float ww,
@@ -96,8 +82,10 @@ __device__ __forceinline__ float4 decode_clip(const float* __restrict__ d, float
   return o;
 }
 
-constexpr int kRowTile = 1024;  // rows handled per block iteration (== threads: one scan element each)
+constexpr int kRowTile = 1024;  // rows handled per block iteration: one row per thread
 
+// One CTA per image, one THREAD per ROI row: the per-row work (K+1 <= a few hundred columns) is tiny, so rows are
+// the parallel axis; a block scan of the per-row candidate counts gives the torch.nonzero() order.
 __global__ void __launch_bounds__(1024)
 softmax_decode_compact_kernel(const float* __restrict__ scores_in, int input_is_prob, const float* __restrict__ deltas,
                               const float* __restrict__ proposals, const int32_t* __restrict__ roi_offsets,
@@ -106,67 +94,46 @@ softmax_decode_compact_kernel(const float* __restrict__ scores_in, int input_is_
                               float* __restrict__ cand_boxes, float* __restrict__ cand_scores,
                               int32_t* __restrict__ cand_roi, int32_t* __restrict__ cand_cls,
                               int32_t* __restrict__ cand_count) {
-  __shared__ int s_cnt[kRowTile];
-  __shared__ int s_base[kRowTile];
   __shared__ int s_warp[33];
   const int img = blockIdx.x;
   const int r0 = roi_offsets[img], r1 = roi_offsets[img + 1];
   const float img_h = image_hw[2 * img], img_w = image_hw[2 * img + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncol = K + 1;
   const size_t out0 = (size_t)r0 * K;  // this image's candidate segment
   int running = 0;
 
   for (int t0 = r0; t0 < r1; t0 += kRowTile) {
-    const int nrows = min(kRowTile, r1 - t0);
-    // phase A: probabilities + per-row candidate counts (warp per row)
-    for (int lr = warp; lr < nrows; lr += 32) {
-      const int r = t0 + lr;
-      float p[kMaxChunks];
-      row_probs(scores_in + (size_t)r * ncol, ncol, input_is_prob, lane, p);
-      int cnt = 0;
-#pragma unroll
-      for (int j = 0; j < kMaxChunks; ++j) {
-        const int k = lane + 32 * j;
-        if (probs_out && k < ncol) probs_out[(size_t)r * ncol + k] = p[j];
-        cnt += __popc(__ballot_sync(0xffffffffu, k < K && p[j] > thresh));
+    const int r = t0 + threadIdx.x;
+    const bool live = r < r1;
+    const float* row = scores_in + (size_t)r * ncol;
+    float mx = 0.f, sum = 1.f;
+    int cnt = 0;
+    if (live) {
+      if (!input_is_prob) row_stats(row, ncol, &mx, &sum);
+      for (int k = 0; k < ncol; ++k) {
+        const float p = row_prob(row, k, input_is_prob, mx, sum);
+        if (probs_out) probs_out[(size_t)r * ncol + k] = p;
+        cnt += (k < K && p > thresh);
       }
-      if (lane == 0) s_cnt[lr] = cnt;
     }
-    __syncthreads();
-    // phase B: exclusive scan of the row counts
     int total;
-    const int mine = (int)threadIdx.x < nrows ? s_cnt[threadIdx.x] : 0;
-    const int ex = block_exclusive_scan_1024(mine, s_warp, &total);
-    s_base[threadIdx.x] = running + ex;
-    __syncthreads();
-    // phase C: ordered write, decode fused
-    for (int lr = warp; lr < nrows; lr += 32) {
-      if (s_cnt[lr] == 0) continue;
-      const int r = t0 + lr;
-      float p[kMaxChunks];
-      row_probs(scores_in + (size_t)r * ncol, ncol, input_is_prob, lane, p);
+    const int ex = block_exclusive_scan_1024(cnt, s_warp, &total);
+    if (live && cnt) {
+      size_t o = out0 + running + ex;
       const float4 pb = *reinterpret_cast<const float4*>(proposals + 4 * (size_t)r);
-      int pos = s_base[lr];
-#pragma unroll
-      for (int j = 0; j < kMaxChunks; ++j) {
-        const int k = lane + 32 * j;
-        const bool pass = k < K && p[j] > thresh;
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-          const size_t o = out0 + pos + __popc(m & ((1u << lane) - 1u));
+      for (int k = 0; k < K; ++k) {
+        const float p = row_prob(row, k, input_is_prob, mx, sum);   // same ops, same bits as the counting pass
+        if (p > thresh) {
           const float* d = deltas + (cls_agnostic ? (size_t)r * 4 : ((size_t)r * K + k) * 4);
-          const float4 bx = decode_clip(d, pb, wx, wy, ww, wh, img_h, img_w);
-          *reinterpret_cast<float4*>(cand_boxes + 4 * o) = bx;
-          cand_scores[o] = p[j];
+          *reinterpret_cast<float4*>(cand_boxes + 4 * o) = decode_clip(d, pb, wx, wy, ww, wh, img_h, img_w);
+          cand_scores[o] = p;
           cand_roi[o] = r - r0;
           cand_cls[o] = k;
+          ++o;
         }
-        pos += __popc(m);
       }
     }
     running += total;
-    __syncthreads();
   }
   if (threadIdx.x == 0) cand_count[img] = running;
 }
@@ -297,7 +264,7 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
                  const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
                  const float* __restrict__ max1, const int32_t* __restrict__ class_start,
                  const int32_t* __restrict__ order, unsigned long long* __restrict__ kept,
-                 unsigned long long* __restrict__ scratch) {
+                 unsigned long long* __restrict__ scratch, int max_keep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keep64;
@@ -344,34 +311,57 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   __syncthreads();
   auto get_box = [&](int j) -> float4 { return in_smem ? sbox[j] : load_box(j); };
 
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nkept = 0;
   for (int b0 = 0; b0 < m; b0 += 64) {
     const int nb = min(64, m - b0);
-    // diagonal 64x64 block: row t = boxes later in the block that box t suppresses
-    if ((int)threadIdx.x < 64) {
-      unsigned long long row = 0ull;
-      if ((int)threadIdx.x < nb) {
-        const float4 a = get_box(b0 + threadIdx.x);
-        for (int j = threadIdx.x + 1; j < nb; ++j)
-          if (iou_gt(a, get_box(b0 + j), thr)) row |= 1ull << j;
+    // diagonal 64x64 block, all 8 warps: warp -> row t, lane -> columns (lane, lane+32); ballots assemble the
+    // 64-bit row mask "boxes later in the block that box t suppresses"
+    for (int t = warp; t < 64; t += kNmsThreads / 32) {
+      unsigned m0 = 0u, m1 = 0u;
+      if (t < nb) {
+        const float4 a = get_box(b0 + t);
+        const int j0 = lane, j1 = lane + 32;
+        const bool h0 = j0 > t && j0 < nb && iou_gt(a, get_box(b0 + j0), thr);
+        const bool h1 = j1 > t && j1 < nb && iou_gt(a, get_box(b0 + j1), thr);
+        m0 = __ballot_sync(0xffffffffu, h0);
+        m1 = __ballot_sync(0xffffffffu, h1);
       }
-      s_diag[threadIdx.x] = row;
+      if (lane == 0) s_diag[t] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+      // serial dependency resolved from registers: lane holds rows (lane, lane+32); the row in turn is broadcast
+      const unsigned long long lo = s_diag[lane], hi = s_diag[lane + 32];
       unsigned long long dead = (unsigned long long)removed[b0 >> 5] |
                                 ((b0 + 32 < m) ? ((unsigned long long)removed[(b0 >> 5) + 1] << 32) : 0ull);
       unsigned long long keep = 0ull;
-      for (int t = 0; t < nb; ++t)
-        if (!((dead >> t) & 1ull)) { keep |= 1ull << t; dead |= s_diag[t]; }
-      s_keep64 = keep;
+      for (int t = 0; t < nb; ++t) {
+        const unsigned long long row = __shfl_sync(0xffffffffu, t < 32 ? lo : hi, t & 31);
+        if (!((dead >> t) & 1ull)) { keep |= 1ull << t; dead |= row; }
+      }
+      if (lane == 0) s_keep64 = keep;
     }
     __syncthreads();
-    const unsigned long long keep = s_keep64;
-    // survivors of this block: emit, then sweep every later box against them
+    unsigned long long keep = s_keep64;
+    // only the image's first max_keep survivors can reach the output: a class never needs more than that
+    const int room = max_keep - nkept;
+    if (__popcll(keep) > room) {
+      int seen = 0;
+      unsigned long long trimmed = 0ull;
+      for (int t = 0; t < nb && seen < room; ++t)
+        if ((keep >> t) & 1ull) { trimmed |= 1ull << t; ++seen; }
+      keep = trimmed;
+    }
+    nkept += __popcll(keep);
     if ((int)threadIdx.x < nb) {
       const int j = b0 + threadIdx.x;
       const uint32_t cand = (uint32_t)ord[(int)(keys[j] & 0xffffffffu)];
       kept_out[j] = ((keep >> threadIdx.x) & 1ull) ? ((keys[j] & 0xffffffff00000000ull) | cand) : ~0ull;
+    }
+    if (nkept >= max_keep) {
+      for (int j = b0 + 64 + threadIdx.x; j < m; j += blockDim.x) kept_out[j] = ~0ull;
+      break;                                            // uniform: every thread computed the same nkept
     }
     if (keep != 0ull) {
       for (int j = b0 + 64 + threadIdx.x; j < m; j += blockDim.x) {
@@ -475,10 +465,6 @@ extern "C" int b200_softmax_decode_compact(const float* scores_in, int input_is_
                                            float* cand_scores, int32_t* cand_roi, int32_t* cand_cls,
                                            int32_t* cand_count, b200_stream_t stream) {
   B200_CHECK_ARG(N >= 0 && R >= 0 && K > 0, "softmax_decode_compact: bad shape");
-  if (K + 1 > 32 * kMaxChunks) {
-    set_error("softmax_decode_compact: K+1=%d exceeds %d", K + 1, 32 * kMaxChunks);
-    return B200_ERR_UNSUPPORTED;
-  }
   B200_CHECK_ARG(roi_offsets && image_hw && cand_count, "softmax_decode_compact: null index tensors");
   B200_CHECK_ARG(R == 0 || (scores_in && deltas && proposals && cand_boxes && cand_scores && cand_roi && cand_cls),
                  "softmax_decode_compact: null tensor");
@@ -526,7 +512,7 @@ extern "C" int b200_batched_nms(const float* boxes, const float* scores, const i
   // `scratch` gives every class slice 4x its length: 2x for pow2 padding of the keys, 2x for the bitmap.
   // slices are addressed at (base+cs)*4 to keep them disjoint.
   nms_class_kernel<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(
-      boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1, w.class_start, w.order, w.kept, w.scratch);
+      boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1, w.class_start, w.order, w.kept, w.scratch, max_keep);
   B200_CUDA_LAUNCH_CHECK("nms_class");
   nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
   B200_CUDA_LAUNCH_CHECK("nms_finalize");

@@ -25,17 +25,25 @@ constexpr int kAttMaxL = 128;
 
 template <int TR>
 __global__ void __launch_bounds__(kAttThreads)
-text_attention_kernel(const __nv_bfloat16* __restrict__ q, const void* __restrict__ xv, int x_is_bf16,
+text_attention_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ scores_in,
+                      const void* __restrict__ xv, int x_is_bf16,
                       const float* __restrict__ kp, const float* __restrict__ vp, float* __restrict__ attn_out,
                       __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int ldp, int R, int d, int L,
                       float inv_temp) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  float* s_q = reinterpret_cast<float*>(s_raw);              // [TR][d] fp32
-  float* s_attn = s_q + (size_t)TR * d;                      // [TR][kAttMaxL]
+  float* s_attn = reinterpret_cast<float*>(s_raw);           // [TR][kAttMaxL]
+  float* s_q = s_attn + (size_t)TR * kAttMaxL;               // [TR][d] fp32 (only when q is given)
   const int r0 = blockIdx.x * TR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = kAttThreads / 32;
 
+  if (scores_in) {
+    // scores precomputed by the folded GEMM S = x (Kp Wq)^T / sqrt(d): skip phase 1
+    for (int i = threadIdx.x; i < TR * L; i += kAttThreads) {
+      const int row = i / L, l = i - row * L;
+      s_attn[row * kAttMaxL + l] = (r0 + row < R) ? scores_in[(size_t)(r0 + row) * L + l] : 0.f;
+    }
+  } else {
   // stage q rows as fp32
   for (int i = threadIdx.x; i < TR * d / 2; i += kAttThreads) {
     const int row = (2 * i) / d, col = (2 * i) % d;
@@ -71,6 +79,7 @@ text_attention_kernel(const __nv_bfloat16* __restrict__ q, const void* __restric
       const int row = warp + k * nwarps;
       if (lane == 0 && row < TR) s_attn[row * kAttMaxL + l] = s * inv_temp;
     }
+  }
   }
   __syncthreads();
   // phase 2: softmax over L (one warp per row)
@@ -251,22 +260,22 @@ pcb_cosine_blend_kernel(float* __restrict__ scores, const float* __restrict__ fe
 using namespace b200;
 
 template <int TR>
-static int launch_att(const void* q, const void* x, int x_dtype, const float* kp, const float* vp, float* attn_out,
-                      void* p1, void* p2, int ldp, int R, int d, int L, cudaStream_t st) {
-  const size_t smem = (size_t)TR * d * 4 + (size_t)TR * kAttMaxL * 4;
+static int launch_att(const void* q, const float* scores_in, const void* x, int x_dtype, const float* kp, const float* vp,
+                      float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L, cudaStream_t st) {
+  const size_t smem = (q ? (size_t)TR * d * 4 : 0) + (size_t)TR * kAttMaxL * 4;
   auto k = text_attention_kernel<TR>;
   B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<ceil_div(R, TR), kAttThreads, smem, st>>>((const __nv_bfloat16*)q, x, x_dtype == B200_BF16, kp, vp, attn_out,
+  k<<<ceil_div(R, TR), kAttThreads, smem, st>>>((const __nv_bfloat16*)q, scores_in, x, x_dtype == B200_BF16, kp, vp, attn_out,
                                                 (__nv_bfloat16*)p1, (__nv_bfloat16*)p2, ldp, R, d, L,
                                                 1.0f / sqrtf((float)d));
   B200_CUDA_LAUNCH_CHECK("text_attention");
   return B200_OK;
 }
 
-extern "C" int b200_text_attention(const void* q, const void* x, int x_dtype, const float* kp, const float* vp,
-                                   float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L,
+extern "C" int b200_text_attention(const void* q, const float* scores_in, const void* x, int x_dtype, const float* kp,
+                                   const float* vp, float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L,
                                    b200_stream_t stream) {
-  B200_CHECK_ARG(q && x && kp && vp && p1 && p2, "text_attention: null tensor");
+  B200_CHECK_ARG((q || scores_in) && x && vp && p1 && p2 && (kp || !q), "text_attention: null tensor");
   B200_CHECK_ARG(R >= 0 && d > 0 && L > 0, "text_attention: bad shape");
   if (L > kAttMaxL || d % 8 != 0 || ldp % 8 != 0 || (size_t)8 * d * 4 > 200 * 1024) {
     set_error("text_attention: unsupported shape (L=%d<=%d, d=%d %% 8, ldp=%d %% 8)", L, kAttMaxL, d, ldp);
@@ -275,8 +284,8 @@ extern "C" int b200_text_attention(const void* q, const void* x, int x_dtype, co
   if (R == 0) return B200_OK;
   cudaStream_t st = (cudaStream_t)stream;
   // enough CTAs to cover the SMs at small R, fewer Kp/Vp re-reads from L2 at large R
-  if (R <= 148 * 4) return launch_att<4>(q, x, x_dtype, kp, vp, attn_out, p1, p2, ldp, R, d, L, st);
-  return launch_att<8>(q, x, x_dtype, kp, vp, attn_out, p1, p2, ldp, R, d, L, st);
+  if (R <= 148 * 4) return launch_att<4>(q, scores_in, x, x_dtype, kp, vp, attn_out, p1, p2, ldp, R, d, L, st);
+  return launch_att<8>(q, scores_in, x, x_dtype, kp, vp, attn_out, p1, p2, ldp, R, d, L, st);
 }
 
 extern "C" int b200_residual_layernorm(const float* y, const float* y2, const float* gamma, const float* beta, float eps,

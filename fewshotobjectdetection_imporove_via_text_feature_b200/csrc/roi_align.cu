@@ -10,8 +10,8 @@
 // [channels x bins] slab leaves as one contiguous burst).
 //
 // Work decomposition: CTA = (roi, chunk of 32*VEC channels), 8 warps; each warp owns output bins
-// b = warp, warp+8, ...; the per-ROI bilinear taps (index + weight per axis, per sample) are computed
-// once per CTA into shared memory, so the inner loop is 4 vector loads + 4*VEC FMAs per sample.
+// b = warp, warp+8, ...; per-ROI, per-axis bin windows (first pixel, count, pre-summed separable weights) are
+// built once per CTA in shared memory, so the inner loop is 1 vector load + VEC FMAs per distinct pixel.
 #include "common.cuh"
 
 namespace b200 {
@@ -109,7 +109,41 @@ template <> __device__ __forceinline__ float from_float<float>(float v) { return
 template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 constexpr int kRoiWarps = 8;
-constexpr int kMaxTaps = 160;  // per axis (PH*gh or PW*gw) held in smem; larger ROIs take the on-the-fly path
+constexpr int kMaxTaps = 192;  // per-axis weight slots P*(g+1) held in smem; larger ROIs take the per-sample path
+
+// Per-bin pixel windows.  ROIAlign's sample average is separable: within bin (ph,pw) the gh x gw bilinear samples
+// touch at most (gh+1) x (gw+1) distinct pixels, and pixel (y,x) carries weight a[ph][y] * b[pw][x] where a / b are
+// the per-axis sums of the samples' (1-frac, frac) weights.  The tables below hold, per axis and per bin, the
+// first pixel, the pixel count and the summed weights, so the inner loop visits every distinct pixel ONCE
+// (1 vector load + VEC FMAs) instead of 4 taps per sample — ~2-3x fewer instructions on the large ROIs that
+// dominate the work (ncu: the per-sample form was issue-bound, 86 % issue-active, DRAM 7 %).
+struct AxisBins {
+  int start[16];   // first pixel of the bin's window, in elements (already multiplied by the axis stride)
+  int count[16];   // pixels in the window (0: every sample of the bin fell outside the map)
+  float w[kMaxTaps];
+};
+
+__device__ __forceinline__ void build_axis_bins(AxisBins& t, int p, int P, int g, float start, float bin, int size,
+                                                int stride) {
+  // one thread per bin; weights were zeroed by the caller
+  int first = -1, cnt = 0;
+  float* w = t.w + p * (g + 1);
+  for (int i = 0; i < g; ++i) {
+    float coord = sample_coord(start, p, bin, i, g);
+    if (coord < -1.0f || coord > (float)size) continue;
+    if (coord <= 0.f) coord = 0.f;
+    int lo = (int)coord, hi;
+    if (lo >= size - 1) { hi = lo = size - 1; coord = (float)lo; } else hi = lo + 1;
+    const float l = coord - (float)lo;
+    if (first < 0) first = lo;
+    w[lo - first] += 1.f - l;
+    w[hi - first] += l;
+    cnt = max(cnt, hi - first + 1);
+  }
+  t.start[p] = max(first, 0) * stride;
+  t.count[p] = cnt;
+  (void)P;
+}
 
 // OUT_MODE 0: NHWC direct, 1: NCHW through smem (dynamic smem: bins*(CH+1) floats), 2: NCHW direct scatter
 template <typename T, int VEC, int OUT_MODE>
@@ -118,7 +152,7 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
                           int H, int W, int PH, int PW, float scale, int sampling_ratio, int aligned) {
   constexpr int CH = 32 * VEC;
   extern __shared__ float s_out[];  // OUT_MODE 1 only
-  __shared__ AxisTap s_ty[kMaxTaps], s_tx[kMaxTaps];
+  __shared__ AxisBins s_by, s_bx;
   __shared__ RoiGeom s_g;
 
   const int r = blockIdx.x;
@@ -128,19 +162,22 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
   const int bins = PH * PW;
 
   if (threadIdx.x == 0) s_g = roi_geom(rois + 5 * (size_t)r, scale, sampling_ratio, aligned, PH, PW);
+  for (int i = threadIdx.x; i < kMaxTaps; i += blockDim.x) { s_by.w[i] = 0.f; s_bx.w[i] = 0.f; }
   __syncthreads();
   const RoiGeom g = s_g;
-  const bool tabled = (PH * g.gh <= kMaxTaps) && (PW * g.gw <= kMaxTaps);
+  // dense windows need sample spacing <= 1 px (always true for the adaptive grid; not for a small fixed sampling_ratio)
+  const bool tabled = PH <= 16 && PW <= 16 && PH * (g.gh + 1) <= kMaxTaps && PW * (g.gw + 1) <= kMaxTaps &&
+                      g.bin_h <= (float)g.gh && g.bin_w <= (float)g.gw;
   if (tabled) {
-    for (int i = threadIdx.x; i < PH * g.gh; i += blockDim.x)
-      s_ty[i] = make_tap(sample_coord(g.start_h, i / g.gh, g.bin_h, i % g.gh, g.gh), H, W * C);
-    for (int i = threadIdx.x; i < PW * g.gw; i += blockDim.x)
-      s_tx[i] = make_tap(sample_coord(g.start_w, i / g.gw, g.bin_w, i % g.gw, g.gw), W, C);
+    if ((int)threadIdx.x < PH) build_axis_bins(s_by, threadIdx.x, PH, g.gh, g.start_h, g.bin_h, H, W * C);
+    else if (threadIdx.x >= 32 && (int)threadIdx.x - 32 < PW)
+      build_axis_bins(s_bx, threadIdx.x - 32, PW, g.gw, g.start_w, g.bin_w, W, C);
   }
   __syncthreads();
 
   const T* fbase = feat + (size_t)g.batch * H * W * C + c;
   const bool active = c < C;
+  const int row_stride = W * C;
 
   for (int b = warp; b < bins; b += kRoiWarps) {
     const int ph = b / PW, pw = b % PW;
@@ -148,22 +185,38 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
     if (active) {
-      for (int iy = 0; iy < g.gh; ++iy) {
-        const AxisTap ty = tabled ? s_ty[ph * g.gh + iy]
-                                  : make_tap(sample_coord(g.start_h, ph, g.bin_h, iy, g.gh), H, W * C);
-        const T* row_lo = fbase + ty.lo;
-        const T* row_hi = fbase + ty.hi;
-#pragma unroll 2
-        for (int ix = 0; ix < g.gw; ++ix) {
-          const AxisTap tx = tabled ? s_tx[pw * g.gw + ix]
-                                    : make_tap(sample_coord(g.start_w, pw, g.bin_w, ix, g.gw), W, C);
-          Vec<T, VEC> v1, v2, v3, v4;
-          v1.load(row_lo + tx.lo); v2.load(row_lo + tx.hi);
-          v3.load(row_hi + tx.lo); v4.load(row_hi + tx.hi);
-          const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+      if (tabled) {
+        const int ny = s_by.count[ph], nx = s_bx.count[pw];
+        const float* wy = s_by.w + ph * (g.gh + 1);
+        const float* wx = s_bx.w + pw * (g.gw + 1);
+        const T* base = fbase + s_by.start[ph] + s_bx.start[pw];
+        for (int ky = 0; ky < ny; ++ky) {
+          const float a = wy[ky];
+          const T* row = base + (size_t)ky * row_stride;
+#pragma unroll 4
+          for (int kx = 0; kx < nx; ++kx) {
+            Vec<T, VEC> v;
+            v.load(row + (size_t)kx * C);
+            const float w = a * wx[kx];
 #pragma unroll
-          for (int k = 0; k < VEC; ++k)
-            acc[k] += w1 * v1.v[k] + w2 * v2.v[k] + w3 * v3.v[k] + w4 * v4.v[k];
+            for (int k = 0; k < VEC; ++k) acc[k] += w * v.v[k];
+          }
+        }
+      } else {
+        for (int iy = 0; iy < g.gh; ++iy) {
+          const AxisTap ty = make_tap(sample_coord(g.start_h, ph, g.bin_h, iy, g.gh), H, W * C);
+          const T* row_lo = fbase + ty.lo;
+          const T* row_hi = fbase + ty.hi;
+          for (int ix = 0; ix < g.gw; ++ix) {
+            const AxisTap tx = make_tap(sample_coord(g.start_w, pw, g.bin_w, ix, g.gw), W, C);
+            Vec<T, VEC> v1, v2, v3, v4;
+            v1.load(row_lo + tx.lo); v2.load(row_lo + tx.hi);
+            v3.load(row_hi + tx.lo); v4.load(row_hi + tx.hi);
+            const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              acc[k] += w1 * v1.v[k] + w2 * v2.v[k] + w3 * v3.v[k] + w4 * v4.v[k];
+          }
         }
       }
 #pragma unroll
@@ -226,7 +279,7 @@ extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, void* out
                                   int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
                                   int dtype, int in_layout, int out_layout, void* workspace, size_t workspace_bytes,
                                   b200_stream_t stream) {
-  B200_CHECK_ARG(feat && out && (rois || R == 0), "roi_align_fwd: null tensor");
+  B200_CHECK_ARG(R == 0 || (feat && out && rois), "roi_align_fwd: null tensor");
   B200_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && pooled_h > 0 && pooled_w > 0, "roi_align_fwd: bad shape");
   B200_CHECK_ARG((dtype | 1) == 1 && (in_layout | 1) == 1 && (out_layout | 1) == 1, "roi_align_fwd: bad dtype/layout");
   const int vec = dtype == B200_BF16 ? 8 : 4;

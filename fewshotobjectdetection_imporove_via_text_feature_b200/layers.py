@@ -124,11 +124,22 @@ class BottleneckBlock(nn.Module):
             self._fold = [None if c is None else c.folded(x.dtype, cl) for c in convs]
             self._fold_key = key
         (w1, b1), (w2, b2), (w3, b3), sc = self._fold
+        if _FUSED_CONV["ok"] and x.is_cuda and not torch.is_grad_enabled():
+            try:   # cuDNN runtime-fused conv + bias + ReLU (+ residual add): no separate elementwise kernels
+                out = torch.cudnn_convolution_relu(x, w1, b1, self.conv1.stride, (0, 0), (1, 1), 1)
+                out = torch.cudnn_convolution_relu(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups)
+                res = x if sc is None else F.conv2d(x, sc[0], sc[1], self.shortcut.stride)
+                return torch.cudnn_convolution_add_relu(out, w3, res, 1.0, b3, (1, 1), (0, 0), (1, 1), 1)
+            except RuntimeError:
+                _FUSED_CONV["ok"] = False
         out = F.relu_(F.conv2d(x, w1, b1, self.conv1.stride))
         out = F.relu_(F.conv2d(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups))
         out = F.conv2d(out, w3, b3)
         out += x if sc is None else F.conv2d(x, sc[0], sc[1], self.shortcut.stride)
         return F.relu_(out)
+
+
+_FUSED_CONV = {"ok": True}
 
 
 def make_stage(block_class, num_blocks, first_stride, *, in_channels, out_channels, **kwargs):

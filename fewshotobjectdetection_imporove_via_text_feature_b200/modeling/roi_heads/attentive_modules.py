@@ -121,6 +121,7 @@ class SematicProposalAttention(nn.Module):
         with torch.no_grad():
             _init_parameters(self.attention, 0.02)
         self._plan = ops.TextFusionWeights()
+        self.fold_query = True   # scores via the cached folded operand Kp.Wq (ops.text_fusion_forward)
 
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
@@ -139,7 +140,7 @@ class SematicProposalAttention(nn.Module):
         named = {k: v for k, v in self.named_parameters()}
         for k, v in (extra or {}).items():
             named["extra." + k] = v
-        return self._plan.refresh(named, self.forward_language_model()["text_feat"])
+        return self._plan.refresh(named, (self.embed, self.bg_feature))
 
     def forward(self, visual_feat, extra=None):
         """Returns (attn (1,R,K+2), {'sim2stext' (R,d), 'text_feat' (K+1,D)}) like the reference; on the fused path
@@ -156,6 +157,6 @@ class SematicProposalAttention(nn.Module):
         if not visual_feat.is_cuda:
             raise RuntimeError("b200roi SematicProposalAttention: inference runs on CUDA only (no CPU fallback)")
         w = self.fused_weights(extra)
-        z, zb, attn, xb = ops.text_fusion_forward(visual_feat, w)
+        z, zb, attn, xb = ops.text_fusion_forward(visual_feat, w, self.fold_query)
         output.update(sim2stext=z, sim2stext_bf16=zb, x_bf16=xb, text_feat=text_feat.detach().clone(), fused_w=w)
         return attn[None], output

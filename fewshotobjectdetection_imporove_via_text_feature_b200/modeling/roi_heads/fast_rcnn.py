@@ -139,8 +139,8 @@ class FastRCNNOutputs(object):
     def inference_device(self, score_thresh, nms_thresh, topk_per_image):
         """Fused logits -> padded detections, no host sync (see ops.fast_rcnn_inference_device)."""
         dev = self.pred_class_logits.device
-        offs = torch.tensor([0] + list(np.cumsum(self.num_preds_per_image)), dtype=torch.int32).to(dev, non_blocking=True)
-        hw = torch.tensor([[float(h), float(w)] for (h, w) in self.image_shapes], dtype=torch.float32).to(dev, non_blocking=True)
+        _, offs = ops._roi_index(tuple(int(n) for n in self.num_preds_per_image), dev)     # cached: no H2D per step
+        hw = ops.image_hw_tensor(self.image_shapes, dev)
         return ops.fast_rcnn_inference_device(self.pred_class_logits, self.pred_proposal_deltas, self.proposals.tensor,
                                               offs, hw, score_thresh, nms_thresh, topk_per_image,
                                               weights=self.box2box_transform.weights)

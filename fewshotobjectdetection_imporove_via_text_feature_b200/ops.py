@@ -12,6 +12,10 @@ from . import _lib
 from ._lib import BF16, F32, NCHW, NHWC
 
 
+# bench.py sets KERNEL_EVENTS = {"roi_align_fwd": []} to have CUDA events recorded right around that launch
+KERNEL_EVENTS = {}
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -126,9 +130,16 @@ class _ROIAlign(torch.autograd.Function):
         out = _empty4(R, C, PH, PW, feat.dtype, feat.device, channels_last_out)
         nbytes = _lib.lib().b200_roi_align_fwd_workspace_bytes(N, C, H, W, _dt(feat), in_layout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device) if nbytes else None
+        ev = KERNEL_EVENTS.get("roi_align_fwd") if KERNEL_EVENTS else None
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.call("b200_roi_align_fwd", feat.data_ptr(), rois.data_ptr(), out.data_ptr(), N, C, H, W, R, PH, PW,
                   float(spatial_scale), int(sampling_ratio), int(bool(aligned)), _dt(feat), in_layout,
                   NHWC if channels_last_out else NCHW, _ptr(ws), nbytes, _stream())
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         ctx.save_for_backward(rois, roi_batch_offsets)
         ctx.meta = (feat.shape, feat.dtype, in_layout, output_size, spatial_scale, sampling_ratio, aligned,
                     channels_last_out)
@@ -163,14 +174,45 @@ def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=
                            channels_last_out)
 
 
+_INDEX_CACHE = {}
+
+
+def _roi_index(counts, device):
+    """(batch-index column (R,1) fp32, int32 offsets (N+1)) on `device`, cached per tuple of per-image ROI counts
+    (they repeat every step: 512 in training, <=1000 at test) so that no host->device copy sits on the hot path."""
+    key = (counts, str(device))
+    hit = _INDEX_CACHE.get(key)
+    if hit is None:
+        if len(_INDEX_CACHE) > 256:
+            _INDEX_CACHE.clear()
+        c = torch.tensor(counts, dtype=torch.int64)
+        idx = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.float32), c)[:, None]
+        offs = torch.tensor([0] + c.cumsum(0).tolist(), dtype=torch.int32)
+        hit = (idx.to(device), offs.to(device))
+        _INDEX_CACHE[key] = hit
+    return hit
+
+
 def boxes_to_rois(box_tensors):
     """detectron2 convert_boxes_to_pooler_format: list[(Ri,4)] -> (rois (R,5), int32 offsets (N+1))."""
     dev = box_tensors[0].device
-    counts = [int(b.shape[0]) for b in box_tensors]
-    offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32)
-    idx = torch.repeat_interleave(torch.arange(len(counts), dtype=torch.float32), torch.tensor(counts)).to(dev, non_blocking=True)
-    rois = torch.cat([idx[:, None], torch.cat(box_tensors, 0).float()], dim=1)
-    return rois, offs.to(dev, non_blocking=True)
+    idx, offs = _roi_index(tuple(int(b.shape[0]) for b in box_tensors), dev)
+    boxes = box_tensors[0] if len(box_tensors) == 1 else torch.cat(box_tensors, 0)
+    return torch.cat([idx, boxes.float()], dim=1), offs
+
+
+_HW_CACHE = {}
+
+
+def image_hw_tensor(image_shapes, device):
+    key = (tuple((float(h), float(w)) for h, w in image_shapes), str(device))
+    hit = _HW_CACHE.get(key)
+    if hit is None:
+        if len(_HW_CACHE) > 256:
+            _HW_CACHE.clear()
+        hit = torch.tensor(key[0], dtype=torch.float32).reshape(-1, 2).to(device)
+        _HW_CACHE[key] = hit
+    return hit
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -293,14 +335,17 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
     return out
 
 
-def text_attention(q, x, kp, vp, p1, p2):
-    """softmax(q Kp^T / sqrt(d)) Vp and the gate operands P1 = O*x, P2 = x-O (bf16, written into p1/p2)."""
-    R, d = q.shape
-    L = kp.shape[0]
-    attn = torch.empty((R, L), dtype=torch.float32, device=q.device)
+def text_attention(q, x, kp, vp, p1, p2, scores=None):
+    """softmax(q Kp^T / sqrt(d)) Vp and the gate operands P1 = O*x, P2 = x-O (bf16, written into p1/p2).
+    With `scores` (R,L) fp32 given (already scaled), q/kp are not used."""
+    R, d = x.shape
+    L = vp.shape[0]
+    attn = torch.empty((R, L), dtype=torch.float32, device=x.device)
     assert p1.stride(0) == p2.stride(0) and p1.stride(1) == 1
-    _lib.call("b200_text_attention", q.data_ptr(), x.data_ptr(), _dt(x), kp.data_ptr(), vp.data_ptr(), attn.data_ptr(),
-              p1.data_ptr(), p2.data_ptr(), p1.stride(0), R, d, L, _stream())
+    if scores is not None:
+        assert scores.shape == (R, L) and scores.is_contiguous() and scores.dtype == torch.float32
+    _lib.call("b200_text_attention", _ptr(None if scores is not None else q), _ptr(scores), x.data_ptr(), _dt(x),
+              _ptr(kp), vp.data_ptr(), attn.data_ptr(), p1.data_ptr(), p2.data_ptr(), p1.stride(0), R, d, L, _stream())
     return attn
 
 
@@ -334,11 +379,14 @@ class TextFusionWeights:
     def _version(params):
         return tuple((p.data_ptr(), p._version) for p in params)
 
-    def refresh(self, named, text_feat):
-        params = [named[k] for k in sorted(named)] + [text_feat]
+    def refresh(self, named, text_parts):
+        """`text_parts`: the persistent tensors the text matrix is concatenated from (class embeddings, bg row);
+        keying on them — not on the freshly concatenated matrix — is what makes the cache hit."""
+        params = [named[k] for k in sorted(named)] + list(text_parts)
         key = self._version(params)
         if key == self.key:
             return self.w
+        text_feat = torch.cat(list(text_parts), dim=0)
         bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().float().contiguous()
         w = {}
@@ -356,6 +404,9 @@ class TextFusionWeights:
         vp = torch.nn.functional.linear(vt, named["attention.w_v.weight"].detach().float())
         w["kp"] = torch.cat([kp, named["attention.dummy"].detach().float().reshape(1, -1)], 0).contiguous()
         w["vp"] = torch.cat([vp, torch.zeros(1, vp.shape[1], device=vp.device)], 0).contiguous()
+        # folded query/key operand: S = (x Wq^T) Kp^T / sqrt(d) = x (Kp Wq)^T / sqrt(d); constant while weights are
+        d = w["kp"].shape[1]
+        w["kq"] = bf((w["kp"] @ named["attention.w_q.weight"].detach().float()) / math.sqrt(d))
         for k in named:
             if k.startswith("extra."):
                 t = named[k]
@@ -364,9 +415,11 @@ class TextFusionWeights:
         return w
 
 
-def text_fusion_forward(x, w):
+def text_fusion_forward(x, w, fold_query=True):
     """A1..A6 on the device.  x (R,d) fp32.  Returns (sim2stext fp32 (R,d), sim2stext bf16, attn (R,K+2),
-    x_bf16 view (R,d) with row stride 2d)."""
+    x_bf16 view (R,d) with row stride 2d).  fold_query: compute the attention scores as x (Kp Wq)^T (one skinny
+    GEMM against the cached folded operand) instead of Q = x Wq^T followed by Q Kp^T — same algebra, 8.4 MFLOP/ROI
+    less work; fold_query=False runs the reference's literal order of operations."""
     _require_cuda(x)
     x = x.float().contiguous()
     R, d = x.shape
@@ -374,10 +427,14 @@ def text_fusion_forward(x, w):
     h = d // 2
     xcat = torch.empty((R, 2 * d), dtype=torch.bfloat16, device=dev)      # [o1 | o2 | x]  (attentive_modules.py:172-174)
     xb = cast_bf16_into(x, xcat[:, d:])
-    q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)
     p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
     p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-    attn = text_attention(q, x, w["kp"], w["vp"], p1, p2)
+    if fold_query:
+        s = gemm_bf16(xb, w["kq"])
+        attn = text_attention(None, x, None, w["vp"], p1, p2, scores=s)
+    else:
+        q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)
+        attn = text_attention(q, x, w["kp"], w["vp"], p1, p2)
     gemm_bf16(p1, w["linear1.0.weight"], w["linear1.0.bias"], relu=True, out=xcat[:, :h])
     gemm_bf16(p2, w["linear2.0.weight"], w["linear2.0.bias"], relu=True, out=xcat[:, h:d])
     yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)

@@ -6,6 +6,7 @@ seeded synthetic generator (unit-norm randn rows, seed 7) stands
 Unlike the reference, nothing here hard-codes 'cuda': tensors are created on CPU and moved by the module.
 """
 import os
+import re
 
 import numpy as np
 import torch
@@ -31,15 +32,12 @@ def get_class_name(cfg):
     k = cfg.MODEL.ROI_HEADS.NUM_CLASSES
     classes = None
     if "voc" in name:
-        try:
-            if "base" in name:
-                classes = PASCAL_VOC_BASE_CATEGORIES[int(name.split("_")[-1][-1])]
-            elif "novel" in name:
-                classes = PASCAL_VOC_NOVEL_CATEGORIES[int(name.split("_")[-1][-1])]
-            elif "all" in name:
-                classes = PASCAL_VOC_ALL_CATEGORIES[int(name.split("_")[-3][-1])]
-        except (KeyError, ValueError, IndexError):
-            classes = None
+        # the reference indexes fixed token positions (class_name.py:8-13), which only works for names shaped like
+        # `..._base1` / `..._all1_1shot_seed0`; the split id is taken from the `<kind><id>` token wherever it is
+        m = re.search(r"(base|novel|all)(\d)", name)
+        if m:
+            table = {"base": PASCAL_VOC_BASE_CATEGORIES, "novel": PASCAL_VOC_NOVEL_CATEGORIES, "all": PASCAL_VOC_ALL_CATEGORIES}
+            classes = table[m.group(1)].get(int(m.group(2)))
     if classes is None or len(classes) != k:
         classes = ["class_%d" % i for i in range(k)]
     return list(classes)

@@ -145,10 +145,12 @@ B200_API int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, cons
 
 /* A3 + A4 prologue: S = Q Kp^T / sqrt(d), softmax over the K+2 keys, O = attn Vp, then the two gate
  * operands P1 = O*x and P2 = x - O written as bf16 (attentive_modules.py:45-55,166,170).
- *   q (R,d) bf16; x (R,d) fp32 or bf16 (x_dtype); kp,vp (L,d) fp32 (L = K+2, dummy key last, its value 0);
+ *   q (R,d) bf16 with kp (L,d) fp32, OR q == NULL and scores_in (R,L) fp32 = the already scaled scores S
+ *   (the folded form S = x (Kp Wq)^T / sqrt(d), one skinny tensor-core GEMM instead of the d x d query GEMM);
+ *   x (R,d) fp32 or bf16 (x_dtype); vp (L,d) fp32 (L = K+2, dummy key last, its value row 0);
  *   attn_out (R,L) fp32; p1,p2 (R, ldp) bf16. */
-B200_API int b200_text_attention(const void* q, const void* x, int x_dtype, const float* kp, const float* vp,
-                        float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L,
+B200_API int b200_text_attention(const void* q, const float* scores_in, const void* x, int x_dtype, const float* kp,
+                        const float* vp, float* attn_out, void* p1, void* p2, int ldp, int R, int d, int L,
                         b200_stream_t stream);
 
 /* A5 tail + A6: out = relu?(LayerNorm(y + y2) * gamma + beta); out_f32 and/or out_bf16 may be NULL

@@ -1,0 +1,145 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b200roi.h declares (no compute
+calls), the product refuses to run without CUDA (no CPU fallback), and the host-side mirror of the reference API
+(registries, state-dict names, containers, class lists) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _build, _lib
+    path = _build.build()
+    L = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "b200roi.h")).read()
+    declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", header))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L.b200_abi_version.restype = ctypes.c_int
+    assert L.b200_abi_version() == 1
+    # every declaration cites the reference interface it replaces
+    assert header.count("defrcn/") >= 8
+
+
+def test_no_cpu_fallback():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, modeling, ops
+    with pytest.raises(_lib.B200Error):
+        ops.roi_align(torch.zeros(1, 8, 4, 4), torch.zeros(1, 5), 7, 1 / 16)
+    with pytest.raises(RuntimeError):
+        modeling.AffineLayer(8, bias=True)(torch.zeros(1, 8, 4, 4))
+    # the oracle is never imported by the product
+    import sys
+    pkg = "fewshotobjectdetection_imporove_via_text_feature_b200"
+    for root, _, files in os.walk(os.path.join(ROOT, pkg)):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_registries_and_state_dict_names():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
+    for name in ("Res5ROIHeads", "SematicRes5ROIHeads", "SematicRes5ROIHeadsCrossOutput"):
+        assert modeling.ROI_HEADS_REGISTRY.get(name).__name__ == name
+    for name in ("FastRCNNOutputLayers", "FastRCNNAttentionOutputLayers"):
+        assert modeling.ROI_HEADS_OUTPUT_REGISTRY.get(name).__name__ == name
+    with pytest.raises(KeyError):
+        modeling.ROI_HEADS_REGISTRY.get("NoSuchHead")
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME, cfg.MODEL.ADDITION.NAME = "SematicRes5ROIHeads", "clip"
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 4, 1
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=16, stride=16)})
+    keys = set(m.state_dict().keys())
+    # names a reference checkpoint / tools/model_surgery.py expects
+    for k in ["res5.0.conv1.weight", "res5.0.conv1.norm.running_var", "res5.0.shortcut.weight", "res5.2.conv3.norm.bias",
+              "box_predictor.cls_score.weight", "box_predictor.bbox_pred.bias", "attention.query_projection.weight",
+              "attention.output_projection.bias", "attention.key_projection.weight", "attention.value_projection.bias",
+              "attention.attention.dummy", "attention.attention.w_q.weight", "attention.attention.w_k.weight",
+              "attention.attention.w_v.weight", "attention.attention.linear1.0.weight", "attention.attention.linear2.0.bias",
+              "attention.attention.linear3.weight", "attention.attention.ffn.linear1.weight",
+              "attention.attention.ffn.linear2.bias", "attention.attention.ffn.norm3.weight", "output_projection.weight",
+              "sematic_projection.bias", "projection_matrix"]:
+        assert k in keys, k
+    assert not any("embed" in k or "bg_feature" in k for k in keys)       # text tensors are not checkpointed
+    assert m.attention.embed.shape == (20, 512) and m.attention.bg_feature.shape == (1, 512)
+    assert m.box_predictor.cls_score.out_features == 21 and m.box_predictor.bbox_pred.out_features == 80
+
+
+def test_golden_state_dict_loads(golden):
+    """The reference's own state dict (from the golden fixture) loads with strict=True."""
+    import numpy as np
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
+    g = golden("head_tiny")
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME, cfg.MODEL.ADDITION.NAME = "SematicRes5ROIHeads", "clip"
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 4, 1
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=16, stride=16)})
+    ours = set(m.state_dict().keys())
+    ref = {k for k in g.files if "." in k or k == "projection_matrix"}
+    assert ours == ref, ours ^ ref
+    m.load_state_dict({k: torch.from_numpy(np.asarray(g[k])) for k in ours}, strict=True)
+
+
+def test_structures_and_class_names():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, pairwise_iou
+    from fewshotobjectdetection_imporove_via_text_feature_b200.utils import class_embedding as ce
+    b = Boxes(torch.tensor([[0.0, 0.0, 10.0, 10.0], [-5.0, 2.0, 30.0, 50.0]]))
+    b.clip((20, 25))
+    assert b.tensor.tolist() == [[0, 0, 10, 10], [0, 2, 25, 20]]
+    inst = Instances((20, 25), pred_boxes=b, scores=torch.tensor([0.9, 0.1]))
+    assert len(inst) == 2 and inst.image_size == (20, 25) and inst.has("scores") and len(inst[torch.tensor([1])]) == 1
+    with pytest.raises(AttributeError):
+        inst.nothing
+    iou = pairwise_iou(b, b)
+    assert torch.allclose(iou.diag(), torch.ones(2))
+    cfg = config.get_cfg()
+    cfg.DATASETS.TRAIN = ("voc_2007_trainval_novel1_10shot_seed0",)
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = 5
+    assert ce.get_class_name(cfg) == ["bird", "bus", "cow", "motorbike", "sofa"]
+    cfg.DATASETS.TRAIN = ("voc_2007_trainval_all1_1shot_seed0",)
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = 20
+    names = ce.get_class_name(cfg)
+    assert names[:2] == ["aeroplane", "bicycle"] and names[15:] == ["bird", "bus", "cow", "motorbike", "sofa"]
+    e = ce.get_class_embed(names, "clip")
+    assert e.shape == (20, 512) and torch.allclose(e.norm(dim=1), torch.ones(20), atol=1e-5)
+    bg = ce.create_normalized_orthogonal_tensor(e.mean(0, keepdim=True), torch.Generator().manual_seed(0))
+    assert abs(float(bg.norm()) - 1) < 1e-5
+    cfg.merge_from_list(["MODEL.ROI_HEADS.NMS_THRESH_TEST", 0.3])
+    assert cfg.MODEL.ROI_HEADS.NMS_THRESH_TEST == 0.3
+    with pytest.raises(KeyError):
+        cfg.merge_from_list(["MODEL.ROI_HEADS.TEACHER_TRAINING", True])   # stale key of the reference's scripts
+
+
+def test_matcher_and_sampler():
+    from fewshotobjectdetection_imporove_via_text_feature_b200.layers import Matcher, subsample_labels
+    iou = torch.tensor([[0.7, 0.2, 0.4], [0.1, 0.6, 0.45]])
+    idx, lab = Matcher([0.5], [0, 1])(iou)
+    assert idx.tolist() == [0, 1, 1] and lab.tolist() == [1, 1, 0]
+    torch.manual_seed(0)
+    labels = torch.tensor([0, 1, 20, 20, 20, -1, 3, 20])
+    fg, bg = subsample_labels(labels, 4, 0.25, 20)
+    assert len(fg) == 1 and len(bg) == 3 and all(labels[i] == 20 for i in bg) and labels[fg[0]] in (0, 1, 3)
+
+
+def test_losses_match_golden(golden):
+    """FastRCNNOutputs.losses on CPU tensors (pure torch, no kernels involved) vs the reference's numbers."""
+    import numpy as np
+    from fewshotobjectdetection_imporove_via_text_feature_b200.layers import Box2BoxTransform
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling import FastRCNNOutputs
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+    g = golden("losses")
+    T = lambda k: torch.from_numpy(np.asarray(g[k]))
+    inst = Instances((600, 800), proposal_boxes=Boxes(T("props")), gt_boxes=Boxes(T("gt_boxes")), gt_classes=T("gt_classes"))
+    o = FastRCNNOutputs(Box2BoxTransform((10.0, 10.0, 5.0, 5.0)), T("logits"), T("deltas"), [inst], 0.0)
+    L = o.losses()
+    assert abs(float(L["loss_cls"]) - float(g["loss_cls"])) < 1e-6
+    assert abs(float(L["loss_box_reg"]) - float(g["loss_box_reg"])) < 1e-6

@@ -71,6 +71,12 @@ def test_text_attention(R, d, L):
     torch.testing.assert_close(got.cpu(), attn, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(p1.float().cpu(), o * x, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(p2.float().cpu(), x - o, rtol=1e-2, atol=1e-2)
+    # scores-in mode (folded query GEMM feeds the kernel): same softmax / AV / gate outputs
+    p1b, p2b = torch.empty_like(p1), torch.empty_like(p2)
+    got2 = ops.text_attention(None, x.cuda(), None, vp.cuda(), p1b, p2b, scores=s.cuda().contiguous())
+    torch.testing.assert_close(got2.cpu(), attn, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(p1b.float().cpu(), o * x, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(p2b.float().cpu(), x - o, rtol=1e-2, atol=1e-2)
 
 
 def test_residual_layernorm():
@@ -100,10 +106,12 @@ def _build_attention(K, d, seed=0):
     return m.eval()
 
 
+@pytest.mark.parametrize("fold", [True, False])
 @pytest.mark.parametrize("R,K", [(512, 20), (200, 80)])
-def test_chain_vs_oracle(R, K):
+def test_chain_vs_oracle(R, K, fold):
     d = 2048
     m = _build_attention(K, d)
+    m.fold_query = fold
     x = torch.relu(torch.randn(R, d, generator=torch.Generator().manual_seed(2)))
     p = {"attention." + k: v.detach() for k, v in m.state_dict().items()}
     text = torch.cat([m.embed, m.bg_feature], 0)

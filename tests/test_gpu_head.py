@@ -5,6 +5,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """fp32 res5 comparisons against the CPU oracle need true fp32 convolutions (cuDNN defaults to TF32)."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
 from oracle import oracle as O
 from oracle.gen_golden import synth_proposals
 
