@@ -153,6 +153,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  // disjoint boxes (the vast majority of pairs): inter == 0 exactly, and 0/union (or 0/0 = NaN) is never > thr for
+  // thr >= 0 — skip the IEEE division without changing any decision
+  if (thr >= 0.f && (w == 0.f || h == 0.f)) return false;
   const float inter = __fmul_rn(w, h);
   const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));

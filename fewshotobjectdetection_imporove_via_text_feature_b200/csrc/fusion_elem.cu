@@ -120,6 +120,7 @@ text_attention_kernel(const __nv_bfloat16* __restrict__ q, const float* __restri
     for (int row = 0; row < TR; ++row)
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[row][k] = 0.f;
+#pragma unroll 4
     for (int l = 0; l < L; ++l) {
       const float4 va = __ldg(reinterpret_cast<const float4*>(vp + (size_t)l * d + c));
       const float4 vb = __ldg(reinterpret_cast<const float4*>(vp + (size_t)l * d + c + 4));

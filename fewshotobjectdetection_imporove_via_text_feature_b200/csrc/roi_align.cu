@@ -189,14 +189,14 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
         const int ny = s_by.count[ph], nx = s_bx.count[pw];
         const float* wy = s_by.w + ph * (g.gh + 1);
         const float* wx = s_bx.w + pw * (g.gw + 1);
-        const T* base = fbase + s_by.start[ph] + s_bx.start[pw];
-        for (int ky = 0; ky < ny; ++ky) {
+        const T* row = fbase + s_by.start[ph] + s_bx.start[pw];
+        for (int ky = 0; ky < ny; ++ky, row += row_stride) {
           const float a = wy[ky];
-          const T* row = base + (size_t)ky * row_stride;
+          const T* p = row;
 #pragma unroll 4
-          for (int kx = 0; kx < nx; ++kx) {
+          for (int kx = 0; kx < nx; ++kx, p += C) {
             Vec<T, VEC> v;
-            v.load(row + (size_t)kx * C);
+            v.load(p);
             const float w = a * wx[kx];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc[k] += w * v.v[k];
@@ -219,8 +219,10 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
           }
         }
       }
+      // sample counts are small integers: 1/count is exact for powers of two and within 1 ulp otherwise
+      const float inv = 1.0f / g.count;
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[k] = __fdiv_rn(acc[k], g.count);
+      for (int k = 0; k < VEC; ++k) acc[k] *= inv;
     }
     if (OUT_MODE == 0) {
       if (active) Vec<T, VEC>::store_stream(out + ((size_t)r * bins + b) * C + c, acc);
