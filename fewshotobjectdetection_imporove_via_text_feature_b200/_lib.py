@@ -19,6 +19,7 @@ c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void
 SIGNATURES = {
     "b200_abi_version": (c_int, []),
     "b200_last_error": (ctypes.c_char_p, []),
+    "b200_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "b200_gdl_affine_fwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     "b200_gdl_affine_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
     "b200_gdl_affine_bwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
@@ -68,6 +69,10 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+def set_option(key, value):
+    return call("b200_set_option", key.encode(), int(value))
 
 
 def call(name, *args):

@@ -41,6 +41,9 @@ enum { B200_NCHW = 0, B200_NHWC = 1 };
 
 B200_API int b200_abi_version(void);
 B200_API const char* b200_last_error(void);
+/* process-wide implementation switches (for A/B measurement; results are parity-tested under every setting):
+ *   "roi_align_bf16_impl": 0 = CUDA-core per-bin-window kernel (default), 1 = TMA + ldmatrix + mma.sync kernel */
+B200_API int b200_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------
  * G1 + G2  Gradient Decoupled Layer + AffineLayer
