@@ -277,6 +277,62 @@ def gen_pcb():
                         exclude=np.array(pcb.exclude_cls, np.int64), alpha=np.float32(0.5))
 
 
+def seeded_fill(module, seed, scale=0.05):
+    """Overwrite every parameter/buffer with values that depend only on (seed, sorted key index, shape): lets a
+    golden produced by the reference module be replayed on the mirror module without storing the weights — and
+    fails loudly if the two state dicts differ in names or shapes."""
+    sd = module.state_dict()
+    with torch.no_grad():
+        for i, k in enumerate(sorted(sd)):
+            g = torch.Generator().manual_seed(seed * 1000 + i)
+            v = torch.randn(sd[k].shape, generator=g) * scale
+            if k.endswith("norm3.weight"):
+                v = v + 1.0
+            sd[k].copy_(v)
+    return sorted((k, tuple(v.shape)) for k, v in sd.items())
+
+
+def gen_teacher():
+    """KD losses (my_module.py:393-437) and the LV / textDomination teacher attentions (attentive_modules.py:297-437,
+    490-634) run unchanged.  (The *_VKV forwards are broken as checked in — SURVEY §2.2 — so they have no golden.)"""
+    rs.install()
+    mm = rs.load("defrcn.modeling.roi_heads.my_module")
+    gen = torch.Generator().manual_seed(13)
+    R, K = 64, 15
+    s_out, t_out = torch.randn(R, K + 1, generator=gen), torch.randn(R, K + 1, generator=gen) * 2
+    labels = torch.randint(0, K + 1, (R,), generator=gen)
+    labels[R // 2:] = K
+    params = {"alpha": 0.7, "temperature": 5.0}
+    d = dict(s_out=s_out.numpy(), t_out=t_out.numpy(), labels=labels.numpy(), alpha=np.float32(0.7), T=np.float32(5.0),
+             kd=mm.loss_fn_kd(s_out, labels, t_out, params).numpy(),
+             kd_only=mm.loss_fn_kd_only(s_out, labels, K, t_out, params).numpy())
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    cfg = rs.default_cfg(num_classes=20, addition="glove")
+    cfg.MODEL.ROI_HEADS.DISTILLATE = False
+    cfg.MODEL.ROI_HEADS.STUDENT_TRAINING = False
+    cfg.MODEL.ROI_HEADS.TEACHER_TRAINING = True
+    dm, Rr = 32, 24
+    x = torch.relu(torch.randn(Rr, dm, generator=gen))
+    lab = torch.randint(0, 21, (Rr,), generator=gen)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with cuda_as_cpu():
+            for cls, tag in ((am.LV_attention, "lv"), (am.LV_attention_textDomination, "td")):
+                torch.manual_seed(2)
+                m = cls(dm, cfg=cfg).eval()
+                keys = seeded_fill(m, 77)
+                with torch.no_grad():
+                    _, out = m(x, lab)
+                d[tag + "_keys"] = np.array(["%s:%s" % (k, "x".join(map(str, shp))) for k, shp in keys])
+                d[tag + "_embed"] = m.embed.numpy()
+                d[tag + "_sim2stext"] = out["sim2stext"].numpy()
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    d.update(x=x.numpy(), lab=lab.numpy())
+    np.savez_compressed(os.path.join(OUT, "teacher.npz"), **d)
+
+
 def gen_known_answer():
     """test.py:80-92 fixture: CE(pred_logits.pt, gt_classes.pt)."""
     pl = torch.load(os.path.join(rs.REFERENCE_ROOT, "pred_logits.pt"), map_location="cpu").detach()
@@ -296,6 +352,7 @@ def main():
     gen_attention()
     gen_head_tiny()
     gen_pcb()
+    gen_teacher()
     gen_known_answer()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -505,6 +505,42 @@ def _pkg_shell(name, path):
     return m
 
 
+class FakeGloVe:
+    """Stand-in for torchnlp GloVe (no vector files offline): a seeded 300-d vector per word."""
+
+    def __init__(self, name="6B", dim=300):
+        self.dim = dim
+
+    def __getitem__(self, word):
+        seed = sum((i + 1) * ord(c) for i, c in enumerate(word)) % (2 ** 31)
+        return torch.randn(self.dim, generator=torch.Generator().manual_seed(seed))
+
+
+VOC_ALL1 = ["aeroplane", "bicycle", "boat", "bottle", "car", "cat", "chair", "diningtable", "dog", "horse", "person",
+            "pottedplant", "sheep", "train", "tvmonitor", "bird", "bus", "cow", "motorbike", "sofa"]
+
+
+class _MetadataCatalog:
+    def get(self, name):
+        m = types.SimpleNamespace()
+        m.thing_classes, m.base_classes, m.novel_classes = VOC_ALL1, VOC_ALL1[:15], VOC_ALL1[15:]
+        m.novel_dataset_id_to_contiguous_id = {}
+        return m
+
+
+def glove_table(classes):
+    """(K,300) class table the way LV_attention builds it (attentive_modules.py:352-364) from FakeGloVe."""
+    map_voc = {"diningtable": "dining table", "pottedplant": "potted plant", "tvmonitor": "tv"}
+    g = FakeGloVe()
+    rows = []
+    for name in classes:
+        v = torch.zeros(300)
+        for w in map_voc.get(name, name).split(" "):
+            v = v + g[w]
+        rows.append(v)
+    return torch.stack(rows)
+
+
 _installed = False
 
 
@@ -534,12 +570,12 @@ def install(class_embed_fn=None, device="cpu"):
     _mod("detectron2.modeling.proposal_generator")
     _mod("detectron2.modeling.proposal_generator.proposal_utils",
          add_ground_truth_to_proposals=add_ground_truth_to_proposals)
-    _mod("detectron2.data", MetadataCatalog=object(), DatasetCatalog=object())
+    _mod("detectron2.data", MetadataCatalog=_MetadataCatalog(), DatasetCatalog=object())
     _mod("fvcore")
     wi = _mod("fvcore.nn.weight_init", c2_msra_fill=lambda m: None, c2_xavier_fill=lambda m: None)
     _mod("fvcore.nn", smooth_l1_loss=smooth_l1_loss, weight_init=wi)
     _mod("torchnlp")
-    _mod("torchnlp.word_to_vector", GloVe=object)
+    _mod("torchnlp.word_to_vector", GloVe=FakeGloVe)
 
     r = os.path.join(REFERENCE_ROOT, "defrcn")
     _pkg_shell("defrcn", r)
