@@ -23,10 +23,10 @@ SIGNATURES = {
     "b200_gdl_affine_fwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p]),
     "b200_gdl_affine_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
     "b200_gdl_affine_bwd": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 3 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
-    "b200_roi_align_fwd_workspace_bytes": (c_size_t, [c_int] * 6),
-    "b200_roi_align_fwd": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
-    "b200_roi_align_bwd_workspace_bytes": (c_size_t, [c_int] * 10),
-    "b200_roi_align_bwd": (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_fwd_workspace_bytes": (c_size_t, [c_int] * 7),
+    "b200_roi_align_fwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_bwd_workspace_bytes": (c_size_t, [c_int] * 11),
+    "b200_roi_align_bwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_void_p]),
     "b200_batched_nms_workspace_bytes": (c_size_t, [c_int] * 3),
     "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
@@ -75,12 +75,13 @@ def set_option(key, value):
     return call("b200_set_option", key.encode(), int(value))
 
 
-def call(name, *args):
-    """Invoke an int-returning entry point and raise on failure."""
+def call(name, *args, launches=None):
+    """Invoke an int-returning entry point and raise on failure.  `launches` overrides the per-call kernel count
+    when the entry point dispatches to a multi-kernel implementation."""
     global LAUNCHES
     L = lib()
     rc = getattr(L, name)(*args)
-    LAUNCHES += KERNELS_PER_CALL.get(name, 0)
+    LAUNCHES += KERNELS_PER_CALL.get(name, 0) if launches is None else launches
     if rc != 0:
         raise B200Error("%s failed (%d): %s" % (name, rc, L.b200_last_error().decode("utf-8", "replace")))
     return rc

@@ -16,63 +16,12 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "roi_geom.cuh"
 
 namespace b200 {
 
 int dispatch_affine(const void* x, const float* w, const float* b, float mult, void* y, int N, int C, int H, int W,
                     int in_dtype, int in_layout, int out_dtype, int out_layout, cudaStream_t st);
-
-struct AxisTap {
-  int lo, hi;      // element offsets along the axis (already multiplied by the axis stride)
-  float wlo, whi;  // (1-frac), frac ; both 0 when the sample is out of range
-};
-
-// One-axis half of torchvision's bilinear_interpolate / pre_calc_for_bilinear_interpolate.
-__device__ __forceinline__ AxisTap make_tap(float coord, int size, int stride) {
-  AxisTap t;
-  if (coord < -1.0f || coord > (float)size) {
-    t.lo = t.hi = 0; t.wlo = t.whi = 0.f;
-    return t;
-  }
-  if (coord <= 0.f) coord = 0.f;
-  int lo = (int)coord, hi;
-  if (lo >= size - 1) { hi = lo = size - 1; coord = (float)lo; } else hi = lo + 1;
-  const float l = coord - (float)lo;
-  t.lo = lo * stride; t.hi = hi * stride; t.wlo = 1.f - l; t.whi = l;
-  return t;
-}
-
-struct RoiGeom {
-  int batch, gh, gw;
-  float start_h, start_w, bin_h, bin_w, count;
-};
-
-__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float scale, int sampling_ratio,
-                                            int aligned, int PH, int PW) {
-  RoiGeom g;
-  g.batch = (int)roi[0];
-  const float off = aligned ? 0.5f : 0.0f;
-  // no FMA contraction: coordinates must round exactly as the CPU reference's
-  g.start_w = __fsub_rn(__fmul_rn(roi[1], scale), off);
-  g.start_h = __fsub_rn(__fmul_rn(roi[2], scale), off);
-  const float end_w = __fsub_rn(__fmul_rn(roi[3], scale), off);
-  const float end_h = __fsub_rn(__fmul_rn(roi[4], scale), off);
-  float rw = __fsub_rn(end_w, g.start_w), rh = __fsub_rn(end_h, g.start_h);
-  if (!aligned) { rw = fmaxf(rw, 1.f); rh = fmaxf(rh, 1.f); }
-  g.bin_h = __fdiv_rn(rh, (float)PH);
-  g.bin_w = __fdiv_rn(rw, (float)PW);
-  g.gh = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)PH));
-  g.gw = sampling_ratio > 0 ? sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)PW));
-  g.gh = max(g.gh, 0); g.gw = max(g.gw, 0);
-  g.count = (float)max(g.gh * g.gw, 1);
-  return g;
-}
-
-__device__ __forceinline__ float sample_coord(float start, int p, float bin, int i, int grid) {
-  // roi_start + p*bin + (i + .5f) * bin / grid   (left-to-right, separate roundings)
-  return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
-                   __fdiv_rn(__fmul_rn((float)i + .5f, bin), (float)grid));
-}
 
 template <typename T, int VEC> struct Vec;
 template <> struct Vec<float, 4> {
@@ -152,7 +101,7 @@ __device__ __forceinline__ void build_axis_bins(AxisBins& t, int p, int P, int g
 template <typename T, int VEC, int OUT_MODE>
 __global__ void __launch_bounds__(kRoiWarps * 32)
 roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ rois, T* __restrict__ out, int C,
-                          int H, int W, int PH, int PW, float scale, int sampling_ratio, int aligned) {
+                          int H, int W, int PH, int PW, int bin_step, float scale, int sampling_ratio, int aligned) {
   constexpr int CH = 32 * VEC;
   extern __shared__ float s_out[];  // OUT_MODE 1 only
   __shared__ AxisBins s_by, s_bx;
@@ -162,7 +111,9 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.y * CH;
   const int c = c0 + lane * VEC;
-  const int bins = PH * PW;
+  // bin_step > 1: only bins (0, step, 2*step, ...) of each axis are computed and stored densely
+  const int PWO = (PW + bin_step - 1) / bin_step;
+  const int bins = ((PH + bin_step - 1) / bin_step) * PWO;
 
   if (threadIdx.x == 0) s_g = roi_geom(rois + 5 * (size_t)r, scale, sampling_ratio, aligned, PH, PW);
   for (int i = threadIdx.x; i < kMaxTaps; i += blockDim.x) { s_by.w[i] = 0.f; s_bx.w[i] = 0.f; }
@@ -183,7 +134,7 @@ roi_align_fwd_nhwc_kernel(const T* __restrict__ feat, const float* __restrict__ 
   const int row_stride = W * C;
 
   for (int b = warp; b < bins; b += kRoiWarps) {
-    const int ph = b / PW, pw = b % PW;
+    const int ph = (b / PWO) * bin_step, pw = (b % PWO) * bin_step;
     float acc[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
@@ -524,29 +475,37 @@ roi_align_fwd_tma_bf16_kernel(const __grid_constant__ CUtensorMap fmap, const __
 
 template <typename T, int VEC>
 static int launch_roi_fwd(const T* feat_nhwc, const float* rois, T* out, int C, int H, int W, int R, int PH, int PW,
-                          float scale, int sr, int aligned, int out_layout, cudaStream_t st) {
+                          int bin_step, float scale, int sr, int aligned, int out_layout, cudaStream_t st) {
   constexpr int CH = 32 * VEC;
   dim3 grid(R, ceil_div(C, CH)), block(kRoiWarps * 32);
   if (out_layout == B200_NHWC) {
-    roi_align_fwd_nhwc_kernel<T, VEC, 0><<<grid, block, 0, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, scale, sr, aligned);
+    roi_align_fwd_nhwc_kernel<T, VEC, 0><<<grid, block, 0, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, bin_step, scale, sr, aligned);
   } else {
-    const size_t smem = (size_t)PH * PW * (CH + 1) * sizeof(float);
+    const size_t smem = (size_t)ceil_div(PH, bin_step) * ceil_div(PW, bin_step) * (CH + 1) * sizeof(float);
     if (smem <= 160 * 1024) {
       auto k = roi_align_fwd_nhwc_kernel<T, VEC, 1>;
       if (smem > 40 * 1024) B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, block, smem, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, scale, sr, aligned);
+      k<<<grid, block, smem, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, bin_step, scale, sr, aligned);
     } else {
-      roi_align_fwd_nhwc_kernel<T, VEC, 2><<<grid, block, 0, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, scale, sr, aligned);
+      roi_align_fwd_nhwc_kernel<T, VEC, 2><<<grid, block, 0, st>>>(feat_nhwc, rois, out, C, H, W, PH, PW, bin_step, scale, sr, aligned);
     }
   }
   B200_CUDA_LAUNCH_CHECK("roi_align_fwd");
   return B200_OK;
 }
 
-// 0: CUDA-core per-bin-window kernel (default, fastest measured: 0.36 ms at R=4096, C=1024)
-// 1: TMA + ldmatrix + mma.sync tensor-core kernel (0.50 ms: 2.5x fewer instructions, but it moves 3.4 GB L2->SM
-//    because windows are padded to 16-pixel boxes and rows shared by adjacent bins are fetched per bin row)
-int g_roi_bf16_impl = 0;
+// 0: CUDA-core per-bin-window kernel (0.36 ms at R=4096, C=1024)
+// 1: TMA + ldmatrix + mma.sync tensor-core kernel, per-ROI windows (0.50 ms: 2.5x fewer instructions, but it moves
+//    3.4 GB L2->SM because windows are padded to 16-pixel boxes and rows shared by adjacent bins are fetched per bin row)
+// 2: slice-resident tensor-core kernel (roi_align_slice.cu; default) — taken when the ROIs come grouped by image
+//    (roi_batch_offsets given), bf16 channels-last in and out, 7x7 bins; otherwise the call falls back to 0
+int g_roi_bf16_impl = 2;
+
+size_t roi_slice_workspace_bytes(int R);
+bool roi_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step, const void* feat);
+int launch_roi_fwd_slice(const __nv_bfloat16* feat, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* out,
+                         int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr,
+                         int aligned, void* workspace, cudaStream_t st);
 
 typedef CUresult (*PFN_encodeTiledRoi)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -584,7 +543,7 @@ using namespace b200;
 extern "C" int b200_set_option(const char* key, int value) {
   B200_CHECK_ARG(key != nullptr, "set_option: null key");
   if (strcmp(key, "roi_align_bf16_impl") == 0) {
-    B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bf16_impl must be 0 (cuda-core) or 1 (tma+mma)");
+    B200_CHECK_ARG(value >= 0 && value <= 2, "set_option: roi_align_bf16_impl must be 0 (cuda-core), 1 (tma+mma) or 2 (slice-resident)");
     g_roi_bf16_impl = value;
     return B200_OK;
   }
@@ -592,18 +551,21 @@ extern "C" int b200_set_option(const char* key, int value) {
   return B200_ERR_INVALID;
 }
 
-extern "C" size_t b200_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int dtype, int in_layout) {
-  if (in_layout == B200_NHWC) return 0;
-  return align_up((size_t)N * C * H * W * (dtype == B200_BF16 ? 2 : 4), 256);
+extern "C" size_t b200_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R, int dtype, int in_layout) {
+  size_t b = 0;
+  if (in_layout == B200_NCHW) b += align_up((size_t)N * C * H * W * (dtype == B200_BF16 ? 2 : 4), 256);
+  if (dtype == B200_BF16) b += roi_slice_workspace_bytes(R);   // per-ROI geometry records of the slice-resident kernel
+  return b;
 }
 
-extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R,
-                                  int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
-                                  int dtype, int in_layout, int out_layout, void* workspace, size_t workspace_bytes,
-                                  b200_stream_t stream) {
+extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, const int32_t* roi_batch_offsets, void* out, int N,
+                                  int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step,
+                                  float spatial_scale, int sampling_ratio, int aligned, int dtype, int in_layout,
+                                  int out_layout, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
   B200_CHECK_ARG(R == 0 || (feat && out && rois), "roi_align_fwd: null tensor");
   B200_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && pooled_h > 0 && pooled_w > 0, "roi_align_fwd: bad shape");
   B200_CHECK_ARG((dtype | 1) == 1 && (in_layout | 1) == 1 && (out_layout | 1) == 1, "roi_align_fwd: bad dtype/layout");
+  B200_CHECK_ARG(bin_step >= 1 && bin_step <= 8, "roi_align_fwd: bin_step must be in [1, 8]");
   const int vec = dtype == B200_BF16 ? 8 : 4;
   if (C % vec != 0) {
     set_error("roi_align_fwd: C=%d must be a multiple of %d for this dtype", C, vec);
@@ -615,21 +577,27 @@ extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, void* out
   }
   if (R == 0) return B200_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t need = b200_roi_align_fwd_workspace_bytes(N, C, H, W, R, dtype, in_layout);
+  if (need && (!workspace || workspace_bytes < need)) {
+    set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return B200_ERR_WORKSPACE;
+  }
+  unsigned char* ws = (unsigned char*)workspace;
   const void* f = feat;
   if (in_layout == B200_NCHW) {
-    const size_t need = b200_roi_align_fwd_workspace_bytes(N, C, H, W, dtype, in_layout);
-    if (!workspace || workspace_bytes < need) {
-      set_error("roi_align_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
-      return B200_ERR_WORKSPACE;
-    }
-    int rc = dispatch_affine(feat, nullptr, nullptr, 1.0f, workspace, N, C, H, W, dtype, B200_NCHW, dtype, B200_NHWC, st);
+    int rc = dispatch_affine(feat, nullptr, nullptr, 1.0f, ws, N, C, H, W, dtype, B200_NCHW, dtype, B200_NHWC, st);
     if (rc != B200_OK) return rc;
-    f = workspace;
+    f = ws;
+    ws += align_up((size_t)N * C * H * W * (dtype == B200_BF16 ? 2 : 4), 256);
   }
   if (dtype == B200_F32)
-    return launch_roi_fwd<float, 4>((const float*)f, rois, (float*)out, C, H, W, R, pooled_h, pooled_w, spatial_scale,
-                                    sampling_ratio, aligned, out_layout, st);
-  if (g_roi_bf16_impl == 1 && out_layout == B200_NHWC && pooled_h <= 8 && pooled_w <= 8 && ((uintptr_t)f & 15) == 0) {
+    return launch_roi_fwd<float, 4>((const float*)f, rois, (float*)out, C, H, W, R, pooled_h, pooled_w, bin_step,
+                                    spatial_scale, sampling_ratio, aligned, out_layout, st);
+  if (g_roi_bf16_impl == 2 && roi_batch_offsets && out_layout == B200_NHWC &&
+      roi_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step, f))
+    return launch_roi_fwd_slice((const __nv_bfloat16*)f, rois, roi_batch_offsets, (__nv_bfloat16*)out, N, C, H, W, R,
+                                pooled_h, pooled_w, bin_step, spatial_scale, sampling_ratio, aligned, ws, st);
+  if (g_roi_bf16_impl == 1 && bin_step == 1 && out_layout == B200_NHWC && pooled_h <= 8 && pooled_w <= 8 && ((uintptr_t)f & 15) == 0) {
     // tensor-core path: 4-D TMA map over the NHWC map {C, W, H, N}, box 64 ch x 16 px, 128B swizzle
     CUtensorMap fmap;
     int rc = make_feature_map(&fmap, f, N, C, H, W);
@@ -647,5 +615,5 @@ extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, void* out
     return B200_OK;
   }
   return launch_roi_fwd<__nv_bfloat16, 8>((const __nv_bfloat16*)f, rois, (__nv_bfloat16*)out, C, H, W, R, pooled_h,
-                                          pooled_w, spatial_scale, sampling_ratio, aligned, out_layout, st);
+                                          pooled_w, bin_step, spatial_scale, sampling_ratio, aligned, out_layout, st);
 }

@@ -119,13 +119,15 @@ template <> struct V4<__nv_bfloat16> {
 template <typename T>
 __global__ void __launch_bounds__(kBwdWarps * 32)
 roi_align_bwd_nhwc_kernel(const T* __restrict__ g, const int32_t* __restrict__ roi_batch_offsets, BwdTables t,
-                          T* __restrict__ grad_feat, int C, int H, int W, int PH, int PW) {
+                          T* __restrict__ grad_feat, int C, int H, int W, int PH, int PW, int bin_step) {
   extern __shared__ int s_list[];  // ROIs of this image whose row extent covers y
   __shared__ int s_n;
   const int y = blockIdx.x, n = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.z * 128 + lane * 4;
   const int r0 = roi_batch_offsets[n], r1 = roi_batch_offsets[n + 1];
+  // bin_step > 1: g holds only the bins (0, step, 2*step, ...) of each axis, densely: [R][PHO][PWO][C]
+  const int PHO = (PH + bin_step - 1) / bin_step, PWO = (PW + bin_step - 1) / bin_step;
   // ordered compaction of the covering ROIs (warp 0, ballot prefix) keeps the summation order fixed
   if (warp == 0) {
     int cnt = 0;
@@ -152,14 +154,14 @@ roi_align_bwd_nhwc_kernel(const T* __restrict__ g, const int32_t* __restrict__ r
       const int ph_lo = ry & 255, ph_hi = ry >> 8, pw_lo = rx & 255, pw_hi = rx >> 8;
       const float* wa = t.ta + ((size_t)r * H + y) * kMaxP;
       const float* wb = t.tb + ((size_t)r * W + x) * kMaxP;
-      for (int ph = ph_lo; ph <= ph_hi; ++ph) {
+      for (int ph = (ph_lo + bin_step - 1) / bin_step * bin_step; ph <= ph_hi; ph += bin_step) {
         const float wy = wa[ph] * e.inv_count;
         if (wy == 0.f) continue;
-        const T* grow = g + (((size_t)r * PH + ph) * PW) * C + c;
-        for (int pw = pw_lo; pw <= pw_hi; ++pw) {
+        const T* grow = g + (((size_t)r * PHO + ph / bin_step) * PWO) * C + c;
+        for (int pw = (pw_lo + bin_step - 1) / bin_step * bin_step; pw <= pw_hi; pw += bin_step) {
           const float w = wy * wb[pw];
           if (w == 0.f) continue;
-          const float4 gv = V4<T>::ld(grow + (size_t)pw * C);
+          const float4 gv = V4<T>::ld(grow + (size_t)(pw / bin_step) * C);
           acc.x += w * gv.x; acc.y += w * gv.y; acc.z += w * gv.z; acc.w += w * gv.w;
         }
       }
@@ -178,25 +180,29 @@ static size_t tables_bytes(int R, int H, int W) {
 using namespace b200;
 
 extern "C" size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
-                                                     int dtype, int grad_in_layout, int grad_out_layout) {
+                                                     int bin_step, int dtype, int grad_in_layout, int grad_out_layout) {
   const size_t e = dtype == B200_BF16 ? 2 : 4;
   size_t b = tables_bytes(R, H, W);
-  if (grad_out_layout == B200_NCHW) b += align_up((size_t)R * C * pooled_h * pooled_w * e, 256);
+  bin_step = max(bin_step, 1);
+  const int pho = ceil_div(pooled_h, bin_step), pwo = ceil_div(pooled_w, bin_step);
+  if (grad_out_layout == B200_NCHW) b += align_up((size_t)R * C * pho * pwo * e, 256);
   if (grad_in_layout == B200_NCHW) b += align_up((size_t)N * C * H * W * e, 256);
   return b;
 }
 
 extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const int32_t* roi_batch_offsets,
                                   void* grad_feat, int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
-                                  float spatial_scale, int sampling_ratio, int aligned, int dtype, int grad_out_layout,
+                                  int bin_step, float spatial_scale, int sampling_ratio, int aligned, int dtype, int grad_out_layout,
                                   int grad_in_layout, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
   B200_CHECK_ARG(grad_feat && roi_batch_offsets && (R == 0 || (grad_out && rois)), "roi_align_bwd: null tensor");
   B200_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0, "roi_align_bwd: bad shape");
+  B200_CHECK_ARG(bin_step >= 1 && bin_step <= 8, "roi_align_bwd: bin_step must be in [1, 8]");
+  const int pho = ceil_div(pooled_h, bin_step), pwo = ceil_div(pooled_w, bin_step);
   if (pooled_h > kMaxP || pooled_w > kMaxP || C % 4 != 0) {
     set_error("roi_align_bwd: pooled size must be <= %d and C %% 4 == 0", kMaxP);
     return B200_ERR_UNSUPPORTED;
   }
-  const size_t need = b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, pooled_h, pooled_w, dtype, grad_in_layout, grad_out_layout);
+  const size_t need = b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, pooled_h, pooled_w, bin_step, dtype, grad_in_layout, grad_out_layout);
   if ((need && !workspace) || workspace_bytes < need) {
     set_error("roi_align_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     return B200_ERR_WORKSPACE;
@@ -216,10 +222,10 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
     roi_bwd_tables_kernel<<<R, 64, 0, st>>>(rois, t, H, W, pooled_h, pooled_w, spatial_scale, sampling_ratio, aligned);
     B200_CUDA_LAUNCH_CHECK("roi_bwd_tables");
     if (grad_out_layout == B200_NCHW) {
-      int rc = dispatch_affine(grad_out, nullptr, nullptr, 1.0f, p, R, C, pooled_h, pooled_w, dtype, B200_NCHW, dtype, B200_NHWC, st);
+      int rc = dispatch_affine(grad_out, nullptr, nullptr, 1.0f, p, R, C, pho, pwo, dtype, B200_NCHW, dtype, B200_NHWC, st);
       if (rc != B200_OK) return rc;
       g = p;
-      p += align_up((size_t)R * C * pooled_h * pooled_w * e, 256);
+      p += align_up((size_t)R * C * pho * pwo * e, 256);
     }
   }
   void* gf = grad_in_layout == B200_NCHW ? (void*)p : grad_feat;
@@ -229,11 +235,11 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
   if (dtype == B200_F32) {
     auto k = roi_align_bwd_nhwc_kernel<float>;
     if (smem > 40 * 1024) B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kBwdWarps * 32, smem, st>>>((const float*)g, roi_batch_offsets, t, (float*)gf, C, H, W, pooled_h, pooled_w);
+    k<<<grid, kBwdWarps * 32, smem, st>>>((const float*)g, roi_batch_offsets, t, (float*)gf, C, H, W, pooled_h, pooled_w, bin_step);
   } else {
     auto k = roi_align_bwd_nhwc_kernel<__nv_bfloat16>;
     if (smem > 40 * 1024) B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kBwdWarps * 32, smem, st>>>((const __nv_bfloat16*)g, roi_batch_offsets, t, (__nv_bfloat16*)gf, C, H, W, pooled_h, pooled_w);
+    k<<<grid, kBwdWarps * 32, smem, st>>>((const __nv_bfloat16*)g, roi_batch_offsets, t, (__nv_bfloat16*)gf, C, H, W, pooled_h, pooled_w, bin_step);
   }
   B200_CUDA_LAUNCH_CHECK("roi_align_bwd");
   if (grad_in_layout == B200_NCHW)

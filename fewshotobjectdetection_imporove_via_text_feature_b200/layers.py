@@ -115,8 +115,20 @@ class BottleneckBlock(nn.Module):
         out += sc
         return F.relu_(out)
 
-    def forward_folded(self, x):
-        """Eval-only: FrozenBN folded into the conv weights, cached per (dtype, layout, parameter versions)."""
+    def reads_strided_1x1(self):
+        """True when this block only ever reads every `stride`-th pixel of its input: conv1 and the shortcut are both
+        1x1 convolutions carrying the stride (RESNETS.STRIDE_IN_1X1=True).  The pooler can then skip the dead bins."""
+        s = (self.stride, self.stride)
+        return (self.stride > 1 and self.shortcut is not None and self.conv1.kernel_size == (1, 1) and
+                self.shortcut.kernel_size == (1, 1) and self.conv1.stride == s and self.shortcut.stride == s and
+                self.conv1.padding == (0, 0) and self.shortcut.padding == (0, 0))
+
+    def forward_folded(self, x, prestrided=False):
+        """Frozen-weights path: FrozenBN folded into the conv weights, cached per (dtype, layout, parameter versions).
+        prestrided: `x` already holds only the pixels [::stride, ::stride] (see `reads_strided_1x1`), so conv1 and
+        the shortcut run with stride 1 — same numbers, 1/stride^2 of the input."""
+        s1 = (1, 1) if prestrided else self.conv1.stride
+        ssc = (1, 1) if (prestrided or self.shortcut is None) else self.shortcut.stride
         convs = [self.conv1, self.conv2, self.conv3, self.shortcut]
         cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
         key = (x.dtype, cl, x.device) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs if c is not None)
@@ -126,22 +138,22 @@ class BottleneckBlock(nn.Module):
         (w1, b1), (w2, b2), (w3, b3), sc = self._fold
         if _FUSED_CONV["ok"] and x.is_cuda and not torch.is_grad_enabled():
             try:   # cuDNN runtime-fused conv + bias + ReLU (+ residual add): no separate elementwise kernels
-                out = torch.cudnn_convolution_relu(x, w1, b1, self.conv1.stride, (0, 0), (1, 1), 1)
+                out = torch.cudnn_convolution_relu(x, w1, b1, s1, (0, 0), (1, 1), 1)
                 out = torch.cudnn_convolution_relu(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups)
                 # the shortcut's (folded-BN) bias rides on conv3's fused bias: a biased F.conv2d would add it with a
                 # separate broadcast-add kernel over the whole (R,2048,4,4) tensor (ncu: 297 us of a 2.7 ms step)
                 if sc is None:
                     res, bias3 = x, b3
                 else:
-                    res = F.conv2d(x, sc[0], None, self.shortcut.stride)
+                    res = F.conv2d(x, sc[0], None, ssc)
                     bias3 = b3 if sc[1] is None else b3 + sc[1]
                 return torch.cudnn_convolution_add_relu(out, w3, res, 1.0, bias3, (1, 1), (0, 0), (1, 1), 1)
             except RuntimeError:
                 _FUSED_CONV["ok"] = False
-        out = F.relu_(F.conv2d(x, w1, b1, self.conv1.stride))
+        out = F.relu_(F.conv2d(x, w1, b1, s1))
         out = F.relu_(F.conv2d(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups))
         out = F.conv2d(out, w3, b3)
-        out += x if sc is None else F.conv2d(x, sc[0], sc[1], self.shortcut.stride)
+        out += x if sc is None else F.conv2d(x, sc[0], sc[1], ssc)
         return F.relu_(out)
 
 

@@ -21,9 +21,10 @@ class ROIPooler(nn.Module):
         self.sampling_ratio, self.aligned = int(sampling_ratio), pooler_type == "ROIAlignV2"
         self.channels_last_out = channels_last_out
 
-    def forward(self, x, box_lists):
+    def forward(self, x, box_lists, bin_step=1):
+        """bin_step=s returns only the bins [::s, ::s] of the pooled map (dead-bin skipping for a stride-s consumer)."""
         assert isinstance(x, list) and len(x) == 1, "ROIPooler expects a single-level feature list"
         tensors = [b.tensor if isinstance(b, Boxes) or hasattr(b, "tensor") else b for b in box_lists]
         rois, offsets = ops.boxes_to_rois(tensors)
         return ops.roi_align(x[0], rois, self.output_size, self.scale, self.sampling_ratio, self.aligned,
-                             self.channels_last_out, offsets)
+                             self.channels_last_out, offsets, bin_step)

@@ -119,6 +119,7 @@ class Res5ROIHeads(ROIHeads):
         assert not cfg.MODEL.KEYPOINT_ON
         self.channels_last = bool(b200_opt(cfg, "CHANNELS_LAST", True))
         self.res5_dtype = getattr(torch, b200_opt(cfg, "RES5_DTYPE", "bfloat16"))
+        self.skip_dead_bins = bool(b200_opt(cfg, "SKIP_DEAD_BINS", True))
         self.pooler = ROIPooler(output_size=bh.POOLER_RESOLUTION, scales=(1.0 / self.feature_strides[self.in_features[0]],),
                                 sampling_ratio=bh.POOLER_SAMPLING_RATIO, pooler_type=bh.POOLER_TYPE,
                                 channels_last_out=self.channels_last)
@@ -136,18 +137,26 @@ class Res5ROIHeads(ROIHeads):
                             num_groups=r.NUM_GROUPS, norm=r.NORM, stride_in_1x1=r.STRIDE_IN_1X1)
         return nn.Sequential(*blocks), out_channels
 
-    def _res5_forward(self, x):
+    def _res5_forward(self, x, prestrided=False):
         """res5 stays on cuDNN.  Unless its weights are being trained, FrozenBN is folded into
         the convolutions and the stage runs in `res5_dtype` channels-last; gradients still flow to `x`."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.res5.parameters()):
+        if self._res5_trainable():
             return self.res5(x)
         y = x.to(self.res5_dtype)
-        for blk in self.res5:
-            y = blk.forward_folded(y)
+        for i, blk in enumerate(self.res5):
+            y = blk.forward_folded(y, prestrided=prestrided and i == 0)
         return y
 
+    def _res5_trainable(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.res5.parameters())
+
     def _shared_roi_transform(self, features, boxes):
-        return self._res5_forward(self.pooler(features, boxes))
+        # res5's first block reads the 7x7 pooled map through 1x1 stride-2 convolutions only (roi_heads.py:313-337 with
+        # RESNETS.STRIDE_IN_1X1): 33 of 49 bins are dead.  On the frozen path the pooler emits just the live bins.
+        blk0 = self.res5[0]
+        skip = (self.skip_dead_bins and not self._res5_trainable() and blk0.reads_strided_1x1())
+        step = blk0.stride if skip else 1
+        return self._res5_forward(self.pooler(features, boxes, bin_step=step), prestrided=skip)
 
     def _pooled(self, features, proposals):
         box_features = self._shared_roi_transform([features[f] for f in self.in_features],

@@ -120,35 +120,36 @@ def gdl_affine(x, weight=None, bias=None, lam=1.0, out_dtype=None, channels_last
 class _ROIAlign(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, rois, roi_batch_offsets, output_size, spatial_scale, sampling_ratio, aligned,
-                channels_last_out):
+                channels_last_out, bin_step):
         _require_cuda(feat, rois)
         in_layout, feat = _layout4(feat)
         rois = rois.detach().float().contiguous()
         N, C, H, W = feat.shape
         R = rois.shape[0]
         PH, PW = output_size
-        out = _empty4(R, C, PH, PW, feat.dtype, feat.device, channels_last_out)
-        nbytes = _lib.lib().b200_roi_align_fwd_workspace_bytes(N, C, H, W, _dt(feat), in_layout)
+        out = _empty4(R, C, -(-PH // bin_step), -(-PW // bin_step), feat.dtype, feat.device, channels_last_out)
+        nbytes = _lib.lib().b200_roi_align_fwd_workspace_bytes(N, C, H, W, R, _dt(feat), in_layout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device) if nbytes else None
         ev = KERNEL_EVENTS.get("roi_align_fwd") if KERNEL_EVENTS else None
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.call("b200_roi_align_fwd", feat.data_ptr(), rois.data_ptr(), out.data_ptr(), N, C, H, W, R, PH, PW,
-                  float(spatial_scale), int(sampling_ratio), int(bool(aligned)), _dt(feat), in_layout,
-                  NHWC if channels_last_out else NCHW, _ptr(ws), nbytes, _stream())
+        _lib.call("b200_roi_align_fwd", feat.data_ptr(), rois.data_ptr(), _ptr(roi_batch_offsets), out.data_ptr(), N, C,
+                  H, W, R, PH, PW, int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)), _dt(feat), in_layout,
+                  NHWC if channels_last_out else NCHW, _ptr(ws), nbytes, _stream(),
+                  launches=(in_layout == NCHW) + (2 if _slice_path(feat, roi_batch_offsets, channels_last_out, PH, PW, bin_step) else 1))
         if ev is not None:
             e1.record()
             ev.append((e0, e1))
         ctx.save_for_backward(rois, roi_batch_offsets)
         ctx.meta = (feat.shape, feat.dtype, in_layout, output_size, spatial_scale, sampling_ratio, aligned,
-                    channels_last_out)
+                    channels_last_out, bin_step)
         return out
 
     @staticmethod
     def backward(ctx, g):
         rois, offs = ctx.saved_tensors
-        shape, dtype, in_layout, (PH, PW), scale, sr, aligned, cl_out = ctx.meta
+        shape, dtype, in_layout, (PH, PW), scale, sr, aligned, cl_out, bin_step = ctx.meta
         if offs is None:
             raise _lib.B200Error("roi_align backward needs roi_batch_offsets (ROIs grouped by image)")
         N, C, H, W = shape
@@ -156,22 +157,34 @@ class _ROIAlign(torch.autograd.Function):
         g = g.contiguous(memory_format=torch.channels_last) if cl_out else g.contiguous()
         gin = _empty4(N, C, H, W, dtype, g.device, in_layout == NHWC)
         g_layout = NHWC if cl_out else NCHW
-        nbytes = _lib.lib().b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, PH, PW, _dt(g), in_layout, g_layout)
+        nbytes = _lib.lib().b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, PH, PW, int(bin_step), _dt(g), in_layout,
+                                                               g_layout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
         _lib.call("b200_roi_align_bwd", g.data_ptr(), rois.data_ptr(), offs.data_ptr(), gin.data_ptr(), N, C, H, W, R,
-                  PH, PW, float(scale), int(sr), int(bool(aligned)), _dt(g), g_layout, in_layout, ws.data_ptr(), nbytes,
-                  _stream())
-        return gin, None, None, None, None, None, None, None
+                  PH, PW, int(bin_step), float(scale), int(sr), int(bool(aligned)), _dt(g), g_layout, in_layout,
+                  ws.data_ptr(), nbytes, _stream())
+        return gin, None, None, None, None, None, None, None, None
+
+
+def _slice_path(feat, offs, cl_out, PH, PW, bin_step):
+    """Mirror of the dispatch in csrc/roi_align.cu (for launch accounting only): the slice-resident kernel runs
+    prepare + main."""
+    if offs is None or feat.dtype != torch.bfloat16 or not cl_out or (PH, PW) != (7, 7) or bin_step not in (1, 2):
+        return False
+    N, C, H, W = feat.shape
+    Wp = (W + 7) & ~7
+    return C % 32 == 0 and H <= 256 and W <= 248 and H * Wp * 64 + 16 * 2 * 1024 + 16 * 3584 + 1024 <= 227 * 1024
 
 
 def roi_align(feat, rois, output_size, spatial_scale, sampling_ratio=0, aligned=True, channels_last_out=False,
-              roi_batch_offsets=None):
+              roi_batch_offsets=None, bin_step=1):
     """torchvision.ops.roi_align semantics.  feat (N,C,H,W) NCHW or channels_last, fp32|bf16; rois (R,5).
-    roi_batch_offsets: int32 (N+1) prefix of per-image ROI counts — required for backward."""
+    roi_batch_offsets: int32 (N+1) prefix of per-image ROI counts (ROIs grouped by image) — required for backward
+    and for the slice-resident bf16 kernel.  bin_step=s returns only the bins [::s, ::s] of the pooled map."""
     if isinstance(output_size, int):
         output_size = (output_size, output_size)
     return _ROIAlign.apply(feat, rois, roi_batch_offsets, tuple(output_size), spatial_scale, sampling_ratio, aligned,
-                           channels_last_out)
+                           channels_last_out, int(bin_step))
 
 
 _INDEX_CACHE = {}

@@ -42,7 +42,8 @@ enum { B200_NCHW = 0, B200_NHWC = 1 };
 B200_API int b200_abi_version(void);
 B200_API const char* b200_last_error(void);
 /* process-wide implementation switches (for A/B measurement; results are parity-tested under every setting):
- *   "roi_align_bf16_impl": 0 = CUDA-core per-bin-window kernel (default), 1 = TMA + ldmatrix + mma.sync kernel */
+ *   "roi_align_bf16_impl": 0 = CUDA-core per-bin-window kernel, 1 = per-ROI TMA + ldmatrix + mma.sync kernel,
+ *                          2 = slice-resident TMA + ldmatrix + mma.sync kernel (default; needs roi_batch_offsets) */
 B200_API int b200_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -67,19 +68,26 @@ B200_API int b200_gdl_affine_bwd(const void* grad_y, const void* x, const float*
  *   replaces the call at defrcn/modeling/roi_heads/roi_heads.py:300-305,339-340 and
  *   defrcn/evaluation/calibration_layer.py:27,100.
  *   feat (N,C,H,W) in (dtype,in_layout); rois (R,5) fp32 [batch_idx,x1,y1,x2,y2] in image coordinates;
- *   out (R,C,PH,PW) in (dtype,out_layout).  sampling_ratio<=0 is the adaptive ceil(roi/pooled) grid.
- *   The workspace holds an NHWC copy of the map when in_layout==NCHW (0 bytes otherwise).
+ *   out (R,C,PHO,PWO) in (dtype,out_layout), PHO = ceil(pooled_h / bin_step).  sampling_ratio<=0 is the adaptive
+ *   ceil(roi/pooled) grid.
+ *   bin_step (>=1): compute and store only the bins (0, step, 2*step, ...) of each axis.  bin_step = 2 with 7x7
+ *   pooling is what res5 actually consumes: its first block reads the pooled map through 1x1 stride-2 convolutions
+ *   (roi_heads.py:313-337, RESNETS.STRIDE_IN_1X1=True), so 33 of the 49 bins are never read.  1 = the reference op.
+ *   roi_batch_offsets (N+1 int32, device; may be NULL in fwd): prefix of per-image ROI counts when the ROIs are
+ *   grouped by image (as detectron2's convert_boxes_to_pooler_format produces them).  Given it, bf16 channels-last
+ *   7x7 pooling runs the slice-resident tensor-core kernel (csrc/roi_align_slice.cu); without it, the per-ROI kernel.
+ *   The workspace holds an NHWC copy of the map when in_layout==NCHW plus, for bf16, R geometry records.
  *   bwd is atomic-free and deterministic: grad_feat is fully overwritten (no pre-zeroing needed).
  * ------------------------------------------------------------------------------------------------- */
-B200_API size_t b200_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int dtype, int in_layout);
-B200_API int b200_roi_align_fwd(const void* feat, const float* rois, void* out, int N, int C, int H, int W, int R,
-                       int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
-                       int dtype, int in_layout, int out_layout, void* workspace, size_t workspace_bytes,
-                       b200_stream_t stream);
+B200_API size_t b200_roi_align_fwd_workspace_bytes(int N, int C, int H, int W, int R, int dtype, int in_layout);
+B200_API int b200_roi_align_fwd(const void* feat, const float* rois, const int32_t* roi_batch_offsets, void* out, int N,
+                       int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step, float spatial_scale,
+                       int sampling_ratio, int aligned, int dtype, int in_layout, int out_layout, void* workspace,
+                       size_t workspace_bytes, b200_stream_t stream);
 B200_API size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
-                                          int dtype, int grad_in_layout, int grad_out_layout);
+                                          int bin_step, int dtype, int grad_in_layout, int grad_out_layout);
 B200_API int b200_roi_align_bwd(const void* grad_out, const float* rois, const int32_t* roi_batch_offsets,
-                       void* grad_feat, int N, int C, int H, int W, int R, int pooled_h, int pooled_w,
+                       void* grad_feat, int N, int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step,
                        float spatial_scale, int sampling_ratio, int aligned, int dtype, int grad_out_layout,
                        int grad_in_layout, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 

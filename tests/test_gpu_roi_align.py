@@ -51,25 +51,96 @@ def test_fwd_fp32(N, C, H, W, R, P, scale, sr, aligned, cl_in, cl_out):
     (1, 64, 50, 84, 30, 7, 1 / 16, 0),         # 800x1333 map: wide windows
     (1, 64, 20, 20, 24, 7, 1 / 16, 2),         # fixed sampling ratio (falls back to the per-sample path when sparse)
 ])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_fwd_bf16(N, C, H, W, R, P, scale, sr, impl):
     """bf16 storage.  impl 0: CUDA-core per-bin-window kernel; impl 1: TMA + ldmatrix + mma.sync tensor-core kernel
     (taken for channels-last output; NCHW output always runs the CUDA-core kernel)."""
     from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
-    x, rois, _ = _inputs(N, C, H, W, R, scale, 3)
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 3)
     xb = x.to(torch.bfloat16)
     ref = O.roi_align_fwd(xb.float(), rois, P, scale, sr, True)
     _lib.set_option("roi_align_bf16_impl", impl)
     try:
         for cl in (False, True):
             xd = xb.cuda().contiguous(memory_format=torch.channels_last) if cl else xb.cuda()
-            out = ops.roi_align(xd, rois.cuda(), P, scale, sr, True, channels_last_out=cl)
+            out = ops.roi_align(xd, rois.cuda(), P, scale, sr, True, channels_last_out=cl,
+                                roi_batch_offsets=offs.cuda() if impl == 2 else None)
             assert out.dtype == torch.bfloat16
             got = out.float().cpu().contiguous()
             torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
             assert float((got - ref).norm() / ref.norm()) < 5e-3      # well inside the 2e-2 bar on aggregate
     finally:
-        _lib.set_option("roi_align_bf16_impl", 0)
+        _lib.set_option("roi_align_bf16_impl", 2)
+
+
+@pytest.mark.parametrize("N,C,H,W,R,scale", [
+    (2, 64, 38, 50, 90, 1 / 16),
+    (3, 32, 25, 32, 61, 1 / 16),        # odd map width -> padded row pitch; one image gets fewer ROIs
+    (1, 1024, 38, 50, 40, 1 / 16),      # all 32 channel slices, more CTAs than ROIs per slice
+    (2, 96, 50, 84, 50, 1 / 16),        # 800x1333 map still fits the resident slice at 32 channels? (falls back if not)
+])
+@pytest.mark.parametrize("bin_step", [1, 2])
+def test_fwd_bf16_slice_resident(N, C, H, W, R, scale, bin_step):
+    """Slice-resident tensor-core kernel (roi_align_slice.cu): taken for bf16 channels-last 7x7 pooling when the
+    per-image ROI offsets are given.  bin_step=2 must equal the full result at bins [::2, ::2]."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 13)
+    xb = x.to(torch.bfloat16)
+    ref = O.roi_align_fwd(xb.float(), rois, 7, scale, 0, True)[:, :, ::bin_step, ::bin_step].contiguous()
+    xd = xb.cuda().contiguous(memory_format=torch.channels_last)
+    out = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda(),
+                        bin_step=bin_step)
+    assert out.shape == ref.shape and out.dtype == torch.bfloat16
+    got = out.float().cpu().contiguous()
+    torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2)
+    assert float((got - ref).norm() / ref.norm()) < 5e-3
+    # same numbers as the per-ROI CUDA-core kernel up to bf16 rounding of the weights
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+    _lib.set_option("roi_align_bf16_impl", 0)
+    try:
+        base = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=True, bin_step=bin_step)
+    finally:
+        _lib.set_option("roi_align_bf16_impl", 2)
+    torch.testing.assert_close(out.float(), base.float(), rtol=2e-2, atol=2e-2)
+
+
+def test_fwd_slice_resident_empty_image_and_fixed_grid():
+    """An image without ROIs in the middle of the batch, and a sparse fixed sampling grid (per-sample fallback inside
+    the slice kernel)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.relu(torch.randn(3, 64, 20, 24, generator=gen)).to(torch.bfloat16)
+    b0 = synth_proposals(17, 320, 384, gen)[0]
+    b2 = synth_proposals(9, 320, 384, gen)[0]
+    rois = O.boxes_to_rois([b0, b0[:0], b2])
+    offs = torch.tensor([0, 17, 17, 26], dtype=torch.int32)
+    xd = x.cuda().contiguous(memory_format=torch.channels_last)
+    for sr in (0, 1, 2):
+        ref = O.roi_align_fwd(x.float(), rois, 7, 1 / 16, sr, True)
+        out = ops.roi_align(xd, rois.cuda(), 7, 1 / 16, sr, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+        torch.testing.assert_close(out.float().cpu().contiguous(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_bwd_bin_step(cl):
+    """Backward of the dead-bin-skipping pooler == full backward with zero gradient on the skipped bins."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    N, C, H, W, R, scale = 2, 32, 24, 31, 70, 1 / 16
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 17)
+    g = torch.randn(R, C, 4, 4, generator=torch.Generator().manual_seed(2))
+    gfull = torch.zeros(R, C, 7, 7)
+    gfull[:, :, ::2, ::2] = g
+    ref = O.roi_align_bwd(gfull, rois, x.shape, scale, 0, True)
+    xd = x.cuda()
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    xd.requires_grad_(True)
+    out = ops.roi_align(xd, rois.cuda(), 7, scale, 0, True, channels_last_out=cl, roi_batch_offsets=offs.cuda(), bin_step=2)
+    assert out.shape == (R, C, 4, 4)
+    fwd_ref = O.roi_align_fwd(x, rois, 7, scale, 0, True, impl="c")[:, :, ::2, ::2]
+    torch.testing.assert_close(out.detach().cpu().contiguous(), fwd_ref.contiguous(), rtol=1e-5, atol=1e-5)
+    out.backward(g.cuda())
+    torch.testing.assert_close(xd.grad.cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("cl", [False, True])

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""ROIAlign forward microbench on the bench shape (B images x P proposals, 1024 x 38 x 50 bf16 channels-last):
+every implementation x bin_step, CUDA-event timed with an L2 flush between launches."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops  # noqa: E402
+from oracle.gen_golden import synth_proposals  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=8)
+    ap.add_argument("--props", type=int, default=512)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--impls", default="0,2")
+    ap.add_argument("--steps", default="1,2")
+    a = ap.parse_args()
+    B, P, C, H, W = a.images, a.props, 1024, 38, 50
+    dev = torch.device("cuda")
+    feat = torch.relu(torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(0))).to(torch.bfloat16)
+    feat = feat.to(dev).contiguous(memory_format=torch.channels_last)
+    boxes = [synth_proposals(P, 600, 800, torch.Generator().manual_seed(1234 + i), n_obj=8)[0].to(dev) for i in range(B)]
+    rois, offs = ops.boxes_to_rois(boxes)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    outs = {}
+    for step in [int(s) for s in a.steps.split(",")]:
+        nb = -(-7 // step)
+        nbytes = B * C * H * W * 2 + B * P * 20 + B * P * C * nb * nb * 2
+        for impl in [int(s) for s in a.impls.split(",")]:
+            _lib.set_option("roi_align_bf16_impl", impl)
+            ts = []
+            for i in range(a.iters + 3):
+                flush.fill_(i & 255)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = ops.roi_align(feat, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs,
+                                    bin_step=step)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            outs[(step, impl)] = out.float()
+            print("bin_step=%d impl=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
+                  (step, impl, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
+        ks = [k for k in outs if k[0] == step]
+        for k in ks[1:]:
+            d = (outs[k] - outs[ks[0]]).abs().max().item()
+            print("   max |impl %d - impl %d| = %.4g (ref max %.3g)" % (k[1], ks[0][1], d, outs[ks[0]].abs().max().item()))
+    _lib.set_option("roi_align_bf16_impl", 2)
+
+
+if __name__ == "__main__":
+    main()
