@@ -117,7 +117,8 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, float* __restrict__ d_f32, __nv_bfloat16* __restrict__ d_bf16,
-                         int ldd, __nv_bfloat16* __restrict__ d2, int ldd2, int M, int N, int K, int relu) {
+                         int ldd, __nv_bfloat16* __restrict__ d2, int ldd2, int M, int N, int K, int relu,
+                         int accumulate, const __nv_bfloat16* __restrict__ mask, int ldmask) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -204,6 +205,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       if (row < M) {
         const int col = n0 + c0;
         const bool full = col + 32 <= N;
+        if (mask) {   // backward of a ReLU: zero where the forward activation was not positive
+          const __nv_bfloat16* mrow = mask + (size_t)row * ldmask + col;
+          for (int i = 0; i < 32; ++i)
+            if (col + i < N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+        }
+        if (accumulate && d_f32) {   // D += result (gradient accumulation over several producers)
+          const float* src = d_f32 + (size_t)row * ldd + col;
+          for (int i = 0; i < 32; ++i)
+            if (col + i < N) v[i] += src[i];
+        }
         if (d_f32) {
           float* dst = d_f32 + (size_t)row * ldd + col;
           if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -291,7 +302,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld,
 
 template <int BN>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd, int out_dtype,
-                       void* D2, int ldd2, int M, int N, int K, int relu, cudaStream_t st) {
+                       void* D2, int ldd2, int M, int N, int K, int relu, int accumulate, const void* mask, int ldmask,
+                       cudaStream_t st) {
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, M, K, lda, kBM);
   if (rc != B200_OK) return rc;
@@ -306,7 +318,8 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, const flo
   dim3 grid(ceil_div(N, BN), ceil_div(M, kBM));
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ma, mb, bias, out_dtype == B200_F32 ? (float*)D : nullptr,
                                                             out_dtype == B200_BF16 ? (__nv_bfloat16*)D : nullptr, ldd,
-                                                            (__nv_bfloat16*)D2, ldd2, M, N, K, relu);
+                                                            (__nv_bfloat16*)D2, ldd2, M, N, K, relu, accumulate,
+                                                            (const __nv_bfloat16*)mask, ldmask);
   B200_CUDA_LAUNCH_CHECK("gemm_bf16");
   return B200_OK;
 }
@@ -315,11 +328,13 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, const flo
 
 using namespace b200;
 
-extern "C" int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
-                              int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, b200_stream_t stream) {
+extern "C" int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
+                                 int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, int accumulate,
+                                 const void* mask, int ldmask, b200_stream_t stream) {
   B200_CHECK_ARG(A && B && (D || D2), "gemm_bf16: null tensor");
   B200_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_bf16: bad shape");
   B200_CHECK_ARG((out_dtype | 1) == 1, "gemm_bf16: bad out_dtype");
+  B200_CHECK_ARG(!accumulate || (D && out_dtype == B200_F32), "gemm_bf16: accumulate needs an fp32 D");
   if (K % 8 || lda % 8 || ldb % 8 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) {
     set_error("gemm_bf16: K, lda, ldb must be multiples of 8 and A, B 16-byte aligned (TMA)");
     return B200_ERR_UNSUPPORTED;
@@ -335,9 +350,14 @@ extern "C" int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, co
   else if (mt * ceil_div(N, 128) >= 100 || N <= 128) bn = 128;
   else bn = 64;
   switch (bn) {
-    case 32: return launch_gemm<32>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
-    case 64: return launch_gemm<64>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
-    case 128: return launch_gemm<128>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
-    default: return launch_gemm<256>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, st);
+    case 32: return launch_gemm<32>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);
+    case 64: return launch_gemm<64>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);
+    case 128: return launch_gemm<128>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);
+    default: return launch_gemm<256>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);
   }
+}
+
+extern "C" int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
+                              int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, b200_stream_t stream) {
+  return b200_gemm_bf16_ex(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, 0, nullptr, 0, stream);
 }

@@ -166,7 +166,7 @@ class _OutputLayersBase(nn.Module):
         self._w = {}
 
     def _bf16(self, name, p):
-        key = (p.data_ptr(), p._version)
+        key = (p.data_ptr(), p._version, ops.PARAM_GENERATION[0])
         hit = self._w.get(name)
         if hit is None or hit[0] != key:
             hit = (key, p.detach().to(torch.bfloat16).contiguous())

@@ -188,6 +188,7 @@ class SematicRes5ROIHeads(Res5ROIHeads):
             cfg, self.out_channels, self.num_classes, self.cls_agnostic_bbox_reg)
 
     def __init_LV_model__(self, input_size, cfg):
+        self.fused_training = bool(b200_opt(cfg, "FUSED_TRAINING", True))
         self.addition_model = cfg.MODEL.ADDITION.NAME
         self.semantic_dim = SEMANTIC_DIM[self.addition_model]
         self.attention = SematicProposalAttention(input_size, cfg=cfg, is_multi=False)
@@ -235,6 +236,32 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         output_att["pred_logits"], output_att["pred_bbox"] = logits, deltas
         return output_att, loss_att
 
+    _DROP_STEP = [0]
+
+    def fused_train_losses(self, feature_pooled, proposals, gt_classes):
+        """Fine-tune direction on the hand-written kernels (train_ops._FusedHeadTrain): text-fusion chain, predictor
+        with classifier dropout, and the three losses in one autograd node; same numbers as `forward_att` +
+        `FastRCNNOutputs.losses` (roi_heads.py:1060-1132) up to bf16 GEMM operands.  The (K+2)-row text side stays
+        in plain torch: it is ~0.5 % of the FLOPs and its gradients arrive as dKq / dVp."""
+        from ... import train_ops
+        att, sa = self.attention, self.attention.attention
+        d = feature_pooled.shape[1]
+        T = att.forward_language_model()["text_feat"]
+        kt, vt = F.relu(att.key_projection(T)), F.relu(att.value_projection(T))
+        kp = torch.cat([sa.w_k(kt), sa.dummy.reshape(1, -1)], dim=0)
+        vp = torch.cat([sa.w_v(vt), kt.new_zeros(1, d)], dim=0)
+        kq = (kp @ sa.w_q.weight) / float(np.power(d, 0.5))
+        props = cat([p.proposal_boxes.tensor for p in proposals], dim=0)
+        gtb = cat([p.gt_boxes.tensor for p in proposals], dim=0)
+        pred = self.box_predictor
+        drop = pred._dropout_ratio if pred._do_cls_dropout else 0.0
+        self._DROP_STEP[0] += 1
+        seed = (torch.initial_seed() * 1000003 + self._DROP_STEP[0]) & 0x7FFFFFFFFFFFFFFF
+        losses, logits = train_ops.fused_head_train(feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb,
+                                                    self.num_classes, self.box2box_transform.weights, self.smooth_l1_beta,
+                                                    drop, seed, True)
+        return {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}, logits
+
     def forward(self, images, features, proposals, targets=None):
         del images
         test_with_gt = (not self.training) and bool(targets)
@@ -245,6 +272,12 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         elif test_with_gt:
             proposals = self.label_proposals(proposals, targets)
         feature_pooled = self._pooled(features, proposals)
+        if (self.training and torch.is_grad_enabled() and feature_pooled.is_cuda and self.fused_training and
+                type(self).forward_att is SematicRes5ROIHeads.forward_att and
+                type(self.box_predictor).__name__ == "FastRCNNOutputLayers"):
+            losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes)
+            FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy()
+            return [], losses
         att_output, att_loss = self.forward_att(feature_pooled, gt_classes)
         outputs = FastRCNNOutputs(self.box2box_transform, att_output["pred_logits"], att_output["pred_bbox"], proposals,
                                   self.smooth_l1_beta)

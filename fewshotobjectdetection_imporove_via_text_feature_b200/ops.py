@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import BF16, F32, NCHW, NHWC
 
 
+# bumped by optimizers that update parameters in place through a kernel (train_ops.FlatSGD): weight caches key on it
+PARAM_GENERATION = [0]
+
 # bench.py sets KERNEL_EVENTS = {"roi_align_fwd": []} to have CUDA events recorded right around that launch
 KERNEL_EVENTS = {}
 
@@ -390,7 +393,7 @@ class TextFusionWeights:
 
     @staticmethod
     def _version(params):
-        return tuple((p.data_ptr(), p._version) for p in params)
+        return (PARAM_GENERATION[0],) + tuple((p.data_ptr(), p._version) for p in params)
 
     def refresh(self, named, text_parts):
         """`text_parts`: the persistent tensors the text matrix is concatenated from (class embeddings, bg row);

@@ -1,0 +1,250 @@
+"""Fine-tuning direction of the text-fused head on the C-ABI kernels (BASELINE configs[1]).
+
+One `torch.autograd.Function` covers everything between the pooled ROI feature and the three losses:
+  A1..A6 (attentive_modules.py:114-177,262-294), C1 with classifier dropout (fast_rcnn.py:403-417), and L1
+  (fast_rcnn.py:222-304 `FastRCNNOutputs.losses`, roi_heads.py:1077-1081 `loss_attentive`).
+Forward is the same tcgen05 GEMM chain as inference (bf16 operands, fp32 accumulate) with the activations kept for
+the backward pass; backward is hand-scheduled: every `dX = dY W` and `dW = dY^T X` is the same GEMM kernel fed with
+transposed bf16 copies (both of its operands are K-contiguous), ReLU backward rides on the GEMM epilogue (`mask`),
+fan-in of gradients on `accumulate`, bias gradients on ordered column sums.  PyTorch supplies memory, the stream
+and the autograd plumbing only; the tiny text-side projections (K+2 rows) stay in plain torch upstream of this
+function and receive `dKq`, `dVp` from it.
+"""
+import torch
+
+from . import _lib
+from . import ops as ops_mod
+from ._lib import BF16, F32
+from .ops import (_dt, _ptr, _require_cuda, _stream, cast_bf16_into, gemm_bf16, residual_layernorm, text_attention)
+
+
+def _rup(n, m=8):
+    return (n + m - 1) // m * m
+
+
+def gemm_ex(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, out2=None, accumulate=False, mask=None):
+    """out[M,N] (+)= act(a[M,K] @ b[N,K]^T + bias), optionally zeroed where mask <= 0 (ReLU backward)."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K, (a.shape, b.shape)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1 and tuple(out.shape) == (M, N)
+    if mask is not None:
+        assert mask.dtype == torch.bfloat16 and tuple(mask.shape) == (M, N) and mask.stride(1) == 1
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    _lib.call("b200_gemm_bf16_ex", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
+              out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu),
+              int(accumulate), _ptr(mask), 0 if mask is None else mask.stride(0), _stream())
+    return out
+
+
+def transpose_bf16(src, pad_rows_to=None):
+    """(rows, cols) fp32|bf16 with unit inner stride -> bf16 (cols[, padded], rup8(rows)); padding is zero so the
+    result can be used directly as a K-contiguous GEMM operand with K = rup8(rows)."""
+    rows, cols = src.shape
+    assert src.stride(1) == 1
+    ld = _rup(rows)
+    orow = cols if pad_rows_to is None else max(cols, pad_rows_to)
+    if ld != rows or orow != cols:
+        dst = torch.zeros((orow, ld), dtype=torch.bfloat16, device=src.device)
+    else:
+        dst = torch.empty((orow, ld), dtype=torch.bfloat16, device=src.device)
+    _lib.call("b200_transpose_bf16", src.data_ptr(), _dt(src), src.stride(0), dst.data_ptr(), ld, rows, cols, _stream())
+    return dst
+
+
+def colsum(src, n=None):
+    rows, cols = src.shape
+    out = torch.empty(cols, dtype=torch.float32, device=src.device)
+    nbytes = _lib.lib().b200_colsum_workspace_bytes(cols)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+    _lib.call("b200_colsum", src.data_ptr(), _dt(src), src.stride(0), rows, cols, out.data_ptr(), 0, ws.data_ptr(), nbytes,
+              _stream())
+    return out if n is None else out[:n]
+
+
+def dropout_bf16(x, p, seed):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("b200_dropout_fwd", x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), _stream())
+    return y
+
+
+def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weights, beta):
+    R = logits.shape[0]
+    out = torch.empty(3, dtype=torch.float32, device=logits.device)
+    agnostic = deltas.shape[1] == 4 and K != 1
+    _lib.call("b200_head_losses", logits.data_ptr(), deltas.data_ptr(), _ptr(attn), gt_classes.data_ptr(),
+              proposals.data_ptr(), gt_boxes.data_ptr(), R, K, 0 if attn is None else attn.shape[1], int(agnostic),
+              *map(float, weights), float(beta), out.data_ptr(), _stream())
+    return out
+
+
+class _FusedHeadTrain(torch.autograd.Function):
+    """(x, kq, vp, weights..., labels) -> (losses (3,), logits (R,K+1) [non-differentiable, for logging])."""
+
+    @staticmethod
+    def forward(ctx, x, kq, vp, W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb,
+                gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss):
+        _require_cuda(x, kq, vp, W1, W3, Wc, Wb, gt_classes, proposals, gt_boxes)
+        x = x.detach().float().contiguous()
+        R, d = x.shape
+        h = d // 2
+        dev = x.device
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        W = dict(W1=bf(W1), W2=bf(W2), W3=bf(W3), Wf1=bf(Wf1), Wf2=bf(Wf2), Wc=bf(Wc), Wb=bf(Wb), kq=bf(kq))
+        vpf, gam, bet = f32(vp), f32(gamma), f32(beta)
+        gt = gt_classes.detach().to(torch.int64).contiguous()
+        props, gtb = f32(proposals), f32(gt_boxes)
+
+        xcat = torch.empty((R, 2 * d), dtype=torch.bfloat16, device=dev)          # [o1 | o2 | x]
+        xb = cast_bf16_into(x, xcat[:, d:])
+        S = gemm_bf16(xb, W["kq"])                                                 # scaled scores (R, L)
+        p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        attn = text_attention(None, x, None, vpf, p1, p2, scores=S)
+        gemm_bf16(p1, W["W1"], b1, relu=True, out=xcat[:, :h])
+        gemm_bf16(p2, W["W2"], b2, relu=True, out=xcat[:, h:d])
+        yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        y = gemm_bf16(xcat, W["W3"], b3, out2=yb)
+        hdn = gemm_bf16(yb, W["Wf1"], bf1, relu=True, out_dtype=torch.bfloat16)
+        y2 = gemm_bf16(hdn, W["Wf2"], bf2)
+        z, _ = residual_layernorm(y, y2, gam, bet, 1e-5, relu=True, want_f32=True, want_bf16=False)
+        zd = dropout_bf16(z, drop_p, seed)
+        logits = gemm_bf16(zd, W["Wc"], bc)
+        deltas = gemm_bf16(xb, W["Wb"], bb)
+        losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
+        ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
+                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
+        ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
+        ctx.mark_non_differentiable(logits)
+        return losses, logits
+
+    @staticmethod
+    def backward(ctx, g_losses, _g_logits):
+        (x, xcat, p1, p2, attn, vp, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
+         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors
+        K, box_w, l1_beta, drop_p, seed, want_attn = ctx.meta
+        R, d = x.shape
+        h = d // 2
+        L = attn.shape[1]
+        C1, C4 = logits.shape[1], deltas.shape[1]
+        C1p, C4p, Lp = _rup(C1), _rup(C4), _rup(L)
+        dev = x.device
+        st = _stream()
+        g3 = g_losses.detach().float().contiguous()
+
+        # ---- L1 backward ------------------------------------------------------------------------------------
+        dlogits = torch.empty((R, C1p), dtype=torch.bfloat16, device=dev)
+        ddeltas = torch.empty((R, C4p), dtype=torch.bfloat16, device=dev)
+        dattn = torch.empty((R, L), dtype=torch.float32, device=dev) if want_attn else None
+        agnostic = C4 == 4 and K != 1
+        _lib.call("b200_head_losses_bwd", logits.data_ptr(), deltas.data_ptr(), attn.data_ptr() if want_attn else 0,
+                  gt.data_ptr(), props.data_ptr(), gtb.data_ptr(), g3.data_ptr(), R, K, L, int(agnostic),
+                  *map(float, box_w), float(l1_beta), dlogits.data_ptr(), C1p, ddeltas.data_ptr(), C4p, _ptr(dattn), st)
+
+        xcatT = transpose_bf16(xcat)                       # (2d, Rp): rows [d, 2d) are x^T
+        xbT = xcatT[d:]
+        # ---- C1: logits = zd Wc^T + bc ; deltas = xb Wb^T + bb -------------------------------------------------
+        dlogitsT, ddeltasT = transpose_bf16(dlogits), transpose_bf16(ddeltas)
+        dzd = gemm_ex(dlogits, _wT(Wc, C1p), out_dtype=torch.bfloat16)
+        dWc = gemm_ex(dlogitsT, transpose_bf16(zd))[:C1]
+        dbc = colsum(dlogits, C1)
+        dx = gemm_ex(ddeltas, _wT(Wb, C4p))                                        # first producer of dL/dx (fp32)
+        dWb = gemm_ex(ddeltasT, xbT)[:C4]
+        dbb = colsum(ddeltas, C4)
+        # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
+        du = torch.empty((R, d), dtype=torch.float32, device=dev)
+        dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        dgamma = torch.empty(d, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+        nb = _lib.lib().b200_layernorm_bwd_workspace_bytes(R, d)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.call("b200_layernorm_relu_dropout_bwd", dzd.data_ptr(), y.data_ptr(), y2.data_ptr(), gam.data_ptr(),
+                  bet.data_ptr(), 1e-5, float(drop_p), int(seed), du.data_ptr(), dub.data_ptr(), dgamma.data_ptr(),
+                  dbeta.data_ptr(), R, d, ws.data_ptr(), nb, st)
+        # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
+        dubT = transpose_bf16(dub)
+        dhdn = gemm_ex(dub, _wT(Wf2, d), out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
+        dWf2 = gemm_ex(dubT, transpose_bf16(hdn))
+        dbf2 = colsum(du)
+        dyb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        gemm_ex(dhdn, _wT(Wf1, Wf1.shape[0]), out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
+        dWf1 = gemm_ex(transpose_bf16(dhdn), transpose_bf16(yb))
+        dbf1 = colsum(dhdn)
+        # ---- linear3: y = [o1 | o2 | xb] W3^T + b3 -----------------------------------------------------------
+        W3T = _wT(W3, d)                                                           # (2d, d)
+        do12 = gemm_ex(dyb, W3T[:d], out_dtype=torch.bfloat16, mask=xcat[:, :d])   # [do1 | do2], ReLU backward fused
+        gemm_ex(dyb, W3T[d:], out=dx, accumulate=True)
+        dW3 = gemm_ex(transpose_bf16(dyb), xcatT)
+        db3 = colsum(du)
+        # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
+        do12T = transpose_bf16(do12)
+        dp1 = gemm_ex(do12[:, :h], _wT(W1, h), out_dtype=torch.bfloat16)
+        dp2 = gemm_ex(do12[:, h:], _wT(W2, h), out_dtype=torch.bfloat16)
+        dW1 = gemm_ex(do12T[:h], transpose_bf16(p1))
+        dW2 = gemm_ex(do12T[h:], transpose_bf16(p2))
+        db12 = colsum(do12)
+        # ---- A3 core: P1 = O * x, P2 = x - O, O = softmax(S) Vp ------------------------------------------------
+        dO = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        dS = torch.empty((R, Lp), dtype=torch.bfloat16, device=dev)
+        _lib.call("b200_text_attention_bwd", dp1.data_ptr(), dp2.data_ptr(), dp1.stride(0), x.data_ptr(), attn.data_ptr(),
+                  vp.data_ptr(), _ptr(dattn), dx.data_ptr(), 1, dO.data_ptr(), dS.data_ptr(), Lp, R, d, L, st)
+        dvp = gemm_ex(transpose_bf16(attn), transpose_bf16(dO))                    # (L, d)
+        # ---- scores: S = xb Kq^T ----------------------------------------------------------------------------------
+        gemm_ex(dS, _wT(kq, Lp), out=dx, accumulate=True)
+        dkq = gemm_ex(transpose_bf16(dS), xbT)[:L]
+        return (dx, dkq, dvp, dW1, db12[:h], dW2, db12[h:], dW3, db3, dWf1, dbf1, dWf2, dbf2, dgamma, dbeta, dWc, dbc,
+                dWb, dbb) + (None,) * 9
+
+
+def _wT(w, k_pad):
+    """W (N, K) bf16 -> W^T as a K-contiguous GEMM operand: (K, rup8(N)) zero padded; k_pad is the contraction size the
+    consumer uses (== rup8(N))."""
+    t = transpose_bf16(w)
+    assert t.shape[1] == k_pad, (t.shape, k_pad)
+    return t
+
+
+def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed,
+                     want_attn_loss=True):
+    """att: SingleHeadSiameseAttention (parameters linear1/2/3, ffn.*), predictor: FastRCNNOutputLayers."""
+    return _FusedHeadTrain.apply(
+        x, kq, vp, att.linear1[0].weight, att.linear1[0].bias, att.linear2[0].weight, att.linear2[0].bias,
+        att.linear3.weight, att.linear3.bias, att.ffn.linear1.weight, att.ffn.linear1.bias, att.ffn.linear2.weight,
+        att.ffn.linear2.bias, att.ffn.norm3.weight, att.ffn.norm3.bias, predictor.cls_score.weight,
+        predictor.cls_score.bias, predictor.bbox_pred.weight, predictor.bbox_pred.bias, gt_classes, proposals, gt_boxes,
+        K, box_weights, l1_beta, drop_p, seed, want_attn_loss)
+
+
+class FlatSGD:
+    """SGD + momentum over one flat fp32 buffer that the parameters are re-pointed into (one kernel per step;
+    torch.optim.SGD semantics as configured by defrcn/solver/build.py: momentum 0.9, weight decay, no dampening)."""
+
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p.data)
+            p.grad = self.grad[off:off + k].view_as(p.data)
+            off += k
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self):
+        _lib.call("b200_sgd_momentum", self.flat.data_ptr(), self.grad.data_ptr(), self.mom.data_ptr(), self.flat.numel(),
+                  float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
+        ops_mod.PARAM_GENERATION[0] += 1     # the bf16 weight caches key on this (in-place kernel updates bypass _version)

@@ -154,6 +154,58 @@ B200_API int b200_pcb_cosine_blend(float* scores, const float* feats, const floa
 B200_API int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
                    int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, b200_stream_t stream);
 
+/* b200_gemm_bf16 with two backward-pass epilogue options:
+ *   accumulate != 0 : D (fp32) += result  — several producers add into one gradient buffer (e.g. dL/dx);
+ *   mask (bf16, same shape as D, row stride ldmask) : result is zeroed where mask <= 0 — the ReLU backward of the
+ *   layer whose forward activation `mask` is (attentive_modules.py:166-171, :72). */
+B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
+                      int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, int accumulate,
+                      const void* mask, int ldmask, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fine-tuning direction (BASELINE configs[1]): what autograd does for the reference's torch modules.
+ * All reductions are fixed-order (deterministic); gradients feed the GEMM as bf16, accumulate in fp32.
+ * ------------------------------------------------------------------------------------------------- */
+/* dst[c][r] = bf16(src[r][c]) — operand preparation for the weight-gradient GEMMs dW = dY^T X (both operands
+ * of b200_gemm_bf16 are K-contiguous, so dY^T and X^T are materialised) and for dX = dY W (W^T). */
+B200_API int b200_transpose_bf16(const void* src, int src_dtype, int ld_src, void* dst, int ld_dst, int rows, int cols,
+                        b200_stream_t stream);
+/* out[c] (+)= sum_r src[r][c] — bias gradients (two-pass, ordered) */
+B200_API size_t b200_colsum_workspace_bytes(int cols);
+B200_API int b200_colsum(const void* src, int src_dtype, int ld, int rows, int cols, float* out, int accumulate,
+                void* workspace, size_t workspace_bytes, b200_stream_t stream);
+/* classifier dropout (fast_rcnn.py:412-414): y = bf16(keep ? x / (1-p) : 0), keep = hash(seed, index) >= p*2^32.
+ * The mask is never stored: the backward kernel re-evaluates the hash. */
+B200_API int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed, b200_stream_t stream);
+/* backward of zd = dropout(relu(LayerNorm(y + y2))) (attentive_modules.py:73-74,285): du = dL/d(y + y2) as fp32
+ * and/or bf16, dgamma / dbeta (may be NULL). */
+B200_API size_t b200_layernorm_bwd_workspace_bytes(int R, int d);
+B200_API int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float* y, const float* y2, const float* gamma,
+                                    const float* beta, float eps, float p, unsigned long long seed, float* du_f32,
+                                    void* du_bf16, float* dgamma, float* dbeta, int R, int d, void* workspace,
+                                    size_t workspace_bytes, b200_stream_t stream);
+/* backward of b200_text_attention (attentive_modules.py:45-55,166,170): given dP1, dP2 (bf16, row stride ldp) and
+ * an optional external gradient on the attention probabilities (loss_attentive, roi_heads.py:1079-1081) computes
+ *   dx (R,d) fp32 (+= when accumulate_dx), dO (R,d) bf16 (for dVp = attn^T dO through the GEMM),
+ *   dS (R,ldds) bf16, zero padded beyond L (the scores' gradient: feeds dx += dS Kq and dKq = dS^T x). */
+B200_API int b200_text_attention_bwd(const void* dp1, const void* dp2, int ldp, const float* x, const float* attn,
+                            const float* vp, const float* dattn_ext, float* dx, int accumulate_dx, void* d_o, void* ds,
+                            int ldds, int R, int d, int L, b200_stream_t stream);
+/* L1: out3 = {loss_cls, loss_box_reg, loss_attentive} (fast_rcnn.py:222-304, roi_heads.py:1079-1081); attn may be
+ * NULL (no attentive loss).  gt_classes int64 in [0, K] (K = background); proposals / gt_boxes (R,4). */
+B200_API int b200_head_losses(const float* logits, const float* deltas, const float* attn, const int64_t* gt_classes,
+                     const float* proposals, const float* gt_boxes, int R, int K, int L, int cls_agnostic, float wx,
+                     float wy, float ww, float wh, float smooth_l1_beta, float* out3, b200_stream_t stream);
+/* gradients of the three losses scaled by grad_scale3[0..2] (device): dlogits (R,ldl) bf16, ddeltas (R,ldd) bf16
+ * (both zero padded to their row stride), dattn (R,L) fp32 (may be NULL). */
+B200_API int b200_head_losses_bwd(const float* logits, const float* deltas, const float* attn, const int64_t* gt_classes,
+                         const float* proposals, const float* gt_boxes, const float* grad_scale3, int R, int K, int L,
+                         int cls_agnostic, float wx, float wy, float ww, float wh, float smooth_l1_beta,
+                         void* dlogits_bf16, int ldl, void* ddeltas_bf16, int ldd, float* dattn, b200_stream_t stream);
+/* torch.optim.SGD step over one flat fp32 buffer: g += wd*p; m = mu*m + g; p -= lr*m (defrcn/solver/build.py) */
+B200_API int b200_sgd_momentum(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
+                      float weight_decay, b200_stream_t stream);
+
 /* A3 + A4 prologue: S = Q Kp^T / sqrt(d), softmax over the K+2 keys, O = attn Vp, then the two gate
  * operands P1 = O*x and P2 = x - O written as bf16 (attentive_modules.py:45-55,166,170).
  *   q (R,d) bf16 with kp (L,d) fp32, OR q == NULL and scores_in (R,L) fp32 = the already scaled scores S

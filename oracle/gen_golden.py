@@ -333,6 +333,58 @@ def gen_teacher():
     np.savez_compressed(os.path.join(OUT, "teacher.npz"), **d)
 
 
+def gen_train_step():
+    """Fine-tune direction pinned on the reference's own autograd: SematicRes5ROIHeads.forward_att +
+    FastRCNNOutputs.losses in train mode (roi_heads.py:1072-1132, dropout off so the numbers are reproducible) on
+    fixed pooled features / labels; stores the three losses and d(sum of losses)/d(feature, every trained
+    parameter of the attention and the predictor)."""
+    emb = lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg)
+    rs.install(class_embed_fn=emb)
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    am.get_class_embed = emb
+    rh = rs.load("defrcn.modeling.roi_heads.roi_heads")
+    fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
+    K, R = 20, 96
+    cfg = rs.default_cfg(num_classes=K, addition="clip", output_layer="FastRCNNOutputLayers", roi_head="SematicRes5ROIHeads")
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS = 8      # res5 out = 64
+    cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 1
+    cfg.MODEL.ROI_HEADS.CLS_DROPOUT = False
+    torch.manual_seed(11)
+    with cuda_as_cpu():
+        m = rh.build_roi_heads(cfg, {"res4": rs.ShapeSpec(channels=32, stride=16)}).train()
+        with torch.no_grad():
+            m.box_predictor.cls_score.weight.mul_(30.0)
+            m.box_predictor.bbox_pred.weight.mul_(100.0)
+            for p_ in m.attention.parameters():     # the 0.02-std init gives near-zero gradients: widen it
+                p_.mul_(4.0)
+        gen = torch.Generator().manual_seed(12)
+        d = m.out_channels
+        x = torch.relu(torch.randn(R, d, generator=gen)).requires_grad_(True)
+        h, w = 600, 800
+        props, _ = synth_proposals(R, h, w, gen)
+        gt_classes = torch.randint(0, K + 1, (R,), generator=gen)
+        gt_classes[R // 3:] = K
+        gt_boxes = props + torch.randn(R, 4, generator=gen) * 4
+        gt_boxes[:, 2:] = torch.maximum(gt_boxes[:, 2:], gt_boxes[:, :2] + 2)
+        inst = rs.Instances((h, w))
+        inst.proposal_boxes = rs.Boxes(props)
+        inst.gt_boxes = rs.Boxes(gt_boxes)
+        inst.gt_classes = gt_classes
+        att_output, att_loss = m.forward_att(x, gt_classes)
+        o = fr.FastRCNNOutputs(m.box2box_transform, att_output["pred_logits"], att_output["pred_bbox"], [inst], m.smooth_l1_beta)
+        L = dict(o.losses())
+        L.update(att_loss)
+        sum(L.values()).backward()
+    out = {k: v for k, v in sd_to_np(m.state_dict()).items() if not k.startswith("res5.")}
+    out.update(x=x.detach().numpy(), props=props.numpy(), gt_boxes=gt_boxes.numpy(), gt_classes=gt_classes.numpy(),
+               embed=m.attention.embed.numpy(), bg_feature=m.attention.bg_feature.numpy(), grad_x=x.grad.numpy(),
+               **{"loss." + k: v.detach().numpy() for k, v in L.items()})
+    for k, p_ in m.named_parameters():
+        if p_.grad is not None:
+            out["grad." + k] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "train_step.npz"), **out)
+
+
 def gen_known_answer():
     """test.py:80-92 fixture: CE(pred_logits.pt, gt_classes.pt)."""
     pl = torch.load(os.path.join(rs.REFERENCE_ROOT, "pred_logits.pt"), map_location="cpu").detach()
@@ -344,6 +396,13 @@ def gen_known_answer():
 
 
 def main():
+    import sys
+    if len(sys.argv) > 1:       # regenerate selected fixtures only: python -m oracle.gen_golden gen_train_step ...
+        os.makedirs(OUT, exist_ok=True)
+        torch.set_num_threads(1)
+        for name in sys.argv[1:]:
+            globals()[name]()
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order in the CPU kernels
     gen_gdl()
@@ -353,6 +412,7 @@ def main():
     gen_head_tiny()
     gen_pcb()
     gen_teacher()
+    gen_train_step()
     gen_known_answer()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,203 @@
+"""Fine-tuning direction (BASELINE configs[1]) on the hand-written kernels vs the reference's own autograd.
+
+`tests/golden/train_step.npz` was produced by the reference's SematicRes5ROIHeads.forward_att + FastRCNNOutputs.losses
+in train mode (oracle/gen_golden.py:gen_train_step).  The fused path computes in bf16 on tensor cores with fp32
+accumulation.  Tolerances (written here): losses 2e-2 relative; gradients of the predictor (one GEMM deep) 1e-2 in
+relative L2 norm; gradients further down the 7-GEMM-deep backward chain 8e-2 in relative L2 norm AND cosine > 0.997 —
+every layer re-rounds its activations and incoming gradient to bf16 (2^-9), and on this small fixture (d = 64, weights
+widened x4 so that gradients are not vanishing) the measured error grows from 0.2 % at the classifier to 5 % at the
+pooled feature, while the same torch expression in fp32 agrees with the fixture to 5e-7.  The CPU oracle
+restatement is held to 1e-3 against the same fixture in tests/test_oracle_golden.py; at full size the fused path is
+checked against the fp32 torch expression on the device (test_full_size_train_step_vs_fp32_expression)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _build(g, K=20, d=64):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
+    cfg.MODEL.ADDITION.NAME = "clip"
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = d // 8, 1
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=d // 2, stride=16)})
+    sd = {k: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith(("attention.", "box_predictor.", "output_projection",
+                                                                             "sematic_projection", "projection_matrix"))}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("res5.") for k in missing), (missing, unexpected)
+    m.attention.embed = torch.from_numpy(np.asarray(g["embed"]))
+    m.attention.class_embed = m.attention.embed
+    m.attention.bg_feature = torch.from_numpy(np.asarray(g["bg_feature"]))
+    return m.cuda().train()
+
+
+def _proposals(g):
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+    inst = Instances((600, 800))
+    inst.proposal_boxes = Boxes(torch.from_numpy(g["props"]).cuda())
+    inst.gt_boxes = Boxes(torch.from_numpy(g["gt_boxes"]).cuda())
+    inst.gt_classes = torch.from_numpy(g["gt_classes"]).cuda()
+    return [inst]
+
+
+def test_fused_train_step_matches_reference_autograd(golden):
+    g = golden("train_step")
+    m = _build(g)
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    props = _proposals(g)
+    losses, logits = m.fused_train_losses(x, props, props[0].gt_classes)
+    for k in ("loss_cls", "loss_box_reg", "loss_attentive"):
+        ref = float(g["loss." + k])
+        assert abs(float(losses[k]) - ref) <= 2e-2 * abs(ref) + 1e-4, (k, float(losses[k]), ref)
+    sum(losses.values()).backward()
+    gx = torch.from_numpy(g["grad_x"])
+    assert _rel(x.grad.cpu(), gx) < 8e-2 and _cos(x.grad.cpu(), gx) > 0.997
+    worst = {}
+    for name, p in m.named_parameters():
+        key = "grad." + name
+        if key not in g:
+            continue
+        assert p.grad is not None, name
+        ref = torch.from_numpy(g[key])
+        worst[name] = (_rel(p.grad.cpu(), ref), _cos(p.grad.cpu(), ref))
+    assert len(worst) >= 24
+    bad = {k: v for k, v in worst.items() if v[0] >= (1e-2 if k.startswith("box_predictor") else 8e-2) or v[1] <= 0.997}
+    assert not bad, bad
+
+
+def test_fused_train_step_is_deterministic_and_matches_torch_path(golden):
+    """Bitwise run-to-run reproducibility (ordered reductions, no atomics) and agreement with the differentiable torch
+    expression of the same head (fp32 library GEMMs) on the same device."""
+    g = golden("train_step")
+    m = _build(g)
+    props = _proposals(g)
+    grads = []
+    for _ in range(2):
+        m.zero_grad(set_to_none=True)
+        x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+        losses, _ = m.fused_train_losses(x, props, props[0].gt_classes)
+        sum(losses.values()).backward()
+        grads.append([x.grad.clone()] + [p.grad.clone() for p in m.parameters() if p.grad is not None])
+    assert all(torch.equal(a, b) for a, b in zip(*grads))
+    # torch path
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
+    m.zero_grad(set_to_none=True)
+    x2 = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    att_out, att_loss = m.forward_att(x2, props[0].gt_classes)
+    o = FastRCNNOutputs(m.box2box_transform, att_out["pred_logits"], att_out["pred_bbox"], props, m.smooth_l1_beta)
+    L = dict(o.losses())
+    L.update(att_loss)
+    sum(L.values()).backward()
+    assert _rel(grads[0][0], x2.grad) < 8e-2
+
+
+def test_full_size_train_step_vs_fp32_expression():
+    """BASELINE size (d = 2048, K = 20, R = 1024 ROIs, reference initialisation): fused bf16 path vs the fp32 torch
+    expression of the same head on the device.  Larger contractions average the bf16 rounding: every gradient within
+    5e-2 relative L2 (most within 1e-2)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, ShapeSpec
+    from oracle.gen_golden import synth_proposals
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ADDITION.NAME = "clip"
+    # beta > 0 keeps the box loss differentiable: with the default pure-L1 (beta = 0) a bf16-sized perturbation of the
+    # predicted delta flips sign(pred - target) on the few entries that sit on the kink, which is a 2/R jump of that
+    # gradient entry in BOTH implementations' terms and says nothing about the backward kernels (measured: 5 % L2)
+    cfg.MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA = 0.5
+    torch.manual_seed(3)
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)}).cuda().train()
+    with torch.no_grad():
+        m.box_predictor.cls_score.weight.mul_(20.0)
+        m.box_predictor.bbox_pred.weight.mul_(50.0)
+    gen = torch.Generator().manual_seed(4)
+    R, K = 1024, 20
+    b, _ = synth_proposals(R, 600, 800, gen)
+    inst = Instances((600, 800))
+    inst.proposal_boxes = Boxes(b.cuda())
+    gtb = b + torch.randn(R, 4, generator=gen) * 4
+    gtb[:, 2:] = torch.maximum(gtb[:, 2:], gtb[:, :2] + 2)
+    inst.gt_boxes = Boxes(gtb.cuda())
+    gt = torch.randint(0, K + 1, (R,), generator=gen)
+    gt[R // 4:] = K
+    inst.gt_classes = gt.cuda()
+    x0 = torch.relu(torch.randn(R, 2048, generator=gen)).cuda()
+    x = x0.clone().requires_grad_(True)
+    losses, _ = m.fused_train_losses(x, [inst], inst.gt_classes)
+    sum(losses.values()).backward()
+    fused = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    x2 = x0.clone().requires_grad_(True)
+    att_out, att_loss = m.forward_att(x2, inst.gt_classes)
+    o = FastRCNNOutputs(m.box2box_transform, att_out["pred_logits"], att_out["pred_bbox"], [inst], m.smooth_l1_beta)
+    L = dict(o.losses())
+    L.update(att_loss)
+    for k in L:
+        assert abs(float(losses[k]) - float(L[k])) <= 2e-2 * abs(float(L[k])) + 1e-4, k
+    sum(L.values()).backward()
+    errs = {"x": _rel(x.grad, x2.grad)}
+    for n, p in m.named_parameters():
+        if p.grad is not None and n in fused:
+            errs[n] = _rel(fused[n], p.grad)
+    bad = {k: v for k, v in errs.items() if v >= 5e-2}
+    assert not bad, (bad, errs)
+
+
+def test_dropout_statistics_and_backward_mask():
+    """Counter-based dropout: keep rate ~ 1-p, kept values scaled by 1/(1-p), and the LayerNorm/ReLU/dropout backward
+    kernel regenerates the same mask (gradient is zero exactly where the forward dropped)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    x = torch.rand(512, 256, device="cuda") + 0.5
+    y = train_ops.dropout_bf16(x, 0.8, 1234).float()
+    keep = y != 0
+    assert abs(float(keep.float().mean()) - 0.2) < 0.01
+    torch.testing.assert_close(y[keep], x[keep] * 5.0, rtol=8e-3, atol=0)     # bf16 output
+    y2 = train_ops.dropout_bf16(x, 0.8, 1234).float()
+    assert torch.equal(y, y2)
+    assert not torch.equal(y, train_ops.dropout_bf16(x, 0.8, 1235).float())
+    assert torch.equal(train_ops.dropout_bf16(x, 0.0, 7).float(), x.to(torch.bfloat16).float())
+
+
+def test_flat_sgd_matches_torch_sgd():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(33, 17, device="cuda")), torch.nn.Parameter(torch.randn(129, device="cuda"))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.SGD(qs, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt = train_ops.FlatSGD(ps, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    for step in range(3):
+        for p, q in zip(ps, qs):
+            gr = torch.randn_like(q)
+            q.grad = gr.clone()
+            p.grad.copy_(gr)
+        ref.step()
+        opt.step()
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.data, q.data, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,cols,dt", [(100, 24, torch.float32), (4096, 2048, torch.bfloat16), (70, 130, torch.bfloat16)])
+def test_transpose_and_colsum(rows, cols, dt):
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    x = torch.randn(rows, cols, device="cuda").to(dt)
+    t = train_ops.transpose_bf16(x)
+    assert t.shape == (cols, (rows + 7) // 8 * 8)
+    assert torch.equal(t[:, :rows], x.to(torch.bfloat16).t())
+    assert float(t[:, rows:].abs().sum()) == 0.0
+    s = train_ops.colsum(x)
+    torch.testing.assert_close(s, x.float().sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.equal(s, train_ops.colsum(x))

@@ -117,3 +117,34 @@ def test_known_answer_ce(golden):
     g = golden("known_answer_ce")
     assert abs(float(g["ce"]) - 2.764926910) < 1e-6          # SURVEY.md §4 / BASELINE.md
     assert tuple(g["shape"]) == (2048, 16) and int(g["n_bg"]) == 1697
+
+
+def test_train_step_autograd(golden):
+    """The oracle restatement, differentiated by torch autograd on the CPU, reproduces the reference's own losses and
+    gradients for the fine-tune direction (fixture from SematicRes5ROIHeads.forward_att + FastRCNNOutputs.losses)."""
+    g = golden("train_step")
+    from oracle import ref_stubs as rs
+    K = 20
+    p = {k: T(g[k]).clone().requires_grad_(True) for k in g.files if k.startswith(("attention.", "box_predictor."))}
+    x = T(g["x"]).clone().requires_grad_(True)
+    text = torch.cat([T(g["embed"]), T(g["bg_feature"])], 0)
+    sim, attn = O.sematic_proposal_attention(x, text, p)
+    logits, deltas = O.output_layers(x, sim, p)
+    gt = T(g["gt_classes"])
+    loss_cls = F.cross_entropy(logits, gt)
+    tgt = rs.Box2BoxTransform((10.0, 10.0, 5.0, 5.0)).get_deltas(T(g["props"]), T(g["gt_boxes"]))
+    fg = torch.nonzero((gt >= 0) & (gt < K)).squeeze(1)
+    cols = 4 * gt[fg][:, None] + torch.arange(4)
+    loss_box = (deltas[fg[:, None], cols] - tgt[fg]).abs().sum() / gt.numel()
+    loss_att = O.loss_attentive(attn, gt)
+    for name, v in (("loss_cls", loss_cls), ("loss_box_reg", loss_box), ("loss_attentive", loss_att)):
+        assert abs(float(v) - float(g["loss." + name])) < 1e-4 * max(1.0, abs(float(g["loss." + name]))), name
+    (loss_cls + loss_box + loss_att).backward()
+    assert torch.allclose(x.grad, T(g["grad_x"]), rtol=1e-3, atol=1e-5)
+    n = 0
+    for k, v in p.items():
+        if "grad." + k in g.files:
+            ref = T(g["grad." + k])
+            assert float((v.grad - ref).norm()) <= 1e-3 * float(ref.norm()) + 1e-6, k
+            n += 1
+    assert n >= 24
