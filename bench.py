@@ -1,16 +1,23 @@
 #!/usr/bin/env python
 """bench.py — ROI-head images/s on B200 (BASELINE.json metric), with roofline, CPU baseline and e2e figures.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode train|infer]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" is one inference pass of the text-fused C4 ROI head over one batch of synthetic input on each GPU:
-  affine_rcnn(GDL) on the res4 map -> ROIAlign 7x7 -> res5 (cuDNN bf16) -> spatial mean -> text-fusion chain
-  (tcgen05 GEMMs) -> cls_score / bbox_pred -> softmax + decode + threshold + per-class NMS + top-100.
-Workload = BASELINE.json configs[1] shape (VOC, K=20, CLIP 512-d, 600x800 px -> res4 38x50x1024, 512
-proposals per image, bf16), inference direction.  Images shard across GPUs with no data-path collective
-(weak scaling); the only exchange is the detection all-gather after the loop.
+Default workload = BASELINE.json configs[1]: "VOC split1 10-shot novel fine-tune with CLIP text-fused ROI head, bf16,
+1 B200".  A "step" is one fine-tune step of the text-fused C4 ROI head over one batch of synthetic input on each GPU
+(8 images x 512 sampled, labelled proposals each; 600x800 px -> res4 38x50x1024; K=20; CLIP 512-d):
+  forward   GDL + affine_rcnn on the res4 map -> ROIAlign 7x7 -> res5 (frozen, FrozenBN folded, cuDNN bf16) -> mean
+            -> text-fusion chain (tcgen05 GEMMs) -> cls_score (dropout 0.8) / bbox_pred -> loss_cls, loss_box_reg,
+            loss_attentive
+  backward  through all of it down to d(res4 map) (GDL scale 0.001) and every trained parameter (attention,
+            predictor, affine_rcnn); res5 is frozen (ROI_HEADS.FREEZE_FEAT) so it only propagates the data gradient
+  update    gradient all-reduce over NCCL when N > 1, then SGD + momentum on the trained parameters
+`--mode infer` times the inference direction instead (forward + softmax/decode/threshold/per-class NMS/top-100).
+Images shard across GPUs (weak scaling); the only exchanges are the gradient all-reduce (train) / the detection
+all-gather after the loop (infer).  Proposal sampling/labelling (marked "next") is not in the step:
+the synthetic proposals arrive sampled and labelled.
 """
 import argparse
 import json
@@ -28,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 H_IMG, W_IMG, HF, WF, C4 = 600, 800, 38, 50, 1024
 METRIC, UNIT = "roi_head_images_per_sec", "images/s"
+GDL_LAMBDA, DROP_P, LR, MOMENTUM, WD = 0.001, 0.8, 0.01, 0.9, 5e-5   # configs/voc/defrcn_fsod_r101_novel*: fine-tune
 
 
 def parse():
@@ -36,6 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--images-per-gpu", type=int, default=8)
     ap.add_argument("--props", type=int, default=512)
     ap.add_argument("--classes", type=int, default=20)
@@ -46,24 +55,41 @@ def parse():
     return ap.parse_args()
 
 
-def synth_inputs(n_images, props, seed0=1234):
-    """SURVEY.md §8(d) synthetic inputs: post-ReLU res4 maps, RPN-like + jittered proposals, per-image seeds."""
+def synth_inputs(n_images, props, seed0=1234, num_classes=20):
+    """SURVEY.md §8(d) synthetic inputs: post-ReLU res4 maps, RPN-like + jittered proposals, per-image seeds; for the
+    fine-tune direction the proposals come sampled and labelled (25 % foreground, GT = jittered proposal)."""
     from oracle.gen_golden import synth_proposals
     feat = torch.relu(torch.randn(n_images, C4, HF, WF, generator=torch.Generator().manual_seed(0)))
-    boxes = [synth_proposals(props, H_IMG, W_IMG, torch.Generator().manual_seed(seed0 + i), n_obj=8)[0]
-             for i in range(n_images)]
-    return feat, boxes
+    boxes, gt_cls, gt_boxes = [], [], []
+    for i in range(n_images):
+        gen = torch.Generator().manual_seed(seed0 + i)
+        b = synth_proposals(props, H_IMG, W_IMG, gen, n_obj=8)[0]
+        c = torch.randint(0, num_classes, (props,), generator=gen)
+        c[props // 4:] = num_classes
+        g = b + torch.randn(props, 4, generator=gen) * 4
+        g[:, 2:] = torch.maximum(g[:, 2:], g[:, :2] + 2)
+        boxes.append(b)
+        gt_cls.append(c)
+        gt_boxes.append(g)
+    return feat, boxes, gt_cls, gt_boxes
 
 
-def build_head(num_classes, device):
+def build_head(num_classes, device, train=False):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
     cfg = config.get_cfg()
     cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
     cfg.MODEL.ROI_HEADS.NUM_CLASSES = num_classes
     cfg.MODEL.ADDITION.NAME = "clip"
+    if train:
+        cfg.MODEL.ROI_HEADS.CLS_DROPOUT = True
+        cfg.MODEL.ROI_HEADS.DROPOUT_RATIO = DROP_P
+        cfg.MODEL.ROI_HEADS.ENABLE_DECOUPLE = True
+        cfg.MODEL.ROI_HEADS.BACKWARD_SCALE = GDL_LAMBDA
+        cfg.MODEL.ROI_HEADS.FREEZE_FEAT = True
     torch.manual_seed(0)
-    head = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=C4, stride=16)}).eval()
+    head = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=C4, stride=16)})
+    head = head.train() if train else head.eval()
     aff = modeling.AffineLayer(C4, bias=True)
     with torch.no_grad():
         # random-init weights of the reference architecture; classifier scaled so that scores are not uniform
@@ -71,6 +97,9 @@ def build_head(num_classes, device):
         head.box_predictor.bbox_pred.weight.mul_(50.0)
         aff.weight.normal_(1.0, 0.05)
         aff.bias.normal_(0.0, 0.05)
+    if train:
+        for p in head.res5.parameters():            # ROI_HEADS.FREEZE_FEAT (roi_heads.py:96-99)
+            p.requires_grad = False
     return cfg, head.to(device), aff.to(device)
 
 
@@ -103,53 +132,69 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_head_step(feat, boxes, sizes, text, params, stages=None):
-    from oracle import oracle as O
-    return O.head_forward(feat, boxes, sizes, text, params, stages=stages)
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference modules' arithmetic + torchvision CPU ops) on this box's host cores
+# ---------------------------------------------------------------------------------------------------------------
+class CpuArm:
+    def __init__(self, args):
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.args, self.train = args, args.mode == "train"
+        _, head, aff = build_head(args.classes, "cpu", train=self.train)
+        self.params = {k: v.detach().float().clone() for k, v in head.state_dict().items()}
+        self.text = torch.cat([head.attention.embed, head.attention.bg_feature], 0).float()
+        self.aff_w, self.aff_b = aff.weight.detach().clone(), aff.bias.detach().clone()
+        self.feat, self.boxes, self.gt_cls, self.gt_boxes = synth_inputs(1, args.props, num_classes=args.classes)
+        if self.train:
+            self.trainable = [v for k, v in self.params.items() if k.startswith(("attention.", "box_predictor."))]
+            self.trainable += [self.aff_w, self.aff_b]
+            for t in self.trainable:
+                t.requires_grad_(True)
+            self.opt = torch.optim.SGD(self.trainable, lr=LR, momentum=MOMENTUM, weight_decay=WD)
+
+    def step(self, stages=None):
+        from oracle import oracle as O
+        a = self.args
+        if not self.train:
+            with torch.no_grad():
+                return O.head_forward(self.feat * self.aff_w + self.aff_b, self.boxes, [(H_IMG, W_IMG)], self.text, self.params,
+                                      stages=stages)
+        self.opt.zero_grad(set_to_none=True)
+        out = O.head_train_step(self.feat, self.boxes, self.gt_cls[0], self.gt_boxes[0], self.text, self.params, self.aff_w,
+                                self.aff_b, GDL_LAMBDA, a.classes, DROP_P, stages=stages)
+        self.opt.step()
+        return out
+
+    def describe(self, n):
+        return "%d image(s) x %d proposals, %s step, fp32, torch %d threads" % (
+            n, self.args.props, "fine-tune (fwd + bwd + SGD)" if self.train else "inference", torch.get_num_threads())
 
 
-def cpu_reference_setup(num_classes):
-    cfg, head, aff = build_head(num_classes, "cpu")
-    params = {k: v.detach().float() for k, v in head.state_dict().items()}
-    text = torch.cat([head.attention.embed, head.attention.bg_feature], 0).float()
-    return params, text, aff
-
-
-def run_cpu_baseline(n_images, props, num_classes, warm=1):
-    """Oracle port (reference modules' arithmetic + torchvision CPU ops) on this box's host cores."""
-    torch.set_num_threads(os.cpu_count() or 1)
-    params, text, aff = cpu_reference_setup(num_classes)
-    feat, boxes = synth_inputs(1, props)
-    with torch.no_grad():
-        f = feat * aff.weight + aff.bias
-        for _ in range(warm):
-            cpu_head_step(f, boxes, [(H_IMG, W_IMG)], text, params)
-        stages, t0 = {}, time.perf_counter()
-        for _ in range(n_images):
-            f = feat * aff.weight + aff.bias
-            cpu_head_step(f, boxes, [(H_IMG, W_IMG)], text, params, stages)
-        dt = time.perf_counter() - t0
-    return {"value": n_images / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": "%d image(s) x %d proposals, fp32, torch %d threads, after %d warm-up" % (n_images, props, torch.get_num_threads(), warm),
-            "stage_ms_per_image": {k: 1e3 * v / n_images for k, v in stages.items()}}
+def run_cpu_baseline(args, warm=1):
+    arm = CpuArm(args)
+    for _ in range(warm):
+        arm.step()
+    stages, t0 = {}, time.perf_counter()
+    for _ in range(args.cpu_baseline_images):
+        arm.step(stages)
+    dt = time.perf_counter() - t0
+    return {"value": args.cpu_baseline_images / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": arm.describe(args.cpu_baseline_images) + ", after %d warm-up" % warm,
+            "stage_ms_per_image": {k: 1e3 * v / args.cpu_baseline_images for k, v in stages.items()}}
 
 
 def main_reference(args, rank, world):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
-    params, text, aff = cpu_reference_setup(args.classes)
-    feat, boxes = synth_inputs(1, args.props)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            cpu_head_step(feat * aff.weight + aff.bias, boxes, [(H_IMG, W_IMG)], text, params)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            cpu_head_step(feat * aff.weight + aff.bias, boxes, [(H_IMG, W_IMG)], text, params)
-        dt = time.perf_counter() - t0
+    arm = CpuArm(args)
+    for _ in range(args.warmup):
+        arm.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.step()
+    dt = time.perf_counter() - t0
     v = args.steps / dt
     cb = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-          "sample": "each step = 1 image x %d proposals of the same workload (bounded sample), fp32, %d torch threads" % (args.props, torch.get_num_threads())}
+          "sample": "each step = " + arm.describe(1) + " (bounded sample of the same workload)"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -159,8 +204,14 @@ def main_reference(args, rank, world):
 
 
 def workload_config(args, images_per_gpu):
-    return {"workload": "DeFRCN R-101 C4 text-fused ROI head (SematicRes5ROIHeads, CLIP 512-d, K=%d), inference step: "
-                        "affine_rcnn -> ROIAlign 7x7 -> res5 -> text fusion -> decode/NMS top-100" % args.classes,
+    if args.mode == "train":
+        what = ("fine-tune step (BASELINE configs[1]): GDL+affine_rcnn -> ROIAlign 7x7 -> res5 (frozen) -> text fusion -> "
+                "cls_score(dropout 0.8)/bbox_pred -> loss_cls+loss_box_reg+loss_attentive -> backward to the res4 map "
+                "and all trained parameters -> (grad all-reduce) -> SGD+momentum; proposals arrive sampled and labelled")
+    else:
+        what = "inference step: affine_rcnn -> ROIAlign 7x7 -> res5 -> text fusion -> decode/NMS top-100"
+    return {"workload": "DeFRCN R-101 C4 text-fused ROI head (SematicRes5ROIHeads, CLIP 512-d, K=%d), %s" % (args.classes, what),
+            "mode": args.mode,
             "roi_align_bins": "all 49" if getattr(args, "full_bins", False) else "16 live of 49 (stride-2 consumer)",
             "images_per_gpu_per_step": images_per_gpu, "proposals_per_image": args.props, "image_px": [H_IMG, W_IMG],
             "res4_map": [C4, HF, WF], "l2": "flushed between timed steps (256 MiB write)", "parallelism": "image-sharded dp%d" % args.gpus}
@@ -175,7 +226,7 @@ def main():
         return main_reference(args, rank, world)
 
     import torch.distributed as dist
-    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, train_ops
     from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
 
@@ -183,88 +234,146 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    train = args.mode == "train"
     B, P, K = args.images_per_gpu, args.props, args.classes
-    cfg, head, aff = build_head(K, dev)
-    feat_h, boxes_h = synth_inputs(B, P, seed0=1234 + 1000 * rank)
-    feat_pin = feat_h.pin_memory()
-    boxes_pin = torch.stack(boxes_h).pin_memory()                 # (B,P,4)
-    feat_d = feat_pin.to(dev)
-    boxes_d = boxes_pin.to(dev)
+    cfg, head, aff = build_head(K, dev, train=train)
+    feat_h, boxes_h, cls_h, gtb_h = synth_inputs(B, P, seed0=1234 + 1000 * rank, num_classes=K)
+    host = {"feat": feat_h.pin_memory(), "boxes": torch.stack(boxes_h).pin_memory()}
+    if train:
+        host["gt_cls"] = torch.stack(cls_h).pin_memory()
+        host["gt_boxes"] = torch.stack(gtb_h).pin_memory()
+    names = list(host)
+    resident = {k: v.to(dev) for k, v in host.items()}
     sizes = [(H_IMG, W_IMG)] * B
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stage_names = ["affine", "roi_align", "res5_mean", "text_fusion_predictor", "decode_nms"]
     # res5's first block reads the pooled 7x7 map through 1x1 stride-2 convs: only bins [::2, ::2] are live
     skip = head.skip_dead_bins and head.res5[0].reads_strided_1x1() and not args.full_bins
     bin_step = head.res5[0].stride if skip else 1
     nb = -(-7 // bin_step)
+    opt = None
+    if train:
+        opt = train_ops.FlatSGD(list(head.attention.parameters()) + list(head.box_predictor.parameters()) + list(aff.parameters()),
+                                lr=LR, momentum=MOMENTUM, weight_decay=WD)
 
-    def step(feat, boxes, ev=None):
-        def mark(i):
-            if ev is not None:
-                ev[i].record()
+    def make_props(d):
         props = []
         for i in range(B):
             inst = Instances(sizes[i])
-            inst.proposal_boxes = Boxes(boxes[i])
+            inst.proposal_boxes = Boxes(d["boxes"][i])
+            if train:
+                inst.gt_boxes = Boxes(d["gt_boxes"][i])
+                inst.gt_classes = d["gt_cls"][i]
             props.append(inst)
-        mark(0)
-        f = aff(feat, None, True, torch.bfloat16)                                     # G2 (+layout/dtype for the gather)
-        mark(1)
-        pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)   # P1
-        mark(2)
-        fp = head._res5_forward(pooled, prestrided=bin_step > 1).mean(dim=[2, 3], dtype=torch.float32)   # P2 (cuDNN)
-        mark(3)
-        att, _ = head.forward_att(fp)                                                 # T1, A1-A6, C1
-        mark(4)
-        outs = FastRCNNOutputs(head.box2box_transform, att["pred_logits"], att["pred_bbox"], props, 0.0)
-        out = outs.inference_device(head.test_score_thresh, head.test_nms_thresh, head.test_detections_per_img)  # D1-D3
-        mark(5)
-        return out
+        return props
 
-    with torch.no_grad():
+    if train:
+        stage_names = ["gdl_affine", "roi_align", "res5_mean", "text_fusion_losses", "bwd_text_fusion", "bwd_res5",
+                       "bwd_roi_align", "bwd_gdl_affine", "allreduce_sgd"]
+    else:
+        stage_names = ["affine", "roi_align", "res5_mean", "text_fusion_predictor", "decode_nms"]
+    n_marks = len(stage_names) + 1
+
+    def step(d, ev=None):
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+        props = make_props(d)
+        if not train:
+            mark(0)
+            f = aff(d["feat"], None, True, torch.bfloat16)                                    # G2 (+layout/dtype for the gather)
+            mark(1)
+            pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)   # P1
+            mark(2)
+            fp = head._res5_forward(pooled, prestrided=bin_step > 1).mean(dim=[2, 3], dtype=torch.float32)   # P2 (cuDNN)
+            mark(3)
+            att, _ = head.forward_att(fp)                                                     # T1, A1-A6, C1
+            mark(4)
+            outs = FastRCNNOutputs(head.box2box_transform, att["pred_logits"], att["pred_bbox"], props, 0.0)
+            out = outs.inference_device(head.test_score_thresh, head.test_nms_thresh, head.test_detections_per_img)  # D1-D3
+            mark(5)
+            return out
+        opt.zero_grad()
+        x = d["feat"].detach().requires_grad_(True)
+        mark(0)
+        f = aff(x, GDL_LAMBDA, True, torch.bfloat16)                                          # G1 + G2
+        mark(1)
+        pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)       # P1
+        mark(2)
+        fp = head._res5_forward(pooled, prestrided=bin_step > 1).mean(dim=[2, 3], dtype=torch.float32)   # P2 (frozen)
+        mark(3)
+        gt = d["gt_cls"].reshape(-1)
+        losses, _ = head.fused_train_losses(fp, props, gt)                                    # T1, A1-A6, C1, L1
+        mark(4)
+        if ev is not None:     # events inside the backward pass: recorded when the gradient of that tensor is ready
+            fp.register_hook(lambda g: ev[5].record())
+            pooled.register_hook(lambda g: ev[6].record())
+            f.register_hook(lambda g: ev[7].record())
+        (losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]).backward()   # L1, A*, P2, P1b, G1/G2 bwd
+        mark(8)
+        if world > 1:
+            dist.all_reduce(opt.grad, op=dist.ReduceOp.AVG)                                   # the one real exchange step
+        opt.step()
+        mark(9)
+        return {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
+                "grad_feat": x.grad}
+
+    grad_ctx = torch.enable_grad() if train else torch.no_grad()
+    with grad_ctx:
         for _ in range(max(args.warmup, 3)):
-            out = step(feat_d, boxes_d)
+            out = step(resident)
         torch.cuda.synchronize()
         # ---- device-resident timing --------------------------------------------------------------------
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
         sampler = ClockSampler(local)
         sampler.start()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         l0 = _lib.LAUNCHES
-        ops.KERNEL_EVENTS["roi_align_fwd"] = []
         for i in range(args.steps):
             flush.fill_(i & 0xff)
-            out = step(feat_d, boxes_d, evs[i])
-        if world > 1:
+            out = step(resident, evs[i])
+        if world > 1 and not train:
             insts = [Instances(sizes[0], pred_boxes=Boxes(out["boxes"][i]), scores=out["scores"][i], pred_classes=out["classes"][i]) for i in range(B)]
             cnt, dets = bdist.pack_detections(insts)
             bdist.all_gather_detections(out["counts"], dets, B * world)
         torch.cuda.synchronize()
         launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
-        roi_ms = float(np.mean([a.elapsed_time(b) for a, b in ops.KERNEL_EVENTS["roi_align_fwd"]]))
-        ops.KERNEL_EVENTS.clear()
-        n_cand = out["n_candidates"].float().mean().item()
-        n_det = out["counts"].float().mean().item()
         sampler.stop_flag = True
         if world > 1:
             dist.barrier()
-        per_step = [evs[i][0].elapsed_time(evs[i][5]) for i in range(args.steps)]
-        stage_ms = [float(np.mean([evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(args.steps)])) for s in range(5)]
+        per_step = [evs[i][0].elapsed_time(evs[i][n_marks - 1]) for i in range(args.steps)]
+        stage_ms = [float(np.mean([evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(args.steps)])) for s in range(n_marks - 1)]
         total_ms = torch.tensor([float(sum(per_step))], device=dev)
         if world > 1:
             dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         total_ms = float(total_ms)
-        # ---- end to end: pinned host inputs -> device, detections -> host, every step --------------------
+        # ---- per-entry-point profile (separate pass: an event pair around every C-ABI call) ---------------------
+        _lib.PROFILE = {}
+        prof_steps = 3
+        for i in range(prof_steps):
+            flush.fill_(i)
+            step(resident)
+        torch.cuda.synchronize()
+        prof = {}
+        for name, rows in _lib.PROFILE.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in rows) / prof_steps
+            fl = sum(t for _, _, t in rows if t) / prof_steps
+            prof[name] = {"ms_per_step": ms, "calls_per_step": len(rows) / prof_steps}
+            if fl:
+                prof[name]["tflops"] = fl / (ms * 1e-3) / 1e12
+                prof[name]["flop_per_step"] = fl
+        _lib.PROFILE = None
+        # ---- end to end: pinned host inputs -> device, result -> host, every step ------------------------------
         # The public call with HOST buffers.  Two device input buffers: the upload of step i+1 (copy stream) overlaps
-        # the compute of step i; every step's inputs are copied from pinned memory and every step's detections are
-        # read back, all inside the timed region.  `serial` is the same loop without the overlap.
-        res_host = {k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("boxes", "scores", "classes", "counts")}
+        # the compute of step i; every step's inputs are copied from pinned memory and every step's result (losses /
+        # detections) is read back, all inside the timed region.  `serial` is the same loop without the overlap.
+        res_keys = ["losses"] if train else ["boxes", "scores", "classes", "counts"]
+        res_host = {k: torch.empty_like(out[k], device="cpu").pin_memory() for k in res_keys}
         e2e_steps = max(3, min(args.steps, 10))
         cur = torch.cuda.current_stream()
         cpy = torch.cuda.Stream()
-        dbuf = [(torch.empty_like(feat_d), torch.empty_like(boxes_d)) for _ in range(2)]
+        dbuf = [{k: torch.empty_like(resident[k]) for k in names} for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
 
@@ -272,8 +381,8 @@ def main():
             b = i & 1
             with torch.cuda.stream(cpy):
                 cpy.wait_event(free[b])
-                dbuf[b][0].copy_(feat_pin, non_blocking=True)
-                dbuf[b][1].copy_(boxes_pin, non_blocking=True)
+                for k in names:
+                    dbuf[b][k].copy_(host[k], non_blocking=True)
                 ready[b].record(cpy)
 
         def run_e2e(n, overlap):
@@ -287,10 +396,10 @@ def main():
                     if i + 1 < n:
                         upload(i + 1)
                     cur.wait_event(ready[b])
-                    o = step(dbuf[b][0], dbuf[b][1])
+                    o = step(dbuf[b])
                     free[b].record(cur)
                 else:
-                    o = step(feat_pin.to(dev, non_blocking=True), boxes_pin.to(dev, non_blocking=True))
+                    o = step({k: host[k].to(dev, non_blocking=True) for k in names})
                 for k in res_host:
                     res_host[k].copy_(o[k], non_blocking=True)
                 if not overlap:
@@ -322,44 +431,61 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tc_peak = float(peaks.get("bf16_tflops_sustained", 1366.0))
         R = B * P
         e = 2
         roi_bytes = B * C4 * HF * WF * e + R * 20 + R * C4 * nb * nb * e
+        roi_ms = prof.get("b200_roi_align_fwd", {}).get("ms_per_step", float("nan"))
         roi_gbs = roi_bytes / (roi_ms * 1e-3) / 1e9
-        # reference order of operations (42.5 MFLOP/ROI at K=20) vs what is executed: the d x d query
-        # GEMM is folded into the cached operand Kp.Wq, so the executed count drops by 2*2048^2 per ROI
-        flops_ref = R * (2 * (2048 ** 2 + 2 * 2048 * 1024 + 4096 * 2048 + 2 * 2048 * 1024) + 4 * 2048 * (K + 2) + 2 * 2048 * (5 * K + 1))
-        flops_fusion = flops_ref - R * 2 * 2048 ** 2
+        roi_roof = {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<%d,%d,%d> (bf16, rank 0)" % (nb, nb, bin_step),
+                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
+                    "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
+                    "timing": "CUDA events recorded around the entry point on the launching stream, mean over %d profiled steps" % prof_steps}
+        # dominant hand-written kernel of the step = the tcgen05 GEMM (all launches of the step together)
+        gem = {"ms": 0.0, "flop": 0.0, "calls": 0.0}
+        for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex"):
+            if name in prof:
+                gem["ms"] += prof[name]["ms_per_step"]
+                gem["flop"] += prof[name].get("flop_per_step", 0.0)
+                gem["calls"] += prof[name]["calls_per_step"]
+        gemm_tf = gem["flop"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] else float("nan")
+        gemm_roof = {"kernel": "gemm_bf16_tcgen05_kernel<BN> (all %d launches of the step, rank 0)" % round(gem["calls"]),
+                     "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
+                     "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gem["ms"],
+                     "timing": "CUDA events recorded around every GEMM entry-point call on the launching stream, summed per step, mean over %d profiled steps" % prof_steps}
+        ours_ms = sum(v["ms_per_step"] for v in prof.values())
+        dominant_is_gemm = gem["ms"] >= roi_ms
         line = {
             "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, B),
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(feat_pin.numel() * 4 + boxes_pin.numel() * 4),
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
                     "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in res_host.values())),
                     "pipeline": "double-buffered device inputs: upload of step i+1 on a copy stream overlaps compute of step i",
                     "serial_value": world * B * e2e_steps / (e2e["serial"] * 1e-3)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<%d,%d,%d> (bf16, rank 0)" % (nb, nb, bin_step), "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
-                         "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
-                         "timing": "CUDA events recorded around the launch on the launching stream, mean over the timed steps"},
+            "roofline": gemm_roof if dominant_is_gemm else roi_roof,
+            "roofline_other": roi_roof if dominant_is_gemm else gemm_roof,
             "stage_ms": dict(zip(stage_names, stage_ms)),
-            "kernels_only_images_per_sec": B / ((sum(stage_ms) - stage_ms[2]) * 1e-3),
-            "fusion_chain": {"tflops_executed": flops_fusion / (stage_ms[3] * 1e-3) / 1e12,
-                             "tflops_reference_equivalent": flops_ref / (stage_ms[3] * 1e-3) / 1e12,
-                             "peak_tflops": peaks.get("bf16_tflops_sustained"),
-                             "note": "whole text-fusion + predictor stage (8 tcgen05 GEMMs, attention core, LayerNorm, cast), event-timed; "
-                                     "per-GEMM tensor-pipe figures are in profiles/"},
-            "nms_us_per_image": 1e3 * stage_ms[4] / B, "candidates_per_image": n_cand, "detections_per_image": n_det,
+            "own_kernels_ms_per_step": ours_ms,
+            "own_kernels_profile": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "flop_per_step"}
+                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         }
+        if train:
+            line["losses_last_step"] = [float(v) for v in out["losses"].tolist()]
+        else:
+            line["nms_us_per_image"] = 1e3 * stage_ms[4] / B
+            line["candidates_per_image"] = out["n_candidates"].float().mean().item()
+            line["detections_per_image"] = out["counts"].float().mean().item()
         if not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = run_cpu_baseline(args.cpu_baseline_images, P, K)
+                line["cpu_baseline"] = run_cpu_baseline(args)
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line))

@@ -64,6 +64,9 @@ KERNELS_PER_CALL = {
     "b200_sgd_momentum": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1,
 }
 LAUNCHES = 0
+# bench.py sets PROFILE = {} to have a CUDA event pair recorded around every entry-point call (name -> [(e0, e1, tag)]);
+# None (the default) costs nothing
+PROFILE = None
 
 
 _lib = None
@@ -88,12 +91,20 @@ def set_option(key, value):
     return call("b200_set_option", key.encode(), int(value))
 
 
-def call(name, *args, launches=None):
+def call(name, *args, launches=None, tag=None):
     """Invoke an int-returning entry point and raise on failure.  `launches` overrides the per-call kernel count
     when the entry point dispatches to a multi-kernel implementation."""
     global LAUNCHES
     L = lib()
-    rc = getattr(L, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, name)(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1, tag))
+    else:
+        rc = getattr(L, name)(*args)
     LAUNCHES += KERNELS_PER_CALL.get(name, 0) if launches is None else launches
     if rc != 0:
         raise B200Error("%s failed (%d): %s" % (name, rc, L.b200_last_error().decode("utf-8", "replace")))

@@ -347,7 +347,8 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
     assert out.stride(1) == 1 and out.shape == (M, N)
     b32 = None if bias is None else bias.detach().float().contiguous()
     _lib.call("b200_gemm_bf16", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
-              out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu), _stream())
+              out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu), _stream(),
+              tag=2.0 * M * N * K)
     return out
 
 

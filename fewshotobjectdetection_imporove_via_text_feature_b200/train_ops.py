@@ -37,7 +37,7 @@ def gemm_ex(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, out2
     b32 = None if bias is None else bias.detach().float().contiguous()
     _lib.call("b200_gemm_bf16_ex", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
               out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu),
-              int(accumulate), _ptr(mask), 0 if mask is None else mask.stride(0), _stream())
+              int(accumulate), _ptr(mask), 0 if mask is None else mask.stride(0), _stream(), tag=2.0 * M * N * K)
     return out
 
 

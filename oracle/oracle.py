@@ -329,6 +329,66 @@ def head_forward(feat, proposals_per_image, image_shapes, text_feat, p, cross_ou
     return dets, dict(pooled=pooled, feature_pooled=x, sim2stext=sim, attn=attn, logits=logits, deltas=deltas)
 
 
+class _GDL(torch.autograd.Function):
+    """meta_arch/gdl.py:6-16 — identity forward, grad * lambda backward."""
+
+    @staticmethod
+    def forward(ctx, x, lam):
+        ctx.lam = lam
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.lam, None
+
+
+def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weights=(10.0, 10.0, 5.0, 5.0), beta=0.0):
+    """FastRCNNOutputs.losses (fast_rcnn.py:222-304) + loss_attentive (roi_heads.py:1079-1081)."""
+    from . import ref_stubs as rs
+    loss_cls = F.cross_entropy(logits, gt_classes, reduction="mean")
+    tgt = rs.Box2BoxTransform(weights).get_deltas(proposals, gt_boxes)
+    fg = torch.nonzero((gt_classes >= 0) & (gt_classes < K)).squeeze(1)
+    cols = 4 * gt_classes[fg][:, None] + torch.arange(4)
+    n = (deltas[fg[:, None], cols] - tgt[fg]).abs()
+    l1 = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n ** 2 / beta, n - 0.5 * beta)
+    return {"loss_cls": loss_cls, "loss_box_reg": l1.sum() / gt_classes.numel(),
+            "loss_attentive": loss_attentive(attn, gt_classes)}
+
+
+def head_train_step(feat, proposals_per_image, gt_classes, gt_boxes, text_feat, p, aff_w, aff_b, lam, K, drop_p=0.0,
+                    stages=None):
+    """Fine-tune direction of the head on CPU, fp32 (rcnn.py:94-98 GDL + affine_rcnn, roi_heads.py:1093-1132 in train
+    mode on pre-sampled, labelled proposals), differentiated by torch autograd: returns (losses, d(sum)/d(feat)); the
+    parameter gradients are left in `.grad` of the tensors of `p` / aff_w / aff_b that require grad."""
+    import time
+    import torchvision
+    t = [time.perf_counter()]
+
+    def tick(name):
+        if stages is not None:
+            now = time.perf_counter()
+            stages[name] = stages.get(name, 0.0) + now - t[0]
+            t[0] = now
+
+    feat = feat.detach().requires_grad_(True)
+    f = _GDL.apply(feat, lam) * aff_w + aff_b
+    rois = boxes_to_rois(proposals_per_image)
+    pooled = torchvision.ops.roi_align(f, rois, (7, 7), 1.0 / 16, 0, True)
+    tick("roi_align")
+    x = res5(pooled, p).mean(dim=[2, 3])
+    tick("res5")
+    sim, attn = sematic_proposal_attention(x, text_feat, p)
+    deltas = F.linear(x, p["box_predictor.bbox_pred.weight"], p["box_predictor.bbox_pred.bias"])
+    logits = F.linear(F.dropout(sim, drop_p, training=drop_p > 0), p["box_predictor.cls_score.weight"],
+                      p["box_predictor.cls_score.bias"])
+    props = torch.cat([torch.as_tensor(b).float() for b in proposals_per_image], 0)
+    losses = head_losses(logits, deltas, attn, gt_classes, props, gt_boxes, K)
+    tick("text_fusion_losses")
+    sum(losses.values()).backward()
+    tick("backward")
+    return losses, feat.grad
+
+
 # ------------------------------------------------------------------ AP (parity of the end metric)
 def voc_ap(rec, prec, use_07_metric=False):
     """defrcn/evaluation/pascal_voc_evaluation.py voc_ap (:227-258)."""
