@@ -501,6 +501,7 @@ static int launch_roi_fwd(const T* feat_nhwc, const float* rois, T* out, int C, 
 //    (roi_batch_offsets given), bf16 channels-last in and out, 7x7 bins; otherwise the call falls back to 0
 int g_roi_bf16_impl = 2;
 
+extern int g_roi_bwd_impl;
 size_t roi_slice_workspace_bytes(int R);
 bool roi_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step, const void* feat);
 int launch_roi_fwd_slice(const __nv_bfloat16* feat, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* out,
@@ -545,6 +546,11 @@ extern "C" int b200_set_option(const char* key, int value) {
   if (strcmp(key, "roi_align_bf16_impl") == 0) {
     B200_CHECK_ARG(value >= 0 && value <= 2, "set_option: roi_align_bf16_impl must be 0 (cuda-core), 1 (tma+mma) or 2 (slice-resident)");
     g_roi_bf16_impl = value;
+    return B200_OK;
+  }
+  if (strcmp(key, "roi_align_bwd_impl") == 0) {
+    B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bwd_impl must be 0 (gather) or 1 (slice-resident)");
+    g_roi_bwd_impl = value;
     return B200_OK;
   }
   set_error("set_option: unknown key '%s'", key);

@@ -18,6 +18,14 @@ int dispatch_affine(const void* x, const float* w, const float* b, float mult, v
 
 constexpr int kMaxP = 8;  // pooled size supported by the backward (the head uses 7)
 
+// 1 (default): slice-resident kernel (roi_align_bwd_slice.cu) for bf16 channels-last 7x7; 0: the gather kernel below
+int g_roi_bwd_impl = 1;
+bool roi_bwd_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step);
+size_t roi_bwd_slice_workspace_bytes(int R);
+int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
+                         int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
+                         void* workspace, cudaStream_t st);
+
 struct RoiExtent {
   int ylo, yhi, xlo, xhi;  // inclusive pixel ranges with non-zero weight (ylo > yhi: empty)
   float inv_count;
@@ -187,6 +195,7 @@ extern "C" size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W,
   const int pho = ceil_div(pooled_h, bin_step), pwo = ceil_div(pooled_w, bin_step);
   if (grad_out_layout == B200_NCHW) b += align_up((size_t)R * C * pho * pwo * e, 256);
   if (grad_in_layout == B200_NCHW) b += align_up((size_t)N * C * H * W * e, 256);
+  if (dtype == B200_BF16) b = max(b, roi_bwd_slice_workspace_bytes(R));
   return b;
 }
 
@@ -208,6 +217,10 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
     return B200_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (R > 0 && g_roi_bwd_impl == 1 && dtype == B200_BF16 && grad_out_layout == B200_NHWC && grad_in_layout == B200_NHWC &&
+      roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step) && (((uintptr_t)grad_out | (uintptr_t)grad_feat) & 15) == 0)
+    return launch_roi_bwd_slice((const __nv_bfloat16*)grad_out, rois, roi_batch_offsets, (__nv_bfloat16*)grad_feat, N, C, H, W,
+                                R, pooled_h, pooled_w, bin_step, spatial_scale, sampling_ratio, aligned, workspace, st);
   unsigned char* p = (unsigned char*)workspace;
   BwdTables t;
   t.ta = (float*)p;      p += align_up((size_t)R * H * kMaxP * 4, 256);

@@ -20,26 +20,9 @@
 
 #include "common.cuh"
 #include "roi_geom.cuh"
+#include "roi_slice_rec.cuh"
 
 namespace b200 {
-
-constexpr int kSliceCh = 32;                 // channels per resident slice (64 B per pixel)
-constexpr int kPixBytes = kSliceCh * 2;
-constexpr int kRecBytes = 1024;              // per-ROI geometry record
-constexpr int kRecChunks = kRecBytes / 16;
-constexpr int kSliceWarps = 16;
-constexpr int kRecRing = 2;                  // geometry records per warp (one in use, one in flight)
-constexpr int kMaxXs = 64;                   // distinct pixel columns an ROI may touch on the table path
-constexpr int kTaps = 9;                     // weight slots per bin and axis (sampling grid <= 8: any ROI of a 38x50 map)
-constexpr int kTabTiles = 3;                 // 8-pixel tiles whose B-fragment weights are tabulated in the record
-constexpr int kStageBytes = 7 * 512;         // epilogue staging per warp: PHO x [8 pw][32 ch] bf16
-
-// record layout (bytes)
-constexpr int kOffBatch = 0, kOffFlags = 4, kOffNxs = 8, kOffNyMax = 12;
-constexpr int kOffYStart = 16, kOffYCount = 24, kOffXStart = 32, kOffXCount = 40, kOffXs = 48;
-constexpr int kOffWy = 128;                  // u32 [7][kTaps], zero padded: bf16x2 (a,a), a = vertical weight / count
-constexpr int kOffWx = 384;                  // fp32 [7][kTaps], zero padded: horizontal weights (tiles >= kTabTiles)
-constexpr int kOffXw2 = 640;                 // u32 [kTabTiles][32 lanes]: bf16x2 B-fragment weights of lane (g,t)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -160,8 +143,14 @@ roi_slice_prepare_kernel(const float* __restrict__ rois, unsigned char* __restri
         }
       }
     }
-    int nymax = 0;
-    for (int ph = 0; ph < PH; ph += bin_step) nymax = max(nymax, (int)rec[kOffYCount + ph]);
+    int nymax = 0, ylo = 1 << 20, yhi = -1;
+    for (int ph = 0; ph < PH; ph += bin_step) {
+      const int yc = rec[kOffYCount + ph];
+      nymax = max(nymax, yc);
+      if (yc > 0) { ylo = min(ylo, (int)rec[kOffYStart + ph]); yhi = max(yhi, (int)rec[kOffYStart + ph] + yc - 1); }
+    }
+    reinterpret_cast<int*>(rec)[kOffYExt / 4] = ylo;
+    reinterpret_cast<int*>(rec)[kOffYExt / 4 + 1] = yhi;
     reinterpret_cast<int*>(rec)[kOffBatch / 4] = g.batch;
     reinterpret_cast<int*>(rec)[kOffFlags / 4] = ok ? 1 : 0;
     reinterpret_cast<int*>(rec)[kOffNxs / 4] = ok ? n : 0;
@@ -419,6 +408,13 @@ static size_t slice_smem_bytes(int H, int Wp) {
   return (size_t)H * Wp * kPixBytes + kSliceWarps * kRecRing * kRecBytes + kSliceWarps * kStageBytes + 1024;
 }
 
+int launch_roi_slice_prepare(const float* rois, unsigned char* recs, int R, int H, int W, int PH, int PW, int bin_step,
+                             float scale, int sr, int aligned, cudaStream_t st) {
+  roi_slice_prepare_kernel<<<ceil_div(R, 8), 256, 0, st>>>(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned);
+  B200_CUDA_LAUNCH_CHECK("roi_slice_prepare");
+  return B200_OK;
+}
+
 size_t roi_slice_workspace_bytes(int R) { return align_up((size_t)max(R, 1) * kRecBytes, 256); }
 
 // true when the slice-resident kernel can run this problem (bf16, channels-last in/out, ROIs grouped by image)
@@ -437,8 +433,8 @@ int launch_roi_fwd_slice(const __nv_bfloat16* feat, const float* rois, const int
   int rc = make_slice_map(&fmap, feat, N, C, H, W, Wp);
   if (rc != B200_OK) return rc;
   unsigned char* recs = (unsigned char*)workspace;
-  roi_slice_prepare_kernel<<<ceil_div(R, 8), 256, 0, st>>>(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned);
-  B200_CUDA_LAUNCH_CHECK("roi_slice_prepare");
+  rc = launch_roi_slice_prepare(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
+  if (rc != B200_OK) return rc;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

@@ -87,6 +87,46 @@ class Conv2d(nn.Conv2d):
         return w, None if b is None else b.to(dtype)
 
 
+class _FrozenBottleneckFn(torch.autograd.Function):
+    """Bottleneck block with frozen, BN-folded weights (ROI_HEADS.FREEZE_FEAT fine-tuning): the forward runs cuDNN's
+    runtime-fused conv+bias+ReLU(+residual) kernels exactly like inference, the backward propagates only the data
+    gradient (no weight gradients exist) — one cuDNN dgrad per convolution plus the ReLU masks.  res5 stays on
+    cuDNN; this node only removes the autograd overhead of the unfused expression."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, wsc, bsc, s1, ssc, conv2_args):
+        stride2, pad2, dil2, groups2 = conv2_args
+        out1 = torch.cudnn_convolution_relu(x, w1, b1, s1, (0, 0), (1, 1), 1)
+        out2 = torch.cudnn_convolution_relu(out1, w2, b2, stride2, pad2, dil2, groups2)
+        if wsc is None:
+            res, bias3 = x, b3
+        else:
+            res = F.conv2d(x, wsc, None, ssc)
+            bias3 = b3 if bsc is None else b3 + bsc
+        out = torch.cudnn_convolution_add_relu(out2, w3, res, 1.0, bias3, (1, 1), (0, 0), (1, 1), 1)
+        ctx.save_for_backward(x, out1, out2, out, w1, w2, w3, wsc if wsc is not None else w1)
+        ctx.meta = (s1, ssc, conv2_args, wsc is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out1, out2, out, w1, w2, w3, wsc = ctx.saved_tensors
+        s1, ssc, (stride2, pad2, dil2, groups2), has_sc = ctx.meta
+        relu_bwd = torch.ops.aten.threshold_backward
+
+        def dgrad(g_out, inp, w, stride=(1, 1), pad=(0, 0), dil=(1, 1), groups=1):
+            # data gradient only (output_mask): the input tensor is passed for its shape / layout, its values are unused
+            return torch.ops.aten.convolution_backward(g_out, inp, w, None, list(stride), list(pad), list(dil), False, [0, 0],
+                                                       groups, [True, False, False])[0]
+
+        g = relu_bwd(g.contiguous(memory_format=torch.channels_last), out, 0)
+        g2 = relu_bwd(dgrad(g, out2, w3), out2, 0)
+        g1 = relu_bwd(dgrad(g2, out1, w2, stride2, pad2, dil2, groups2), out1, 0)
+        gx = dgrad(g1, x, w1, s1)
+        gx = gx + (dgrad(g, x, wsc, ssc) if has_sc else g)
+        return (gx,) + (None,) * 11
+
+
 class BottleneckBlock(nn.Module):
     def __init__(self, in_channels, out_channels, *, bottleneck_channels, stride=1, num_groups=1, norm="BN",
                  stride_in_1x1=False, dilation=1):
@@ -136,6 +176,10 @@ class BottleneckBlock(nn.Module):
             self._fold = [None if c is None else c.folded(x.dtype, cl) for c in convs]
             self._fold_key = key
         (w1, b1), (w2, b2), (w3, b3), sc = self._fold
+        if _FUSED_CONV["ok"] and x.is_cuda and torch.is_grad_enabled() and x.requires_grad:
+            return _FrozenBottleneckFn.apply(
+                x, w1, b1, w2, b2, w3, b3, None if sc is None else sc[0], None if sc is None else sc[1], s1, ssc,
+                (self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups))
         if _FUSED_CONV["ok"] and x.is_cuda and not torch.is_grad_enabled():
             try:   # cuDNN runtime-fused conv + bias + ReLU (+ residual add): no separate elementwise kernels
                 out = torch.cudnn_convolution_relu(x, w1, b1, s1, (0, 0), (1, 1), 1)

@@ -43,7 +43,8 @@ B200_API int b200_abi_version(void);
 B200_API const char* b200_last_error(void);
 /* process-wide implementation switches (for A/B measurement; results are parity-tested under every setting):
  *   "roi_align_bf16_impl": 0 = CUDA-core per-bin-window kernel, 1 = per-ROI TMA + ldmatrix + mma.sync kernel,
- *                          2 = slice-resident TMA + ldmatrix + mma.sync kernel (default; needs roi_batch_offsets) */
+ *                          2 = slice-resident TMA + ldmatrix + mma.sync kernel (default; needs roi_batch_offsets)
+ *   "roi_align_bwd_impl":  0 = per-pixel gather kernel, 1 = slice-resident row-owner kernel (default, bf16 NHWC 7x7) */
 B200_API int b200_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -143,6 +143,43 @@ def test_bwd_bin_step(cl):
     torch.testing.assert_close(xd.grad.cpu().contiguous(), ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("N,C,H,W,R", [(2, 64, 38, 50, 90), (3, 32, 25, 31, 61), (1, 1024, 38, 50, 40)])
+@pytest.mark.parametrize("bin_step", [1, 2])
+def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
+    """Slice-resident backward (roi_align_bwd_slice.cu: smem-resident fp32 gradient slice, row-owner accumulation):
+    vs the CPU oracle (2e-2: bf16 gradient in, bf16 map out, bf16 vertical weights), vs the gather kernel, and bitwise
+    run-to-run."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+    scale = 1 / 16
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 23)
+    nb = -(-7 // bin_step)
+    g = torch.randn(R, C, nb, nb, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16)
+    gfull = torch.zeros(R, C, 7, 7)
+    gfull[:, :, ::bin_step, ::bin_step] = g.float()
+    ref = O.roi_align_bwd(gfull, rois, x.shape, scale, 0, True)
+    xd = x.to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    gd = g.cuda().contiguous(memory_format=torch.channels_last)
+
+    def run():
+        xin = xd.clone().requires_grad_(True)
+        out = ops.roi_align(xin, rois.cuda(), 7, scale, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda(),
+                            bin_step=bin_step)
+        out.backward(gd)
+        return xin.grad
+    got = run()
+    assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    gf = got.float().cpu().contiguous()
+    assert float((gf - ref).norm() / ref.norm()) < 8e-3
+    torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    assert torch.equal(got, run())                                  # fixed summation order
+    _lib.set_option("roi_align_bwd_impl", 0)
+    try:
+        base = run()
+    finally:
+        _lib.set_option("roi_align_bwd_impl", 1)
+    assert float((got.float() - base.float()).norm() / base.float().norm()) < 8e-3
+
+
 @pytest.mark.parametrize("cl", [False, True])
 def test_bwd_fp32(cl):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
