@@ -356,6 +356,11 @@ def main():
             step(resident)
         torch.cuda.synchronize()
         prof = {}
+        if os.environ.get("BENCH_DUMP_CALLS"):
+            for name, rows in _lib.PROFILE.items():
+                for a, b, t in rows[: len(rows) // prof_steps]:
+                    ms = a.elapsed_time(b)
+                    print("CALL %-34s %8.4f ms %s" % (name, ms, ("%.1f GF  %.0f TF/s" % (t / 1e9, t / ms / 1e9)) if t else ""), file=sys.stderr)
         for name, rows in _lib.PROFILE.items():
             ms = sum(a.elapsed_time(b) for a, b, _ in rows) / prof_steps
             fl = sum(t for _, _, t in rows if t) / prof_steps

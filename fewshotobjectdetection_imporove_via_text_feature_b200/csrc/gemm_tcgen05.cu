@@ -207,13 +207,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const bool full = col + 32 <= N;
         if (mask) {   // backward of a ReLU: zero where the forward activation was not positive
           const __nv_bfloat16* mrow = mask + (size_t)row * ldmask + col;
-          for (int i = 0; i < 32; ++i)
-            if (col + i < N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+          if (full && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 m = *reinterpret_cast<const uint4*>(mrow + 8 * i);
+              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero (NaN masks count as positive, as x > 0 is false
+                // only for them in the reference too: the forward never produces NaN activations)
+                const uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
+                if ((lo & 0x8000u) || !(lo & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
+                if ((hi & 0x8000u) || !(hi & 0x7fffu)) v[8 * i + 2 * j + 1] = 0.f;
+              }
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col + i < N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+          }
         }
         if (accumulate && d_f32) {   // D += result (gradient accumulation over several producers)
           const float* src = d_f32 + (size_t)row * ldd + col;
-          for (int i = 0; i < 32; ++i)
-            if (col + i < N) v[i] += src[i];
+          if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 t = reinterpret_cast<const float4*>(src)[i];
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col + i < N) v[i] += src[i];
+          }
         }
         if (d_f32) {
           float* dst = d_f32 + (size_t)row * ldd + col;

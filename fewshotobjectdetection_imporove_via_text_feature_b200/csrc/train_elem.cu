@@ -22,31 +22,53 @@ __device__ __forceinline__ uint32_t t_pack(float a, float b) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const T* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst, int rows,
-                      int cols) {
-  __shared__ __nv_bfloat16 tile[64][66];
+                      int cols, int vec_ok) {
+  __shared__ __nv_bfloat16 tile[64][72];     // [src row][src col]; 144-byte pitch keeps the 16-byte rows aligned
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (int i = ty; i < 64; i += 8) {
-    const int r = r0 + i;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = c0 + tx + 32 * j;
-      float v = 0.f;
-      if (r < rows && c < cols) {
-        if (sizeof(T) == 4) v = reinterpret_cast<const float*>(src)[(size_t)r * ld_src + c];
-        else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[(size_t)r * ld_src + c]);
+  // load: 64 rows x 8 groups of 8 columns; thread t -> row t / 8 (+32), column group t % 8
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int lr = i >> 3, gc = (i & 7) * 8;
+    const int r = r0 + lr, c = c0 + gc;
+    __nv_bfloat16 v[8];
+    if (vec_ok && r < rows && c + 8 <= cols) {
+      if (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)r * ld_src + c);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)r * ld_src + c + 4);
+        v[0] = __float2bfloat16_rn(a.x); v[1] = __float2bfloat16_rn(a.y); v[2] = __float2bfloat16_rn(a.z); v[3] = __float2bfloat16_rn(a.w);
+        v[4] = __float2bfloat16_rn(b.x); v[5] = __float2bfloat16_rn(b.y); v[6] = __float2bfloat16_rn(b.z); v[7] = __float2bfloat16_rn(b.w);
+      } else {
+        *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + (size_t)r * ld_src + c);
       }
-      tile[i][tx + 32 * j] = __float2bfloat16_rn(v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float f = 0.f;
+        if (r < rows && c + k < cols) {
+          if (sizeof(T) == 4) f = reinterpret_cast<const float*>(src)[(size_t)r * ld_src + c + k];
+          else f = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[(size_t)r * ld_src + c + k]);
+        }
+        v[k] = __float2bfloat16_rn(f);
+      }
     }
+    // 8-column groups are XOR-swizzled with the row's 8-row block so that the transposed reads below (8 lanes, rows
+    // 8 apart, same column) fall on 8 different 16-byte bank groups
+    *reinterpret_cast<uint4*>(&tile[lr][gc ^ ((lr >> 3) << 3)]) = *reinterpret_cast<const uint4*>(v);
   }
   __syncthreads();
-  for (int i = ty; i < 64; i += 8) {
-    const int c = c0 + i;   // destination row
+  // store: destination row = source column; 8 consecutive source rows per 16-byte store
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {
+    const int lc = i >> 3, gr = (i & 7) * 8;
+    const int c = c0 + lc, r = r0 + gr;
     if (c >= cols) continue;
+    __nv_bfloat16 v[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int r = r0 + tx + 32 * j;
-      if (r < rows) dst[(size_t)c * ld_dst + r] = tile[tx + 32 * j][i];
+    for (int k = 0; k < 8; ++k) v[k] = tile[gr + k][lc ^ gr];      // (gr + k) >> 3 == gr >> 3; gr is a multiple of 8
+    __nv_bfloat16* d = dst + (size_t)c * ld_dst + r;
+    if (r + 8 <= rows && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(v);
+    } else {
+      for (int k = 0; k < 8; ++k)
+        if (r + k < rows) d[k] = v[k];
     }
   }
 }
@@ -437,10 +459,12 @@ extern "C" int b200_transpose_bf16(const void* src, int src_dtype, int ld_src, v
   if (rows == 0 || cols == 0) return B200_OK;
   B200_CHECK_ARG(src && dst && ld_src >= cols && ld_dst >= rows, "transpose_bf16: null tensor or short leading dimension");
   dim3 grid(ceil_div(cols, 64), ceil_div(rows, 64));
+  const int esz = src_dtype == B200_F32 ? 4 : 2;
+  const int vec_ok = (((uintptr_t)src & 15) == 0) && ((size_t)ld_src * esz % 16 == 0);
   if (src_dtype == B200_F32)
-    transpose_bf16_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+    transpose_bf16_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, vec_ok);
   else
-    transpose_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+    transpose_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, vec_ok);
   B200_CUDA_LAUNCH_CHECK("transpose_bf16");
   return B200_OK;
 }
