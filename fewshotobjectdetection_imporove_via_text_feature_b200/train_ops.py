@@ -147,16 +147,35 @@ class _FusedHeadTrain(torch.autograd.Function):
                   gt.data_ptr(), props.data_ptr(), gtb.data_ptr(), g3.data_ptr(), R, K, L, int(agnostic),
                   *map(float, box_w), float(l1_beta), dlogits.data_ptr(), C1p, ddeltas.data_ptr(), C4p, _ptr(dattn), st)
 
-        xcatT = transpose_bf16(xcat)                       # (2d, Rp): rows [d, 2d) are x^T
-        xbT = xcatT[d:]
+        # Two streams: the data-gradient chain (dX GEMMs, LayerNorm / attention backward) is the critical path and stays
+        # on the current stream; everything that only feeds parameter gradients (operand transposes, dW GEMMs, bias
+        # column sums) runs on a side stream behind an event, filling the SMs the skinny / tail waves leave idle.
+        main = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        out = {}
+
+        def fork(fn):
+            e = torch.cuda.Event()
+            e.record(main)
+            side.wait_event(e)
+            with torch.cuda.stream(side):
+                fn()
+
+        def side_acts():     # transposes of saved forward activations: no dependence on any gradient
+            out["xcatT"] = transpose_bf16(xcat)             # (2d, Rp): rows [d, 2d) are x^T
+            out["zdT"], out["hdnT"], out["ybT"] = transpose_bf16(zd), transpose_bf16(hdn), transpose_bf16(yb)
+            out["p1T"], out["p2T"], out["attnT"] = transpose_bf16(p1), transpose_bf16(p2), transpose_bf16(attn)
+        fork(side_acts)
+
         # ---- C1: logits = zd Wc^T + bc ; deltas = xb Wb^T + bb -------------------------------------------------
-        dlogitsT, ddeltasT = transpose_bf16(dlogits), transpose_bf16(ddeltas)
+        def side_c1():
+            out["dWc"] = gemm_ex(transpose_bf16(dlogits), out["zdT"])[:C1]
+            out["dbc"] = colsum(dlogits, C1)
+            out["dWb"] = gemm_ex(transpose_bf16(ddeltas), out["xcatT"][d:])[:C4]
+            out["dbb"] = colsum(ddeltas, C4)
+        fork(side_c1)
         dzd = gemm_ex(dlogits, _wT(Wc, C1p), out_dtype=torch.bfloat16)
-        dWc = gemm_ex(dlogitsT, transpose_bf16(zd))[:C1]
-        dbc = colsum(dlogits, C1)
         dx = gemm_ex(ddeltas, _wT(Wb, C4p))                                        # first producer of dL/dx (fp32)
-        dWb = gemm_ex(ddeltasT, xbT)[:C4]
-        dbb = colsum(ddeltas, C4)
         # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
         du = torch.empty((R, d), dtype=torch.float32, device=dev)
         dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
@@ -168,38 +187,64 @@ class _FusedHeadTrain(torch.autograd.Function):
                   bet.data_ptr(), 1e-5, float(drop_p), int(seed), du.data_ptr(), dub.data_ptr(), dgamma.data_ptr(),
                   dbeta.data_ptr(), R, d, ws.data_ptr(), nb, st)
         # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
-        dubT = transpose_bf16(dub)
+        def side_ffn2():
+            out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"])
+            out["dbf2"] = colsum(dub)        # the bf16 copy: `du` is overwritten in place by the dy GEMM below
+        fork(side_ffn2)
         dhdn = gemm_ex(dub, _wT(Wf2, d), out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
-        dWf2 = gemm_ex(dubT, transpose_bf16(hdn))
-        dbf2 = colsum(du)
+
+        def side_ffn1():
+            out["dWf1"] = gemm_ex(transpose_bf16(dhdn), out["ybT"])
+            out["dbf1"] = colsum(dhdn)
+        fork(side_ffn1)
         dyb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         gemm_ex(dhdn, _wT(Wf1, Wf1.shape[0]), out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
-        dWf1 = gemm_ex(transpose_bf16(dhdn), transpose_bf16(yb))
-        dbf1 = colsum(dhdn)
         # ---- linear3: y = [o1 | o2 | xb] W3^T + b3 -----------------------------------------------------------
+        def side_l3():
+            out["dW3"] = gemm_ex(transpose_bf16(dyb), out["xcatT"])
+            out["db3"] = colsum(du)
+        fork(side_l3)
         W3T = _wT(W3, d)                                                           # (2d, d)
         do12 = gemm_ex(dyb, W3T[:d], out_dtype=torch.bfloat16, mask=xcat[:, :d])   # [do1 | do2], ReLU backward fused
         gemm_ex(dyb, W3T[d:], out=dx, accumulate=True)
-        dW3 = gemm_ex(transpose_bf16(dyb), xcatT)
-        db3 = colsum(du)
         # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
-        do12T = transpose_bf16(do12)
+        def side_l12():
+            do12T = transpose_bf16(do12)
+            out["dW1"] = gemm_ex(do12T[:h], out["p1T"])
+            out["dW2"] = gemm_ex(do12T[h:], out["p2T"])
+            out["db12"] = colsum(do12)
+        fork(side_l12)
         dp1 = gemm_ex(do12[:, :h], _wT(W1, h), out_dtype=torch.bfloat16)
         dp2 = gemm_ex(do12[:, h:], _wT(W2, h), out_dtype=torch.bfloat16)
-        dW1 = gemm_ex(do12T[:h], transpose_bf16(p1))
-        dW2 = gemm_ex(do12T[h:], transpose_bf16(p2))
-        db12 = colsum(do12)
         # ---- A3 core: P1 = O * x, P2 = x - O, O = softmax(S) Vp ------------------------------------------------
         dO = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         dS = torch.empty((R, Lp), dtype=torch.bfloat16, device=dev)
         _lib.call("b200_text_attention_bwd", dp1.data_ptr(), dp2.data_ptr(), dp1.stride(0), x.data_ptr(), attn.data_ptr(),
                   vp.data_ptr(), _ptr(dattn), dx.data_ptr(), 1, dO.data_ptr(), dS.data_ptr(), Lp, R, d, L, st)
-        dvp = gemm_ex(transpose_bf16(attn), transpose_bf16(dO))                    # (L, d)
+
+        def side_att():
+            out["dvp"] = gemm_ex(out["attnT"], transpose_bf16(dO))                 # (L, d)
+            out["dkq"] = gemm_ex(transpose_bf16(dS), out["xcatT"][d:])[:L]
+        fork(side_att)
         # ---- scores: S = xb Kq^T ----------------------------------------------------------------------------------
         gemm_ex(dS, _wT(kq, Lp), out=dx, accumulate=True)
-        dkq = gemm_ex(transpose_bf16(dS), xbT)[:L]
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+        dkq, dvp, dW1, dW2, dW3, dWf1, dWf2, dWc, dWb = (out[k] for k in ("dkq", "dvp", "dW1", "dW2", "dW3", "dWf1", "dWf2", "dWc", "dWb"))
+        db12, db3, dbf1, dbf2, dbc, dbb = (out[k] for k in ("db12", "db3", "dbf1", "dbf2", "dbc", "dbb"))
         return (dx, dkq, dvp, dW1, db12[:h], dW2, db12[h:], dW3, db3, dWf1, dbf1, dWf2, dbf2, dgamma, dbeta, dWc, dbc,
                 dWb, dbb) + (None,) * 9
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def _wT(w, k_pad):
