@@ -241,16 +241,11 @@ class SematicRes5ROIHeads(Res5ROIHeads):
     def fused_train_losses(self, feature_pooled, proposals, gt_classes):
         """Fine-tune direction on the hand-written kernels (train_ops._FusedHeadTrain): text-fusion chain, predictor
         with classifier dropout, and the three losses in one autograd node; same numbers as `forward_att` +
-        `FastRCNNOutputs.losses` (roi_heads.py:1060-1132) up to bf16 GEMM operands.  The (K+2)-row text side stays
-        in plain torch: it is ~0.5 % of the FLOPs and its gradients arrive as dKq / dVp."""
+        `FastRCNNOutputs.losses` (roi_heads.py:1060-1132) up to bf16 GEMM operands.  The (K+2)-row text side runs in
+        fp32 on its own small kernels (train_ops._TextSide) and receives dKq / dVp from the fused node."""
         from ... import train_ops
         att, sa = self.attention, self.attention.attention
-        d = feature_pooled.shape[1]
-        T = att.forward_language_model()["text_feat"]
-        kt, vt = F.relu(att.key_projection(T)), F.relu(att.value_projection(T))
-        kp = torch.cat([sa.w_k(kt), sa.dummy.reshape(1, -1)], dim=0)
-        vp = torch.cat([sa.w_v(vt), kt.new_zeros(1, d)], dim=0)
-        kq = (kp @ sa.w_q.weight) / float(np.power(d, 0.5))
+        kq, vp = train_ops.text_side(att)
         props = cat([p.proposal_boxes.tensor for p in proposals], dim=0)
         gtb = cat([p.gt_boxes.tensor for p in proposals], dim=0)
         pred = self.box_predictor

@@ -83,6 +83,89 @@ def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weight
     return out
 
 
+def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias=False):
+    """fp32 contractions with a short side (csrc/text_side.cu).  mode 'nt': A (M,K), B (N,K) -> (M,N);
+    'nn': A (M,N), B (N,K) -> (M,K); 'tn': A (M,N), B (M,K) -> (N,K) [+ column sums of A].  Taller A goes in row blocks
+    of 32 (the big operand B is streamed once per block)."""
+    A, B = A.float(), B.float()
+    if A.stride(-1) != 1:
+        A = A.contiguous()
+    if B.stride(-1) != 1:
+        B = B.contiguous()
+    M = A.shape[0]
+    dev = A.device
+    code = {"nt": 0, "nn": 1, "tn": 2}[mode]
+    if mode == "nt":
+        N, K = B.shape[0], B.shape[1]
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    elif mode == "nn":
+        N, K = B.shape
+        out = torch.empty((M, K), dtype=torch.float32, device=dev)
+    else:
+        N, K = A.shape[1], B.shape[1]
+        out = torch.empty((N, K), dtype=torch.float32, device=dev)
+    ob = torch.empty(N, dtype=torch.float32, device=dev) if (out_bias and mode == "tn") else None
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    nbytes = _lib.lib().b200_skinny_gemm_workspace_bytes(min(M, 32), K) if mode == "nn" else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
+    for m0 in range(0, M, 32):
+        mb = min(32, M - m0)
+        a = A[m0:m0 + mb]
+        ref = None if relu_ref is None else relu_ref[m0:m0 + mb]
+        b = B[m0:m0 + mb] if mode == "tn" else B
+        o = out if mode == "tn" else out[m0:m0 + mb]
+        _lib.call("b200_skinny_gemm", code, a.data_ptr(), a.stride(0), _ptr(ref), 0 if ref is None else ref.stride(0),
+                  b.data_ptr(), b.stride(0), _ptr(b32), int(relu), float(scale), o.data_ptr(), o.stride(0), _ptr(ob), mb, N, K,
+                  int(mode == "tn" and m0 > 0), _ptr(ws), nbytes, _stream(), launches=2 if mode == "nn" else 1)
+    return (out, ob) if (out_bias and mode == "tn") else out
+
+
+class _TextSide(torch.autograd.Function):
+    """(T, key_projection, value_projection, w_k, w_v, dummy, w_q) -> (Kq (L,d) = [w_k(relu(key_proj T)); dummy] Wq / sqrt(d),
+    Vp (L,d) = [w_v(relu(value_proj T)); 0]) — attentive_modules.py:274-277,125-135 plus the folded query operand."""
+
+    @staticmethod
+    def forward(ctx, T, Wkp, bkp, Wvp, bvp, Wk, Wv, dummy, Wq):
+        _require_cuda(T, Wkp, Wvp, Wk, Wv, dummy, Wq)
+        f = lambda t: t.detach().float().contiguous()
+        T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq = map(f, (T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq))
+        d = Wq.shape[0]
+        kt = skinny("nt", T, Wkp, bkp, relu=True)
+        vt = skinny("nt", T, Wvp, bvp, relu=True)
+        kp = torch.cat([skinny("nt", kt, Wk), f(dummy).reshape(1, -1)], 0)
+        vp = torch.cat([skinny("nt", vt, Wv), kt.new_zeros(1, d)], 0)
+        kq = skinny("nn", kp, Wq, scale=1.0 / float(d) ** 0.5)
+        ctx.save_for_backward(T, kt, vt, kp, Wk, Wv, Wq)
+        return kq, vp
+
+    @staticmethod
+    def backward(ctx, dkq, dvp):
+        T, kt, vt, kp, Wk, Wv, Wq = ctx.saved_tensors
+        d = Wq.shape[0]
+        s = 1.0 / float(d) ** 0.5
+        dkq = (dkq.float() * s).contiguous()
+        dvp = dvp.float().contiguous()
+        dkp = skinny("nt", dkq, Wq)                               # dKp = dKq Wq^T
+        dWq = skinny("tn", kp, dkq)                               # dWq[i][j] = sum_l Kp[l][i] dKq[l][j]
+        ddummy = dkp[-1:].clone()
+        dkp0, dvp0 = dkp[:-1], dvp[:-1]
+        dWk = skinny("tn", dkp0, kt)
+        dWv = skinny("tn", dvp0, vt)
+        dkt = skinny("nn", dkp0, Wk)                              # before the ReLU mask (applied as relu_ref below)
+        dvt = skinny("nn", dvp0, Wv)
+        dWkp, dbkp = skinny("tn", dkt, T, relu_ref=kt, out_bias=True)
+        dWvp, dbvp = skinny("tn", dvt, T, relu_ref=vt, out_bias=True)
+        return None, dWkp, dbkp, dWvp, dbvp, dWk, dWv, ddummy, dWq
+
+
+def text_side(att):
+    """att: SematicProposalAttention -> (Kq, Vp) with autograd through the hand-written fp32 kernels."""
+    sa = att.attention
+    T = att.forward_language_model()["text_feat"]
+    return _TextSide.apply(T, att.key_projection.weight, att.key_projection.bias, att.value_projection.weight,
+                           att.value_projection.bias, sa.w_k.weight, sa.w_v.weight, sa.dummy, sa.w_q.weight)
+
+
 class _FusedHeadTrain(torch.autograd.Function):
     """(x, kq, vp, weights..., labels) -> (losses (3,), logits (R,K+1) [non-differentiable, for logging])."""
 

@@ -203,6 +203,15 @@ B200_API int b200_head_losses_bwd(const float* logits, const float* deltas, cons
                          const float* proposals, const float* gt_boxes, const float* grad_scale3, int R, int K, int L,
                          int cls_agnostic, float wx, float wy, float ww, float wh, float smooth_l1_beta,
                          void* dlogits_bf16, int ldl, void* ddeltas_bf16, int ldd, float* dattn, b200_stream_t stream);
+/* T1 + text half of A1/A2 (attentive_modules.py:274-277, :125-135; Kq = Kp Wq / sqrt(d)): fp32 contractions with at
+ * most 32 rows on one side, forward and backward (tensor-core tiles would be > 80 % padding; cuBLAS takes 30-50 us per
+ * call here).  mode 0 "NT": out[m][n] = act(sum_k A[m][k] B[n][k] + bias[n]);  mode 1 "NN": out[m][k] = scale *
+ * sum_n A'[m][n] B[n][k];  mode 2 "TN": out[n][k] (+)= sum_m A'[m][n] B[m][k], out_bias[n] (+)= sum_m A'[m][n].
+ * A' = A zeroed where relu_ref <= 0 (ReLU backward; relu_ref may be NULL).  M <= 32 per call. */
+B200_API size_t b200_skinny_gemm_workspace_bytes(int M, int K);
+B200_API int b200_skinny_gemm(int mode, const float* A, int lda, const float* relu_ref, int ldref, const float* B, int ldb,
+                     const float* bias, int relu, float scale, float* out, int ldo, float* out_bias, int M, int N, int K,
+                     int accumulate, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 /* torch.optim.SGD step over one flat fp32 buffer: g += wd*p; m = mu*m + g; p -= lr*m (defrcn/solver/build.py) */
 B200_API int b200_sgd_momentum(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
                       float weight_decay, b200_stream_t stream);

@@ -201,3 +201,23 @@ def test_transpose_and_colsum(rows, cols, dt):
     s = train_ops.colsum(x)
     torch.testing.assert_close(s, x.float().sum(0), rtol=1e-4, atol=1e-3)
     assert torch.equal(s, train_ops.colsum(x))
+
+
+@pytest.mark.parametrize("M,N,K", [(21, 2048, 512), (22, 2048, 2048), (81, 2048, 300 // 4 * 4), (5, 64, 32), (33, 100, 64)])
+def test_skinny_gemm_modes_vs_fp64(M, N, K):
+    """Text-side fp32 contractions (csrc/text_side.cu) against torch in fp64 on the host; fp32 bar 1e-5 relative.
+    Covers the K+1 = 21 / 81 row text matrices (row blocks of 32), ReLU masking and the bias column sums."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    gen = torch.Generator().manual_seed(M * 7 + N)
+    A, W, b = torch.randn(M, K, generator=gen), torch.randn(N, K, generator=gen) / K ** 0.5, torch.randn(N, generator=gen)
+    out = train_ops.skinny("nt", A.cuda(), W.cuda(), b.cuda(), relu=True)
+    ref = torch.relu(A.double() @ W.double().t() + b.double())
+    assert _rel(out.cpu(), ref) < 1e-5
+    G = torch.randn(M, N, generator=gen)
+    dA = train_ops.skinny("nn", G.cuda(), W.cuda(), scale=0.5)
+    assert _rel(dA.cpu(), 0.5 * (G.double() @ W.double())) < 1e-5
+    assert torch.equal(dA, train_ops.skinny("nn", G.cuda(), W.cuda(), scale=0.5))          # ordered partial sums
+    Gm = torch.where(ref > 0, G.double(), torch.zeros((), dtype=torch.float64))
+    dW, db = train_ops.skinny("tn", G.cuda(), A.cuda(), relu_ref=out, out_bias=True)
+    assert _rel(dW.cpu(), Gm.t() @ A.double()) < 1e-5
+    assert _rel(db.cpu(), Gm.sum(0)) < 1e-5
