@@ -18,10 +18,10 @@ int dispatch_affine(const void* x, const float* w, const float* b, float mult, v
 
 constexpr int kMaxP = 8;  // pooled size supported by the backward (the head uses 7)
 
-// 1 (default): slice-resident kernel (roi_align_bwd_slice.cu) for bf16 channels-last 7x7; 0: the gather kernel below
+// 1 (default): per-pixel CSR gather (roi_align_bwd_slice.cu) for bf16 channels-last 7x7; 0: the table kernel below
 int g_roi_bwd_impl = 1;
 bool roi_bwd_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step);
-size_t roi_bwd_slice_workspace_bytes(int R);
+size_t roi_bwd_slice_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step);
 int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
                          int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
                          void* workspace, cudaStream_t st);
@@ -195,7 +195,8 @@ extern "C" size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W,
   const int pho = ceil_div(pooled_h, bin_step), pwo = ceil_div(pooled_w, bin_step);
   if (grad_out_layout == B200_NCHW) b += align_up((size_t)R * C * pho * pwo * e, 256);
   if (grad_in_layout == B200_NCHW) b += align_up((size_t)N * C * H * W * e, 256);
-  if (dtype == B200_BF16) b = max(b, roi_bwd_slice_workspace_bytes(R));
+  if (dtype == B200_BF16 && roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step))
+    b = max(b, roi_bwd_slice_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step));
   return b;
 }
 

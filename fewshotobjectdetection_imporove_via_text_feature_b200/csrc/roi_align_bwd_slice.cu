@@ -1,226 +1,354 @@
-// P1b: ROIAlign backward, row-gather bf16 kernel — atomic-free, deterministic, the fine-tune path's default.
-// Reference: autograd of the roi_align call at defrcn/modeling/roi_heads/roi_heads.py:340 (torchvision scatters with
-// atomicAdd; fine-tuning reaches it with BACKWARD_SCALE = 0.001 through the GDL).
+// P1b: ROIAlign backward, per-pixel CSR gather (bf16, channels-last) — atomic-free, deterministic, the fine-tune
+// path's default.  Reference: autograd of the roi_align call at defrcn/modeling/roi_heads/roi_heads.py:340
+// (torchvision scatters with atomicAdd; fine-tuning reaches it with BACKWARD_SCALE = 0.001 through the GDL).
 //
-// Gather form of the separable identity (see roi_align_bwd.cu), driven by the per-ROI geometry records that the
-// forward's prepare kernel builds (roi_align_slice.cu):
-//   grad_feat[n,y,x,c] = sum over ROIs r of image n (index order), output rows ph whose window contains y,
-//                        output columns pw whose window contains x:  a_r,ph[y] * b_r,pw[x] * g[r,ph,pw,c]
-// CTA = (map row y, image n, 128 channels).  Phase 1 compacts, in ROI order, the (roi, ph, a) pairs that touch row y
-// into shared memory (one warp, ballot/scan).  Phase 2 gives every (pixel, 8-channel group) of the row a thread that
-// walks the list and accumulates in registers — each output element has exactly one writer and a fixed summation
-// order, so the result is bitwise reproducible and nothing is zero-filled or atomically updated.
+//   grad_feat[n,y,x,c] = sum over ROIs r of image n (index order), computed bins (ph,pw) whose pixel windows contain
+//                        (y,x):  a_r,ph[y] * b_r,pw[x] * g[r,ph,pw,c]          (separable identity, roi_align_bwd.cu)
+// Launches:
+//   1. roi_slice_prepare_kernel (roi_align_slice.cu): the per-ROI geometry records the forward uses.
+//   2. roi_bwd_csr_build_kernel<false> then <true>: CTA = (map row, image, one of kCsrGroups groups of the image's ROIs),
+//      thread = pixel.  The ROIs of the group that touch the row are compacted in index order into shared memory
+//      together with their row weights and horizontal tables, then every thread walks them from shared memory.  The
+//      first launch counts, the second places each (pixel, group) by prefix sums of the counts and writes the pixel's
+//      ordered list of (gradient row index, weight) pairs.  Geometry is channel independent: built once, not once
+//      per channel chunk.
+//   3. roi_bwd_csr_gather_kernel: warp = (pixel, 256 channels), lane = 8 channels.  Lanes fetch 32 list entries with
+//      one coalesced load, broadcast them by shuffle and stream 16 B of gradient per entry into fp32 registers;
+//      every lane is busy on every entry (the row-gather kernel this replaces idled ~3/4 of its lanes on ROIs that
+//      did not cover their pixel: 0.99 ms on the bench shape, see profiles/).
+// Each output element has exactly one writer and a fixed summation order: bitwise reproducible, nothing zero-filled
+// or atomically accumulated in floating point (the only atomics are integer list-size totals).
 #include "common.cuh"
 #include "roi_geom.cuh"
 #include "roi_slice_rec.cuh"
 
 namespace b200 {
 
-constexpr int kGatherLanes = 16;      // threads per pixel: 16 x 8 channels = 128 channels per CTA
-constexpr int kGatherMaxPx = 64;      // pixels per pass of the CTA
-constexpr int kGatherMaxPass = 4;     // map width <= 256 (2 passes up to 64 columns: smaller CTAs, more of them per SM)
-constexpr int kGatherCap = 2048;      // row-list entries held in shared memory at a time (longer lists go in rounds)
-constexpr int kGatherMaxGroups = 16;  // 32-ROI groups scanned per round, one warp each
+constexpr int kCsrMaxW = 256;         // map width handled by one CTA of the build kernel
+constexpr int kCsrGroups = 8;         // ROI groups per image: CTAs of the list builder per map row
+constexpr int kCsrSlots = 64;         // ROIs staged per round of a builder CTA
+constexpr int kCsrLaneCh = 8;         // channels per lane of the gather kernel (one 16-byte load)
+constexpr int kCsrWarps = 8;          // pixels per CTA of the gather kernel
 
-struct RowEntry {
-  int roi;
-  int pho;        // computed output row (index into the strided gradient), -1: table-less ROI (per-sample path)
-  float a;        // vertical weight a_ph[y] / count (bf16-rounded, as the forward uses it)
-  int xext;       // xlo | xhi << 16 : pixel columns touched by the computed bins
+struct CsrEntry {
+  int row;        // (roi * PHO + pho) * PWO + pwo : row of the (strided) gradient tensor, C channels each
+  float w;        // a_ph[y] / count * b_pw[x]
 };
 
-__global__ void __launch_bounds__(kGatherLanes* kGatherMaxPx)
-roi_align_bwd_gather_kernel(const __nv_bfloat16* __restrict__ g, const unsigned char* __restrict__ recs,
-                            const float* __restrict__ rois, const int32_t* __restrict__ roi_offsets,
-                            __nv_bfloat16* __restrict__ grad_feat, int C, int H, int W, int PH, int PW, int bin_step,
-                            float scale, int sampling_ratio, int aligned) {
-  __shared__ RowEntry s_ent[kGatherCap];
-  __shared__ int s_n, s_next, s_gtot[kGatherMaxGroups];
-  const int y = blockIdx.x, n = blockIdx.y;
-  const int r0 = roi_offsets[n], r1 = roi_offsets[n + 1];
-  const int PHO = (PH + bin_step - 1) / bin_step, PWO = (PW + bin_step - 1) / bin_step;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int sub = threadIdx.x & (kGatherLanes - 1);
-  const int c = blockIdx.z * (kGatherLanes * 8) + sub * 8;
-  const int px_per_pass = blockDim.x / kGatherLanes;
-  const int x0 = threadIdx.x / kGatherLanes;
-  float acc[kGatherMaxPass][8];
-#pragma unroll
-  for (int p = 0; p < kGatherMaxPass; ++p)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
-  if (threadIdx.x == 0) s_next = r0;
-  __syncthreads();
-
-  for (;;) {
-  const int rstart = s_next;
-  if (rstart >= r1) break;
-  __syncthreads();                                   // everyone has read s_next / finished the previous round's list
-  // ---- phase 1: ordered list of the (roi, ph) windows that contain row y.  Each warp scans one group of 32 ROIs
-  // (lane <-> ROI); group totals are exchanged through shared memory so that the list keeps the ROI index order.
-  const int nwarps = blockDim.x >> 5;
-  const int ngroups = min(min(nwarps, kGatherMaxGroups), min((r1 - rstart + 31) >> 5, kGatherCap / (32 * PHO)));
-  int cnt = 0, first_pho = 0, flags = 0, xext = 0, incl = 0;
-  const int r = rstart + warp * 32 + lane;
-  const unsigned char* rec = recs + (size_t)min(r, r1 - 1) * kRecBytes;
-  if (warp < ngroups) {
-    if (r < r1) {
-      flags = reinterpret_cast<const int*>(rec)[kOffFlags / 4];
-      if (!flags) {
-        cnt = 1;                                  // table-less ROI: one entry, resolved per sample in phase 2
-      } else {
-        const int ylo = reinterpret_cast<const int*>(rec)[kOffYExt / 4], yhi = reinterpret_cast<const int*>(rec)[kOffYExt / 4 + 1];
-        if (y >= ylo && y <= yhi) {
-          const uint2 ysb = *reinterpret_cast<const uint2*>(rec + kOffYStart);
-          const uint2 ycb = *reinterpret_cast<const uint2*>(rec + kOffYCount);
-          bool seen = false;
-          for (int pho = 0; pho < PHO; ++pho) {
-            const int ph = pho * bin_step;
-            const int ys = ((ph < 4 ? ysb.x : ysb.y) >> (8 * (ph & 3))) & 255;
-            const int yc = ((ph < 4 ? ycb.x : ycb.y) >> (8 * (ph & 3))) & 255;
-            if (y >= ys && y < ys + yc) {         // windows containing y are consecutive in ph
-              if (!seen) { first_pho = pho; seen = true; }
-              ++cnt;
-            }
-          }
-          if (cnt) {
-            int xlo = 1 << 15, xhi = -1;
-            for (int pw = 0; pw < PW; pw += bin_step) {
-              const int xs = rec[kOffXStart + pw], xc = rec[kOffXCount + pw];
-              if (xc) { xlo = min(xlo, xs); xhi = max(xhi, xs + xc - 1); }
-            }
-            if (xhi < 0) cnt = 0;
-            xext = xlo | (xhi << 16);
-          }
-        }
-      }
+// Per-sample path for the rare shapes the tables do not cover (sparse fixed sampling grids, windows wider than kTaps):
+// visits every computed bin of ROI r whose samples touch pixel (y, x) with non-zero weight.
+template <typename F>
+__device__ __forceinline__ void for_each_bin_sampled(const float* __restrict__ rois, int r, int y, int x, int H, int W, int PH,
+                                                     int PW, int PHO, int PWO, int bin_step, float scale,
+                                                     int sampling_ratio, int aligned, F&& emit) {
+  const RoiGeom q = roi_geom(rois + 5 * (size_t)r, scale, sampling_ratio, aligned, PH, PW);
+  const float inv = 1.0f / q.count;
+  for (int pho = 0; pho < PHO; ++pho) {
+    float wyv = 0.f;
+    for (int iy = 0; iy < q.gh; ++iy) {
+      const AxisTap ty = make_tap(sample_coord(q.start_h, pho * bin_step, q.bin_h, iy, q.gh), H, 1);
+      wyv += (ty.lo == y ? ty.wlo : 0.f) + (ty.hi == y ? ty.whi : 0.f);
     }
-    incl = cnt;                                   // inclusive warp scan of the per-ROI entry counts
+    if (wyv == 0.f) continue;
+    for (int pwo = 0; pwo < PWO; ++pwo) {
+      float wxv = 0.f;
+      for (int ix = 0; ix < q.gw; ++ix) {
+        const AxisTap tx = make_tap(sample_coord(q.start_w, pwo * bin_step, q.bin_w, ix, q.gw), W, 1);
+        wxv += (tx.lo == x ? tx.wlo : 0.f) + (tx.hi == x ? tx.whi : 0.f);
+      }
+      const float w = wyv * wxv * inv;
+      if (w != 0.f) emit((r * PHO + pho) * PWO + pwo, w);
+    }
+  }
+}
+
+// One staged ROI that touches the CTA's map row: everything the per-pixel walk needs, in shared memory.
+struct CsrSlot {
+  int roi, table;          // table == 0: resolved per sample (for_each_bin's fallback)
+  int xlo, xhi;            // pixel columns touched by the computed bins
+  int ny;                  // computed output rows whose window contains the CTA's row y
+  unsigned char pho[8];
+  float a[7];              // a_ph[y] / count (bf16-rounded, as the forward uses it)
+  unsigned char xs[8], xc[8];
+  float wx[7 * kTaps];
+};
+
+// grid (H, N, kCsrGroups), block = max(64, W rounded up to whole warps).  CTA = (map row, image, group of the image's
+// ROIs), thread = pixel.  FILL = false: counts[group][pixel] and row_total[row] (integer atomics);  FILL = true: the
+// ordered (gradient row, weight) lists, placed by prefix sums of those counts, and lists[pixel] = {offset, count}.
+template <bool FILL>
+__global__ void __launch_bounds__(kCsrMaxW)
+roi_bwd_csr_build_kernel(const unsigned char* __restrict__ recs, const float* __restrict__ rois,
+                         const int32_t* __restrict__ roi_offsets, int* __restrict__ counts, unsigned int* __restrict__ row_total,
+                         int2* __restrict__ lists, CsrEntry* __restrict__ entries, unsigned int capacity, int N, int H, int W,
+                         int PH, int PW, int bin_step, float scale, int sampling_ratio, int aligned) {
+  __shared__ CsrSlot s_slot[kCsrSlots];
+  __shared__ int s_warp[kCsrMaxW / 32];
+  __shared__ unsigned int s_red[kCsrMaxW / 32];
+  const int y = blockIdx.x, n = blockIdx.y, grp = blockIdx.z, x = threadIdx.x;
+  const int r0 = roi_offsets[n], r1 = roi_offsets[n + 1];
+  const int per = (r1 - r0 + kCsrGroups - 1) / kCsrGroups;
+  const int gb = r0 + grp * per, ge = min(r1, gb + per);
+  const int PHO = (PH + bin_step - 1) / bin_step, PWO = (PW + bin_step - 1) / bin_step;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const size_t npix = (size_t)N * H * W;
+  const size_t pix = ((size_t)n * H + y) * W + min(x, W - 1);
+  unsigned int pos = 0;
+  int cnt = 0;
+
+  if (FILL) {
+    // offset of this (pixel, group): lists of earlier rows + lists of earlier pixels of the row + earlier groups
+    unsigned int before_rows = 0;
+    for (int i = threadIdx.x; i < n * H + y; i += blockDim.x) before_rows += row_total[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before_rows += __shfl_xor_sync(0xffffffffu, before_rows, o);
+    if (lane == 0) s_red[warp] = before_rows;
+    int tot = 0, mine_before = 0;
+    if (x < W)
+      for (int g2 = 0; g2 < kCsrGroups; ++g2) {
+        const int c = counts[(size_t)g2 * npix + pix];
+        tot += c;
+        if (g2 < grp) mine_before += c;
+      }
+    int incl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    if (lane == 31) s_gtot[warp] = incl;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int row_base = 0;
+    int before = 0;
+    for (int i = 0; i < nwarps; ++i) {
+      row_base += s_red[i];
+      if (i < warp) before += s_warp[i];
+    }
+    const unsigned int list_begin = row_base + (unsigned)(before + incl - tot);
+    pos = list_begin + (unsigned)mine_before;
+    // a list that would run past the workspace is dropped whole; the capacity is the worst case, so this never fires
+    if (grp == 0 && x < W) lists[pix] = make_int2((int)list_begin, list_begin + (unsigned)tot <= capacity ? tot : 0);
   }
-  __syncthreads();
-  if (warp < ngroups) {
-    int pos = incl - cnt;
-    for (int i = 0; i < warp; ++i) pos += s_gtot[i];
-    if (cnt) {
-      if (!flags) {
-        s_ent[pos] = RowEntry{r, -1, 0.f, 0};
+
+  for (int rb = gb; rb < ge; rb += kCsrSlots) {
+    __syncthreads();                                   // the previous round's slots are no longer read
+    // ---- ordered compaction of the ROIs of this round that touch row y (first two warps, lane <-> ROI) ---------
+    int hit = 0, table = 0;
+    const int r = rb + threadIdx.x;
+    if (threadIdx.x < kCsrSlots && r < ge) {
+      const unsigned char* rec = recs + (size_t)r * kRecBytes;
+      table = __ldg(reinterpret_cast<const int*>(rec + kOffFlags));
+      if (table) {
+        const int2 yext = __ldg(reinterpret_cast<const int2*>(rec + kOffYExt));
+        hit = y >= yext.x && y <= yext.y;
       } else {
-        const uint32_t* wy2 = reinterpret_cast<const uint32_t*>(rec + kOffWy);
-        for (int i = 0; i < cnt; ++i) {
-          const int pho = first_pho + i, ph = pho * bin_step;
-          const int ys = rec[kOffYStart + ph];
-          s_ent[pos + i] = RowEntry{r, pho, __uint_as_float(wy2[ph * kTaps + (y - ys)] << 16), xext};
-        }
+        hit = 1;
       }
     }
-  }
-  if (threadIdx.x == 0) {
-    int total = 0;
-    for (int i = 0; i < ngroups; ++i) total += s_gtot[i];
-    s_n = total;
-    s_next = rstart + ngroups * 32;
-  }
-  __syncthreads();
-  const int nent = s_n;
-
-  // ---- phase 2: one thread per (pixel, 8 channels), accumulators live in registers across the rounds -------------
-#pragma unroll
-  for (int p = 0; p < kGatherMaxPass; ++p) {
-    const int x = x0 + p * px_per_pass;
-    if (x < W && c < C) {
-      float* ac = acc[p];
-      for (int e = 0; e < nent; ++e) {
-        const RowEntry en = s_ent[e];
-        if (en.pho >= 0) {
-          if (x < (en.xext & 0xffff) || x > (en.xext >> 16)) continue;
-          const unsigned char* rec = recs + (size_t)en.roi * kRecBytes;
-          const uint2 xsb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXStart));
-          const uint2 xcb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXCount));
-          const float* wx = reinterpret_cast<const float*>(rec + kOffWx);
-          const __nv_bfloat16* grow = g + ((size_t)en.roi * PHO + en.pho) * PWO * C + c;
+    const unsigned int bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    const int nhit = s_warp[0] + s_warp[1];
+    if (hit) {
+      const int k = (warp ? s_warp[0] : 0) + __popc(bal & ((1u << lane) - 1u));
+      CsrSlot& sl = s_slot[k];
+      sl.roi = r;
+      sl.table = table;
+      sl.xlo = 0; sl.xhi = W - 1; sl.ny = 0;
+      if (table) {
+        const unsigned char* rec = recs + (size_t)r * kRecBytes;
+        const uint2 ysb = __ldg(reinterpret_cast<const uint2*>(rec + kOffYStart));
+        const uint2 ycb = __ldg(reinterpret_cast<const uint2*>(rec + kOffYCount));
+        const uint2 xsb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXStart));
+        const uint2 xcb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXCount));
+        const uint32_t* wy2 = reinterpret_cast<const uint32_t*>(rec + kOffWy);
+        int ny = 0;
+        for (int pho = 0; pho < PHO; ++pho) {
+          const int ph = pho * bin_step;
+          const int ky = y - (int)(((ph < 4 ? ysb.x : ysb.y) >> (8 * (ph & 3))) & 255);
+          const int yc = ((ph < 4 ? ycb.x : ycb.y) >> (8 * (ph & 3))) & 255;
+          if ((unsigned)ky >= (unsigned)yc) continue;
+          const float a = __uint_as_float(__ldg(wy2 + ph * kTaps + ky) << 16);
+          if (a == 0.f) continue;
+          sl.pho[ny] = (unsigned char)pho;
+          sl.a[ny] = a;
+          ++ny;
+        }
+        int xlo = 255, xhi = -1;
+        for (int pwo = 0; pwo < PWO; ++pwo) {
+          const int pw = pwo * bin_step;
+          const int xs = ((pw < 4 ? xsb.x : xsb.y) >> (8 * (pw & 3))) & 255;
+          const int xc = ((pw < 4 ? xcb.x : xcb.y) >> (8 * (pw & 3))) & 255;
+          sl.xs[pwo] = (unsigned char)xs;
+          sl.xc[pwo] = (unsigned char)xc;
+          if (xc) { xlo = min(xlo, xs); xhi = max(xhi, xs + xc - 1); }
+        }
+        sl.ny = ny;
+        sl.xlo = xlo; sl.xhi = ny ? xhi : -1;
+      }
+    }
+    __syncthreads();
+    // horizontal weight tables of the staged ROIs (PWO x kTaps floats each), coalesced
+    for (int i = threadIdx.x; i < nhit * PWO * kTaps; i += blockDim.x) {
+      const int k = i / (PWO * kTaps), j = i - k * (PWO * kTaps);
+      const int pwo = j / kTaps, t = j - pwo * kTaps;
+      const CsrSlot& sl = s_slot[k];
+      if (sl.table)
+        s_slot[k].wx[j] = __ldg(reinterpret_cast<const float*>(recs + (size_t)sl.roi * kRecBytes + kOffWx) + pwo * bin_step * kTaps + t);
+    }
+    __syncthreads();
+    // ---- per-pixel walk: shared memory only on the table path ------------------------------------------------------
+    if (x < W) {
+      for (int k = 0; k < nhit; ++k) {
+        const CsrSlot& sl = s_slot[k];
+        if (x < sl.xlo || x > sl.xhi) continue;
+        if (sl.table) {
+          const int ny = sl.ny;
           for (int pwo = 0; pwo < PWO; ++pwo) {
-            const int pw = pwo * bin_step;
-            const int xs = ((pw < 4 ? xsb.x : xsb.y) >> (8 * (pw & 3))) & 255;
-            const int xc = ((pw < 4 ? xcb.x : xcb.y) >> (8 * (pw & 3))) & 255;
-            const int k = x - xs;
-            if ((unsigned)k < (unsigned)xc) {
-              const float w = en.a * __ldg(wx + pw * kTaps + k);
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(grow + (size_t)pwo * C));
-              ac[0] += w * __uint_as_float(t.x << 16); ac[1] += w * __uint_as_float(t.x & 0xffff0000u);
-              ac[2] += w * __uint_as_float(t.y << 16); ac[3] += w * __uint_as_float(t.y & 0xffff0000u);
-              ac[4] += w * __uint_as_float(t.z << 16); ac[5] += w * __uint_as_float(t.z & 0xffff0000u);
-              ac[6] += w * __uint_as_float(t.w << 16); ac[7] += w * __uint_as_float(t.w & 0xffff0000u);
+            const int kx = x - (int)sl.xs[pwo];
+            if ((unsigned)kx >= (unsigned)sl.xc[pwo]) continue;
+            const float b = sl.wx[pwo * kTaps + kx];
+            if (b == 0.f) continue;
+            // (pho, pwo) order within the ROI is not needed for reproducibility (any fixed order is), pwo-major here
+            for (int i = 0; i < ny; ++i) {
+              const float w = sl.a[i] * b;
+              if (w == 0.f) continue;
+              if (FILL) {
+                if (pos < capacity) entries[pos] = CsrEntry{(sl.roi * PHO + (int)sl.pho[i]) * PWO + pwo, w};
+                ++pos;
+              } else {
+                ++cnt;
+              }
             }
           }
         } else {
-          // rare shapes (sparse fixed sampling grids, windows wider than the tables): per-sample taps
-          const RoiGeom q = roi_geom(rois + 5 * (size_t)en.roi, scale, sampling_ratio, aligned, PH, PW);
-          const float inv = 1.0f / q.count;
-          for (int pho = 0; pho < PHO; ++pho)
-            for (int iy = 0; iy < q.gh; ++iy) {
-              const AxisTap ty = make_tap(sample_coord(q.start_h, pho * bin_step, q.bin_h, iy, q.gh), H, 1);
-              const float wyv = (ty.lo == y ? ty.wlo : 0.f) + (ty.hi == y ? ty.whi : 0.f);
-              if (wyv == 0.f) continue;
-              for (int pwo = 0; pwo < PWO; ++pwo) {
-                float wxv = 0.f;
-                for (int ix = 0; ix < q.gw; ++ix) {
-                  const AxisTap tx = make_tap(sample_coord(q.start_w, pwo * bin_step, q.bin_w, ix, q.gw), W, 1);
-                  wxv += (tx.lo == x ? tx.wlo : 0.f) + (tx.hi == x ? tx.whi : 0.f);
-                }
-                if (wxv == 0.f) continue;
-                const float w = wyv * wxv * inv;
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(g + (((size_t)en.roi * PHO + pho) * PWO + pwo) * C + c));
-                ac[0] += w * __uint_as_float(t.x << 16); ac[1] += w * __uint_as_float(t.x & 0xffff0000u);
-                ac[2] += w * __uint_as_float(t.y << 16); ac[3] += w * __uint_as_float(t.y & 0xffff0000u);
-                ac[4] += w * __uint_as_float(t.z << 16); ac[5] += w * __uint_as_float(t.z & 0xffff0000u);
-                ac[6] += w * __uint_as_float(t.w << 16); ac[7] += w * __uint_as_float(t.w & 0xffff0000u);
-              }
-            }
+          for_each_bin_sampled(rois, sl.roi, y, x, H, W, PH, PW, PHO, PWO, bin_step, scale, sampling_ratio, aligned,
+                               [&](int row, float w) {
+                         if (FILL) {
+                           if (pos < capacity) entries[pos] = CsrEntry{row, w};
+                           ++pos;
+                         } else {
+                           ++cnt;
+                         }
+                       });
         }
       }
     }
   }
-  }   // rounds
+  if (!FILL) {
+    if (x < W) counts[(size_t)grp * npix + pix] = cnt;
+    unsigned int tot = (unsigned)cnt;
 #pragma unroll
-  for (int p = 0; p < kGatherMaxPass; ++p) {
-    const int x = x0 + p * px_per_pass;
-    if (x < W && c < C) {
-      const float* ac = acc[p];
-      uint4 o;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(ac[0], ac[1]), h1 = __floats2bfloat162_rn(ac[2], ac[3]);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(ac[4], ac[5]), h3 = __floats2bfloat162_rn(ac[6], ac[7]);
-      o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-      o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(grad_feat + (((size_t)n * H + y) * W + x) * C + c) = o;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) atomicAdd(row_total + n * H + y, tot);
+  }
+}
+
+// grid (ceil(N*H*W / kCsrWarps), ceil(C / 256)), block kCsrWarps warps
+__global__ void __launch_bounds__(kCsrWarps * 32)
+roi_bwd_csr_gather_kernel(const __nv_bfloat16* __restrict__ g, const int2* __restrict__ lists,
+                          const CsrEntry* __restrict__ entries, __nv_bfloat16* __restrict__ grad_feat, int npix, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * kCsrWarps + warp;
+  const int c = (blockIdx.y * 32 + lane) * kCsrLaneCh;
+  if (pix >= npix) return;
+  const int2 lst = __ldg(lists + pix);
+  const bool live = c < C;
+  const __nv_bfloat16* gc = g + (live ? c : 0);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int e0 = 0; e0 < lst.y; e0 += 32) {
+    const int m = min(32, lst.y - e0);
+    int2 mine = make_int2(0, 0);
+    if (lane < m) mine = __ldg(reinterpret_cast<const int2*>(entries) + lst.x + e0 + lane);
+    int j = 0;
+    for (; j + 4 <= m; j += 4) {                     // four independent 16-byte loads in flight per lane
+      uint4 t[4];
+      float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int row = __shfl_sync(0xffffffffu, mine.x, j + u);
+        w[u] = __int_as_float(__shfl_sync(0xffffffffu, mine.y, j + u));
+        t[u] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)row * C));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += w[u] * __uint_as_float(t[u].x << 16); acc[1] += w[u] * __uint_as_float(t[u].x & 0xffff0000u);
+        acc[2] += w[u] * __uint_as_float(t[u].y << 16); acc[3] += w[u] * __uint_as_float(t[u].y & 0xffff0000u);
+        acc[4] += w[u] * __uint_as_float(t[u].z << 16); acc[5] += w[u] * __uint_as_float(t[u].z & 0xffff0000u);
+        acc[6] += w[u] * __uint_as_float(t[u].w << 16); acc[7] += w[u] * __uint_as_float(t[u].w & 0xffff0000u);
+      }
     }
+    for (; j < m; ++j) {
+      const int row = __shfl_sync(0xffffffffu, mine.x, j);
+      const float w = __int_as_float(__shfl_sync(0xffffffffu, mine.y, j));
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)row * C));
+      acc[0] += w * __uint_as_float(t.x << 16); acc[1] += w * __uint_as_float(t.x & 0xffff0000u);
+      acc[2] += w * __uint_as_float(t.y << 16); acc[3] += w * __uint_as_float(t.y & 0xffff0000u);
+      acc[4] += w * __uint_as_float(t.z << 16); acc[5] += w * __uint_as_float(t.z & 0xffff0000u);
+      acc[6] += w * __uint_as_float(t.w << 16); acc[7] += w * __uint_as_float(t.w & 0xffff0000u);
+    }
+  }
+  if (live) {
+    uint4 o;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(grad_feat + (size_t)pix * C + c) = o;
   }
 }
 
 bool roi_bwd_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step) {
-  return PH <= 7 && PW <= 7 && bin_step >= 1 && C % 8 == 0 && H <= 256 && W <= 256;
+  return PH <= 7 && PW <= 7 && bin_step >= 1 && C % 8 == 0 && H <= 256 && W <= kCsrMaxW;
 }
 
-size_t roi_bwd_slice_workspace_bytes(int R) { return align_up((size_t)max(R, 1) * kRecBytes, 256); }
+// Worst case of the list entries: windows of consecutive bins overlap by at most 2 pixels per axis, so one ROI
+// contributes at most (H + 2 PHO)(W + 2 PWO) (pixel, bin) pairs; ROIs on the table path (every ROI of a <= 56-pixel-high
+// map region per bin, i.e. all of a 600 x 800 image) at most (PHO kTaps)(PWO kTaps).
+static size_t csr_capacity(int R, int H, int W, int PHO, int PWO) {
+  return (size_t)max(R, 1) * (size_t)(H + 2 * PHO) * (size_t)(W + 2 * PWO);
+}
+
+size_t roi_bwd_slice_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step) {
+  const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
+  const size_t npix = (size_t)N * H * W;
+  return align_up((size_t)max(R, 1) * kRecBytes, 256) + align_up(npix * sizeof(int2), 256) +
+         align_up(npix * kCsrGroups * sizeof(int), 256) + align_up((size_t)N * H * sizeof(unsigned int), 256) +
+         align_up(csr_capacity(R, H, W, PHO, PWO) * sizeof(CsrEntry), 256);
+}
 
 int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
                          int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
                          void* workspace, cudaStream_t st) {
-  unsigned char* recs = (unsigned char*)workspace;
+  const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
+  const size_t npix = (size_t)N * H * W;
+  unsigned char* p = (unsigned char*)workspace;
+  unsigned char* recs = p;                      p += align_up((size_t)max(R, 1) * kRecBytes, 256);
+  int2* lists = (int2*)p;                       p += align_up(npix * sizeof(int2), 256);
+  int* counts = (int*)p;                        p += align_up(npix * kCsrGroups * sizeof(int), 256);
+  unsigned int* row_total = (unsigned int*)p;   p += align_up((size_t)N * H * sizeof(unsigned int), 256);
+  CsrEntry* entries = (CsrEntry*)p;
+  const size_t cap = csr_capacity(R, H, W, PHO, PWO);
+  if (cap > 0x7fffffffull || npix > 0x7fffffffull) {
+    set_error("roi_align_bwd: %d ROIs on a %d x %d map exceed the 2^31-entry list index", R, H, W);
+    return B200_ERR_UNSUPPORTED;
+  }
   int rc = launch_roi_slice_prepare(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
   if (rc != B200_OK) return rc;
-  const int passes = W <= 64 ? 2 : 4;
-  const int px = (max(2, ceil_div(W, passes)) + 1) & ~1;      // even: whole warps
-  dim3 grid(H, N, ceil_div(C, kGatherLanes * 8));
-  roi_align_bwd_gather_kernel<<<grid, px * kGatherLanes, 0, st>>>(g, recs, rois, roi_offsets, grad_feat, C, H, W, PH, PW,
-                                                                 bin_step, scale, sr, aligned);
-  B200_CUDA_LAUNCH_CHECK("roi_align_bwd_gather");
+  B200_CUDA_CALL(cudaMemsetAsync(row_total, 0, (size_t)N * H * sizeof(unsigned int), st));
+  const dim3 grid(H, N, kCsrGroups);
+  const int block = max(kCsrSlots, ceil_div(W, 32) * 32);
+  roi_bwd_csr_build_kernel<false><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
+                                                          (unsigned int)cap, N, H, W, PH, PW, bin_step, scale, sr, aligned);
+  B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_count");
+  roi_bwd_csr_build_kernel<true><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
+                                                         (unsigned int)cap, N, H, W, PH, PW, bin_step, scale, sr, aligned);
+  B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_fill");
+  roi_bwd_csr_gather_kernel<<<dim3(ceil_div((int)npix, kCsrWarps), ceil_div(C, 32 * kCsrLaneCh)), kCsrWarps * 32, 0, st>>>(
+      g, lists, entries, grad_feat, (int)npix, C);
+  B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_gather");
   return B200_OK;
 }
 

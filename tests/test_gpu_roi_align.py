@@ -146,9 +146,8 @@ def test_bwd_bin_step(cl):
 @pytest.mark.parametrize("N,C,H,W,R", [(2, 64, 38, 50, 90), (3, 32, 25, 31, 61), (1, 1024, 38, 50, 40)])
 @pytest.mark.parametrize("bin_step", [1, 2])
 def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
-    """Slice-resident backward (roi_align_bwd_slice.cu: smem-resident fp32 gradient slice, row-owner accumulation):
-    vs the CPU oracle (2e-2: bf16 gradient in, bf16 map out, bf16 vertical weights), vs the gather kernel, and bitwise
-    run-to-run."""
+    """Per-pixel CSR gather backward (roi_align_bwd_slice.cu): vs the CPU oracle (2e-2: bf16 gradient in, bf16 map out,
+    bf16 vertical weights), vs the fp32-table kernel, and bitwise run-to-run."""
     from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
     scale = 1 / 16
     x, rois, offs = _inputs(N, C, H, W, R, scale, 23)
@@ -178,6 +177,30 @@ def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
     finally:
         _lib.set_option("roi_align_bwd_impl", 1)
     assert float((got.float() - base.float()).norm() / base.float().norm()) < 8e-3
+
+
+def test_bwd_bf16_csr_empty_image_and_fixed_grid():
+    """Backward twin of test_fwd_slice_resident_empty_image_and_fixed_grid: an image without ROIs in the middle of the
+    batch (its gradient map must be written as zeros), sparse fixed sampling grids (per-sample fallback of the list
+    builder), boxes partly outside the map."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(6)
+    x = torch.relu(torch.randn(3, 64, 20, 24, generator=gen)).to(torch.bfloat16)
+    b0 = synth_proposals(17, 320, 384, gen)[0]
+    b2 = synth_proposals(9, 320, 384, gen)[0]
+    b2[0] = torch.tensor([-40.0, -30.0, 500.0, 400.0])
+    rois = O.boxes_to_rois([b0, b0[:0], b2])
+    offs = torch.tensor([0, 17, 17, 26], dtype=torch.int32)
+    g = torch.randn(26, 64, 7, 7, generator=gen).to(torch.bfloat16)
+    for sr in (0, 1, 2):
+        ref = O.roi_align_bwd(g.float(), rois, x.shape, 1 / 16, sr, True)
+        xin = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, sr, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+        out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+        gf = xin.grad.float().cpu().contiguous()
+        assert float(gf[1].abs().max()) == 0.0
+        assert float((gf - ref).norm() / ref.norm()) < 8e-3, sr
+        torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("cl", [False, True])

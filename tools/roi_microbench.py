@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--impls", default="0,2")
     ap.add_argument("--steps", default="1,2")
+    ap.add_argument("--bwd", action="store_true", help="time the backward (b200_roi_align_bwd entry point) instead")
     a = ap.parse_args()
     B, P, C, H, W = a.images, a.props, 1024, 38, 50
     dev = torch.device("cuda")
@@ -29,6 +30,8 @@ def main():
     boxes = [synth_proposals(P, 600, 800, torch.Generator().manual_seed(1234 + i), n_obj=8)[0].to(dev) for i in range(B)]
     rois, offs = ops.boxes_to_rois(boxes)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if a.bwd:
+        return bench_bwd(a, feat, rois, offs, flush)
     outs = {}
     for step in [int(s) for s in a.steps.split(",")]:
         nb = -(-7 // step)
@@ -55,6 +58,38 @@ def main():
             d = (outs[k] - outs[ks[0]]).abs().max().item()
             print("   max |impl %d - impl %d| = %.4g (ref max %.3g)" % (k[1], ks[0][1], d, outs[ks[0]].abs().max().item()))
     _lib.set_option("roi_align_bf16_impl", 2)
+
+
+def bench_bwd(a, feat, rois, offs, flush):
+    B, C, H, W = feat.shape
+    P = a.props
+    for step in [int(s) for s in a.steps.split(",")]:
+        nb = -(-7 // step)
+        nbytes = B * C * H * W * 2 + B * P * 20 + B * P * C * nb * nb * 2
+        g = torch.randn(B * P, C, nb, nb, device=feat.device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        res = {}
+        for impl in (0, 1):
+            _lib.set_option("roi_align_bwd_impl", impl)
+            x = feat.clone().requires_grad_(True)
+            out = ops.roi_align(x, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs, bin_step=step)
+            ts = []
+            for i in range(a.iters + 3):
+                flush.fill_(i & 255)
+                x.grad = None
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out.backward(g, retain_graph=True)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            res[impl] = x.grad.float()
+            print("bwd bin_step=%d impl=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
+                  (step, impl, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
+        d = (res[1] - res[0]).norm() / res[0].norm()
+        print("   rel |impl 1 - impl 0| = %.3g" % d.item())
+    _lib.set_option("roi_align_bwd_impl", 1)
 
 
 if __name__ == "__main__":
