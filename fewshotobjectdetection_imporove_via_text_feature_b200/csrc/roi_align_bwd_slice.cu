@@ -62,49 +62,42 @@ __device__ __forceinline__ void for_each_bin_sampled(const float* __restrict__ r
   }
 }
 
-// One staged ROI that touches the CTA's map row: everything the per-pixel walk needs, in shared memory.
-struct CsrSlot {
-  int roi, table;          // table == 0: resolved per sample (for_each_bin's fallback)
-  int xlo, xhi;            // pixel columns touched by the computed bins
-  int ny;                  // computed output rows whose window contains the CTA's row y
-  unsigned char pho[8];
-  float a[7];              // a_ph[y] / count (bf16-rounded, as the forward uses it)
-  unsigned char xs[8], xc[8];
-  float wx[7 * kTaps];
-};
-
-// grid (H, N, kCsrGroups), block = max(64, W rounded up to whole warps).  CTA = (map row, image, group of the image's
-// ROIs), thread = pixel.  FILL = false: counts[group][pixel] and row_total[row] (integer atomics);  FILL = true: the
-// ordered (gradient row, weight) lists, placed by prefix sums of those counts, and lists[pixel] = {offset, count}.
+// grid (ceil(H / RB), N, kCsrGroups), block = RB x Wp threads (Wp = W rounded up to whole warps, RB rows so that the
+// CTA has ~256 threads).  CTA = (block of map rows, image, group of the image's ROIs), thread = pixel.
+// FILL = false: counts[group][pixel] and row_total[row] (integer atomics);  FILL = true: the ordered (gradient row,
+// weight) lists, placed by prefix sums of those counts, and lists[pixel] = {offset, count}.
 template <bool FILL>
 __global__ void __launch_bounds__(kCsrMaxW)
 roi_bwd_csr_build_kernel(const unsigned char* __restrict__ recs, const float* __restrict__ rois,
                          const int32_t* __restrict__ roi_offsets, int* __restrict__ counts, unsigned int* __restrict__ row_total,
                          int2* __restrict__ lists, CsrEntry* __restrict__ entries, unsigned int capacity, int N, int H, int W,
-                         int PH, int PW, int bin_step, float scale, int sampling_ratio, int aligned) {
-  __shared__ CsrSlot s_slot[kCsrSlots];
+                         int Wp, int RB, int PH, int PW, int bin_step, float scale, int sampling_ratio, int aligned) {
+  __shared__ __align__(16) unsigned char s_rec[kCsrSlots][kRecBwdBytes];   // leading part of the staged geometry records
+  __shared__ int s_roi[kCsrSlots];
   __shared__ int s_warp[kCsrMaxW / 32];
   __shared__ unsigned int s_red[kCsrMaxW / 32];
-  const int y = blockIdx.x, n = blockIdx.y, grp = blockIdx.z, x = threadIdx.x;
+  const int n = blockIdx.y, grp = blockIdx.z;
+  const int yb = blockIdx.x * RB, ry = threadIdx.x / Wp, x = threadIdx.x - ry * Wp, y = yb + ry;
+  const bool px_ok = y < H && x < W;
   const int r0 = roi_offsets[n], r1 = roi_offsets[n + 1];
   const int per = (r1 - r0 + kCsrGroups - 1) / kCsrGroups;
   const int gb = r0 + grp * per, ge = min(r1, gb + per);
   const int PHO = (PH + bin_step - 1) / bin_step, PWO = (PW + bin_step - 1) / bin_step;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, wpr = Wp >> 5;
   const size_t npix = (size_t)N * H * W;
-  const size_t pix = ((size_t)n * H + y) * W + min(x, W - 1);
+  const size_t pix = ((size_t)n * H + min(y, H - 1)) * W + min(x, W - 1);
   unsigned int pos = 0;
   int cnt = 0;
 
   if (FILL) {
-    // offset of this (pixel, group): lists of earlier rows + lists of earlier pixels of the row + earlier groups
+    // offset of this (pixel, group): lists of earlier map rows + earlier pixels of the row + earlier groups
     unsigned int before_rows = 0;
-    for (int i = threadIdx.x; i < n * H + y; i += blockDim.x) before_rows += row_total[i];
+    for (int i = threadIdx.x; i < n * H + yb; i += blockDim.x) before_rows += row_total[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before_rows += __shfl_xor_sync(0xffffffffu, before_rows, o);
     if (lane == 0) s_red[warp] = before_rows;
     int tot = 0, mine_before = 0;
-    if (x < W)
+    if (px_ok)
       for (int g2 = 0; g2 < kCsrGroups; ++g2) {
         const int c = counts[(size_t)g2 * npix + pix];
         tot += c;
@@ -118,103 +111,62 @@ roi_bwd_csr_build_kernel(const unsigned char* __restrict__ recs, const float* __
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    unsigned int row_base = 0;
+    unsigned int base = 0;
+    for (int i = 0; i < nwarps; ++i) base += s_red[i];
+    for (int i = 0; i < ry && yb + i < H; ++i) base += row_total[n * H + yb + i];      // earlier rows of this CTA
     int before = 0;
-    for (int i = 0; i < nwarps; ++i) {
-      row_base += s_red[i];
-      if (i < warp) before += s_warp[i];
-    }
-    const unsigned int list_begin = row_base + (unsigned)(before + incl - tot);
+    for (int i = ry * wpr; i < warp; ++i) before += s_warp[i];                           // earlier warps of this row
+    const unsigned int list_begin = base + (unsigned)(before + incl - tot);
     pos = list_begin + (unsigned)mine_before;
     // a list that would run past the workspace is dropped whole; the capacity is the worst case, so this never fires
-    if (grp == 0 && x < W) lists[pix] = make_int2((int)list_begin, list_begin + (unsigned)tot <= capacity ? tot : 0);
+    if (grp == 0 && px_ok) lists[pix] = make_int2((int)list_begin, list_begin + (unsigned)tot <= capacity ? tot : 0);
   }
 
   for (int rb = gb; rb < ge; rb += kCsrSlots) {
     __syncthreads();                                   // the previous round's slots are no longer read
-    // ---- ordered compaction of the ROIs of this round that touch row y (first two warps, lane <-> ROI) ---------
-    int hit = 0, table = 0;
+    // ---- ordered compaction of the ROIs of this round that touch the row block (first two warps, lane <-> ROI) -----
+    int hit = 0;
     const int r = rb + threadIdx.x;
     if (threadIdx.x < kCsrSlots && r < ge) {
-      const unsigned char* rec = recs + (size_t)r * kRecBytes;
-      table = __ldg(reinterpret_cast<const int*>(rec + kOffFlags));
-      if (table) {
-        const int2 yext = __ldg(reinterpret_cast<const int2*>(rec + kOffYExt));
-        hit = y >= yext.x && y <= yext.y;
-      } else {
-        hit = 1;
-      }
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(recs + (size_t)r * kRecBytes + kOffYExt));   // yext, xext
+      const int table = __ldg(reinterpret_cast<const int*>(recs + (size_t)r * kRecBytes + kOffFlags));
+      hit = table ? ((int)h.x <= min(yb + RB, H) - 1 && (int)h.y >= yb && (int)h.z <= (int)h.w) : 1;
     }
     const unsigned int bal = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
     const int nhit = s_warp[0] + s_warp[1];
-    if (hit) {
-      const int k = (warp ? s_warp[0] : 0) + __popc(bal & ((1u << lane) - 1u));
-      CsrSlot& sl = s_slot[k];
-      sl.roi = r;
-      sl.table = table;
-      sl.xlo = 0; sl.xhi = W - 1; sl.ny = 0;
-      if (table) {
-        const unsigned char* rec = recs + (size_t)r * kRecBytes;
-        const uint2 ysb = __ldg(reinterpret_cast<const uint2*>(rec + kOffYStart));
-        const uint2 ycb = __ldg(reinterpret_cast<const uint2*>(rec + kOffYCount));
-        const uint2 xsb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXStart));
-        const uint2 xcb = __ldg(reinterpret_cast<const uint2*>(rec + kOffXCount));
-        const uint32_t* wy2 = reinterpret_cast<const uint32_t*>(rec + kOffWy);
-        int ny = 0;
-        for (int pho = 0; pho < PHO; ++pho) {
-          const int ph = pho * bin_step;
-          const int ky = y - (int)(((ph < 4 ? ysb.x : ysb.y) >> (8 * (ph & 3))) & 255);
-          const int yc = ((ph < 4 ? ycb.x : ycb.y) >> (8 * (ph & 3))) & 255;
-          if ((unsigned)ky >= (unsigned)yc) continue;
-          const float a = __uint_as_float(__ldg(wy2 + ph * kTaps + ky) << 16);
-          if (a == 0.f) continue;
-          sl.pho[ny] = (unsigned char)pho;
-          sl.a[ny] = a;
-          ++ny;
-        }
-        int xlo = 255, xhi = -1;
-        for (int pwo = 0; pwo < PWO; ++pwo) {
-          const int pw = pwo * bin_step;
-          const int xs = ((pw < 4 ? xsb.x : xsb.y) >> (8 * (pw & 3))) & 255;
-          const int xc = ((pw < 4 ? xcb.x : xcb.y) >> (8 * (pw & 3))) & 255;
-          sl.xs[pwo] = (unsigned char)xs;
-          sl.xc[pwo] = (unsigned char)xc;
-          if (xc) { xlo = min(xlo, xs); xhi = max(xhi, xs + xc - 1); }
-        }
-        sl.ny = ny;
-        sl.xlo = xlo; sl.xhi = ny ? xhi : -1;
-      }
-    }
+    if (hit) s_roi[(warp ? s_warp[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = r;
     __syncthreads();
-    // horizontal weight tables of the staged ROIs (PWO x kTaps floats each), coalesced
-    for (int i = threadIdx.x; i < nhit * PWO * kTaps; i += blockDim.x) {
-      const int k = i / (PWO * kTaps), j = i - k * (PWO * kTaps);
-      const int pwo = j / kTaps, t = j - pwo * kTaps;
-      const CsrSlot& sl = s_slot[k];
-      if (sl.table)
-        s_slot[k].wx[j] = __ldg(reinterpret_cast<const float*>(recs + (size_t)sl.roi * kRecBytes + kOffWx) + pwo * bin_step * kTaps + t);
+    for (int i = threadIdx.x; i < nhit * (kRecBwdBytes / 16); i += blockDim.x) {
+      const int k = i / (kRecBwdBytes / 16), j = i - k * (kRecBwdBytes / 16);
+      reinterpret_cast<uint4*>(s_rec[k])[j] = __ldg(reinterpret_cast<const uint4*>(recs + (size_t)s_roi[k] * kRecBytes) + j);
     }
     __syncthreads();
     // ---- per-pixel walk: shared memory only on the table path ------------------------------------------------------
-    if (x < W) {
+    if (px_ok) {
       for (int k = 0; k < nhit; ++k) {
-        const CsrSlot& sl = s_slot[k];
-        if (x < sl.xlo || x > sl.xhi) continue;
-        if (sl.table) {
-          const int ny = sl.ny;
-          for (int pwo = 0; pwo < PWO; ++pwo) {
-            const int kx = x - (int)sl.xs[pwo];
-            if ((unsigned)kx >= (unsigned)sl.xc[pwo]) continue;
-            const float b = sl.wx[pwo * kTaps + kx];
-            if (b == 0.f) continue;
-            // (pho, pwo) order within the ROI is not needed for reproducibility (any fixed order is), pwo-major here
-            for (int i = 0; i < ny; ++i) {
-              const float w = sl.a[i] * b;
+        const unsigned char* rec = s_rec[k];
+        const int roi = s_roi[k];
+        if (*reinterpret_cast<const int*>(rec + kOffFlags)) {
+          const int4 ext = *reinterpret_cast<const int4*>(rec + kOffYExt);
+          if (y < ext.x || y > ext.y || x < ext.z || x > ext.w) continue;
+          const uint32_t* wy2 = reinterpret_cast<const uint32_t*>(rec + kOffWy);
+          const float* wx = reinterpret_cast<const float*>(rec + kOffWx);
+          for (int pho = 0; pho < PHO; ++pho) {
+            const int ph = pho * bin_step;
+            const int ky = y - (int)rec[kOffYStart + ph];
+            if ((unsigned)ky >= (unsigned)rec[kOffYCount + ph]) continue;
+            const float a = __uint_as_float(wy2[ph * kTaps + ky] << 16);      // bf16(a / count), as the forward uses it
+            if (a == 0.f) continue;
+            for (int pwo = 0; pwo < PWO; ++pwo) {
+              const int pw = pwo * bin_step;
+              const int kx = x - (int)rec[kOffXStart + pw];
+              if ((unsigned)kx >= (unsigned)rec[kOffXCount + pw]) continue;
+              const float w = a * wx[pw * kTaps + kx];
               if (w == 0.f) continue;
               if (FILL) {
-                if (pos < capacity) entries[pos] = CsrEntry{(sl.roi * PHO + (int)sl.pho[i]) * PWO + pwo, w};
+                if (pos < capacity) entries[pos] = CsrEntry{(roi * PHO + pho) * PWO + pwo, w};
                 ++pos;
               } else {
                 ++cnt;
@@ -222,25 +174,25 @@ roi_bwd_csr_build_kernel(const unsigned char* __restrict__ recs, const float* __
             }
           }
         } else {
-          for_each_bin_sampled(rois, sl.roi, y, x, H, W, PH, PW, PHO, PWO, bin_step, scale, sampling_ratio, aligned,
+          for_each_bin_sampled(rois, roi, y, x, H, W, PH, PW, PHO, PWO, bin_step, scale, sampling_ratio, aligned,
                                [&](int row, float w) {
-                         if (FILL) {
-                           if (pos < capacity) entries[pos] = CsrEntry{row, w};
-                           ++pos;
-                         } else {
-                           ++cnt;
-                         }
-                       });
+                                 if (FILL) {
+                                   if (pos < capacity) entries[pos] = CsrEntry{row, w};
+                                   ++pos;
+                                 } else {
+                                   ++cnt;
+                                 }
+                               });
         }
       }
     }
   }
   if (!FILL) {
-    if (x < W) counts[(size_t)grp * npix + pix] = cnt;
+    if (px_ok) counts[(size_t)grp * npix + pix] = cnt;
     unsigned int tot = (unsigned)cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && tot) atomicAdd(row_total + n * H + y, tot);
+    if (lane == 0 && tot) atomicAdd(row_total + n * H + y, tot);       // a warp never spans two map rows
   }
 }
 
@@ -338,13 +290,14 @@ int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_
   int rc = launch_roi_slice_prepare(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
   if (rc != B200_OK) return rc;
   B200_CUDA_CALL(cudaMemsetAsync(row_total, 0, (size_t)N * H * sizeof(unsigned int), st));
-  const dim3 grid(H, N, kCsrGroups);
-  const int block = max(kCsrSlots, ceil_div(W, 32) * 32);
+  const int Wp = ceil_div(W, 32) * 32, RB = max(kCsrMaxW / Wp, kCsrSlots / Wp);
+  const dim3 grid(ceil_div(H, RB), N, kCsrGroups);
+  const int block = RB * Wp;
   roi_bwd_csr_build_kernel<false><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
-                                                          (unsigned int)cap, N, H, W, PH, PW, bin_step, scale, sr, aligned);
+                                                          (unsigned int)cap, N, H, W, Wp, RB, PH, PW, bin_step, scale, sr, aligned);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_count");
   roi_bwd_csr_build_kernel<true><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
-                                                         (unsigned int)cap, N, H, W, PH, PW, bin_step, scale, sr, aligned);
+                                                         (unsigned int)cap, N, H, W, Wp, RB, PH, PW, bin_step, scale, sr, aligned);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_fill");
   roi_bwd_csr_gather_kernel<<<dim3(ceil_div((int)npix, kCsrWarps), ceil_div(C, 32 * kCsrLaneCh)), kCsrWarps * 32, 0, st>>>(
       g, lists, entries, grad_feat, (int)npix, C);

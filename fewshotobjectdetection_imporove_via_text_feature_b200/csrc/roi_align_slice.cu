@@ -151,6 +151,13 @@ roi_slice_prepare_kernel(const float* __restrict__ rois, unsigned char* __restri
     }
     reinterpret_cast<int*>(rec)[kOffYExt / 4] = ylo;
     reinterpret_cast<int*>(rec)[kOffYExt / 4 + 1] = yhi;
+    int xlo = 1 << 20, xhi = -1;
+    for (int pw = 0; pw < PW; pw += bin_step) {
+      const int xc = rec[kOffXCount + pw];
+      if (xc > 0) { xlo = min(xlo, (int)rec[kOffXStart + pw]); xhi = max(xhi, (int)rec[kOffXStart + pw] + xc - 1); }
+    }
+    reinterpret_cast<int*>(rec)[kOffXExt / 4] = xlo;
+    reinterpret_cast<int*>(rec)[kOffXExt / 4 + 1] = xhi;
     reinterpret_cast<int*>(rec)[kOffBatch / 4] = g.batch;
     reinterpret_cast<int*>(rec)[kOffFlags / 4] = ok ? 1 : 0;
     reinterpret_cast<int*>(rec)[kOffNxs / 4] = ok ? n : 0;

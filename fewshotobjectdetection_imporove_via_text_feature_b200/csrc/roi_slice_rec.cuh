@@ -20,6 +20,8 @@ constexpr int kStageBytes = 7 * 512;         // epilogue staging per warp: PHO x
 constexpr int kOffBatch = 0, kOffFlags = 4, kOffNxs = 8, kOffNyMax = 12;
 constexpr int kOffYStart = 16, kOffYCount = 24, kOffXStart = 32, kOffXCount = 40, kOffXs = 48;
 constexpr int kOffYExt = 112;                // int32 x2: first / last map row touched by the computed bins (last < first: none)
+constexpr int kOffXExt = 120;                // int32 x2: first / last map column touched by the computed bins
+constexpr int kRecBwdBytes = 640;            // leading part of the record the backward's list builder stages (header, Wy, Wx)
 constexpr int kOffWy = 128;                  // u32 [7][kTaps], zero padded: bf16x2 (a,a), a = vertical weight / count
 constexpr int kOffWx = 384;                  // fp32 [7][kTaps], zero padded: horizontal weights (tiles >= kTabTiles)
 constexpr int kOffXw2 = 640;                 // u32 [kTabTiles][32 lanes]: bf16x2 B-fragment weights of lane (g,t)

@@ -127,6 +127,80 @@ class _FrozenBottleneckFn(torch.autograd.Function):
         return (gx,) + (None,) * 11
 
 
+class _FrozenRes5MeanFn(torch.autograd.Function):
+    """Whole frozen res5 stage + spatial mean as one autograd node (roi_heads.py:313-344 + :1109 under
+    ROI_HEADS.FREEZE_FEAT): pooled ROI map (R, C, h, w) bf16 channels-last -> (R, C_out) fp32.
+
+    Convolutions stay on cuDNN / cuBLAS (fused conv+bias+ReLU(+residual) forward, data-gradient-only backward); the
+    elementwise passes between them are the C-ABI kernels of csrc/res5_elem.cu — spatial mean, mean-backward fused
+    with the last ReLU mask, residual fan-in fused with the previous block's ReLU mask — instead of one torch kernel
+    per algebraic step (0.81 + 3 x 0.22 ms of a 7.8 ms step in the round-1 launch list)."""
+
+    @staticmethod
+    def forward(ctx, x, metas, *params):
+        from . import train_ops
+        saved = []
+        y = x
+        for i, (s1, ssc, conv2_args, has_sc) in enumerate(metas):
+            w1, b1, w2, b2, w3, b3, wsc, bsc = params[8 * i: 8 * i + 8]
+            stride2, pad2, dil2, groups2 = conv2_args
+            out1 = torch.cudnn_convolution_relu(y, w1, b1, s1, (0, 0), (1, 1), 1)
+            out2 = torch.cudnn_convolution_relu(out1, w2, b2, stride2, pad2, dil2, groups2)
+            if has_sc:
+                res = F.conv2d(y, wsc, None, ssc)
+                bias3 = b3 if bsc is None else b3 + bsc
+            else:
+                res, bias3 = y, b3
+            out = torch.cudnn_convolution_add_relu(out2, w3, res, 1.0, bias3, (1, 1), (0, 0), (1, 1), 1)
+            saved += [y, out1, out2, w1, w2, w3, wsc if has_sc else w1]
+            y = out
+        pooled = train_ops.spatial_mean(y)
+        ctx.save_for_backward(y, *saved)
+        ctx.metas = metas
+        return pooled
+
+    @staticmethod
+    def backward(ctx, gp):
+        from . import train_ops
+        out_last, *saved = ctx.saved_tensors
+        metas = ctx.metas
+        relu_bwd = torch.ops.aten.threshold_backward
+
+        def dgrad(g_out, inp, w, stride=(1, 1), pad=(0, 0), dil=(1, 1), groups=1):
+            # data gradient only (output_mask): the input tensor is passed for its shape / layout, its values are unused
+            return torch.ops.aten.convolution_backward(g_out, inp, w, None, list(stride), list(pad), list(dil), False, [0, 0],
+                                                       groups, [True, False, False])[0]
+
+        g = train_ops.mean_bwd_relu_mask(gp, out_last)
+        for i in reversed(range(len(metas))):
+            s1, ssc, (stride2, pad2, dil2, groups2), has_sc = metas[i]
+            x, out1, out2, w1, w2, w3, wsc = saved[7 * i: 7 * i + 7]
+            g2 = relu_bwd(dgrad(g, out2, w3), out2, 0)
+            g1 = relu_bwd(dgrad(g2, out1, w2, stride2, pad2, dil2, groups2), out1, 0)
+            gx = dgrad(g1, x, w1, s1)
+            # fan-in of the two branches (shortcut convolution or identity); for i > 0 the block input is the previous
+            # block's post-ReLU output, whose mask is applied in the same pass
+            gsc = dgrad(g, x, wsc, ssc) if has_sc else g
+            cl = torch.channels_last
+            g = train_ops.add_relu_mask(gx.contiguous(memory_format=cl), gsc.contiguous(memory_format=cl), x if i > 0 else None)
+        return (g, None) + (None,) * (8 * len(metas))
+
+
+def frozen_res5_mean(blocks, x, prestrided=False):
+    """res5 (frozen, BN folded) + mean over (h, w) -> (R, C_out) fp32 through `_FrozenRes5MeanFn`; None when the fused
+    node does not apply (CPU tensors, cuDNN fused ops unavailable, non-bf16 / non-channels-last input)."""
+    if not (_FUSED_CONV["ok"] and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[0] > 0 and
+            x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()):
+        return None
+    metas, params = [], []
+    for i, blk in enumerate(blocks):
+        (w1, b1), (w2, b2), (w3, b3), sc, s1, ssc = blk.folded_params(x, prestrided and i == 0)
+        c2 = blk.conv2
+        metas.append((s1, ssc, (c2.stride, c2.padding, c2.dilation, c2.groups), sc is not None))
+        params += [w1, b1, w2, b2, w3, b3, None if sc is None else sc[0], None if sc is None else sc[1]]
+    return _FrozenRes5MeanFn.apply(x, tuple(metas), *params)
+
+
 class BottleneckBlock(nn.Module):
     def __init__(self, in_channels, out_channels, *, bottleneck_channels, stride=1, num_groups=1, norm="BN",
                  stride_in_1x1=False, dilation=1):
@@ -163,10 +237,9 @@ class BottleneckBlock(nn.Module):
                 self.shortcut.kernel_size == (1, 1) and self.conv1.stride == s and self.shortcut.stride == s and
                 self.conv1.padding == (0, 0) and self.shortcut.padding == (0, 0))
 
-    def forward_folded(self, x, prestrided=False):
-        """Frozen-weights path: FrozenBN folded into the conv weights, cached per (dtype, layout, parameter versions).
-        prestrided: `x` already holds only the pixels [::stride, ::stride] (see `reads_strided_1x1`), so conv1 and
-        the shortcut run with stride 1 — same numbers, 1/stride^2 of the input."""
+    def folded_params(self, x, prestrided=False):
+        """FrozenBN folded into the conv weights, cached per (dtype, layout, parameter versions):
+        ((w1, b1), (w2, b2), (w3, b3), shortcut (w, b) | None, conv1 stride, shortcut stride)."""
         s1 = (1, 1) if prestrided else self.conv1.stride
         ssc = (1, 1) if (prestrided or self.shortcut is None) else self.shortcut.stride
         convs = [self.conv1, self.conv2, self.conv3, self.shortcut]
@@ -175,7 +248,12 @@ class BottleneckBlock(nn.Module):
         if key != self._fold_key:
             self._fold = [None if c is None else c.folded(x.dtype, cl) for c in convs]
             self._fold_key = key
-        (w1, b1), (w2, b2), (w3, b3), sc = self._fold
+        return tuple(self._fold) + (s1, ssc)
+
+    def forward_folded(self, x, prestrided=False):
+        """Frozen-weights path.  prestrided: `x` already holds only the pixels [::stride, ::stride] (see
+        `reads_strided_1x1`), so conv1 and the shortcut run with stride 1 — same numbers, 1/stride^2 of the input."""
+        (w1, b1), (w2, b2), (w3, b3), sc, s1, ssc = self.folded_params(x, prestrided)
         if _FUSED_CONV["ok"] and x.is_cuda and torch.is_grad_enabled() and x.requires_grad:
             return _FrozenBottleneckFn.apply(
                 x, w1, b1, w2, b2, w3, b3, None if sc is None else sc[0], None if sc is None else sc[1], s1, ssc,

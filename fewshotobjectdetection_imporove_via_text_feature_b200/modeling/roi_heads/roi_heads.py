@@ -18,7 +18,7 @@ from torch import nn
 
 from ... import ops
 from ...config import b200_opt
-from ...layers import (BottleneckBlock, Box2BoxTransform, Matcher, add_ground_truth_to_proposals, cat,
+from ...layers import (BottleneckBlock, Box2BoxTransform, Matcher, add_ground_truth_to_proposals, cat, frozen_res5_mean,
                        get_event_storage, make_stage, nonzero_tuple, subsample_labels)
 from ...structures import Boxes, Instances, Registry, ShapeSpec, pairwise_iou
 from ..poolers import ROIPooler
@@ -159,8 +159,18 @@ class Res5ROIHeads(ROIHeads):
         return self._res5_forward(self.pooler(features, boxes, bin_step=step), prestrided=skip)
 
     def _pooled(self, features, proposals):
-        box_features = self._shared_roi_transform([features[f] for f in self.in_features],
-                                                  [x.proposal_boxes for x in proposals])
+        feats, boxes = [features[f] for f in self.in_features], [x.proposal_boxes for x in proposals]
+        if torch.is_grad_enabled() and not self._res5_trainable() and self.res5_dtype == torch.bfloat16:
+            # fine-tuning with frozen res5: one autograd node for the stage + spatial mean (layers._FrozenRes5MeanFn)
+            blk0 = self.res5[0]
+            skip = self.skip_dead_bins and blk0.reads_strided_1x1()
+            x = self.pooler(feats, boxes, bin_step=blk0.stride if skip else 1)
+            if x.requires_grad:
+                pooled = frozen_res5_mean(self.res5, x.to(self.res5_dtype), prestrided=skip)
+                if pooled is not None:
+                    return pooled
+            return self._res5_forward(x, prestrided=skip).mean(dim=[2, 3], dtype=torch.float32)
+        box_features = self._shared_roi_transform(feats, boxes)
         return box_features.mean(dim=[2, 3], dtype=torch.float32)
 
     def forward(self, images, features, proposals, targets=None):

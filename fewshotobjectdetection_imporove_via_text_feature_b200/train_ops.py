@@ -83,6 +83,43 @@ def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weight
     return out
 
 
+def _nhwc(x):
+    assert x.dim() == 4 and x.dtype == torch.bfloat16 and (x.numel() == 0 or x.permute(0, 2, 3, 1).is_contiguous()), \
+        "expected a bf16 channels-last (R, C, h, w) tensor"
+    return x
+
+
+def spatial_mean(x):
+    """x (R, C, h, w) bf16 channels-last -> (R, C) fp32 mean over (h, w)  [roi_heads.py:1109]."""
+    _require_cuda(x)
+    R, C, h, w = _nhwc(x).shape
+    out = torch.empty((R, C), dtype=torch.float32, device=x.device)
+    _lib.call("b200_spatial_mean", x.data_ptr(), out.data_ptr(), C, R, h * w, C, _stream())
+    return out
+
+
+def mean_bwd_relu_mask(gpooled, out):
+    """Backward of `spatial_mean` fused with the ReLU backward of `out` (the tensor that was averaged)."""
+    _require_cuda(gpooled, out)
+    R, C, h, w = _nhwc(out).shape
+    gp = gpooled.detach().float()
+    if gp.stride(1) != 1 or gp.stride(0) % 4 or gp.data_ptr() % 16:
+        gp = gp.contiguous()
+    g = torch.empty_like(out)
+    _lib.call("b200_mean_bwd_relu_mask", gp.data_ptr(), gp.stride(0), out.data_ptr(), g.data_ptr(), R, h * w, C, _stream())
+    return g
+
+
+def add_relu_mask(a, b=None, ref=None):
+    """bf16(a + b) zeroed where ref <= 0; a, b, ref bf16 channels-last tensors of one shape (b / ref optional)."""
+    _require_cuda(a)
+    for t in (b, ref):
+        assert t is None or (t.shape == a.shape and t.stride() == a.stride() and t.dtype == a.dtype)
+    y = torch.empty_like(_nhwc(a))
+    _lib.call("b200_add_relu_mask", a.data_ptr(), _ptr(b), _ptr(ref), y.data_ptr(), a.numel(), _stream())
+    return y
+
+
 def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias=False):
     """fp32 contractions with a short side (csrc/text_side.cu).  mode 'nt': A (M,K), B (N,K) -> (M,N);
     'nn': A (M,N), B (N,K) -> (M,K); 'tn': A (M,N), B (M,K) -> (N,K) [+ column sums of A].  Taller A goes in row blocks

@@ -231,6 +231,21 @@ B200_API int b200_text_attention(const void* q, const float* scores_in, const vo
 B200_API int b200_residual_layernorm(const float* y, const float* y2, const float* gamma, const float* beta, float eps,
                             int relu, float* out_f32, void* out_bf16, int R, int d, b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Elementwise passes around the frozen res5 convolutions (roi_heads.py:313-344, spatial mean at :1109); all tensors
+ * bf16 channels-last (R, HW, C) unless noted, C % 8 == 0, 16-byte aligned.
+ *   b200_spatial_mean        pooled[r,c] (fp32, row stride ld_pooled) = mean over the HW pixels  — x.mean(dim=[2,3])
+ *   b200_mean_bwd_relu_mask  g[r,p,c] = out[r,p,c] > 0 ? bf16(gpooled[r,c] / HW) : 0  — backward of the mean fused with
+ *                            the ReLU backward of the last bottleneck's output `out`
+ *   b200_add_relu_mask       y[i] = ref[i] > 0 ? bf16(a[i] + b[i]) : 0 over n elements — residual fan-in of a bottleneck
+ *                            fused with the ReLU backward of the previous block's output `ref`; b and/or ref may be NULL
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_spatial_mean(const void* x_bf16, float* pooled, int ld_pooled, int R, int HW, int C, b200_stream_t stream);
+B200_API int b200_mean_bwd_relu_mask(const float* gpooled, int ld_g, const void* out_bf16, void* g_bf16, int R, int HW, int C,
+                            b200_stream_t stream);
+B200_API int b200_add_relu_mask(const void* a_bf16, const void* b_bf16, const void* ref_bf16, void* y_bf16, size_t n,
+                       b200_stream_t stream);
+
 /* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
  * in place, without a torch.cat) */
 B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,

@@ -221,3 +221,55 @@ def test_skinny_gemm_modes_vs_fp64(M, N, K):
     dW, db = train_ops.skinny("tn", G.cuda(), A.cuda(), relu_ref=out, out_bias=True)
     assert _rel(dW.cpu(), Gm.t() @ A.double()) < 1e-5
     assert _rel(db.cpu(), Gm.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("R,C,h,w", [(37, 64, 4, 4), (5, 2048, 4, 4), (9, 40, 7, 7)])
+def test_res5_elementwise_kernels(R, C, h, w):
+    """csrc/res5_elem.cu against the torch expressions autograd would run: spatial mean (fp32 accumulate, 1e-6), mean
+    backward fused with the ReLU mask and the residual fan-in fused with the ReLU mask (bf16: bit-exact for a
+    power-of-two window, 1 bf16 ulp otherwise — multiplication by 1/HW vs division)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    gen = torch.Generator().manual_seed(R + C)
+    cl = torch.channels_last
+    out = torch.randn(R, C, h, w, generator=gen).clamp_min(0).to(torch.bfloat16).cuda().contiguous(memory_format=cl)
+    out[0, :8, 0, 0] = torch.tensor([0.0, -0.0, 1e-30, float("inf"), float("nan"), -1.0, 3.0, -float("inf")]).to(out)
+    pooled = train_ops.spatial_mean(out)
+    fin = torch.isfinite(out.float()).all(dim=(2, 3))
+    torch.testing.assert_close(pooled[fin], out.float().mean(dim=(2, 3))[fin], rtol=1e-6, atol=1e-7)
+    gp = torch.randn(R, C, generator=gen).cuda()
+    g = train_ops.mean_bwd_relu_mask(gp, out)
+    ref = torch.ops.aten.threshold_backward((gp / (h * w)).to(torch.bfloat16)[:, :, None, None].expand(R, C, h, w).contiguous(memory_format=cl), out, 0)
+    assert g.is_contiguous(memory_format=cl)
+    if (h * w) & (h * w - 1) == 0:
+        assert torch.equal(g.view(torch.int16), ref.view(torch.int16))
+    else:
+        torch.testing.assert_close(g.float(), ref.float(), rtol=2 ** -7, atol=0)
+    a = torch.randn(R, C, h, w, generator=gen).to(torch.bfloat16).cuda().contiguous(memory_format=cl)
+    b = torch.randn(R, C, h, w, generator=gen).to(torch.bfloat16).cuda().contiguous(memory_format=cl)
+    assert torch.equal(train_ops.add_relu_mask(a, b, out).view(torch.int16), torch.ops.aten.threshold_backward(a + b, out, 0).view(torch.int16))
+    assert torch.equal(train_ops.add_relu_mask(a, b), a + b)
+    assert torch.equal(train_ops.add_relu_mask(a, None, out).view(torch.int16), torch.ops.aten.threshold_backward(a, out, 0).view(torch.int16))
+
+
+@pytest.mark.parametrize("skip", [True, False])
+def test_frozen_res5_mean_node_vs_per_block_autograd(golden, skip):
+    """layers._FrozenRes5MeanFn (stage + mean as one node with the fused elementwise kernels) against the per-block
+    node + torch.mean it replaces: same cuDNN convolutions, so the pooled feature agrees to fp32 rounding of the mean
+    and the gradient w.r.t. the pooled map to bf16 rounding."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import layers
+    m = _build(golden("train_step"))
+    for p in m.res5.parameters():          # ROI_HEADS.FREEZE_FEAT
+        p.requires_grad_(False)
+    gen = torch.Generator().manual_seed(11)
+    side = 4 if skip else 7
+    x = torch.randn(50, 32, side, side, generator=gen).clamp_min(0).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    pa = layers.frozen_res5_mean(m.res5, xa, prestrided=skip)
+    assert pa is not None and pa.dtype == torch.float32
+    pb = m._res5_forward(xb, prestrided=skip).mean(dim=[2, 3], dtype=torch.float32)
+    torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    gp = torch.randn(pa.shape, generator=gen).cuda()
+    pa.backward(gp)
+    pb.backward(gp)
+    assert _rel(xa.grad.float(), xb.grad.float()) < 1e-2
+    assert _cos(xa.grad.float(), xb.grad.float()) > 0.9999
