@@ -284,7 +284,7 @@ def main():
             mark(1)
             pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)   # P1
             mark(2)
-            fp = head._res5_forward(pooled, prestrided=bin_step > 1).mean(dim=[2, 3], dtype=torch.float32)   # P2 (cuDNN)
+            fp = head._res5_mean(pooled, prestrided=bin_step > 1)                               # P2 (cuDNN + own mean)
             mark(3)
             att, _ = head.forward_att(fp)                                                     # T1, A1-A6, C1
             mark(4)
@@ -299,7 +299,7 @@ def main():
         mark(1)
         pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)       # P1
         mark(2)
-        fp = head._res5_forward(pooled, prestrided=bin_step > 1).mean(dim=[2, 3], dtype=torch.float32)   # P2 (frozen)
+        fp = head._res5_mean(pooled, prestrided=bin_step > 1)                                 # P2 (frozen: one node)
         mark(3)
         gt = d["gt_cls"].reshape(-1)
         losses, _ = head.fused_train_losses(fp, props, gt)                                    # T1, A1-A6, C1, L1

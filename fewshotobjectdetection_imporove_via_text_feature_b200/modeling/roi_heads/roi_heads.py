@@ -158,20 +158,30 @@ class Res5ROIHeads(ROIHeads):
         step = blk0.stride if skip else 1
         return self._res5_forward(self.pooler(features, boxes, bin_step=step), prestrided=skip)
 
+    def _res5_mean(self, x, prestrided=False):
+        """res5 + mean over (h, w) of the pooled ROI map -> (R, C_out) fp32  [roi_heads.py:339-344 + :1109].
+        Frozen res5 under autograd runs as one node (layers._FrozenRes5MeanFn: cuDNN convolutions, fused elementwise
+        kernels); the spatial mean of a bf16 channels-last stage output is the C-ABI kernel in every mode."""
+        from ... import train_ops
+        frozen = not self._res5_trainable()
+        if frozen and torch.is_grad_enabled() and x.requires_grad and self.res5_dtype == torch.bfloat16:
+            pooled = frozen_res5_mean(self.res5, x.to(self.res5_dtype), prestrided=prestrided)
+            if pooled is not None:
+                return pooled
+        y = self._res5_forward(x, prestrided=prestrided)
+        if (not y.requires_grad and y.is_cuda and y.dtype == torch.bfloat16 and y.shape[0] > 0 and y.shape[1] % 8 == 0 and
+                y.permute(0, 2, 3, 1).is_contiguous()):
+            return train_ops.spatial_mean(y)
+        return y.mean(dim=[2, 3], dtype=torch.float32)
+
     def _pooled(self, features, proposals):
-        feats, boxes = [features[f] for f in self.in_features], [x.proposal_boxes for x in proposals]
-        if torch.is_grad_enabled() and not self._res5_trainable() and self.res5_dtype == torch.bfloat16:
-            # fine-tuning with frozen res5: one autograd node for the stage + spatial mean (layers._FrozenRes5MeanFn)
-            blk0 = self.res5[0]
-            skip = self.skip_dead_bins and blk0.reads_strided_1x1()
-            x = self.pooler(feats, boxes, bin_step=blk0.stride if skip else 1)
-            if x.requires_grad:
-                pooled = frozen_res5_mean(self.res5, x.to(self.res5_dtype), prestrided=skip)
-                if pooled is not None:
-                    return pooled
-            return self._res5_forward(x, prestrided=skip).mean(dim=[2, 3], dtype=torch.float32)
-        box_features = self._shared_roi_transform(feats, boxes)
-        return box_features.mean(dim=[2, 3], dtype=torch.float32)
+        # res5's first block reads the 7x7 pooled map through 1x1 stride-2 convolutions only (roi_heads.py:313-337 with
+        # RESNETS.STRIDE_IN_1X1): 33 of 49 bins are dead.  On the frozen path the pooler emits just the live bins.
+        blk0 = self.res5[0]
+        skip = self.skip_dead_bins and not self._res5_trainable() and blk0.reads_strided_1x1()
+        x = self.pooler([features[f] for f in self.in_features], [p.proposal_boxes for p in proposals],
+                        bin_step=blk0.stride if skip else 1)
+        return self._res5_mean(x, prestrided=skip)
 
     def forward(self, images, features, proposals, targets=None):
         del images

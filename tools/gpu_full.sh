@@ -5,7 +5,7 @@ timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short > g
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1
+BENCH_DUMP_CALLS=1 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2> gpurun_out/bench_calls.log
 echo "bench exit $?" >> gpurun_out/bench.log
 timeout 600 python bench.py --mode infer --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_infer.log 2>&1
 echo "bench exit $?" >> gpurun_out/bench_infer.log
