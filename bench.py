@@ -292,9 +292,10 @@ def main():
             out = outs.inference_device(head.test_score_thresh, head.test_nms_thresh, head.test_detections_per_img)  # D1-D3
             mark(5)
             return out
-        opt.zero_grad()
-        x = d["feat"].detach().requires_grad_(True)
         mark(0)
+        opt.zero_grad()
+        head.prefetch_text_side()                                                             # T1 (+ text half of A1/A2) on a side stream
+        x = d["feat"].detach().requires_grad_(True)
         f = aff(x, GDL_LAMBDA, True, torch.bfloat16)                                          # G1 + G2
         mark(1)
         pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)       # P1

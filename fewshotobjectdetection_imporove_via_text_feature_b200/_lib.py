@@ -27,6 +27,9 @@ SIGNATURES = {
     "b200_roi_align_fwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "b200_roi_align_bwd_workspace_bytes": (c_size_t, [c_int] * 11),
     "b200_roi_align_bwd": (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_float] + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_bwd_plan_bytes": (c_size_t, [c_int] * 8),
+    "b200_roi_align_bwd_plan": (c_int, [c_void_p] * 2 + [c_int] * 8 + [c_float] + [c_int] * 2 + [c_void_p, c_size_t, c_void_p]),
+    "b200_roi_align_bwd_planned": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p] + [c_int] * 8 + [c_void_p]),
     "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_void_p]),
     "b200_batched_nms_workspace_bytes": (c_size_t, [c_int] * 3),
     "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
@@ -63,7 +66,7 @@ class B200Error(RuntimeError):
 # kernels launched per entry point (upper bound for the optional layout-conversion launches is counted where it
 # happens); used by bench.py to report `gpu_launches`
 KERNELS_PER_CALL = {
-    "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2,
+    "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 3, "b200_roi_align_bwd_planned": 1,
     "b200_softmax_decode_compact": 1, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,

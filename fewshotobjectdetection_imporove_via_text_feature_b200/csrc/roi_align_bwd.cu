@@ -22,6 +22,10 @@ constexpr int kMaxP = 8;  // pooled size supported by the backward (the head use
 int g_roi_bwd_impl = 1;
 bool roi_bwd_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step);
 size_t roi_bwd_slice_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step);
+int launch_roi_bwd_plan(const float* rois, const int32_t* roi_offsets, int N, int H, int W, int R, int PH, int PW,
+                        int bin_step, float scale, int sr, int aligned, void* workspace, cudaStream_t st);
+int launch_roi_bwd_gather(const __nv_bfloat16* g, const void* workspace, __nv_bfloat16* grad_feat, int N, int C, int H, int W,
+                          int R, int PH, int PW, int bin_step, cudaStream_t st);
 int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
                          int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
                          void* workspace, cudaStream_t st);
@@ -259,4 +263,43 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
   if (grad_in_layout == B200_NCHW)
     return dispatch_affine(gf, nullptr, nullptr, 1.0f, grad_feat, N, C, H, W, dtype, B200_NHWC, dtype, B200_NCHW, st);
   return B200_OK;
+}
+
+// ---- split form of the bf16 channels-last path: the geometry plan depends only on the ROIs, so it can be built ahead
+// of the backward pass (on a side stream during the forward) and consumed by one gather launch ------------------------
+extern "C" size_t b200_roi_align_bwd_plan_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step) {
+  bin_step = max(bin_step, 1);
+  if (N <= 0 || H <= 0 || W <= 0 || R < 0 || !roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step)) return 0;
+  return roi_bwd_slice_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step);
+}
+
+extern "C" int b200_roi_align_bwd_plan(const float* rois, const int32_t* roi_batch_offsets, int N, int C, int H, int W, int R,
+                                       int pooled_h, int pooled_w, int bin_step, float spatial_scale, int sampling_ratio,
+                                       int aligned, void* plan, size_t plan_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(roi_batch_offsets && (R == 0 || rois), "roi_align_bwd_plan: null tensor");
+  B200_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && bin_step >= 1 && bin_step <= 8, "roi_align_bwd_plan: bad shape");
+  const size_t need = b200_roi_align_bwd_plan_bytes(N, C, H, W, R, pooled_h, pooled_w, bin_step);
+  if (need == 0) {
+    set_error("roi_align_bwd_plan: shape not covered by the planned path (7x7 pooling, C %% 8 == 0, map <= 256 x 256)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (!plan || plan_bytes < need) {
+    set_error("roi_align_bwd_plan: plan buffer too small (%zu < %zu)", plan_bytes, need);
+    return B200_ERR_WORKSPACE;
+  }
+  return launch_roi_bwd_plan(rois, roi_batch_offsets, N, H, W, R, pooled_h, pooled_w, bin_step, spatial_scale, sampling_ratio,
+                             aligned, plan, (cudaStream_t)stream);
+}
+
+extern "C" int b200_roi_align_bwd_planned(const void* grad_out, const void* plan, size_t plan_bytes, void* grad_feat, int N, int C,
+                                          int H, int W, int R, int pooled_h, int pooled_w, int bin_step, b200_stream_t stream) {
+  B200_CHECK_ARG(grad_feat && plan && (R == 0 || grad_out), "roi_align_bwd_planned: null tensor");
+  B200_CHECK_ARG((((uintptr_t)grad_out | (uintptr_t)grad_feat) & 15) == 0, "roi_align_bwd_planned: tensors must be 16-byte aligned");
+  const size_t need = b200_roi_align_bwd_plan_bytes(N, C, H, W, R, pooled_h, pooled_w, bin_step);
+  if (need == 0 || plan_bytes < need) {
+    set_error("roi_align_bwd_planned: plan buffer does not match the shape (%zu < %zu)", plan_bytes, need);
+    return B200_ERR_WORKSPACE;
+  }
+  return launch_roi_bwd_gather((const __nv_bfloat16*)grad_out, plan, (__nv_bfloat16*)grad_feat, N, C, H, W, R, pooled_h,
+                               pooled_w, bin_step, (cudaStream_t)stream);
 }

@@ -271,38 +271,71 @@ size_t roi_bwd_slice_workspace_bytes(int N, int H, int W, int R, int PH, int PW,
          align_up(csr_capacity(R, H, W, PHO, PWO) * sizeof(CsrEntry), 256);
 }
 
-int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
-                         int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
-                         void* workspace, cudaStream_t st) {
-  const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
+struct CsrPlan {
+  unsigned char* recs;
+  int2* lists;
+  int* counts;
+  unsigned int* row_total;
+  CsrEntry* entries;
+  size_t capacity;
+};
+
+static CsrPlan carve_plan(void* workspace, int N, int H, int W, int R, int PHO, int PWO) {
   const size_t npix = (size_t)N * H * W;
   unsigned char* p = (unsigned char*)workspace;
-  unsigned char* recs = p;                      p += align_up((size_t)max(R, 1) * kRecBytes, 256);
-  int2* lists = (int2*)p;                       p += align_up(npix * sizeof(int2), 256);
-  int* counts = (int*)p;                        p += align_up(npix * kCsrGroups * sizeof(int), 256);
-  unsigned int* row_total = (unsigned int*)p;   p += align_up((size_t)N * H * sizeof(unsigned int), 256);
-  CsrEntry* entries = (CsrEntry*)p;
-  const size_t cap = csr_capacity(R, H, W, PHO, PWO);
-  if (cap > 0x7fffffffull || npix > 0x7fffffffull) {
+  CsrPlan pl;
+  pl.recs = p;                          p += align_up((size_t)max(R, 1) * kRecBytes, 256);
+  pl.lists = (int2*)p;                  p += align_up(npix * sizeof(int2), 256);
+  pl.counts = (int*)p;                  p += align_up(npix * kCsrGroups * sizeof(int), 256);
+  pl.row_total = (unsigned int*)p;      p += align_up((size_t)N * H * sizeof(unsigned int), 256);
+  pl.entries = (CsrEntry*)p;
+  pl.capacity = csr_capacity(R, H, W, PHO, PWO);
+  return pl;
+}
+
+// geometry only (no gradient, no channels): may run ahead of the backward pass, e.g. on a side stream during the forward
+int launch_roi_bwd_plan(const float* rois, const int32_t* roi_offsets, int N, int H, int W, int R, int PH, int PW,
+                        int bin_step, float scale, int sr, int aligned, void* workspace, cudaStream_t st) {
+  const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
+  const CsrPlan pl = carve_plan(workspace, N, H, W, R, PHO, PWO);
+  if (pl.capacity > 0x7fffffffull || (size_t)N * H * W > 0x7fffffffull) {
     set_error("roi_align_bwd: %d ROIs on a %d x %d map exceed the 2^31-entry list index", R, H, W);
     return B200_ERR_UNSUPPORTED;
   }
-  int rc = launch_roi_slice_prepare(rois, recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
+  int rc = launch_roi_slice_prepare(rois, pl.recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
   if (rc != B200_OK) return rc;
-  B200_CUDA_CALL(cudaMemsetAsync(row_total, 0, (size_t)N * H * sizeof(unsigned int), st));
-  const int Wp = ceil_div(W, 32) * 32, RB = max(kCsrMaxW / Wp, kCsrSlots / Wp);
+  B200_CUDA_CALL(cudaMemsetAsync(pl.row_total, 0, (size_t)N * H * sizeof(unsigned int), st));
+  const int Wp = ceil_div(W, 32) * 32, RB = max(1, kCsrMaxW / Wp);
   const dim3 grid(ceil_div(H, RB), N, kCsrGroups);
   const int block = RB * Wp;
-  roi_bwd_csr_build_kernel<false><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
-                                                          (unsigned int)cap, N, H, W, Wp, RB, PH, PW, bin_step, scale, sr, aligned);
+  roi_bwd_csr_build_kernel<false><<<grid, block, 0, st>>>(pl.recs, rois, roi_offsets, pl.counts, pl.row_total, pl.lists,
+                                                          pl.entries, (unsigned int)pl.capacity, N, H, W, Wp, RB, PH, PW,
+                                                          bin_step, scale, sr, aligned);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_count");
-  roi_bwd_csr_build_kernel<true><<<grid, block, 0, st>>>(recs, rois, roi_offsets, counts, row_total, lists, entries,
-                                                         (unsigned int)cap, N, H, W, Wp, RB, PH, PW, bin_step, scale, sr, aligned);
+  roi_bwd_csr_build_kernel<true><<<grid, block, 0, st>>>(pl.recs, rois, roi_offsets, pl.counts, pl.row_total, pl.lists,
+                                                         pl.entries, (unsigned int)pl.capacity, N, H, W, Wp, RB, PH, PW,
+                                                         bin_step, scale, sr, aligned);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_fill");
+  return B200_OK;
+}
+
+int launch_roi_bwd_gather(const __nv_bfloat16* g, const void* workspace, __nv_bfloat16* grad_feat, int N, int C, int H, int W,
+                          int R, int PH, int PW, int bin_step, cudaStream_t st) {
+  const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
+  const CsrPlan pl = carve_plan(const_cast<void*>(workspace), N, H, W, R, PHO, PWO);
+  const size_t npix = (size_t)N * H * W;
   roi_bwd_csr_gather_kernel<<<dim3(ceil_div((int)npix, kCsrWarps), ceil_div(C, 32 * kCsrLaneCh)), kCsrWarps * 32, 0, st>>>(
-      g, lists, entries, grad_feat, (int)npix, C);
+      g, pl.lists, pl.entries, grad_feat, (int)npix, C);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_csr_gather");
   return B200_OK;
+}
+
+int launch_roi_bwd_slice(const __nv_bfloat16* g, const float* rois, const int32_t* roi_offsets, __nv_bfloat16* grad_feat,
+                         int N, int C, int H, int W, int R, int PH, int PW, int bin_step, float scale, int sr, int aligned,
+                         void* workspace, cudaStream_t st) {
+  int rc = launch_roi_bwd_plan(rois, roi_offsets, N, H, W, R, PH, PW, bin_step, scale, sr, aligned, workspace, st);
+  if (rc != B200_OK) return rc;
+  return launch_roi_bwd_gather(g, workspace, grad_feat, N, C, H, W, R, PH, PW, bin_step, st);
 }
 
 }  // namespace b200

@@ -2,173 +2,206 @@
 // Reference: defrcn/modeling/roi_heads/attentive_modules.py:274-277 (key/value projection + ReLU of the class-name
 // embeddings), :125-135 (w_k / w_v, dummy key, zero value) and the folded query operand Kq = Kp Wq / sqrt(d).
 //
-// All of these are contractions with at most 32 rows on one side (the text matrix has K+1 <= 81 rows in general but
-// the head's tables are built per <= 32-row block): tensor-core tiles would be > 80 % padding and cuBLAS falls back
-// to SIMT sgemm kernels that take 30-50 us each for < 0.2 GFLOP (ncu launch list, round 1).  Three small fp32 kernels
-// cover every product of the forward and of autograd's backward; each streams the big operand (the 2048 x 2048 or
-// 2048 x D weight) once, coalesced, and is bound by that read:
-//   NT  out[m][n] = act(sum_k A[m][k] B[n][k] + bias[n])          linear forward          (B = weight)
-//   NN  out[m][k] = scale * sum_n A'[m][n] B[n][k]                 linear data gradient    (B = weight), Kq = Kp Wq
-//   TN  out[n][k] = sum_m A'[m][n] B[m][k],  ob[n] = sum_m A'[m][n]  linear weight / bias gradient
-// A' = A masked by (ref > 0) when a ReLU sits between (ref = the forward activation).  Deterministic: NN splits the
-// n-range over CTAs into partials that are summed in a fixed order.
+// All of these are contractions with at most 32 rows on one side (the text matrix has K+1 <= 81 rows in general; the
+// host feeds taller ones in 32-row blocks): tensor-core tiles would be > 80 % padding and cuBLAS falls back to SIMT
+// sgemm kernels that take 30-50 us each for < 0.2 GFLOP (ncu launch list, round 1).  What bounds them is streaming the
+// big operand (a 2048 x 2048 or 2048 x D fp32 weight, 16.8 MB) once, so the kernels are organised for parallelism
+// and bytes in flight, not FLOPs:
+//   NT  out[m][n] = act(sum_k A[m][k] B[n][k] + bias[n])            linear forward          (B = weight)
+//   NN  out[m][k] = scale * sum_n A'[m][n] B[n][k]                   linear data gradient    (B = weight), Kq = Kp Wq
+//   TN  out[n][k] = sum_m A'[m][n] B[m][k],  ob[n] = sum_m A'[m][n]   linear weight / bias gradient
+// A' = A masked by (ref > 0) when a ReLU sits between (ref = the forward activation).
+// NT / NN: a 32 x 64 output tile per CTA with the reduction split over up to 16 CTAs (512 CTAs for a 2048 x 2048
+// weight, each streaming a 32 KB slab through padded shared-memory tiles, 2 x 4 register blocking); partials are
+// summed in a fixed order by a small second kernel — deterministic.  TN: 4 x 4 outputs per thread, 22 FMAs each,
+// bound by the 16.8 MB write.
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr int kSkMaxM = 32;
+constexpr int kSkCols = 64;        // output columns per CTA (NT / NN)
+constexpr int kSkRc = 64;          // reduction chunk staged per iteration
+constexpr int kSkPad = 4;          // row padding (floats) of the shared tiles: conflict-free float4 reads across rows
+constexpr int kSkMaxSplit = 16;
 
-__device__ __forceinline__ float masked(const float* a, const float* ref, size_t i) {
-  const float v = a[i];
-  return (ref && !(ref[i] > 0.f)) ? 0.f : v;
-}
+__host__ __device__ inline int sk_split(int reduce) { return max(1, min(kSkMaxSplit, reduce / 128)); }
 
-// ---- NT: warp <-> 2 output columns, lanes over k ------------------------------------------------------------------
-template <int MM>
+// MODE 0 (NT): cols = n, reduce = k, B[col][r].  MODE 1 (NN): cols = k, reduce = n, B[r][col].
+// grid (ceil(cols / 64), split), 256 threads: thread (tm, tc) owns rows {2tm, 2tm+1} x 4 columns.
+template <int MODE>
 __global__ void __launch_bounds__(256)
-skinny_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, const float* __restrict__ bias,
-                 int relu, float* __restrict__ out, int ldo, int M, int N, int K) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * 8 + warp) * 2;
-  if (n0 >= N) return;
-  const bool two = n0 + 1 < N;
-  float acc0[MM], acc1[MM];
+skinny_reduce_kernel(const float* __restrict__ A, int lda, const float* __restrict__ ref, int ldref,
+                     const float* __restrict__ B, int ldb, float* __restrict__ partial, int M, int cols, int reduce) {
+  __shared__ __align__(16) float s_a[kSkMaxM][kSkRc + kSkPad];
+  __shared__ __align__(16) float s_b[kSkCols][kSkRc + kSkPad];      // MODE 0: [col][r]   MODE 1: [r][col] (kSkRc == kSkCols)
+  const int tid = threadIdx.x, tm = tid >> 4, tc = tid & 15;
+  const int c0 = blockIdx.x * kSkCols;
+  const int S = gridDim.y;
+  const int per = ((reduce + S - 1) / S + 3) & ~3;                  // multiple of 4: float4 loads stay aligned
+  const int rb = blockIdx.y * per, re = min(reduce, rb + per);
+  float acc[2][4];
 #pragma unroll
-  for (int m = 0; m < MM; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
-  const float* b0 = B + (size_t)n0 * ldb;
-  const float* b1 = B + (size_t)(two ? n0 + 1 : n0) * ldb;
-  for (int k = lane * 4; k < K; k += 128) {
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(b0 + k));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(b1 + k));
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int m = 0; m < MM; ++m) {
-      if (m < M) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(A + (size_t)m * lda + k));
-        acc0[m] += a.x * w0.x + a.y * w0.y + a.z * w0.z + a.w * w0.w;
-        acc1[m] += a.x * w1.x + a.y * w1.y + a.z * w1.z + a.w * w1.w;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int r0 = rb; r0 < re; r0 += kSkRc) {
+    __syncthreads();
+    // A tile: rows m, kSkRc reduction entries (zero beyond M / re), ReLU mask applied
+    for (int i = tid; i < kSkMaxM * (kSkRc / 4); i += 256) {
+      const int m = i / (kSkRc / 4), q = (i - m * (kSkRc / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && r0 + q < re) {
+        v = __ldg(reinterpret_cast<const float4*>(A + (size_t)m * lda + r0 + q));
+        if (ref) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(ref + (size_t)m * ldref + r0 + q));
+          if (!(f.x > 0.f)) v.x = 0.f;
+          if (!(f.y > 0.f)) v.y = 0.f;
+          if (!(f.z > 0.f)) v.z = 0.f;
+          if (!(f.w > 0.f)) v.w = 0.f;
+        }
+        if (r0 + q + 1 >= re) v.y = 0.f;
+        if (r0 + q + 2 >= re) v.z = 0.f;
+        if (r0 + q + 3 >= re) v.w = 0.f;
       }
+      *reinterpret_cast<float4*>(&s_a[m][q]) = v;
     }
-  }
-#pragma unroll
-  for (int m = 0; m < MM; ++m) {
-    if (m < M) {
-      float s0 = warp_sum(acc0[m]), s1 = warp_sum(acc1[m]);
-      if (lane == 0) {
-        s0 += bias ? bias[n0] : 0.f;
-        out[(size_t)m * ldo + n0] = relu ? fmaxf(s0, 0.f) : s0;
-        if (two) {
-          s1 += bias ? bias[n0 + 1] : 0.f;
-          out[(size_t)m * ldo + n0 + 1] = relu ? fmaxf(s1, 0.f) : s1;
+    // B tile, 64 x 64, one coalesced 256-byte row segment per 16 threads
+    for (int i = tid; i < kSkCols * (kSkRc / 4); i += 256) {
+      const int row = i / (kSkRc / 4), q = (i - row * (kSkRc / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == 0) {          // row = output column n, q = reduction offset
+        if (c0 + row < cols && r0 + q < re) {
+          v = __ldg(reinterpret_cast<const float4*>(B + (size_t)(c0 + row) * ldb + r0 + q));
+          if (r0 + q + 1 >= re) v.y = 0.f;
+          if (r0 + q + 2 >= re) v.z = 0.f;
+          if (r0 + q + 3 >= re) v.w = 0.f;
+        }
+      } else {                  // row = reduction offset, q = output column offset
+        if (r0 + row < re && c0 + q < cols) {
+          v = __ldg(reinterpret_cast<const float4*>(B + (size_t)(r0 + row) * ldb + c0 + q));
+          if (c0 + q + 1 >= cols) v.y = 0.f;
+          if (c0 + q + 2 >= cols) v.z = 0.f;
+          if (c0 + q + 3 >= cols) v.w = 0.f;
         }
       }
+      *reinterpret_cast<float4*>(&s_b[row][q]) = v;
+    }
+    __syncthreads();
+    if (MODE == 0) {            // columns tc + 16 j: rows of s_b 16 apart land on distinct banks
+#pragma unroll 4
+      for (int q = 0; q < kSkRc; q += 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&s_a[2 * tm][q]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s_a[2 * tm + 1][q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b = *reinterpret_cast<const float4*>(&s_b[tc + 16 * j][q]);
+          acc[0][j] += a0.x * b.x + a0.y * b.y + a0.z * b.z + a0.w * b.w;
+          acc[1][j] += a1.x * b.x + a1.y * b.y + a1.z * b.z + a1.w * b.w;
+        }
+      }
+    } else {                    // columns 4 tc .. 4 tc + 3
+#pragma unroll 8
+      for (int r = 0; r < kSkRc; ++r) {
+        const float a0 = s_a[2 * tm][r], a1 = s_a[2 * tm + 1][r];
+        const float4 b = *reinterpret_cast<const float4*>(&s_b[r][4 * tc]);
+        acc[0][0] += a0 * b.x; acc[0][1] += a0 * b.y; acc[0][2] += a0 * b.z; acc[0][3] += a0 * b.w;
+        acc[1][0] += a1 * b.x; acc[1][1] += a1 * b.y; acc[1][2] += a1 * b.z; acc[1][3] += a1 * b.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = 2 * tm + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + (MODE == 0 ? tc + 16 * j : 4 * tc + j);
+      if (c < cols) partial[((size_t)blockIdx.y * M + m) * cols + c] = acc[i][j];
     }
   }
 }
 
-// ---- NN: thread <-> output column k, CTAs split the n-range; partial[split][m][k] then an ordered sum --------------
-constexpr int kNnSplit = 16;
-
-template <int MM>
-__global__ void __launch_bounds__(256)
-skinny_nn_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ ref, int ldref,
-                         const float* __restrict__ B, int ldb, float* __restrict__ partial, int M, int N, int K) {
-  __shared__ float s_a[MM][64];
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  const int per = (N + kNnSplit - 1) / kNnSplit;
-  const int nb = blockIdx.y * per, ne = min(N, nb + per);
-  float acc[MM];
-#pragma unroll
-  for (int m = 0; m < MM; ++m) acc[m] = 0.f;
-  for (int n0 = nb; n0 < ne; n0 += 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < MM * 64; i += 256) {
-      const int m = i >> 6, j = i & 63;
-      float v = 0.f;
-      if (m < M && n0 + j < ne) {
-        v = A[(size_t)m * lda + n0 + j];
-        if (ref && !(ref[(size_t)m * ldref + n0 + j] > 0.f)) v = 0.f;
-      }
-      s_a[m][j] = v;
-    }
-    __syncthreads();
-    if (k < K) {
-      const int lim = min(64, ne - n0);
-      for (int j = 0; j < lim; ++j) {
-        const float w = __ldg(B + (size_t)(n0 + j) * ldb + k);
-#pragma unroll
-        for (int m = 0; m < MM; ++m) acc[m] += s_a[m][j] * w;
-      }
-    }
-  }
-  if (k < K) {
-#pragma unroll
-    for (int m = 0; m < MM; ++m)
-      if (m < M) partial[((size_t)blockIdx.y * M + m) * K + k] = acc[m];
-  }
-}
-
-__global__ void skinny_nn_final_kernel(const float* __restrict__ partial, float scale, float* __restrict__ out, int ldo, int M,
-                                       int K) {
+__global__ void skinny_final_kernel(const float* __restrict__ partial, int S, const float* __restrict__ bias, int relu,
+                                    float scale, float* __restrict__ out, int ldo, int M, int cols) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * K) return;
-  const int m = i / K, k = i - m * K;
+  if (i >= M * cols) return;
+  const int m = i / cols, c = i - m * cols;
   float s = 0.f;
-  for (int sp = 0; sp < kNnSplit; ++sp) s += partial[((size_t)sp * M + m) * K + k];
-  out[(size_t)m * ldo + k] = s * scale;
+  for (int sp = 0; sp < S; ++sp) s += partial[((size_t)sp * M + m) * cols + c];
+  s = s * scale + (bias ? bias[c] : 0.f);
+  out[(size_t)m * ldo + c] = relu ? fmaxf(s, 0.f) : s;
 }
 
-// ---- TN: thread <-> (n, 4 consecutive k) --------------------------------------------------------------------------
-template <int MM>
+// ---- TN: thread <-> 4 rows n x 4 consecutive k; warp = 128 consecutive k, 8 warps = 32 rows n -------------------------
 __global__ void __launch_bounds__(256)
 skinny_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ ref, int ldref, const float* __restrict__ B,
                  int ldb, float* __restrict__ out, int ldo, float* __restrict__ out_bias, int M, int N, int K, int accumulate) {
-  const int k = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-  const int n = blockIdx.y * 4 + (threadIdx.x >> 6);
-  if (n >= N || k >= K) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float bsum = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = (blockIdx.x * 32 + lane) * 4;
+  const int n0 = (blockIdx.y * 8 + warp) * 4;
+  if (n0 >= N) return;
+  const bool k_ok = k < K;
+  const bool full = n0 + 3 < N && (lda & 3) == 0 && (!ref || (ldref & 3) == 0);
+  float acc[4][4], bsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int m = 0; m < MM; ++m) {
-    if (m < M) {
-      float a = A[(size_t)m * lda + n];
-      if (ref && !(ref[(size_t)m * ldref + n] > 0.f)) a = 0.f;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (size_t)m * ldb + k));
-      acc.x += a * b.x; acc.y += a * b.y; acc.z += a * b.z; acc.w += a * b.w;
-      bsum += a;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int m = 0; m < M; ++m) {
+    float a[4];
+    if (full) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(A + (size_t)m * lda + n0));
+      a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+      if (ref) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(ref + (size_t)m * ldref + n0));
+        if (!(f.x > 0.f)) a[0] = 0.f;
+        if (!(f.y > 0.f)) a[1] = 0.f;
+        if (!(f.z > 0.f)) a[2] = 0.f;
+        if (!(f.w > 0.f)) a[3] = 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = 0.f;
+        if (n0 + i < N) {
+          a[i] = A[(size_t)m * lda + n0 + i];
+          if (ref && !(ref[(size_t)m * ldref + n0 + i] > 0.f)) a[i] = 0.f;
+        }
+      }
+    }
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k_ok) b = __ldg(reinterpret_cast<const float4*>(B + (size_t)m * ldb + k));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[i][0] += a[i] * b.x; acc[i][1] += a[i] * b.y; acc[i][2] += a[i] * b.z; acc[i][3] += a[i] * b.w;
+      bsum[i] += a[i];
     }
   }
-  float4* dst = reinterpret_cast<float4*>(out + (size_t)n * ldo + k);
-  if (accumulate) {                       // row blocks of a taller A are summed in call order
-    const float4 p = *dst;
-    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (n0 + i >= N) break;
+    if (k_ok) {
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)(n0 + i) * ldo + k);
+      float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (accumulate) {                   // row blocks of a taller A are summed in call order
+        const float4 p = *dst;
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      *dst = v;
+    }
+    if (out_bias && blockIdx.x == 0 && lane == 0) out_bias[n0 + i] = accumulate ? out_bias[n0 + i] + bsum[i] : bsum[i];
   }
-  *dst = acc;
-  if (out_bias && k == 0) out_bias[n] = accumulate ? out_bias[n] + bsum : bsum;
-}
-
-template <int MM>
-static int launch_skinny(int mode, const float* A, int lda, const float* ref, int ldref, const float* B, int ldb,
-                         const float* bias, int relu, float scale, float* out, int ldo, float* out_bias, int M, int N, int K,
-                         int accumulate, float* ws, cudaStream_t st) {
-  if (mode == 0) {
-    skinny_nt_kernel<MM><<<ceil_div(N, 16), 256, 0, st>>>(A, lda, B, ldb, bias, relu, out, ldo, M, N, K);
-  } else if (mode == 1) {
-    dim3 grid(ceil_div(K, 256), kNnSplit);
-    skinny_nn_partial_kernel<MM><<<grid, 256, 0, st>>>(A, lda, ref, ldref, B, ldb, ws, M, N, K);
-    skinny_nn_final_kernel<<<ceil_div(M * K, 256), 256, 0, st>>>(ws, scale, out, ldo, M, K);
-  } else {
-    dim3 grid(ceil_div(K, 256), ceil_div(N, 4));
-    skinny_tn_kernel<MM><<<grid, 256, 0, st>>>(A, lda, ref, ldref, B, ldb, out, ldo, out_bias, M, N, K, accumulate);
-  }
-  B200_CUDA_LAUNCH_CHECK("skinny_gemm");
-  return B200_OK;
 }
 
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" size_t b200_skinny_gemm_workspace_bytes(int M, int K) { return (size_t)kNnSplit * max(M, 1) * max(K, 1) * 4; }
+extern "C" size_t b200_skinny_gemm_workspace_bytes(int M, int cols) {
+  return (size_t)kSkMaxSplit * max(M, 1) * max(cols, 1) * 4;
+}
 
 extern "C" int b200_skinny_gemm(int mode, const float* A, int lda, const float* relu_ref, int ldref, const float* B, int ldb,
                                 const float* bias, int relu, float scale, float* out, int ldo, float* out_bias, int M,
@@ -177,15 +210,34 @@ extern "C" int b200_skinny_gemm(int mode, const float* A, int lda, const float* 
   B200_CHECK_ARG(mode >= 0 && mode <= 2 && A && B && out, "skinny_gemm: bad mode or null tensor");
   B200_CHECK_ARG(M > 0 && M <= kSkMaxM && N > 0 && K > 0, "skinny_gemm: need 0 < M <= 32");
   B200_CHECK_ARG(!accumulate || mode == 2, "skinny_gemm: accumulate is a TN-mode option");
+  B200_CHECK_ARG(!(relu_ref && mode == 0), "skinny_gemm: the ReLU mask applies to the NN / TN modes");
+  // vector accesses: rows of B (all modes), rows of A along the reduction (NT: k, NN: n), rows of the TN output
   if (K % 4 || ldb % 4 || ((uintptr_t)B & 15) || (mode == 0 && (lda % 4 || ((uintptr_t)A & 15))) ||
-      (mode == 2 && (ldo % 4 || ((uintptr_t)out & 15)))) {
-    set_error("skinny_gemm: K and the leading dimensions of the vector-accessed operands must be multiples of 4 floats");
+      (mode == 1 && (N % 4 || lda % 4 || ((uintptr_t)A & 15) || (relu_ref && (ldref % 4 || ((uintptr_t)relu_ref & 15))))) ||
+      (mode == 2 && (ldo % 4 || ((uintptr_t)out & 15) || ((uintptr_t)A & 15) || (relu_ref && ((uintptr_t)relu_ref & 15))))) {
+    set_error("skinny_gemm: K (and N in NN mode) and the leading dimensions of the vector-accessed operands must be "
+              "multiples of 4 floats, pointers 16-byte aligned");
     return B200_ERR_UNSUPPORTED;
   }
-  if (mode == 1) B200_CHECK_ARG(workspace && workspace_bytes >= b200_skinny_gemm_workspace_bytes(M, K), "skinny_gemm: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 2) {
+    dim3 grid(ceil_div(K, 128), ceil_div(N, 32));
+    skinny_tn_kernel<<<grid, 256, 0, st>>>(A, lda, relu_ref, ldref, B, ldb, out, ldo, out_bias, M, N, K, accumulate);
+    B200_CUDA_LAUNCH_CHECK("skinny_gemm(tn)");
+    return B200_OK;
+  }
+  const int cols = mode == 0 ? N : K, reduce = mode == 0 ? K : N;
+  B200_CHECK_ARG(workspace && workspace_bytes >= b200_skinny_gemm_workspace_bytes(M, cols), "skinny_gemm: workspace too small");
   float* ws = (float*)workspace;
-  if (M <= 8) return launch_skinny<8>(mode, A, lda, relu_ref, ldref, B, ldb, bias, relu, scale, out, ldo, out_bias, M, N, K, accumulate, ws, st);
-  if (M <= 24) return launch_skinny<24>(mode, A, lda, relu_ref, ldref, B, ldb, bias, relu, scale, out, ldo, out_bias, M, N, K, accumulate, ws, st);
-  return launch_skinny<32>(mode, A, lda, relu_ref, ldref, B, ldb, bias, relu, scale, out, ldo, out_bias, M, N, K, accumulate, ws, st);
+  const int S = sk_split(reduce);
+  dim3 grid(ceil_div(cols, kSkCols), S);
+  if (mode == 0)
+    skinny_reduce_kernel<0><<<grid, 256, 0, st>>>(A, lda, nullptr, 0, B, ldb, ws, M, cols, reduce);
+  else
+    skinny_reduce_kernel<1><<<grid, 256, 0, st>>>(A, lda, relu_ref, ldref, B, ldb, ws, M, cols, reduce);
+  B200_CUDA_LAUNCH_CHECK("skinny_gemm(partial)");
+  skinny_final_kernel<<<ceil_div(M * cols, 256), 256, 0, st>>>(ws, S, mode == 0 ? bias : nullptr, mode == 0 ? relu : 0,
+                                                               mode == 0 ? 1.0f : scale, out, ldo, M, cols);
+  B200_CUDA_LAUNCH_CHECK("skinny_gemm(final)");
+  return B200_OK;
 }

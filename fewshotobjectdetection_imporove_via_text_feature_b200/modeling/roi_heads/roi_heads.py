@@ -265,7 +265,15 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         fp32 on its own small kernels (train_ops._TextSide) and receives dKq / dVp from the fused node."""
         from ... import train_ops
         att, sa = self.attention, self.attention.attention
-        kq, vp = train_ops.text_side(att)
+        pending, self._text_pending = getattr(self, "_text_pending", None), None
+        if pending is None:
+            kq, vp = train_ops.text_side(att)
+        else:
+            kq, vp, done = pending
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done)
+            kq.record_stream(cur)
+            vp.record_stream(cur)
         props = cat([p.proposal_boxes.tensor for p in proposals], dim=0)
         gtb = cat([p.gt_boxes.tensor for p in proposals], dim=0)
         pred = self.box_predictor
@@ -277,19 +285,31 @@ class SematicRes5ROIHeads(Res5ROIHeads):
                                                     drop, seed, True)
         return {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}, logits
 
+    def _fused_train_path(self):
+        return (self.training and torch.is_grad_enabled() and self.fused_training and
+                type(self).forward_att is SematicRes5ROIHeads.forward_att and
+                type(self.box_predictor).__name__ == "FastRCNNOutputLayers")
+
+    def prefetch_text_side(self):
+        """Start this step's text-side projections on a side stream (train_ops.text_side_async); `fused_train_losses`
+        picks the result up.  Called at the top of `forward` so that they run under ROIAlign / res5."""
+        from ... import train_ops
+        if self.attention.attention.w_q.weight.is_cuda:
+            self._text_pending = train_ops.text_side_async(self.attention)
+
     def forward(self, images, features, proposals, targets=None):
         del images
         test_with_gt = (not self.training) and bool(targets)
         gt_classes = 0
+        if self._fused_train_path():
+            self.prefetch_text_side()
         if self.training:
             proposals = self.label_and_sample_proposals(proposals, targets)
             gt_classes = cat([p.gt_classes for p in proposals], dim=0)
         elif test_with_gt:
             proposals = self.label_proposals(proposals, targets)
         feature_pooled = self._pooled(features, proposals)
-        if (self.training and torch.is_grad_enabled() and feature_pooled.is_cuda and self.fused_training and
-                type(self).forward_att is SematicRes5ROIHeads.forward_att and
-                type(self.box_predictor).__name__ == "FastRCNNOutputLayers"):
+        if feature_pooled.is_cuda and self._fused_train_path():
             losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes)
             FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy()
             return [], losses

@@ -120,6 +120,17 @@ def gdl_affine(x, weight=None, bias=None, lam=1.0, out_dtype=None, channels_last
 # ---------------------------------------------------------------------------------------------------
 # P1 / P1b  (roi_heads.py:300-305,339-340 -> detectron2 ROIPooler -> torchvision.ops.roi_align)
 # ---------------------------------------------------------------------------------------------------
+PLAN_AHEAD = [True]      # build the ROIAlign backward's gather lists during the forward, on a side stream
+_PLAN_STREAMS = {}
+
+
+def _plan_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _PLAN_STREAMS:
+        _PLAN_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _PLAN_STREAMS[key]
+
+
 class _ROIAlign(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, rois, roi_batch_offsets, output_size, spatial_scale, sampling_ratio, aligned,
@@ -147,6 +158,25 @@ class _ROIAlign(torch.autograd.Function):
         ctx.save_for_backward(rois, roi_batch_offsets)
         ctx.meta = (feat.shape, feat.dtype, in_layout, output_size, spatial_scale, sampling_ratio, aligned,
                     channels_last_out, bin_step)
+        ctx.plan = None
+        if (PLAN_AHEAD[0] and ctx.needs_input_grad[0] and R > 0 and roi_batch_offsets is not None and
+                feat.dtype == torch.bfloat16 and channels_last_out and in_layout == NHWC):
+            # The backward's per-pixel gather lists depend only on the ROIs: build them now on a side stream, under the
+            # forward / res5 kernels, so that the backward pass is a single gather launch.
+            pbytes = _lib.lib().b200_roi_align_bwd_plan_bytes(N, C, H, W, R, PH, PW, int(bin_step))
+            if pbytes:
+                main, side = torch.cuda.current_stream(), _plan_stream(feat.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    plan = torch.empty(pbytes, dtype=torch.uint8, device=feat.device)
+                    _lib.call("b200_roi_align_bwd_plan", rois.data_ptr(), roi_batch_offsets.data_ptr(), N, C, H, W, R, PH, PW,
+                              int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)), plan.data_ptr(),
+                              pbytes, side.cuda_stream)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                rois.record_stream(side)
+                roi_batch_offsets.record_stream(side)
+                ctx.plan = (plan, done)
         return out
 
     @staticmethod
@@ -160,6 +190,14 @@ class _ROIAlign(torch.autograd.Function):
         g = g.contiguous(memory_format=torch.channels_last) if cl_out else g.contiguous()
         gin = _empty4(N, C, H, W, dtype, g.device, in_layout == NHWC)
         g_layout = NHWC if cl_out else NCHW
+        if ctx.plan is not None and g.dtype == torch.bfloat16 and g.data_ptr() % 16 == 0:
+            plan, done = ctx.plan
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done)
+            plan.record_stream(cur)
+            _lib.call("b200_roi_align_bwd_planned", g.data_ptr(), plan.data_ptr(), plan.numel(), gin.data_ptr(), N, C, H, W, R,
+                      PH, PW, int(bin_step), _stream())
+            return gin, None, None, None, None, None, None, None, None
         nbytes = _lib.lib().b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, PH, PW, int(bin_step), _dt(g), in_layout,
                                                                g_layout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)

@@ -143,7 +143,7 @@ def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias
         out = torch.empty((N, K), dtype=torch.float32, device=dev)
     ob = torch.empty(N, dtype=torch.float32, device=dev) if (out_bias and mode == "tn") else None
     b32 = None if bias is None else bias.detach().float().contiguous()
-    nbytes = _lib.lib().b200_skinny_gemm_workspace_bytes(min(M, 32), K) if mode == "nn" else 0
+    nbytes = 0 if mode == "tn" else _lib.lib().b200_skinny_gemm_workspace_bytes(min(M, 32), N if mode == "nt" else K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
     for m0 in range(0, M, 32):
         mb = min(32, M - m0)
@@ -153,7 +153,7 @@ def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias
         o = out if mode == "tn" else out[m0:m0 + mb]
         _lib.call("b200_skinny_gemm", code, a.data_ptr(), a.stride(0), _ptr(ref), 0 if ref is None else ref.stride(0),
                   b.data_ptr(), b.stride(0), _ptr(b32), int(relu), float(scale), o.data_ptr(), o.stride(0), _ptr(ob), mb, N, K,
-                  int(mode == "tn" and m0 > 0), _ptr(ws), nbytes, _stream(), launches=2 if mode == "nn" else 1)
+                  int(mode == "tn" and m0 > 0), _ptr(ws), nbytes, _stream(), launches=1 if mode == "tn" else 2)
     return (out, ob) if (out_bias and mode == "tn") else out
 
 
@@ -201,6 +201,26 @@ def text_side(att):
     T = att.forward_language_model()["text_feat"]
     return _TextSide.apply(T, att.key_projection.weight, att.key_projection.bias, att.value_projection.weight,
                            att.value_projection.bias, sa.w_k.weight, sa.w_v.weight, sa.dummy, sa.w_q.weight)
+
+
+_TEXT_STREAMS = {}
+
+
+def text_side_async(att):
+    """`text_side` on a side stream: the (K+2)-row text side depends only on parameters, so its forward can run under
+    the ROIAlign / res5 kernels of the same step and — autograd replays a node on the stream its forward ran on — its
+    backward under the res5 / ROIAlign backward.  Returns (kq, vp, event); the consumer waits on the event."""
+    dev = att.attention.w_q.weight.device
+    key = (dev.type, dev.index)
+    if key not in _TEXT_STREAMS:
+        _TEXT_STREAMS[key] = torch.cuda.Stream(device=dev)
+    main, side = torch.cuda.current_stream(), _TEXT_STREAMS[key]
+    side.wait_stream(main)               # parameters were last written (optimizer step) on the current stream
+    with torch.cuda.stream(side):
+        kq, vp = text_side(att)
+        done = torch.cuda.Event()
+        done.record(side)
+    return kq, vp, done
 
 
 class _FusedHeadTrain(torch.autograd.Function):

@@ -91,6 +91,16 @@ B200_API int b200_roi_align_bwd(const void* grad_out, const float* rois, const i
                        void* grad_feat, int N, int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step,
                        float spatial_scale, int sampling_ratio, int aligned, int dtype, int grad_out_layout,
                        int grad_in_layout, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+/* Split form of b200_roi_align_bwd for bf16 channels-last gradients (7x7 pooling): the per-pixel gather lists depend
+ * only on the ROIs, so `_plan` can run ahead of the backward pass (e.g. on a side stream during the forward) and
+ * `_planned` is then a single gather launch.  `_plan_bytes` returns 0 when the shape is not covered. */
+B200_API size_t b200_roi_align_bwd_plan_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step);
+B200_API int b200_roi_align_bwd_plan(const float* rois, const int32_t* roi_batch_offsets, int N, int C, int H, int W, int R,
+                            int pooled_h, int pooled_w, int bin_step, float spatial_scale, int sampling_ratio, int aligned,
+                            void* plan, size_t plan_bytes, b200_stream_t stream);
+B200_API int b200_roi_align_bwd_planned(const void* grad_out, const void* plan, size_t plan_bytes, void* grad_feat, int N, int C,
+                               int H, int W, int R, int pooled_h, int pooled_w, int bin_step, b200_stream_t stream);
+
 
 /* ---------------------------------------------------------------------------------------------------
  * D1 + D2 + D3 (front)  softmax, Box2BoxTransform.apply_deltas, Boxes.clip, score threshold, ordered
@@ -208,7 +218,7 @@ B200_API int b200_head_losses_bwd(const float* logits, const float* deltas, cons
  * call here).  mode 0 "NT": out[m][n] = act(sum_k A[m][k] B[n][k] + bias[n]);  mode 1 "NN": out[m][k] = scale *
  * sum_n A'[m][n] B[n][k];  mode 2 "TN": out[n][k] (+)= sum_m A'[m][n] B[m][k], out_bias[n] (+)= sum_m A'[m][n].
  * A' = A zeroed where relu_ref <= 0 (ReLU backward; relu_ref may be NULL).  M <= 32 per call. */
-B200_API size_t b200_skinny_gemm_workspace_bytes(int M, int K);
+B200_API size_t b200_skinny_gemm_workspace_bytes(int M, int cols);   /* cols = N (NT) or K (NN); TN needs none */
 B200_API int b200_skinny_gemm(int mode, const float* A, int lda, const float* relu_ref, int ldref, const float* B, int ldb,
                      const float* bias, int relu, float scale, float* out, int ldo, float* out_bias, int M, int N, int K,
                      int accumulate, void* workspace, size_t workspace_bytes, b200_stream_t stream);

@@ -171,11 +171,14 @@ def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
     assert float((gf - ref).norm() / ref.norm()) < 8e-3
     torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
     assert torch.equal(got, run())                                  # fixed summation order
-    _lib.set_option("roi_align_bwd_impl", 0)
-    try:
+    ops.PLAN_AHEAD[0] = False                                       # lists built inside the backward call instead of
+    try:                                                            # ahead of it on the side stream: same bits
+        assert torch.equal(got, run())
+        _lib.set_option("roi_align_bwd_impl", 0)
         base = run()
     finally:
         _lib.set_option("roi_align_bwd_impl", 1)
+        ops.PLAN_AHEAD[0] = True
     assert float((got.float() - base.float()).norm() / base.float().norm()) < 8e-3
 
 

@@ -68,8 +68,9 @@ def bench_bwd(a, feat, rois, offs, flush):
         nbytes = B * C * H * W * 2 + B * P * 20 + B * P * C * nb * nb * 2
         g = torch.randn(B * P, C, nb, nb, device=feat.device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         res = {}
-        for impl in (0, 1):
-            _lib.set_option("roi_align_bwd_impl", impl)
+        for impl in (0, 1, 2):          # 0: fp32-table kernel, 1: CSR lists built inside the call, 2: lists planned ahead
+            _lib.set_option("roi_align_bwd_impl", min(impl, 1))
+            ops.PLAN_AHEAD[0] = impl == 2
             x = feat.clone().requires_grad_(True)
             out = ops.roi_align(x, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs, bin_step=step)
             ts = []
@@ -88,7 +89,7 @@ def bench_bwd(a, feat, rois, offs, flush):
             print("bwd bin_step=%d impl=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
                   (step, impl, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
         d = (res[1] - res[0]).norm() / res[0].norm()
-        print("   rel |impl 1 - impl 0| = %.3g" % d.item())
+        print("   rel |impl 1 - impl 0| = %.3g, impl 2 == impl 1: %s" % (d.item(), torch.equal(res[1], res[2])))
     _lib.set_option("roi_align_bwd_impl", 1)
 
 
