@@ -10,8 +10,9 @@ for r in csv.DictReader(lines):
         v = float(r["Metric Value"].replace(",", "")); u = r["Metric Unit"]
         v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
         rows.append((r["Kernel Name"], v))
-starts = [i for i, (n, _) in enumerate(rows) if "affine_transpose" in n]
-a, b = starts[0], starts[1]
+# a step starts at the forward affine pass (fp32 map in); the backward one (bf16 gradient in) is mid-step
+starts = [i for i, (n, _) in enumerate(rows) if "affine_transpose_kernel<float" in n]
+a, b = starts[-2], starts[-1]
 tot = sum(v for _, v in rows[a:b])
 ours = sum(v for n, v in rows[a:b] if "b200::" in n)
 print("| # | kernel | us | share of step |\n|---|---|---:|---:|")
