@@ -443,8 +443,13 @@ def main():
         roi_bytes = B * C4 * HF * WF * e + R * 20 + R * C4 * nb * nb * e
         roi_ms = prof.get("b200_roi_align_fwd", {}).get("ms_per_step", float("nan"))
         roi_gbs = roi_bytes / (roi_ms * 1e-3) / 1e9
+        # DRAM traffic per launch from the committed `ncu --set full` capture of exactly this configuration
+        # (profiles/r01_ncu_full_step_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: not captured
+        default_cfg = train and (B, P, K, bin_step) == (8, 512, 20, 2)
+        roi_traffic = 41548288 + 108157952 if default_cfg else None
+        gemm_traffic = 656233472 if default_cfg else None           # sum over the step's 26 GEMM launches
         roi_roof = {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<%d,%d,%d> (bf16, rank 0)" % (nb, nb, bin_step),
-                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": None,
+                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": roi_traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
                     "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
@@ -458,7 +463,7 @@ def main():
                 gem["calls"] += prof[name]["calls_per_step"]
         gemm_tf = gem["flop"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] else float("nan")
         gemm_roof = {"kernel": "gemm_bf16_tcgen05_kernel<BN> (all %d launches of the step, rank 0)" % round(gem["calls"]),
-                     "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": None,
+                     "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": gemm_traffic,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
                      "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gem["ms"],
                      "timing": "CUDA events recorded around every GEMM entry-point call on the launching stream, summed per step, mean over %d profiled steps" % prof_steps}

@@ -4,14 +4,16 @@
 // :166-175 (linear1/2/3), :72 (FFN linear1/2), fast_rcnn.py:407,415 (bbox_pred, cls_score),
 // roi_heads.py:1157-1159 (output_projection and the product with the text prototypes).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (persistent: one CTA per SM walks 128 x BN output tiles, 192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of A (128 x 64) and B (BN x 64) bf16 into a
 //               STAGES-deep ring of 128B-swizzled shared-memory tiles, completion on `full` mbarriers;
-//   warp 1      allocates TMEM (BN fp32 columns x 128 lanes), then one elected lane issues
+//   warp 1      allocates TMEM (two accumulators of BN fp32 columns x 128 lanes), then one elected lane issues
 //               tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage and releases the stage
-//               with tcgen05.commit -> `empty` mbarrier; a final commit signals `acc_full`;
-//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (each warp owns its TMEM lane quarter = 32 output rows),
-//               bias + optional ReLU in registers, fp32 and/or bf16 stores (16 B vectors, row-contiguous).
+//               with tcgen05.commit -> `empty` mbarrier; a final commit per tile signals `acc_full[buf]`;
+//   warps 2..5  epilogue of tile i while the MMA warp already runs tile i+1 into the other accumulator:
+//               tcgen05.ld 32x32b.x32 (each warp owns its TMEM lane quarter = 32 output rows), `acc_empty[buf]` arrive
+//               after the last read, transpose through a padded shared staging chunk, then bias / ReLU / ReLU-backward
+//               mask / fp32 accumulate and fp32 and/or bf16 stores as full 128-byte row segments.
 // OOB handling is TMA's: boxes hanging over M, N or K are zero-filled, stores are masked.
 #include <cuda.h>
 
@@ -107,12 +109,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kEpiWarps = 4;
+constexpr int kEpiLd = 36;                       // staging row pitch in floats: 16-byte aligned, conflict-free float4 access
+constexpr int kEpiStageBytes = 32 * kEpiLd * 4;  // one 32 x 32 fp32 chunk per epilogue warp
+
 template <int BN> struct GemmCfg {
   static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  static constexpr int kAccBufs = 2;             // TMEM accumulators: tile i's epilogue overlaps tile i+1's MMAs
+  static constexpr int kTmemCols = (kAccBufs * BN) < 32 ? 32 : kAccBufs * BN;   // power of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kEpiWarps * kEpiStageBytes;
 };
 
+// Persistent: CTA b runs tiles b, b + gridDim.x, ... (m fastest, so that concurrently running CTAs share a B panel in L2).
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -125,27 +138,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + S * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + S;
-  uint64_t* acc_bar = empty_bar + S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(tiles + S * Cfg::kStageBytes + 256);
+  uint64_t* acc_full = empty_bar + S;
+  uint64_t* acc_empty = acc_full + Cfg::kAccBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::kAccBufs);
+  float* s_epi = reinterpret_cast<float*>(tiles + S * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+  const int m_tiles = (M + kBM - 1) / kBM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < Cfg::kAccBufs; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64) s_bias[i] = (bias && n0 + i < N) ? bias[n0 + i] : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -154,133 +166,149 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        unsigned char* sa = tiles + s * Cfg::kStageBytes;
-        unsigned char* sb = sa + kBM * kBK * 2;
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d(sa, &map_a, &full_bar[s], kb * kBK, m0);
-        tma_load_2d(sb, &map_b, &full_bar[s], kb * kBK, n0);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * kBM, n0 = (t / m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          unsigned char* sa = tiles + s * Cfg::kStageBytes;
+          unsigned char* sb = sa + kBM * kBK * 2;
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(sa, &map_a, &full_bar[s], kb * kBK, m0);
+          tma_load_2d(sb, &map_b, &full_bar[s], kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % S;
-      const uint32_t ph = (kb / S) & 1;
-      mbar_wait(&full_bar[s], ph);
+    int it = 0, lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator
       tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(tiles + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + kBM * kBK * 2;
-        const uint64_t adesc = make_smem_desc_sw128(sa), bdesc = make_smem_desc_sw128(sb);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(tiles + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + kBM * kBK * 2;
+          const uint64_t adesc = make_smem_desc_sw128(sa), bdesc = make_smem_desc_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte descriptor units
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte descriptor units
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);                         // stage reusable once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&acc_full[buf]);  // accumulator complete
         }
-        umma_commit(&empty_bar[s]);                    // stage reusable once these MMAs have read it
-        if (kb == num_kb - 1) umma_commit(acc_bar);    // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // epilogue warps: TMEM lane quarter = warp % 4
+    // epilogue warps: TMEM lane quarter = warp % 4.  Each 32 x 32 chunk goes TMEM -> registers (row per lane) -> padded
+    // shared staging -> registers (8 lanes per row) so that every global access is a full 128-byte row segment.
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(acc_bar, 0);
-    tcgen05_fence_after();
+    float* stage = s_epi + (warp - 2) * (kEpiStageBytes / 4);
+    const int tr = lane >> 3, tc = (lane & 7) * 4;           // transposed mapping: rows tr + 4 j, columns tc .. tc + 3
+    int lt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
+      const int m0 = (t % m_tiles) * kBM, n0 = (t / m_tiles) * BN;
+      const int buf = lt & 1;
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      const int row0 = m0 + q * 32;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      float v[32];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        if (c0 + 32 >= BN) {                                 // last read of this accumulator: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        const int col0 = n0 + c0;
+        if (row0 >= M || col0 >= N) continue;               // warp-uniform
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = __uint_as_float(r[i]) + s_bias[c0 + i];
-        if (relu) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (row < M) {
-        const int col = n0 + c0;
-        const bool full = col + 32 <= N;
-        if (mask) {   // backward of a ReLU: zero where the forward activation was not positive
-          const __nv_bfloat16* mrow = mask + (size_t)row * ldmask + col;
-          if (full && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stage + lane * kEpiLd + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        __syncwarp();
+        const int col = col0 + tc;
+        const bool vec = col + 3 < N;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) {
+          if (vec) bv = *reinterpret_cast<const float4*>(bias + col);
+          else {
+            if (col < N) bv.x = bias[col];
+            if (col + 1 < N) bv.y = bias[col + 1];
+            if (col + 2 < N) bv.z = bias[col + 2];
+          }
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 m = *reinterpret_cast<const uint4*>(mrow + 8 * i);
-              const uint32_t w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero (NaN masks count as positive, as x > 0 is false
-                // only for them in the reference too: the forward never produces NaN activations)
-                const uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
-                if ((lo & 0x8000u) || !(lo & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
-                if ((hi & 0x8000u) || !(hi & 0x7fffu)) v[8 * i + 2 * j + 1] = 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const int rr = tr + 4 * j, row = row0 + rr;
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiLd + tc);
+          if (row >= M || col >= N) continue;
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (mask) {   // backward of a ReLU: zero where the forward activation was not positive
+            const __nv_bfloat16* mp = mask + (size_t)row * ldmask + col;
+            if (vec && ((reinterpret_cast<uintptr_t>(mp) & 7) == 0)) {
+              const uint2 mw = *reinterpret_cast<const uint2*>(mp);
+              // bf16 > 0  <=>  sign bit clear and magnitude non-zero (the forward never produces NaN activations)
+              if ((mw.x & 0x8000u) || !(mw.x & 0x7fffu)) v.x = 0.f;
+              if ((mw.x & 0x80000000u) || !(mw.x & 0x7fff0000u)) v.y = 0.f;
+              if ((mw.y & 0x8000u) || !(mw.y & 0x7fffu)) v.z = 0.f;
+              if ((mw.y & 0x80000000u) || !(mw.y & 0x7fff0000u)) v.w = 0.f;
+            } else {
+              if (!(__bfloat162float(mp[0]) > 0.f)) v.x = 0.f;
+              if (col + 1 < N && !(__bfloat162float(mp[1]) > 0.f)) v.y = 0.f;
+              if (col + 2 < N && !(__bfloat162float(mp[2]) > 0.f)) v.z = 0.f;
+              if (col + 3 < N && !(__bfloat162float(mp[3]) > 0.f)) v.w = 0.f;
+            }
+          }
+          if (d_f32) {
+            float* dst = d_f32 + (size_t)row * ldd + col;
+            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              if (accumulate) {   // D += result (gradient accumulation over several producers)
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
               }
+              *reinterpret_cast<float4*>(dst) = v;
+            } else {
+              const float e[4] = {v.x, v.y, v.z, v.w};
+              float f[4];
+              for (int k = 0; k < 4; ++k)
+                if (col + k < N) { f[k] = e[k] + (accumulate ? dst[k] : 0.f); dst[k] = f[k]; } else f[k] = 0.f;
+              v = make_float4(f[0], f[1], f[2], f[3]);
             }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col + i < N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
           }
-        }
-        if (accumulate && d_f32) {   // D += result (gradient accumulation over several producers)
-          const float* src = d_f32 + (size_t)row * ldd + col;
-          if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 t = reinterpret_cast<const float4*>(src)[i];
-              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+          uint2 hw;
+          hw.x = *reinterpret_cast<const uint32_t*>(&h0);
+          hw.y = *reinterpret_cast<const uint32_t*>(&h1);
+          if (d_bf16) {
+            __nv_bfloat16* dst = d_bf16 + (size_t)row * ldd + col;
+            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = hw;
+            else {
+              const __nv_bfloat16 e[4] = {h0.x, h0.y, h1.x, h1.y};
+              for (int k = 0; k < 4; ++k) if (col + k < N) dst[k] = e[k];
             }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (col + i < N) v[i] += src[i];
           }
-        }
-        if (d_f32) {
-          float* dst = d_f32 + (size_t)row * ldd + col;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = v[i];
-          }
-        }
-        if (d_bf16) {
-          __nv_bfloat16* dst = d_bf16 + (size_t)row * ldd + col;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-              w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
-              reinterpret_cast<uint4*>(dst)[i] = w;
+          if (d2) {
+            __nv_bfloat16* dst = d2 + (size_t)row * ldd2 + col;
+            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = hw;
+            else {
+              const __nv_bfloat16 e[4] = {h0.x, h0.y, h1.x, h1.y};
+              for (int k = 0; k < 4; ++k) if (col + k < N) dst[k] = e[k];
             }
-          } else {
-            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = __float2bfloat16_rn(v[i]);
           }
         }
-        if (d2) {
-          __nv_bfloat16* dst = d2 + (size_t)row * ldd2 + col;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 w;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-              w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
-              reinterpret_cast<uint4*>(dst)[i] = w;
-            }
-          } else {
-            for (int i = 0; i < 32; ++i) if (col + i < N) dst[i] = __float2bfloat16_rn(v[i]);
-          }
-        }
+        __syncwarp();                                        // staging reusable
       }
     }
   }
@@ -288,7 +316,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -324,6 +352,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld,
   return B200_OK;
 }
 
+int g_gemm_ctas = 0;   // 0: one persistent CTA per SM; tests lower it to force several tiles per CTA on small shapes
+
 template <int BN>
 static int launch_gemm(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd, int out_dtype,
                        void* D2, int ldd2, int M, int N, int K, int relu, int accumulate, const void* mask, int ldmask,
@@ -339,7 +369,8 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, const flo
     B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
     attr_done = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, kBM));
+  const int tiles = ceil_div(N, BN) * ceil_div(M, kBM);
+  dim3 grid(min(tiles, g_gemm_ctas > 0 ? g_gemm_ctas : kNumSMs));
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ma, mb, bias, out_dtype == B200_F32 ? (float*)D : nullptr,
                                                             out_dtype == B200_BF16 ? (__nv_bfloat16*)D : nullptr, ldd,
                                                             (__nv_bfloat16*)D2, ldd2, M, N, K, relu, accumulate,

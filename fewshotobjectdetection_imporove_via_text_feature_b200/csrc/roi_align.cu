@@ -539,6 +539,7 @@ static int make_feature_map(CUtensorMap* m, const void* ptr, int N, int C, int H
 
 }  // namespace b200
 
+namespace b200 { extern int g_gemm_ctas; }
 using namespace b200;
 
 extern "C" int b200_set_option(const char* key, int value) {
@@ -549,8 +550,13 @@ extern "C" int b200_set_option(const char* key, int value) {
     return B200_OK;
   }
   if (strcmp(key, "roi_align_bwd_impl") == 0) {
-    B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bwd_impl must be 0 (gather) or 1 (slice-resident)");
+    B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bwd_impl must be 0 (fp32 tables) or 1 (per-pixel CSR gather)");
     g_roi_bwd_impl = value;
+    return B200_OK;
+  }
+  if (strcmp(key, "gemm_ctas") == 0) {
+    B200_CHECK_ARG(value >= 0 && value <= 4096, "set_option: gemm_ctas must be in [0, 4096] (0 = one persistent CTA per SM)");
+    g_gemm_ctas = value;
     return B200_OK;
   }
   set_error("set_option: unknown key '%s'", key);

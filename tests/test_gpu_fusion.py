@@ -36,6 +36,36 @@ def test_gemm_bf16(M, N, K, relu, use_bias):
     torch.testing.assert_close(outb.cpu().double(), ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("ctas", [1, 3, 5])
+@pytest.mark.parametrize("M,N,K", [(1000, 2048, 512), (700, 80, 2048), (515, 1000, 136)])
+def test_gemm_persistent_many_tiles_per_cta(M, N, K, ctas):
+    """Persistent scheduler under pressure: few CTAs walk many tiles each, so both TMEM accumulators and every smem
+    stage wrap their mbarrier phases several times; the backward epilogue options (ReLU mask, fp32 accumulate, second
+    bf16 copy) ride along.  Results must not depend on the number of CTAs."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, train_ops
+    gen = torch.Generator().manual_seed(M + K)
+    a = (torch.randn(M, K, generator=gen) * 0.5).to(torch.bfloat16).cuda()
+    b = (torch.randn(N, K, generator=gen) * 0.05).to(torch.bfloat16).cuda()
+    mask = torch.randn(M, (N + 7) // 8 * 8, generator=gen).to(torch.bfloat16).cuda()[:, :N]
+    acc0 = torch.randn(M, N, generator=gen).cuda()
+    ref = a.double() @ b.double().t()
+    ref = torch.where(mask.double() > 0, ref, torch.zeros((), dtype=torch.float64, device="cuda")) + acc0.double()
+
+    def run():
+        out, d2 = acc0.clone(), torch.empty(M, (N + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")[:, :N]
+        train_ops.gemm_ex(a, b, out=out, out2=d2, accumulate=True, mask=mask)
+        return out, d2
+    base, base2 = run()
+    torch.testing.assert_close(base.double(), ref, rtol=1e-3, atol=1e-3)
+    _lib.set_option("gemm_ctas", ctas)
+    try:
+        out, d2 = run()
+    finally:
+        _lib.set_option("gemm_ctas", 0)
+    assert torch.equal(out, base) and torch.equal(d2, base2)
+    assert torch.equal(d2, base.to(torch.bfloat16))
+
+
 def test_gemm_strided_and_second_output():
     from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
     gen = torch.Generator().manual_seed(0)
