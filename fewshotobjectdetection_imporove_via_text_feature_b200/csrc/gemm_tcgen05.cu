@@ -4,16 +4,16 @@
 // :166-175 (linear1/2/3), :72 (FFN linear1/2), fast_rcnn.py:407,415 (bbox_pred, cls_score),
 // roi_heads.py:1157-1159 (output_projection and the product with the text prototypes).
 //
-// Structure (persistent: one CTA per SM walks 128 x BN output tiles, 192 threads):
+// Structure (persistent: one CTA per SM walks 128 x BN output tiles, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of A (128 x 64) and B (BN x 64) bf16 into a
 //               STAGES-deep ring of 128B-swizzled shared-memory tiles, completion on `full` mbarriers;
 //   warp 1      allocates TMEM (two accumulators of BN fp32 columns x 128 lanes), then one elected lane issues
 //               tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage and releases the stage
 //               with tcgen05.commit -> `empty` mbarrier; a final commit per tile signals `acc_full[buf]`;
-//   warps 2..5  epilogue of tile i while the MMA warp already runs tile i+1 into the other accumulator:
-//               tcgen05.ld 32x32b.x32 (each warp owns its TMEM lane quarter = 32 output rows), `acc_empty[buf]` arrive
-//               after the last read, transpose through a padded shared staging chunk, then bias / ReLU / ReLU-backward
-//               mask / fp32 accumulate and fp32 and/or bf16 stores as full 128-byte row segments.
+//   warps 2..9  epilogue of tile i while the MMA warp already runs tile i+1 into the other accumulator:
+//               tcgen05.ld 32x32b.x32 (warp w owns TMEM lane quarter w % 4 = 32 output rows and one column half),
+//               `acc_empty[buf]` arrive after the last read, bias / ReLU / ReLU-backward mask / fp32 accumulate with
+//               the global operands prefetched a chunk ahead, fp32 and/or bf16 16-byte stores.
 // OOB handling is TMA's: boxes hanging over M, N or K are zero-filled, stores are masked.
 #include <cuda.h>
 
@@ -24,7 +24,7 @@ namespace b200 {
 constexpr int kBM = 128;
 constexpr int kBK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -113,9 +113,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kEpiWarps = 4;
-constexpr int kEpiLd = 36;                       // staging row pitch in floats: 16-byte aligned, conflict-free float4 access
-constexpr int kEpiStageBytes = 32 * kEpiLd * 4;  // one 32 x 32 fp32 chunk per epilogue warp
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStageBytes = 128 * 4;          // per epilogue warp: its bias slice (<= 128 columns)
 
 template <int BN> struct GemmCfg {
   static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const float* __restrict__ bias, float* __restrict__ d_f32, __nv_bfloat16* __restrict__ d_bf16,
                          int ldd, __nv_bfloat16* __restrict__ d2, int ldd2, int M, int N, int K, int relu,
-                         int accumulate, const __nv_bfloat16* __restrict__ mask, int ldmask) {
+                         int accumulate, const __nv_bfloat16* __restrict__ mask, int ldmask, int vec) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -210,105 +209,133 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
     }
   } else {
-    // epilogue warps: TMEM lane quarter = warp % 4.  Each 32 x 32 chunk goes TMEM -> registers (row per lane) -> padded
-    // shared staging -> registers (8 lanes per row) so that every global access is a full 128-byte row segment.
-    const int q = warp & 3;
-    float* stage = s_epi + (warp - 2) * (kEpiStageBytes / 4);
-    const int tr = lane >> 3, tc = (lane & 7) * 4;           // transposed mapping: rows tr + 4 j, columns tc .. tc + 3
+    // Epilogue: 8 warps.  Warp w reads TMEM lane quarter w % 4 (32 output rows, one per lane) and the column half
+    // (w - 2) / 4 of the tile, in 32-column chunks.  A chunk's global operands (ReLU-backward mask, fp32 addend) are
+    // fetched one chunk ahead, all of them at once, so their latency hides under the previous chunk's stores; the
+    // tile's bias slice sits in a per-warp shared copy.  Running a whole tile behind the MMA warp (second TMEM
+    // accumulator), the epilogue only has to keep up with the mainloop, not be fast.
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    constexpr int kCw = BN >= 64 ? BN / 2 : BN;              // columns per warp; BN = 32: the second half has no work
+    const bool has_cols = BN >= 64 || half == 0;
+    const int cbeg = half * kCw;
+    float* sb = s_epi + ew * 128;                            // kCw <= 128 floats
     int lt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++lt) {
       const int m0 = (t % m_tiles) * kBM, n0 = (t / m_tiles) * BN;
       const int buf = lt & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+      uint4 pm[4];
+      float4 pa[8];
+      auto prefetch = [&](int c0n) {
+        const int col = n0 + c0n;
+        const bool ok = vec && row_ok && c0n < cbeg + kCw && col + 32 <= N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pm[i] = (mask && ok) ? __ldg(reinterpret_cast<const uint4*>(mask + (size_t)row * ldmask + col) + i)
+                               : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pa[i] = (accumulate && ok) ? *(reinterpret_cast<const float4*>(d_f32 + (size_t)row * ldd + col) + i)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (has_cols) {
+        __syncwarp();                                        // previous tile's reads of `sb` are done
+        for (int i = lane; i < kCw; i += 32) sb[i] = (bias && n0 + cbeg + i < N) ? bias[n0 + cbeg + i] : 0.f;
+        __syncwarp();
+        prefetch(cbeg);
+      }
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
-      const int row0 = m0 + q * 32;
+      if (!has_cols) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = cbeg; c0 < cbeg + kCw; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
-        if (c0 + 32 >= BN) {                                 // last read of this accumulator: hand it back to the MMA warp
+        if (c0 + 32 >= cbeg + kCw) {                         // last read of this accumulator: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        const int col0 = n0 + c0;
-        if (row0 >= M || col0 >= N) continue;               // warp-uniform
+        const int col = n0 + c0;
+        if (col >= N) continue;                              // warp-uniform
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(stage + lane * kEpiLd + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-        __syncwarp();
-        const int col = col0 + tc;
-        const bool vec = col + 3 < N;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) {
-          if (vec) bv = *reinterpret_cast<const float4*>(bias + col);
-          else {
-            if (col < N) bv.x = bias[col];
-            if (col + 1 < N) bv.y = bias[col + 1];
-            if (col + 2 < N) bv.z = bias[col + 2];
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + (c0 - cbeg) + 4 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
+          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
+          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
+        if (relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = tr + 4 * j, row = row0 + rr;
-          float4 v = *reinterpret_cast<const float4*>(stage + rr * kEpiLd + tc);
-          if (row >= M || col >= N) continue;
-          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (mask) {   // backward of a ReLU: zero where the forward activation was not positive
-            const __nv_bfloat16* mp = mask + (size_t)row * ldmask + col;
-            if (vec && ((reinterpret_cast<uintptr_t>(mp) & 7) == 0)) {
-              const uint2 mw = *reinterpret_cast<const uint2*>(mp);
-              // bf16 > 0  <=>  sign bit clear and magnitude non-zero (the forward never produces NaN activations)
-              if ((mw.x & 0x8000u) || !(mw.x & 0x7fffu)) v.x = 0.f;
-              if ((mw.x & 0x80000000u) || !(mw.x & 0x7fff0000u)) v.y = 0.f;
-              if ((mw.y & 0x8000u) || !(mw.y & 0x7fffu)) v.z = 0.f;
-              if ((mw.y & 0x80000000u) || !(mw.y & 0x7fff0000u)) v.w = 0.f;
-            } else {
-              if (!(__bfloat162float(mp[0]) > 0.f)) v.x = 0.f;
-              if (col + 1 < N && !(__bfloat162float(mp[1]) > 0.f)) v.y = 0.f;
-              if (col + 2 < N && !(__bfloat162float(mp[2]) > 0.f)) v.z = 0.f;
-              if (col + 3 < N && !(__bfloat162float(mp[3]) > 0.f)) v.w = 0.f;
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (vec && col + 32 <= N) {
+          // ReLU backward: zero where the forward activation (bf16) was not positive: sign set or magnitude zero
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t w[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if ((w[j] & 0x8000u) || !(w[j] & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
+              if ((w[j] & 0x80000000u) || !(w[j] & 0x7fff0000u)) v[8 * i + 2 * j + 1] = 0.f;
             }
           }
-          if (d_f32) {
-            float* dst = d_f32 + (size_t)row * ldd + col;
-            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-              if (accumulate) {   // D += result (gradient accumulation over several producers)
-                const float4 o = *reinterpret_cast<const float4*>(dst);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[4 * i] += pa[i].x; v[4 * i + 1] += pa[i].y; v[4 * i + 2] += pa[i].z; v[4 * i + 3] += pa[i].w; }
+          prefetch(c0 + 32);                                 // next chunk's operands, in flight during the stores below
+          if (row_ok) {
+            if (d_f32) {
+              float4* dst = reinterpret_cast<float4*>(d_f32 + (size_t)row * ldd + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (d_bf16 || d2) {
+              uint4 w[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                w[i].x = *reinterpret_cast<const uint32_t*>(&h0); w[i].y = *reinterpret_cast<const uint32_t*>(&h1);
+                w[i].z = *reinterpret_cast<const uint32_t*>(&h2); w[i].w = *reinterpret_cast<const uint32_t*>(&h3);
               }
-              *reinterpret_cast<float4*>(dst) = v;
-            } else {
-              const float e[4] = {v.x, v.y, v.z, v.w};
-              float f[4];
-              for (int k = 0; k < 4; ++k)
-                if (col + k < N) { f[k] = e[k] + (accumulate ? dst[k] : 0.f); dst[k] = f[k]; } else f[k] = 0.f;
-              v = make_float4(f[0], f[1], f[2], f[3]);
+              if (d_bf16) {
+                uint4* dst = reinterpret_cast<uint4*>(d_bf16 + (size_t)row * ldd + col);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = w[i];
+              }
+              if (d2) {
+                uint4* dst = reinterpret_cast<uint4*>(d2 + (size_t)row * ldd2 + col);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = w[i];
+              }
             }
           }
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-          uint2 hw;
-          hw.x = *reinterpret_cast<const uint32_t*>(&h0);
-          hw.y = *reinterpret_cast<const uint32_t*>(&h1);
-          if (d_bf16) {
-            __nv_bfloat16* dst = d_bf16 + (size_t)row * ldd + col;
-            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = hw;
-            else {
-              const __nv_bfloat16 e[4] = {h0.x, h0.y, h1.x, h1.y};
-              for (int k = 0; k < 4; ++k) if (col + k < N) dst[k] = e[k];
+        } else if (row_ok) {
+          // element-wise tail: the chunk hangs over N, or an operand is not aligned for vector access
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {                     // static indexing keeps v[] in registers
+            if (col + i >= N) continue;
+            float x = v[i];
+            if (mask && !(__bfloat162float(mask[(size_t)row * ldmask + col + i]) > 0.f)) x = 0.f;
+            if (d_f32) {
+              float* dst = d_f32 + (size_t)row * ldd + col + i;
+              if (accumulate) x += *dst;
+              *dst = x;
             }
+            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+            if (d_bf16) d_bf16[(size_t)row * ldd + col + i] = h;
+            if (d2) d2[(size_t)row * ldd2 + col + i] = h;
           }
-          if (d2) {
-            __nv_bfloat16* dst = d2 + (size_t)row * ldd2 + col;
-            if (vec && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<uint2*>(dst) = hw;
-            else {
-              const __nv_bfloat16 e[4] = {h0.x, h0.y, h1.x, h1.y};
-              for (int k = 0; k < 4; ++k) if (col + k < N) dst[k] = e[k];
-            }
-          }
+          prefetch(c0 + 32);
         }
-        __syncwarp();                                        // staging reusable
       }
     }
   }
@@ -352,6 +379,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld,
   return B200_OK;
 }
 
+int g_gemm_generic_epilogue = 0;   // tests: force the element-wise epilogue on shapes the vector one covers
 int g_gemm_ctas = 0;   // 0: one persistent CTA per SM; tests lower it to force several tiles per CTA on small shapes
 
 template <int BN>
@@ -369,12 +397,17 @@ static int launch_gemm(const void* A, int lda, const void* B, int ldb, const flo
     B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
     attr_done = true;
   }
+  // vector epilogue (16-byte accesses on full 32-column chunks) needs aligned operand rows; chunks hanging over N and
+  // unaligned operands take the element-wise path
+  const uintptr_t al = (uintptr_t)D | (uintptr_t)D2 | (uintptr_t)mask;
+  const int vec = (al & 15) == 0 && (!D || ldd % (out_dtype == B200_F32 ? 4 : 8) == 0) && (!D2 || ldd2 % 8 == 0) &&
+                  (!mask || ldmask % 8 == 0) && !g_gemm_generic_epilogue;
   const int tiles = ceil_div(N, BN) * ceil_div(M, kBM);
   dim3 grid(min(tiles, g_gemm_ctas > 0 ? g_gemm_ctas : kNumSMs));
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, st>>>(ma, mb, bias, out_dtype == B200_F32 ? (float*)D : nullptr,
                                                             out_dtype == B200_BF16 ? (__nv_bfloat16*)D : nullptr, ldd,
                                                             (__nv_bfloat16*)D2, ldd2, M, N, K, relu, accumulate,
-                                                            (const __nv_bfloat16*)mask, ldmask);
+                                                            (const __nv_bfloat16*)mask, ldmask, vec);
   B200_CUDA_LAUNCH_CHECK("gemm_bf16");
   return B200_OK;
 }

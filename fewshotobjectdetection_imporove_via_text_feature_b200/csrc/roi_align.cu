@@ -539,7 +539,7 @@ static int make_feature_map(CUtensorMap* m, const void* ptr, int N, int C, int H
 
 }  // namespace b200
 
-namespace b200 { extern int g_gemm_ctas; }
+namespace b200 { extern int g_gemm_ctas; extern int g_gemm_generic_epilogue; }
 using namespace b200;
 
 extern "C" int b200_set_option(const char* key, int value) {
@@ -552,6 +552,10 @@ extern "C" int b200_set_option(const char* key, int value) {
   if (strcmp(key, "roi_align_bwd_impl") == 0) {
     B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bwd_impl must be 0 (fp32 tables) or 1 (per-pixel CSR gather)");
     g_roi_bwd_impl = value;
+    return B200_OK;
+  }
+  if (strcmp(key, "gemm_generic_epilogue") == 0) {
+    g_gemm_generic_epilogue = value != 0;
     return B200_OK;
   }
   if (strcmp(key, "gemm_ctas") == 0) {

@@ -29,6 +29,12 @@ def test_gemm_bf16(M, N, K, relu, use_bias):
         ref = ref + bias.double()
     if relu:
         ref = ref.clamp_min(0)
+    if bias is not None:      # biases are views into the optimizer's flat buffer: any 4-byte alignment must work
+        bias_d = torch.zeros(N + 3, device="cuda")[3:]
+        bias_d.copy_(bias)
+        assert bias_d.data_ptr() % 16 != 0
+        out = ops.gemm_bf16(a.cuda(), b.cuda(), bias_d, relu=relu)
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-3, atol=1e-3)
     out = ops.gemm_bf16(a.cuda(), b.cuda(), None if bias is None else bias.cuda(), relu=relu)
     assert out.dtype == torch.float32 and out.shape == (M, N)
     torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-3, atol=1e-3)
@@ -64,6 +70,12 @@ def test_gemm_persistent_many_tiles_per_cta(M, N, K, ctas):
         _lib.set_option("gemm_ctas", 0)
     assert torch.equal(out, base) and torch.equal(d2, base2)
     assert torch.equal(d2, base.to(torch.bfloat16))
+    _lib.set_option("gemm_generic_epilogue", 1)          # element-wise epilogue == vector epilogue, bit for bit
+    try:
+        out, d2 = run()
+    finally:
+        _lib.set_option("gemm_generic_epilogue", 0)
+    assert torch.equal(out, base) and torch.equal(d2, base2)
 
 
 def test_gemm_strided_and_second_output():
