@@ -253,7 +253,7 @@ def main():
     opt = None
     if train:
         opt = train_ops.FlatSGD(list(head.attention.parameters()) + list(head.box_predictor.parameters()) + list(aff.parameters()),
-                                lr=LR, momentum=MOMENTUM, weight_decay=WD)
+                                lr=LR, momentum=MOMENTUM, weight_decay=WD, direct_grads=True)
 
     def make_props(d):
         props = []
@@ -312,6 +312,7 @@ def main():
         (losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]).backward()   # L1, A*, P2, P1b, G1/G2 bwd
         mark(8)
         if world > 1:
+            opt.sync_grads()                                                                  # join the parameter-gradient stream
             dist.all_reduce(opt.grad, op=dist.ReduceOp.AVG)                                   # the one real exchange step
         opt.step()
         mark(9)

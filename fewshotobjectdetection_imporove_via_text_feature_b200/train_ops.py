@@ -56,9 +56,12 @@ def transpose_bf16(src, pad_rows_to=None):
     return dst
 
 
-def colsum(src, n=None):
+def colsum(src, n=None, out=None):
+    """Column sums of `src` (rows, cols) -> fp32 (cols,) [or into `out`], two-pass and ordered (bias gradients)."""
     rows, cols = src.shape
-    out = torch.empty(cols, dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=src.device)
+    assert out.dtype == torch.float32 and out.numel() == cols and out.is_contiguous()
     nbytes = _lib.lib().b200_colsum_workspace_bytes(cols)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
     _lib.call("b200_colsum", src.data_ptr(), _dt(src), src.stride(0), rows, cols, out.data_ptr(), 0, ws.data_ptr(), nbytes,
@@ -180,6 +183,12 @@ class _TextSide(torch.autograd.Function):
         T, kt, vt, kp, Wk, Wv, Wq = ctx.saved_tensors
         d = Wq.shape[0]
         s = 1.0 / float(d) ** 0.5
+        cur = torch.cuda.current_stream()
+        for g in (dkq, dvp):           # produced on another stream by _FusedHeadTrain.backward (deferred mode)
+            ev = _READY_EVENTS.pop(g.data_ptr(), None)
+            if ev is not None:
+                cur.wait_event(ev)
+                g.record_stream(cur)
         dkq = (dkq.float() * s).contiguous()
         dvp = dvp.float().contiguous()
         dkp = skinny("nt", dkq, Wq)                               # dKp = dKq Wq^T
@@ -261,6 +270,13 @@ class _FusedHeadTrain(torch.autograd.Function):
         ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
                               *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
         ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
+        # Deferred weight gradients (FlatSGD(direct_grads=True)): every parameter carries a view of the optimizer's flat
+        # gradient buffer; the backward then writes dW / db straight into it from the side stream and does not join that
+        # stream — the optimizer does, so the parameter-gradient work overlaps the res5 / ROIAlign backward.
+        params = (W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb)
+        sinks = [getattr(p, "_b200_grad_sink", None) for p in params]
+        ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
+                                 s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
         ctx.mark_non_differentiable(logits)
         return losses, logits
 
@@ -287,40 +303,47 @@ class _FusedHeadTrain(torch.autograd.Function):
                   gt.data_ptr(), props.data_ptr(), gtb.data_ptr(), g3.data_ptr(), R, K, L, int(agnostic),
                   *map(float, box_w), float(l1_beta), dlogits.data_ptr(), C1p, ddeltas.data_ptr(), C4p, _ptr(dattn), st)
 
-        # Two streams: the data-gradient chain (dX GEMMs, LayerNorm / attention backward) is the critical path and stays
-        # on the current stream; everything that only feeds parameter gradients (operand transposes, dW GEMMs, bias
-        # column sums) runs on a side stream behind an event, filling the SMs the skinny / tail waves leave idle.
+        # Streams: the data-gradient chain (dX GEMMs, LayerNorm / attention backward) is the critical path and stays on the
+        # current stream; everything that only feeds parameter gradients (operand transposes, dW GEMMs, bias column sums)
+        # runs on a side stream behind events; the two text-side operand gradients (dKq, dVp) on the text stream, where
+        # their consumer (_TextSide.backward) runs.
         main = torch.cuda.current_stream()
         side = _side_stream(dev)
+        sinks = ctx.sinks
+        deferred = sinks is not None
+        sk = dict(zip(("W1", "b1", "W2", "b2", "W3", "b3", "Wf1", "bf1", "Wf2", "bf2", "gamma", "beta", "Wc", "bc", "Wb", "bb"),
+                      sinks if deferred else [None] * 16))
         out = {}
 
-        def fork(fn):
+        def fork(fn, *consumed, stream=side):
             e = torch.cuda.Event()
             e.record(main)
-            side.wait_event(e)
-            with torch.cuda.stream(side):
+            stream.wait_event(e)
+            for t in consumed:          # allocated on the current stream, read on the other one after this call returns
+                t.record_stream(stream)
+            with torch.cuda.stream(stream):
                 fn()
 
         def side_acts():     # transposes of saved forward activations: no dependence on any gradient
             out["xcatT"] = transpose_bf16(xcat)             # (2d, Rp): rows [d, 2d) are x^T
             out["zdT"], out["hdnT"], out["ybT"] = transpose_bf16(zd), transpose_bf16(hdn), transpose_bf16(yb)
-            out["p1T"], out["p2T"], out["attnT"] = transpose_bf16(p1), transpose_bf16(p2), transpose_bf16(attn)
-        fork(side_acts)
+            out["p1T"], out["p2T"] = transpose_bf16(p1), transpose_bf16(p2)
+        fork(side_acts, xcat, zd, hdn, yb, p1, p2)
 
         # ---- C1: logits = zd Wc^T + bc ; deltas = xb Wb^T + bb -------------------------------------------------
         def side_c1():
-            out["dWc"] = gemm_ex(transpose_bf16(dlogits), out["zdT"])[:C1]
-            out["dbc"] = colsum(dlogits, C1)
-            out["dWb"] = gemm_ex(transpose_bf16(ddeltas), out["xcatT"][d:])[:C4]
-            out["dbb"] = colsum(ddeltas, C4)
-        fork(side_c1)
+            out["dWc"] = gemm_ex(transpose_bf16(dlogits)[:C1], out["zdT"], out=sk["Wc"])
+            out["dbc"] = colsum(dlogits[:, :C1], out=sk["bc"])
+            out["dWb"] = gemm_ex(transpose_bf16(ddeltas)[:C4], out["xcatT"][d:], out=sk["Wb"])
+            out["dbb"] = colsum(ddeltas[:, :C4], out=sk["bb"])
+        fork(side_c1, dlogits, ddeltas)
         dzd = gemm_ex(dlogits, _wT(Wc, C1p), out_dtype=torch.bfloat16)
         dx = gemm_ex(ddeltas, _wT(Wb, C4p))                                        # first producer of dL/dx (fp32)
         # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
         du = torch.empty((R, d), dtype=torch.float32, device=dev)
         dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-        dgamma = torch.empty(d, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(d, dtype=torch.float32, device=dev)
+        dgamma = sk["gamma"] if deferred else torch.empty(d, dtype=torch.float32, device=dev)
+        dbeta = sk["beta"] if deferred else torch.empty(d, dtype=torch.float32, device=dev)
         nb = _lib.lib().b200_layernorm_bwd_workspace_bytes(R, d)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         _lib.call("b200_layernorm_relu_dropout_bwd", dzd.data_ptr(), y.data_ptr(), y2.data_ptr(), gam.data_ptr(),
@@ -328,32 +351,33 @@ class _FusedHeadTrain(torch.autograd.Function):
                   dbeta.data_ptr(), R, d, ws.data_ptr(), nb, st)
         # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
         def side_ffn2():
-            out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"])
-            out["dbf2"] = colsum(dub)        # the bf16 copy: `du` is overwritten in place by the dy GEMM below
-        fork(side_ffn2)
+            out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"], out=sk["Wf2"])
+            out["dbf2"] = colsum(dub, out=sk["bf2"])   # the bf16 copy: `du` is overwritten in place by the dy GEMM below
+        fork(side_ffn2, dub)
         dhdn = gemm_ex(dub, _wT(Wf2, d), out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
 
         def side_ffn1():
-            out["dWf1"] = gemm_ex(transpose_bf16(dhdn), out["ybT"])
-            out["dbf1"] = colsum(dhdn)
-        fork(side_ffn1)
+            out["dWf1"] = gemm_ex(transpose_bf16(dhdn), out["ybT"], out=sk["Wf1"])
+            out["dbf1"] = colsum(dhdn, out=sk["bf1"])
+        fork(side_ffn1, dhdn)
         dyb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         gemm_ex(dhdn, _wT(Wf1, Wf1.shape[0]), out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
         # ---- linear3: y = [o1 | o2 | xb] W3^T + b3 -----------------------------------------------------------
         def side_l3():
-            out["dW3"] = gemm_ex(transpose_bf16(dyb), out["xcatT"])
-            out["db3"] = colsum(du)
-        fork(side_l3)
+            out["dW3"] = gemm_ex(transpose_bf16(dyb), out["xcatT"], out=sk["W3"])
+            out["db3"] = colsum(du, out=sk["b3"])      # du now holds dy (fp32)
+        fork(side_l3, dyb, du)
         W3T = _wT(W3, d)                                                           # (2d, d)
         do12 = gemm_ex(dyb, W3T[:d], out_dtype=torch.bfloat16, mask=xcat[:, :d])   # [do1 | do2], ReLU backward fused
         gemm_ex(dyb, W3T[d:], out=dx, accumulate=True)
         # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
         def side_l12():
             do12T = transpose_bf16(do12)
-            out["dW1"] = gemm_ex(do12T[:h], out["p1T"])
-            out["dW2"] = gemm_ex(do12T[h:], out["p2T"])
-            out["db12"] = colsum(do12)
-        fork(side_l12)
+            out["dW1"] = gemm_ex(do12T[:h], out["p1T"], out=sk["W1"])
+            out["dW2"] = gemm_ex(do12T[h:], out["p2T"], out=sk["W2"])
+            out["db1"] = colsum(do12[:, :h], out=sk["b1"])
+            out["db2"] = colsum(do12[:, h:], out=sk["b2"])
+        fork(side_l12, do12)
         dp1 = gemm_ex(do12[:, :h], _wT(W1, h), out_dtype=torch.bfloat16)
         dp2 = gemm_ex(do12[:, h:], _wT(W2, h), out_dtype=torch.bfloat16)
         # ---- A3 core: P1 = O * x, P2 = x - O, O = softmax(S) Vp ------------------------------------------------
@@ -362,21 +386,35 @@ class _FusedHeadTrain(torch.autograd.Function):
         _lib.call("b200_text_attention_bwd", dp1.data_ptr(), dp2.data_ptr(), dp1.stride(0), x.data_ptr(), attn.data_ptr(),
                   vp.data_ptr(), _ptr(dattn), dx.data_ptr(), 1, dO.data_ptr(), dS.data_ptr(), Lp, R, d, L, st)
 
+        text = _TEXT_STREAMS.get((dev.type, dev.index), side)
+
         def side_att():
-            out["dvp"] = gemm_ex(out["attnT"], transpose_bf16(dO))                 # (L, d)
-            out["dkq"] = gemm_ex(transpose_bf16(dS), out["xcatT"][d:])[:L]
-        fork(side_att)
+            out["dvp"] = gemm_ex(transpose_bf16(attn), transpose_bf16(dO))         # (L, d)
+            out["dkq"] = gemm_ex(transpose_bf16(dS), transpose_bf16(xcat[:, d:]))[:L]
+        fork(side_att, attn, dO, dS, xcat, stream=text)
         # ---- scores: S = xb Kq^T ----------------------------------------------------------------------------------
         gemm_ex(dS, _wT(kq, Lp), out=dx, accumulate=True)
         done = torch.cuda.Event()
         done.record(side)
+        tdone = torch.cuda.Event()
+        tdone.record(text)
+        if deferred:
+            # The parameter gradients are awaited by the optimizer (FlatSGD.sync_grads), dKq / dVp by their consumer
+            # (_TextSide.backward looks the event up by the gradient's address), not by this stream.
+            PENDING_GRAD_EVENTS.append(done)
+            for g in (out["dkq"], out["dvp"]):
+                g.record_stream(main)
+                _READY_EVENTS[g.data_ptr()] = tdone
+            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 9
         main.wait_event(done)
+        main.wait_event(tdone)
         dkq, dvp, dW1, dW2, dW3, dWf1, dWf2, dWc, dWb = (out[k] for k in ("dkq", "dvp", "dW1", "dW2", "dW3", "dWf1", "dWf2", "dWc", "dWb"))
-        db12, db3, dbf1, dbf2, dbc, dbb = (out[k] for k in ("db12", "db3", "dbf1", "dbf2", "dbc", "dbb"))
-        return (dx, dkq, dvp, dW1, db12[:h], dW2, db12[h:], dW3, db3, dWf1, dbf1, dWf2, dbf2, dgamma, dbeta, dWc, dbc,
-                dWb, dbb) + (None,) * 9
+        return (dx, dkq, dvp, dW1, out["db1"], dW2, out["db2"], dW3, out["db3"], dWf1, out["dbf1"], dWf2, out["dbf2"], dgamma,
+                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 9
 
 
+_READY_EVENTS = {}           # gradient address -> event after which it may be read (producer on another stream)
+PENDING_GRAD_EVENTS = []     # side-stream completion events of deferred parameter gradients (drained by FlatSGD.sync_grads)
 _SIDE = {}
 
 
@@ -408,28 +446,42 @@ def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes,
 
 class FlatSGD:
     """SGD + momentum over one flat fp32 buffer that the parameters are re-pointed into (one kernel per step;
-    torch.optim.SGD semantics as configured by defrcn/solver/build.py: momentum 0.9, weight decay, no dampening)."""
+    torch.optim.SGD semantics as configured by defrcn/solver/build.py: momentum 0.9, weight decay, no dampening).
+    Every parameter starts on a 256-byte boundary of the buffer.  direct_grads=True additionally hands each parameter
+    its slice of the flat gradient buffer as `_b200_grad_sink`: `_FusedHeadTrain.backward` then writes parameter
+    gradients there itself, from its side stream, and `sync_grads` (called by `step`, and by the caller before a
+    gradient all-reduce) is where that stream is joined.  Requires every such parameter to be used once per step."""
 
-    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0):
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0, direct_grads=False):
         self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n = (n + p.numel() + 63) // 64 * 64
         dev = self.params[0].device
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
-            off += k
+            if direct_grads:
+                p._b200_grad_sink = p.grad
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
 
     def zero_grad(self):
         self.grad.zero_()
 
+    def sync_grads(self):
+        """Make the current stream wait for parameter gradients still being written on side streams."""
+        cur = torch.cuda.current_stream()
+        while PENDING_GRAD_EVENTS:
+            cur.wait_event(PENDING_GRAD_EVENTS.pop())
+
     def step(self):
+        self.sync_grads()
         _lib.call("b200_sgd_momentum", self.flat.data_ptr(), self.grad.data_ptr(), self.mom.data_ptr(), self.flat.numel(),
                   float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
         ops_mod.PARAM_GENERATION[0] += 1     # the bf16 weight caches key on this (in-place kernel updates bypass _version)

@@ -273,3 +273,30 @@ def test_frozen_res5_mean_node_vs_per_block_autograd(golden, skip):
     pb.backward(gp)
     assert _rel(xa.grad.float(), xb.grad.float()) < 1e-2
     assert _cos(xa.grad.float(), xb.grad.float()) > 0.9999
+
+
+def test_deferred_parameter_gradients_match_autograd_accumulation(golden):
+    """FlatSGD(direct_grads=True): `_FusedHeadTrain.backward` writes dW / db into the optimizer's flat gradient buffer
+    from its side stream and leaves the join to `sync_grads`.  Same bits as the path where autograd accumulates the
+    returned gradients, including the text-side parameters that receive dKq / dVp across streams."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    g = golden("train_step")
+    grads = []
+    for direct in (False, True):
+        m = _build(g)
+        params = list(m.attention.parameters()) + list(m.box_predictor.parameters())
+        opt = train_ops.FlatSGD(params, lr=0.01, direct_grads=direct)
+        m._DROP_STEP[0] = 0
+        for step in range(2):            # second step: sinks reused after zero_grad
+            opt.zero_grad()
+            m.prefetch_text_side()
+            x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+            props = _proposals(g)
+            losses, _ = m.fused_train_losses(x, props, props[0].gt_classes)
+            sum(losses.values()).backward()
+            opt.sync_grads()
+        torch.cuda.synchronize()
+        assert not train_ops.PENDING_GRAD_EVENTS and not train_ops._READY_EVENTS
+        grads.append((opt.grad.clone(), x.grad.clone()))
+    assert float(grads[0][0].abs().sum()) > 0
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
