@@ -58,7 +58,7 @@ def parse():
 def synth_inputs(n_images, props, seed0=1234, num_classes=20):
     """SURVEY.md §8(d) synthetic inputs: post-ReLU res4 maps, RPN-like + jittered proposals, per-image seeds; for the
     fine-tune direction the proposals come sampled and labelled (25 % foreground, GT = jittered proposal)."""
-    from oracle.gen_golden import synth_proposals
+    from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals
     feat = torch.relu(torch.randn(n_images, C4, HF, WF, generator=torch.Generator().manual_seed(0)))
     boxes, gt_cls, gt_boxes = [], [], []
     for i in range(n_images):
@@ -211,7 +211,7 @@ def workload_config(args, images_per_gpu):
     else:
         what = "inference step: affine_rcnn -> ROIAlign 7x7 -> res5 -> text fusion -> decode/NMS top-100"
     return {"workload": "DeFRCN R-101 C4 text-fused ROI head (SematicRes5ROIHeads, CLIP 512-d, K=%d), %s" % (args.classes, what),
-            "mode": args.mode,
+            "mode": args.mode, "classes": args.classes,
             "roi_align_bins": "all 49" if getattr(args, "full_bins", False) else "16 live of 49 (stride-2 consumer)",
             "images_per_gpu_per_step": images_per_gpu, "proposals_per_image": args.props, "image_px": [H_IMG, W_IMG],
             "res4_map": [C4, HF, WF], "l2": "flushed between timed steps (256 MiB write)", "parallelism": "image-sharded dp%d" % args.gpus}

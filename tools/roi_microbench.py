@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops  # noqa: E402
-from oracle.gen_golden import synth_proposals  # noqa: E402
+from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals  # noqa: E402
 
 
 def main():
