@@ -92,6 +92,107 @@ __global__ void affine_transpose_kernel(const Tin* __restrict__ x, const float* 
   }
 }
 
+// Vectorised layout-changing variant: 64 x 64 tiles, 16-byte (fp32) / 8-byte (bf16) global accesses on both sides,
+// 16 elements per thread.  x viewed as [N][A][B] -> y [N][B][A]; needs A % 4 == 0, B % 4 == 0 and aligned bases.
+// WITH_GRAD (backward, NHWC gradient -> NCHW grad_x, so B = C): the same pass also reads the forward input x (NCHW, the
+// output's addressing) and leaves per-(image, tile) partial sums of dw[c] = sum g x and db[c] = sum g for an ordered
+// final reduction — the separate parameter-gradient pass re-read both maps with channel-strided accesses.
+constexpr int kAT = 64;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t*>(&h0);
+    t.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+template <typename Tin, typename Tout, bool WITH_GRAD>
+__global__ void __launch_bounds__(256)
+affine_tile_kernel(const Tin* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, float mult,
+                   Tout* __restrict__ y, int A, int B, int a_is_channel, const float* __restrict__ fwd_x,
+                   float* __restrict__ partial) {
+  __shared__ float tile[kAT][kAT + 1];
+  const int tiles_b = (B + kAT - 1) / kAT;
+  const int n = blockIdx.x / tiles_b;               // batch folded into grid.x (grid.z is limited to 65535)
+  const int a0 = blockIdx.y * kAT, b0 = (blockIdx.x % tiles_b) * kAT;
+  const size_t base = (size_t)n * A * B;
+  const int t = threadIdx.x;
+  // load: thread <-> (row a = t / 16 + 16 i, 4 consecutive b); raw values (the affine is applied on the way out)
+  {
+    const int bq = (t & 15) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ar = (t >> 4) + 16 * i;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a0 + ar < A && b0 + bq < B) Vec4<Tin>::load(x + base + (size_t)(a0 + ar) * B + b0 + bq, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tile[ar][bq + k] = v[k];
+    }
+  }
+  __syncthreads();
+  // store: thread <-> (column b = t / 16 + 16 i, 4 consecutive a)
+  const int aq = (t & 15) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int br = (t >> 4) + 16 * i;
+    const int bb = b0 + br, a = a0 + aq;
+    const bool ok = bb < B && a < A;
+    float g[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = tile[aq + k][br];
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = a_is_channel ? a + k : bb;
+        v[k] = affine_op(g[k], w ? __ldg(w + c) : 1.f, mult, b != nullptr, b ? __ldg(b + c) : 0.f);
+      }
+      Vec4<Tout>::store(y + base + (size_t)bb * A + a, v);
+    }
+    if (WITH_GRAD) {
+      float gw = 0.f, gb = 0.f;
+      if (ok) {
+        float xv[4];
+        Vec4<float>::load(fwd_x + base + (size_t)bb * A + a, xv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { gw += g[k] * xv[k]; gb += g[k]; }
+      }
+      // the 16 lanes of a half-warp hold the tile's 64 positions of channel bb
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        gw += __shfl_xor_sync(0xffffffffu, gw, o);
+        gb += __shfl_xor_sync(0xffffffffu, gb, o);
+      }
+      if ((t & 15) == 0 && bb < B) {
+        const size_t chunk = (size_t)n * gridDim.y + blockIdx.y;
+        partial[(chunk * B + bb) * 2 + 0] = gw;
+        partial[(chunk * B + bb) * 2 + 1] = gb;
+      }
+    }
+  }
+}
+
+static bool affine_tile_ok(const void* x, const void* y, int A, int B) {
+  return A % 4 == 0 && B % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0;
+}
+
 template <typename Tin, typename Tout>
 static int launch_affine(const void* x, const float* w, const float* b, float mult, void* y, int N, int C,
                          int H, int W, int in_layout, int out_layout, cudaStream_t st) {
@@ -116,8 +217,14 @@ static int launch_affine(const void* x, const float* w, const float* b, float mu
   } else {
     const int a_is_channel = in_layout == B200_NCHW;
     const int A = a_is_channel ? C : HW, B = a_is_channel ? HW : C;
-    dim3 grid(ceil_div(B, 32) * N, ceil_div(A, 32)), block(32, 8);
-    affine_transpose_kernel<Tin, Tout><<<grid, block, 0, st>>>((const Tin*)x, w, b, mult, (Tout*)y, A, B, a_is_channel);
+    if (affine_tile_ok(x, y, A, B)) {
+      dim3 grid(ceil_div(B, kAT) * N, ceil_div(A, kAT));
+      affine_tile_kernel<Tin, Tout, false><<<grid, 256, 0, st>>>((const Tin*)x, w, b, mult, (Tout*)y, A, B, a_is_channel,
+                                                                 nullptr, nullptr);
+    } else {
+      dim3 grid(ceil_div(B, 32) * N, ceil_div(A, 32)), block(32, 8);
+      affine_transpose_kernel<Tin, Tout><<<grid, block, 0, st>>>((const Tin*)x, w, b, mult, (Tout*)y, A, B, a_is_channel);
+    }
   }
   B200_CUDA_LAUNCH_CHECK("gdl_affine");
   return B200_OK;
@@ -202,8 +309,8 @@ extern "C" int b200_gdl_affine_fwd(const void* x, const float* weight, const flo
 }
 
 extern "C" size_t b200_gdl_affine_bwd_workspace_bytes(int N, int C, int H, int W) {
-  (void)N; (void)H; (void)W;
-  return (size_t)kRedChunks * C * 2 * sizeof(float);
+  const size_t chunks = max((size_t)kRedChunks, (size_t)max(N, 1) * (size_t)ceil_div(H * W, kAT));
+  return chunks * C * 2 * sizeof(float);
 }
 
 extern "C" int b200_gdl_affine_bwd(const void* grad_y, const void* x, const float* weight, float lambda,
@@ -212,6 +319,25 @@ extern "C" int b200_gdl_affine_bwd(const void* grad_y, const void* x, const floa
                                    size_t workspace_bytes, b200_stream_t stream) {
   B200_CHECK_ARG(grad_y, "gdl_affine_bwd: null grad_y");
   cudaStream_t st = (cudaStream_t)stream;
+  const int HW_ = H * W;
+  // The fine-tune path's shape: bf16 channels-last gradient in, fp32 NCHW grad_x out, parameter gradients wanted:
+  // one pass does the layout change, the scaling and the per-tile partial sums of dw / db.
+  if (grad_x && (grad_w || grad_b) && x && in_dtype == B200_F32 && in_layout == B200_NCHW && out_dtype == B200_BF16 &&
+      out_layout == B200_NHWC && affine_tile_ok(grad_y, grad_x, HW_, C) && ((uintptr_t)x & 15) == 0 && N > 0) {
+    const int chunks = N * ceil_div(HW_, kAT);
+    if (!workspace || workspace_bytes < (size_t)chunks * C * 2 * sizeof(float)) {
+      set_error("gdl_affine_bwd: workspace too small");
+      return B200_ERR_WORKSPACE;
+    }
+    float* partial = (float*)workspace;
+    dim3 grid(ceil_div(C, kAT) * N, ceil_div(HW_, kAT));
+    affine_tile_kernel<__nv_bfloat16, float, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)grad_y, weight, nullptr, lambda,
+                                                                         (float*)grad_x, HW_, C, 0, (const float*)x, partial);
+    B200_CUDA_LAUNCH_CHECK("gdl_affine_bwd tile");
+    affine_param_grad_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partial, grad_w, grad_b, C, chunks);
+    B200_CUDA_LAUNCH_CHECK("gdl_affine_bwd final");
+    return B200_OK;
+  }
   if (grad_x) {
     // grad_x (in_dtype,in_layout) = grad_y (out_dtype,out_layout) * w * lambda
     int rc = dispatch_affine(grad_y, weight, nullptr, lambda, grad_x, N, C, H, W, out_dtype, out_layout, in_dtype,
