@@ -312,8 +312,9 @@ def main():
         (losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]).backward()   # L1, A*, P2, P1b, G1/G2 bwd
         mark(8)
         if world > 1:
-            opt.sync_grads()                                                                  # join the parameter-gradient stream
-            dist.all_reduce(opt.grad, op=dist.ReduceOp.AVG)                                   # the one real exchange step
+            # the one real exchange step: head gradients on a communication stream behind the parameter-gradient streams
+            # (under the res5 / ROIAlign backward still queued on the GPU), affine_rcnn's two vectors at the end
+            opt.all_reduce_grads(n_late_params=len(list(aff.parameters())))
         opt.step()
         mark(9)
         return {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),

@@ -123,7 +123,7 @@ def add_relu_mask(a, b=None, ref=None):
     return y
 
 
-def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias=False):
+def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias=False, out=None, out_b=None):
     """fp32 contractions with a short side (csrc/text_side.cu).  mode 'nt': A (M,K), B (N,K) -> (M,N);
     'nn': A (M,N), B (N,K) -> (M,K); 'tn': A (M,N), B (M,K) -> (N,K) [+ column sums of A].  Taller A goes in row blocks
     of 32 (the big operand B is streamed once per block)."""
@@ -137,14 +137,20 @@ def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias
     code = {"nt": 0, "nn": 1, "tn": 2}[mode]
     if mode == "nt":
         N, K = B.shape[0], B.shape[1]
-        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        oshape = (M, N)
     elif mode == "nn":
         N, K = B.shape
-        out = torch.empty((M, K), dtype=torch.float32, device=dev)
+        oshape = (M, K)
     else:
         N, K = A.shape[1], B.shape[1]
-        out = torch.empty((N, K), dtype=torch.float32, device=dev)
-    ob = torch.empty(N, dtype=torch.float32, device=dev) if (out_bias and mode == "tn") else None
+        oshape = (N, K)
+    if out is None:
+        out = torch.empty(oshape, dtype=torch.float32, device=dev)
+    assert out.dtype == torch.float32 and tuple(out.shape) == oshape and out.stride(-1) == 1
+    ob = None
+    if out_bias and mode == "tn":
+        ob = out_b if out_b is not None else torch.empty(N, dtype=torch.float32, device=dev)
+        assert ob.dtype == torch.float32 and ob.numel() == N and ob.is_contiguous()
     b32 = None if bias is None else bias.detach().float().contiguous()
     nbytes = 0 if mode == "tn" else _lib.lib().b200_skinny_gemm_workspace_bytes(min(M, 32), N if mode == "nt" else K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
@@ -167,6 +173,10 @@ class _TextSide(torch.autograd.Function):
     @staticmethod
     def forward(ctx, T, Wkp, bkp, Wvp, bvp, Wk, Wv, dummy, Wq):
         _require_cuda(T, Wkp, Wvp, Wk, Wv, dummy, Wq)
+        params = (Wkp, bkp, Wvp, bvp, Wk, Wv, dummy, Wq)
+        sinks = [getattr(p, "_b200_grad_sink", None) for p in params]        # see _FusedHeadTrain.forward
+        ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
+                                 s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
         f = lambda t: t.detach().float().contiguous()
         T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq = map(f, (T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq))
         d = Wq.shape[0]
@@ -189,18 +199,28 @@ class _TextSide(torch.autograd.Function):
             if ev is not None:
                 cur.wait_event(ev)
                 g.record_stream(cur)
+        sk = dict(zip(("Wkp", "bkp", "Wvp", "bvp", "Wk", "Wv", "dummy", "Wq"), ctx.sinks or [None] * 8))
         dkq = (dkq.float() * s).contiguous()
         dvp = dvp.float().contiguous()
         dkp = skinny("nt", dkq, Wq)                               # dKp = dKq Wq^T
-        dWq = skinny("tn", kp, dkq)                               # dWq[i][j] = sum_l Kp[l][i] dKq[l][j]
-        ddummy = dkp[-1:].clone()
+        dWq = skinny("tn", kp, dkq, out=sk["Wq"])                 # dWq[i][j] = sum_l Kp[l][i] dKq[l][j]
+        if ctx.sinks is not None:
+            sk["dummy"].copy_(dkp[-1:].reshape(sk["dummy"].shape))
+            ddummy = None
+        else:
+            ddummy = dkp[-1:].clone()
         dkp0, dvp0 = dkp[:-1], dvp[:-1]
-        dWk = skinny("tn", dkp0, kt)
-        dWv = skinny("tn", dvp0, vt)
+        dWk = skinny("tn", dkp0, kt, out=sk["Wk"])
+        dWv = skinny("tn", dvp0, vt, out=sk["Wv"])
         dkt = skinny("nn", dkp0, Wk)                              # before the ReLU mask (applied as relu_ref below)
         dvt = skinny("nn", dvp0, Wv)
-        dWkp, dbkp = skinny("tn", dkt, T, relu_ref=kt, out_bias=True)
-        dWvp, dbvp = skinny("tn", dvt, T, relu_ref=vt, out_bias=True)
+        dWkp, dbkp = skinny("tn", dkt, T, relu_ref=kt, out_bias=True, out=sk["Wkp"], out_b=sk["bkp"])
+        dWvp, dbvp = skinny("tn", dvt, T, relu_ref=vt, out_bias=True, out=sk["Wvp"], out_b=sk["bvp"])
+        if ctx.sinks is not None:      # gradients written in place on this stream: the optimizer joins it (sync_grads)
+            done = torch.cuda.Event()
+            done.record(cur)
+            PENDING_GRAD_EVENTS.append(done)
+            return (None,) * 9
         return None, dWkp, dbkp, dWvp, dbvp, dWk, dWv, ddummy, dWq
 
 
@@ -413,6 +433,7 @@ class _FusedHeadTrain(torch.autograd.Function):
                 dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 9
 
 
+_COMM_STREAMS = {}
 _READY_EVENTS = {}           # gradient address -> event after which it may be read (producer on another stream)
 PENDING_GRAD_EVENTS = []     # side-stream completion events of deferred parameter gradients (drained by FlatSGD.sync_grads)
 _SIDE = {}
@@ -458,6 +479,7 @@ class FlatSGD:
         for p in self.params:
             offs.append(n)
             n = (n + p.numel() + 63) // 64 * 64
+        self.offsets = offs + [n]
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -470,15 +492,47 @@ class FlatSGD:
             if direct_grads:
                 p._b200_grad_sink = p.grad
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self._zeroed = None
 
     def zero_grad(self):
         self.grad.zero_()
+        self._zeroed = torch.cuda.Event()
+        self._zeroed.record()
 
     def sync_grads(self):
         """Make the current stream wait for parameter gradients still being written on side streams."""
         cur = torch.cuda.current_stream()
         while PENDING_GRAD_EVENTS:
             cur.wait_event(PENDING_GRAD_EVENTS.pop())
+
+    def all_reduce_grads(self, n_late_params=0, group=None):
+        """Gradient all-reduce (replaces DDP at engine/defaults.py:252-258) for one process per GPU.  The gradients of all
+        but the last `n_late_params` parameters are complete once the side streams recorded in PENDING_GRAD_EVENTS are
+        (the head's parameters: frozen res5 means nothing upstream of the head trains except affine_rcnn), so their
+        all-reduce goes on a communication stream behind those events and runs under the res5 / ROIAlign backward that
+        the current stream still has queued; only the late tail is reduced on the current stream."""
+        import torch.distributed as dist
+        cur = torch.cuda.current_stream()
+        dev = self.grad.device
+        key = (dev.type, dev.index)
+        if key not in _COMM_STREAMS:
+            _COMM_STREAMS[key] = torch.cuda.Stream(device=dev)
+        comm = _COMM_STREAMS[key]
+        split = self.offsets[len(self.params) - n_late_params] if n_late_params else self.grad.numel()
+        if not PENDING_GRAD_EVENTS or n_late_params == 0:
+            self.sync_grads()
+            dist.all_reduce(self.grad, op=dist.ReduceOp.AVG, group=group)
+            return
+        if self._zeroed is not None:
+            comm.wait_event(self._zeroed)            # not before this step's zero_grad
+        while PENDING_GRAD_EVENTS:
+            comm.wait_event(PENDING_GRAD_EVENTS.pop())
+        with torch.cuda.stream(comm):
+            dist.all_reduce(self.grad[:split], op=dist.ReduceOp.AVG, group=group)
+            done = torch.cuda.Event()
+            done.record(comm)
+        dist.all_reduce(self.grad[split:], op=dist.ReduceOp.AVG, group=group)
+        cur.wait_event(done)
 
     def step(self):
         self.sync_grads()
