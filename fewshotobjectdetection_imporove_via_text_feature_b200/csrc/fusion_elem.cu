@@ -300,6 +300,41 @@ extern "C" int b200_residual_layernorm(const float* y, const float* y2, const fl
   return B200_OK;
 }
 
+// Optional cosine + temperature form of the prototype logits (C1'): rows scaled to unit L2 norm (norm clamped at eps, the
+// reference helper's rule: my_module.py:461-469 `sim_matrix`), times `scale`, as the bf16 operand of the logits GEMM.
+// One warp per row, two passes over a row that stays in L1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+l2_normalize_rows_kernel(const T* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst, int rows, int cols,
+                         float eps, float scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* s = src + (size_t)row * ld_src;
+  float ss = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = (float)s[c];
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  const float inv = scale / fmaxf(sqrtf(ss), eps);
+  __nv_bfloat16* d = dst + (size_t)row * ld_dst;
+  for (int c = lane; c < cols; c += 32) d[c] = __float2bfloat16_rn((float)s[c] * inv);
+}
+
+extern "C" int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols,
+                                      float eps, float scale, b200_stream_t stream) {
+  B200_CHECK_ARG(src && dst_bf16, "l2_normalize_rows: null tensor");
+  B200_CHECK_ARG(rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols && (src_dtype | 1) == 1, "l2_normalize_rows: bad shape");
+  if (rows == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == B200_F32)
+    l2_normalize_rows_kernel<float><<<ceil_div(rows, 8), 256, 0, st>>>((const float*)src, ld_src, (__nv_bfloat16*)dst_bf16, ld_dst, rows, cols, eps, scale);
+  else
+    l2_normalize_rows_kernel<__nv_bfloat16><<<ceil_div(rows, 8), 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst_bf16, ld_dst, rows, cols, eps, scale);
+  B200_CUDA_LAUNCH_CHECK("l2_normalize_rows");
+  return B200_OK;
+}
+
 extern "C" int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,
                               b200_stream_t stream) {
   B200_CHECK_ARG(src && dst, "cast_bf16: null tensor");

@@ -209,6 +209,10 @@ class SematicRes5ROIHeads(Res5ROIHeads):
 
     def __init_LV_model__(self, input_size, cfg):
         self.fused_training = bool(b200_opt(cfg, "FUSED_TRAINING", True))
+        # optional cosine + temperature logits against the text prototypes (CrossOutput head); off = the reference's
+        # un-normalised dot product (roi_heads.py:1157-1159)
+        self.cosine_logits = bool(b200_opt(cfg, "COSINE_LOGITS", False))
+        self.cosine_tau = float(b200_opt(cfg, "COSINE_TAU", 20.0))
         self.addition_model = cfg.MODEL.ADDITION.NAME
         self.semantic_dim = SEMANTIC_DIM[self.addition_model]
         self.attention = SematicProposalAttention(input_size, cfg=cfg, is_multi=False)
@@ -333,7 +337,11 @@ class SematicRes5ROIHeadsCrossOutput(SematicRes5ROIHeads):
         if self.training and torch.is_grad_enabled():
             _, output_att = self.attention(feature_pooled)
             a = F.relu(self.output_projection(output_att["sim2stext"]))
-            score = torch.matmul(a, output_att["text_feat"].transpose(0, 1))
+            t = output_att["text_feat"]
+            if self.cosine_logits:         # my_module.py:461-469 `sim_matrix` x temperature (:449-458)
+                a = a / a.norm(dim=1, keepdim=True).clamp_min(1e-12)
+                t = t / t.norm(dim=1, keepdim=True).clamp_min(1e-12) * self.cosine_tau
+            score = torch.matmul(a, t.transpose(0, 1))
             xb = None
         else:
             extra = {"output_projection.weight": self.output_projection.weight, "output_projection.bias": self.output_projection.bias}
@@ -341,7 +349,11 @@ class SematicRes5ROIHeadsCrossOutput(SematicRes5ROIHeads):
             w = output_att["fused_w"]
             a = ops.gemm_bf16(output_att["sim2stext_bf16"], w["extra.output_projection.weight"],
                               w["extra.output_projection.bias"], relu=True, out_dtype=torch.bfloat16)
-            tb = output_att["text_feat"].to(torch.bfloat16).contiguous()
+            if self.cosine_logits:         # unit rows on both sides, temperature folded into the (K+1)-row text operand
+                a = ops.l2_normalize_rows(a)
+                tb = ops.l2_normalize_rows(output_att["text_feat"].float().contiguous(), scale=self.cosine_tau)
+            else:
+                tb = output_att["text_feat"].to(torch.bfloat16).contiguous()
             score = ops.gemm_bf16(a, tb)
             xb = output_att.get("x_bf16")
         logits, deltas = self.box_predictor(feature_pooled, score, xb, None)

@@ -423,6 +423,20 @@ def cast_bf16_into(src, dst):
     return dst
 
 
+def l2_normalize_rows(src, scale=1.0, eps=1e-12):
+    """(rows, cols) fp32|bf16 -> bf16, each row scaled to `scale` / max(||row||, eps): the cosine form of the prototype
+    logits (my_module.py:461-469 `sim_matrix`), as the K-contiguous operand of the logits GEMM (row stride rup8(cols))."""
+    _require_cuda(src)
+    rows, cols = src.shape
+    assert src.stride(1) == 1 and src.dtype in (torch.float32, torch.bfloat16)
+    ld = (cols + 7) // 8 * 8
+    dst = torch.zeros((rows, ld), dtype=torch.bfloat16, device=src.device) if ld != cols else \
+        torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device)
+    _lib.call("b200_l2_normalize_rows", src.data_ptr(), _dt(src), src.stride(0), dst.data_ptr(), ld, rows, cols, float(eps),
+              float(scale), _stream())
+    return dst[:, :cols]
+
+
 class TextFusionWeights:
     """bf16 copies of the attention / predictor weights laid out for the GEMM kernel, plus the projected text
     keys/values.  Rebuilt whenever the parameters' versions change (constant at inference — the reference

@@ -256,6 +256,12 @@ B200_API int b200_mean_bwd_relu_mask(const float* gpooled, int ld_g, const void*
 B200_API int b200_add_relu_mask(const void* a_bf16, const void* b_bf16, const void* ref_bf16, void* y_bf16, size_t n,
                        b200_stream_t stream);
 
+/* dst[r][:] = bf16(scale * src[r][:] / max(||src[r]||_2, eps)) — row normalisation for the optional cosine + temperature
+ * form of the prototype logits (the reference's helper: my_module.py:461-469 `sim_matrix`, :449-458 `bsim_matrix`);
+ * src fp32 or bf16 (src_dtype), leading dimensions in elements. */
+B200_API int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols,
+                           float eps, float scale, b200_stream_t stream);
+
 /* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
  * in place, without a torch.cat) */
 B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,

@@ -372,6 +372,19 @@ def gen_known_answer():
                         logits_head=pl[:64].float().numpy(), gt_head=gt[:64].numpy())
 
 
+def gen_cosine():
+    """Cosine similarity helpers of the reference (my_module.py:449-469: bsim_matrix, sim_matrix), run unchanged: the
+    semantics behind the optional cosine + temperature logits against the text prototypes."""
+    rs.install()
+    mm = rs.load("defrcn.modeling.roi_heads.my_module")
+    gen = torch.Generator().manual_seed(21)
+    a = torch.relu(torch.randn(40, 64, generator=gen))
+    a[3] = 0                                                   # zero row: the eps clamp
+    t = torch.randn(21, 64, generator=gen)
+    np.savez(os.path.join(OUT, "cosine.npz"), a=a.numpy(), t=t.numpy(), sim=mm.sim_matrix(a, t).numpy(),
+             bsim=mm.bsim_matrix(a[None], t[None], tau=20.0)[0].numpy(), tau=np.float32(20.0))
+
+
 def main():
     import sys
     if len(sys.argv) > 1:       # regenerate selected fixtures only: python -m oracle.gen_golden gen_train_step ...
@@ -391,6 +404,7 @@ def main():
     gen_teacher()
     gen_train_step()
     gen_known_answer()
+    gen_cosine()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -439,3 +439,13 @@ def voc_eval_class(dets, gts, ovthresh=0.5, use_07_metric=False):
     rec = tp / float(max(npos, 1))
     prec = tp / np.maximum(tp + fp, np.finfo(np.float64).eps)
     return float(voc_ap(rec, prec, use_07_metric))
+
+
+# ------------------------------------------------------------------ cosine logits (optional epilogue of C1')
+def sim_matrix(a, b, eps=1e-12, tau=1.0):
+    """my_module.py:461-469 `sim_matrix` (row-wise L2 normalisation with the norm clamped at eps, then a @ b^T), times a
+    temperature as in `bsim_matrix` (:449-458)."""
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    a_n = a / torch.clamp(a.norm(dim=1)[:, None], min=eps)
+    b_n = b / torch.clamp(b.norm(dim=1)[:, None], min=eps)
+    return torch.mm(a_n, b_n.transpose(0, 1)) * tau

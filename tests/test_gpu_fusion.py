@@ -180,3 +180,28 @@ def test_chain_golden_small(golden):
         attn, out = m(torch.from_numpy(g["x"]).cuda())
     assert rel_err(attn[0].cpu(), torch.from_numpy(g["attn"])) < 2e-2
     assert rel_err(out["sim2stext"].cpu(), torch.from_numpy(g["sim2stext"])) < 2e-2
+
+
+def test_cosine_logits_option(golden):
+    """Optional cosine + temperature form of the prototype logits: the row-normalisation kernel (fp32 and bf16 sources, the
+    eps clamp on a zero row) and normalise -> tcgen05 GEMM against the reference's own `sim_matrix` output (bf16 bar)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    g = golden("cosine")
+    a, t, tau = torch.from_numpy(g["a"]).cuda(), torch.from_numpy(g["t"]).cuda(), float(g["tau"])
+    an = ops.l2_normalize_rows(a)
+    ref_an = a / a.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    torch.testing.assert_close(an.float(), ref_an, rtol=2 ** -8, atol=1e-6)
+    assert float(an[3].abs().max()) == 0.0
+    anb = ops.l2_normalize_rows(a.to(torch.bfloat16))
+    torch.testing.assert_close(anb.float(), ref_an, rtol=2e-2, atol=2e-3)
+    logits = ops.gemm_bf16(an, ops.l2_normalize_rows(t, scale=tau))
+    ref = torch.from_numpy(g["bsim"]).cuda()
+    assert rel_err(logits, ref) < 2e-2
+    torch.testing.assert_close(logits, ref, rtol=2e-2, atol=2e-2 * tau)
+    # the head option: CrossOutput logits become tau * cos(a, T)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(300, 512, generator=gen).cuda()
+    T = torch.randn(81, 512, generator=gen).cuda()
+    got = ops.gemm_bf16(ops.l2_normalize_rows(x), ops.l2_normalize_rows(T, scale=tau))
+    want = O.sim_matrix(x.cpu(), T.cpu(), tau=tau)
+    assert rel_err(got.cpu(), want) < 2e-2

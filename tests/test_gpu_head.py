@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -75,6 +76,24 @@ def test_head_tiny_golden(golden, tag, head, layer):
             d = (gb - b).abs().max(dim=1).values
             hit += bool(((d < 2.0) & (gc == c)).any())
         assert hit >= 0.9 * len(ref_b)
+
+
+def test_cross_output_cosine_logits_option(golden):
+    """MODEL.B200.COSINE_LOGITS: the CrossOutput head's prototype logits become tau * cos(projected feature, text
+    prototype) (the reference's `sim_matrix` semantics, my_module.py:461-469); kernel path (eval) vs the torch expression
+    of the training branch on the same weights, bf16 bar.  Default off = the golden (un-normalised) logits."""
+    g, m, props = _tiny_head(golden, "head_tiny_cross", "SematicRes5ROIHeadsCrossOutput", "FastRCNNAttentionOutputLayers")
+    assert m.cosine_logits is False
+    feat = T(g["feat"]).cuda()
+    m.cosine_logits, m.cosine_tau = True, 10.0
+    with torch.no_grad():
+        fp = m._pooled({"res4": feat}, props)
+        got = m.forward_att(fp)[0]["pred_logits"].float()
+        _, oa = m.attention(fp)
+        a = F.relu(m.output_projection(oa["sim2stext"].float()))
+        want = O.sim_matrix(a.cpu(), oa["text_feat"].float().cpu(), tau=10.0)
+    assert got.shape == want.shape and float(want.abs().max()) <= 10.0 + 1e-3
+    assert float((got.cpu() - want).norm() / want.norm()) < 2e-2
 
 
 def test_head_full_width_vs_oracle():

@@ -148,3 +148,13 @@ def test_train_step_autograd(golden):
             assert float((v.grad - ref).norm()) <= 1e-3 * float(ref.norm()) + 1e-6, k
             n += 1
     assert n >= 24
+
+
+def test_cosine_similarity_helpers(golden):
+    """Oracle restatement of the reference's cosine helpers (my_module.py:449-469) against their own outputs — the
+    semantics of the optional cosine + temperature logits (zero row: the eps clamp)."""
+    g = golden("cosine")
+    assert torch.allclose(O.sim_matrix(g["a"], g["t"]), T(g["sim"]), rtol=1e-6, atol=1e-7)
+    # bsim_matrix normalises with F.normalize (same eps) and multiplies by tau
+    assert torch.allclose(O.sim_matrix(g["a"], g["t"], tau=float(g["tau"])), T(g["bsim"]), rtol=1e-5, atol=1e-5)
+    assert float(O.sim_matrix(g["a"], g["t"])[3].abs().max()) == 0.0
