@@ -294,13 +294,15 @@ def main():
             return out
         mark(0)
         opt.zero_grad()
-        head.prefetch_text_side()                                                             # T1 (+ text half of A1/A2) on a side stream
+        begin = torch.cuda.Event()
+        begin.record()                                                                        # parameters hold this step's values
         x = d["feat"].detach().requires_grad_(True)
         f = aff(x, GDL_LAMBDA, True, torch.bfloat16)                                          # G1 + G2
         mark(1)
         pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)       # P1
         mark(2)
         fp = head._res5_mean(pooled, prestrided=bin_step > 1)                                 # P2 (frozen: one node)
+        head.prefetch_text_side(after=begin)                                                  # T1 (+ text half of A1/A2): side stream, under res5
         mark(3)
         gt = d["gt_cls"].reshape(-1)
         losses, _ = head.fused_train_losses(fp, props, gt)                                    # T1, A1-A6, C1, L1
@@ -333,9 +335,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         l0 = _lib.LAUNCHES
+        host_prof = None
+        if os.environ.get("BENCH_HOST_PROFILE"):        # where the host time of a step goes (cProfile, stderr)
+            import cProfile
+            host_prof = cProfile.Profile()
+            host_prof.enable()
+        t_cpu0 = time.perf_counter()
         for i in range(args.steps):
             flush.fill_(i & 0xff)
             out = step(resident, evs[i])
+        if host_prof is not None:
+            import pstats
+            host_prof.disable()
+            pstats.Stats(host_prof, stream=sys.stderr).sort_stats("tottime").print_stats(45)
+        cpu_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / max(args.steps, 1)    # host time to enqueue one step (no sync)
         if world > 1 and not train:
             insts = [Instances(sizes[0], pred_boxes=Boxes(out["boxes"][i]), scores=out["scores"][i], pred_classes=out["classes"][i]) for i in range(B)]
             cnt, dets = bdist.pack_detections(insts)
@@ -486,7 +499,7 @@ def main():
             "roofline": gemm_roof if dominant_is_gemm else roi_roof,
             "roofline_other": roi_roof if dominant_is_gemm else gemm_roof,
             "stage_ms": dict(zip(stage_names, stage_ms)),
-            "own_kernels_ms_per_step": ours_ms,
+            "own_kernels_ms_per_step": ours_ms, "host_enqueue_ms_per_step": cpu_enqueue_ms,
             "own_kernels_profile": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "flop_per_step"}
                                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         }

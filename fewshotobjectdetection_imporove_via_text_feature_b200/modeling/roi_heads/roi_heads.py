@@ -181,7 +181,13 @@ class Res5ROIHeads(ROIHeads):
         skip = self.skip_dead_bins and not self._res5_trainable() and blk0.reads_strided_1x1()
         x = self.pooler([features[f] for f in self.in_features], [p.proposal_boxes for p in proposals],
                         bin_step=blk0.stride if skip else 1)
-        return self._res5_mean(x, prestrided=skip)
+        pooled = self._res5_mean(x, prestrided=skip)
+        self._after_res5_enqueued()
+        return pooled
+
+    def _after_res5_enqueued(self):
+        """Hook: res5 has been enqueued (not finished) — the place to start side-stream work that should share the GPU
+        with res5's tensor-core kernels rather than with the pooler."""
 
     def forward(self, images, features, proposals, targets=None):
         del images
@@ -294,19 +300,27 @@ class SematicRes5ROIHeads(Res5ROIHeads):
                 type(self).forward_att is SematicRes5ROIHeads.forward_att and
                 type(self.box_predictor).__name__ == "FastRCNNOutputLayers")
 
-    def prefetch_text_side(self):
+    def prefetch_text_side(self, after=None):
         """Start this step's text-side projections on a side stream (train_ops.text_side_async); `fused_train_losses`
-        picks the result up.  Called at the top of `forward` so that they run under ROIAlign / res5."""
+        picks the result up.  Called once res5 has been enqueued, gated on an event from the top of `forward`, so that
+        on the GPU they run under res5 (the slice-resident ROIAlign kernel is persistent with a static work split and
+        needs whole SMs: sharing them costs its tail) while the host has nothing queued ahead of the pooler."""
         from ... import train_ops
         if self.attention.attention.w_q.weight.is_cuda:
-            self._text_pending = train_ops.text_side_async(self.attention)
+            self._text_pending = train_ops.text_side_async(self.attention, after=after)
+
+    def _after_res5_enqueued(self):
+        if self._fused_train_path() and getattr(self, "_step_begin", None) is not None:
+            self.prefetch_text_side(after=self._step_begin)
+            self._step_begin = None
 
     def forward(self, images, features, proposals, targets=None):
         del images
         test_with_gt = (not self.training) and bool(targets)
         gt_classes = 0
-        if self._fused_train_path():
-            self.prefetch_text_side()
+        if self._fused_train_path() and self.attention.attention.w_q.weight.is_cuda:
+            self._step_begin = torch.cuda.Event()          # the parameters hold this step's values from here on
+            self._step_begin.record()
         if self.training:
             proposals = self.label_and_sample_proposals(proposals, targets)
             gt_classes = cat([p.gt_classes for p in proposals], dim=0)

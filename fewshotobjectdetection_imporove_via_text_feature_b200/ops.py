@@ -20,7 +20,10 @@ KERNEL_EVENTS = {}
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current CUDA stream of the current device.  The C-level accessors cost well under a microsecond;
+    `torch.cuda.current_stream()` builds a Stream object and re-validates the device on every call (> 10 us, and it is
+    needed ~100 times per fine-tune step)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _require_cuda(*ts):
@@ -131,6 +134,28 @@ def _plan_stream(dev):
     return _PLAN_STREAMS[key]
 
 
+class _PlanBuffer:
+    """Workspace of one ROIAlign backward plan, drawn from a small per-(device, size) free list instead of the caching
+    allocator: a ~100 MB block that crosses streams every step would otherwise be re-requested while its cross-stream
+    use is still pending, and the allocator answers that with a fresh cudaMalloc (a host stall of about a millisecond).
+    Returned to the list when the autograd context that holds it goes away; reuse is ordered by the streams themselves
+    (the next plan launch waits for the current stream, which has the previous consumer queued)."""
+    _free = {}
+
+    def __init__(self, device, nbytes):
+        self.key = (device.type, device.index, int(nbytes))
+        pool = _PlanBuffer._free.setdefault(self.key, [])
+        self.buf = pool.pop() if pool else torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+    def __del__(self):
+        try:
+            pool = _PlanBuffer._free.setdefault(self.key, [])
+            if len(pool) < 4:
+                pool.append(self.buf)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 class _ROIAlign(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, rois, roi_batch_offsets, output_size, spatial_scale, sampling_ratio, aligned,
@@ -167,16 +192,15 @@ class _ROIAlign(torch.autograd.Function):
             if pbytes:
                 main, side = torch.cuda.current_stream(), _plan_stream(feat.device)
                 side.wait_stream(main)
+                holder = _PlanBuffer(feat.device, pbytes)
                 with torch.cuda.stream(side):
-                    plan = torch.empty(pbytes, dtype=torch.uint8, device=feat.device)
                     _lib.call("b200_roi_align_bwd_plan", rois.data_ptr(), roi_batch_offsets.data_ptr(), N, C, H, W, R, PH, PW,
-                              int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)), plan.data_ptr(),
-                              pbytes, side.cuda_stream)
+                              int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                              holder.buf.data_ptr(), pbytes, side.cuda_stream)
                     done = torch.cuda.Event()
                     done.record(side)
-                rois.record_stream(side)
-                roi_batch_offsets.record_stream(side)
-                ctx.plan = (plan, done)
+                # `rois` / offsets stay referenced by ctx until the backward, which waits on `done` first
+                ctx.plan = (holder, done)
         return out
 
     @staticmethod
@@ -191,12 +215,10 @@ class _ROIAlign(torch.autograd.Function):
         gin = _empty4(N, C, H, W, dtype, g.device, in_layout == NHWC)
         g_layout = NHWC if cl_out else NCHW
         if ctx.plan is not None and g.dtype == torch.bfloat16 and g.data_ptr() % 16 == 0:
-            plan, done = ctx.plan
-            cur = torch.cuda.current_stream()
-            cur.wait_event(done)
-            plan.record_stream(cur)
-            _lib.call("b200_roi_align_bwd_planned", g.data_ptr(), plan.data_ptr(), plan.numel(), gin.data_ptr(), N, C, H, W, R,
-                      PH, PW, int(bin_step), _stream())
+            holder, done = ctx.plan
+            torch.cuda.current_stream().wait_event(done)
+            _lib.call("b200_roi_align_bwd_planned", g.data_ptr(), holder.buf.data_ptr(), holder.buf.numel(), gin.data_ptr(), N, C,
+                      H, W, R, PH, PW, int(bin_step), _stream())
             return gin, None, None, None, None, None, None, None, None
         nbytes = _lib.lib().b200_roi_align_bwd_workspace_bytes(N, C, H, W, R, PH, PW, int(bin_step), _dt(g), in_layout,
                                                                g_layout)

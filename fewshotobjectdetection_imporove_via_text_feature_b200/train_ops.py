@@ -219,7 +219,7 @@ class _TextSide(torch.autograd.Function):
         if ctx.sinks is not None:      # gradients written in place on this stream: the optimizer joins it (sync_grads)
             done = torch.cuda.Event()
             done.record(cur)
-            PENDING_GRAD_EVENTS.append(done)
+            PENDING_GRAD_EVENTS.append((done, [dkq, dvp]))
             return (None,) * 9
         return None, dWkp, dbkp, dWvp, dbvp, dWk, dWv, ddummy, dWq
 
@@ -235,16 +235,21 @@ def text_side(att):
 _TEXT_STREAMS = {}
 
 
-def text_side_async(att):
+def text_side_async(att, after=None):
     """`text_side` on a side stream: the (K+2)-row text side depends only on parameters, so its forward can run under
-    the ROIAlign / res5 kernels of the same step and — autograd replays a node on the stream its forward ran on — its
-    backward under the res5 / ROIAlign backward.  Returns (kq, vp, event); the consumer waits on the event."""
+    the res5 kernels of the same step and — autograd replays a node on the stream its forward ran on — its backward
+    under the res5 / ROIAlign backward.  `after`: an event recorded on the current stream once the parameters hold this
+    step's values (e.g. at the top of the head's forward); without it the side stream waits for everything enqueued on
+    the current stream so far.  Returns (kq, vp, event); the consumer waits on the event."""
     dev = att.attention.w_q.weight.device
     key = (dev.type, dev.index)
     if key not in _TEXT_STREAMS:
         _TEXT_STREAMS[key] = torch.cuda.Stream(device=dev)
     main, side = torch.cuda.current_stream(), _TEXT_STREAMS[key]
-    side.wait_stream(main)               # parameters were last written (optimizer step) on the current stream
+    if after is not None:
+        side.wait_event(after)
+    else:
+        side.wait_stream(main)           # parameters were last written (optimizer step) on the current stream
     with torch.cuda.stream(side):
         kq, vp = text_side(att)
         done = torch.cuda.Event()
@@ -335,12 +340,13 @@ class _FusedHeadTrain(torch.autograd.Function):
                       sinks if deferred else [None] * 16))
         out = {}
 
+        keep = []                       # current-stream tensors read on the other streams after this call returns
+
         def fork(fn, *consumed, stream=side):
             e = torch.cuda.Event()
             e.record(main)
             stream.wait_event(e)
-            for t in consumed:          # allocated on the current stream, read on the other one after this call returns
-                t.record_stream(stream)
+            keep.extend(consumed)
             with torch.cuda.stream(stream):
                 fn()
 
@@ -421,9 +427,11 @@ class _FusedHeadTrain(torch.autograd.Function):
         if deferred:
             # The parameter gradients are awaited by the optimizer (FlatSGD.sync_grads), dKq / dVp by their consumer
             # (_TextSide.backward looks the event up by the gradient's address), not by this stream.
-            PENDING_GRAD_EVENTS.append(done)
+            # Tensors those streams still read are kept referenced next to the event (dropped in sync_grads, once the
+            # current stream has waited on it) rather than handed to record_stream: blocks with pending cross-stream
+            # uses make the caching allocator cudaMalloc afresh when the next step asks for the same sizes.
+            PENDING_GRAD_EVENTS.append((done, keep))
             for g in (out["dkq"], out["dvp"]):
-                g.record_stream(main)
                 _READY_EVENTS[g.data_ptr()] = tdone
             return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 9
         main.wait_event(done)
@@ -503,7 +511,8 @@ class FlatSGD:
         """Make the current stream wait for parameter gradients still being written on side streams."""
         cur = torch.cuda.current_stream()
         while PENDING_GRAD_EVENTS:
-            cur.wait_event(PENDING_GRAD_EVENTS.pop())
+            ev, _keepalive = PENDING_GRAD_EVENTS.pop()
+            cur.wait_event(ev)
 
     def all_reduce_grads(self, n_late_params=0, group=None):
         """Gradient all-reduce (replaces DDP at engine/defaults.py:252-258) for one process per GPU.  The gradients of all
@@ -525,14 +534,18 @@ class FlatSGD:
             return
         if self._zeroed is not None:
             comm.wait_event(self._zeroed)            # not before this step's zero_grad
+        held = []
         while PENDING_GRAD_EVENTS:
-            comm.wait_event(PENDING_GRAD_EVENTS.pop())
+            ev, keepalive = PENDING_GRAD_EVENTS.pop()
+            comm.wait_event(ev)
+            held.append(keepalive)
         with torch.cuda.stream(comm):
             dist.all_reduce(self.grad[:split], op=dist.ReduceOp.AVG, group=group)
             done = torch.cuda.Event()
             done.record(comm)
         dist.all_reduce(self.grad[split:], op=dist.ReduceOp.AVG, group=group)
         cur.wait_event(done)
+        del held                                     # the current stream is now behind every stream that read them
 
     def step(self):
         self.sync_grads()
