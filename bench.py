@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--cpu-baseline-images", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="fine-tune mode: enqueue every step from the host instead of replaying one captured CUDA graph")
     ap.add_argument("--full-bins", action="store_true",
                     help="pool all 49 bins (the stand-alone ROIAlign op) instead of only the 16 that res5's stride-2 1x1 convs read")
     return ap.parse_args()
@@ -273,7 +275,7 @@ def main():
         stage_names = ["affine", "roi_align", "res5_mean", "text_fusion_predictor", "decode_nms"]
     n_marks = len(stage_names) + 1
 
-    def step(d, ev=None):
+    def step(d, ev=None, exchange=True):
         def mark(i):
             if ev is not None:
                 ev[i].record()
@@ -313,20 +315,52 @@ def main():
             f.register_hook(lambda g: ev[7].record())
         (losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]).backward()   # L1, A*, P2, P1b, G1/G2 bwd
         mark(8)
+        res = {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
+               "grad_feat": x.grad}
+        if not exchange:
+            opt.sync_grads()         # join the parameter-gradient streams (a captured region must end on one stream)
+            return res
         if world > 1:
             # the one real exchange step: head gradients on a communication stream behind the parameter-gradient streams
             # (under the res5 / ROIAlign backward still queued on the GPU), affine_rcnn's two vectors at the end
             opt.all_reduce_grads(n_late_params=len(list(aff.parameters())))
         opt.step()
         mark(9)
-        return {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
-                "grad_feat": x.grad}
+        return res
 
     grad_ctx = torch.enable_grad() if train else torch.no_grad()
     with grad_ctx:
         for _ in range(max(args.warmup, 3)):
             out = step(resident)
         torch.cuda.synchronize()
+        # ---- fine-tune step as one CUDA graph ------------------------------------------------------------
+        # ~200 launches on five streams per step cost the host about as long to enqueue as the GPU takes to run them;
+        # a busy host then stalls the GPU.  The whole step (zero_grad .. backward [.. SGD at world 1]) is captured once
+        # and replayed; inputs are copied into the graph's static buffers, the classifier-dropout step counter lives
+        # in device memory so every replay draws a new mask.  World > 1: the gradient all-reduce and SGD stay outside.
+        graph, graph_note = None, "off (--no-graph)" if train else "n/a"
+        if train and not args.no_graph:
+            try:
+                head.use_device_dropout_counter(True)
+                graph = train_ops.GraphedStep(lambda d: step(d, exchange=world == 1), resident)
+                graph_note = "whole step" if world == 1 else "forward + backward (all-reduce and SGD outside)"
+            except Exception as e:  # noqa: BLE001
+                graph, graph_note = None, "capture failed, running eagerly: %s" % str(e).splitlines()[0][:200]
+                head.use_device_dropout_counter(False)
+                torch.cuda.synchronize()
+
+        def run_step(d, ev=None):
+            if graph is None:
+                return step(d, ev)
+            if ev is not None:
+                ev[0].record()
+            static_out = graph(d)
+            if world > 1:
+                dist.all_reduce(opt.grad, op=dist.ReduceOp.AVG)
+                opt.step()
+            if ev is not None:
+                ev[n_marks - 1].record()
+            return static_out
         # ---- device-resident timing --------------------------------------------------------------------
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
         sampler = ClockSampler(local)
@@ -343,7 +377,7 @@ def main():
         t_cpu0 = time.perf_counter()
         for i in range(args.steps):
             flush.fill_(i & 0xff)
-            out = step(resident, evs[i])
+            out = run_step(resident, evs[i])
         if host_prof is not None:
             import pstats
             host_prof.disable()
@@ -359,7 +393,15 @@ def main():
         if world > 1:
             dist.barrier()
         per_step = [evs[i][0].elapsed_time(evs[i][n_marks - 1]) for i in range(args.steps)]
-        stage_ms = [float(np.mean([evs[i][s].elapsed_time(evs[i][s + 1]) for i in range(args.steps)])) for s in range(n_marks - 1)]
+        if graph is not None:        # stage marks cannot sit inside the graph: a few eager steps give the stage split
+            for _ in range(3):           # the eager path's allocations settle again after the capture
+                step(resident)
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(5)]
+            for i in range(5):
+                flush.fill_(i)
+                step(resident, evs[i])
+            torch.cuda.synchronize()
+        stage_ms = [float(np.mean([e[s].elapsed_time(e[s + 1]) for e in evs])) for s in range(n_marks - 1)]
         total_ms = torch.tensor([float(sum(per_step))], device=dev)
         if world > 1:
             dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -417,10 +459,10 @@ def main():
                     if i + 1 < n:
                         upload(i + 1)
                     cur.wait_event(ready[b])
-                    o = step(dbuf[b])
+                    o = run_step(dbuf[b])
                     free[b].record(cur)
                 else:
-                    o = step({k: host[k].to(dev, non_blocking=True) for k in names})
+                    o = run_step({k: host[k].to(dev, non_blocking=True) for k in names})
                 for k in res_host:
                     res_host[k].copy_(o[k], non_blocking=True)
                 if not overlap:
@@ -488,7 +530,7 @@ def main():
             "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, B),
+            "config": dict(workload_config(args, B), cuda_graph=graph_note),
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
                     "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in res_host.values())),
@@ -499,6 +541,7 @@ def main():
             "roofline": gemm_roof if dominant_is_gemm else roi_roof,
             "roofline_other": roi_roof if dominant_is_gemm else gemm_roof,
             "stage_ms": dict(zip(stage_names, stage_ms)),
+            "stage_ms_note": "eager steps (the timed steps replay one CUDA graph)" if graph is not None else "timed steps",
             "own_kernels_ms_per_step": ours_ms, "host_enqueue_ms_per_step": cpu_enqueue_ms,
             "own_kernels_profile": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "flop_per_step"}
                                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},

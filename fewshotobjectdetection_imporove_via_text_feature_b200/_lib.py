@@ -40,9 +40,9 @@ SIGNATURES = {
     "b200_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_colsum_workspace_bytes": (c_size_t, [c_int]),
     "b200_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
-    "b200_dropout_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_float, ctypes.c_ulonglong, c_void_p]),
+    "b200_dropout_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_float, ctypes.c_ulonglong, c_void_p, c_void_p]),
     "b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "b200_layernorm_relu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_float, c_float, ctypes.c_ulonglong] + [c_void_p] * 4 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "b200_layernorm_relu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_float, c_float, ctypes.c_ulonglong] + [c_void_p] * 5 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_text_attention_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "b200_head_losses": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float] * 5 + [c_void_p, c_void_p]),
     "b200_head_losses_bwd": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_float] * 5 + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),

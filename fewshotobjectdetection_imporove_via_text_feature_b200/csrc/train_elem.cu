@@ -121,7 +121,8 @@ __host__ __device__ inline uint32_t dropout_thresh(float p) {
 }
 
 __global__ void dropout_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, float p,
-                                   unsigned long long seed) {
+                                   unsigned long long seed, const unsigned long long* __restrict__ salt) {
+  if (salt) seed += *salt;              // device-resident step counter: a captured CUDA graph draws a new mask per replay
   const uint32_t th = dropout_thresh(p);
   const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (size_t)gridDim.x * blockDim.x * 2) {
@@ -151,8 +152,9 @@ __global__ void __launch_bounds__(256)
 layernorm_relu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dzd, const float* __restrict__ y,
                                   const float* __restrict__ y2, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float eps, float p, unsigned long long seed,
-                                  float* __restrict__ du_f32, __nv_bfloat16* __restrict__ du_bf16,
-                                  float* __restrict__ stats, int R, int d) {
+                                  const unsigned long long* __restrict__ salt, float* __restrict__ du_f32,
+                                  __nv_bfloat16* __restrict__ du_bf16, float* __restrict__ stats, int R, int d) {
+  if (salt) seed += *salt;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -187,8 +189,9 @@ __global__ void __launch_bounds__(256)
 layernorm_param_grad_partial_kernel(const __nv_bfloat16* __restrict__ dzd, const float* __restrict__ y,
                                     const float* __restrict__ y2, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, const float* __restrict__ stats, float p,
-                                    unsigned long long seed, float* __restrict__ part_g, float* __restrict__ part_b, int R,
-                                    int d) {
+                                    unsigned long long seed, const unsigned long long* __restrict__ salt,
+                                    float* __restrict__ part_g, float* __restrict__ part_b, int R, int d) {
+  if (salt) seed += *salt;
   const int c = blockIdx.x * 256 + threadIdx.x;
   const int rb = blockIdx.y;
   const int per = (R + kColBlocks - 1) / kColBlocks;
@@ -485,12 +488,13 @@ extern "C" int b200_colsum(const void* src, int src_dtype, int ld, int rows, int
   return B200_OK;
 }
 
-extern "C" int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed, b200_stream_t stream) {
+extern "C" int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed,
+                                const unsigned long long* seed_salt, b200_stream_t stream) {
   B200_CHECK_ARG(p >= 0.f && p <= 1.f, "dropout: p must be in [0, 1]");
   if (n == 0) return B200_OK;
   B200_CHECK_ARG(x && y_bf16, "dropout: null tensor");
   const int blocks = (int)min((size_t)kNumSMs * 8, (n / 2 + 255) / 256 + 1);
-  dropout_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, n, p, seed);
+  dropout_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, n, p, seed, seed_salt);
   B200_CUDA_LAUNCH_CHECK("dropout_fwd");
   return B200_OK;
 }
@@ -501,8 +505,9 @@ extern "C" size_t b200_layernorm_bwd_workspace_bytes(int R, int d) {
 
 extern "C" int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float* y, const float* y2, const float* gamma,
                                                const float* beta, float eps, float p, unsigned long long seed,
-                                               float* du_f32, void* du_bf16, float* dgamma, float* dbeta, int R, int d,
-                                               void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+                                               const unsigned long long* seed_salt, float* du_f32, void* du_bf16,
+                                               float* dgamma, float* dbeta, int R, int d, void* workspace,
+                                               size_t workspace_bytes, b200_stream_t stream) {
   B200_CHECK_ARG(dzd_bf16 && y && y2 && gamma && beta && (du_f32 || du_bf16), "layernorm_bwd: null tensor");
   B200_CHECK_ARG(R >= 0 && d > 0, "layernorm_bwd: bad shape");
   B200_CHECK_ARG(workspace && workspace_bytes >= b200_layernorm_bwd_workspace_bytes(R, d), "layernorm_bwd: workspace too small");
@@ -512,11 +517,11 @@ extern "C" int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float
   float* pg = (float*)((unsigned char*)workspace + align_up((size_t)R * 2 * 4, 256));
   float* pb = pg + (size_t)kColBlocks * d;
   layernorm_relu_dropout_bwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, eps, p,
-                                                                    seed, du_f32, (__nv_bfloat16*)du_bf16, stats, R, d);
+                                                                    seed, seed_salt, du_f32, (__nv_bfloat16*)du_bf16, stats, R, d);
   if (dgamma || dbeta) {
     dim3 grid(ceil_div(d, 256), kColBlocks);
     layernorm_param_grad_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, stats, p,
-                                                              seed, pg, pb, R, d);
+                                                              seed, seed_salt, pg, pb, R, d);
     if (dgamma) colsum_final_kernel<<<ceil_div(d, 256), 256, 0, st>>>(pg, kColBlocks, d, dgamma, 0);
     if (dbeta) colsum_final_kernel<<<ceil_div(d, 256), 256, 0, st>>>(pb, kColBlocks, d, dbeta, 0);
   }

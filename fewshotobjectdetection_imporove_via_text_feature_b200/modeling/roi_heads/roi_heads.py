@@ -288,12 +288,23 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         gtb = cat([p.gt_boxes.tensor for p in proposals], dim=0)
         pred = self.box_predictor
         drop = pred._dropout_ratio if pred._do_cls_dropout else 0.0
-        self._DROP_STEP[0] += 1
-        seed = (torch.initial_seed() * 1000003 + self._DROP_STEP[0]) & 0x7FFFFFFFFFFFFFFF
+        salt = getattr(self, "_drop_salt", None)
+        if salt is None:
+            self._DROP_STEP[0] += 1
+            seed = (torch.initial_seed() * 1000003 + self._DROP_STEP[0]) & 0x7FFFFFFFFFFFFFFF
+        else:              # device-resident step counter (graph capture): the host part of the seed stays constant
+            salt.add_(1)
+            seed = (torch.initial_seed() * 1000003) & 0x7FFFFFFFFFFFFFFF
         losses, logits = train_ops.fused_head_train(feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb,
                                                     self.num_classes, self.box2box_transform.weights, self.smooth_l1_beta,
-                                                    drop, seed, True)
+                                                    drop, seed, True, salt)
         return {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}, logits
+
+    def use_device_dropout_counter(self, enable=True):
+        """Keep the classifier-dropout step counter in device memory (incremented by a kernel each step) instead of on the
+        host, so that a CUDA graph captured over the training step draws a fresh mask on every replay."""
+        dev = self.attention.attention.w_q.weight.device
+        self._drop_salt = torch.zeros(1, dtype=torch.int64, device=dev) if enable else None
 
     def _fused_train_path(self):
         return (self.training and torch.is_grad_enabled() and self.fused_training and

@@ -69,10 +69,11 @@ def colsum(src, n=None, out=None):
     return out if n is None else out[:n]
 
 
-def dropout_bf16(x, p, seed):
+def dropout_bf16(x, p, seed, salt=None):
+    """salt: optional int64 device scalar added to `seed` on the device (a step counter that survives graph replay)."""
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.call("b200_dropout_fwd", x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), _stream())
+    _lib.call("b200_dropout_fwd", x.data_ptr(), y.data_ptr(), x.numel(), float(p), int(seed), _ptr(salt), _stream())
     return y
 
 
@@ -262,7 +263,7 @@ class _FusedHeadTrain(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, kq, vp, W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb,
-                gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss):
+                gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt=None):
         _require_cuda(x, kq, vp, W1, W3, Wc, Wb, gt_classes, proposals, gt_boxes)
         x = x.detach().float().contiguous()
         R, d = x.shape
@@ -288,13 +289,14 @@ class _FusedHeadTrain(torch.autograd.Function):
         hdn = gemm_bf16(yb, W["Wf1"], bf1, relu=True, out_dtype=torch.bfloat16)
         y2 = gemm_bf16(hdn, W["Wf2"], bf2)
         z, _ = residual_layernorm(y, y2, gam, bet, 1e-5, relu=True, want_f32=True, want_bf16=False)
-        zd = dropout_bf16(z, drop_p, seed)
+        zd = dropout_bf16(z, drop_p, seed, salt)
         logits = gemm_bf16(zd, W["Wc"], bc)
         deltas = gemm_bf16(xb, W["Wb"], bb)
         losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
         ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
                               *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
         ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
+        ctx.salt = salt
         # Deferred weight gradients (FlatSGD(direct_grads=True)): every parameter carries a view of the optimizer's flat
         # gradient buffer; the backward then writes dW / db straight into it from the side stream and does not join that
         # stream — the optimizer does, so the parameter-gradient work overlaps the res5 / ROIAlign backward.
@@ -373,7 +375,7 @@ class _FusedHeadTrain(torch.autograd.Function):
         nb = _lib.lib().b200_layernorm_bwd_workspace_bytes(R, d)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         _lib.call("b200_layernorm_relu_dropout_bwd", dzd.data_ptr(), y.data_ptr(), y2.data_ptr(), gam.data_ptr(),
-                  bet.data_ptr(), 1e-5, float(drop_p), int(seed), du.data_ptr(), dub.data_ptr(), dgamma.data_ptr(),
+                  bet.data_ptr(), 1e-5, float(drop_p), int(seed), _ptr(ctx.salt), du.data_ptr(), dub.data_ptr(), dgamma.data_ptr(),
                   dbeta.data_ptr(), R, d, ws.data_ptr(), nb, st)
         # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
         def side_ffn2():
@@ -433,12 +435,12 @@ class _FusedHeadTrain(torch.autograd.Function):
             PENDING_GRAD_EVENTS.append((done, keep))
             for g in (out["dkq"], out["dvp"]):
                 _READY_EVENTS[g.data_ptr()] = tdone
-            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 9
+            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 10
         main.wait_event(done)
         main.wait_event(tdone)
         dkq, dvp, dW1, dW2, dW3, dWf1, dWf2, dWc, dWb = (out[k] for k in ("dkq", "dvp", "dW1", "dW2", "dW3", "dWf1", "dWf2", "dWc", "dWb"))
         return (dx, dkq, dvp, dW1, out["db1"], dW2, out["db2"], dW3, out["db3"], dWf1, out["dbf1"], dWf2, out["dbf2"], dgamma,
-                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 9
+                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 10
 
 
 _COMM_STREAMS = {}
@@ -463,14 +465,14 @@ def _wT(w, k_pad):
 
 
 def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed,
-                     want_attn_loss=True):
+                     want_attn_loss=True, salt=None):
     """att: SingleHeadSiameseAttention (parameters linear1/2/3, ffn.*), predictor: FastRCNNOutputLayers."""
     return _FusedHeadTrain.apply(
         x, kq, vp, att.linear1[0].weight, att.linear1[0].bias, att.linear2[0].weight, att.linear2[0].bias,
         att.linear3.weight, att.linear3.bias, att.ffn.linear1.weight, att.ffn.linear1.bias, att.ffn.linear2.weight,
         att.ffn.linear2.bias, att.ffn.norm3.weight, att.ffn.norm3.bias, predictor.cls_score.weight,
         predictor.cls_score.bias, predictor.bbox_pred.weight, predictor.bbox_pred.bias, gt_classes, proposals, gt_boxes,
-        K, box_weights, l1_beta, drop_p, seed, want_attn_loss)
+        K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt)
 
 
 class FlatSGD:
@@ -552,3 +554,35 @@ class FlatSGD:
         _lib.call("b200_sgd_momentum", self.flat.data_ptr(), self.grad.data_ptr(), self.mom.data_ptr(), self.flat.numel(),
                   float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
         ops_mod.PARAM_GENERATION[0] += 1     # the bf16 weight caches key on this (in-place kernel updates bypass _version)
+
+
+class GraphedStep:
+    """Capture `fn(static_inputs) -> outputs` as one CUDA graph and replay it.
+
+    The fine-tune step is ~200 launches on five streams; enqueueing them costs the host about as long as the GPU needs
+    to run them, so a busy host stalls the GPU.  `fn` must be capture-safe: fixed shapes, no host synchronisation, every
+    stream it forks joined again before it returns (`FlatSGD.sync_grads` / `step`), and step-dependent randomness keyed
+    on device memory (`SematicRes5ROIHeads.use_device_dropout_counter`).  `warmup` eager calls run first on a side
+    stream (they execute; the capture itself only records), then every call copies the inputs into the graph's static
+    buffers and replays."""
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        cur = torch.cuda.current_stream()
+        self.static_in = {k: v.clone() for k, v in example_inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(self.static_in)
+        torch.cuda.synchronize()
+
+    def __call__(self, inputs):
+        for k, v in inputs.items():
+            self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

@@ -186,15 +186,19 @@ B200_API size_t b200_colsum_workspace_bytes(int cols);
 B200_API int b200_colsum(const void* src, int src_dtype, int ld, int rows, int cols, float* out, int accumulate,
                 void* workspace, size_t workspace_bytes, b200_stream_t stream);
 /* classifier dropout (fast_rcnn.py:412-414): y = bf16(keep ? x / (1-p) : 0), keep = hash(seed, index) >= p*2^32.
- * The mask is never stored: the backward kernel re-evaluates the hash. */
-B200_API int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed, b200_stream_t stream);
+ * The mask is never stored: the backward kernel re-evaluates the hash.  seed_salt (device pointer, may be NULL) is
+ * added to `seed` on the device: a step counter that lives in device memory lets a captured CUDA graph draw a new
+ * mask on every replay. */
+B200_API int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed,
+                     const unsigned long long* seed_salt, b200_stream_t stream);
 /* backward of zd = dropout(relu(LayerNorm(y + y2))) (attentive_modules.py:73-74,285): du = dL/d(y + y2) as fp32
  * and/or bf16, dgamma / dbeta (may be NULL). */
 B200_API size_t b200_layernorm_bwd_workspace_bytes(int R, int d);
 B200_API int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float* y, const float* y2, const float* gamma,
-                                    const float* beta, float eps, float p, unsigned long long seed, float* du_f32,
-                                    void* du_bf16, float* dgamma, float* dbeta, int R, int d, void* workspace,
-                                    size_t workspace_bytes, b200_stream_t stream);
+                                    const float* beta, float eps, float p, unsigned long long seed,
+                                    const unsigned long long* seed_salt, float* du_f32, void* du_bf16, float* dgamma,
+                                    float* dbeta, int R, int d, void* workspace, size_t workspace_bytes,
+                                    b200_stream_t stream);
 /* backward of b200_text_attention (attentive_modules.py:45-55,166,170): given dP1, dP2 (bf16, row stride ldp) and
  * an optional external gradient on the attention probabilities (loss_attentive, roi_heads.py:1079-1081) computes
  *   dx (R,d) fp32 (+= when accumulate_dx), dO (R,d) bf16 (for dVp = attn^T dO through the GEMM),

@@ -170,6 +170,9 @@ def test_dropout_statistics_and_backward_mask():
     assert torch.equal(y, y2)
     assert not torch.equal(y, train_ops.dropout_bf16(x, 0.8, 1235).float())
     assert torch.equal(train_ops.dropout_bf16(x, 0.0, 7).float(), x.to(torch.bfloat16).float())
+    # device-resident salt (graph-replay step counter): seed + salt on the device == the summed seed on the host
+    salt = torch.tensor([3], dtype=torch.int64, device="cuda")
+    assert torch.equal(train_ops.dropout_bf16(x, 0.8, 1231, salt=salt), train_ops.dropout_bf16(x, 0.8, 1234))
 
 
 def test_flat_sgd_matches_torch_sgd():
@@ -300,3 +303,57 @@ def test_deferred_parameter_gradients_match_autograd_accumulation(golden):
         grads.append((opt.grad.clone(), x.grad.clone()))
     assert float(grads[0][0].abs().sum()) > 0
     assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
+def test_graphed_train_step_matches_eager(golden):
+    """train_ops.GraphedStep: the whole fine-tune step (zero_grad, frozen res5 + mean, fused head, backward on the side
+    streams, deferred gradients, SGD) captured as one CUDA graph and replayed gives the same parameters and losses, bit
+    for bit, as the same steps enqueued from the host — including a fresh dropout mask per replay (device counter)."""
+    import copy
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    g = golden("train_step")
+    base = _build(g)
+    for p in base.res5.parameters():
+        p.requires_grad_(False)
+    x0 = torch.relu(torch.randn(50, 32, 4, 4, generator=torch.Generator().manual_seed(5))).to(torch.bfloat16).cuda()
+    x0 = x0.contiguous(memory_format=torch.channels_last)
+    # 50 rows of pooled-map input; proposals / labels of the fixture are cycled to 50 rows
+    pr = _proposals(g)[0]
+    idx = torch.arange(50, device="cuda") % len(pr.gt_classes)
+    results = []
+    for graphed in (False, True):
+        m = copy.deepcopy(base)
+        m.use_device_dropout_counter(True)
+        params = list(m.attention.parameters()) + list(m.box_predictor.parameters())
+        opt = train_ops.FlatSGD(params, lr=0.02, momentum=0.9, direct_grads=True)
+        from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+        inst = Instances((600, 800))
+        inst.proposal_boxes, inst.gt_boxes = Boxes(pr.proposal_boxes.tensor[idx]), Boxes(pr.gt_boxes.tensor[idx])
+        inst.gt_classes = pr.gt_classes[idx]
+        losses_seen = []
+
+        def one_step(d):
+            opt.zero_grad()
+            begin = torch.cuda.Event()
+            begin.record()
+            xin = d["x"].detach().requires_grad_(True)
+            fp = m._res5_mean(xin, prestrided=True)
+            m.prefetch_text_side(after=begin)
+            losses, _ = m.fused_train_losses(fp, [inst], inst.gt_classes)
+            sum(losses.values()).backward()
+            opt.step()
+            return {"losses": torch.stack(list(losses.values())).detach(), "gx": xin.grad}
+
+        runner = train_ops.GraphedStep(one_step, {"x": x0}, warmup=3) if graphed else None
+        if not graphed:
+            for _ in range(3):
+                one_step({"x": x0})
+        for i in range(3):
+            xi = (x0.float() * (1.0 + 0.1 * i)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            out = runner({"x": xi}) if graphed else one_step({"x": xi})
+            losses_seen.append(out["losses"].clone())
+        torch.cuda.synchronize()
+        results.append((opt.flat.clone(), torch.stack(losses_seen), out["gx"].clone()))
+    assert not torch.equal(results[0][1][0], results[0][1][1])          # the steps differ (inputs, dropout mask, weights)
+    for a, b in zip(results[0], results[1]):
+        assert torch.equal(a, b)
