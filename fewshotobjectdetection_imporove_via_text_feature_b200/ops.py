@@ -410,7 +410,8 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
     b32 = None if bias is None else bias.detach().float().contiguous()
     _lib.call("b200_gemm_bf16", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
               out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu), _stream(),
-              tag=2.0 * M * N * K)
+              tag=(2.0 * M * N * K, (M, N, K, out.dtype == torch.bfloat16, out2 is not None, bool(relu), False, False,
+                                     bias is not None)))
     return out
 
 

@@ -37,7 +37,9 @@ def gemm_ex(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, out2
     b32 = None if bias is None else bias.detach().float().contiguous()
     _lib.call("b200_gemm_bf16_ex", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _ptr(b32), out.data_ptr(),
               out.stride(0), _dt(out), _ptr(out2), 0 if out2 is None else out2.stride(0), M, N, K, int(relu),
-              int(accumulate), _ptr(mask), 0 if mask is None else mask.stride(0), _stream(), tag=2.0 * M * N * K)
+              int(accumulate), _ptr(mask), 0 if mask is None else mask.stride(0), _stream(),
+              tag=(2.0 * M * N * K, (M, N, K, out.dtype == torch.bfloat16, out2 is not None, bool(relu), bool(accumulate),
+                                     mask is not None, bias is not None)))
     return out
 
 
@@ -577,8 +579,10 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
         with torch.cuda.graph(self.graph):
             self.static_out = fn(self.static_in)
+        self.kernel_launches = _lib.LAUNCHES - l0        # C-ABI kernels recorded into the graph = launched per replay
         torch.cuda.synchronize()
 
     def __call__(self, inputs):

@@ -11,7 +11,7 @@ for r in csv.DictReader(lines):
         v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
         rows.append((r["Kernel Name"], v))
 # a step starts at the forward affine pass (fp32 map in); the backward one (bf16 gradient in) is mid-step
-starts = [i for i, (n, _) in enumerate(rows) if "affine_transpose_kernel<float" in n]
+starts = [i for i, (n, _) in enumerate(rows) if "affine_tile_kernel<float" in n or "affine_transpose_kernel<float" in n]
 a, b = starts[-2], starts[-1]
 tot = sum(v for _, v in rows[a:b])
 ours = sum(v for n, v in rows[a:b] if "b200::" in n)
