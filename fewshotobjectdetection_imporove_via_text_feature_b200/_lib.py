@@ -56,6 +56,7 @@ SIGNATURES = {
     "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
     "b200_cast_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_label_sample_proposals": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.c_ulonglong] + [c_void_p] * 7 + [c_void_p]),
     "b200_l2_normalize_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p]),
 }
 
@@ -71,7 +72,7 @@ KERNELS_PER_CALL = {
     "b200_softmax_decode_compact": 1, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
-    "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1,
+    "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1, "b200_label_sample_proposals": 1,
 }
 LAUNCHES = 0
 # bench.py sets PROFILE = {} to have a CUDA event pair recorded around every entry-point call (name -> [(e0, e1, tag)]);

@@ -78,10 +78,41 @@ class ROIHeads(nn.Module):
         idx = torch.cat([fg, bg], dim=0)
         return idx, gt_classes[idx]
 
+    def _label_and_sample_device(self, proposals, targets):
+        """One kernel for the whole batch (ops.label_and_sample_proposals) and one small device->host read (the per-image
+        row counts, which the reference's logging needs on the host anyway) instead of a Python loop of torch ops with
+        several synchronisations per image.  Labels / matches are the reference's bit for bit; the random subsample
+        has its distribution but not torch's RNG stream."""
+        r = ops.label_and_sample_proposals([p.proposal_boxes.tensor for p in proposals], [t.gt_boxes.tensor for t in targets],
+                                           [t.gt_classes for t in targets], self.num_classes, self.proposal_matcher.thresholds[1],
+                                           self.batch_size_per_image, self.positive_sample_fraction)
+        counts = r["counts"].cpu().tolist()
+        out = []
+        for i, (p, t) in enumerate(zip(proposals, targets)):
+            n = counts[i][1]
+            idx = r["sampled_idx"][i, :n].long()
+            q = p[idx]
+            q.proposal_boxes = Boxes(r["boxes"][i, :n])
+            q.gt_classes = r["classes"][i, :n]
+            q.gt_boxes = Boxes(r["gt_boxes"][i, :n])
+            out.append(q)
+        n_fg = [c[0] for c in counts]
+        n_bg = [c[1] - c[0] for c in counts]
+        return out, n_fg, n_bg
+
     @torch.no_grad()
     def label_and_sample_proposals(self, proposals, targets):
         if self.proposal_append_gt:
             proposals = add_ground_truth_to_proposals([t.gt_boxes for t in targets], proposals)
+        th, lb = self.proposal_matcher.thresholds, self.proposal_matcher.labels
+        extra_gt = any(name.startswith("gt_") and name not in ("gt_boxes", "gt_classes") for t in targets for name in t.get_fields())
+        if (proposals and all(p.proposal_boxes.tensor.is_cuda for p in proposals) and len(th) == 3 and list(lb) == [0, 1] and
+                not extra_gt and max(len(p) for p in proposals) <= 4096 and max(len(t) for t in targets) <= 256):
+            out, n_fg, n_bg = self._label_and_sample_device(proposals, targets)
+            st = get_event_storage()
+            st.put_scalar("roi_head/num_fg_samples", np.mean(n_fg))
+            st.put_scalar("roi_head/num_bg_samples", np.mean(n_bg))
+            return out
         out, n_fg, n_bg = [], [], []
         for p, t in zip(proposals, targets):
             has_gt = len(t) > 0

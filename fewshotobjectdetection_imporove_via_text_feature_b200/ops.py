@@ -446,6 +446,46 @@ def cast_bf16_into(src, dst):
     return dst
 
 
+_LS_CALLS = [0]
+
+
+def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, iou_thresh=0.5, batch_per_image=512,
+                               positive_fraction=0.25, seed=None, want_labels=False):
+    """S1 on the device, one launch for the batch (csrc/label_sample.cu; reference roi_heads.py:157-250).
+    prop_boxes / gt_boxes / gt_classes: per-image lists of (P_i,4) fp32, (M_i,4) fp32, (M_i,) int64 CUDA tensors.
+    Returns dict: sampled_idx (N,B) int32, boxes (N,B,4), classes (N,B) int64, gt_boxes (N,B,4), counts (N,2) int32
+    [(#fg rows, #valid rows); rows past #valid are padding with class -1], and with want_labels the per-proposal
+    matched_idx / matched_label (concatenated over images)."""
+    N = len(prop_boxes)
+    dev = prop_boxes[0].device
+    _require_cuda(*prop_boxes)
+    pc, gc = [int(b.shape[0]) for b in prop_boxes], [int(b.shape[0]) for b in gt_boxes]
+    props = torch.cat([b.detach().float().reshape(-1, 4) for b in prop_boxes], 0).contiguous()
+    gts = torch.cat([b.detach().float().reshape(-1, 4) for b in gt_boxes], 0).contiguous() if sum(gc) else torch.zeros((0, 4), device=dev)
+    gcl = torch.cat([c.detach().to(torch.int64).reshape(-1) for c in gt_classes], 0).contiguous() if sum(gc) else torch.zeros(0, dtype=torch.int64, device=dev)
+    _, poff = _roi_index(tuple(pc), dev)
+    _, goff = _roi_index(tuple(gc), dev)
+    B = int(batch_per_image)
+    out = {"sampled_idx": torch.empty((N, B), dtype=torch.int32, device=dev),
+           "boxes": torch.empty((N, B, 4), dtype=torch.float32, device=dev),
+           "classes": torch.empty((N, B), dtype=torch.int64, device=dev),
+           "gt_boxes": torch.empty((N, B, 4), dtype=torch.float32, device=dev),
+           "counts": torch.empty((N, 2), dtype=torch.int32, device=dev)}
+    mi = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
+    ml = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
+    if seed is None:
+        _LS_CALLS[0] += 1
+        seed = (torch.initial_seed() * 2654435761 + _LS_CALLS[0]) & 0x7FFFFFFFFFFFFFFF
+    _lib.call("b200_label_sample_proposals", props.data_ptr(), poff.data_ptr(), _ptr(gts) if gts.numel() else 0,
+              _ptr(gcl) if gcl.numel() else 0, goff.data_ptr(), N, max(pc) if pc else 0, max(gc) if gc else 0, int(num_classes),
+              float(iou_thresh), B, int(B * positive_fraction), int(seed), _ptr(mi), _ptr(ml), out["sampled_idx"].data_ptr(),
+              out["boxes"].data_ptr(), out["classes"].data_ptr(), out["gt_boxes"].data_ptr(), out["counts"].data_ptr(),
+              _stream())
+    if want_labels:
+        out["matched_idx"], out["matched_label"] = mi, ml
+    return out
+
+
 def l2_normalize_rows(src, scale=1.0, eps=1e-12):
     """(rows, cols) fp32|bf16 -> bf16, each row scaled to `scale` / max(||row||, eps): the cosine form of the prototype
     logits (my_module.py:461-469 `sim_matrix`), as the K-contiguous operand of the logits GEMM (row stride rup8(cols))."""

@@ -266,6 +266,25 @@ B200_API int b200_add_relu_mask(const void* a_bf16, const void* b_bf16, const vo
 B200_API int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src, void* dst_bf16, int ld_dst, int rows, int cols,
                            float eps, float scale, b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * S1  ROIHeads.label_and_sample_proposals — defrcn/modeling/roi_heads/roi_heads.py:118-250
+ *     (detectron2 pairwise_iou + Matcher([0.5],[0,1]) + subsample_labels), one launch for the whole batch.
+ *   proposals (sum P_i, 4) / gt_boxes (sum M_i, 4) fp32 xyxy grouped by image with int32 offsets (num_images + 1);
+ *   P_i <= 4096, M_i <= 256.  Per image: best ground-truth match per proposal (first maximum; foreground iff
+ *   IoU >= iou_thresh; optional outputs matched_idx / matched_label over all proposals, bit-exact with the reference),
+ *   then min(max_positive, #fg) foreground + min(batch - that, #bg) background proposals chosen uniformly at random
+ *   (counter-based hash of (seed, image, proposal): the reference's distribution, not torch's RNG stream),
+ *   foreground rows first.  Outputs have batch_per_image rows per image: sampled_idx (index within the image, -1 =
+ *   padding), the sampled boxes, their class (num_classes = background, -1 = padding), the matched ground-truth box;
+ *   counts (num_images, 2) = (#foreground rows, #valid rows).
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_label_sample_proposals(const float* proposals, const int32_t* prop_offsets, const float* gt_boxes,
+                                const int64_t* gt_classes, const int32_t* gt_offsets, int num_images,
+                                int max_props_per_image, int max_gt_per_image, int num_classes, float iou_thresh,
+                                int batch_per_image, int max_positive, unsigned long long seed, int32_t* matched_idx,
+                                int32_t* matched_label, int32_t* sampled_idx, float* out_proposals, int64_t* out_classes,
+                                float* out_gt_boxes, int32_t* counts, b200_stream_t stream);
+
 /* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
  * in place, without a torch.cat) */
 B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,

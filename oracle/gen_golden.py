@@ -372,6 +372,57 @@ def gen_known_answer():
                         logits_head=pl[:64].float().numpy(), gt_head=gt[:64].numpy())
 
 
+def gen_label_sample():
+    """The reference's own ROIHeads.label_and_sample_proposals (roi_heads.py:157-250) on three synthetic images: many
+    proposals around a few objects, an image with more foreground than the 128 cap, and an image without ground truth.
+    Matching / labels are deterministic; of the random subsample the fixture keeps what is: the counts, and the sampled
+    foreground set where it is not subsampled."""
+    emb = lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg)
+    rs.install(class_embed_fn=emb)
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    am.get_class_embed = emb
+    rh = rs.load("defrcn.modeling.roi_heads.roi_heads")
+    K = 20
+    cfg = rs.default_cfg(num_classes=K, addition="clip", output_layer="FastRCNNOutputLayers", roi_head="SematicRes5ROIHeads")
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 4, 1
+    torch.manual_seed(1)
+    with cuda_as_cpu():
+        m = rh.build_roi_heads(cfg, {"res4": rs.ShapeSpec(channels=16, stride=16)}).train()
+    gen = torch.Generator().manual_seed(31)
+    d = dict(batch=np.int64(m.batch_size_per_image), pos_frac=np.float32(m.positive_sample_fraction),
+             append_gt=np.int64(bool(m.proposal_append_gt)), num_classes=np.int64(K))
+    props, targets = [], []
+    for i, (n, n_obj, jit) in enumerate(((1500, 6, 0.3), (900, 3, 0.9), (700, 0, 0.3), (320, 2, 0.3))):
+        h, w = 600, 800
+        b, objs = synth_proposals(n, h, w, gen, n_obj=max(n_obj, 1))
+        if jit > 0.5:          # most proposals hug the objects: more foreground than the cap
+            k = int(0.8 * n)
+            b[:k] = objs[torch.randint(0, len(objs), (k,), generator=gen)] + torch.randn(k, 4, generator=gen) * 3.0
+            b[:, 2:] = torch.maximum(b[:, 2:], b[:, :2] + 1.0)
+        p = rs.Instances((h, w))
+        p.proposal_boxes = rs.Boxes(b)
+        p.objectness_logits = torch.zeros(n)
+        t = rs.Instances((h, w))
+        t.gt_boxes = rs.Boxes(objs[:n_obj].clone())
+        t.gt_classes = torch.randint(0, K, (n_obj,), generator=gen)
+        props.append(p)
+        targets.append(t)
+        d["props%d" % i], d["gt_boxes%d" % i], d["gt_classes%d" % i] = b.numpy(), objs[:n_obj].numpy(), t.gt_classes.numpy()
+    torch.manual_seed(7)
+    out = m.label_and_sample_proposals(props, targets)
+    for i, (o, p, t) in enumerate(zip(out, props, targets)):
+        allp = torch.cat([p.proposal_boxes.tensor, t.gt_boxes.tensor], 0) if m.proposal_append_gt else p.proposal_boxes.tensor
+        d["all_props%d" % i] = allp.numpy()
+        if len(t) > 0:
+            iou = rs.pairwise_iou(t.gt_boxes, rs.Boxes(allp))
+            midx, mlab = m.proposal_matcher(iou)
+            d["matched_idx%d" % i], d["matched_label%d" % i] = midx.numpy(), mlab.numpy().astype(np.int64)
+        d["out_classes%d" % i] = o.gt_classes.numpy()
+        d["out_props%d" % i] = o.proposal_boxes.tensor.numpy()
+        d["out_gt%d" % i] = o.gt_boxes.tensor.numpy()
+    np.savez(os.path.join(OUT, "label_sample.npz"), **d)
+
+
 def gen_cosine():
     """Cosine similarity helpers of the reference (my_module.py:449-469: bsim_matrix, sim_matrix), run unchanged: the
     semantics behind the optional cosine + temperature logits against the text prototypes."""
@@ -405,6 +456,7 @@ def main():
     gen_train_step()
     gen_known_answer()
     gen_cosine()
+    gen_label_sample()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

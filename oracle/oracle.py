@@ -449,3 +449,27 @@ def sim_matrix(a, b, eps=1e-12, tau=1.0):
     a_n = a / torch.clamp(a.norm(dim=1)[:, None], min=eps)
     b_n = b / torch.clamp(b.norm(dim=1)[:, None], min=eps)
     return torch.mm(a_n, b_n.transpose(0, 1)) * tau
+
+
+# ------------------------------------------------------------------ S1: proposal labelling / sampling
+def label_proposals(props, gt_boxes, iou_thresh=0.5):
+    """detectron2 pairwise_iou + Matcher(thresholds=[iou_thresh], labels=[0, 1], allow_low_quality_matches=False) as called
+    from roi_heads.py:200-204: per proposal the ground-truth box of highest IoU (first maximum) and the fg (1) / bg (0)
+    label.  Returns (matched_idx int64 (P,), matched_label int64 (P,), max_iou fp32 (P,))."""
+    p, g = torch.as_tensor(props).float(), torch.as_tensor(gt_boxes).float().reshape(-1, 4)
+    P = p.shape[0]
+    if g.shape[0] == 0:
+        return torch.zeros(P, dtype=torch.int64), torch.zeros(P, dtype=torch.int64), torch.zeros(P)
+    a1 = (g[:, 2] - g[:, 0]) * (g[:, 3] - g[:, 1])
+    a2 = (p[:, 2] - p[:, 0]) * (p[:, 3] - p[:, 1])
+    wh = (torch.min(g[:, None, 2:], p[:, 2:]) - torch.max(g[:, None, :2], p[:, :2])).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    iou = torch.where(inter > 0, inter / (a1[:, None] + a2 - inter), torch.zeros(()))
+    vals, idx = iou.max(dim=0)
+    return idx, (vals >= iou_thresh).to(torch.int64), vals
+
+
+def sample_counts(n_fg, n_bg, batch=512, positive_fraction=0.25):
+    """detectron2 subsample_labels counts (roi_heads.py:118-155 `_sample_proposals`): (#fg rows, #bg rows)."""
+    num_pos = min(n_fg, int(batch * positive_fraction))
+    return num_pos, min(n_bg, batch - num_pos)

@@ -158,3 +158,20 @@ def test_cosine_similarity_helpers(golden):
     # bsim_matrix normalises with F.normalize (same eps) and multiplies by tau
     assert torch.allclose(O.sim_matrix(g["a"], g["t"], tau=float(g["tau"])), T(g["bsim"]), rtol=1e-5, atol=1e-5)
     assert float(O.sim_matrix(g["a"], g["t"])[3].abs().max()) == 0.0
+
+
+def test_label_proposals_vs_reference(golden):
+    """Oracle restatement of the matching / sampling counts of ROIHeads.label_and_sample_proposals against the
+    reference's own run (fixture: 3 images with ground truth — few objects, more foreground than the cap, fewer
+    proposals than the batch — and one without)."""
+    g = golden("label_sample")
+    B, frac, K = int(g["batch"]), float(g["pos_frac"]), int(g["num_classes"])
+    for i in (0, 1, 3):
+        idx, lab, _ = O.label_proposals(g["all_props%d" % i], g["gt_boxes%d" % i])
+        assert torch.equal(idx, T(g["matched_idx%d" % i])) and torch.equal(lab, T(g["matched_label%d" % i]))
+        n_fg = int(lab.sum())
+        npos, nneg = O.sample_counts(n_fg, len(lab) - n_fg, B, frac)
+        oc = T(g["out_classes%d" % i])
+        assert (int((oc < K).sum()), int((oc == K).sum())) == (npos, nneg)
+    idx, lab, _ = O.label_proposals(g["all_props2"], g["gt_boxes2"])
+    assert int(lab.sum()) == 0 and O.sample_counts(0, len(lab), B, frac) == (0, len(g["out_classes2"]))
