@@ -342,9 +342,9 @@ def main():
         if train and not args.no_graph:
             try:
                 head.use_device_dropout_counter(True)
-                # world > 1: the NCCL all-reduce stays outside the graph (captured, it ran 2.5 % faster at N = 2 in round 1
-                # but the processes then hung in teardown)
-                in_graph = world == 1
+                # world > 1: the NCCL gradient all-reduce is captured too (on the communication stream, behind the
+                # parameter-gradient streams and under res5's backward); BENCH_GRAPH_ALLREDUCE=0 keeps it and SGD outside
+                in_graph = world == 1 or os.environ.get("BENCH_GRAPH_ALLREDUCE", "1") == "1"
                 graph = train_ops.GraphedStep(lambda d: step(d, exchange=in_graph), resident)
                 graph_note = "whole step" if in_graph else "forward + backward (all-reduce and SGD outside)"
             except Exception as e:  # noqa: BLE001
@@ -594,6 +594,12 @@ def main():
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line))
     if world > 1:
+        # drop the captured graph (it may hold NCCL work) before the communicator goes away
+        graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
