@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-step table (markdown).
-usage: tools_launch_summary.py gpurun_out/launches.csv > profiles/rNN_launches.md"""
+usage: launch_summary.py gpurun_out/launches.csv > profiles/rNN_launches.md"""
 import csv, re, sys
 rows = []
 with open(sys.argv[1]) as f:
