@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Hottest CUDA source lines of one kernel from an .ncu-rep (compile with -lineinfo).
-usage: tools_ncu_src.py <report> <kernel-regex> [top]"""
+usage: ncu_src.py <report> <kernel-regex> [top]"""
 import csv, subprocess, sys
 rep, rx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
