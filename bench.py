@@ -533,8 +533,8 @@ def main():
         # DRAM traffic per launch from the committed `ncu --set full` capture of exactly this configuration
         # (profiles/r01_ncu_full_step_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: not captured
         default_cfg = train and (B, P, K, bin_step) == (8, 512, 20, 2)
-        roi_traffic = 41548288 + 108157952 if default_cfg else None
-        gemm_traffic = 656233472 if default_cfg else None           # sum over the step's 26 GEMM launches
+        roi_traffic = 143825920 if default_cfg else None
+        gemm_traffic = 652731904 if default_cfg else None           # sum over the step's 26 GEMM launches
         roi_roof = {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<%d,%d,%d> (bf16, rank 0)" % (nb, nb, bin_step),
                     "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": roi_traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
