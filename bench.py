@@ -399,14 +399,14 @@ def main():
             dist.barrier()
         per_step = [evs[i][0].elapsed_time(evs[i][n_marks - 1]) for i in range(args.steps)]
         if graph is not None:        # stage marks cannot sit inside the graph: a few eager steps give the stage split
-            for _ in range(3):           # the eager path's allocations settle again after the capture
+            for _ in range(6):           # the eager path's allocations settle again after the capture
                 step(resident)
             evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(5)]
             for i in range(5):
                 flush.fill_(i)
                 step(resident, evs[i])
             torch.cuda.synchronize()
-        stage_ms = [float(np.mean([e[s].elapsed_time(e[s + 1]) for e in evs])) for s in range(n_marks - 1)]
+        stage_ms = [float(np.median([e[s].elapsed_time(e[s + 1]) for e in evs])) for s in range(n_marks - 1)]
         total_ms = torch.tensor([float(sum(per_step))], device=dev)
         if world > 1:
             dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)

@@ -185,6 +185,86 @@ layernorm_relu_dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dzd, const f
   }
 }
 
+// Register-resident variant for d = 128 V: a lane holds V float4 of its row, so y, y2 and dzd are read once (16-byte / 8-byte
+// accesses, all of a row's loads in flight together) instead of four strided passes over the row.
+template <int V>
+__global__ void __launch_bounds__(256)
+layernorm_relu_dropout_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dzd, const float* __restrict__ y,
+                                      const float* __restrict__ y2, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, float p, unsigned long long seed,
+                                      const unsigned long long* __restrict__ salt, float* __restrict__ du_f32,
+                                      __nv_bfloat16* __restrict__ du_bf16, float* __restrict__ stats, int R) {
+  constexpr int d = 128 * V;
+  if (salt) seed += *salt;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const uint32_t th = dropout_thresh(p);
+  const float dscale = p > 0.f ? (p < 1.f ? 1.f / (1.f - p) : 0.f) : 1.f;
+  const float4* a = reinterpret_cast<const float4*>(y + (size_t)row * d);
+  const float4* b = reinterpret_cast<const float4*>(y2 + (size_t)row * d);
+  const uint2* gz = reinterpret_cast<const uint2*>(dzd + (size_t)row * d);
+  float4 u[V];
+  uint2 z[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 pa = __ldcs(a + i * 32 + lane), pb = __ldcs(b + i * 32 + lane);
+    z[i] = __ldcs(gz + i * 32 + lane);
+    u[i] = make_float4(pa.x + pb.x, pa.y + pb.y, pa.z + pb.z, pa.w + pb.w);
+    s += (u[i].x + u[i].y) + (u[i].z + u[i].w);
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float dx = u[i].x - mean, dy = u[i].y - mean, dz = u[i].z - mean, dw = u[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+  float m1 = 0.f, m2 = 0.f;
+  float4 dxh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + col)), b4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float xv[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+    const float zv[4] = {__uint_as_float(z[i].x << 16), __uint_as_float(z[i].x & 0xffff0000u), __uint_as_float(z[i].y << 16),
+                         __uint_as_float(z[i].y & 0xffff0000u)};
+    float dv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (xv[k] - mean) * rstd;
+      float dz = zv[k];
+      if (p > 0.f) dz = dropout_keep(seed, (size_t)row * d + col + k, th) ? dz * dscale : 0.f;
+      if (!(xh * gv[k] + bv[k] > 0.f)) dz = 0.f;
+      dv[k] = dz * gv[k];
+      m1 += dv[k];
+      m2 += dv[k] * xh;
+      xv[k] = xh;
+    }
+    u[i] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    dxh[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+  }
+  m1 = warp_sum(m1) / (float)d;
+  m2 = warp_sum(m2) / (float)d;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    float4 o;
+    o.x = rstd * (dxh[i].x - m1 - u[i].x * m2); o.y = rstd * (dxh[i].y - m1 - u[i].y * m2);
+    o.z = rstd * (dxh[i].z - m1 - u[i].z * m2); o.w = rstd * (dxh[i].w - m1 - u[i].w * m2);
+    if (du_f32) *reinterpret_cast<float4*>(du_f32 + (size_t)row * d + col) = o;
+    if (du_bf16) {
+      uint2 w;
+      w.x = t_pack(o.x, o.y); w.y = t_pack(o.z, o.w);
+      *reinterpret_cast<uint2*>(du_bf16 + (size_t)row * d + col) = w;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 layernorm_param_grad_partial_kernel(const __nv_bfloat16* __restrict__ dzd, const float* __restrict__ y,
                                     const float* __restrict__ y2, const float* __restrict__ gamma,
@@ -516,8 +596,15 @@ extern "C" int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float
   float* stats = (float*)workspace;
   float* pg = (float*)((unsigned char*)workspace + align_up((size_t)R * 2 * 4, 256));
   float* pb = pg + (size_t)kColBlocks * d;
-  layernorm_relu_dropout_bwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, eps, p,
-                                                                    seed, seed_salt, du_f32, (__nv_bfloat16*)du_bf16, stats, R, d);
+  const bool aligned = ((((uintptr_t)dzd_bf16 | (uintptr_t)du_bf16) & 7) | (((uintptr_t)y | (uintptr_t)y2 | (uintptr_t)gamma |
+                                                                             (uintptr_t)beta | (uintptr_t)du_f32) & 15)) == 0;
+  if (d == 2048 && aligned)
+    layernorm_relu_dropout_bwd_vec_kernel<16><<<ceil_div(R, 8), 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta,
+                                                                              eps, p, seed, seed_salt, du_f32,
+                                                                              (__nv_bfloat16*)du_bf16, stats, R);
+  else
+    layernorm_relu_dropout_bwd_kernel<<<ceil_div(R, 8), 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, eps, p,
+                                                                      seed, seed_salt, du_f32, (__nv_bfloat16*)du_bf16, stats, R, d);
   if (dgamma || dbeta) {
     dim3 grid(ceil_div(d, 256), kColBlocks);
     layernorm_param_grad_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, stats, p,
