@@ -295,8 +295,17 @@ class _FusedHeadTrain(torch.autograd.Function):
         logits = gemm_bf16(zd, W["Wc"], bc)
         deltas = gemm_bf16(xb, W["Wb"], bb)
         losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
+        # K-contiguous transposes of the weights, the B operands of the backward's dX = dY W products: they depend on
+        # nothing but the weights, so they run now on the side stream, under the forward chain / losses, instead of on the
+        # backward's critical path
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            WT = [transpose_bf16(W[k]) for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")]
+            ctx.wt_ready = torch.cuda.Event()
+            ctx.wt_ready.record(side)
         ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
+                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")], *WT)
         ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
         ctx.salt = salt
         # Deferred weight gradients (FlatSGD(direct_grads=True)): every parameter carries a view of the optimizer's flat
@@ -312,7 +321,8 @@ class _FusedHeadTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_losses, _g_logits):
         (x, xcat, p1, p2, attn, vp, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors
+         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq, W1T, W2T, W3T, Wf1T, Wf2T, WcT, WbT, kqT) = ctx.saved_tensors
+        torch.cuda.current_stream().wait_event(ctx.wt_ready)
         K, box_w, l1_beta, drop_p, seed, want_attn = ctx.meta
         R, d = x.shape
         h = d // 2
@@ -367,8 +377,8 @@ class _FusedHeadTrain(torch.autograd.Function):
             out["dWb"] = gemm_ex(transpose_bf16(ddeltas)[:C4], out["xcatT"][d:], out=sk["Wb"])
             out["dbb"] = colsum(ddeltas[:, :C4], out=sk["bb"])
         fork(side_c1, dlogits, ddeltas)
-        dzd = gemm_ex(dlogits, _wT(Wc, C1p), out_dtype=torch.bfloat16)
-        dx = gemm_ex(ddeltas, _wT(Wb, C4p))                                        # first producer of dL/dx (fp32)
+        dzd = gemm_ex(dlogits, WcT, out_dtype=torch.bfloat16)
+        dx = gemm_ex(ddeltas, WbT)                                        # first producer of dL/dx (fp32)
         # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
         du = torch.empty((R, d), dtype=torch.float32, device=dev)
         dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
@@ -384,20 +394,19 @@ class _FusedHeadTrain(torch.autograd.Function):
             out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"], out=sk["Wf2"])
             out["dbf2"] = colsum(dub, out=sk["bf2"])   # the bf16 copy: `du` is overwritten in place by the dy GEMM below
         fork(side_ffn2, dub)
-        dhdn = gemm_ex(dub, _wT(Wf2, d), out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
+        dhdn = gemm_ex(dub, Wf2T, out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
 
         def side_ffn1():
             out["dWf1"] = gemm_ex(transpose_bf16(dhdn), out["ybT"], out=sk["Wf1"])
             out["dbf1"] = colsum(dhdn, out=sk["bf1"])
         fork(side_ffn1, dhdn)
         dyb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-        gemm_ex(dhdn, _wT(Wf1, Wf1.shape[0]), out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
+        gemm_ex(dhdn, Wf1T, out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
         # ---- linear3: y = [o1 | o2 | xb] W3^T + b3 -----------------------------------------------------------
         def side_l3():
             out["dW3"] = gemm_ex(transpose_bf16(dyb), out["xcatT"], out=sk["W3"])
             out["db3"] = colsum(du, out=sk["b3"])      # du now holds dy (fp32)
         fork(side_l3, dyb, du)
-        W3T = _wT(W3, d)                                                           # (2d, d)
         do12 = gemm_ex(dyb, W3T[:d], out_dtype=torch.bfloat16, mask=xcat[:, :d])   # [do1 | do2], ReLU backward fused
         gemm_ex(dyb, W3T[d:], out=dx, accumulate=True)
         # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
@@ -408,8 +417,8 @@ class _FusedHeadTrain(torch.autograd.Function):
             out["db1"] = colsum(do12[:, :h], out=sk["b1"])
             out["db2"] = colsum(do12[:, h:], out=sk["b2"])
         fork(side_l12, do12)
-        dp1 = gemm_ex(do12[:, :h], _wT(W1, h), out_dtype=torch.bfloat16)
-        dp2 = gemm_ex(do12[:, h:], _wT(W2, h), out_dtype=torch.bfloat16)
+        dp1 = gemm_ex(do12[:, :h], W1T, out_dtype=torch.bfloat16)
+        dp2 = gemm_ex(do12[:, h:], W2T, out_dtype=torch.bfloat16)
         # ---- A3 core: P1 = O * x, P2 = x - O, O = softmax(S) Vp ------------------------------------------------
         dO = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         dS = torch.empty((R, Lp), dtype=torch.bfloat16, device=dev)
@@ -423,7 +432,7 @@ class _FusedHeadTrain(torch.autograd.Function):
             out["dkq"] = gemm_ex(transpose_bf16(dS), transpose_bf16(xcat[:, d:]))[:L]
         fork(side_att, attn, dO, dS, xcat, stream=text)
         # ---- scores: S = xb Kq^T ----------------------------------------------------------------------------------
-        gemm_ex(dS, _wT(kq, Lp), out=dx, accumulate=True)
+        gemm_ex(dS, kqT, out=dx, accumulate=True)
         done = torch.cuda.Event()
         done.record(side)
         tdone = torch.cuda.Event()
@@ -456,14 +465,6 @@ def _side_stream(dev):
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
-
-
-def _wT(w, k_pad):
-    """W (N, K) bf16 -> W^T as a K-contiguous GEMM operand: (K, rup8(N)) zero padded; k_pad is the contraction size the
-    consumer uses (== rup8(N))."""
-    t = transpose_bf16(w)
-    assert t.shape[1] == k_pad, (t.shape, k_pad)
-    return t
 
 
 def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed,
