@@ -616,6 +616,29 @@ extern "C" int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float
   return B200_OK;
 }
 
+// dgamma / dbeta of the same backward, from the row statistics the call above left at the head of its workspace: a
+// separate entry point so that a caller can keep it off the critical path (side stream) — only the optimizer needs it.
+extern "C" int b200_layernorm_param_grads(const void* dzd_bf16, const float* y, const float* y2, const float* gamma,
+                                          const float* beta, float p, unsigned long long seed,
+                                          const unsigned long long* seed_salt, float* dgamma, float* dbeta, int R, int d,
+                                          void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(dzd_bf16 && y && y2 && gamma && beta && (dgamma || dbeta), "layernorm_param_grads: null tensor");
+  B200_CHECK_ARG(R >= 0 && d > 0, "layernorm_param_grads: bad shape");
+  B200_CHECK_ARG(workspace && workspace_bytes >= b200_layernorm_bwd_workspace_bytes(R, d), "layernorm_param_grads: workspace too small");
+  if (R == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* stats = (const float*)workspace;
+  float* pg = (float*)((unsigned char*)workspace + align_up((size_t)R * 2 * 4, 256));
+  float* pb = pg + (size_t)kColBlocks * d;
+  dim3 grid(ceil_div(d, 256), kColBlocks);
+  layernorm_param_grad_partial_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)dzd_bf16, y, y2, gamma, beta, stats, p, seed,
+                                                            seed_salt, pg, pb, R, d);
+  if (dgamma) colsum_final_kernel<<<ceil_div(d, 256), 256, 0, st>>>(pg, kColBlocks, d, dgamma, 0);
+  if (dbeta) colsum_final_kernel<<<ceil_div(d, 256), 256, 0, st>>>(pb, kColBlocks, d, dbeta, 0);
+  B200_CUDA_LAUNCH_CHECK("layernorm_param_grads");
+  return B200_OK;
+}
+
 extern "C" int b200_text_attention_bwd(const void* dp1, const void* dp2, int ldp, const float* x, const float* attn,
                                        const float* vp, const float* dattn_ext, float* dx, int accumulate_dx, void* d_o,
                                        void* ds, int ldds, int R, int d, int L, b200_stream_t stream) {

@@ -387,8 +387,14 @@ class _FusedHeadTrain(torch.autograd.Function):
         nb = _lib.lib().b200_layernorm_bwd_workspace_bytes(R, d)
         ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         _lib.call("b200_layernorm_relu_dropout_bwd", dzd.data_ptr(), y.data_ptr(), y2.data_ptr(), gam.data_ptr(),
-                  bet.data_ptr(), 1e-5, float(drop_p), int(seed), _ptr(ctx.salt), du.data_ptr(), dub.data_ptr(), dgamma.data_ptr(),
-                  dbeta.data_ptr(), R, d, ws.data_ptr(), nb, st)
+                  bet.data_ptr(), 1e-5, float(drop_p), int(seed), _ptr(ctx.salt), du.data_ptr(), dub.data_ptr(), 0, 0, R, d,
+                  ws.data_ptr(), nb, st, launches=1)
+
+        def side_ln():       # dgamma / dbeta from the row statistics left in `ws`: only the optimizer needs them
+            _lib.call("b200_layernorm_param_grads", dzd.data_ptr(), y.data_ptr(), y2.data_ptr(), gam.data_ptr(), bet.data_ptr(),
+                      float(drop_p), int(seed), _ptr(ctx.salt), dgamma.data_ptr(), dbeta.data_ptr(), R, d, ws.data_ptr(), nb,
+                      _stream())
+        fork(side_ln, dzd, y, y2, gam, bet, ws)
         # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
         def side_ffn2():
             out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"], out=sk["Wf2"])

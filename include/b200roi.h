@@ -199,6 +199,12 @@ B200_API int b200_layernorm_relu_dropout_bwd(const void* dzd_bf16, const float* 
                                     const unsigned long long* seed_salt, float* du_f32, void* du_bf16, float* dgamma,
                                     float* dbeta, int R, int d, void* workspace, size_t workspace_bytes,
                                     b200_stream_t stream);
+/* dgamma / dbeta of the LayerNorm backward above, computed from the row statistics that call left in `workspace` (same
+ * buffer, same arguments): separate so that it can run off the critical path, on another stream. */
+B200_API int b200_layernorm_param_grads(const void* dzd_bf16, const float* y, const float* y2, const float* gamma,
+                               const float* beta, float p, unsigned long long seed, const unsigned long long* seed_salt,
+                               float* dgamma, float* dbeta, int R, int d, void* workspace, size_t workspace_bytes,
+                               b200_stream_t stream);
 /* backward of b200_text_attention (attentive_modules.py:45-55,166,170): given dP1, dP2 (bf16, row stride ldp) and
  * an optional external gradient on the attention probabilities (loss_attentive, roi_heads.py:1079-1081) computes
  *   dx (R,d) fp32 (+= when accumulate_dx), dO (R,d) bf16 (for dVp = attn^T dO through the GEMM),
