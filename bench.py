@@ -228,7 +228,7 @@ def main():
         return main_reference(args, rank, world)
 
     import torch.distributed as dist
-    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, train_ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, ops, train_ops
     from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
 
@@ -438,6 +438,36 @@ def main():
                 prof[name]["tflops"] = fl / (ms * 1e-3) / 1e12
                 prof[name]["flop_per_step"] = fl
         _lib.PROFILE = None
+        # the stand-alone ROIAlign operator (all 49 bins, what torchvision.ops.roi_align computes) on the same maps / ROIs, and
+        # its backward (lists planned ahead, as in the step), L2 flushed before every launch
+        roi_op = {}
+        with torch.enable_grad():
+            fmap = resident["feat"].to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            rois_l = [resident["boxes"][i] for i in range(B)]
+            rr, oo = ops.boxes_to_rois(rois_l)
+            tf, tb = [], []
+            for i in range(5):
+                flush.fill_(i)
+                e0_, e1_, e2_, e3_ = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+                e0_.record()
+                pooled_full = ops.roi_align(fmap, rr, 7, 1.0 / 16, 0, True, channels_last_out=True, roi_batch_offsets=oo, bin_step=1)
+                e1_.record()
+                gfull = torch.ones_like(pooled_full)
+                flush.fill_(i + 1)
+                e2_.record()
+                pooled_full.backward(gfull)
+                e3_.record()
+                torch.cuda.synchronize()
+                fmap.grad = None
+                if i >= 2:
+                    tf.append(e0_.elapsed_time(e1_))
+                    tb.append(e2_.elapsed_time(e3_))
+            full_bytes = B * C4 * HF * WF * 2 + B * P * 20 + B * P * C4 * 49 * 2
+            roi_op = {"bins": "7x7", "algorithmic_bytes": full_bytes,
+                      "fwd_ms": float(np.median(tf)), "fwd_gbs": full_bytes / float(np.median(tf)) / 1e6,
+                      "bwd_ms": float(np.median(tb)), "bwd_gbs": full_bytes / float(np.median(tb)) / 1e6,
+                      "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
+            del pooled_full, gfull, fmap
         gemm_alone = {"ms": 0.0, "flop": 0.0, "calls": len(gemm_cases)}
         for (M_, N_, K_, obf, d2_, relu_, acc_, msk_, bias_) in gemm_cases:
             ld = (N_ + 7) // 8 * 8
@@ -540,7 +570,8 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
                     "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
-                    "timing": "CUDA events recorded around the entry point on the launching stream, mean over %d profiled steps" % prof_steps}
+                    "timing": "CUDA events recorded around the entry point on the launching stream, mean over %d profiled steps" % prof_steps,
+                    "standalone_op": dict(roi_op, fwd_frac=roi_op["fwd_gbs"] / hbm_peak, bwd_frac=roi_op["bwd_gbs"] / hbm_peak) if roi_op else None}
         # dominant hand-written kernel of the step = the tcgen05 GEMM (all launches of the step together)
         gem = {"ms": 0.0, "flop": 0.0, "calls": 0.0}
         for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex"):
