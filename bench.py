@@ -413,7 +413,7 @@ def main():
         total_ms = float(total_ms)
         # ---- per-entry-point profile (separate pass: an event pair around every C-ABI call) ---------------------
         _lib.PROFILE = {}
-        prof_steps = 3
+        prof_steps = 5
         for i in range(prof_steps):
             flush.fill_(i)
             step(resident)
@@ -431,7 +431,8 @@ def main():
         gemm_cases = [t[1] for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex") for _, _, t in _lib.PROFILE.get(name, [])[: len(_lib.PROFILE.get(name, [])) // prof_steps]
                       if isinstance(t, tuple)]
         for name, rows in _lib.PROFILE.items():
-            ms = sum(a.elapsed_time(b) for a, b, _ in rows) / prof_steps
+            per = max(len(rows) // prof_steps, 1)            # the same calls every step: median over the profiled steps
+            ms = float(np.median([sum(a.elapsed_time(b) for a, b, _ in rows[i * per:(i + 1) * per]) for i in range(prof_steps)]))
             fl = sum(fl_of(t) for _, _, t in rows if t) / prof_steps
             prof[name] = {"ms_per_step": ms, "calls_per_step": len(rows) / prof_steps}
             if fl:
@@ -570,7 +571,7 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
                     "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
-                    "timing": "CUDA events recorded around the entry point on the launching stream, mean over %d profiled steps" % prof_steps,
+                    "timing": "CUDA events recorded around the entry point on the launching stream, median over %d profiled steps" % prof_steps,
                     "standalone_op": dict(roi_op, fwd_frac=roi_op["fwd_gbs"] / hbm_peak, bwd_frac=roi_op["bwd_gbs"] / hbm_peak) if roi_op else None}
         # dominant hand-written kernel of the step = the tcgen05 GEMM (all launches of the step together)
         gem = {"ms": 0.0, "flop": 0.0, "calls": 0.0}
@@ -585,7 +586,7 @@ def main():
                      "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": gemm_traffic,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
                      "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gem["ms"],
-                     "timing": "CUDA events recorded around every GEMM entry-point call on the launching stream, summed per step, mean over "
+                     "timing": "CUDA events recorded around every GEMM entry-point call on the launching stream, summed per step, median over "
                                "%d profiled eager steps (the weight-gradient GEMMs of the fine-tune step share the SMs with res5's kernels there)" % prof_steps,
                      "launched_alone": {"achieved": alone_tf, "ms_per_step": gemm_alone["ms"],
                                         "note": "every GEMM shape / epilogue of the step re-issued alone with a synchronize between launches: "
