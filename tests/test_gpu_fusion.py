@@ -205,3 +205,18 @@ def test_cosine_logits_option(golden):
     got = ops.gemm_bf16(ops.l2_normalize_rows(x), ops.l2_normalize_rows(T, scale=tau))
     want = O.sim_matrix(x.cpu(), T.cpu(), tau=tau)
     assert rel_err(got.cpu(), want) < 2e-2
+
+
+def test_gemm_res5_sized_problem_with_mask():
+    """A res5-sized product (65536 rows: 4096 ROIs x 16 pixels; 512 tiles of 128 x 256 on 148 persistent CTAs) with the
+    ReLU-backward mask epilogue, against torch's bf16 matmul of the same operands (fp32 accumulate both; bf16 output)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    M, N, K = 65536, 2048, 512
+    a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda", generator=gen) * 0.05).to(torch.bfloat16)
+    mask = torch.randn(M, N, device="cuda", generator=gen).to(torch.bfloat16)
+    out = train_ops.gemm_ex(a, b, out_dtype=torch.bfloat16, mask=mask)
+    ref = torch.where(mask > 0, (a @ b.t()).float(), torch.zeros((), device="cuda"))
+    assert rel_err(out.float(), ref) < 4e-3
+    assert float(out[mask <= 0].abs().max()) == 0.0

@@ -108,3 +108,28 @@ def test_head_api_uses_the_kernel(golden):
         ref_c = T(g["out_classes%d" % i])
         assert len(o) == len(ref_c) and int((o.gt_classes < K).sum()) == int((ref_c < K).sum())
         assert o.gt_boxes.tensor.shape == (len(ref_c), 4) and o.proposal_boxes.tensor.shape == (len(ref_c), 4)
+
+
+def test_limits_empty_image_and_ties():
+    """Maximum sizes (4096 proposals, 256 ground-truth boxes per image), an image without proposals, duplicate ground-truth
+    boxes (exact IoU ties resolve to the first index, as torch.max does on the CPU), and the refusal beyond the limits."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals
+    gen = torch.Generator().manual_seed(3)
+    big, objs = synth_proposals(4096, 600, 800, gen, n_obj=128)
+    gts = torch.cat([objs, objs], 0)                                   # 256 boxes, every one duplicated -> ties
+    cls = torch.arange(256) % 20
+    props = [big.cuda(), big[:0].cuda(), big[:700].cuda()]
+    gtb = [gts.cuda(), gts[:3].cuda(), gts[:0].cuda()]
+    gtc = [cls.cuda(), cls[:3].cuda(), cls[:0].cuda()]
+    r = ops.label_and_sample_proposals(props, gtb, gtc, 20, 0.5, 512, 0.25, seed=1, want_labels=True)
+    idx, lab, _ = O.label_proposals(big, gts)
+    assert int(idx.max()) < 128                                         # first of the two identical boxes
+    assert torch.equal(r["matched_idx"][:4096].cpu().long(), idx) and torch.equal(r["matched_label"][:4096].cpu().long(), lab)
+    counts = r["counts"].cpu().tolist()
+    n_fg = int(lab.sum())
+    assert counts[0] == [min(128, n_fg), min(128, n_fg) + min(512 - min(128, n_fg), 4096 - n_fg)]
+    assert counts[1] == [0, 0] and bool((r["sampled_idx"][1] == -1).all())
+    assert counts[2] == [0, 512] and bool((r["classes"][2] == 20).all())
+    with pytest.raises(_lib.B200Error):
+        ops.label_and_sample_proposals([torch.zeros(4097, 4).cuda()], [gts[:1].cuda()], [cls[:1].cuda()], 20)

@@ -267,3 +267,33 @@ def test_empty_and_errors():
         ops.roi_align(torch.zeros(1, 6, 5, 5, device="cuda"), torch.zeros(1, 5, device="cuda"), 7, 1 / 16)  # C % 4
     with pytest.raises(_lib.B200Error):
         ops.roi_align(torch.zeros(1, 8, 5, 5), torch.zeros(1, 5), 7, 1 / 16)                                 # CPU tensor
+
+
+def test_bwd_bf16_large_map_and_table_less_rois():
+    """800 x 1333-pixel images (50 x 84 map): ROIs wider than 8 samples per bin leave the tabulated path (the list builder's
+    per-sample fallback), mixed with ordinary ones; bf16 bar against the CPU oracle, bitwise run to run."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    N, C, H, W = 2, 64, 50, 84
+    x = torch.relu(torch.randn(N, C, H, W, generator=gen)).to(torch.bfloat16)
+    boxes = []
+    for n in range(N):
+        b = synth_proposals(40, 800, 1333, gen)[0]
+        b[0] = torch.tensor([3.0, 5.0, 1330.0, 795.0])            # whole image: 12 samples per bin horizontally
+        b[1] = torch.tensor([100.0, 20.0, 1300.0, 400.0])
+        boxes.append(b)
+    rois = O.boxes_to_rois(boxes)
+    offs = torch.tensor([0, 40, 80], dtype=torch.int32)
+    g = torch.randn(80, C, 7, 7, generator=gen).to(torch.bfloat16)
+    ref = O.roi_align_bwd(g.float(), rois, x.shape, 1 / 16, 0, True)
+
+    def run():
+        xin = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+        out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+        return xin.grad
+    got = run()
+    gf = got.float().cpu().contiguous()
+    assert float((gf - ref).norm() / ref.norm()) < 8e-3
+    torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    assert torch.equal(got, run())
