@@ -17,40 +17,11 @@
 // All comparisons that decide membership (score > thresh, iou > thresh) use round-to-nearest fp32 ops in
 // the reference's order with FMA contraction disabled, so keep indices and counts are bit-exact.
 #include "common.cuh"
+#include "sort_scan.cuh"
 
 namespace b200 {
 
 constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), detectron2 _DEFAULT_SCALE_CLAMP
-
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp /*[33]*/, int* total) {
-  // blockDim.x == 1024.  returns exclusive prefix of v over threads; *total = block sum
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int w = s_warp[lane];
-    int winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += t;
-    }
-    s_warp[lane] = winc - w;
-    if (lane == 31) s_warp[32] = winc;
-  }
-  __syncthreads();
-  const int res = s_warp[warp] + inc - v;
-  *total = s_warp[32];
-  __syncthreads();
-  return res;
-}
 
 // softmax statistics of one row (sequential over the K+1 columns: a thread owns a row)
 __device__ __forceinline__ void row_stats(const float* __restrict__ row, int ncol, float* mx_out, float* sum_out) {
@@ -141,13 +112,6 @@ softmax_decode_compact_kernel(const float* __restrict__ scores_in, int input_is_
 // ------------------------------------------------------------------------------------------------
 // NMS
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t desc_key(float s) {
-  // monotone map float -> uint32 such that larger float => SMALLER key (ascending sort == descending score)
-  uint32_t u = __float_as_uint(s);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return ~u;
-}
-
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
   // torchvision nms kernel: inter / (areaA + areaB - inter) > thr, widths clamped at 0
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
@@ -160,28 +124,6 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
   const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
-}
-
-// block-wide bitonic sort (ascending) of n2 (power of two) 64-bit keys in shared or global memory
-__device__ void bitonic_sort_u64(unsigned long long* keys, int n2) {
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-        const int i = ((t / j) * (j << 1)) + (t % j);
-        const int l = i + j;
-        const bool asc = (i & k) == 0;
-        const unsigned long long a = keys[i], b = keys[l];
-        if ((a > b) == asc) { keys[i] = b; keys[l] = a; }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-__device__ __forceinline__ int next_pow2(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
 }
 
 struct NmsWorkspace {
@@ -261,8 +203,14 @@ nms_prepare_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ 
 
 constexpr int kNmsThreads = 256;
 constexpr int kNmsSmemBoxes = 4096;  // per (class, image) handled fully in shared memory; larger -> global path
+// PRESORTED variant (RPN proposal selection, rpn_select.cu): the candidates of a class already arrive in
+// (score desc, index asc) order, so no keys are built or sorted and shared memory holds boxes + bitmap only:
+// 12288 boxes x 16 B + 1.5 KB = 198 KB, one 1024-thread CTA per (level, image).
+constexpr int kNmsPresortedBoxes = 12288;
+constexpr int kNmsPresortedThreads = 1024;
 
-__global__ void __launch_bounds__(kNmsThreads)
+template <int THREADS, bool PRESORTED>
+__global__ void __launch_bounds__(THREADS)
 nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                  const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
                  const float* __restrict__ max1, const int32_t* __restrict__ class_start,
@@ -285,20 +233,25 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     return;
   }
   const int m2 = next_pow2(m);
-  const bool in_smem = m <= kNmsSmemBoxes;
+  constexpr int kCap = PRESORTED ? kNmsPresortedBoxes : kNmsSmemBoxes;
+  const bool in_smem = m <= kCap;
   unsigned long long* gslice = scratch + 4 * (size_t)(base + cs);  // 4*m u64 per class slice (host sizes scratch 4x)
-  unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(s_raw) : gslice;
-  float4* sbox = reinterpret_cast<float4*>(s_raw + (size_t)kNmsSmemBoxes * 8);
-  uint32_t* removed = reinterpret_cast<uint32_t*>(s_raw + (size_t)kNmsSmemBoxes * 24);
+  unsigned long long* keys = PRESORTED ? nullptr : (in_smem ? reinterpret_cast<unsigned long long*>(s_raw) : gslice);
+  float4* sbox = reinterpret_cast<float4*>(s_raw + (PRESORTED ? 0 : (size_t)kCap * 8));
+  uint32_t* removed = reinterpret_cast<uint32_t*>(s_raw + (size_t)kCap * (PRESORTED ? 16 : 24));
 
-  // (score desc, position-in-class asc); positions are ascending candidate index (stable counting sort)
-  for (int p = threadIdx.x; p < m2; p += blockDim.x)
-    keys[p] = p < m ? (((unsigned long long)desc_key(scores[base + ord[p]]) << 32) | (uint32_t)p) : ~0ull;
-  __syncthreads();
-  bitonic_sort_u64(keys, m2);
+  if (!PRESORTED) {
+    // (score desc, position-in-class asc); positions are ascending candidate index (stable counting sort)
+    for (int p = threadIdx.x; p < m2; p += blockDim.x)
+      keys[p] = p < m ? (((unsigned long long)desc_key(scores[base + ord[p]]) << 32) | (uint32_t)p) : ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(keys, m2);
+  }
+  // position in the class slice of the j-th box in (score desc, index asc) order
+  auto pos_of = [&](int j) -> int { return PRESORTED ? j : (int)(keys[j] & 0xffffffffu); };
 
   auto load_box = [&](int j) -> float4 {
-    const int cand = ord[(int)(keys[j] & 0xffffffffu)];
+    const int cand = ord[pos_of(j)];
     float4 b = *reinterpret_cast<const float4*>(boxes + 4 * (size_t)(base + cand));
     b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
     return b;
@@ -320,7 +273,7 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     const int nb = min(64, m - b0);
     // diagonal 64x64 block, all 8 warps: warp -> row t, lane -> columns (lane, lane+32); ballots assemble the
     // 64-bit row mask "boxes later in the block that box t suppresses"
-    for (int t = warp; t < 64; t += kNmsThreads / 32) {
+    for (int t = warp; t < 64; t += THREADS / 32) {
       unsigned m0 = 0u, m1 = 0u;
       if (t < nb) {
         const float4 a = get_box(b0 + t);
@@ -359,8 +312,10 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     nkept += __popcll(keep);
     if ((int)threadIdx.x < nb) {
       const int j = b0 + threadIdx.x;
-      const uint32_t cand = (uint32_t)ord[(int)(keys[j] & 0xffffffffu)];
-      kept_out[j] = ((keep >> threadIdx.x) & 1ull) ? ((keys[j] & 0xffffffff00000000ull) | cand) : ~0ull;
+      const uint32_t cand = (uint32_t)ord[pos_of(j)];
+      const unsigned long long hi = PRESORTED ? ((unsigned long long)desc_key(scores[base + cand]) << 32)
+                                              : (keys[j] & 0xffffffff00000000ull);
+      kept_out[j] = ((keep >> threadIdx.x) & 1ull) ? (hi | cand) : ~0ull;
     }
     if (nkept >= max_keep) {
       for (int j = b0 + 64 + threadIdx.x; j < m; j += blockDim.x) kept_out[j] = ~0ull;
@@ -446,6 +401,55 @@ __global__ void gather_detections_kernel(const float* __restrict__ cand_boxes, c
   }
 }
 
+// detectron2 0.3 detector_postprocess (called from defrcn/modeling/meta_arch/rcnn.py:69-73) on the padded
+// detection tensors: scale to the requested output resolution, clip, drop empty boxes (ordered, in place).
+__global__ void __launch_bounds__(1024)
+detector_postprocess_kernel(float* __restrict__ boxes, float* __restrict__ scores, int64_t* __restrict__ classes,
+                            int64_t* __restrict__ roi_inds, int32_t* __restrict__ counts,
+                            const float* __restrict__ scale_xy, const float* __restrict__ out_hw, int max_keep) {
+  __shared__ int s_warp[33];
+  const int img = blockIdx.x;
+  const int n = min(counts[img], max_keep);
+  const float sx = scale_xy[2 * img], sy = scale_xy[2 * img + 1];
+  const float oh = out_hw[2 * img], ow = out_hw[2 * img + 1];
+  const size_t base = (size_t)img * max_keep;
+  int running = 0;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int64_t c = -1, r = -1;
+    int keepf = 0;
+    if (i < n) {
+      b = *reinterpret_cast<const float4*>(boxes + 4 * (base + i));
+      sc = scores[base + i];
+      if (classes) c = classes[base + i];
+      if (roi_inds) r = roi_inds[base + i];
+      b.x = fminf(fmaxf(__fmul_rn(b.x, sx), 0.f), ow); b.y = fminf(fmaxf(__fmul_rn(b.y, sy), 0.f), oh);
+      b.z = fminf(fmaxf(__fmul_rn(b.z, sx), 0.f), ow); b.w = fminf(fmaxf(__fmul_rn(b.w, sy), 0.f), oh);
+      keepf = (__fsub_rn(b.z, b.x) > 0.f) && (__fsub_rn(b.w, b.y) > 0.f);
+    }
+    int total;
+    const int ex = block_exclusive_scan_1024(keepf, s_warp, &total);   // every read of this tile precedes its writes
+    if (keepf) {
+      const size_t o = base + running + ex;
+      *reinterpret_cast<float4*>(boxes + 4 * o) = b;
+      scores[o] = sc;
+      if (classes) classes[o] = c;
+      if (roi_inds) roi_inds[o] = r;
+    }
+    running += total;
+  }
+  __syncthreads();
+  for (int i = running + threadIdx.x; i < n; i += 1024) {
+    *reinterpret_cast<float4*>(boxes + 4 * (base + i)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    scores[base + i] = 0.f;
+    if (classes) classes[base + i] = -1;
+    if (roi_inds) roi_inds[base + i] = -1;
+  }
+  if (threadIdx.x == 0) counts[img] = running;
+}
+
 static NmsWorkspace carve(void* ws, int N, int total_capacity, int num_classes) {
   NmsWorkspace w;
   unsigned char* p = (unsigned char*)ws;
@@ -485,6 +489,57 @@ extern "C" size_t b200_batched_nms_workspace_bytes(int N, int total_capacity, in
          align_up((size_t)N * 4, 256);
 }
 
+namespace b200 {
+// shared by b200_batched_nms and b200_rpn_select_proposals (rpn_select.cu); `presorted` = within every class the
+// candidates already are in (score desc, index asc) order
+int run_batched_nms(const float* boxes, const float* scores, const int32_t* classes, const int32_t* seg_offsets,
+                    const int32_t* seg_count, int N, int total_capacity, int num_classes, float iou_thresh,
+                    int max_keep, int32_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
+                    bool presorted, cudaStream_t st) {
+  if (!workspace || workspace_bytes < b200_batched_nms_workspace_bytes(N, total_capacity, num_classes)) {
+    set_error("batched_nms: workspace too small");
+    return B200_ERR_WORKSPACE;
+  }
+  NmsWorkspace w = carve(workspace, N, total_capacity, num_classes);
+  const size_t prep_smem = (size_t)(2 + 32) * num_classes * sizeof(int);
+  if (prep_smem > 48 * 1024)
+    B200_CUDA_CALL(cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+  nms_prepare_kernel<<<N, kPrepThreads, prep_smem, st>>>(boxes, classes, seg_offsets, seg_count, num_classes, w.max1,
+                                                        w.class_start, w.order);
+  B200_CUDA_LAUNCH_CHECK("nms_prepare");
+  // `scratch` gives every class slice 4x its length: 2x for pow2 padding of the keys, 2x for the bitmap.
+  // slices are addressed at (base+cs)*4 to keep them disjoint.
+  if (presorted) {
+    // shifted boxes (16 B) + removed bitmap
+    const size_t cls_smem = (size_t)kNmsPresortedBoxes * 16 + kNmsPresortedBoxes / 8;
+    auto k = nms_class_kernel<kNmsPresortedThreads, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
+      attr_set = true;
+    }
+    k<<<dim3(num_classes, N), kNmsPresortedThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh,
+                                                                   w.max1, w.class_start, w.order, w.kept, w.scratch,
+                                                                   max_keep);
+  } else {
+    // keys (8 B) + shifted boxes (16 B) + removed bitmap
+    const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
+    auto k = nms_class_kernel<kNmsThreads, false>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
+      attr_set = true;
+    }
+    k<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1,
+                                                          w.class_start, w.order, w.kept, w.scratch, max_keep);
+  }
+  B200_CUDA_LAUNCH_CHECK("nms_class");
+  nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
+  B200_CUDA_LAUNCH_CHECK("nms_finalize");
+  return B200_OK;
+}
+}  // namespace b200
+
 extern "C" int b200_batched_nms(const float* boxes, const float* scores, const int32_t* classes,
                                 const int32_t* seg_offsets, const int32_t* seg_count, int N, int total_capacity,
                                 int num_classes, float iou_thresh, int max_keep, int32_t* keep, int32_t* keep_count,
@@ -493,33 +548,8 @@ extern "C" int b200_batched_nms(const float* boxes, const float* scores, const i
   B200_CHECK_ARG(max_keep >= 0, "batched_nms: max_keep must be >= 0 (pass the capacity for 'all')");
   B200_CHECK_ARG(seg_offsets && seg_count && keep_count && (keep || max_keep == 0), "batched_nms: null tensor");
   if (N == 0) return B200_OK;
-  if (!workspace || workspace_bytes < b200_batched_nms_workspace_bytes(N, total_capacity, num_classes)) {
-    set_error("batched_nms: workspace too small");
-    return B200_ERR_WORKSPACE;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  NmsWorkspace w = carve(workspace, N, total_capacity, num_classes);
-  const size_t prep_smem = (size_t)(2 + 32) * num_classes * sizeof(int);
-  if (prep_smem > 48 * 1024)
-    B200_CUDA_CALL(cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-  nms_prepare_kernel<<<N, kPrepThreads, prep_smem, st>>>(boxes, classes, seg_offsets, seg_count, num_classes, w.max1,
-                                                        w.class_start, w.order);
-  B200_CUDA_LAUNCH_CHECK("nms_prepare");
-  // keys (8 B) + shifted boxes (16 B) + removed bitmap
-  const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_CALL(cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
-    attr_set = true;
-  }
-  // `scratch` gives every class slice 4x its length: 2x for pow2 padding of the keys, 2x for the bitmap.
-  // slices are addressed at (base+cs)*4 to keep them disjoint.
-  nms_class_kernel<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(
-      boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1, w.class_start, w.order, w.kept, w.scratch, max_keep);
-  B200_CUDA_LAUNCH_CHECK("nms_class");
-  nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
-  B200_CUDA_LAUNCH_CHECK("nms_finalize");
-  return B200_OK;
+  return run_batched_nms(boxes, scores, classes, seg_offsets, seg_count, N, total_capacity, num_classes, iou_thresh,
+                         max_keep, keep, keep_count, workspace, workspace_bytes, false, (cudaStream_t)stream);
 }
 
 extern "C" int b200_gather_detections(const float* cand_boxes, const float* cand_scores, const int32_t* cand_roi,
@@ -533,5 +563,17 @@ extern "C" int b200_gather_detections(const float* cand_boxes, const float* cand
                                                                keep, keep_count, max_keep, out_boxes, out_scores,
                                                                out_classes, out_roi_inds);
   B200_CUDA_LAUNCH_CHECK("gather_detections");
+  return B200_OK;
+}
+
+extern "C" int b200_detector_postprocess(float* boxes, float* scores, int64_t* classes, int64_t* roi_inds,
+                                         int32_t* counts, const float* scale_xy, const float* out_hw, int N,
+                                         int max_keep, b200_stream_t stream) {
+  B200_CHECK_ARG(N >= 0 && max_keep >= 0, "detector_postprocess: bad shape");
+  if (N == 0 || max_keep == 0) return B200_OK;
+  B200_CHECK_ARG(boxes && scores && counts && scale_xy && out_hw, "detector_postprocess: null tensor");
+  detector_postprocess_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(boxes, scores, classes, roi_inds, counts, scale_xy,
+                                                                   out_hw, max_keep);
+  B200_CUDA_LAUNCH_CHECK("detector_postprocess");
   return B200_OK;
 }

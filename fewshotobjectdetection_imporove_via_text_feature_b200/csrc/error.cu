@@ -12,5 +12,5 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace b200
 
-extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int b200_abi_version(void) { return 3; }
 extern "C" const char* b200_last_error(void) { return b200::g_err; }

@@ -378,6 +378,71 @@ def fast_rcnn_inference_device(scores, deltas, proposals, roi_offsets, image_hw,
 
 
 # ---------------------------------------------------------------------------------------------------
+# the stages either side of the head
+# ---------------------------------------------------------------------------------------------------
+def rpn_select_proposals(proposals, logits, level_sizes, image_hw, nms_thresh, pre_nms_topk, post_nms_topk,
+                         min_box_size=0.0):
+    """find_top_rpn_proposals (proposal_generator/proposal_utils.py:13-118) on the device, no host synchronisation.
+    proposals (N, A, 4) / logits (N, A) with the levels concatenated along A in `level_sizes` order.  Returns padded
+    dict(boxes (N,post,4), logits (N,post), counts (N) int32, n_invalid (N) int32)."""
+    _require_cuda(proposals, logits)
+    proposals, logits = proposals.float().contiguous(), logits.float().contiguous()
+    N, A = logits.shape
+    L = len(level_sizes)
+    assert sum(level_sizes) == A and proposals.shape == (N, A, 4)
+    dev = logits.device
+    key = (tuple(int(v) for v in level_sizes), str(dev))
+    lo = _LEVEL_CACHE.get(key)
+    if lo is None:
+        acc = [0]
+        for v in level_sizes:
+            acc.append(acc[-1] + int(v))
+        lo = torch.tensor(acc, dtype=torch.int32).to(dev)
+        _LEVEL_CACHE[key] = lo
+    cap = sum(min(int(pre_nms_topk), int(v)) for v in level_sizes)
+    post = int(post_nms_topk)
+    ob = torch.empty((N, post, 4), dtype=torch.float32, device=dev)
+    ol = torch.empty((N, post), dtype=torch.float32, device=dev)
+    oc = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+    bad = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+    if N == 0 or cap == 0:
+        return dict(boxes=ob, logits=ol, counts=oc[:N], n_invalid=bad[:N])
+    nbytes = _lib.lib().b200_rpn_select_workspace_bytes(N, cap, L, post)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.call("b200_rpn_select_proposals", proposals.data_ptr(), logits.data_ptr(), lo.data_ptr(), image_hw.data_ptr(),
+              N, A, L, int(pre_nms_topk), post, cap, float(nms_thresh), float(min_box_size), ob.data_ptr(), ol.data_ptr(),
+              oc.data_ptr(), bad.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return dict(boxes=ob, logits=ol, counts=oc[:N], n_invalid=bad[:N])
+
+
+_LEVEL_CACHE = {}
+
+
+def detector_postprocess_(boxes, scores, classes, roi_inds, counts, image_sizes, output_sizes):
+    """detectron2 detector_postprocess (rcnn.py:69-73) in place on padded detections: boxes (N,topk,4), scores (N,topk),
+    classes / roi_inds (N,topk) int64 or None, counts (N) int32; image_sizes / output_sizes: per image (h, w)."""
+    _require_cuda(boxes, scores)
+    N, topk = scores.shape
+    assert boxes.is_contiguous() and scores.is_contiguous() and counts.is_contiguous()
+    key = (tuple((int(h), int(w)) for h, w in image_sizes), tuple((int(h), int(w)) for h, w in output_sizes), str(boxes.device))
+    hit = _POST_CACHE.get(key)
+    if hit is None:
+        if len(_POST_CACHE) > 256:
+            _POST_CACHE.clear()
+        # python-float ratios like the reference, rounded to fp32 where torch multiplies an fp32 tensor by them
+        sc = [(ow / w, oh / h) for (h, w), (oh, ow) in zip(key[0], key[1])]
+        hit = (torch.tensor(sc, dtype=torch.float64).to(torch.float32).reshape(-1, 2).to(boxes.device),
+               torch.tensor(key[1], dtype=torch.float32).reshape(-1, 2).to(boxes.device))
+        _POST_CACHE[key] = hit
+    _lib.call("b200_detector_postprocess", boxes.data_ptr(), scores.data_ptr(), _ptr(classes), _ptr(roi_inds),
+              counts.data_ptr(), hit[0].data_ptr(), hit[1].data_ptr(), N, topk, _stream())
+    return boxes, scores, classes, roi_inds, counts
+
+
+_POST_CACHE = {}
+
+
+# ---------------------------------------------------------------------------------------------------
 # Q2  (calibration_layer.py:110-123)
 # ---------------------------------------------------------------------------------------------------
 def pcb_cosine_blend_(scores, feats, prototypes, classes, exclude_mask, alpha, lower, upper):

@@ -291,6 +291,38 @@ B200_API int b200_label_sample_proposals(const float* proposals, const int32_t* 
                                 int32_t* matched_label, int32_t* sampled_idx, float* out_proposals, int64_t* out_classes,
                                 float* out_gt_boxes, int32_t* counts, b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * SURVEY 8f-3  RPN proposal selection == detectron2 0.3 find_top_rpn_proposals, vendored at
+ *     defrcn/modeling/proposal_generator/proposal_utils.py:13-118 — the stage that feeds the ROI head.
+ *   proposals (N, A, 4) fp32 xyxy (decoded anchors, levels concatenated along A), logits (N, A) fp32;
+ *   level_offsets (L + 1) int32 DEVICE array, level l = anchors [level_offsets[l], level_offsets[l+1]).
+ *   Per image and level: the min(pre_nms_topk, A_l) highest logits in descending order (ties: lower anchor
+ *   index first; NaN sorts first like torch.sort); then per image: drop non-finite candidates (their number
+ *   is written to n_invalid (N) — the reference raises FloatingPointError in training when it is non-zero),
+ *   clip to image_hw (N,2) = (h, w), drop boxes whose width or height is not > min_box_size,
+ *   batched_nms by level (coordinate-offset trick below 40000 candidates) at nms_thresh, keep the first
+ *   post_nms_topk.  out_boxes (N, post_nms_topk, 4), out_logits (N, post_nms_topk) zero padded, out_count (N).
+ *   cap_per_image = sum_l min(pre_nms_topk, A_l) (the caller knows the level sizes); pre_nms_topk <= 16384.
+ *   Keep indices / counts are bit-exact with the reference's CPU path.  No host synchronisation.
+ * ------------------------------------------------------------------------------------------------- */
+B200_API size_t b200_rpn_select_workspace_bytes(int N, int cap_per_image, int L, int post_nms_topk);
+B200_API int b200_rpn_select_proposals(const float* proposals, const float* logits, const int32_t* level_offsets,
+                              const float* image_hw, int N, int A, int L, int pre_nms_topk, int post_nms_topk,
+                              int cap_per_image, float nms_thresh, float min_box_size, float* out_boxes,
+                              float* out_logits, int32_t* out_count, int32_t* n_invalid, void* workspace,
+                              size_t workspace_bytes, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * SURVEY 8f-4  detectron2 0.3 detector_postprocess (call site defrcn/modeling/meta_arch/rcnn.py:69-73) on the
+ *     padded detection tensors of b200_gather_detections, in place: boxes (N,max_keep,4) scaled by
+ *     scale_xy (N,2) = (out_w / w, out_h / h) rounded to fp32, clipped to out_hw (N,2) = (out_h, out_w),
+ *     empty boxes dropped (order kept; scores / classes / roi_inds rows move with their box; classes and
+ *     roi_inds may be NULL); counts (N) updated.
+ * ------------------------------------------------------------------------------------------------- */
+B200_API int b200_detector_postprocess(float* boxes, float* scores, int64_t* classes, int64_t* roi_inds,
+                              int32_t* counts, const float* scale_xy, const float* out_hw, int N, int max_keep,
+                              b200_stream_t stream);
+
 /* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
  * in place, without a torch.cat) */
 B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,

@@ -436,6 +436,68 @@ def gen_cosine():
              bsim=mm.bsim_matrix(a[None], t[None], tau=20.0)[0].numpy(), tau=np.float32(20.0))
 
 
+def synth_rpn_outputs(N, level_sizes, h, w, gen, quant=0.0):
+    """Decoded anchors + objectness the way an RPN head leaves them: boxes partly outside the image, clusters around a
+    few objects (so NMS suppresses), logits optionally quantised (exact ties)."""
+    props, logits = [], []
+    for A in level_sizes:
+        pb, pl = [], []
+        for _ in range(N):
+            b, objs = synth_proposals(A, h, w, gen, n_obj=6)
+            b = b + torch.randn(A, 4, generator=gen) * 6.0 - 3.0           # un-clipped, a few inverted / outside
+            l = torch.randn(A, generator=gen) * 2.0
+            if quant > 0:
+                l = torch.round(l / quant) * quant
+            pb.append(b)
+            pl.append(l)
+        props.append(torch.stack(pb))
+        logits.append(torch.stack(pl))
+    return props, logits
+
+
+def gen_rpn_select():
+    """The reference's own find_top_rpn_proposals (proposal_generator/proposal_utils.py:13-118), eval mode, on
+    synthetic RPN outputs: one level with ties / non-finite entries / boxes that clip to nothing, and three levels."""
+    rs.install()
+    pu = rs.load("defrcn.modeling.proposal_generator.proposal_utils")
+    gen = torch.Generator().manual_seed(41)
+    d = {}
+    # no exact logit ties here: the reference asks torch for an UNSTABLE sort (:64), so their order is not defined by
+    # it (torch 2.x's CPU sort really is unstable); the tie rule of the CUDA path (lower anchor first) is tested
+    # against the oracle's stable sort instead
+    cases = (("c4", 2, [3000], (600, 800), 0.7, 600, 200, 0.0, 0.0),
+             ("c4_minsize", 2, [2000], (480, 672), 0.7, 2000, 1500, 4.0, 0.0),
+             ("fpn3", 3, [1200, 300, 75], (600, 800), 0.6, 250, 300, 0.0, 0.0))
+    for tag, N, sizes, (h, w), thr, pre, post, min_size, quant in cases:
+        props, logits = synth_rpn_outputs(N, sizes, h, w, gen, quant)
+        if tag == "c4":
+            props[0][1, 17, 2] = float("inf")
+            props[0][1, 400, 0] = float("nan")
+            logits[0][1, 33] = float("nan")
+            logits[0][0, 5] = float("inf")
+            top = logits[0][0].argsort(descending=True)[:3]
+            props[0][0, top[1]] = torch.tensor([900.0, 10.0, 950.0, 50.0])       # clips to zero width
+            props[0][0, top[2]] = torch.tensor([50.0, 700.0, 90.0, 800.0])       # clips to zero height
+        for lg in logits:
+            for row in lg:
+                fin = row[torch.isfinite(row)]
+                assert len(torch.unique(fin)) == len(fin), "exact logit tie in a golden case"
+        image_sizes = [(h, w) if i % 2 == 0 else (h - 24, w - 40) for i in range(N)]
+        res = pu.find_top_rpn_proposals([p.clone() for p in props], [l.clone() for l in logits], image_sizes, thr, pre,
+                                        post, min_size, False)
+        d[tag + "_meta"] = np.array([N, len(sizes), pre, post], np.int64)
+        d[tag + "_sizes"] = np.array(sizes, np.int64)
+        d[tag + "_image_sizes"] = np.array(image_sizes, np.int64)
+        d[tag + "_thr"] = np.float32(thr)
+        d[tag + "_min_size"] = np.float32(min_size)
+        for l, (p, lg) in enumerate(zip(props, logits)):
+            d["%s_props%d" % (tag, l)], d["%s_logits%d" % (tag, l)] = p.numpy(), lg.numpy()
+        for n, r in enumerate(res):
+            d["%s_out_boxes%d" % (tag, n)] = r.proposal_boxes.tensor.numpy()
+            d["%s_out_logits%d" % (tag, n)] = r.objectness_logits.numpy()
+    np.savez_compressed(os.path.join(OUT, "rpn_select.npz"), **d)
+
+
 def main():
     import sys
     if len(sys.argv) > 1:       # regenerate selected fixtures only: python -m oracle.gen_golden gen_train_step ...
@@ -457,6 +519,7 @@ def main():
     gen_known_answer()
     gen_cosine()
     gen_label_sample()
+    gen_rpn_select()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -473,3 +473,52 @@ def sample_counts(n_fg, n_bg, batch=512, positive_fraction=0.25):
     """detectron2 subsample_labels counts (roi_heads.py:118-155 `_sample_proposals`): (#fg rows, #bg rows)."""
     num_pos = min(n_fg, int(batch * positive_fraction))
     return num_pos, min(n_bg, batch - num_pos)
+
+
+# ------------------------------------------------------------------ RPN proposal selection
+def find_top_rpn_proposals(proposals, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk,
+                           min_box_size=0.0):
+    """detectron2 0.3 find_top_rpn_proposals as vendored at defrcn/modeling/proposal_generator/proposal_utils.py:13-118
+    (eval behaviour: non-finite candidates are dropped).  proposals[l] (N,A_l,4), logits[l] (N,A_l).
+    Returns per image dict(boxes, logits, n_invalid).  The descending sort is stable (what torch's CPU sort does;
+    :64 asks for an unstable one, so ties are only pinned on the CPU)."""
+    N = len(image_sizes)
+    tb, ts, tl = [], [], []
+    for lvl, (p, l) in enumerate(zip(proposals, pred_objectness_logits)):
+        p, l = torch.as_tensor(p).float(), torch.as_tensor(l).float()
+        k = min(pre_nms_topk, l.shape[1])
+        sl, idx = l.sort(descending=True, dim=1, stable=True)                                  # :64
+        idx = idx[:, :k]
+        ts.append(sl[:, :k])                                                                   # :65
+        tb.append(torch.gather(p, 1, idx[:, :, None].expand(-1, -1, 4)))                       # :69
+        tl.append(torch.full((k,), lvl, dtype=torch.int64))
+    ts, tb, tl = torch.cat(ts, 1), torch.cat(tb, 1), torch.cat(tl, 0)                          # :76-78
+    out = []
+    for n, (h, w) in enumerate(image_sizes):
+        b, s, lv = tb[n].clone(), ts[n], tl
+        valid = torch.isfinite(b).all(dim=1) & torch.isfinite(s)                               # :87
+        n_invalid = int((~valid).sum())
+        b, s, lv = b[valid], s[valid], lv[valid]
+        b[:, 0::2] = b[:, 0::2].clamp(min=0, max=w)                                            # :96 Boxes.clip
+        b[:, 1::2] = b[:, 1::2].clamp(min=0, max=h)
+        keep = ((b[:, 2] - b[:, 0]) > min_box_size) & ((b[:, 3] - b[:, 1]) > min_box_size)     # :99 Boxes.nonempty
+        b, s, lv = b[keep], s[keep], lv[keep]
+        k = batched_nms(b, s, lv, nms_thresh)[:post_nms_topk]                                  # :103-111
+        out.append(dict(boxes=b[k], logits=s[k], n_invalid=n_invalid))
+    return out
+
+
+# ------------------------------------------------------------------ detector_postprocess
+def detector_postprocess(boxes, image_size, output_height, output_width):
+    """detectron2 0.3 modeling/postprocessing.py::detector_postprocess on the boxes (call site
+    defrcn/modeling/meta_arch/rcnn.py:69-73): scale by python-float ratios (torch multiplies the fp32 tensor by the
+    ratio rounded to fp32), clip, keep non-empty.  Returns (boxes, keep_mask).  detectron2 is absent from
+    /root/reference and from this image: this part is restated from the published v0.3 source, unpinned."""
+    b = torch.as_tensor(boxes).float().clone()
+    scale_x, scale_y = output_width / image_size[1], output_height / image_size[0]
+    b[:, 0::2] *= scale_x
+    b[:, 1::2] *= scale_y
+    b[:, 0::2] = b[:, 0::2].clamp(min=0, max=output_width)
+    b[:, 1::2] = b[:, 1::2].clamp(min=0, max=output_height)
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return b[keep], keep

@@ -102,6 +102,18 @@ class Boxes:
         self.tensor[:, 2].clamp_(min=0, max=w)
         self.tensor[:, 3].clamp_(min=0, max=h)
 
+    def nonempty(self, threshold=0.0):
+        # detectron2 0.3 structures/boxes.py::Boxes.nonempty
+        box = self.tensor
+        widths = box[:, 2] - box[:, 0]
+        heights = box[:, 3] - box[:, 1]
+        return (widths > threshold) & (heights > threshold)
+
+    def scale(self, scale_x, scale_y):
+        # detectron2 0.3 structures/boxes.py::Boxes.scale
+        self.tensor[:, 0::2] *= scale_x
+        self.tensor[:, 1::2] *= scale_y
+
     def __getitem__(self, item):
         if isinstance(item, int):
             return Boxes(self.tensor[item].view(1, -1))
@@ -579,7 +591,8 @@ def install(class_embed_fn=None, device="cpu"):
 
     r = os.path.join(REFERENCE_ROOT, "defrcn")
     _pkg_shell("defrcn", r)
-    for sub in ("modeling", "modeling/roi_heads", "modeling/meta_arch", "utils", "data", "evaluation"):
+    for sub in ("modeling", "modeling/roi_heads", "modeling/meta_arch", "modeling/proposal_generator", "utils", "data",
+                "evaluation"):
         _pkg_shell("defrcn." + sub.replace("/", "."), os.path.join(r, sub))
     _installed = True
 

@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(L, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     L.b200_abi_version.restype = ctypes.c_int
-    assert L.b200_abi_version() == 2
+    assert L.b200_abi_version() == 3
     # every declaration cites the reference interface it replaces
     assert header.count("defrcn/") >= 8
 

@@ -175,3 +175,39 @@ def test_label_proposals_vs_reference(golden):
         assert (int((oc < K).sum()), int((oc == K).sum())) == (npos, nneg)
     idx, lab, _ = O.label_proposals(g["all_props2"], g["gt_boxes2"])
     assert int(lab.sum()) == 0 and O.sample_counts(0, len(lab), B, frac) == (0, len(g["out_classes2"]))
+
+
+def _rpn_case(g, tag):
+    N, L, pre, post = (int(v) for v in g[tag + "_meta"])
+    props = [T(g["%s_props%d" % (tag, l)]) for l in range(L)]
+    logits = [T(g["%s_logits%d" % (tag, l)]) for l in range(L)]
+    image_sizes = [tuple(int(v) for v in s) for s in g[tag + "_image_sizes"]]
+    return N, props, logits, image_sizes, float(g[tag + "_thr"]), pre, post, float(g[tag + "_min_size"])
+
+
+def test_rpn_select(golden):
+    """find_top_rpn_proposals restatement vs the reference's own function (proposal_utils.py:13-118): bit-exact."""
+    g = golden("rpn_select")
+    for tag in ("c4", "c4_minsize", "fpn3"):
+        N, props, logits, image_sizes, thr, pre, post, min_size = _rpn_case(g, tag)
+        out = O.find_top_rpn_proposals(props, logits, image_sizes, thr, pre, post, min_size)
+        for n in range(N):
+            assert torch.equal(out[n]["boxes"], T(g["%s_out_boxes%d" % (tag, n)])), (tag, n)
+            assert torch.equal(out[n]["logits"], T(g["%s_out_logits%d" % (tag, n)])), (tag, n)
+    assert O.find_top_rpn_proposals(*_rpn_case(g, "c4")[1:])[1]["n_invalid"] >= 1     # the planted inf / NaN entries
+
+
+def test_detector_postprocess_restatement():
+    """detector_postprocess restatement against the Boxes.scale / clip / nonempty stubs used for the reference run."""
+    from oracle import ref_stubs as rs
+    gen = torch.Generator().manual_seed(3)
+    b = torch.rand(64, 4, generator=gen) * 600
+    b[:, 2:] = b[:, :2] + torch.rand(64, 2, generator=gen) * 300
+    b[5] = torch.tensor([700.0, 10.0, 790.0, 40.0])
+    h, w, oh, ow = 600, 800, 375, 500
+    out, keep = O.detector_postprocess(b, (h, w), oh, ow)
+    bx = rs.Boxes(b.clone())
+    bx.scale(ow / w, oh / h)
+    bx.clip((oh, ow))
+    k = bx.nonempty()
+    assert torch.equal(keep, k) and torch.equal(out, bx.tensor[k])
