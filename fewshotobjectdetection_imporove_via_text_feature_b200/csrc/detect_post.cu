@@ -16,6 +16,8 @@
 //       emit the first max_keep.
 // All comparisons that decide membership (score > thresh, iou > thresh) use round-to-nearest fp32 ops in
 // the reference's order with FMA contraction disabled, so keep indices and counts are bit-exact.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "sort_scan.cuh"
 
@@ -208,6 +210,7 @@ constexpr int kNmsSmemBoxes = 4096;  // per (class, image) handled fully in shar
 // 12288 boxes x 16 B + 1.5 KB = 198 KB, one 1024-thread CTA per (level, image).
 constexpr int kNmsPresortedBoxes = 12288;
 constexpr int kNmsPresortedThreads = 1024;
+constexpr int kNmsCluster = 8;       // portable cluster size
 
 template <int THREADS, bool PRESORTED>
 __global__ void __launch_bounds__(THREADS)
@@ -215,7 +218,7 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
                  const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
                  const float* __restrict__ max1, const int32_t* __restrict__ class_start,
                  const int32_t* __restrict__ order, unsigned long long* __restrict__ kept,
-                 unsigned long long* __restrict__ scratch, int max_keep) {
+                 unsigned long long* __restrict__ scratch, int max_keep, int skip_upto) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keep64;
@@ -223,7 +226,7 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   const int base = seg_offsets[img];
   const int cs = class_start[(size_t)img * (num_classes + 1) + c];
   const int m = class_start[(size_t)img * (num_classes + 1) + c + 1] - cs;
-  if (m == 0) return;
+  if (m == 0 || m <= skip_upto) return;                     // slices up to skip_upto belong to the cluster kernel
   const float off = __fmul_rn((float)c, max1[img]);
   const int32_t* ord = order + base + cs;
   unsigned long long* kept_out = kept + base + cs;
@@ -337,6 +340,121 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     }
     __syncthreads();
   }
+}
+
+// PRESORTED slices of up to kNmsPresortedBoxes boxes on a thread-block CLUSTER (RPN proposal selection: one level of one
+// image is 6000-12000 boxes, far more survivor x box work than one SM issues in reasonable time).  Every CTA of the
+// cluster keeps all boxes of the slice in its own shared memory and resolves each 64-box diagonal block redundantly (same
+// inputs, same result), but sweeps the survivors only over the bitmap words it owns (word w belongs to rank w % CL).
+// The two `removed` words a diagonal block needs are read from their owners through distributed shared memory; one
+// cluster barrier per block orders the sweeps before those reads.  Rank 0 writes the result.
+template <int CL>
+__global__ void __launch_bounds__(kNmsPresortedThreads)
+nms_presorted_cluster_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                             const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
+                             const float* __restrict__ max1, const int32_t* __restrict__ class_start,
+                             const int32_t* __restrict__ order, unsigned long long* __restrict__ kept, int max_keep) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_keep64;
+  __shared__ uint32_t s_dead[2];
+  const int rank = (int)cluster.block_rank();
+  const int c = blockIdx.x / CL, img = blockIdx.y;
+  const int base = seg_offsets[img];
+  const int cs = class_start[(size_t)img * (num_classes + 1) + c];
+  const int m = class_start[(size_t)img * (num_classes + 1) + c + 1] - cs;
+  if (m == 0 || m > kNmsPresortedBoxes) return;              // uniform over the cluster; larger slices: fallback kernel
+  const float off = __fmul_rn((float)c, max1[img]);
+  const int32_t* ord = order + base + cs;
+  unsigned long long* kept_out = kept + base + cs;
+  float4* sbox = reinterpret_cast<float4*>(s_raw);
+  uint32_t* removed = reinterpret_cast<uint32_t*>(s_raw + (size_t)kNmsPresortedBoxes * 16);
+
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    float4 b = *reinterpret_cast<const float4*>(boxes + 4 * (size_t)(base + ord[j]));
+    b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+    sbox[j] = b;
+  }
+  for (int j = threadIdx.x; j < kNmsPresortedBoxes / 32; j += blockDim.x) removed[j] = 0u;
+  cluster.sync();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int nkept = 0;
+  for (int b0 = 0; b0 < m; b0 += 64) {
+    const int nb = min(64, m - b0);
+    if (threadIdx.x < 2) {
+      const int w = (b0 >> 5) + threadIdx.x;
+      s_dead[threadIdx.x] = (w * 32 < m) ? *cluster.map_shared_rank(removed + w, w % CL) : 0u;
+    }
+    for (int t = warp; t < 64; t += kNmsPresortedThreads / 32) {
+      unsigned m0 = 0u, m1 = 0u;
+      if (t < nb) {
+        const float4 a = sbox[b0 + t];
+        const int j0 = lane, j1 = lane + 32;
+        const bool h0 = j0 > t && j0 < nb && iou_gt(a, sbox[b0 + j0], thr);
+        const bool h1 = j1 > t && j1 < nb && iou_gt(a, sbox[b0 + j1], thr);
+        m0 = __ballot_sync(0xffffffffu, h0);
+        m1 = __ballot_sync(0xffffffffu, h1);
+      }
+      if (lane == 0) s_diag[t] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long lo = s_diag[lane], hi = s_diag[lane + 32];
+      unsigned long long dead = (unsigned long long)s_dead[0] | ((unsigned long long)s_dead[1] << 32);
+      unsigned long long keep = 0ull;
+      for (int t = 0; t < nb; ++t) {
+        const unsigned long long row = __shfl_sync(0xffffffffu, t < 32 ? lo : hi, t & 31);
+        if (!((dead >> t) & 1ull)) { keep |= 1ull << t; dead |= row; }
+      }
+      if (lane == 0) s_keep64 = keep;
+    }
+    __syncthreads();
+    unsigned long long keep = s_keep64;
+    const int room = max_keep - nkept;
+    if (__popcll(keep) > room) {
+      int seen = 0;
+      unsigned long long trimmed = 0ull;
+      for (int t = 0; t < nb && seen < room; ++t)
+        if ((keep >> t) & 1ull) { trimmed |= 1ull << t; ++seen; }
+      keep = trimmed;
+    }
+    nkept += __popcll(keep);
+    if (rank == 0 && (int)threadIdx.x < nb) {
+      const int j = b0 + threadIdx.x;
+      const uint32_t cand = (uint32_t)ord[j];
+      kept_out[j] = ((keep >> threadIdx.x) & 1ull) ? (((unsigned long long)desc_key(scores[base + cand]) << 32) | cand) : ~0ull;
+    }
+    if (nkept >= max_keep) {                                   // identical in every CTA of the cluster
+      if (rank == 0)
+        for (int j = b0 + 64 + threadIdx.x; j < m; j += blockDim.x) kept_out[j] = ~0ull;
+      break;
+    }
+    if (keep != 0ull) {
+      // own words: w = w_first + CL * i, one box per thread and step
+      const int wlo = (b0 + 64) >> 5;
+      const int w_first = wlo + ((rank - wlo) % CL + CL) % CL;
+      for (int idx = threadIdx.x;; idx += blockDim.x) {
+        const int w = w_first + CL * (idx >> 5);
+        const int j = w * 32 + (idx & 31);
+        if (w * 32 >= m) break;
+        if (j >= m || ((removed[w] >> (j & 31)) & 1u)) continue;
+        const float4 bj = sbox[j];
+        unsigned long long kk = keep;
+        bool dead = false;
+        while (kk && !dead) {
+          const int t = __ffsll((long long)kk) - 1;
+          kk &= kk - 1;
+          dead = iou_gt(sbox[b0 + t], bj, thr);
+        }
+        if (dead) atomicOr(&removed[w], 1u << (j & 31));
+      }
+    }
+    cluster.sync();
+  }
+  cluster.sync();                                              // nobody leaves while a peer may still read its bitmap
 }
 
 constexpr int kFinalSmemKeys = 4096;
@@ -491,11 +609,11 @@ extern "C" size_t b200_batched_nms_workspace_bytes(int N, int total_capacity, in
 
 namespace b200 {
 // shared by b200_batched_nms and b200_rpn_select_proposals (rpn_select.cu); `presorted` = within every class the
-// candidates already are in (score desc, index asc) order
+// candidates already are in (score desc, index asc) order; max_slice_hint = upper bound of a class slice (0 = unknown)
 int run_batched_nms(const float* boxes, const float* scores, const int32_t* classes, const int32_t* seg_offsets,
                     const int32_t* seg_count, int N, int total_capacity, int num_classes, float iou_thresh,
                     int max_keep, int32_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
-                    bool presorted, cudaStream_t st) {
+                    bool presorted, int max_slice_hint, cudaStream_t st) {
   if (!workspace || workspace_bytes < b200_batched_nms_workspace_bytes(N, total_capacity, num_classes)) {
     set_error("batched_nms: workspace too small");
     return B200_ERR_WORKSPACE;
@@ -510,17 +628,35 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
   // `scratch` gives every class slice 4x its length: 2x for pow2 padding of the keys, 2x for the bitmap.
   // slices are addressed at (base+cs)*4 to keep them disjoint.
   if (presorted) {
-    // shifted boxes (16 B) + removed bitmap
+    // shifted boxes (16 B) + removed bitmap; slices <= kNmsPresortedBoxes on a cluster of kNmsCluster CTAs, larger ones
+    // (not reachable from b200_rpn_select_proposals with pre_nms_topk <= 12288) on the single-CTA kernel's global path
     const size_t cls_smem = (size_t)kNmsPresortedBoxes * 16 + kNmsPresortedBoxes / 8;
+    auto kc = nms_presorted_cluster_kernel<kNmsCluster>;
     auto k = nms_class_kernel<kNmsPresortedThreads, true>;
     static bool attr_set = false;
     if (!attr_set) {
+      B200_CUDA_CALL(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
       B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
       attr_set = true;
     }
-    k<<<dim3(num_classes, N), kNmsPresortedThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh,
-                                                                   w.max1, w.class_start, w.order, w.kept, w.scratch,
-                                                                   max_keep);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNmsCluster * num_classes, N);
+    cfg.blockDim = dim3(kNmsPresortedThreads);
+    cfg.dynamicSmemBytes = cls_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kNmsCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_CALL(cudaLaunchKernelEx(&cfg, kc, boxes, scores, seg_offsets, num_classes, iou_thresh, (const float*)w.max1,
+                                      (const int32_t*)w.class_start, (const int32_t*)w.order, w.kept, max_keep));
+    if ((max_slice_hint > 0 ? max_slice_hint : total_capacity) > kNmsPresortedBoxes)
+      k<<<dim3(num_classes, N), kNmsPresortedThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh,
+                                                                     w.max1, w.class_start, w.order, w.kept, w.scratch,
+                                                                     max_keep, kNmsPresortedBoxes);
   } else {
     // keys (8 B) + shifted boxes (16 B) + removed bitmap
     const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
@@ -531,7 +667,7 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
       attr_set = true;
     }
     k<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1,
-                                                          w.class_start, w.order, w.kept, w.scratch, max_keep);
+                                                          w.class_start, w.order, w.kept, w.scratch, max_keep, 0);
   }
   B200_CUDA_LAUNCH_CHECK("nms_class");
   nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
@@ -549,7 +685,7 @@ extern "C" int b200_batched_nms(const float* boxes, const float* scores, const i
   B200_CHECK_ARG(seg_offsets && seg_count && keep_count && (keep || max_keep == 0), "batched_nms: null tensor");
   if (N == 0) return B200_OK;
   return run_batched_nms(boxes, scores, classes, seg_offsets, seg_count, N, total_capacity, num_classes, iou_thresh,
-                         max_keep, keep, keep_count, workspace, workspace_bytes, false, (cudaStream_t)stream);
+                         max_keep, keep, keep_count, workspace, workspace_bytes, false, 0, (cudaStream_t)stream);
 }
 
 extern "C" int b200_gather_detections(const float* cand_boxes, const float* cand_scores, const int32_t* cand_roi,

@@ -10,8 +10,10 @@
 //       network (<= 16384 keys, 128 KB); then, in sorted order, finite check + clip + min-size test + ORDERED
 //       compaction (block scan) write the image's candidate segment.  Ties keep the lower anchor index first, i.e.
 //       the order of the stable descending sort the reference's CPU path performs.
-//   nms_class_kernel<1024, PRESORTED> (detect_post.cu) : the candidates of a level arrive sorted, so one CTA per
-//       (level, image) keeps all <= 12288 boxes in shared memory and runs the survivor-sweep NMS without a key sort.
+//   nms_presorted_cluster_kernel (detect_post.cu) : the candidates of a level arrive sorted, so no key sort; a cluster
+//       of 8 CTAs per (level, image) keeps all <= 12288 boxes in each CTA's shared memory, resolves the 64-box diagonal
+//       blocks redundantly and splits the survivor sweep by bitmap word, exchanging two words per block through
+//       distributed shared memory.
 //   rpn_gather_kernel      : kept candidates -> padded (N, post_nms_topk) outputs.
 #include "common.cuh"
 #include "sort_scan.cuh"
@@ -21,7 +23,7 @@ namespace b200 {
 int run_batched_nms(const float* boxes, const float* scores, const int32_t* classes, const int32_t* seg_offsets,
                     const int32_t* seg_count, int N, int total_capacity, int num_classes, float iou_thresh,
                     int max_keep, int32_t* keep, int32_t* keep_count, void* workspace, size_t workspace_bytes,
-                    bool presorted, cudaStream_t st);
+                    bool presorted, int max_slice_hint, cudaStream_t st);
 
 constexpr int kRpnThreads = 1024;
 constexpr int kRpnMaxTopk = 16384;   // shared-memory sort capacity (reference configs use 6000 / 12000 / 1000 / 2000)
@@ -29,7 +31,6 @@ constexpr int kRpnMaxTopk = 16384;   // shared-memory sort capacity (reference c
 // ascending key == descending logit; every NaN first (torch's sort treats NaN as the largest value), -0 == +0
 __device__ __forceinline__ uint32_t rpn_key(float s) {
   if (s != s) return 0u;
-  if (s == 0.f) return desc_key(0.f);          // -0 and +0 compare equal in the reference's sort
   return desc_key(s);
 }
 
@@ -242,7 +243,7 @@ extern "C" int b200_rpn_select_proposals(const float* proposals, const float* lo
                                                       w.cand_lvl, w.seg_offsets, w.cand_count, n_invalid);
   B200_CUDA_LAUNCH_CHECK("rpn_topk_filter");
   int rc = run_batched_nms(w.cand_boxes, w.cand_scores, w.cand_lvl, w.seg_offsets, w.cand_count, N, (int)tot, L,
-                           nms_thresh, post_nms_topk, w.keep, out_count, w.nms, w.nms_bytes, true, st);
+                           nms_thresh, post_nms_topk, w.keep, out_count, w.nms, w.nms_bytes, true, pre_nms_topk, st);
   if (rc != B200_OK) return rc;
   rpn_gather_kernel<<<N, 256, 0, st>>>(w.cand_boxes, w.cand_scores, w.seg_offsets, w.keep, out_count, post_nms_topk,
                                       out_boxes, out_logits);

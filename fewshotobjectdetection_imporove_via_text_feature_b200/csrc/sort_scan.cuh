@@ -34,8 +34,9 @@ __device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp /*[3
 }
 
 __device__ __forceinline__ uint32_t desc_key(float s) {
-  // monotone map float -> uint32 such that larger float => SMALLER key (ascending sort == descending score)
-  uint32_t u = __float_as_uint(s);
+  // monotone map float -> uint32 such that larger float => SMALLER key (ascending sort == descending score);
+  // -0 and +0 share a key, as they compare equal in the reference's sorts
+  uint32_t u = s == 0.f ? 0u : __float_as_uint(s);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return ~u;
 }
