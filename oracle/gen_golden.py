@@ -498,6 +498,64 @@ def gen_rpn_select():
     np.savez_compressed(os.path.join(OUT, "rpn_select.npz"), **d)
 
 
+def gen_eval_formats():
+    """The reference's own PascalVOCDetectionEvaluator.process (pascal_voc_evaluation.py:57-78, with
+    instances_to_coco_json :172-203) on synthetic detections of three images (one empty)."""
+    rs.install()
+    sys.modules.setdefault("defrcn.dataloader", types.ModuleType("defrcn.dataloader"))
+    sys.modules["defrcn.dataloader"].build_detection_test_loader = None
+    archs = types.ModuleType("defrcn.evaluation.archs")
+    archs.resnet101 = None
+    sys.modules["defrcn.evaluation.archs"] = archs
+
+    class BoxMode:                      # detectron2 0.3 structures/boxes.py::BoxMode.convert, the one conversion used
+        XYXY_ABS, XYWH_ABS = 0, 1
+
+        @staticmethod
+        def convert(box, from_mode, to_mode):
+            assert (from_mode, to_mode) == (BoxMode.XYXY_ABS, BoxMode.XYWH_ABS)
+            arr = torch.from_numpy(np.asarray(box)).clone()
+            arr[:, 2] -= arr[:, 0]
+            arr[:, 3] -= arr[:, 1]
+            return arr.numpy()
+    sys.modules["detectron2.structures"].BoxMode = BoxMode
+    rs._mod("detectron2.utils.comm", is_main_process=lambda: True, gather=lambda x, dst=0: [x], synchronize=lambda: None)
+    sys.modules["detectron2.utils"].comm = sys.modules["detectron2.utils.comm"]
+    rs._mod("detectron2.utils.logger", create_small_table=lambda d: str(d))
+    rs._mod("fvcore.common")
+    rs._mod("fvcore.common.file_io", PathManager=object())
+    pv = rs.load("defrcn.evaluation.pascal_voc_evaluation")
+    ev = object.__new__(pv.PascalVOCDetectionEvaluator)
+    ev._cpu_device = torch.device("cpu")
+    ev.reset()
+    gen = torch.Generator().manual_seed(17)
+    ids = ["000012", "2008_000123", "000999"]
+    counts = [37, 100, 0]
+    T_ = 100
+    boxes, scores, classes = np.zeros((3, T_, 4), np.float32), np.zeros((3, T_), np.float32), np.full((3, T_), -1, np.int64)
+    inputs, outputs = [], []
+    for i, (iid, n) in enumerate(zip(ids, counts)):
+        b = torch.rand(n, 4, generator=gen) * 500
+        b[:, 2:] = b[:, :2] + torch.rand(n, 2, generator=gen) * 333.3
+        s = torch.rand(n, generator=gen).sort(descending=True).values
+        if n > 4:
+            s[1], s[2] = 0.99949997, 0.0005                     # rounding edges of :.3f
+            b[0] = torch.tensor([0.04999, 10.25, 99.95, 100.05])
+        c = torch.randint(0, 20, (n,), generator=gen)
+        boxes[i, :n], scores[i, :n], classes[i, :n] = b.numpy(), s.numpy(), c.numpy()
+        inst = rs.Instances((600, 800))
+        inst.pred_boxes, inst.scores, inst.pred_classes = rs.Boxes(b.clone()), s.clone(), c.clone()
+        inputs.append({"image_id": iid})
+        outputs.append({"instances": inst})
+    rs.Instances.to = lambda self, *a, **k: self
+    ev.process(inputs, outputs)
+    import json
+    np.savez_compressed(os.path.join(OUT, "eval_formats.npz"), boxes=boxes, scores=scores, classes=classes,
+                        counts=np.array(counts, np.int64), ids=np.array(ids),
+                        voc_lines=np.array(json.dumps({str(k): v for k, v in ev._predictions.items()})),
+                        coco=np.array(json.dumps([p["instances"] for p in ev._coco_preditions])))
+
+
 def main():
     import sys
     if len(sys.argv) > 1:       # regenerate selected fixtures only: python -m oracle.gen_golden gen_train_step ...
@@ -520,6 +578,7 @@ def main():
     gen_cosine()
     gen_label_sample()
     gen_rpn_select()
+    gen_eval_formats()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

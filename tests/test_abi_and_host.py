@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -193,3 +194,19 @@ def test_teacher_vkv_variants_run_and_differ():
         assert ya.shape == yb.shape == (1, 10, 32) and not torch.allclose(ya, yb)
         yb.sum().backward()
         assert b.w_bg.grad is not None and b.attention.w_q.weight.grad is not None
+
+
+def test_eval_formats_match_reference_evaluator(golden):
+    """VOC text lines and COCO records vs the reference's own PascalVOCDetectionEvaluator.process."""
+    import json
+    from fewshotobjectdetection_imporove_via_text_feature_b200.evaluation import detection_formats as F
+    g = golden("eval_formats")
+    det = dict(boxes=torch.from_numpy(g["boxes"]), scores=torch.from_numpy(g["scores"]),
+               classes=torch.from_numpy(g["classes"]), counts=torch.from_numpy(g["counts"]).int())
+    ids = [str(s) for s in g["ids"]]
+    b, s, c, n = F.pack_batch(det)
+    assert np.array_equal(b, g["boxes"]) and np.array_equal(s, g["scores"]) and np.array_equal(n, g["counts"])
+    lines = F.voc_prediction_lines(ids, b, s, c, n)
+    want = json.loads(str(g["voc_lines"]))
+    assert {str(k): v for k, v in lines.items()} == want
+    assert F.coco_json_records(ids, b, s, c, n) == json.loads(str(g["coco"]))

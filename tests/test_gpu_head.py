@@ -169,3 +169,80 @@ def test_training_step_runs_and_backprops():
     assert base.grad is not None and torch.isfinite(base.grad).all() and float(base.grad.abs().sum()) > 0
     assert aff.weight.grad is not None and torch.isfinite(aff.weight.grad).all()
     assert m.attention.attention.w_q.weight.grad is not None
+
+
+def test_end_to_end_voc_ap_within_0p1():
+    """north_star: end-to-end VOC-style AP within 0.1.  Proposals -> head (bf16 fusion chain, CUDA post-processing) ->
+    detector_postprocess -> VOC text lines -> AP, against the fp32 CPU oracle taken through the same records.  Ground
+    truth = the oracle's own confident detections (threshold placed in the widest score gap), so the oracle scores
+    AP = 100 and every ranking flip, lost or spurious detection of the CUDA path costs AP."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling, ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200.evaluation import detection_formats as DF
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.postprocessing import detector_postprocess_batch
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, ShapeSpec
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ADDITION.NAME = "clip"
+    cfg.MODEL.B200.RES5_DTYPE = "float32"
+    torch.manual_seed(0)
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)}).eval()
+    with torch.no_grad():
+        m.box_predictor.cls_score.weight.mul_(60.0)
+        m.box_predictor.bbox_pred.weight.mul_(50.0)
+    gen = torch.Generator().manual_seed(12)
+    sizes = [(400, 512), (384, 500), (416, 480)]
+    out_sizes = [(333, 426), (384, 500), (832, 960)]
+    feat = torch.relu(torch.randn(3, 1024, 26, 32, generator=gen)) * 0.5
+    boxes = [synth_proposals(64, h, w, gen)[0] for (h, w) in sizes]
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    text = torch.cat([m.attention.embed, m.attention.bg_feature], 0)
+    dets_ref, _ = O.head_forward(feat, boxes, sizes, text, p)
+    ids = ["img%d" % i for i in range(3)]
+
+    def records(b, s, c, n):
+        lines = DF.voc_prediction_lines(ids, b, s, c, n)
+        return {cls: [(l.split()[0],) + tuple(float(v) for v in l.split()[1:]) for l in ls] for cls, ls in lines.items()}
+
+    # oracle side: postprocess + the same record format
+    T_ = 100
+    rb, rs_, rc, rn = np.zeros((3, T_, 4), np.float32), np.zeros((3, T_), np.float32), np.zeros((3, T_), np.int64), np.zeros(3, np.int64)
+    for i, d in enumerate(dets_ref):
+        bb, keep = O.detector_postprocess(d["boxes"], sizes[i], *out_sizes[i])
+        k = len(bb)
+        rb[i, :k], rs_[i, :k], rc[i, :k], rn[i] = bb.numpy(), d["scores"][keep].numpy(), d["classes"][keep].numpy(), k
+    ref = records(rb, rs_, rc, rn)
+    all_scores = np.sort(np.concatenate([rs_[i, :rn[i]] for i in range(3)]))
+    band = all_scores[(all_scores > 0.2) & (all_scores < 0.8)]
+    assert len(band) >= 2
+    gi = int(np.argmax(np.diff(band)))
+    tau = 0.5 * (band[gi] + band[gi + 1])
+    gts = {}
+    for cls, ds in ref.items():
+        for (img, sc, x1, y1, x2, y2) in ds:
+            if sc > tau:
+                gts.setdefault(cls, {}).setdefault(img, []).append([x1, y1, x2, y2])
+    assert len(gts) >= 3, "degenerate synthetic case: too few confident classes"
+
+    # CUDA side
+    m = m.cuda()
+    props = []
+    for b, s in zip(boxes, sizes):
+        inst = Instances(s)
+        inst.proposal_boxes = Boxes(b.cuda())
+        props.append(inst)
+    with torch.no_grad():
+        fp = m._pooled({"res4": feat.cuda()}, props)
+        att, _ = m.forward_att(fp)
+        offs = torch.tensor([0, 64, 128, 192], dtype=torch.int32, device="cuda")
+        det = ops.fast_rcnn_inference_device(att["pred_logits"], att["pred_bbox"], torch.cat(boxes).cuda(), offs,
+                                             ops.image_hw_tensor(sizes, "cuda"), 0.05, 0.5, 100)
+    detector_postprocess_batch(det, sizes, out_sizes)
+    got = records(*DF.pack_batch(det))
+
+    aps_ref, aps_got = [], []
+    for cls, g in gts.items():
+        g = {k: np.array(v) for k, v in g.items()}
+        aps_ref.append(O.voc_eval_class(ref.get(cls, []), g) * 100)
+        aps_got.append(O.voc_eval_class(got.get(cls, []), g) * 100)
+    assert min(aps_ref) > 99.999                         # the oracle against its own confident detections
+    assert abs(np.mean(aps_got) - np.mean(aps_ref)) <= 0.1, (aps_got, aps_ref)
