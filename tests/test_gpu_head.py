@@ -186,9 +186,6 @@ def test_end_to_end_voc_ap_within_0p1():
     cfg.MODEL.B200.RES5_DTYPE = "float32"
     torch.manual_seed(0)
     m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)}).eval()
-    with torch.no_grad():
-        m.box_predictor.cls_score.weight.mul_(60.0)
-        m.box_predictor.bbox_pred.weight.mul_(50.0)
     gen = torch.Generator().manual_seed(12)
     sizes = [(400, 512), (384, 500), (416, 480)]
     out_sizes = [(333, 426), (384, 500), (832, 960)]
@@ -196,7 +193,16 @@ def test_end_to_end_voc_ap_within_0p1():
     boxes = [synth_proposals(64, h, w, gen)[0] for (h, w) in sizes]
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     text = torch.cat([m.attention.embed, m.attention.bg_feature], 0)
-    dets_ref, _ = O.head_forward(feat, boxes, sizes, text, p)
+    _, mid = O.head_forward(feat, boxes, sizes, text, p)
+    # a random-init classifier puts every ROI in one class: sharpen it and centre its logits on the mean fused feature,
+    # so that the detections spread over (nearly) all 20 classes with scores across (0, 1)
+    with torch.no_grad():
+        m.box_predictor.cls_score.weight.mul_(60.0)
+        m.box_predictor.cls_score.bias.copy_(-(m.box_predictor.cls_score.weight @ mid["sim2stext"].mean(0)))
+        m.box_predictor.bbox_pred.weight.mul_(50.0)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    logits, deltas = O.output_layers(mid["feature_pooled"], mid["sim2stext"], p)
+    dets_ref = O.fast_rcnn_inference(logits, deltas, boxes, sizes, 0.05, 0.5, 100)
     ids = ["img%d" % i for i in range(3)]
 
     def records(b, s, c, n):
@@ -221,7 +227,7 @@ def test_end_to_end_voc_ap_within_0p1():
         for (img, sc, x1, y1, x2, y2) in ds:
             if sc > tau:
                 gts.setdefault(cls, {}).setdefault(img, []).append([x1, y1, x2, y2])
-    assert len(gts) >= 3, "degenerate synthetic case: too few confident classes"
+    assert len(gts) >= 8, "degenerate synthetic case: too few confident classes"
 
     # CUDA side
     m = m.cuda()
