@@ -335,6 +335,115 @@ extern "C" int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src
   return B200_OK;
 }
 
+// A7 (teacher attention): dst[r][:] = bf16(act(table[idx[r]][:])) — the per-ROI text feature of the teachers is a row of
+// the (K+1)-row class table picked by the ground-truth label (attentive_modules.py:380-401: one_hot(label) @ table)
+__global__ void __launch_bounds__(256)
+gather_rows_bf16_kernel(const float* __restrict__ table, int ld_table, const int64_t* __restrict__ idx, int num_rows_table,
+                        __nv_bfloat16* __restrict__ dst, int ld_dst, int rows, int cols4, int relu) {
+  const size_t total = (size_t)rows * cols4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols4), c = (int)(i % cols4) * 4;
+    long long t = idx[r];
+    t = t < 0 ? 0 : (t >= num_rows_table ? num_rows_table - 1 : t);
+    float4 v = *reinterpret_cast<const float4*>(table + (size_t)t * ld_table + c);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + (size_t)r * ld_dst + c) = o;
+  }
+}
+
+// A7 (teacher attention): per-class mean of feature rows and class counts.  The teachers attend over one key / value per
+// ROI of the batch, but ROIs of one class share their key, so softmax(Q K^T) V over R + 1 keys equals a (K+2)-key attention
+// whose class-c logit carries + log n_c and whose class-c value is the MEAN of the class's value rows (see
+// ops.teacher_attention_forward).  Two fixed-order stages: 128-row chunks accumulate per-class partial sums in shared
+// memory (a thread owns a column: no conflicts, no atomics), then the chunks are summed in order and divided by n_c.
+constexpr int kCmRows = 128, kCmCols = 256;
+__global__ void __launch_bounds__(kCmCols)
+class_sum_partial_kernel(const float* __restrict__ x, int ldx, const int64_t* __restrict__ labels, int R, int d, int C,
+                         float* __restrict__ partial /*[chunks][C][d]*/) {
+  extern __shared__ float s_acc[];                 // [C][kCmCols]
+  __shared__ int s_lab[kCmRows];
+  const int chunk = blockIdx.y, col = blockIdx.x * kCmCols + threadIdx.x;
+  const int r0 = chunk * kCmRows, nr = min(kCmRows, R - r0);
+  for (int c = 0; c < C; ++c) s_acc[c * kCmCols + threadIdx.x] = 0.f;
+  if ((int)threadIdx.x < nr) {
+    long long l = labels[r0 + threadIdx.x];
+    s_lab[threadIdx.x] = (int)(l < 0 ? 0 : (l >= C ? C - 1 : l));
+  }
+  __syncthreads();
+  if (col < d)
+    for (int r = 0; r < nr; ++r) s_acc[s_lab[r] * kCmCols + threadIdx.x] += x[(size_t)(r0 + r) * ldx + col];
+  if (col < d)
+    for (int c = 0; c < C; ++c) partial[((size_t)chunk * C + c) * d + col] = s_acc[c * kCmCols + threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256)
+class_mean_final_kernel(const float* __restrict__ partial, const int64_t* __restrict__ labels, int R, int d, int C, int chunks,
+                        float* __restrict__ mean /*[C][d]*/, float* __restrict__ counts /*[C]*/) {
+  __shared__ int s_cnt;
+  const int c = blockIdx.y;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int local = 0;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    long long l = labels[r];
+    l = l < 0 ? 0 : (l >= C ? C - 1 : l);
+    local += (l == c);
+  }
+  if (local) atomicAdd(&s_cnt, local);             // integer: order independent
+  __syncthreads();
+  const int n = s_cnt;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < d) {
+    float acc = 0.f;
+    for (int k = 0; k < chunks; ++k) acc += partial[((size_t)k * C + c) * d + col];
+    mean[(size_t)c * d + col] = n > 0 ? acc / (float)n : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[c] = (float)n;
+}
+
+extern "C" size_t b200_class_mean_rows_workspace_bytes(int R, int d, int C) {
+  if (R <= 0 || d <= 0 || C <= 0) return 256;
+  return align_up((size_t)ceil_div(R, kCmRows) * C * d * sizeof(float), 256);
+}
+
+extern "C" int b200_class_mean_rows(const float* x, int ldx, const int64_t* labels, int R, int d, int C, float* mean,
+                                    float* counts, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(x && labels && mean && counts, "class_mean_rows: null tensor");
+  B200_CHECK_ARG(R > 0 && d > 0 && C > 0 && (size_t)C * kCmCols * sizeof(float) <= 200 * 1024, "class_mean_rows: bad shape");
+  if (!workspace || workspace_bytes < b200_class_mean_rows_workspace_bytes(R, d, C)) {
+    set_error("class_mean_rows: workspace too small");
+    return B200_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = ceil_div(R, kCmRows);
+  const size_t smem = (size_t)C * kCmCols * sizeof(float);
+  if (smem > 48 * 1024)
+    B200_CUDA_CALL(cudaFuncSetAttribute(class_sum_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  class_sum_partial_kernel<<<dim3(ceil_div(d, kCmCols), chunks), kCmCols, smem, st>>>(x, ldx, labels, R, d, C, (float*)workspace);
+  B200_CUDA_LAUNCH_CHECK("class_mean_rows(partial)");
+  class_mean_final_kernel<<<dim3(ceil_div(d, 256), C), 256, 0, st>>>((const float*)workspace, labels, R, d, C, chunks, mean, counts);
+  B200_CUDA_LAUNCH_CHECK("class_mean_rows(final)");
+  return B200_OK;
+}
+
+extern "C" int b200_gather_rows_bf16(const float* table, int ld_table, int num_rows_table, const int64_t* idx, void* dst,
+                                     int ld_dst, int rows, int cols, int relu, b200_stream_t stream) {
+  B200_CHECK_ARG(table && idx && dst, "gather_rows_bf16: null tensor");
+  B200_CHECK_ARG(rows >= 0 && cols >= 0 && num_rows_table > 0 && cols % 4 == 0 && ld_table % 4 == 0 && ld_dst % 4 == 0,
+                 "gather_rows_bf16: cols/ld must be multiples of 4");
+  if (rows == 0 || cols == 0) return B200_OK;
+  const size_t total = (size_t)rows * (cols / 4);
+  const int blocks = (int)min((size_t)kNumSMs * 8, (total + 255) / 256);
+  gather_rows_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, ld_table, idx, num_rows_table,
+                                                                   (__nv_bfloat16*)dst, ld_dst, rows, cols / 4, relu);
+  B200_CUDA_LAUNCH_CHECK("gather_rows_bf16");
+  return B200_OK;
+}
+
 extern "C" int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,
                               b200_stream_t stream) {
   B200_CHECK_ARG(src && dst, "cast_bf16: null tensor");

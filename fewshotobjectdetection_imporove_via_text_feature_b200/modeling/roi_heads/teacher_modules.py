@@ -6,8 +6,11 @@ names (`attention.*`, `proj_k`, `proj2`, `proj_visual`, `proj_value`, `w_bg`).
 
 These modules are *teachers*: they consume ground-truth labels (the text key of ROI i is the embedding of its GT
 class), so they only run while training or in the reference's test-with-GT mode, and their key set is per-ROI: the
-attention matrix is (R, R+1) over the ROIs of the local batch.  They run as differentiable torch expressions on
-the GPU (their backward is needed), sharing `SingleHeadSiameseAttention` with the student path.
+attention matrix is (R, R+1) over the ROIs of the local batch.  With autograd on (the teacher itself is being trained)
+they run as differentiable torch expressions on the GPU, sharing `SingleHeadSiameseAttention` with the student path.
+Without autograd — the frozen teacher of student training, test-with-GT — `LV_attention` / `LV_attention_VKV` take the
+fused path `ops.teacher_attention_forward`: ROIs of one class share their key, so the dense attention collapses to a
+(K+2)-key attention (logit + log n_c, per-class mean values) and runs on the student's tcgen05 / fused kernels.
 
 Where the checked-in reference is broken (`LV_attention_VKV.forward` calls
 `forward_language_model(visual_feat, text)` against a one-argument signature and concatenates a 2-d with a 3-d
@@ -17,6 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ... import ops
 from ...utils.class_embedding import get_class_embed, get_class_name
 from .attentive_modules import SingleHeadSiameseAttention, _init_parameters
 
@@ -61,7 +65,21 @@ class LV_attention(nn.Module):
         # one_hot(label) @ table == table[label]
         return {}, {"text_feat": self.class_table()[label]}
 
+    _vkv = False
+
+    def _frozen_forward(self, visual_feat, text):
+        """Forward without autograd (frozen teacher while the student trains, test-with-GT): the class-collapsed fused
+        path, ops.teacher_attention_forward."""
+        if not hasattr(self, "_plan"):
+            self._plan = ops.TeacherFusionWeights()
+        w = self._plan.refresh({k: v for k, v in self.named_parameters()}, (self.embed,))
+        z, zb = ops.teacher_attention_forward(visual_feat, text, w, self._vkv)
+        t = w["table"][text]
+        return {}, {"text_feat": t[None, :] if self._vkv else t, "sim2stext": z[None, :], "sim2stext_bf16": zb}
+
     def forward(self, visual_feat, text, num_preds_per_image=None):
+        if visual_feat.is_cuda and not torch.is_grad_enabled():
+            return self._frozen_forward(visual_feat, text)
         loss, output = self.forward_language_model(text)
         t = output["text_feat"]
         value = F.relu(self.proj_k(torch.cat([visual_feat, t], dim=-1)))
@@ -72,8 +90,11 @@ class LV_attention(nn.Module):
 
 class LV_attention_VKV(LV_attention):
     """Query and value are both the fused [visual ‖ text] projection; keys are the GT-class text features."""
+    _vkv = True
 
     def forward(self, visual_feat, text, num_preds_per_image=None):
+        if visual_feat.is_cuda and not torch.is_grad_enabled():
+            return self._frozen_forward(visual_feat, text)
         loss, output = self.forward_language_model(text)
         t = output["text_feat"][None, :]
         value = F.relu(self.proj_k(torch.cat([visual_feat[None, :], t], dim=2)))

@@ -614,7 +614,7 @@ class TextFusionWeights:
         return w
 
 
-def text_fusion_forward(x, w, fold_query=True):
+def text_fusion_forward(x, w, fold_query=True, score_bias=None):
     """A1..A6 on the device.  x (R,d) fp32.  Returns (sim2stext fp32 (R,d), sim2stext bf16, attn (R,K+2),
     x_bf16 view (R,d) with row stride 2d).  fold_query: compute the attention scores as x (Kp Wq)^T (one skinny
     GEMM against the cached folded operand) instead of Q = x Wq^T followed by Q Kp^T — same algebra, 8.4 MFLOP/ROI
@@ -629,7 +629,7 @@ def text_fusion_forward(x, w, fold_query=True):
     p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
     p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
     if fold_query:
-        s = gemm_bf16(xb, w["kq"])
+        s = gemm_bf16(xb, w["kq"], score_bias)       # score_bias (L,): per-key logit offset (teacher attention: log n_c)
         attn = text_attention(None, x, None, w["vp"], p1, p2, scores=s)
     else:
         q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)
@@ -642,3 +642,97 @@ def text_fusion_forward(x, w, fold_query=True):
     y2 = gemm_bf16(hdn, w["ffn.linear2.weight"], w["ffn.linear2.bias"])
     z, zb = residual_layernorm(y, y2, w["ffn.norm3.weight"], w["ffn.norm3.bias"], 1e-5, relu=True)
     return z, zb, attn, xb
+
+
+# ---------------------------------------------------------------------------------------------------
+# A7: teacher ("language-vision") attention, forward direction — attentive_modules.py:297-487
+# ---------------------------------------------------------------------------------------------------
+def gather_rows_bf16(table, idx, dst, relu=False):
+    """dst (rows, cols) bf16 view <- bf16(act(table[idx])) ; table (T, cols) fp32, idx (rows,) int64."""
+    rows, cols = dst.shape
+    assert table.dtype == torch.float32 and table.stride(1) == 1 and dst.dtype == torch.bfloat16 and dst.stride(1) == 1
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.numel() == rows and table.shape[1] == cols
+    _lib.call("b200_gather_rows_bf16", table.data_ptr(), table.stride(0), table.shape[0], idx.data_ptr(), dst.data_ptr(),
+              dst.stride(0), rows, cols, int(relu), _stream())
+    return dst
+
+
+def class_mean_rows(x, labels, num_classes):
+    """(mean (C,d) fp32, counts (C,) fp32): per-class mean of the rows of x (R,d) fp32, fixed summation order."""
+    _require_cuda(x, labels)
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and labels.dtype == torch.int64 and labels.is_contiguous()
+    R, d = x.shape
+    mean = torch.empty((num_classes, d), dtype=torch.float32, device=x.device)
+    counts = torch.empty(num_classes, dtype=torch.float32, device=x.device)
+    nbytes = _lib.lib().b200_class_mean_rows_workspace_bytes(R, d, num_classes)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    _lib.call("b200_class_mean_rows", x.data_ptr(), x.stride(0), labels.data_ptr(), R, d, num_classes, mean.data_ptr(),
+              counts.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return mean, counts
+
+
+class TeacherFusionWeights:
+    """bf16 / fp32 operand copies of a teacher module (LV_attention / LV_attention_VKV) and its label-independent text
+    side: class table `proj2([embed; w_bg])`, projected keys + dummy, folded query operand.  Same caching rule as
+    TextFusionWeights (constant while the teacher is frozen — the student-training and test-with-GT cases)."""
+
+    def __init__(self):
+        self.key = None
+        self.w = {}
+
+    def refresh(self, named, text_parts):
+        params = [named[k] for k in sorted(named)] + list(text_parts)
+        key = TextFusionWeights._version(params)
+        if key == self.key:
+            return self.w
+        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        w = {}
+        for name in ("linear1.0.weight", "linear2.0.weight", "linear3.weight", "ffn.linear1.weight", "ffn.linear2.weight"):
+            w[name] = bf(named["attention." + name])
+        for name in ("linear1.0.bias", "linear2.0.bias", "linear3.bias", "ffn.linear1.bias", "ffn.linear2.bias",
+                     "ffn.norm3.weight", "ffn.norm3.bias"):
+            w[name] = f32(named["attention." + name])
+        w["proj_k.weight"], w["proj_k.bias"] = bf(named["proj_k.weight"]), f32(named["proj_k.bias"])
+        w["w_v"] = f32(named["attention.w_v.weight"])
+        # text side: K+1 rows; plain torch ops, cached
+        table = torch.nn.functional.linear(torch.cat([f32(text_parts[0]), f32(named["w_bg"])], 0),
+                                           f32(named["proj2.weight"]), f32(named["proj2.bias"]))
+        w["table"] = table.contiguous()
+        kp = torch.nn.functional.linear(torch.relu(table), f32(named["attention.w_k.weight"]))
+        kp = torch.cat([kp, f32(named["attention.dummy"]).reshape(1, -1)], 0)
+        d = kp.shape[1]
+        w["kq"] = bf((kp @ f32(named["attention.w_q.weight"])) / math.sqrt(d))
+        self.key, self.w = key, w
+        return w
+
+
+def teacher_attention_forward(x, labels, w, vkv):
+    """LV_attention (vkv=False) / LV_attention_VKV (vkv=True) forward on the device, no autograd.
+
+    The reference attends every ROI over one key / value per ROI of the batch — a dense (R, R+1) attention,
+    2 R (R+1) d 2 FLOP (attentive_modules.py:403-437, :452-487).  Keys are relu(table[label_j]): ROIs of one class
+    share their key, so with n_c ROIs of class c and scores s_ic = q_i . k_c / sqrt(d)
+        softmax_j(S)_ij V_j  summed over j  ==  sum_c softmax_c(s_ic + log n_c) . mean_{j in c} V_j      (+ the dummy key)
+    i.e. a (K+2)-key attention: logits get + log n_c, values are per-class means (absent classes: -inf).  What remains
+    is the student's chain (ops.text_fusion_forward) with per-batch value rows; no R x R matrix is ever formed.
+    x (R,d) fp32 pooled features, labels (R,) int64 in [0, K].  Returns (sim2stext fp32 (R,d), bf16 copy)."""
+    from .train_ops import skinny
+    _require_cuda(x, labels)
+    x = x.float().contiguous()
+    labels = labels.to(torch.int64).contiguous()
+    R, d = x.shape
+    table = w["table"]
+    C = table.shape[0]
+    cat = torch.empty((R, 2 * d), dtype=torch.bfloat16, device=x.device)          # [x | t]  (:417, :466)
+    cast_bf16_into(x, cat[:, :d])
+    gather_rows_bf16(table, labels, cat[:, d:])
+    val = gemm_bf16(cat, w["proj_k.weight"], w["proj_k.bias"], relu=True)         # value = relu(proj_k([x | t]))
+    vmean, counts = class_mean_rows(val, labels, C)
+    vp = torch.cat([skinny("nt", vmean, w["w_v"]), vmean.new_zeros(1, d)], 0).contiguous()
+    bias = torch.cat([torch.where(counts > 0, torch.log(counts.clamp(min=1.0)), counts.new_full((), -1e30)),
+                      counts.new_zeros(1)]).contiguous()
+    wt = dict(w)
+    wt["vp"] = vp
+    z, zb, _, _ = text_fusion_forward(val if vkv else x, wt, True, score_bias=bias)
+    return z, zb

@@ -323,6 +323,17 @@ B200_API int b200_detector_postprocess(float* boxes, float* scores, int64_t* cla
                               int32_t* counts, const float* scale_xy, const float* out_hw, int N, int max_keep,
                               b200_stream_t stream);
 
+/* A7  teacher attention (attentive_modules.py:380-401 `one_hot(label) @ table`): dst[r][:] = bf16(act(table[idx[r]][:])),
+ * table (num_rows_table, cols) fp32, idx (rows) int64 clamped to the table, dst bf16 with row stride ld_dst. */
+B200_API int b200_gather_rows_bf16(const float* table, int ld_table, int num_rows_table, const int64_t* idx, void* dst,
+                          int ld_dst, int rows, int cols, int relu, b200_stream_t stream);
+
+/* A7  teacher attention: mean (C,d) = per-class mean of the rows of x (R,d) fp32 (row stride ldx) grouped by labels (R)
+ * int64 in [0, C), counts (C) fp32 = rows per class (classes without rows: mean 0).  Fixed summation order. */
+B200_API size_t b200_class_mean_rows_workspace_bytes(int R, int d, int C);
+B200_API int b200_class_mean_rows(const float* x, int ldx, const int64_t* labels, int R, int d, int C, float* mean,
+                         float* counts, void* workspace, size_t workspace_bytes, b200_stream_t stream);
+
 /* fp32 -> bf16 cast with row stride (builds the [o1|o2|x] concat buffer of attentive_modules.py:172-174
  * in place, without a torch.cat) */
 B200_API int b200_cast_bf16(const float* src, int ld_src, void* dst, int ld_dst, int rows, int cols,

@@ -220,3 +220,57 @@ def test_gemm_res5_sized_problem_with_mask():
     ref = torch.where(mask > 0, (a @ b.t()).float(), torch.zeros((), device="cuda"))
     assert rel_err(out.float(), ref) < 4e-3
     assert float(out[mask <= 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cls_name", ["LV_attention", "LV_attention_VKV"])
+@pytest.mark.parametrize("R,d,K", [(1024, 2048, 20), (203, 256, 7)])
+def test_teacher_attention_fused_forward_vs_dense_torch(cls_name, R, d, K):
+    """A7: the class-collapsed fused forward (no (R, R+1) matrix) vs the module's dense fp32 torch expression
+    (attentive_modules.py:403-437 / :452-487 semantics), bf16 bar 2e-2.  Sharpened attention weights so that the
+    softmax — and with it the + log n_c / class-mean identity — matters; one class has no ROI at all."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads import teacher_modules as tm
+    torch.manual_seed(3)
+    gen = torch.Generator().manual_seed(5)
+    embed = torch.randn(K, 300, generator=gen)
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    cfg = config.get_cfg()
+    cfg.MODEL.ADDITION.NAME = "glove"
+    m = getattr(tm, cls_name)(d, cfg=cfg, class_embed=embed).cuda().eval()
+    with torch.no_grad():
+        m.attention.w_q.weight.mul_(12.0)
+        m.attention.w_k.weight.mul_(12.0)
+    x = torch.relu(torch.randn(R, d, generator=gen)).cuda()
+    labels = torch.randint(0, K, (R,), generator=gen)
+    labels[torch.rand(R, generator=gen) < 0.6] = K                       # background majority
+    labels[labels == 2] = 3                                              # class 2 absent
+    labels = labels.cuda()
+    with torch.enable_grad():
+        _, ref = m(x, labels)                                            # dense torch path
+    with torch.no_grad():
+        _, out = m(x, labels)                                            # fused path
+    got, want = out["sim2stext"], ref["sim2stext"].detach()
+    assert got.shape == want.shape == (1, R, d)
+    rel = float((got - want).norm() / want.norm())
+    assert rel < 2e-2, rel
+    assert out["text_feat"].shape == ref["text_feat"].shape
+    torch.testing.assert_close(out["text_feat"], ref["text_feat"].detach(), rtol=1e-5, atol=1e-5)
+
+
+def test_class_mean_rows_and_gather_rows():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(8)
+    R, d, C = 777, 320, 9
+    x = torch.randn(R, d, generator=gen).cuda()
+    lab = torch.randint(0, C - 1, (R,), generator=gen).cuda()           # last class empty
+    mean, cnt = ops.class_mean_rows(x, lab, C)
+    ref = torch.zeros(C, d, dtype=torch.float64, device="cuda").index_add_(0, lab, x.double())
+    n = torch.bincount(lab, minlength=C)
+    assert torch.equal(cnt.long(), n)
+    torch.testing.assert_close(mean.double(), ref / n.clamp(min=1)[:, None], rtol=1e-5, atol=1e-6)
+    assert float(mean[C - 1].abs().max()) == 0.0
+    m2, _ = ops.class_mean_rows(x, lab, C)
+    assert torch.equal(mean, m2)                                         # fixed summation order
+    table = torch.randn(C, d, generator=gen).cuda()
+    dst = torch.zeros(R, 2 * d, dtype=torch.bfloat16, device="cuda")
+    ops.gather_rows_bf16(table, lab, dst[:, d:], relu=True)
+    assert torch.equal(dst[:, d:], torch.relu(table[lab]).to(torch.bfloat16)) and float(dst[:, :d].abs().max()) == 0.0
