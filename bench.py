@@ -470,6 +470,7 @@ def main():
                       "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
             del pooled_full, gfull, fmap
         gemm_alone = {"ms": 0.0, "flop": 0.0, "calls": len(gemm_cases)}
+        gemm_ops = []
         for (M_, N_, K_, obf, d2_, relu_, acc_, msk_, bias_) in gemm_cases:
             ld = (N_ + 7) // 8 * 8
             a_ = torch.randn(M_, K_, device=dev).to(torch.bfloat16)
@@ -478,6 +479,7 @@ def main():
             o2_ = torch.empty(M_, ld, device=dev, dtype=torch.bfloat16)[:, :N_] if d2_ else None
             m_ = torch.randn(M_, ld, device=dev).to(torch.bfloat16)[:, :N_] if msk_ else None
             bi_ = torch.randn(N_, device=dev) if bias_ else None
+            gemm_ops.append((a_, b_, bi_, relu_, o_, o2_, acc_, m_))
             ts_ = []
             for _ in range(4):
                 e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -488,6 +490,23 @@ def main():
                 ts_.append(e0_.elapsed_time(e1_))
             gemm_alone["ms"] += float(np.median(ts_[1:]))
             gemm_alone["flop"] += 2.0 * M_ * N_ * K_
+        # the same launches BACK TO BACK on the launching stream, one event pair around the whole sequence, L2 flushed
+        # before it: the sum of the kernels' durations without the cross-stream SM sharing of the step (where the
+        # weight-gradient GEMMs run under res5's kernels by design) and without per-launch host latency
+        gemm_b2b = {"ms": float("nan"), "flop": gemm_alone["flop"]}
+        if gemm_ops:
+            ts_ = []
+            for it in range(6):
+                flush.fill_(it)
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0_.record()
+                for (a_, b_, bi_, relu_, o_, o2_, acc_, m_) in gemm_ops:
+                    train_ops.gemm_ex(a_, b_, bi_, relu=relu_, out=o_, out2=o2_, accumulate=acc_, mask=m_)
+                e1_.record()
+                torch.cuda.synchronize()
+                ts_.append(e0_.elapsed_time(e1_))
+            gemm_b2b["ms"] = float(np.median(ts_[2:]))
+        del gemm_ops
         # ---- end to end: pinned host inputs -> device, result -> host, every step ------------------------------
         # The public call with HOST buffers.  Two device input buffers: the upload of step i+1 (copy stream) overlaps
         # the compute of step i; every step's inputs are copied from pinned memory and every step's result (losses /
@@ -582,12 +601,19 @@ def main():
                 gem["calls"] += prof[name]["calls_per_step"]
         gemm_tf = gem["flop"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] else float("nan")
         alone_tf = gemm_alone["flop"] / (gemm_alone["ms"] * 1e-3) / 1e12 if gemm_alone["ms"] else float("nan")
+        b2b_ok = gemm_b2b["ms"] == gemm_b2b["ms"] and gemm_b2b["ms"] > 0
+        b2b_tf = gemm_b2b["flop"] / (gemm_b2b["ms"] * 1e-3) / 1e12 if b2b_ok else gemm_tf
         gemm_roof = {"kernel": "gemm_bf16_tcgen05_kernel<BN> (all %d launches of the step, rank 0)" % round(gem["calls"]),
-                     "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": gemm_traffic,
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback",
-                     "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gem["ms"],
-                     "timing": "CUDA events recorded around every GEMM entry-point call on the launching stream, summed per step, median over "
-                               "%d profiled eager steps (the weight-gradient GEMMs of the fine-tune step share the SMs with res5's kernels there)" % prof_steps,
+                     "bound": "tensor", "achieved": b2b_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": b2b_tf / tc_peak, "traffic": gemm_traffic,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long sequence)" if peaks else "fallback",
+                     "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gemm_b2b["ms"] if b2b_ok else gem["ms"],
+                     "timing": "every GEMM launch of one step (same shapes / epilogues, fresh operands) issued back to back on the launching "
+                               "stream, ONE CUDA event pair around the sequence, L2 flushed before it, median of 4: the sum of the kernels' "
+                               "durations.  Inside the step the weight-gradient GEMMs run on a side stream under res5's kernels by design, so "
+                               "per-call event pairs there also measure that sharing: see in_step",
+                     "in_step": {"achieved": gemm_tf, "ms_per_step": gem["ms"], "frac": gemm_tf / tc_peak,
+                                 "note": "CUDA events around every GEMM entry-point call on its launching stream, summed per step, median over "
+                                         "%d profiled eager steps (SMs shared with the other streams' kernels)" % prof_steps},
                      "launched_alone": {"achieved": alone_tf, "ms_per_step": gemm_alone["ms"],
                                         "note": "every GEMM shape / epilogue of the step re-issued alone with a synchronize between launches: "
                                                 "includes the launch latency that back-to-back launches hide"}}
