@@ -436,7 +436,8 @@ extern "C" int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb,
   else if (N <= 64) bn = 64;
   else if (mt * ceil_div(N, 256) >= 120) bn = 256;
   else if (mt * ceil_div(N, 128) >= 100 || N <= 128) bn = 128;
-  else bn = 64;
+  else if (mt * ceil_div(N, 64) >= kNumSMs / 2) bn = 64;
+  else bn = 32;   // few tiles (the M <= 128 weight-gradient products, K = R): twice the CTAs streaming the K panel
   switch (bn) {
     case 32: return launch_gemm<32>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);
     case 64: return launch_gemm<64>(A, lda, B, ldb, bias, D, ldd, out_dtype, D2, ldd2, M, N, K, relu, accumulate, mask, ldmask, st);

@@ -53,6 +53,7 @@ def test_rpn_select_training_raises_on_nonfinite(golden):
     (1, [50 * 84 * 15], (800, 1333), 12000, 2000, 0.01),     # 800 x 1333 map, quantised logits: many exact ties
     (2, [9000, 2300, 600, 150, 40], (600, 800), 1000, 1000, 0.0),   # five levels, per-level top-k, level-batched NMS
     (1, [700], (600, 800), 6000, 1000, 0.0),                 # fewer anchors than pre_nms_topk
+    (1, [20000], (600, 800), 14000, 1500, 0.0),              # a level slice beyond the cluster kernel's 12288 boxes: fallback kernel
 ])
 def test_rpn_select_full_size_vs_oracle(N, sizes, hw, pre, post, quant):
     gen = torch.Generator().manual_seed(5 + len(sizes) + pre)
