@@ -28,3 +28,22 @@ def synth_proposals(n, h, w, gen, n_obj=4):
     b[:, 0] = torch.minimum(b[:, 0], b[:, 2] - 1.0).clamp(min=0)
     b[:, 1] = torch.minimum(b[:, 1], b[:, 3] - 1.0).clamp(min=0)
     return b, objs
+
+
+def synth_rpn_outputs(N, level_sizes, h, w, gen, quant=0.0):
+    """Decoded anchors + objectness the way an RPN head leaves them: boxes partly outside the image, clusters around a
+    few objects (so NMS suppresses), logits optionally quantised (exact ties)."""
+    props, logits = [], []
+    for A in level_sizes:
+        pb, pl = [], []
+        for _ in range(N):
+            b, objs = synth_proposals(A, h, w, gen, n_obj=6)
+            b = b + torch.randn(A, 4, generator=gen) * 6.0 - 3.0           # un-clipped, a few inverted / outside
+            l = torch.randn(A, generator=gen) * 2.0
+            if quant > 0:
+                l = torch.round(l / quant) * quant
+            pb.append(b)
+            pl.append(l)
+        props.append(torch.stack(pb))
+        logits.append(torch.stack(pl))
+    return props, logits

@@ -43,7 +43,7 @@ def sd_to_np(sd, prefix=""):
     return {prefix + k: v.detach().cpu().numpy() for k, v in sd.items()}
 
 
-from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals  # noqa: E402,F401
+from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals, synth_rpn_outputs  # noqa: E402,F401
 
 
 def gen_gdl():
@@ -434,25 +434,6 @@ def gen_cosine():
     t = torch.randn(21, 64, generator=gen)
     np.savez(os.path.join(OUT, "cosine.npz"), a=a.numpy(), t=t.numpy(), sim=mm.sim_matrix(a, t).numpy(),
              bsim=mm.bsim_matrix(a[None], t[None], tau=20.0)[0].numpy(), tau=np.float32(20.0))
-
-
-def synth_rpn_outputs(N, level_sizes, h, w, gen, quant=0.0):
-    """Decoded anchors + objectness the way an RPN head leaves them: boxes partly outside the image, clusters around a
-    few objects (so NMS suppresses), logits optionally quantised (exact ties)."""
-    props, logits = [], []
-    for A in level_sizes:
-        pb, pl = [], []
-        for _ in range(N):
-            b, objs = synth_proposals(A, h, w, gen, n_obj=6)
-            b = b + torch.randn(A, 4, generator=gen) * 6.0 - 3.0           # un-clipped, a few inverted / outside
-            l = torch.randn(A, generator=gen) * 2.0
-            if quant > 0:
-                l = torch.round(l / quant) * quant
-            pb.append(b)
-            pl.append(l)
-        props.append(torch.stack(pb))
-        logits.append(torch.stack(pl))
-    return props, logits
 
 
 def gen_rpn_select():

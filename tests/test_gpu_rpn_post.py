@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import oracle as O
-from oracle.gen_golden import synth_rpn_outputs
+from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_rpn_outputs
 
 
 def T(a):

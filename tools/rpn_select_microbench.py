@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.proposal_generator import (  # noqa: E402
     find_top_rpn_proposals, find_top_rpn_proposals_device)
-from oracle.gen_golden import synth_rpn_outputs  # noqa: E402
+from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_rpn_outputs  # noqa: E402
 
 
 def torch_path(props, logits, image_sizes, thr, pre, post, nms):
