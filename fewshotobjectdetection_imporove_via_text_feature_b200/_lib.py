@@ -53,6 +53,10 @@ SIGNATURES = {
     "b200_spatial_mean": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_mean_bwd_relu_mask": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_add_relu_mask": (c_int, [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "b200_spatial_mean_bits": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_pack_relu_bits": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200_mean_bwd_relu_bits": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_add_relu_bits": (c_int, [c_void_p] * 4 + [c_size_t, c_void_p]),
     "b200_sgd_momentum": (c_int, [c_void_p] * 3 + [c_size_t] + [c_float] * 3 + [c_void_p]),
     "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
@@ -80,7 +84,7 @@ KERNELS_PER_CALL = {
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_layernorm_param_grads": 3, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
     "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1, "b200_label_sample_proposals": 1,
-    "b200_rpn_select_proposals": 5, "b200_gather_rows_bf16": 1, "b200_class_mean_rows": 2, "b200_detector_postprocess": 1,
+    "b200_rpn_select_proposals": 5, "b200_gather_rows_bf16": 1, "b200_spatial_mean_bits": 1, "b200_pack_relu_bits": 1, "b200_mean_bwd_relu_bits": 1, "b200_add_relu_bits": 1, "b200_class_mean_rows": 2, "b200_detector_postprocess": 1,
 }
 LAUNCHES = 0
 # bench.py sets PROFILE = {} to have a CUDA event pair recorded around every entry-point call (name -> [(e0, e1, tag)]);

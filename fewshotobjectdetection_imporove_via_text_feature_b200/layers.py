@@ -141,22 +141,50 @@ class _FrozenRes5MeanFn(torch.autograd.Function):
         from . import train_ops
         saved = []
         y = x
+        # 1-bit ReLU masks of activations whose only use in the backward is `> 0` (csrc/res5_elem.cu): the last one falls
+        # out of the spatial mean for free (default); RELU_BITS = 2 also packs the others on a side stream
+        last_bits = int(train_ops.RELU_BITS) >= 1 and ctx.needs_input_grad[0]
+        use_bits = int(train_ops.RELU_BITS) >= 2 and ctx.needs_input_grad[0] and _nhwc_dense(x)
+        cur = torch.cuda.current_stream()
+        side = train_ops.mask_stream(x.device) if use_bits else None
+        bits = []
+
+        def pack_async(t):
+            b = torch.empty(t.numel() // 8, dtype=torch.uint8, device=t.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                train_ops.pack_relu_bits(t, b)
+            return b
+
         for i, (s1, ssc, conv2_args, has_sc) in enumerate(metas):
             w1, b1, w2, b2, w3, b3, wsc, bsc = params[8 * i: 8 * i + 8]
             stride2, pad2, dil2, groups2 = conv2_args
             out1 = torch.cudnn_convolution_relu(y, w1, b1, s1, (0, 0), (1, 1), 1)
+            use_bits = use_bits and _nhwc_dense(out1)
+            m1 = pack_async(out1) if use_bits else None
             out2 = torch.cudnn_convolution_relu(out1, w2, b2, stride2, pad2, dil2, groups2)
+            m2 = pack_async(out2) if use_bits and _nhwc_dense(out2) else None
             if has_sc:
                 res = F.conv2d(y, wsc, None, ssc)
                 bias3 = b3 if bsc is None else b3 + bsc
             else:
                 res, bias3 = y, b3
             out = torch.cudnn_convolution_add_relu(out2, w3, res, 1.0, bias3, (1, 1), (0, 0), (1, 1), 1)
+            my = pack_async(out) if use_bits and m2 is not None and i + 1 < len(metas) and _nhwc_dense(out) else None
             saved += [y, out1, out2, w1, w2, w3, wsc if has_sc else w1]
+            bits += [m1 if m2 is not None else None, m2, my]
             y = out
-        pooled = train_ops.spatial_mean(y)
+        if last_bits and _nhwc_dense(y):
+            pooled, mlast = train_ops.spatial_mean_bits(y)
+        else:
+            pooled, mlast = train_ops.spatial_mean(y), None
+        if side is not None:
+            cur.wait_stream(side)        # the masks (and the activations they were read from) are safe to free from here on
         ctx.save_for_backward(y, *saved)
         ctx.metas = metas
+        ctx.bits = (bits, mlast)
         return pooled
 
     @staticmethod
@@ -164,6 +192,7 @@ class _FrozenRes5MeanFn(torch.autograd.Function):
         from . import train_ops
         out_last, *saved = ctx.saved_tensors
         metas = ctx.metas
+        bits, mlast = ctx.bits
         relu_bwd = torch.ops.aten.threshold_backward
 
         def dgrad(g_out, inp, w, stride=(1, 1), pad=(0, 0), dil=(1, 1), groups=1):
@@ -171,19 +200,35 @@ class _FrozenRes5MeanFn(torch.autograd.Function):
             return torch.ops.aten.convolution_backward(g_out, inp, w, None, list(stride), list(pad), list(dil), False, [0, 0],
                                                        groups, [True, False, False])[0]
 
-        g = train_ops.mean_bwd_relu_mask(gp, out_last)
+        def relu_back(g_raw, act, m):
+            if m is not None and _nhwc_dense(g_raw):
+                return train_ops.add_relu_bits(g_raw, None, m, inplace=True)
+            return relu_bwd(g_raw, act, 0)
+
+        g = train_ops.mean_bwd_relu_mask(gp, out_last) if mlast is None else train_ops.mean_bwd_relu_bits(gp, mlast, out_last)
         for i in reversed(range(len(metas))):
             s1, ssc, (stride2, pad2, dil2, groups2), has_sc = metas[i]
             x, out1, out2, w1, w2, w3, wsc = saved[7 * i: 7 * i + 7]
-            g2 = relu_bwd(dgrad(g, out2, w3), out2, 0)
-            g1 = relu_bwd(dgrad(g2, out1, w2, stride2, pad2, dil2, groups2), out1, 0)
+            m1, m2, _ = bits[3 * i: 3 * i + 3]
+            mx = bits[3 * (i - 1) + 2] if i > 0 else None
+            g2 = relu_back(dgrad(g, out2, w3), out2, m2)
+            g1 = relu_back(dgrad(g2, out1, w2, stride2, pad2, dil2, groups2), out1, m1)
             gx = dgrad(g1, x, w1, s1)
             # fan-in of the two branches (shortcut convolution or identity); for i > 0 the block input is the previous
             # block's post-ReLU output, whose mask is applied in the same pass
             gsc = dgrad(g, x, wsc, ssc) if has_sc else g
             cl = torch.channels_last
-            g = train_ops.add_relu_mask(gx.contiguous(memory_format=cl), gsc.contiguous(memory_format=cl), x if i > 0 else None)
+            gx, gsc = gx.contiguous(memory_format=cl), gsc.contiguous(memory_format=cl)
+            if i > 0 and mx is not None:
+                g = train_ops.add_relu_bits(gx, gsc, mx)
+            else:
+                g = train_ops.add_relu_mask(gx, gsc, x if i > 0 else None)
         return (g, None) + (None,) * (8 * len(metas))
+
+
+def _nhwc_dense(t):
+    """bf16 4-d tensor whose channels-last memory is dense (flat element order == (n, h, w, c))."""
+    return t.dim() == 4 and t.dtype == torch.bfloat16 and t.numel() % 8 == 0 and t.permute(0, 2, 3, 1).is_contiguous()
 
 
 def frozen_res5_mean(blocks, x, prestrided=False):

@@ -10,6 +10,8 @@ fan-in of gradients on `accumulate`, bias gradients on ordered column sums.  PyT
 and the autograd plumbing only; the tiny text-side projections (K+2 rows) stay in plain torch upstream of this
 function and receive `dKq`, `dVp` from it.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -123,6 +125,61 @@ def add_relu_mask(a, b=None, ref=None):
         assert t is None or (t.shape == a.shape and t.stride() == a.stride() and t.dtype == a.dtype)
     y = torch.empty_like(_nhwc(a))
     _lib.call("b200_add_relu_mask", a.data_ptr(), _ptr(b), _ptr(ref), y.data_ptr(), a.numel(), _stream())
+    return y
+
+
+# 1-bit ReLU masks for the res5 backward's elementwise passes (csrc/res5_elem.cu).  B200_RELU_BITS: 0 = every pass re-reads
+# its activation; 1 (default) = the mask of the averaged tensor, which the spatial mean writes for free, feeds the mean
+# backward; 2 = masks of all activations, packed on a side stream during the forward (measured: the packs are not hidden
+# under cuDNN's kernels — forward +0.17 ms, backward -0.18 ms at R = 4096 — so this is not the default)
+RELU_BITS = int(os.environ.get("B200_RELU_BITS", "1"))
+_MASK_STREAMS = {}
+
+
+def mask_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _MASK_STREAMS:
+        _MASK_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _MASK_STREAMS[key]
+
+
+def spatial_mean_bits(x):
+    """`spatial_mean` that also returns the 1-bit ReLU mask of x (uint8, one byte per 8 consecutive elements)."""
+    _require_cuda(x)
+    R, C, h, w = _nhwc(x).shape
+    out = torch.empty((R, C), dtype=torch.float32, device=x.device)
+    bits = torch.empty(x.numel() // 8, dtype=torch.uint8, device=x.device)
+    _lib.call("b200_spatial_mean_bits", x.data_ptr(), out.data_ptr(), C, bits.data_ptr(), R, h * w, C, _stream())
+    return out, bits
+
+
+def pack_relu_bits(x, bits):
+    """bits (numel / 8,) uint8 <- 1-bit ReLU mask of the bf16 tensor x (dense in memory), on the current stream."""
+    _require_cuda(x, bits)
+    assert x.dtype == torch.bfloat16 and bits.dtype == torch.uint8 and bits.numel() * 8 == x.numel()
+    _lib.call("b200_pack_relu_bits", x.data_ptr(), bits.data_ptr(), x.numel(), _stream())
+    return bits
+
+
+def mean_bwd_relu_bits(gpooled, bits, like):
+    """`mean_bwd_relu_mask` reading the 1-bit mask of the averaged tensor (shape / layout of `like`)."""
+    _require_cuda(gpooled, bits)
+    R, C, h, w = _nhwc(like).shape
+    gp = gpooled.detach().float()
+    if gp.stride(1) != 1 or gp.stride(0) % 4 or gp.data_ptr() % 16:
+        gp = gp.contiguous()
+    g = torch.empty_like(like)
+    _lib.call("b200_mean_bwd_relu_bits", gp.data_ptr(), gp.stride(0), bits.data_ptr(), g.data_ptr(), R, h * w, C, _stream())
+    return g
+
+
+def add_relu_bits(a, b, bits, inplace=False):
+    """bf16(a + b) (b optional) zeroed where the 1-bit mask says the activation was <= 0; `inplace` writes into a."""
+    _require_cuda(a, bits)
+    assert b is None or (b.shape == a.shape and b.stride() == a.stride() and b.dtype == a.dtype)
+    assert bits.numel() * 8 == a.numel()
+    y = a if inplace else torch.empty_like(_nhwc(a))
+    _lib.call("b200_add_relu_bits", a.data_ptr(), _ptr(b), bits.data_ptr(), y.data_ptr(), a.numel(), _stream())
     return y
 
 

@@ -266,6 +266,19 @@ B200_API int b200_mean_bwd_relu_mask(const float* gpooled, int ld_g, const void*
 B200_API int b200_add_relu_mask(const void* a_bf16, const void* b_bf16, const void* ref_bf16, void* y_bf16, size_t n,
                        b200_stream_t stream);
 
+/* 1-bit ReLU masks for the passes above: relu_bits holds one byte per 8 consecutive elements of the activation (bit k
+ * <-> element 8 i + k passes the ReLU backward), 1/16 of the activation's bytes.  b200_spatial_mean_bits = b200_spatial_mean
+ * that also writes the mask of the tensor it averages; b200_pack_relu_bits writes the mask of any bf16 tensor (n elements,
+ * n % 8 == 0); b200_mean_bwd_relu_bits / b200_add_relu_bits = the _mask entry points reading the mask instead of the
+ * activation (add_relu_bits with a == the gradient, b == NULL is the in-place-capable ReLU backward y = a where kept). */
+B200_API int b200_spatial_mean_bits(const void* x_bf16, float* pooled, int ld_pooled, void* relu_bits, int R, int HW, int C,
+                           b200_stream_t stream);
+B200_API int b200_pack_relu_bits(const void* x_bf16, void* relu_bits, size_t n, b200_stream_t stream);
+B200_API int b200_mean_bwd_relu_bits(const float* gpooled, int ld_g, const void* relu_bits, void* g_bf16, int R, int HW, int C,
+                            b200_stream_t stream);
+B200_API int b200_add_relu_bits(const void* a_bf16, const void* b_bf16, const void* relu_bits, void* y_bf16, size_t n,
+                       b200_stream_t stream);
+
 /* dst[r][:] = bf16(scale * src[r][:] / max(||src[r]||_2, eps)) — row normalisation for the optional cosine + temperature
  * form of the prototype logits (the reference's helper: my_module.py:461-469 `sim_matrix`, :449-458 `bsim_matrix`);
  * src fp32 or bf16 (src_dtype), leading dimensions in elements. */

@@ -252,6 +252,45 @@ def test_res5_elementwise_kernels(R, C, h, w):
     assert torch.equal(train_ops.add_relu_mask(a, b, out).view(torch.int16), torch.ops.aten.threshold_backward(a + b, out, 0).view(torch.int16))
     assert torch.equal(train_ops.add_relu_mask(a, b), a + b)
     assert torch.equal(train_ops.add_relu_mask(a, None, out).view(torch.int16), torch.ops.aten.threshold_backward(a, out, 0).view(torch.int16))
+    # 1-bit mask variants: the mask written by the spatial mean equals the packed one and the one torch would apply
+    # (incl. -0, NaN, inf), and every pass reading it gives the bits of the pass reading the activation
+    pooled2, bits = train_ops.spatial_mean_bits(out)
+    assert torch.equal(pooled2.view(torch.int32), pooled.view(torch.int32))
+    bits2 = train_ops.pack_relu_bits(out, torch.empty_like(bits))
+    assert torch.equal(bits, bits2)
+    keep = torch.ops.aten.threshold_backward(torch.ones_like(out), out, 0).permute(0, 2, 3, 1).reshape(-1, 8).to(torch.int32)
+    want = (keep * (2 ** torch.arange(8, device="cuda", dtype=torch.int32))).sum(1).to(torch.uint8)
+    assert torch.equal(bits, want)
+    assert torch.equal(train_ops.mean_bwd_relu_bits(gp, bits, out).view(torch.int16), g.view(torch.int16))
+    assert torch.equal(train_ops.add_relu_bits(a, b, bits).view(torch.int16), train_ops.add_relu_mask(a, b, out).view(torch.int16))
+    a2 = a.clone()
+    assert train_ops.add_relu_bits(a2, None, bits, inplace=True) is a2
+    assert torch.equal(a2.view(torch.int16), train_ops.add_relu_mask(a, None, out).view(torch.int16))
+
+
+@pytest.mark.parametrize("skip", [True, False])
+def test_frozen_res5_mean_node_relu_bits_match_activation_masks(golden, skip, monkeypatch):
+    """The 1-bit-mask backward (side-stream packs in the forward) gives the bits of the backward that re-reads the
+    activations."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import layers, train_ops
+    m = _build(golden("train_step"))
+    for p in m.res5.parameters():
+        p.requires_grad_(False)
+    gen = torch.Generator().manual_seed(13)
+    side = 4 if skip else 7
+    x = torch.randn(64, 32, side, side, generator=gen).clamp_min(0).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    gp = None
+    grads = []
+    for on in (2, 0, 1):
+        monkeypatch.setattr(train_ops, "RELU_BITS", on)
+        xa = x.clone().requires_grad_(True)
+        pa = layers.frozen_res5_mean(m.res5, xa, prestrided=skip)
+        if gp is None:
+            gp = torch.randn(pa.shape, generator=gen).cuda()
+        pa.backward(gp)
+        grads.append(xa.grad.clone())
+    assert torch.equal(grads[0].view(torch.int16), grads[1].view(torch.int16))
+    assert torch.equal(grads[0].view(torch.int16), grads[2].view(torch.int16))
 
 
 @pytest.mark.parametrize("skip", [True, False])
