@@ -235,8 +235,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own log lines (e.g. "NCCL version ..." under NCCL_DEBUG=VERSION) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NB the GPU box exports NCCL_DEBUG=VERSION: NCCL itself prints one "NCCL version ..." line to stdout before the JSON line
         dist.init_process_group("nccl", device_id=dev)
     train = args.mode == "train"
     B, P, K = args.images_per_gpu, args.props, args.classes
