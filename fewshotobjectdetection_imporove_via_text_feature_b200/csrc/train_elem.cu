@@ -521,6 +521,65 @@ head_losses_bwd_kernel(const float* __restrict__ logits, const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// distillation loss of the student head (my_module.py:409-437 loss_fn_kd_only, called from roi_heads.py:760 with
+// alpha = 1 and T = KL_TEMP): out[0] = alpha T^2 / R * sum_r w_r sum_c pt_rc (log pt_rc - log ps_rc), with
+// pt = softmax(teacher / T), ps = softmax(student / T), w_r = 1.5 on background rows (gt_r == bg_label), else 1.
+// One CTA, rows strided over the threads, fixed-order tree (bitwise reproducible).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+kd_loss_kernel(const float* __restrict__ student, const float* __restrict__ teacher, const int64_t* __restrict__ gt, int R,
+               int C1, int bg_label, float T, float alpha, float* __restrict__ out) {
+  __shared__ float s_red[1024];
+  const float invT = 1.0f / T;
+  float acc = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float* s = student + (size_t)r * C1;
+    const float* t = teacher + (size_t)r * C1;
+    float ms = -INFINITY, mt = -INFINITY;
+    for (int c = 0; c < C1; ++c) { ms = fmaxf(ms, s[c] * invT); mt = fmaxf(mt, t[c] * invT); }
+    float zs = 0.f, zt = 0.f;
+    for (int c = 0; c < C1; ++c) { zs += expf(s[c] * invT - ms); zt += expf(t[c] * invT - mt); }
+    const float ls = ms + logf(zs), lt = mt + logf(zt);
+    float kl = 0.f;
+    for (int c = 0; c < C1; ++c) {
+      const float lpt = t[c] * invT - lt;
+      const float pt = expf(lpt);
+      if (pt > 0.f) kl += pt * (lpt - (s[c] * invT - ls));
+    }
+    acc += ((int)gt[r] == bg_label) ? 1.5f * kl : kl;
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s_red[0] / (float)R * T * T * alpha;
+}
+
+// dlogits[r][c] (bf16, the student's logit gradient left by head_losses_bwd) += gscale[0] w_r alpha T / R (ps_rc - pt_rc)
+__global__ void __launch_bounds__(256)
+kd_loss_bwd_kernel(const float* __restrict__ student, const float* __restrict__ teacher, const int64_t* __restrict__ gt,
+                   const float* __restrict__ gscale, int R, int C1, int bg_label, float T, float alpha,
+                   __nv_bfloat16* __restrict__ dlogits, int ldl) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float invT = 1.0f / T;
+  const float* s = student + (size_t)r * C1;
+  const float* t = teacher + (size_t)r * C1;
+  float ms = -INFINITY, mt = -INFINITY;
+  for (int c = 0; c < C1; ++c) { ms = fmaxf(ms, s[c] * invT); mt = fmaxf(mt, t[c] * invT); }
+  float zs = 0.f, zt = 0.f;
+  for (int c = 0; c < C1; ++c) { zs += expf(s[c] * invT - ms); zt += expf(t[c] * invT - mt); }
+  const float w = (((int)gt[r] == bg_label) ? 1.5f : 1.0f) * gscale[0] * alpha * T / (float)R;
+  for (int c = 0; c < C1; ++c) {
+    const float ps = expf(s[c] * invT - ms) / zs, pt = expf(t[c] * invT - mt) / zt;
+    __nv_bfloat16* d = dlogits + (size_t)r * ldl + c;
+    *d = __float2bfloat16_rn(__bfloat162float(*d) + w * (ps - pt));
+  }
+}
+
 // SGD with momentum over one flat fp32 buffer (torch.optim.SGD: g += wd * p; m = mu * m + g; p -= lr * m)
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
                                     float lr, float mu, float wd) {
@@ -690,5 +749,27 @@ extern "C" int b200_sgd_momentum(float* params, const float* grads, float* momen
   const int blocks = (int)min((size_t)kNumSMs * 8, (n + 255) / 256);
   sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay);
   B200_CUDA_LAUNCH_CHECK("sgd_momentum");
+  return B200_OK;
+}
+
+extern "C" int b200_kd_loss(const float* student_logits, const float* teacher_logits, const int64_t* gt_classes, int R, int C1,
+                            int bg_label, float temperature, float alpha, float* out1, b200_stream_t stream) {
+  B200_CHECK_ARG(student_logits && teacher_logits && gt_classes && out1, "kd_loss: null tensor");
+  B200_CHECK_ARG(R > 0 && C1 > 0 && temperature > 0.f, "kd_loss: bad shape / temperature");
+  kd_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(student_logits, teacher_logits, gt_classes, R, C1, bg_label, temperature,
+                                                      alpha, out1);
+  B200_CUDA_LAUNCH_CHECK("kd_loss");
+  return B200_OK;
+}
+
+extern "C" int b200_kd_loss_bwd(const float* student_logits, const float* teacher_logits, const int64_t* gt_classes,
+                                const float* grad_scale1, int R, int C1, int bg_label, float temperature, float alpha,
+                                void* dlogits_bf16, int ldl, b200_stream_t stream) {
+  B200_CHECK_ARG(student_logits && teacher_logits && gt_classes && grad_scale1 && dlogits_bf16, "kd_loss_bwd: null tensor");
+  B200_CHECK_ARG(R > 0 && C1 > 0 && ldl >= C1 && temperature > 0.f, "kd_loss_bwd: bad shape / temperature");
+  kd_loss_bwd_kernel<<<ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(student_logits, teacher_logits, gt_classes, grad_scale1,
+                                                                        R, C1, bg_label, temperature, alpha,
+                                                                        (__nv_bfloat16*)dlogits_bf16, ldl);
+  B200_CUDA_LAUNCH_CHECK("kd_loss_bwd");
   return B200_OK;
 }

@@ -299,7 +299,7 @@ class SematicRes5ROIHeads(Res5ROIHeads):
 
     _DROP_STEP = [0]
 
-    def fused_train_losses(self, feature_pooled, proposals, gt_classes):
+    def fused_train_losses(self, feature_pooled, proposals, gt_classes, teacher_logits=None, kd=None):
         """Fine-tune direction on the hand-written kernels (train_ops._FusedHeadTrain): text-fusion chain, predictor
         with classifier dropout, and the three losses in one autograd node; same numbers as `forward_att` +
         `FastRCNNOutputs.losses` (roi_heads.py:1060-1132) up to bf16 GEMM operands.  The (K+2)-row text side runs in
@@ -328,8 +328,11 @@ class SematicRes5ROIHeads(Res5ROIHeads):
             seed = (torch.initial_seed() * 1000003) & 0x7FFFFFFFFFFFFFFF
         losses, logits = train_ops.fused_head_train(feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb,
                                                     self.num_classes, self.box2box_transform.weights, self.smooth_l1_beta,
-                                                    drop, seed, True, salt)
-        return {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}, logits
+                                                    drop, seed, True, salt, teacher_logits, kd)
+        out = {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}
+        if teacher_logits is not None:
+            out["loss_kl"] = losses[3]
+        return out, logits
 
     def use_device_dropout_counter(self, enable=True):
         """Keep the classifier-dropout step counter in device memory (incremented by a kernel each step) instead of on the
@@ -369,8 +372,10 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         elif test_with_gt:
             proposals = self.label_proposals(proposals, targets)
         feature_pooled = self._pooled(features, proposals)
+        teacher_logits = self._teacher_logits(feature_pooled, gt_classes) if self.training else None
         if feature_pooled.is_cuda and self._fused_train_path():
-            losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes)
+            losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes, teacher_logits,
+                                                     self._kd_params() if teacher_logits is not None else None)
             FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy()
             return [], losses
         att_output, att_loss = self.forward_att(feature_pooled, gt_classes)
@@ -379,9 +384,61 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         if self.training:
             losses = dict(outputs.losses())
             losses.update(att_loss)
+            if teacher_logits is not None:
+                from .my_module import loss_fn_kd_only
+                T, alpha = self._kd_params()
+                losses["loss_kl"] = loss_fn_kd_only(att_output["pred_logits"], gt_classes, self.num_classes, teacher_logits,
+                                                    {"alpha": alpha, "temperature": T})
             return [], losses
         pred, _ = outputs.inference(self.test_score_thresh, self.test_nms_thresh, self.test_detections_per_img)
         return pred, {}
+
+
+    def _teacher_logits(self, feature_pooled, gt_classes):
+        """Hook of the distillation head: logits of a frozen teacher for this batch, or None."""
+        return None
+
+    def _kd_params(self):
+        return 1.0, 1.0
+
+
+@ROI_HEADS_REGISTRY.register()
+class SematicRes5ROIHeadsDistill(SematicRes5ROIHeads):
+    """Student fine-tuning against a frozen, ground-truth-conditioned teacher (BASELINE configs[3]).
+
+    The reference's distillation heads (`TextRes5ROIHeads*`, roi_heads.py:529-919) do not run as checked in
+    (SURVEY §2.2); this is their intended flow (our_roi_heads_dnt.py:338-410, roi_heads.py:740-765): the teacher —
+    `LV_attention_VKV` over the GT class embeddings plus its own classifier — sees the pooled ROI features and their
+    labels, the student is the text-fused head, and `loss_kl = loss_fn_kd_only(student logits, gt, bg, teacher logits,
+    alpha = 1, T = KL_TEMP)` (my_module.py:409-437; run_text_train_teacher_novel.sh: KL_TEMP 5) joins the student's own
+    losses.  The teacher runs without autograd on the fused kernels (ops.teacher_attention_forward + the tcgen05 GEMM for
+    its classifier); the student's step is the fused node with the KL term as a fourth loss."""
+
+    def __init__(self, cfg, input_shape):
+        super().__init__(cfg, input_shape)
+        from .teacher_modules import LV_attention_VKV
+        self.teacher = LV_attention_VKV(self.out_channels, cfg=cfg)
+        self.teacher_cls_score = nn.Linear(self.out_channels, self.num_classes + 1)
+        nn.init.normal_(self.teacher_cls_score.weight, std=0.01)
+        nn.init.constant_(self.teacher_cls_score.bias, 0)
+        for p in list(self.teacher.parameters()) + list(self.teacher_cls_score.parameters()):
+            p.requires_grad = False
+        self.kd_temp = float(b200_opt(cfg, "KD_TEMP", 5.0))
+        self._teacher_w = None
+
+    def _kd_params(self):
+        return self.kd_temp, 1.0
+
+    @torch.no_grad()
+    def _teacher_logits(self, feature_pooled, gt_classes):
+        _, out = self.teacher(feature_pooled.detach(), gt_classes)
+        w, b = self.teacher_cls_score.weight, self.teacher_cls_score.bias
+        if feature_pooled.is_cuda and "sim2stext_bf16" in out:
+            key = (w.data_ptr(), w._version, ops.PARAM_GENERATION[0])
+            if self._teacher_w is None or self._teacher_w[0] != key:
+                self._teacher_w = (key, w.detach().to(torch.bfloat16).contiguous(), b.detach().float().contiguous())
+            return ops.gemm_bf16(out["sim2stext_bf16"], self._teacher_w[1], self._teacher_w[2])
+        return F.linear(out["sim2stext"][0], w, b)
 
 
 @ROI_HEADS_REGISTRY.register()

@@ -322,7 +322,8 @@ class _FusedHeadTrain(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, kq, vp, W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb,
-                gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt=None):
+                gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt=None,
+                teacher_logits=None, kd=None):
         _require_cuda(x, kq, vp, W1, W3, Wc, Wb, gt_classes, proposals, gt_boxes)
         x = x.detach().float().contiguous()
         R, d = x.shape
@@ -352,6 +353,16 @@ class _FusedHeadTrain(torch.autograd.Function):
         logits = gemm_bf16(zd, W["Wc"], bc)
         deltas = gemm_bf16(xb, W["Wb"], bb)
         losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
+        # distillation (BASELINE configs[3]): a fourth loss, KL against the frozen teacher's logits (my_module.py:409-437)
+        tl = None
+        if teacher_logits is not None:
+            tl = f32(teacher_logits)
+            assert tl.shape == logits.shape and kd is not None
+            kl = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.call("b200_kd_loss", logits.data_ptr(), tl.data_ptr(), gt.data_ptr(), R, logits.shape[1], int(K), float(kd[0]),
+                      float(kd[1]), kl.data_ptr(), _stream())
+            losses = torch.cat([losses, kl])
+        ctx.kd = (tl, kd)
         # K-contiguous transposes of the weights, the B operands of the backward's dX = dY W products: they depend on
         # nothing but the weights, so they run now on the side stream, under the forward chain / losses, instead of on the
         # backward's critical path
@@ -388,7 +399,7 @@ class _FusedHeadTrain(torch.autograd.Function):
         C1p, C4p, Lp = _rup(C1), _rup(C4), _rup(L)
         dev = x.device
         st = _stream()
-        g3 = g_losses.detach().float().contiguous()
+        g3 = g_losses.detach().float().contiguous()          # (3,) or, with the distillation loss, (4,)
 
         # ---- L1 backward ------------------------------------------------------------------------------------
         dlogits = torch.empty((R, C1p), dtype=torch.bfloat16, device=dev)
@@ -398,6 +409,10 @@ class _FusedHeadTrain(torch.autograd.Function):
         _lib.call("b200_head_losses_bwd", logits.data_ptr(), deltas.data_ptr(), attn.data_ptr() if want_attn else 0,
                   gt.data_ptr(), props.data_ptr(), gtb.data_ptr(), g3.data_ptr(), R, K, L, int(agnostic),
                   *map(float, box_w), float(l1_beta), dlogits.data_ptr(), C1p, ddeltas.data_ptr(), C4p, _ptr(dattn), st)
+        tl, kd = ctx.kd
+        if tl is not None:
+            _lib.call("b200_kd_loss_bwd", logits.data_ptr(), tl.data_ptr(), gt.data_ptr(), g3[3:].data_ptr(), R, C1, int(K),
+                      float(kd[0]), float(kd[1]), dlogits.data_ptr(), C1p, st)
 
         # Streams: the data-gradient chain (dX GEMMs, LayerNorm / attention backward) is the critical path and stays on the
         # current stream; everything that only feeds parameter gradients (operand transposes, dW GEMMs, bias column sums)
@@ -509,12 +524,12 @@ class _FusedHeadTrain(torch.autograd.Function):
             PENDING_GRAD_EVENTS.append((done, keep))
             for g in (out["dkq"], out["dvp"]):
                 _READY_EVENTS[g.data_ptr()] = tdone
-            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 10
+            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 12
         main.wait_event(done)
         main.wait_event(tdone)
         dkq, dvp, dW1, dW2, dW3, dWf1, dWf2, dWc, dWb = (out[k] for k in ("dkq", "dvp", "dW1", "dW2", "dW3", "dWf1", "dWf2", "dWc", "dWb"))
         return (dx, dkq, dvp, dW1, out["db1"], dW2, out["db2"], dW3, out["db3"], dWf1, out["dbf1"], dWf2, out["dbf2"], dgamma,
-                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 10
+                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 12
 
 
 _COMM_STREAMS = {}
@@ -531,14 +546,15 @@ def _side_stream(dev):
 
 
 def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed,
-                     want_attn_loss=True, salt=None):
-    """att: SingleHeadSiameseAttention (parameters linear1/2/3, ffn.*), predictor: FastRCNNOutputLayers."""
+                     want_attn_loss=True, salt=None, teacher_logits=None, kd=None):
+    """att: SingleHeadSiameseAttention (parameters linear1/2/3, ffn.*), predictor: FastRCNNOutputLayers.
+    teacher_logits (R, K+1) + kd = (temperature, alpha): adds the distillation loss as a fourth entry of `losses`."""
     return _FusedHeadTrain.apply(
         x, kq, vp, att.linear1[0].weight, att.linear1[0].bias, att.linear2[0].weight, att.linear2[0].bias,
         att.linear3.weight, att.linear3.bias, att.ffn.linear1.weight, att.ffn.linear1.bias, att.ffn.linear2.weight,
         att.ffn.linear2.bias, att.ffn.norm3.weight, att.ffn.norm3.bias, predictor.cls_score.weight,
         predictor.cls_score.bias, predictor.bbox_pred.weight, predictor.bbox_pred.bias, gt_classes, proposals, gt_boxes,
-        K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt)
+        K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt, teacher_logits, kd)
 
 
 class FlatSGD:

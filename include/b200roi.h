@@ -223,6 +223,15 @@ B200_API int b200_head_losses_bwd(const float* logits, const float* deltas, cons
                          const float* proposals, const float* gt_boxes, const float* grad_scale3, int R, int K, int L,
                          int cls_agnostic, float wx, float wy, float ww, float wh, float smooth_l1_beta,
                          void* dlogits_bf16, int ldl, void* ddeltas_bf16, int ldd, float* dattn, b200_stream_t stream);
+/* Distillation loss of the student head — my_module.py:409-437 loss_fn_kd_only as called at roi_heads.py:760
+ * (BASELINE configs[3]): out1[0] = alpha T^2 / R sum_r w_r KL(softmax(teacher_r / T) || softmax(student_r / T)),
+ * w_r = 1.5 where gt_r == bg_label.  logits (R, C1) fp32.  b200_kd_loss_bwd ADDS grad_scale1[0] (device) times its
+ * gradient to the bf16 student-logit gradient (R, ldl) that b200_head_losses_bwd left. */
+B200_API int b200_kd_loss(const float* student_logits, const float* teacher_logits, const int64_t* gt_classes, int R, int C1,
+                 int bg_label, float temperature, float alpha, float* out1, b200_stream_t stream);
+B200_API int b200_kd_loss_bwd(const float* student_logits, const float* teacher_logits, const int64_t* gt_classes,
+                     const float* grad_scale1, int R, int C1, int bg_label, float temperature, float alpha,
+                     void* dlogits_bf16, int ldl, b200_stream_t stream);
 /* T1 + text half of A1/A2 (attentive_modules.py:274-277, :125-135; Kq = Kp Wq / sqrt(d)): fp32 contractions with at
  * most 32 rows on one side, forward and backward (tensor-core tiles would be > 80 % padding; cuBLAS takes 30-50 us per
  * call here).  mode 0 "NT": out[m][n] = act(sum_k A[m][k] B[n][k] + bias[n]);  mode 1 "NN": out[m][k] = scale *

@@ -25,11 +25,11 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-def _build(g, K=20, d=64):
+def _build(g, K=20, d=64, name="SematicRes5ROIHeads"):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
     cfg = config.get_cfg()
-    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ROI_HEADS.NAME = name
     cfg.MODEL.ROI_HEADS.NUM_CLASSES = K
     cfg.MODEL.ADDITION.NAME = "clip"
     cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = d // 8, 1
@@ -37,7 +37,7 @@ def _build(g, K=20, d=64):
     sd = {k: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith(("attention.", "box_predictor.", "output_projection",
                                                                              "sematic_projection", "projection_matrix"))}
     missing, unexpected = m.load_state_dict(sd, strict=False)
-    assert not unexpected and all(k.startswith("res5.") for k in missing), (missing, unexpected)
+    assert not unexpected and all(k.startswith(("res5.", "teacher")) for k in missing), (missing, unexpected)
     m.attention.embed = torch.from_numpy(np.asarray(g["embed"]))
     m.attention.class_embed = m.attention.embed
     m.attention.bg_feature = torch.from_numpy(np.asarray(g["bg_feature"]))
@@ -396,3 +396,70 @@ def test_graphed_train_step_matches_eager(golden):
     assert not torch.equal(results[0][1][0], results[0][1][1])          # the steps differ (inputs, dropout mask, weights)
     for a, b in zip(results[0], results[1]):
         assert torch.equal(a, b)
+
+
+def test_kd_loss_kernels_vs_reference_formula():
+    """b200_kd_loss / b200_kd_loss_bwd vs loss_fn_kd_only (my_module.py:409-437, pinned on the reference's own function in
+    tests/test_abi_and_host.py) and its autograd gradient; the gradient is ADDED to an existing bf16 logit gradient."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.my_module import loss_fn_kd_only
+    gen = torch.Generator().manual_seed(2)
+    R, C1, T, alpha = 777, 21, 5.0, 1.0
+    s = (torch.randn(R, C1, generator=gen) * 3).cuda().requires_grad_(True)
+    t = (torch.randn(R, C1, generator=gen) * 3).cuda()
+    gt = torch.randint(0, C1, (R,), generator=gen).cuda()
+    ref = loss_fn_kd_only(s, gt, C1 - 1, t, {"alpha": alpha, "temperature": T})
+    ref.backward()
+    out = torch.empty(1, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("b200_kd_loss", s.data_ptr(), t.data_ptr(), gt.data_ptr(), R, C1, C1 - 1, T, alpha, out.data_ptr(), st)
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-7
+    base = (torch.randn(R, 24, generator=gen) * 1e-3).to(torch.bfloat16).cuda()
+    d = base.clone()
+    scale = torch.tensor([0.7], device="cuda")
+    _lib.call("b200_kd_loss_bwd", s.data_ptr(), t.data_ptr(), gt.data_ptr(), scale.data_ptr(), R, C1, C1 - 1, T, alpha,
+              d.data_ptr(), 24, st)
+    want = base[:, :C1].float() + 0.7 * s.grad
+    assert float((d[:, :C1].float() - want).abs().max()) <= 2 ** -8 * float(want.abs().max()) + 1e-8
+    assert torch.equal(d[:, C1:], base[:, C1:])
+
+
+def test_distillation_step_fused_vs_torch_expression(golden):
+    """BASELINE configs[3]: student step with the KL term against the frozen VKV teacher.  Fused node (four losses) vs the
+    differentiable torch expression of the same head + loss_fn_kd_only on the device; teacher logits from the fused
+    frozen-teacher path vs its dense torch expression."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.my_module import loss_fn_kd_only
+    g = golden("train_step")
+    torch.manual_seed(5)
+    m = _build(g, name="SematicRes5ROIHeadsDistill")
+    with torch.no_grad():
+        m.teacher_cls_score.weight.mul_(40.0)
+        m.teacher.attention.w_q.weight.mul_(8.0)
+        m.teacher.attention.w_k.weight.mul_(8.0)
+    assert not any(p.requires_grad for p in m.teacher.parameters())
+    props = _proposals(g)
+    gt = props[0].gt_classes
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    tl = m._teacher_logits(x, gt)
+    with torch.enable_grad():
+        _, dense = m.teacher(x.detach(), gt)
+    tl_ref = torch.nn.functional.linear(dense["sim2stext"][0].detach(), m.teacher_cls_score.weight, m.teacher_cls_score.bias)
+    assert _rel(tl, tl_ref) < 2e-2
+    losses, _ = m.fused_train_losses(x, props, gt, tl, m._kd_params())
+    assert set(losses) == {"loss_cls", "loss_box_reg", "loss_attentive", "loss_kl"}
+    sum(losses.values()).backward()
+    fused_gx = x.grad.clone()
+    fused_gc = m.box_predictor.cls_score.weight.grad.clone()
+    m.zero_grad(set_to_none=True)
+    x2 = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    att_out, att_loss = m.forward_att(x2, gt)
+    L = dict(FastRCNNOutputs(m.box2box_transform, att_out["pred_logits"], att_out["pred_bbox"], props, m.smooth_l1_beta).losses())
+    L.update(att_loss)
+    L["loss_kl"] = loss_fn_kd_only(att_out["pred_logits"], gt, m.num_classes, tl, {"alpha": 1.0, "temperature": m.kd_temp})
+    assert float(L["loss_kl"]) > 1e-4                      # the teacher really disagrees with the student
+    for k in L:
+        assert abs(float(losses[k]) - float(L[k])) <= 2e-2 * abs(float(L[k])) + 1e-4, (k, float(losses[k]), float(L[k]))
+    sum(L.values()).backward()
+    assert _rel(fused_gx, x2.grad) < 8e-2 and _cos(fused_gx, x2.grad) > 0.997
+    assert _rel(fused_gc, m.box_predictor.cls_score.weight.grad) < 2e-2
