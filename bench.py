@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--cpu-baseline-images", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--distill", action="store_true",
+                    help="train mode: BASELINE configs[3] — the student step with the KL loss against a frozen VKV teacher "
+                         "(SematicRes5ROIHeadsDistill); not the default metric line")
     ap.add_argument("--no-graph", action="store_true",
                     help="fine-tune mode: enqueue every step from the host instead of replaying one captured CUDA graph")
     ap.add_argument("--full-bins", action="store_true",
@@ -76,11 +79,11 @@ def synth_inputs(n_images, props, seed0=1234, num_classes=20):
     return feat, boxes, gt_cls, gt_boxes
 
 
-def build_head(num_classes, device, train=False):
+def build_head(num_classes, device, train=False, distill=False):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
     cfg = config.get_cfg()
-    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeadsDistill" if (train and distill) else "SematicRes5ROIHeads"
     cfg.MODEL.ROI_HEADS.NUM_CLASSES = num_classes
     cfg.MODEL.ADDITION.NAME = "clip"
     if train:
@@ -97,6 +100,8 @@ def build_head(num_classes, device, train=False):
         # random-init weights of the reference architecture; classifier scaled so that scores are not uniform
         head.box_predictor.cls_score.weight.mul_(40.0)
         head.box_predictor.bbox_pred.weight.mul_(50.0)
+        if train and distill:
+            head.teacher_cls_score.weight.mul_(40.0)
         aff.weight.normal_(1.0, 0.05)
         aff.bias.normal_(0.0, 0.05)
     if train:
@@ -206,7 +211,10 @@ def main_reference(args, rank, world):
 
 
 def workload_config(args, images_per_gpu):
-    if args.mode == "train":
+    if args.mode == "train" and getattr(args, "distill", False):
+        what = ("distillation fine-tune step (BASELINE configs[3]): the configs[1] step + frozen LV_attention_VKV teacher forward "
+                "(GT-conditioned, GloVe 300-d) + loss_kl (T = 5) on the student's logits")
+    elif args.mode == "train":
         what = ("fine-tune step (BASELINE configs[1]): GDL+affine_rcnn -> ROIAlign 7x7 -> res5 (frozen) -> text fusion -> "
                 "cls_score(dropout 0.8)/bbox_pred -> loss_cls+loss_box_reg+loss_attentive -> backward to the res4 map "
                 "and all trained parameters -> (grad all-reduce) -> SGD+momentum; proposals arrive sampled and labelled")
@@ -239,7 +247,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     train = args.mode == "train"
     B, P, K = args.images_per_gpu, args.props, args.classes
-    cfg, head, aff = build_head(K, dev, train=train)
+    distill = train and getattr(args, "distill", False)
+    cfg, head, aff = build_head(K, dev, train=train, distill=distill)
     feat_h, boxes_h, cls_h, gtb_h = synth_inputs(B, P, seed0=1234 + 1000 * rank, num_classes=K)
     host = {"feat": feat_h.pin_memory(), "boxes": torch.stack(boxes_h).pin_memory()}
     if train:
@@ -308,13 +317,19 @@ def main():
         head.prefetch_text_side(after=begin)                                                  # T1 (+ text half of A1/A2): side stream, under res5
         mark(3)
         gt = d["gt_cls"].reshape(-1)
-        losses, _ = head.fused_train_losses(fp, props, gt)                                    # T1, A1-A6, C1, L1
+        if distill:            # frozen teacher forward (fused, no autograd) + KL as the fourth loss of the fused node
+            losses, _ = head.fused_train_losses(fp, props, gt, head._teacher_logits(fp, gt), head._kd_params())
+        else:
+            losses, _ = head.fused_train_losses(fp, props, gt)                                # T1, A1-A6, C1, L1
         mark(4)
         if ev is not None:     # events inside the backward pass: recorded when the gradient of that tensor is ready
             fp.register_hook(lambda g: ev[5].record())
             pooled.register_hook(lambda g: ev[6].record())
             f.register_hook(lambda g: ev[7].record())
-        (losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]).backward()   # L1, A*, P2, P1b, G1/G2 bwd
+        total = losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]
+        if distill:
+            total = total + losses["loss_kl"]
+        total.backward()                                                                      # L1, A*, P2, P1b, G1/G2 bwd
         mark(8)
         res = {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
                "grad_feat": x.grad}
