@@ -134,13 +134,15 @@ def test_head_full_width_vs_oracle():
     assert len(res) == 2 and all(len(r) <= 100 for r in res)
 
 
-def test_training_step_runs_and_backprops():
-    """Fine-tune step: losses (loss_cls, loss_box_reg, loss_attentive) and gradients reach the res4 map through
-    the ROIAlign backward kernel and the fused GDL/affine backward."""
+@pytest.mark.parametrize("head_name", ["SematicRes5ROIHeads", "SematicRes5ROIHeadsDistill"])
+def test_training_step_runs_and_backprops(head_name):
+    """Fine-tune step through the Detectron2-style forward: losses (loss_cls, loss_box_reg, loss_attentive; + loss_kl for
+    the distillation head, BASELINE configs[3]) and gradients reach the res4 map through the ROIAlign backward kernel and
+    the fused GDL/affine backward."""
     from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, ShapeSpec
     cfg = config.get_cfg()
-    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ROI_HEADS.NAME = head_name
     cfg.MODEL.ADDITION.NAME = "clip"
     cfg.MODEL.ROI_HEADS.BATCH_SIZE_PER_IMAGE = 64
     cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 16, 4
@@ -164,7 +166,10 @@ def test_training_step_runs_and_backprops():
         t.gt_classes = torch.randint(0, 20, (len(objs),), generator=gen).cuda()
         tgts.append(t)
     _, losses = m(None, {"res4": feat}, props, tgts)
-    assert set(losses) == {"loss_cls", "loss_box_reg", "loss_attentive"}
+    want = {"loss_cls", "loss_box_reg", "loss_attentive"} | ({"loss_kl"} if head_name.endswith("Distill") else set())
+    assert set(losses) == want and all(torch.isfinite(v) for v in losses.values())
+    if head_name.endswith("Distill"):
+        assert float(losses["loss_kl"]) >= 0 and all(p_.grad is None for p_ in m.teacher.parameters())
     sum(losses.values()).backward()
     assert base.grad is not None and torch.isfinite(base.grad).all() and float(base.grad.abs().sum()) > 0
     assert aff.weight.grad is not None and torch.isfinite(aff.weight.grad).all()
