@@ -485,6 +485,40 @@ def main():
                       "bwd_ms": float(np.median(tb)), "bwd_gbs": full_bytes / float(np.median(tb)) / 1e6,
                       "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
             del pooled_full, gfull, fmap
+        # the post-processing operator (BASELINE metric "NMS us"): softmax + decode + threshold compaction, per-class NMS,
+        # top-100 gather on this batch's proposals with SURVEY 8(d)'s logits (30 % of the ROIs peaked on a random foreground
+        # class, the rest on background), L2 flushed before every call
+        nms_op = {}
+        with torch.no_grad():
+            gen_ = torch.Generator().manual_seed(99)
+            lg_ = torch.randn(B * P, K + 1, generator=gen_)
+            peak_ = torch.rand(B * P, generator=gen_) < 0.3
+            cls_ = torch.randint(0, K, (B * P,), generator=gen_)
+            lg_[torch.arange(B * P)[peak_], cls_[peak_]] += 4.0
+            lg_[~peak_, K] += 4.0
+            lg_, dl_ = lg_.to(dev), (torch.randn(B * P, 4 * K, generator=gen_) * 0.5).to(dev)
+            pb_ = torch.cat([resident["boxes"][i] for i in range(B)], 0).float().contiguous()
+            offs_ = torch.arange(0, B * P + 1, P, dtype=torch.int32, device=dev)
+            hw_ = ops.image_hw_tensor([(H_IMG, W_IMG)] * B, dev)
+            tn_, tt_ = [], []
+            for i in range(6):
+                flush.fill_(i)
+                _lib.PROFILE = {}
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0_.record()
+                det_ = ops.fast_rcnn_inference_device(lg_, dl_, pb_, offs_, hw_, 0.05, 0.5, 100)
+                e1_.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    tt_.append(e0_.elapsed_time(e1_))
+                    tn_.append(sum(a.elapsed_time(b) for a, b, _ in _lib.PROFILE.get("b200_batched_nms", [])))
+                _lib.PROFILE = None
+            nms_op = {"nms_us_per_image": 1e3 * float(np.median(tn_)) / B, "postprocess_us_per_image": 1e3 * float(np.median(tt_)) / B,
+                      "candidates_per_image": float(det_["n_candidates"].float().mean()),
+                      "detections_per_image": float(det_["counts"].float().mean()), "images": B, "classes": K,
+                      "note": "b200_batched_nms (3 kernels: class sort, per-class NMS, merge) / whole fast_rcnn_inference on the device, "
+                              "CUDA events, median of 4, bit-exact keep indices (tests/test_gpu_detect_post.py)"}
+            del lg_, dl_, det_
         gemm_alone = {"ms": 0.0, "flop": 0.0, "calls": len(gemm_cases)}
         gemm_ops = []
         for (M_, N_, K_, obf, d2_, relu_, acc_, msk_, bias_) in gemm_cases:
@@ -651,6 +685,8 @@ def main():
             "roofline_other": roi_roof if dominant_is_gemm else gemm_roof,
             "stage_ms": dict(zip(stage_names, stage_ms)),
             "stage_ms_note": "eager steps (the timed steps replay one CUDA graph)" if graph is not None else "timed steps",
+            "roi_align_gbs": {"in_step_%dx%d_bins" % (nb, nb): roi_gbs, "operator_7x7_fwd": roi_op.get("fwd_gbs"), "operator_7x7_bwd": roi_op.get("bwd_gbs")},
+            "nms": nms_op,
             "own_kernels_ms_per_step": ours_ms, "host_enqueue_ms_per_step": cpu_enqueue_ms,
             "own_kernels_profile": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "flop_per_step"}
                                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
