@@ -223,7 +223,7 @@ def test_gemm_res5_sized_problem_with_mask():
 
 
 @pytest.mark.parametrize("cls_name", ["LV_attention", "LV_attention_VKV"])
-@pytest.mark.parametrize("R,d,K", [(1024, 2048, 20), (203, 256, 7)])
+@pytest.mark.parametrize("R,d,K", [(1024, 2048, 20), (203, 256, 7), (640, 512, 80)])
 def test_teacher_attention_fused_forward_vs_dense_torch(cls_name, R, d, K):
     """A7: the class-collapsed fused forward (no (R, R+1) matrix) vs the module's dense fp32 torch expression
     (attentive_modules.py:403-437 / :452-487 semantics), bf16 bar 2e-2.  Sharpened attention weights so that the
