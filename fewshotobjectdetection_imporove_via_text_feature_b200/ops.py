@@ -394,6 +394,8 @@ def rpn_select_proposals(proposals, logits, level_sizes, image_hw, nms_thresh, p
     key = (tuple(int(v) for v in level_sizes), str(dev))
     lo = _LEVEL_CACHE.get(key)
     if lo is None:
+        if len(_LEVEL_CACHE) > 256:
+            _LEVEL_CACHE.clear()
         acc = [0]
         for v in level_sizes:
             acc.append(acc[-1] + int(v))
