@@ -210,3 +210,28 @@ def test_eval_formats_match_reference_evaluator(golden):
     want = json.loads(str(g["voc_lines"]))
     assert {str(k): v for k, v in lines.items()} == want
     assert F.coco_json_records(ids, b, s, c, n) == json.loads(str(g["coco"]))
+
+
+def test_bench_cli_contract(monkeypatch):
+    """bench.py's flags and defaults as the driver uses them (`--gpus N --steps K --warmup W [--impl reference]`), and the
+    workload description per mode; no GPU needed."""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    spec.loader.exec_module(b)
+    a = b.parse()
+    assert (a.gpus, a.impl, a.mode) == (1, "b200", "train") and a.warmup >= 3 and a.steps > 0
+    cfg = b.workload_config(a, a.images_per_gpu)
+    assert "configs[1]" in cfg["workload"] and cfg["proposals_per_image"] == 512 and "model" not in cfg
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "8", "--steps", "7", "--warmup", "4", "--impl", "reference"])
+    a = b.parse()
+    assert (a.gpus, a.steps, a.warmup, a.impl) == (8, 7, 4, "reference")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--distill"])
+    assert "configs[3]" in b.workload_config(b.parse(), 8)["workload"]
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--mode", "infer", "--classes", "80"])
+    a = b.parse()
+    assert "inference step" in b.workload_config(a, 8)["workload"] and a.classes == 80
+    assert b.METRIC == "roi_head_images_per_sec" and b.UNIT == "images/s"
