@@ -75,3 +75,44 @@ def test_voc_ap_sanity():
     ap = O.voc_eval_class(dets, gts)
     assert 0.8 < ap <= 1.0
     assert O.voc_eval_class([], gts) == 0.0
+
+
+def test_nms_random_small_cases_vs_torchvision():
+    """Many small adversarial cases: integer-grid boxes (exact IoU ties at the threshold, duplicates, zero-area boxes),
+    few distinct scores (long tie runs).  Thresholds are the reference's (0.5, 0.7) and other values whose fp32 rounding
+    is exact or downwards: torchvision 0.8.1 (the pinned version, CPU and CUDA) compares `iou > thr` with a FLOAT
+    threshold, which the oracle and the CUDA kernels follow; the installed 0.26 CPU kernel compares against the double,
+    so for a threshold like 1/3 (fp32 rounds it up) it suppresses a box whose IoU equals float(1/3) and 0.8.1 does not."""
+    gen = torch.Generator().manual_seed(123)
+    for case in range(300):
+        n = int(torch.randint(1, 40, (1,), generator=gen))
+        xy = torch.randint(0, 12, (n, 2), generator=gen).float()
+        wh = torch.randint(0, 6, (n, 2), generator=gen).float()
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.randint(0, 4, (n,), generator=gen).float() / 4
+        thr = [0.25, 0.5, 0.7, 0.0, 0.75][case % 5]
+        assert torch.equal(O.nms(boxes, scores, thr), torchvision.ops.nms(boxes, scores, thr)), case
+        idxs = torch.randint(0, 3, (n,), generator=gen)
+        off = idxs.to(boxes) * (boxes.max() + torch.tensor(1).to(boxes))
+        assert torch.equal(O.batched_nms(boxes, scores, idxs, thr), torchvision.ops.nms(boxes + off[:, None], scores, thr)), case
+
+
+def test_rpn_select_restatement_random_cases_vs_reference():
+    """find_top_rpn_proposals restatement vs the reference's own function on random cases generated here (beyond the three
+    committed fixtures); only where /root/reference is mounted (the authoring container)."""
+    from oracle import ref_stubs as rs
+    if not rs.reference_available():
+        pytest.skip("reference sources not mounted")
+    from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_rpn_outputs
+    rs.install()
+    pu = rs.load("defrcn.modeling.proposal_generator.proposal_utils")
+    gen = torch.Generator().manual_seed(77)
+    for case, (N, sizes, pre, post, thr, ms) in enumerate([(1, [500], 200, 50, 0.7, 0.0), (2, [800, 200], 300, 400, 0.5, 2.0),
+                                                           (3, [64], 1000, 1000, 0.9, 0.0), (1, [1500, 400, 100, 25], 120, 250, 0.7, 8.0)]):
+        props, logits = synth_rpn_outputs(N, sizes, 320, 416, gen)
+        sizes_hw = [(320, 416)] * N
+        ref = pu.find_top_rpn_proposals([p.clone() for p in props], [l.clone() for l in logits], sizes_hw, thr, pre, post, ms, False)
+        ours = O.find_top_rpn_proposals(props, logits, sizes_hw, thr, pre, post, ms)
+        for n in range(N):
+            assert torch.equal(ours[n]["boxes"], ref[n].proposal_boxes.tensor), (case, n)
+            assert torch.equal(ours[n]["logits"], ref[n].objectness_logits), (case, n)
