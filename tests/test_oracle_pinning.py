@@ -116,3 +116,38 @@ def test_rpn_select_restatement_random_cases_vs_reference():
         for n in range(N):
             assert torch.equal(ours[n]["boxes"], ref[n].proposal_boxes.tensor), (case, n)
             assert torch.equal(ours[n]["logits"], ref[n].objectness_logits), (case, n)
+
+
+def test_fast_rcnn_inference_restatement_random_cases_vs_reference():
+    """fast_rcnn_inference_single_image (fast_rcnn.py:90-134) restated in C vs the reference's own function on random
+    cases beyond the committed fixtures: quantised probabilities (exact score ties, values exactly at the 0.05
+    threshold), integer-grid boxes (IoU exactly 0.5), class-agnostic regression, topk = -1.  Authoring container only."""
+    from oracle import ref_stubs as rs
+    if not rs.reference_available():
+        pytest.skip("reference sources not mounted")
+    rs.install()
+    fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
+    gen = torch.Generator().manual_seed(2024)
+    for case in range(40):
+        R = int(torch.randint(1, 60, (1,), generator=gen))
+        K = [3, 20, 1][case % 3]
+        agnostic = case % 4 == 3
+        xy = torch.randint(-3, 30, (R, K, 2), generator=gen).float() * 4
+        wh = torch.randint(0, 8, (R, K, 2), generator=gen).float() * 4
+        boxes = torch.cat([xy, xy + wh], 2)
+        if agnostic:
+            boxes = boxes[:, :1]
+        probs = torch.randint(0, 21, (R, K + 1), generator=gen).float() / 20          # 0.05 steps: ties and the threshold itself
+        hw = (100, 120)
+        topk = [100, 5, -1][case % 3]
+        res, kept = fr.fast_rcnn_inference_single_image(boxes.reshape(R, -1).clone(), probs.clone(), hw, 0.05, 0.5, topk)
+        if agnostic:
+            ob = boxes.expand(R, K, 4).reshape(R, -1).contiguous()
+        else:
+            ob = boxes.reshape(R, -1)
+        r = O.fast_rcnn_inference_single_image(ob, probs, hw, 0.05, 0.5, topk)
+        assert r["n_candidates"] == int((probs[:, :-1] > 0.05).sum()), case
+        assert torch.equal(r["roi_inds"], kept), case
+        assert torch.equal(r["classes"], res.pred_classes), case
+        assert torch.equal(r["scores"], res.scores), case
+        assert torch.equal(r["boxes"], res.pred_boxes.tensor), case
