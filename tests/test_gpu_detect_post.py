@@ -144,3 +144,40 @@ def test_multi_image_full_size():
         assert bool((out["scores"][i, :k - 1] >= out["scores"][i, 1:k]).all())          # sorted
         again = ops.batched_nms(out["boxes"][i, :k], out["scores"][i, :k], out["classes"][i, :k], 0.5)
         assert torch.equal(again.cpu(), torch.arange(k))                                 # idempotent
+
+
+def test_adversarial_grid_cases_bit_exact():
+    """Integer-grid boxes (IoU exactly 0.5 after the class offset, duplicates, boxes that clip to nothing), probabilities in
+    0.05 steps (long runs of exact ties, values exactly at the score threshold): candidates, keep order and counts
+    must equal the oracle's — itself pinned on the reference's own function for this family of cases
+    (tests/test_oracle_pinning.py)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(2025)
+    for case in range(30):
+        R = int(torch.randint(1, 200, (1,), generator=gen))
+        K = [3, 20, 1, 80][case % 4]
+        xy = torch.randint(-3, 30, (R, 2), generator=gen).float() * 4
+        wh = torch.randint(0, 8, (R, 2), generator=gen).float() * 4 + (4 if case % 5 else 0)
+        props = torch.cat([xy, xy + wh], 1)
+        probs = torch.randint(0, 21, (R, K + 1), generator=gen).float() / 20
+        hw = (100, 120)
+        topk = [100, 7][case % 2]
+        deltas = torch.zeros(R, 4 * K)
+        out = _run(probs, deltas, props, hw, True, topk)
+        # zero deltas decode to the proposal itself only where that is exact in fp32: take the kernel's own decoded boxes
+        n = int(out["n_candidates"][0])
+        c = out["cand"]
+        ref_idx = (probs[:, :-1] > 0.05).nonzero()
+        assert n == len(ref_idx), case
+        assert torch.equal(c["cand_roi"][:n].cpu().long(), ref_idx[:, 0]) and torch.equal(c["cand_cls"][:n].cpu().long(), ref_idx[:, 1])
+        clipped = props.clone()
+        clipped[:, 0::2] = clipped[:, 0::2].clamp(0, hw[1])
+        clipped[:, 1::2] = clipped[:, 1::2].clamp(0, hw[0])
+        assert torch.equal(c["cand_boxes"][:n].cpu(), clipped[ref_idx[:, 0]]), case     # small-integer boxes decode exactly
+        r = O.fast_rcnn_inference_single_image(props.repeat(1, K), probs, hw, 0.05, 0.5, topk)
+        k = int(out["counts"][0])
+        assert k == len(r["scores"]), case
+        assert torch.equal(out["roi_inds"][0, :k].cpu(), r["roi_inds"]), case
+        assert torch.equal(out["classes"][0, :k].cpu(), r["classes"]), case
+        assert torch.equal(out["scores"][0, :k].cpu(), r["scores"]), case
+        assert torch.equal(out["boxes"][0, :k].cpu(), r["boxes"]), case
