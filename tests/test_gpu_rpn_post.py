@@ -136,3 +136,28 @@ def test_detector_postprocess_vs_oracle():
     assert out.image_size == (oh, ow)
     assert torch.equal(out.pred_boxes.tensor.cpu(), rb)
     assert torch.equal(out.scores.cpu(), scores[0][keep]) and torch.equal(out.pred_classes.cpu(), classes[0][keep])
+
+
+def test_rpn_select_adversarial_grid_cases():
+    """Integer-grid anchors (duplicates, IoU exactly at the threshold, boxes that clip to nothing or fall under min_size)
+    and logits in 0.25 steps (long exact-tie runs across the pre_nms_topk boundary): selection and order equal the
+    oracle's stable-sort restatement."""
+    gen = torch.Generator().manual_seed(31)
+    for case in range(12):
+        N = 1 + case % 3
+        sizes = [[900], [400, 100], [64, 32, 16]][case % 3]
+        A = sum(sizes)
+        xy = torch.randint(-4, 40, (N, A, 2), generator=gen).float() * 4
+        wh = torch.randint(0, 10, (N, A, 2), generator=gen).float() * 4
+        boxes = torch.cat([xy, xy + wh], 2)
+        lg = torch.randint(-8, 9, (N, A), generator=gen).float() / 4
+        props = list(boxes.split(sizes, dim=1))
+        logits = list(lg.split(sizes, dim=1))
+        pre, post = [50, 300, 1000][case % 3], [20, 1000, 100][(case // 3) % 3]
+        thr, ms = [0.5, 0.7, 0.25][case % 3], [0.0, 4.0][case % 2]
+        image_sizes = [(120, 150)] * N
+        ref = O.find_top_rpn_proposals(props, logits, image_sizes, thr, pre, post, ms)
+        res = _device_call(props, logits, image_sizes, thr, pre, post, ms)
+        for n in range(N):
+            assert torch.equal(res[n].objectness_logits.cpu(), ref[n]["logits"]), (case, n)
+            assert torch.equal(res[n].proposal_boxes.tensor.cpu(), ref[n]["boxes"]), (case, n)
