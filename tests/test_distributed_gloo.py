@@ -33,6 +33,16 @@ def _worker(rank, world, port, n_images):
     assert gc.tolist() == [i % 4 for i in range(n_images)]
     for i in range(n_images):
         assert bool((gd[i, :i % 4, 5] == i).all()) and bool((gd[i, i % 4:] == 0).all())
+    # the evaluators' records after the exchange == the records of one process holding every image
+    # (replaces comm.gather of the per-rank `_predictions` dicts, pascal_voc_evaluation.py:84-91)
+    from fewshotobjectdetection_imporove_via_text_feature_b200.evaluation import detection_formats as F
+    ids = ["%06d" % i for i in range(n_images)]
+    lines = F.voc_prediction_lines(ids, gd[..., :4].numpy(), gd[..., 4].numpy(), gd[..., 5].numpy().astype("int64"), gc.numpy())
+    want = {}
+    for i in range(n_images):
+        for _ in range(i % 4):
+            want.setdefault(i, []).append(f"{ids[i]} {i / 10.0:.3f} {i + 1:.1f} {i + 1:.1f} {float(i):.1f} {float(i):.1f}")
+    assert dict(lines) == want
     # gradient all-reduce: rank r holds grad = r+1 everywhere -> mean 1.5
     ps = [torch.nn.Parameter(torch.zeros(1000)), torch.nn.Parameter(torch.zeros(37, 3)), torch.nn.Parameter(torch.zeros(5))]
     for p in ps[:2]:
