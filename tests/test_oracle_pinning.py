@@ -125,6 +125,7 @@ def test_fast_rcnn_inference_restatement_random_cases_vs_reference():
     from oracle import ref_stubs as rs
     if not rs.reference_available():
         pytest.skip("reference sources not mounted")
+    import fewshotobjectdetection_imporove_via_text_feature_b200  # noqa: F401  (before the detectron2 stand-ins enter sys.modules)
     rs.install()
     fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
     gen = torch.Generator().manual_seed(2024)
