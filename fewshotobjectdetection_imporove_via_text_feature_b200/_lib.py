@@ -15,8 +15,24 @@ NCHW, NHWC = 0, 1
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
+
+
+class Gemm2Desc(ctypes.Structure):
+    """struct b200_gemm2_desc (include/b200roi.h), field for field."""
+    _fields_ = [("A", c_void_p), ("lda", c_int), ("A2", c_void_p), ("lda2", c_int), ("K2", c_int),
+                ("B", c_void_p), ("ldb", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+                ("a_mn", c_int), ("b_mn", c_int), ("conv_c", c_int), ("bias", c_void_p),
+                ("residual", c_void_p), ("ld_res", c_int), ("relu", c_int),
+                ("mask_act", c_void_p), ("ld_mask", c_int), ("mask_bits", c_void_p), ("ld_mask_bits", c_int),
+                ("out_bf16", c_void_p), ("ld_out", c_int), ("out2_bf16", c_void_p), ("ld_out2", c_int),
+                ("out_f32", c_void_p), ("ld_out_f32", c_int), ("accumulate", c_int),
+                ("bits_out", c_void_p), ("ld_bits_out", c_int), ("rowmean_out", c_void_p), ("ld_rowmean", c_int),
+                ("tile_n", c_int), ("max_clusters", c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/b200roi.h declaration by declaration
 SIGNATURES = {
+    "b200_gemm2": (c_int, [ctypes.POINTER(Gemm2Desc), c_void_p]),
     "b200_abi_version": (c_int, []),
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_set_option": (c_int, [ctypes.c_char_p, c_int]),
@@ -83,7 +99,7 @@ class B200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 3, "b200_roi_align_bwd_planned": 1,
     "b200_softmax_decode_compact": 1, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
-    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
+    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm2": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_layernorm_param_grads": 3, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
     "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1, "b200_label_sample_proposals": 1,
     "b200_rpn_select_proposals": 5, "b200_gather_rows_bf16": 1, "b200_kd_loss": 1, "b200_kd_loss_bwd": 1, "b200_spatial_mean_bits": 1, "b200_pack_relu_bits": 1, "b200_mean_bwd_relu_bits": 1, "b200_add_relu_bits": 1, "b200_class_mean_rows": 2, "b200_detector_postprocess": 1,

@@ -633,12 +633,9 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
     const size_t cls_smem = (size_t)kNmsPresortedBoxes * 16 + kNmsPresortedBoxes / 8;
     auto kc = nms_presorted_cluster_kernel<kNmsCluster>;
     auto k = nms_class_kernel<kNmsPresortedThreads, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      B200_CUDA_CALL(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
-      B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
-      attr_set = true;
-    }
+    // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
+    B200_CUDA_CALL(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
+    B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kNmsCluster * num_classes, N);
     cfg.blockDim = dim3(kNmsPresortedThreads);
@@ -661,11 +658,8 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
     // keys (8 B) + shifted boxes (16 B) + removed bitmap
     const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
     auto k = nms_class_kernel<kNmsThreads, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
-      attr_set = true;
-    }
+    // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
+    B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
     k<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1,
                                                           w.class_start, w.order, w.kept, w.scratch, max_keep, 0);
   }

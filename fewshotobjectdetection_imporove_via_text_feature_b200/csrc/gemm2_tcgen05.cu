@@ -1,0 +1,546 @@
+// CTA-pair bf16 tensor-core GEMM / implicit-GEMM convolution for sm_100a (tcgen05.mma.cta_group::2):
+//   D[M,N] = epi( A[M,K] . B[N,K]^T )         bf16 operands, fp32 accumulation in TMEM
+// used for the wide products of the ROI head: the res5 bottleneck convolutions and their data gradients
+// (defrcn/modeling/roi_heads/roi_heads.py:313-344, detectron2 BottleneckBlock) and the large text-fusion GEMMs
+// (attentive_modules.py:123-126,166-175,71-75) forward, dX and dW.
+//
+// A thread-block cluster of two CTAs (one SM pair) owns a 256 x BN output tile.  Per 64-wide K block each CTA brings its
+// own 128 rows of A and its own BN/2 rows of B into shared memory with TMA (128B swizzle); the pair's leader issues ONE
+// tcgen05.mma.cta_group::2 (M = 256, N = BN, K = 16) x 4 that reads both CTAs' shared memory, so every operand byte is
+// fetched once per pair and each SM's shared-memory read traffic per flop is half that of a single-CTA tile.  Each CTA's
+// TMEM holds the 128 x BN fp32 accumulator of its own rows, double-buffered: 8 epilogue warps per CTA drain tile i while
+// the MMAs of tile i+1 run.  Persistent: cluster c walks tiles c, c + #clusters, ... (m fastest: the concurrently running
+// clusters share a B panel in L2).
+//
+// A operand sources (per K block):
+//   plain     2-D K-major [M][K] (TMA box 64 x 128), optionally a second tensor A2 for the tail of K ("K-concat":
+//             out = [A | A2] . B^T — the bottleneck's conv3 + shortcut in one accumulator);
+//   M-major   2-D [K][M] (the transposed operand of a weight-gradient product, no transposed copy in HBM);
+//   conv3x3   4-D NHWC activation (R, 4, 4, C): K block kb = (tap, 64 channels); the box of 8 ROIs x 4 x 4 pixels x 64
+//             channels is fetched at pixel offset (dy-1, dx-1) and TMA's out-of-bounds zero fill IS the padding.
+// B: K-major [N][K] or N-major [K][N].
+// Epilogue (fp32, per 32-column chunk, lane = output row): + bias[n], + residual[m][n] (bf16, TMA-loaded), ReLU,
+// ReLU-backward gate from a packed 1-bit mask or a bf16 activation, then bf16 output through swizzled shared-memory
+// staging and TMA stores (coalesced 64-byte rows, M / N tails clipped by TMA), an optional second bf16 copy, an optional
+// fp32 output (direct 128-byte row stores, optionally accumulating), and the packed 1-bit mask (out > 0) for the backward.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace b200 {
+
+constexpr int kG2BK = 64;            // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int kG2Threads = 320;      // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2..9: epilogue
+constexpr int kG2EpiWarps = 8;
+constexpr int kG2StageOutBytes = 2048;   // 32 rows x 32 bf16, 64B swizzle
+
+struct Gemm2Args {
+  const float* bias;
+  const __nv_bfloat16* mask_act;     // ReLU backward gate from a bf16 activation [M][ldmask] (zero where <= 0)
+  int ldmask;
+  const uint32_t* mask_bits;         // ... or from a packed mask [M][ldbits_in] (bit n % 32 of word n / 32)
+  int ldbits_in;
+  uint32_t* bits_out;                // packed mask of the output (value > 0 after the activation) [M][ldbits_out]
+  int ldbits_out;
+  float* d_f32;                      // optional fp32 output [M][ldd32] (direct stores), `accumulate`: D += result
+  int ldd32;
+  int accumulate;
+  float* rowmean_out;                // optional: mean over each group of 16 consecutive rows -> [M/16][ld_rowmean] fp32
+  int ld_rowmean;
+  int M, N;
+  int kb1, kb2;                      // K blocks taken from A (map_a) and from A2 (map_a2)
+  int conv_cb;                       // conv3x3 mode: K blocks per tap (C / 64); 0 = plain
+  int a_mn, b_mn;                    // operand stored M- / N-contiguous
+  int relu;
+  int has_out, has_out2, has_res;    // map_d / map_d2 / map_res are valid
+};
+
+template <int BN> struct G2Cfg {
+  static constexpr int kABytes = 128 * kG2BK * 2;                 // 16 KB: this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * kG2BK * 2;            // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;                        // two accumulators
+  static constexpr int kEpiBytesPerWarp = 4 * kG2StageOutBytes + 512;   // out x2, residual x2, bias slice
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kG2EpiWarps * kEpiBytesPerWarp + kBarBytes + 1024 /*align*/;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
+                  const __grid_constant__ CUtensorMap map_d2, const __grid_constant__ CUtensorMap map_res,
+                  const Gemm2Args p) {
+  using Cfg = G2Cfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* epi = tiles + S * Cfg::kStageBytes;                                   // 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + kG2EpiWarps * Cfg::kEpiBytesPerWarp);
+  uint64_t* empty_bar = full_bar + S;
+  uint64_t* acc_full = empty_bar + S;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* res_bar = acc_empty + 2;                      // [warp][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kG2EpiWarps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                // 0 = leader of the pair
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int m_tiles = (p.M + 255) / 256, n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.conv_cb ? 9 * p.conv_cb : p.kb1 + p.kb2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.kb2) tma_prefetch_desc(&map_a2);
+    if (p.has_out) tma_prefetch_desc(&map_d);
+    if (p.has_out2) tma_prefetch_desc(&map_d2);
+    if (p.has_res) tma_prefetch_desc(&map_res);
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 2 * kG2EpiWarps); }
+    for (int i = 0; i < 2 * kG2EpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                     // both CTAs' barriers are initialised, both TMEM allocations done
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer (both CTAs): own A rows, own half of B; the bytes of both CTAs complete on the LEADER's barrier
+    if (lane == 0) {
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m0 = (t % m_tiles) * 256 + (int)rank * 128;
+        const int n0 = (t / m_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t sa = smem_u32(tiles + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+          if (p.conv_cb) {
+            const int tap = kb / p.conv_cb, kc = kb - tap * p.conv_cb;
+            tma_load_4d_pair(sa, &map_a, bar, kc * kG2BK, tap % 3 - 1, tap / 3 - 1, m0 >> 4);
+          } else if (p.a_mn) {
+            const int k0 = kb * kG2BK;                   // source [K][M]: two boxes of 64 m x 64 k
+            tma_load_2d_pair(sa, &map_a, bar, m0, k0);
+            tma_load_2d_pair(sa + 8192, &map_a, bar, m0 + 64, k0);
+          } else if (kb < p.kb1) {
+            tma_load_2d_pair(sa, &map_a, bar, kb * kG2BK, m0);
+          } else {
+            tma_load_2d_pair(sa, &map_a2, bar, (kb - p.kb1) * kG2BK, m0);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * 8192, &map_b, bar, n0 + 64 * c, kb * kG2BK);
+          } else {
+            tma_load_2d_pair(sb, &map_b, bar, kb * kG2BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue: the leader's elected lane, for the pair
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, BN, p.a_mn, p.b_mn);
+      // descriptor step per 16 k: K-major +32 B inside the swizzle row; MN-major +16 rows of 128 B
+      const uint64_t a_step = p.a_mn ? (2048 >> 4) : (32 >> 4), b_step = p.b_mn ? (2048 >> 4) : (32 >> 4);
+      const uint32_t a_lbo = p.a_mn ? 8192 : 0, b_lbo = p.b_mn ? 8192 : 0;
+      int it = 0, lt = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(tiles + s * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
+            const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo), bdesc = make_smem_desc_sw128(sb, b_lbo);
+#pragma unroll
+            for (int k = 0; k < kG2BK / 16; ++k)
+              umma_bf16_pair(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[s], 3);                        // both CTAs' stage s is reusable
+            if (kb == num_kb - 1) umma_commit_pair(&acc_full[buf], 3); // both CTAs' accumulator halves are complete
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---- epilogue: 8 warps per CTA; warp w reads TMEM lane quarter w % 4 (32 rows) and one column half of the tile
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    constexpr int kCw = BN / 2;                              // columns per warp
+    constexpr int kChunks = kCw / 32;
+    const int cbeg = half * kCw;
+    unsigned char* my = epi + ew * Cfg::kEpiBytesPerWarp;
+    const uint32_t s_out = smem_u32(my), s_res = s_out + 2 * kG2StageOutBytes;
+    float* s_bias = reinterpret_cast<float*>(my + 4 * kG2StageOutBytes);
+    uint64_t* rbar = res_bar + 2 * ew;
+    const int swz = (lane >> 1) & 3;                         // 64B swizzle: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
+    const uint32_t row_off = (uint32_t)lane * 64;
+    int lt = 0;
+    uint32_t gc = 0;                                         // running chunk counter of this warp (staging buffer parity)
+    auto issue_res = [&](int t, int ci, uint32_t g) {        // lane 0: residual box of tile t, chunk ci -> buffer g & 1
+      const int m0 = (t % m_tiles) * 256 + (int)rank * 128 + q * 32;
+      const int n0 = (t / m_tiles) * BN + cbeg + ci * 32;
+      mbar_expect_tx(&rbar[g & 1], kG2StageOutBytes);
+      tma_load_2d_u32(s_res + (g & 1) * kG2StageOutBytes, &map_res, &rbar[g & 1], n0, m0);
+    };
+    if (p.has_res && lane == 0 && cluster_id < num_tiles) issue_res(cluster_id, 0, 0);
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+      const int m0 = (t % m_tiles) * 256 + (int)rank * 128, n0 = (t / m_tiles) * BN;
+      const int buf = lt & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      __syncwarp();                                          // previous tile's reads of the bias slice are done
+      for (int i = lane; i < kCw; i += 32) s_bias[i] = (p.bias && n0 + cbeg + i < p.N) ? __ldg(p.bias + n0 + cbeg + i) : 0.f;
+      __syncwarp();
+      // operands of the first chunk that come straight from global memory, fetched before the accumulator is ready
+      uint4 pm[4];
+      float4 pa[8];
+      uint32_t pbits = 0xffffffffu;
+      const bool vec32 = p.d_f32 && (p.ldd32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d_f32) & 15) == 0);
+      const bool vecm = p.mask_act && (p.ldmask % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_act) & 15) == 0);
+      auto prefetch = [&](int ci) {
+        const int col = n0 + cbeg + ci * 32;
+        const bool in = row_ok && ci < kChunks && col + 32 <= p.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pm[i] = (vecm && in) ? __ldg(reinterpret_cast<const uint4*>(p.mask_act + (size_t)row * p.ldmask + col) + i)
+                               : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          pa[i] = (p.accumulate && vec32 && in) ? *(reinterpret_cast<const float4*>(p.d_f32 + (size_t)row * p.ldd32 + col) + i)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.mask_bits) pbits = (row_ok && ci < kChunks && col < p.N) ? __ldg(p.mask_bits + (size_t)row * p.ldbits_in + (col >> 5)) : 0u;
+      };
+      prefetch(0);
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int ci = 0; ci < kChunks; ++ci, ++gc) {
+        const int c0 = cbeg + ci * 32;
+        const int col = n0 + c0;
+        // residual of the NEXT chunk (this tile or the next one) goes in flight now; its buffer was last read, by every
+        // lane, in the previous chunk
+        if (p.has_res) {
+          __syncwarp();
+          if (lane == 0) {
+            if (ci + 1 < kChunks) issue_res(t, ci + 1, gc + 1);
+            else if (t + num_clusters < num_tiles) issue_res(t + num_clusters, 0, gc + 1);
+          }
+        }
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        if (ci == kChunks - 1) {                             // last read of this accumulator: hand it back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+        }
+        if (col >= p.N) {                                    // warp-uniform: chunk entirely beyond N
+          if (p.has_res) mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
+          prefetch(ci + 1);
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + (c0 - cbeg) + 4 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
+          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
+          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+        }
+        if (p.has_res) {                                     // residual tile (bf16, 64B-swizzled rows) from shared memory
+          mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
+          const uint32_t base = s_res + (gc & 1) * kG2StageOutBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + ((j ^ swz) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+              v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.mask_bits) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (!(pbits & (1u << i))) v[i] = 0.f;
+        }
+        const bool full = col + 32 <= p.N;                   // warp-uniform
+        if (p.mask_act) {
+          if (vecm && full) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t w[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if ((w[j] & 0x8000u) || !(w[j] & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
+                if ((w[j] & 0x80000000u) || !(w[j] & 0x7fff0000u)) v[8 * i + 2 * j + 1] = 0.f;
+              }
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col + i < p.N && !(__bfloat162float(p.mask_act[(size_t)row * p.ldmask + col + i]) > 0.f)) v[i] = 0.f;
+          }
+        }
+        if (p.d_f32) {
+          if (vec32 && full) {
+            if (p.accumulate) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[4 * i] += pa[i].x; v[4 * i + 1] += pa[i].y; v[4 * i + 2] += pa[i].z; v[4 * i + 3] += pa[i].w; }
+            }
+            if (row_ok) {
+              float4* dst = reinterpret_cast<float4*>(p.d_f32 + (size_t)row * p.ldd32 + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col + i >= p.N) continue;
+              float* dst = p.d_f32 + (size_t)row * p.ldd32 + col + i;
+              if (p.accumulate) v[i] += *dst;
+              *dst = v[i];
+            }
+          }
+        }
+        prefetch(ci + 1);                                    // next chunk's global operands, in flight during the stores below
+        if (p.bits_out && row_ok) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (v[i] > 0.f) w |= 1u << i;
+          p.bits_out[(size_t)row * p.ldbits_out + (col >> 5)] = w;
+        }
+        if (p.rowmean_out) {
+          // mean over the 16 rows (the 4x4 pixels) of each ROI: lanes 0-15 hold one ROI, lanes 16-31 the next.  Butterfly
+          // reduce-scatter: at distance 8, 4, 2, 1 a lane keeps one half of its columns and adds the partner's copy of
+          // them, so 30 shuffles leave lane l (of 16) with the sums of columns 2l and 2l + 1.
+          float u[16];
+          {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool up = lane & 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float send = up ? u[i] : u[i + 8], keep = up ? u[i + 8] : u[i];
+              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+          }
+          {
+            const bool up = lane & 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? u[i] : u[i + 4], keep = up ? u[i + 4] : u[i];
+              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+          }
+          {
+            const bool up = lane & 1;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? u[i] : u[i + 2], keep = up ? u[i + 2] : u[i];
+              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+          }
+          const int roi = ((m0 + q * 32) >> 4) + (lane >> 4);
+          const int cc = col + 2 * (lane & 15);
+          if (roi * 16 < p.M) {
+            float* dst = p.rowmean_out + (size_t)roi * p.ld_rowmean + cc;
+            if (cc < p.N) dst[0] = u[0] * (1.f / 16.f);
+            if (cc + 1 < p.N) dst[1] = u[1] * (1.f / 16.f);
+          }
+        }
+        if (p.has_out || p.has_out2) {
+          // staging buffer gc & 1 was last read by the TMA store(s) of chunk gc - 2
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t base = s_out + (gc & 1) * kG2StageOutBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((j ^ swz) << 4)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t src = s_out + (gc & 1) * kG2StageOutBytes;
+            if (p.has_out) tma_store_2d(&map_d, src, col, m0 + q * 32);
+            if (p.has_out2) tma_store_2d(&map_d2, src, col, m0 + q * 32);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();            // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  PFN_encodeTiled enc = get_tensor_map_encoder();
+  if (!enc) { set_error("gemm2: cuTensorMapEncodeTiled unavailable"); return B200_ERR_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm2: cuTensorMapEncodeTiled(%s) failed (%d)", what, (int)r); return B200_ERR_CUDA; }
+  return B200_OK;
+}
+// 2-D bf16 [rows][cols] row-major, leading dimension ld (elements)
+static int map_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_cols, int box_rows,
+                  CUtensorMapSwizzle swz, const char* what) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  return encode_map(m, ptr, 2, dims, strides, box, swz, what);
+}
+
+template <int BN>
+static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
+  CUtensorMap ma, ma2, mb, md, md2, mr;
+  Gemm2Args a = {};
+  const int K1 = d->K, K2 = d->A2 ? d->K2 : 0;
+  int rc;
+  if (d->conv_c) {
+    // A: (R, 4, 4, C) NHWC; box = 64 channels x 4 x 4 pixels x 8 ROIs = 128 rows of 128 B
+    cuuint64_t dims[4] = {(cuuint64_t)d->conv_c, 4, 4, (cuuint64_t)(d->M / 16)};
+    cuuint64_t strides[3] = {(cuuint64_t)d->conv_c * 2, (cuuint64_t)d->conv_c * 8, (cuuint64_t)d->conv_c * 32};
+    cuuint32_t box[4] = {(cuuint32_t)kG2BK, 4, 4, 8};
+    rc = encode_map(&ma, d->A, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "A conv");
+  } else if (d->a_mn) {
+    rc = map_2d(&ma, d->A, K1, d->M, d->lda, 64, kG2BK, CU_TENSOR_MAP_SWIZZLE_128B, "A mn");
+  } else {
+    rc = map_2d(&ma, d->A, d->M, K1, d->lda, kG2BK, 128, CU_TENSOR_MAP_SWIZZLE_128B, "A");
+  }
+  if (rc != B200_OK) return rc;
+  ma2 = ma;
+  if (K2) {
+    rc = map_2d(&ma2, d->A2, d->M, K2, d->lda2, kG2BK, 128, CU_TENSOR_MAP_SWIZZLE_128B, "A2");
+    if (rc != B200_OK) return rc;
+  }
+  const int Ktot = d->conv_c ? 9 * d->conv_c : K1 + K2;
+  if (d->b_mn) rc = map_2d(&mb, d->B, Ktot, d->N, d->ldb, 64, kG2BK, CU_TENSOR_MAP_SWIZZLE_128B, "B mn");
+  else rc = map_2d(&mb, d->B, d->N, Ktot, d->ldb, kG2BK, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, "B");
+  if (rc != B200_OK) return rc;
+  md = ma; md2 = ma; mr = ma;
+  if (d->out_bf16) {
+    rc = map_2d(&md, d->out_bf16, d->M, d->N, d->ld_out, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "out");
+    if (rc != B200_OK) return rc;
+  }
+  if (d->out2_bf16) {
+    rc = map_2d(&md2, d->out2_bf16, d->M, d->N, d->ld_out2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "out2");
+    if (rc != B200_OK) return rc;
+  }
+  if (d->residual) {
+    rc = map_2d(&mr, d->residual, d->M, d->N, d->ld_res, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "residual");
+    if (rc != B200_OK) return rc;
+  }
+  a.bias = d->bias;
+  a.mask_act = (const __nv_bfloat16*)d->mask_act; a.ldmask = d->ld_mask;
+  a.mask_bits = (const uint32_t*)d->mask_bits; a.ldbits_in = d->ld_mask_bits;
+  a.bits_out = (uint32_t*)d->bits_out; a.ldbits_out = d->ld_bits_out;
+  a.d_f32 = d->out_f32; a.ldd32 = d->ld_out_f32; a.accumulate = d->accumulate;
+  a.rowmean_out = d->rowmean_out; a.ld_rowmean = d->ld_rowmean;
+  a.M = d->M; a.N = d->N;
+  a.kb1 = ceil_div(K1, kG2BK); a.kb2 = ceil_div(K2, kG2BK);
+  a.conv_cb = d->conv_c / kG2BK;
+  a.a_mn = d->a_mn; a.b_mn = d->b_mn; a.relu = d->relu;
+  a.has_out = d->out_bf16 != nullptr; a.has_out2 = d->out2_bf16 != nullptr; a.has_res = d->residual != nullptr;
+
+  auto kern = gemm2_pair_kernel<BN>;
+  B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<BN>::kSmemBytes));
+  const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, BN);
+  int clusters = min(tiles, kNumSMs / 2);
+  if (d->max_clusters > 0) clusters = min(clusters, d->max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kG2Threads);
+  cfg.dynamicSmemBytes = G2Cfg<BN>::kSmemBytes;
+  cfg.stream = st;
+  B200_CUDA_CALL(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, md, md2, mr, a));
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
+  B200_CHECK_ARG(d, "gemm2: null descriptor");
+  B200_CHECK_ARG(d->A && d->B, "gemm2: null operand");
+  B200_CHECK_ARG(d->out_bf16 || d->out2_bf16 || d->out_f32 || d->rowmean_out, "gemm2: no output");
+  B200_CHECK_ARG(d->M >= 0 && d->N > 0 && d->K > 0, "gemm2: bad shape");
+  B200_CHECK_ARG(!d->accumulate || d->out_f32, "gemm2: accumulate needs an fp32 output");
+  B200_CHECK_ARG(!(d->mask_act && d->mask_bits), "gemm2: one ReLU-backward gate at most");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(d->A) || !al16(d->B) || !al16(d->A2) || !al16(d->out_bf16) || !al16(d->out2_bf16) || !al16(d->residual)) {
+    set_error("gemm2: bf16 tensors must be 16-byte aligned (TMA)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (d->lda % 8 || d->ldb % 8 || (d->A2 && d->lda2 % 8) || (d->out_bf16 && d->ld_out % 8) || (d->out2_bf16 && d->ld_out2 % 8) ||
+      (d->residual && d->ld_res % 8)) {
+    set_error("gemm2: leading dimensions of bf16 tensors must be multiples of 8 (TMA)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (d->conv_c) {
+    B200_CHECK_ARG(d->conv_c % kG2BK == 0 && d->M % 16 == 0 && !d->A2 && !d->a_mn && d->K == 9 * d->conv_c,
+                   "gemm2: conv3x3 mode needs C %% 64 == 0, M = 16 R, K = 9 C, a K-major 4x4 NHWC activation");
+  } else {
+    B200_CHECK_ARG(d->K % 8 == 0, "gemm2: K must be a multiple of 8");
+    B200_CHECK_ARG(!d->A2 || (d->K % kG2BK == 0 && d->K2 > 0 && d->K2 % 8 == 0 && !d->a_mn && !d->b_mn),
+                   "gemm2: K-concat needs K %% 64 == 0 and K-major operands");
+  }
+  B200_CHECK_ARG(!d->bits_out || (d->N % 32 == 0), "gemm2: bits_out needs N %% 32 == 0");
+  B200_CHECK_ARG(!d->rowmean_out || d->M % 16 == 0, "gemm2: rowmean_out needs M %% 16 == 0");
+  if (d->M == 0) return B200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int bn = d->tile_n;
+  if (bn == 0) {
+    // 256-wide tiles unless that leaves SM pairs idle for most of the launch
+    const int mt = ceil_div(d->M, 256);
+    bn = (d->N > 128 && mt * ceil_div(d->N, 256) >= kNumSMs / 2) ? 256 : 128;
+    if (d->N <= 128) bn = 128;
+  }
+  B200_CHECK_ARG(bn == 128 || bn == 256, "gemm2: tile_n must be 0, 128 or 256");
+  return bn == 256 ? launch_gemm2<256>(d, st) : launch_gemm2<128>(d, st);
+}

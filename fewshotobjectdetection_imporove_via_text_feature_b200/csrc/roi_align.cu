@@ -620,11 +620,8 @@ extern "C" int b200_roi_align_fwd(const void* feat, const float* rois, const int
     if (rc != B200_OK) return rc;
     const int warps = max(2, pooled_h);
     const size_t smem = (size_t)pooled_h * (kWarpRingBytes + kWarpOutBytes) + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-      B200_CUDA_CALL(cudaFuncSetAttribute(roi_align_fwd_tma_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kWarpRingBytes + kWarpOutBytes) + 1024));
-      attr_done = true;
-    }
+    // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
+    B200_CUDA_CALL(cudaFuncSetAttribute(roi_align_fwd_tma_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (kWarpRingBytes + kWarpOutBytes) + 1024));
     roi_align_fwd_tma_bf16_kernel<<<R, 32 * warps, smem, st>>>(fmap, (const __nv_bfloat16*)f, rois, (__nv_bfloat16*)out, C, H,
                                                                W, pooled_h, pooled_w, spatial_scale, sampling_ratio, aligned);
     B200_CUDA_LAUNCH_CHECK("roi_align_fwd_tma");

@@ -233,11 +233,8 @@ extern "C" int b200_rpn_select_proposals(const float* proposals, const float* lo
   w.nms_bytes = workspace_bytes - (size_t)(p - (unsigned char*)workspace);
 
   const size_t smem = (size_t)kRpnMaxTopk * 8 + 32 * 256 * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_CALL(cudaFuncSetAttribute(rpn_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
+  B200_CUDA_CALL(cudaFuncSetAttribute(rpn_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rpn_topk_filter_kernel<<<N, kRpnThreads, smem, st>>>(proposals, logits, level_offsets, image_hw, A, L, pre_nms_topk,
                                                       cap_per_image, min_box_size, w.cand_boxes, w.cand_scores,
                                                       w.cand_lvl, w.seg_offsets, w.cand_count, n_invalid);

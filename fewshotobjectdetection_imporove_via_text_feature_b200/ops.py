@@ -482,6 +482,79 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
     return out
 
 
+GEMM2_TILE_N = [0]          # tests / microbenchmarks force 128 or 256
+GEMM2_MAX_CLUSTERS = [0]    # tests lower it to force several tiles per CTA pair on small shapes
+
+
+def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residual=None, relu=False, mask_act=None,
+          mask_bits=None, out=None, out2=None, out_f32=None, accumulate=False, bits_out=None, rowmean_out=None,
+          want_out=True, M=None):
+    """CTA-pair tcgen05 GEMM / implicit 3x3 convolution (csrc/gemm2_tcgen05.cu, `b200_gemm2`).
+
+    out[M,N] = epi([a | a2] @ b^T): a (M,K) bf16 (a_mn: stored (K,M)); conv_c: `a` is the NHWC activation (R,4,4,C) viewed
+    as (16 R, C) and K = 9 C; b (N,K) bf16 (b_mn: stored (K,N)).  Epilogue: + bias, + residual (bf16), ReLU, ReLU-backward
+    gate (mask_bits packed uint32 | mask_act bf16).  Outputs: `out` bf16 (allocated unless want_out=False), out2 bf16,
+    out_f32 (+= when accumulate), bits_out (packed out > 0), rowmean_out (mean over groups of 16 rows)."""
+    _require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    if conv_c:
+        assert a.dim() == 2 and a.shape[1] == conv_c and a.is_contiguous() and a.shape[0] % 16 == 0
+        Mx, K = a.shape[0], 9 * conv_c
+    elif a_mn:
+        K, Mx = a.shape
+    else:
+        Mx, K = a.shape
+    M = Mx if M is None else M
+    K2 = 0 if a2 is None else a2.shape[1]
+    if b_mn:
+        assert b.shape[0] == K and a2 is None
+        N = b.shape[1]
+    else:
+        N = b.shape[0]
+        assert b.shape[1] == K + K2, (a.shape, b.shape, K2)
+    dev = a.device
+    if out is None and want_out:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    for t in (out, out2, residual, mask_act):
+        assert t is None or (t.dtype == torch.bfloat16 and tuple(t.shape) == (M, N) and t.stride(1) == 1), (M, N)
+    assert out_f32 is None or (out_f32.dtype == torch.float32 and tuple(out_f32.shape) == (M, N) and out_f32.stride(1) == 1)
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    d = _lib.Gemm2Desc()
+    d.A, d.lda = a.data_ptr(), a.stride(0)
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and a2.shape[0] == M and a2.stride(1) == 1
+        d.A2, d.lda2, d.K2 = a2.data_ptr(), a2.stride(0), K2
+    d.B, d.ldb = b.data_ptr(), b.stride(0)
+    d.M, d.N, d.K = M, N, K
+    d.a_mn, d.b_mn, d.conv_c = int(a_mn), int(b_mn), int(conv_c)
+    d.bias = _ptr(b32)
+    if residual is not None:
+        d.residual, d.ld_res = residual.data_ptr(), residual.stride(0)
+    d.relu = int(relu)
+    if mask_act is not None:
+        d.mask_act, d.ld_mask = mask_act.data_ptr(), mask_act.stride(0)
+    if mask_bits is not None:
+        assert mask_bits.dtype in (torch.int32, torch.uint32) and mask_bits.shape[0] == M and mask_bits.stride(1) == 1
+        d.mask_bits, d.ld_mask_bits = mask_bits.data_ptr(), mask_bits.stride(0)
+    if out is not None:
+        d.out_bf16, d.ld_out = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        d.out2_bf16, d.ld_out2 = out2.data_ptr(), out2.stride(0)
+    if out_f32 is not None:
+        d.out_f32, d.ld_out_f32, d.accumulate = out_f32.data_ptr(), out_f32.stride(0), int(accumulate)
+    if bits_out is not None:
+        assert bits_out.dtype in (torch.int32, torch.uint32) and tuple(bits_out.shape) == (M, N // 32) and bits_out.stride(1) == 1
+        d.bits_out, d.ld_bits_out = bits_out.data_ptr(), bits_out.stride(0)
+    if rowmean_out is not None:
+        assert rowmean_out.dtype == torch.float32 and tuple(rowmean_out.shape) == (M // 16, N) and rowmean_out.stride(1) == 1
+        d.rowmean_out, d.ld_rowmean = rowmean_out.data_ptr(), rowmean_out.stride(0)
+    d.tile_n, d.max_clusters = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0]
+    import ctypes
+    _lib.call("b200_gemm2", ctypes.byref(d), _stream(),
+              tag=(2.0 * M * N * (K + K2), ("gemm2", M, N, K + K2, int(conv_c), int(a_mn), int(b_mn))))
+    return out
+
+
 def text_attention(q, x, kp, vp, p1, p2, scores=None):
     """softmax(q Kp^T / sqrt(d)) Vp and the gate operands P1 = O*x, P2 = x-O (bf16, written into p1/p2).
     With `scores` (R,L) fp32 given (already scaled), q/kp are not used."""

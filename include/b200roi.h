@@ -10,8 +10,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless named host_*; no allocation happens inside the library:
  *     the caller passes outputs and (where needed) a workspace sized by the matching *_workspace_bytes();
- *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream, and
- *     keeps no global state;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and re-entrant per stream.  The only
+ *     process-wide state is the set of implementation switches of b200_set_option (A/B measurement and tests; every
+ *     setting computes the same results) and a cached driver entry point; neither is written after start-up by the
+ *     compute calls themselves;
  *   - return value: B200_OK or a negative B200_ERR_*; never throws.  b200_last_error() returns a
  *     thread-local description of the last failure on the calling thread;
  *   - dtype: B200_F32 | B200_BF16 (storage type of the feature maps / activations; accumulation is fp32);
@@ -172,6 +174,50 @@ B200_API int b200_gemm_bf16(const void* A, int lda, const void* B, int ldb, cons
 B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, const float* bias, void* D, int ldd,
                       int out_dtype, void* D2, int ldd2, int M, int N, int K, int relu, int accumulate,
                       const void* mask, int ldmask, b200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * P2 + the wide products of A1..A5 and their gradients: CTA-pair tcgen05 GEMM / implicit-GEMM convolution.
+ *   D[M,N] = epi( [A | A2][M, K (+K2)] * B[N, K (+K2)]^T )      bf16 operands, fp32 accumulation
+ * Replaces, with FrozenBN folded into the weights, the detectron2 BottleneckBlock convolutions the reference builds at
+ * defrcn/modeling/roi_heads/roi_heads.py:313-337 and runs at :339-344 (1x1 convolutions = GEMMs over the NHWC pixels;
+ * the 3x3 convolution = implicit GEMM whose A operand is fetched tap by tap by TMA with out-of-bounds zero fill as the
+ * padding), their data gradients (autograd of the same), the `mean(dim=[2,3])` of roi_heads.py:1109 (rowmean_out), and
+ * the nn.Linear products of attentive_modules.py:123-126,166-175,71-75 / their dX = dY W and dW = dY^T X without
+ * transposed copies (a_mn / b_mn: the operand is stored M- / N-contiguous, i.e. transposed, in memory).
+ *
+ *   A         bf16.  a_mn = 0: [M][lda] (K contiguous);  a_mn = 1: [K][lda] (M contiguous);
+ *             conv_c > 0: NHWC activation (M/16, 4, 4, conv_c) contiguous, K = 9 * conv_c ordered (tap = ky*3+kx, channel),
+ *             stride 1, padding 1 (lda unused)
+ *   A2, K2    optional second K segment (K-major, [M][lda2]); requires K % 64 == 0
+ *   B         bf16.  b_mn = 0: [N][ldb] (K contiguous, K + K2 columns);  b_mn = 1: [K][ldb] (N contiguous)
+ *   epilogue  v = acc + bias[n] (fp32, optional) + residual[m][n] (bf16, optional);  relu != 0: v = max(v, 0);
+ *             mask_bits (packed, bit n%32 of word [m][n/32]) or mask_act (bf16 activation): v = 0 where the bit is clear /
+ *             the activation is <= 0  (ReLU backward)
+ *   outputs   out_bf16 / out2_bf16 [M][ld] (TMA stores), out_f32 [M][ld_out_f32] (accumulate != 0: +=),
+ *             bits_out: packed (v > 0) [M][ld_bits_out] words (needs N % 32 == 0),
+ *             rowmean_out [M/16][ld_rowmean] fp32: mean of v over each group of 16 consecutive rows (the 4x4 pixels of a ROI)
+ *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it)
+ * Alignment: bf16 tensors 16-byte aligned, their leading dimensions multiples of 8 elements.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct b200_gemm2_desc {
+  const void* A; int lda;
+  const void* A2; int lda2; int K2;
+  const void* B; int ldb;
+  int M, N, K;
+  int a_mn, b_mn, conv_c;
+  const float* bias;
+  const void* residual; int ld_res;
+  int relu;
+  const void* mask_act; int ld_mask;
+  const void* mask_bits; int ld_mask_bits;
+  void* out_bf16; int ld_out;
+  void* out2_bf16; int ld_out2;
+  float* out_f32; int ld_out_f32; int accumulate;
+  void* bits_out; int ld_bits_out;
+  float* rowmean_out; int ld_rowmean;
+  int tile_n, max_clusters;
+} b200_gemm2_desc;
+B200_API int b200_gemm2(const b200_gemm2_desc* desc, b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fine-tuning direction (BASELINE configs[1]): what autograd does for the reference's torch modules.

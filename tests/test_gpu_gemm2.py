@@ -1,0 +1,184 @@
+"""CTA-pair tcgen05 GEMM / implicit 3x3 convolution (csrc/gemm2_tcgen05.cu, `b200_gemm2`) vs fp64 torch on the same
+bf16-rounded operands.  Tolerances: fp32 outputs 1e-3 (accumulation order only); bf16 outputs one bf16 rounding (2^-8
+relative, written as rtol = atol = 1e-2 like the single-CTA kernel's test); packed masks and row gates bit-exact against
+the kernel's own bf16 output."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    return ops
+
+
+def _rand(gen, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).to(torch.bfloat16)
+
+
+def _bits_of(t):
+    """packed (t > 0) words of a (M, N) tensor, bit n % 32 of word n / 32."""
+    M, N = t.shape
+    b = (t > 0).reshape(M, N // 32, 32).to(torch.int64)
+    w = (b << torch.arange(32, dtype=torch.int64)).sum(-1)
+    return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+
+
+def _unpack(words, N):
+    w = words.cpu().to(torch.int64) & 0xffffffff
+    return ((w[:, :, None] >> torch.arange(32, dtype=torch.int64)) & 1).reshape(w.shape[0], -1)[:, :N].bool()
+
+
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 200), (256, 128, 64), (4096, 2048, 1024), (77, 200, 72), (513, 520, 4096)])
+def test_gemm2_plain(M, N, K, tile_n):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(M + N + K)
+    a, b = _rand(gen, M, K, scale=0.5), _rand(gen, N, K, scale=0.05)
+    bias = torch.randn(N, generator=gen)
+    ref = a.double() @ b.double().t() + bias.double()
+    ops.GEMM2_TILE_N[0] = tile_n
+    try:
+        out = ops.gemm2(a.cuda(), b.cuda(), bias=bias.cuda())
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+        of = torch.full((M, N), 7.0, device="cuda")
+        out2 = torch.empty(M, N + 8, dtype=torch.bfloat16, device="cuda")[:, :N]
+        outr = ops.gemm2(a.cuda(), b.cuda(), bias=bias.cuda(), relu=True, out2=out2, out_f32=of)
+        torch.testing.assert_close(of.cpu().double(), ref.clamp_min(0), rtol=1e-3, atol=1e-3)
+        assert torch.equal(outr, out2) and torch.equal(outr.float(), of.to(torch.bfloat16).float())
+        # accumulate into the fp32 output
+        ops.gemm2(a.cuda(), b.cuda(), out_f32=of, accumulate=True, want_out=False)
+        torch.testing.assert_close(of.cpu().double(), ref.clamp_min(0) + ref - bias.double(), rtol=1e-3, atol=2e-3)
+    finally:
+        ops.GEMM2_TILE_N[0] = 0
+
+
+@pytest.mark.parametrize("clusters", [1, 3])
+@pytest.mark.parametrize("tile_n", [128, 256])
+def test_gemm2_many_tiles_per_pair(clusters, tile_n):
+    """Few CTA pairs walk many tiles: stage / accumulator / staging-buffer phases wrap several times; every epilogue
+    option rides along.  The result must not depend on the number of pairs."""
+    ops = _ops()
+    M, N, K = 1300, 768, 328
+    gen = torch.Generator().manual_seed(5)
+    a, b = _rand(gen, M, K, scale=0.5).cuda(), _rand(gen, N, K, scale=0.05).cuda()
+    bias = torch.randn(N, generator=gen).cuda()
+    res = _rand(gen, M, N).cuda()
+    act = _rand(gen, M, N).cuda()
+    bits = _bits_of(act.cpu()).cuda()
+
+    def run():
+        o1 = ops.gemm2(a, b, bias=bias, residual=res, relu=True, bits_out=(bo := torch.zeros(M, N // 32, dtype=torch.int32, device="cuda")))
+        o2 = ops.gemm2(a, b, residual=res, mask_bits=bits)
+        o3 = ops.gemm2(a, b, mask_act=act)
+        return o1, bo, o2, o3
+    ops.GEMM2_TILE_N[0] = tile_n
+    try:
+        base = run()
+        ops.GEMM2_MAX_CLUSTERS[0] = clusters
+        few = run()
+    finally:
+        ops.GEMM2_TILE_N[0], ops.GEMM2_MAX_CLUSTERS[0] = 0, 0
+    for x, y in zip(base, few):
+        assert torch.equal(x, y)
+    o1, bo, o2, o3 = (t.cpu() for t in base)
+    prod = a.cpu().double() @ b.cpu().double().t()
+    ref1 = (prod + bias.cpu().double() + res.cpu().double()).clamp_min(0)
+    torch.testing.assert_close(o1.double(), ref1, rtol=1e-2, atol=1e-2)
+    assert torch.equal(_unpack(bo, N), o1 > 0)                      # the packed mask is the sign of the stored output
+    gate = act.cpu() > 0
+    torch.testing.assert_close(o2.double(), (prod + res.cpu().double()) * gate, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(o3.double(), prod * gate, rtol=1e-2, atol=1e-2)
+    assert bool((o2[~gate] == 0).all()) and bool((o3[~gate] == 0).all())
+
+
+def test_gemm2_k_concat():
+    """out = [a | a2] b^T in one accumulator (the bottleneck's conv3 + shortcut)."""
+    ops = _ops()
+    M, N, K1, K2 = 2048, 512, 128, 320
+    gen = torch.Generator().manual_seed(11)
+    a, a2, b = _rand(gen, M, K1, scale=0.5), _rand(gen, M, K2, scale=0.5), _rand(gen, N, K1 + K2, scale=0.05)
+    out = ops.gemm2(a.cuda(), b.cuda(), a2=a2.cuda(), relu=True)
+    ref = (torch.cat([a, a2], 1).double() @ b.double().t()).clamp_min(0)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 192), (2048, 4096, 1000), (300, 200, 4096)])
+def test_gemm2_transposed_operands(M, N, K, a_mn, b_mn):
+    """a_mn / b_mn: the operand sits transposed in memory ((K, M) / (K, N)); no transposed copy is made."""
+    ops = _ops()
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("leading dimension of a transposed operand must be a multiple of 8")
+    gen = torch.Generator().manual_seed(M + N + K + 2 * a_mn + b_mn)
+    a, b = _rand(gen, M, K, scale=0.5), _rand(gen, N, K, scale=0.05)
+    ref = a.double() @ b.double().t()
+    A = a.t().contiguous().cuda() if a_mn else a.cuda()
+    B = b.t().contiguous().cuda() if b_mn else b.cuda()
+    of = torch.empty(M, N, device="cuda")
+    ops.gemm2(A, B, a_mn=a_mn, b_mn=b_mn, out_f32=of, want_out=False)
+    torch.testing.assert_close(of.cpu().double(), ref, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("R,C,N", [(64, 64, 128), (100, 512, 512), (9, 128, 256)])
+def test_gemm2_conv3x3(R, C, N):
+    """Implicit GEMM of a 3x3 / stride 1 / padding 1 convolution over (R, 4, 4, C) NHWC: TMA's zero fill is the padding."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(R + C + N)
+    x = _rand(gen, R, C, 4, 4, scale=0.5)                            # NCHW values
+    w = _rand(gen, N, C, 3, 3, scale=0.05)
+    bias = torch.randn(N, generator=gen)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).clamp_min(0)         # (R, N, 4, 4)
+    xa = x.permute(0, 2, 3, 1).contiguous().reshape(R * 16, C).cuda()                    # NHWC rows
+    wb = w.permute(0, 2, 3, 1).contiguous().reshape(N, 9 * C).cuda()                     # (co, ky, kx, ci)
+    out = ops.gemm2(xa, wb, conv_c=C, bias=bias.cuda(), relu=True)
+    got = out.cpu().reshape(R, 4, 4, N).permute(0, 3, 1, 2).double()
+    torch.testing.assert_close(got, ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm2_rowmean():
+    """rowmean_out: mean over the 16 pixels of each ROI of the epilogue's fp32 values (roi_heads.py:1109)."""
+    ops = _ops()
+    R, N, K = 300, 2048, 512
+    gen = torch.Generator().manual_seed(3)
+    a, b = _rand(gen, R * 16, K, scale=0.5), _rand(gen, N, K, scale=0.05)
+    res = _rand(gen, R * 16, N)
+    bias = torch.randn(N, generator=gen)
+    ref = (a.double() @ b.double().t() + bias.double() + res.double()).clamp_min(0)
+    rm = torch.empty(R, N, device="cuda")
+    bo = torch.zeros(R * 16, N // 32, dtype=torch.int32, device="cuda")
+    out = ops.gemm2(a.cuda(), b.cuda(), bias=bias.cuda(), residual=res.cuda(), relu=True, rowmean_out=rm, bits_out=bo)
+    torch.testing.assert_close(rm.cpu().double(), ref.reshape(R, 16, N).mean(1), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-2, atol=1e-2)
+    assert torch.equal(_unpack(bo, N), out.cpu() > 0)
+    # without the bf16 output (the last block of a frozen res5 keeps only the mean and the mask)
+    rm2 = torch.empty(R, N, device="cuda")
+    ops.gemm2(a.cuda(), b.cuda(), bias=bias.cuda(), residual=res.cuda(), relu=True, rowmean_out=rm2, want_out=False)
+    assert torch.equal(rm, rm2)
+
+
+def test_gemm2_full_size_res5_shapes():
+    """BASELINE shapes (R = 4096 ROIs): 65536 rows; checked against torch's bf16 matmul on the same GPU."""
+    ops = _ops()
+    M = 65536
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for N, K in [(512, 1024), (2048, 512)]:
+        a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+        b = (torch.randn(N, K, device="cuda", generator=gen) * 0.05).to(torch.bfloat16)
+        out = ops.gemm2(a, b, relu=True)
+        ref = torch.relu(a.float() @ b.float().t())
+        torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm2_rejects_bad_arguments():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+    ops = _ops()
+    a = torch.zeros(64, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.B200Error):
+        ops.gemm2(a[:, :60], a[:, :60])                               # K % 8 != 0
+    with pytest.raises(_lib.B200Error):
+        ops.gemm2(a, a, want_out=False)                               # no output
+    with pytest.raises(_lib.B200Error):
+        ops.gemm2(a[:, 1:57], a[:, 1:57])                             # operand not 16-byte aligned
