@@ -27,7 +27,7 @@ class Gemm2Desc(ctypes.Structure):
                 ("out_bf16", c_void_p), ("ld_out", c_int), ("out2_bf16", c_void_p), ("ld_out2", c_int),
                 ("out_f32", c_void_p), ("ld_out_f32", c_int), ("accumulate", c_int),
                 ("bits_out", c_void_p), ("ld_bits_out", c_int), ("rowmean_out", c_void_p), ("ld_rowmean", c_int),
-                ("tile_n", c_int), ("max_clusters", c_int)]
+                ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int)]
 
 
 # name -> (restype, argtypes); mirrors include/b200roi.h declaration by declaration

@@ -9,8 +9,9 @@
 // tcgen05.mma.cta_group::2 (M = 256, N = BN, K = 16) x 4 that reads both CTAs' shared memory, so every operand byte is
 // fetched once per pair and each SM's shared-memory read traffic per flop is half that of a single-CTA tile.  Each CTA's
 // TMEM holds the 128 x BN fp32 accumulator of its own rows, double-buffered: 8 epilogue warps per CTA drain tile i while
-// the MMAs of tile i+1 run.  Persistent: cluster c walks tiles c, c + #clusters, ... (m fastest: the concurrently running
-// clusters share a B panel in L2).
+// the MMAs of tile i+1 run.  Persistent: cluster c walks tiles c, c + #clusters, ... (n fastest: the n-tiles of one
+// 256-row block of A run back to back / side by side, so A streams from HBM once while the much smaller B — a weight
+// matrix — stays L2-resident).
 //
 // A operand sources (per K block):
 //   plain     2-D K-major [M][K] (TMA box 64 x 128), optionally a second tensor A2 for the tail of K ("K-concat":
@@ -33,7 +34,12 @@ namespace b200 {
 constexpr int kG2BK = 64;            // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kG2Threads = 320;      // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2..9: epilogue
 constexpr int kG2EpiWarps = 8;
-constexpr int kG2StageOutBytes = 2048;   // 32 rows x 32 bf16, 64B swizzle
+constexpr int kG2BoxBytes = 4096;    // epilogue box: 32 rows x 64 bf16 (128-byte rows, 128B swizzle)
+// epilogue features an instantiation carries (dead code for the others is compiled out)
+constexpr uint32_t kFRes = 1, kFMaskBits = 2, kFMaskAct = 4, kFF32 = 8, kFBitsOut = 16, kFRowMean = 32, kFOut2 = 64;
+constexpr uint32_t kFFwd = kFRes | kFBitsOut | kFRowMean;      // res5 forward: bias, residual, ReLU, mask out, mean
+constexpr uint32_t kFBwd = kFRes | kFMaskBits;                 // res5 backward: mask in, residual
+constexpr uint32_t kFAll = 127;
 
 struct Gemm2Args {
   const float* bias;
@@ -60,14 +66,14 @@ template <int BN> struct G2Cfg {
   static constexpr int kABytes = 128 * kG2BK * 2;                 // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kG2BK * 2;            // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kStages = BN >= 256 ? 4 : 5;
   static constexpr int kTmemCols = 2 * BN;                        // two accumulators
-  static constexpr int kEpiBytesPerWarp = 4 * kG2StageOutBytes + 512;   // out x2, residual x2, bias slice
+  static constexpr int kEpiBytesPerWarp = 3 * kG2BoxBytes;         // output staging, residual x2
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + kG2EpiWarps * kEpiBytesPerWarp + kBarBytes + 1024 /*align*/;
 };
 
-template <int BN>
+template <int BN, uint32_t F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_d,
@@ -118,8 +124,8 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m0 = (t % m_tiles) * 256 + (int)rank * 128;
-        const int n0 = (t / m_tiles) * BN + (int)rank * (BN / 2);
+        const int m0 = (t / n_tiles) * 256 + (int)rank * 128;
+        const int n0 = (t % n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
@@ -182,226 +188,260 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ---- epilogue: 8 warps per CTA; warp w reads TMEM lane quarter w % 4 (32 rows) and one column half of the tile
+    // ---- epilogue: 8 warps per CTA; warp w owns TMEM lane quarter w % 4 (32 rows, one per lane) and one column half of
+    // the tile, in 64-column chunks (two 32-column tcgen05.ld in flight together, 128-byte rows in the staging buffers).
+    // F (compile time) lists the features this instantiation carries; the descriptor's flags choose among them.
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
     constexpr int kCw = BN / 2;                              // columns per warp
-    constexpr int kChunks = kCw / 32;
+    constexpr int kChunks = kCw / 64;                        // 2 (BN = 256) or 1 (BN = 128)
     const int cbeg = half * kCw;
     unsigned char* my = epi + ew * Cfg::kEpiBytesPerWarp;
-    const uint32_t s_out = smem_u32(my), s_res = s_out + 2 * kG2StageOutBytes;
-    float* s_bias = reinterpret_cast<float*>(my + 4 * kG2StageOutBytes);
+    const uint32_t s_out = smem_u32(my), s_res = s_out + kG2BoxBytes;     // output staging x1, residual boxes x2
     uint64_t* rbar = res_bar + 2 * ew;
-    const int swz = (lane >> 1) & 3;                         // 64B swizzle: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
-    const uint32_t row_off = (uint32_t)lane * 64;
+    const int swz = lane & 7;                                // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
+    const uint32_t row_off = (uint32_t)lane * 128;
+    const bool f_res = (F & kFRes) && p.has_res;
+    const bool f_mbits = (F & kFMaskBits) && p.mask_bits;
+    const bool f_mact = (F & kFMaskAct) && p.mask_act;
+    const bool f_f32 = (F & kFF32) && p.d_f32;
+    const bool f_bout = (F & kFBitsOut) && p.bits_out;
+    const bool f_mean = (F & kFRowMean) && p.rowmean_out;
+    const bool f_out2 = (F & kFOut2) && p.has_out2;
+    const bool f_store = p.has_out || f_out2;
+    const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    const bool vec32 = f_f32 && (p.ldd32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d_f32) & 15) == 0);
+    const bool vecm = f_mact && (p.ldmask % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_act) & 15) == 0);
     int lt = 0;
-    uint32_t gc = 0;                                         // running chunk counter of this warp (staging buffer parity)
+    uint32_t gc = 0;                                         // running chunk counter of this warp (residual buffer parity)
     auto issue_res = [&](int t, int ci, uint32_t g) {        // lane 0: residual box of tile t, chunk ci -> buffer g & 1
-      const int m0 = (t % m_tiles) * 256 + (int)rank * 128 + q * 32;
-      const int n0 = (t / m_tiles) * BN + cbeg + ci * 32;
-      mbar_expect_tx(&rbar[g & 1], kG2StageOutBytes);
-      tma_load_2d_u32(s_res + (g & 1) * kG2StageOutBytes, &map_res, &rbar[g & 1], n0, m0);
+      const int m0 = (t / n_tiles) * 256 + (int)rank * 128 + q * 32;
+      const int n0 = (t % n_tiles) * BN + cbeg + ci * 64;
+      mbar_expect_tx(&rbar[g & 1], kG2BoxBytes);
+      tma_load_2d_u32(s_res + (g & 1) * kG2BoxBytes, &map_res, &rbar[g & 1], n0, m0);
     };
-    if (p.has_res && lane == 0 && cluster_id < num_tiles) issue_res(cluster_id, 0, 0);
+    // residual boxes run one chunk ahead in shared memory and one whole tile ahead in L2
+    if (f_res && lane == 0 && cluster_id < num_tiles) issue_res(cluster_id, 0, 0);
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
-      const int m0 = (t % m_tiles) * 256 + (int)rank * 128, n0 = (t / m_tiles) * BN;
+      const int m0 = (t / n_tiles) * 256 + (int)rank * 128, n0 = (t % n_tiles) * BN;
       const int buf = lt & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      __syncwarp();                                          // previous tile's reads of the bias slice are done
-      for (int i = lane; i < kCw; i += 32) s_bias[i] = (p.bias && n0 + cbeg + i < p.N) ? __ldg(p.bias + n0 + cbeg + i) : 0.f;
-      __syncwarp();
-      // operands of the first chunk that come straight from global memory, fetched before the accumulator is ready
-      uint4 pm[4];
-      float4 pa[8];
-      uint32_t pbits = 0xffffffffu;
-      const bool vec32 = p.d_f32 && (p.ldd32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d_f32) & 15) == 0);
-      const bool vecm = p.mask_act && (p.ldmask % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_act) & 15) == 0);
-      auto prefetch = [&](int ci) {
-        const int col = n0 + cbeg + ci * 32;
-        const bool in = row_ok && ci < kChunks && col + 32 <= p.N;
+      if (f_res && lane == 0 && t + num_clusters < num_tiles) {      // next tile's residual boxes -> L2
+        const int tn = t + num_clusters;
+        const int pm0 = (tn / n_tiles) * 256 + (int)rank * 128 + q * 32, pn0 = (tn % n_tiles) * BN + cbeg;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          pm[i] = (vecm && in) ? __ldg(reinterpret_cast<const uint4*>(p.mask_act + (size_t)row * p.ldmask + col) + i)
-                               : make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        for (int ci = 0; ci < kChunks; ++ci)
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&map_res), "r"(pn0 + 64 * ci), "r"(pm0) : "memory");
+      }
+      // packed ReLU masks: this lane's row has kCw / 32 consecutive words per tile — read once, before the accumulator is
+      // ready; the output's own mask words are collected and written once at the end of the tile
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, bw[4] = {0u, 0u, 0u, 0u};
+      if (f_mbits) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          pa[i] = (p.accumulate && vec32 && in) ? *(reinterpret_cast<const float4*>(p.d_f32 + (size_t)row * p.ldd32 + col) + i)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.mask_bits) pbits = (row_ok && ci < kChunks && col < p.N) ? __ldg(p.mask_bits + (size_t)row * p.ldbits_in + (col >> 5)) : 0u;
-      };
-      prefetch(0);
+        for (int c = 0; c < kCw / 32; ++c) {
+          const int col = n0 + cbeg + 32 * c;
+          mw[c] = (row_ok && col < p.N) ? __ldg(p.mask_bits + (size_t)row * p.ldbits_in + (col >> 5)) : 0u;
+        }
+      }
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int ci = 0; ci < kChunks; ++ci, ++gc) {
-        const int c0 = cbeg + ci * 32;
-        const int col = n0 + c0;
-        // residual of the NEXT chunk (this tile or the next one) goes in flight now; its buffer was last read, by every
-        // lane, in the previous chunk
-        if (p.has_res) {
+        const int c0 = cbeg + ci * 64;
+        const int col0 = n0 + c0;
+        // the residual box one chunk ahead (this tile or the next one) goes in flight now; its buffer was last read, by
+        // every lane, in the previous chunk
+        if (f_res) {
           __syncwarp();
           if (lane == 0) {
             if (ci + 1 < kChunks) issue_res(t, ci + 1, gc + 1);
             else if (t + num_clusters < num_tiles) issue_res(t + num_clusters, 0, gc + 1);
           }
         }
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+        tmem_ld_32x32_nowait(taddr, r);
+        tmem_ld_32x32_nowait(taddr + 32, r + 32);
+        tmem_ld_wait();
         if (ci == kChunks - 1) {                             // last read of this accumulator: hand it back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
         }
-        if (col >= p.N) {                                    // warp-uniform: chunk entirely beyond N
-          if (p.has_res) mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
-          prefetch(ci + 1);
-          continue;
+        if (f_res) mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
+        if (col0 >= p.N) continue;                           // warp-uniform: chunk entirely beyond N
+        if (f_store) {                                       // the staging buffer was last read by the previous chunk's store
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
         }
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + (c0 - cbeg) + 4 * i);
-          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x;
-          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
-          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z;
-          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
-        }
-        if (p.has_res) {                                     // residual tile (bf16, 64B-swizzled rows) from shared memory
-          mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
-          const uint32_t base = s_res + (gc & 1) * kG2StageOutBytes + row_off;
+        for (int h = 0; h < 2; ++h) {
+          const int col = col0 + 32 * h;
+          if (col >= p.N) continue;                          // warp-uniform
+          const bool full = col + 32 <= p.N;
+          float v[32];
+          if (p.bias) {
+            if (bias_vec && full) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + ((j ^ swz) << 4)));
-            const uint32_t w[4] = {w0, w1, w2, w3};
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
+                v[4 * i] = __uint_as_float(r[32 * h + 4 * i]) + b4.x;
+                v[4 * i + 1] = __uint_as_float(r[32 * h + 4 * i + 1]) + b4.y;
+                v[4 * i + 2] = __uint_as_float(r[32 * h + 4 * i + 2]) + b4.z;
+                v[4 * i + 3] = __uint_as_float(r[32 * h + 4 * i + 3]) + b4.w;
+              }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
-              v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[32 * h + i]) + (col + i < p.N ? __ldg(p.bias + col + i) : 0.f);
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[32 * h + i]);
           }
-        }
-        if (p.relu) {
+          if (f_res) {                                       // residual tile (bf16, 128B-swizzled rows) from shared memory
+            const uint32_t base = s_res + (gc & 1) * kG2BoxBytes + row_off;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.mask_bits) {
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + (((4 * h + j) ^ swz) << 4)));
+              const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (!(pbits & (1u << i))) v[i] = 0.f;
-        }
-        const bool full = col + 32 <= p.N;                   // warp-uniform
-        if (p.mask_act) {
-          if (vecm && full) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t w[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if ((w[j] & 0x8000u) || !(w[j] & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
-                if ((w[j] & 0x80000000u) || !(w[j] & 0x7fff0000u)) v[8 * i + 2 * j + 1] = 0.f;
+              for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
               }
             }
-          } else if (row_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col + i < p.N && !(__bfloat162float(p.mask_act[(size_t)row * p.ldmask + col + i]) > 0.f)) v[i] = 0.f;
           }
-        }
-        if (p.d_f32) {
-          if (vec32 && full) {
-            if (p.accumulate) {
+          if (p.relu) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { v[4 * i] += pa[i].x; v[4 * i + 1] += pa[i].y; v[4 * i + 2] += pa[i].z; v[4 * i + 3] += pa[i].w; }
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (f_mbits) {
+            const uint32_t pbits = (kChunks == 2 && ci) ? mw[2 + h] : mw[h];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (!(pbits & (1u << i))) v[i] = 0.f;
+          }
+          if (f_mact) {
+            if (vecm && full && row_ok) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 pm = __ldg(reinterpret_cast<const uint4*>(p.mask_act + (size_t)row * p.ldmask + col) + i);
+                const uint32_t w[4] = {pm.x, pm.y, pm.z, pm.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if ((w[j] & 0x8000u) || !(w[j] & 0x7fffu)) v[8 * i + 2 * j] = 0.f;
+                  if ((w[j] & 0x80000000u) || !(w[j] & 0x7fff0000u)) v[8 * i + 2 * j + 1] = 0.f;
+                }
+              }
+            } else if (row_ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col + i < p.N && !(__bfloat162float(p.mask_act[(size_t)row * p.ldmask + col + i]) > 0.f)) v[i] = 0.f;
             }
-            if (row_ok) {
+          }
+          if (f_f32 && row_ok) {
+            if (vec32 && full) {
               float4* dst = reinterpret_cast<float4*>(p.d_f32 + (size_t)row * p.ldd32 + col);
+              if (p.accumulate) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 pa = dst[i];
+                  v[4 * i] += pa.x; v[4 * i + 1] += pa.y; v[4 * i + 2] += pa.z; v[4 * i + 3] += pa.w;
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-          } else if (row_ok) {
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (col + i >= p.N) continue;
-              float* dst = p.d_f32 + (size_t)row * p.ldd32 + col + i;
-              if (p.accumulate) v[i] += *dst;
-              *dst = v[i];
+              for (int i = 0; i < 32; ++i) {
+                if (col + i >= p.N) continue;
+                float* dst = p.d_f32 + (size_t)row * p.ldd32 + col + i;
+                if (p.accumulate) v[i] += *dst;
+                *dst = v[i];
+              }
+            }
+          }
+          if (f_bout) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (v[i] > 0.f) w |= 1u << i;
+            if (kChunks == 2 && ci) bw[2 + h] = w; else bw[h] = w;
+          }
+          if (f_mean) {
+            // mean over the 16 rows (the 4x4 pixels) of each ROI: lanes 0-15 hold one ROI, lanes 16-31 the next.  Butterfly
+            // reduce-scatter: at distance 8, 4, 2, 1 a lane keeps one half of its columns and adds the partner's copy of
+            // them, so 30 shuffles leave lane l (of 16) with the sums of columns 2l and 2l + 1.
+            float u[16];
+            {
+              const bool up = lane & 8;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+            }
+            {
+              const bool up = lane & 4;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = up ? u[i] : u[i + 8], keep = up ? u[i + 8] : u[i];
+                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+            }
+            {
+              const bool up = lane & 2;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = up ? u[i] : u[i + 4], keep = up ? u[i + 4] : u[i];
+                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+            }
+            {
+              const bool up = lane & 1;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = up ? u[i] : u[i + 2], keep = up ? u[i + 2] : u[i];
+                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+              }
+            }
+            const int roi = ((m0 + q * 32) >> 4) + (lane >> 4);
+            const int cc = col + 2 * (lane & 15);
+            if (roi * 16 < p.M) {
+              float* dst = p.rowmean_out + (size_t)roi * p.ld_rowmean + cc;
+              if (cc < p.N) dst[0] = u[0] * (1.f / 16.f);
+              if (cc + 1 < p.N) dst[1] = u[1] * (1.f / 16.f);
+            }
+          }
+          if (f_store) {
+            const uint32_t base = s_out + row_off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((4 * h + j) ^ swz) << 4)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3))
+                           : "memory");
             }
           }
         }
-        prefetch(ci + 1);                                    // next chunk's global operands, in flight during the stores below
-        if (p.bits_out && row_ok) {
-          uint32_t w = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (v[i] > 0.f) w |= 1u << i;
-          p.bits_out[(size_t)row * p.ldbits_out + (col >> 5)] = w;
-        }
-        if (p.rowmean_out) {
-          // mean over the 16 rows (the 4x4 pixels) of each ROI: lanes 0-15 hold one ROI, lanes 16-31 the next.  Butterfly
-          // reduce-scatter: at distance 8, 4, 2, 1 a lane keeps one half of its columns and adds the partner's copy of
-          // them, so 30 shuffles leave lane l (of 16) with the sums of columns 2l and 2l + 1.
-          float u[16];
-          {
-            const bool up = lane & 8;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-          }
-          {
-            const bool up = lane & 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float send = up ? u[i] : u[i + 8], keep = up ? u[i + 8] : u[i];
-              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-          }
-          {
-            const bool up = lane & 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = up ? u[i] : u[i + 4], keep = up ? u[i + 4] : u[i];
-              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-          }
-          {
-            const bool up = lane & 1;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = up ? u[i] : u[i + 2], keep = up ? u[i + 2] : u[i];
-              u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-          }
-          const int roi = ((m0 + q * 32) >> 4) + (lane >> 4);
-          const int cc = col + 2 * (lane & 15);
-          if (roi * 16 < p.M) {
-            float* dst = p.rowmean_out + (size_t)roi * p.ld_rowmean + cc;
-            if (cc < p.N) dst[0] = u[0] * (1.f / 16.f);
-            if (cc + 1 < p.N) dst[1] = u[1] * (1.f / 16.f);
-          }
-        }
-        if (p.has_out || p.has_out2) {
-          // staging buffer gc & 1 was last read by the TMA store(s) of chunk gc - 2
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          const uint32_t base = s_out + (gc & 1) * kG2StageOutBytes + row_off;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((j ^ swz) << 4)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3))
-                         : "memory");
-          }
+        if (f_store) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            const uint32_t src = s_out + (gc & 1) * kG2StageOutBytes;
-            if (p.has_out) tma_store_2d(&map_d, src, col, m0 + q * 32);
-            if (p.has_out2) tma_store_2d(&map_d2, src, col, m0 + q * 32);
+            if (p.has_out) tma_store_2d(&map_d, s_out, col0, m0 + q * 32);
+            if (f_out2) tma_store_2d(&map_d2, s_out, col0, m0 + q * 32);
             tma_store_commit();
           }
+        }
+      }
+      if (f_bout && row_ok) {
+        uint32_t* dst = p.bits_out + (size_t)row * p.ldbits_out + ((n0 + cbeg) >> 5);
+        if (kCw == 128 && n0 + cbeg + 128 <= p.N && (p.ldbits_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bits_out) & 15) == 0) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(bw[0], bw[1], bw[2], bw[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCw / 32; ++c) if (n0 + cbeg + 32 * c < p.N) dst[c] = bw[c];
         }
       }
     }
@@ -435,7 +475,7 @@ static int map_2d(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, i
   return encode_map(m, ptr, 2, dims, strides, box, swz, what);
 }
 
-template <int BN>
+template <int BN, uint32_t F>
 static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   CUtensorMap ma, ma2, mb, md, md2, mr;
   Gemm2Args a = {};
@@ -464,15 +504,15 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   if (rc != B200_OK) return rc;
   md = ma; md2 = ma; mr = ma;
   if (d->out_bf16) {
-    rc = map_2d(&md, d->out_bf16, d->M, d->N, d->ld_out, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "out");
+    rc = map_2d(&md, d->out_bf16, d->M, d->N, d->ld_out, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, "out");
     if (rc != B200_OK) return rc;
   }
   if (d->out2_bf16) {
-    rc = map_2d(&md2, d->out2_bf16, d->M, d->N, d->ld_out2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "out2");
+    rc = map_2d(&md2, d->out2_bf16, d->M, d->N, d->ld_out2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, "out2");
     if (rc != B200_OK) return rc;
   }
   if (d->residual) {
-    rc = map_2d(&mr, d->residual, d->M, d->N, d->ld_res, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, "residual");
+    rc = map_2d(&mr, d->residual, d->M, d->N, d->ld_res, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, "residual");
     if (rc != B200_OK) return rc;
   }
   a.bias = d->bias;
@@ -487,7 +527,7 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   a.a_mn = d->a_mn; a.b_mn = d->b_mn; a.relu = d->relu;
   a.has_out = d->out_bf16 != nullptr; a.has_out2 = d->out2_bf16 != nullptr; a.has_res = d->residual != nullptr;
 
-  auto kern = gemm2_pair_kernel<BN>;
+  auto kern = gemm2_pair_kernel<BN, F>;
   B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<BN>::kSmemBytes));
   const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, BN);
   int clusters = min(tiles, kNumSMs / 2);
@@ -542,5 +582,17 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
     if (d->N <= 128) bn = 128;
   }
   B200_CHECK_ARG(bn == 128 || bn == 256, "gemm2: tile_n must be 0, 128 or 256");
-  return bn == 256 ? launch_gemm2<256>(d, st) : launch_gemm2<128>(d, st);
+  // smallest instantiation whose compiled-in epilogue features cover the descriptor
+  uint32_t need = 0;
+  if (d->residual) need |= kFRes;
+  if (d->mask_bits) need |= kFMaskBits;
+  if (d->mask_act) need |= kFMaskAct;
+  if (d->out_f32) need |= kFF32;
+  if (d->bits_out) need |= kFBitsOut;
+  if (d->rowmean_out) need |= kFRowMean;
+  if (d->out2_bf16) need |= kFOut2;
+  if (d->epilogue_variant == 1) need = kFAll;          // tests: force the generic instantiation
+  if ((need & ~kFFwd) == 0) return bn == 256 ? launch_gemm2<256, kFFwd>(d, st) : launch_gemm2<128, kFFwd>(d, st);
+  if ((need & ~kFBwd) == 0) return bn == 256 ? launch_gemm2<256, kFBwd>(d, st) : launch_gemm2<128, kFBwd>(d, st);
+  return bn == 256 ? launch_gemm2<256, kFAll>(d, st) : launch_gemm2<128, kFAll>(d, st);
 }

@@ -9,6 +9,7 @@ Hot path in eval mode: ROIAlign kernel (channels-last gather) -> res5 (cuDNN, Fr
 -> spatial mean -> tcgen05 text-fusion chain -> predictor GEMMs -> fused softmax/decode/threshold/NMS kernels.
 """
 import logging
+import os
 from typing import Dict
 
 import numpy as np
@@ -151,6 +152,9 @@ class Res5ROIHeads(ROIHeads):
         self.channels_last = bool(b200_opt(cfg, "CHANNELS_LAST", True))
         self.res5_dtype = getattr(torch, b200_opt(cfg, "RES5_DTYPE", "bfloat16"))
         self.skip_dead_bins = bool(b200_opt(cfg, "SKIP_DEAD_BINS", True))
+        # frozen res5: "tcgen05" = every convolution on the CTA-pair GEMM kernel (res5_ops.py);
+        # "cudnn" = the library path (layers._FrozenRes5MeanFn / forward_folded)
+        self.res5_impl = os.environ.get("B200_RES5_IMPL") or str(b200_opt(cfg, "RES5_IMPL", "tcgen05"))
         self.pooler = ROIPooler(output_size=bh.POOLER_RESOLUTION, scales=(1.0 / self.feature_strides[self.in_features[0]],),
                                 sampling_ratio=bh.POOLER_SAMPLING_RATIO, pooler_type=bh.POOLER_TYPE,
                                 channels_last_out=self.channels_last)
@@ -193,8 +197,12 @@ class Res5ROIHeads(ROIHeads):
         """res5 + mean over (h, w) of the pooled ROI map -> (R, C_out) fp32  [roi_heads.py:339-344 + :1109].
         Frozen res5 under autograd runs as one node (layers._FrozenRes5MeanFn: cuDNN convolutions, fused elementwise
         kernels); the spatial mean of a bf16 channels-last stage output is the C-ABI kernel in every mode."""
-        from ... import train_ops
+        from ... import res5_ops, train_ops
         frozen = not self._res5_trainable()
+        if frozen and self.res5_impl == "tcgen05" and self.res5_dtype == torch.bfloat16 and x.is_cuda:
+            pooled = res5_ops.frozen_res5_mean(self.res5, x.to(self.res5_dtype), prestrided)
+            if pooled is not None:
+                return pooled
         if frozen and torch.is_grad_enabled() and x.requires_grad and self.res5_dtype == torch.bfloat16:
             pooled = frozen_res5_mean(self.res5, x.to(self.res5_dtype), prestrided=prestrided)
             if pooled is not None:

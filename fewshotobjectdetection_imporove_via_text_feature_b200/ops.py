@@ -484,6 +484,7 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
 
 GEMM2_TILE_N = [0]          # tests / microbenchmarks force 128 or 256
 GEMM2_MAX_CLUSTERS = [0]    # tests lower it to force several tiles per CTA pair on small shapes
+GEMM2_GENERIC_EPILOGUE = [0]   # tests: 1 = always the generic epilogue instantiation
 
 
 def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residual=None, relu=False, mask_act=None,
@@ -548,7 +549,7 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
     if rowmean_out is not None:
         assert rowmean_out.dtype == torch.float32 and tuple(rowmean_out.shape) == (M // 16, N) and rowmean_out.stride(1) == 1
         d.rowmean_out, d.ld_rowmean = rowmean_out.data_ptr(), rowmean_out.stride(0)
-    d.tile_n, d.max_clusters = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0]
+    d.tile_n, d.max_clusters, d.epilogue_variant = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0], GEMM2_GENERIC_EPILOGUE[0]
     import ctypes
     _lib.call("b200_gemm2", ctypes.byref(d), _stream(),
               tag=(2.0 * M * N * (K + K2), ("gemm2", M, N, K + K2, int(conv_c), int(a_mn), int(b_mn))))

@@ -196,7 +196,9 @@ B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, c
  *   outputs   out_bf16 / out2_bf16 [M][ld] (TMA stores), out_f32 [M][ld_out_f32] (accumulate != 0: +=),
  *             bits_out: packed (v > 0) [M][ld_bits_out] words (needs N % 32 == 0),
  *             rowmean_out [M/16][ld_rowmean] fp32: mean of v over each group of 16 consecutive rows (the 4x4 pixels of a ROI)
- *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it)
+ *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it);
+ *             epilogue_variant: 0 = the smallest compiled epilogue that covers the requested features, 1 = the generic one
+ *             (same results; tests compare them)
  * Alignment: bf16 tensors 16-byte aligned, their leading dimensions multiples of 8 elements.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct b200_gemm2_desc {
@@ -216,6 +218,7 @@ typedef struct b200_gemm2_desc {
   void* bits_out; int ld_bits_out;
   float* rowmean_out; int ld_rowmean;
   int tile_n, max_clusters;
+  int epilogue_variant;
 } b200_gemm2_desc;
 B200_API int b200_gemm2(const b200_gemm2_desc* desc, b200_stream_t stream);
 

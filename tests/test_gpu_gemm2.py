@@ -79,10 +79,12 @@ def test_gemm2_many_tiles_per_pair(clusters, tile_n):
         base = run()
         ops.GEMM2_MAX_CLUSTERS[0] = clusters
         few = run()
+        ops.GEMM2_GENERIC_EPILOGUE[0] = 1            # the all-features instantiation computes the same bits
+        gen_epi = run()
     finally:
-        ops.GEMM2_TILE_N[0], ops.GEMM2_MAX_CLUSTERS[0] = 0, 0
-    for x, y in zip(base, few):
-        assert torch.equal(x, y)
+        ops.GEMM2_TILE_N[0], ops.GEMM2_MAX_CLUSTERS[0], ops.GEMM2_GENERIC_EPILOGUE[0] = 0, 0, 0
+    for x, y, z in zip(base, few, gen_epi):
+        assert torch.equal(x, y) and torch.equal(x, z)
     o1, bo, o2, o3 = (t.cpu() for t in base)
     prod = a.cpu().double() @ b.cpu().double().t()
     ref1 = (prod + bias.cpu().double() + res.cpu().double()).clamp_min(0)

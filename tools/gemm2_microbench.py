@@ -14,7 +14,16 @@ sys.path.insert(0, ROOT)
 from fewshotobjectdetection_imporove_via_text_feature_b200 import ops  # noqa: E402
 
 
-def timed(fn, flush, n=10, warm=3):
+ONLY = [x for x in os.environ.get("CASES", "").split(",") if x]
+ITERS = int(os.environ.get("ITERS", "10"))
+
+
+def want(name):
+    return not ONLY or any(x in name for x in ONLY)
+
+
+def timed(fn, flush, n=None, warm=3):
+    n = ITERS if n is None else n
     ts = []
     for i in range(n + warm):
         flush.fill_(i & 255)
@@ -38,12 +47,17 @@ def main():
     print("%-44s %9s %9s   %s" % ("case", "ms", "TF/s", "library ms (TF/s)"))
     plain = [("res5 conv1 b0   N=512  K=1024 relu", 512, 1024, {}),
              ("res5 conv1 b1/2 N=512  K=2048 relu", 512, 2048, {}),
+             ("iso N=2048 K=512 bias+relu out only", 2048, 512, {"nobits": True}),
+             ("iso N=2048 K=512 + bits_out", 2048, 512, {}),
+             ("iso N=2048 K=512 + res (no bits)", 2048, 512, {"res": True, "nobits": True}),
              ("res5 conv3      N=2048 K=512  relu+res", 2048, 512, {"res": True}),
              ("res5 conv3+sc   N=2048 K=512+1024 relu", 2048, 512, {"k2": 1024}),
              ("res5 dgrad3     N=512  K=2048 bits", 512, 2048, {"bits": True}),
              ("res5 dgrad1     N=2048 K=512  bits+res", 2048, 512, {"bits": True, "res": True}),
              ("res5 conv3 last N=2048 K=512 mean only", 2048, 512, {"res": True, "mean": True})]
     for name, N, K, o in plain:
+        if not want(name):
+            continue
         a, b = rnd(M, K), rnd(N, K + o.get("k2", 0), sc=0.05)
         a2 = rnd(M, o["k2"]) if o.get("k2") else None
         bias = torch.randn(N, device=dev)
@@ -57,7 +71,7 @@ def main():
             ops.GEMM2_TILE_N[0] = tn
             ms = timed(lambda: ops.gemm2(a, b, a2=a2, bias=bias, residual=res, relu=not o.get("bits"), mask_bits=bits,
                                          out=None if o.get("mean") else out, want_out=not o.get("mean"),
-                                         bits_out=None if o.get("bits") else bo, rowmean_out=rm), flush)
+                                         bits_out=None if (o.get("bits") or o.get("nobits")) else bo, rowmean_out=rm), flush)
             aa = a if a2 is None else torch.cat([a, a2], 1)
             lib = timed(lambda: torch.relu_(torch.addmm(bias.to(torch.bfloat16), aa, b.t())), flush) if tn == tiles[0] else float("nan")
             print("%-40s t%-3d %9.4f %9.1f   %.4f (%.1f)" % (name, tn, ms, fl / ms / 1e9, lib, fl / lib / 1e9), flush=True)
@@ -71,7 +85,7 @@ def main():
     fl = 2.0 * M * C * 9 * C
     bo = torch.empty(M, C // 32, dtype=torch.int32, device=dev)
     out = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
-    for tn in tiles:
+    for tn in tiles if want("conv2 3x3") else []:
         ops.GEMM2_TILE_N[0] = tn
         ms = timed(lambda: ops.gemm2(xa, wb, conv_c=C, bias=bias, relu=True, out=out, bits_out=bo), flush)
         lib = timed(lambda: torch.cudnn_convolution_relu(x, w, bias.to(torch.bfloat16), (1, 1), (1, 1), (1, 1), 1), flush)
@@ -84,6 +98,8 @@ def main():
              ("dW (a_mn,b_mn) M=2048 N=4096 K=4096", 2048, 4096, Rr, True, True),
              ("dW (a_mn,b_mn) M=1024 N=2048 K=4096", 1024, 2048, Rr, True, True)]
     for name, Mm, N, K, amn, bmn in chain:
+        if not want(name):
+            continue
         a = rnd(K, Mm) if amn else rnd(Mm, K)
         b = rnd(K, N, sc=0.05) if bmn else rnd(N, K, sc=0.05)
         of = torch.empty(Mm, N, device=dev)
