@@ -6,18 +6,20 @@
         bench.py --gpus N --steps K --warmup W
 
 Default workload = BASELINE.json configs[1]: "VOC split1 10-shot novel fine-tune with CLIP text-fused ROI head, bf16,
-1 B200".  A "step" is one fine-tune step of the text-fused C4 ROI head over one batch of synthetic input on each GPU
-(8 images x 512 sampled, labelled proposals each; 600x800 px -> res4 38x50x1024; K=20; CLIP 512-d):
-  forward   GDL + affine_rcnn on the res4 map -> ROIAlign 7x7 -> res5 (frozen, FrozenBN folded, cuDNN bf16) -> mean
-            -> text-fusion chain (tcgen05 GEMMs) -> cls_score (dropout 0.8) / bbox_pred -> loss_cls, loss_box_reg,
-            loss_attentive
-  backward  through all of it down to d(res4 map) (GDL scale 0.001) and every trained parameter (attention,
-            predictor, affine_rcnn); res5 is frozen (ROI_HEADS.FREEZE_FEAT) so it only propagates the data gradient
-  update    gradient all-reduce over NCCL when N > 1, then SGD + momentum on the trained parameters
-`--mode infer` times the inference direction instead (forward + softmax/decode/threshold/per-class NMS/top-100).
+1 B200".  A "step" is one fine-tune step of the text-fused C4 ROI head over one batch of synthetic input on each GPU,
+driven through the reference-facing API exactly as defrcn/modeling/meta_arch/rcnn.py:94-98 drives it:
+
+    f = affine_rcnn(decouple_layer(features["res4"], lambda))            # G1 + G2 (caller side of the head)
+    _, losses = roi_heads(images, {"res4": f}, proposals, targets)        # SematicRes5ROIHeads.forward(...)
+    sum(losses.values()).backward();  [gradient all-reduce];  SGD + momentum
+
+with 8 images x 2000 RPN-like proposals + 8 ground-truth boxes per image (600x800 px -> res4 38x50x1024, K = 20, CLIP
+512-d).  Inside `forward`: label_and_sample_proposals (S1: 2008 candidates -> 512 sampled rows per image) -> ROIAlign ->
+res5 (frozen, own tcgen05 kernels) -> mean -> text fusion -> cls_score (dropout 0.8) / bbox_pred -> the three losses.
+`--mode infer` times the eval-mode forward (512 proposals per image -> softmax/decode/threshold/per-class NMS/top-100).
 Images shard across GPUs (weak scaling); the only exchanges are the gradient all-reduce (train) / the detection
-all-gather after the loop (infer).  Proposal sampling/labelling (marked "next") is not in the step:
-the synthetic proposals arrive sampled and labelled.
+all-gather (infer).  After the headline measurement the same process also measures BASELINE configs[2] / [3] and the
+inference direction briefly and attaches them as `extra` (skip with --no-extras).
 """
 import argparse
 import json
@@ -46,40 +48,39 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--images-per-gpu", type=int, default=8)
-    ap.add_argument("--props", type=int, default=512)
+    ap.add_argument("--props", type=int, default=512, help="ROIs per image through the head (sampled rows in training)")
+    ap.add_argument("--rpn-props", type=int, default=2000, help="training: unsampled proposals per image handed to forward()")
+    ap.add_argument("--gt-per-image", type=int, default=8)
     ap.add_argument("--classes", type=int, default=20)
     ap.add_argument("--cpu-baseline-images", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short configs[2] / [3] / inference passes")
     ap.add_argument("--distill", action="store_true",
                     help="train mode: BASELINE configs[3] — the student step with the KL loss against a frozen VKV teacher "
                          "(SematicRes5ROIHeadsDistill); not the default metric line")
     ap.add_argument("--no-graph", action="store_true",
                     help="fine-tune mode: enqueue every step from the host instead of replaying one captured CUDA graph")
-    ap.add_argument("--full-bins", action="store_true",
-                    help="pool all 49 bins (the stand-alone ROIAlign op) instead of only the 16 that res5's stride-2 1x1 convs read")
     return ap.parse_args()
 
 
-def synth_inputs(n_images, props, seed0=1234, num_classes=20):
-    """SURVEY.md §8(d) synthetic inputs: post-ReLU res4 maps, RPN-like + jittered proposals, per-image seeds; for the
-    fine-tune direction the proposals come sampled and labelled (25 % foreground, GT = jittered proposal)."""
+def synth_inputs(n_images, props, seed0=1234, num_classes=20, n_obj=8):
+    """SURVEY.md §8(d) synthetic inputs: post-ReLU res4 maps; per image `props` RPN-like + jittered proposals around
+    `n_obj` objects, which are also the image's ground truth (random classes); per-image seeds."""
     from fewshotobjectdetection_imporove_via_text_feature_b200.utils.synthetic import synth_proposals
     feat = torch.relu(torch.randn(n_images, C4, HF, WF, generator=torch.Generator().manual_seed(0)))
     boxes, gt_cls, gt_boxes = [], [], []
     for i in range(n_images):
         gen = torch.Generator().manual_seed(seed0 + i)
-        b = synth_proposals(props, H_IMG, W_IMG, gen, n_obj=8)[0]
-        c = torch.randint(0, num_classes, (props,), generator=gen)
-        c[props // 4:] = num_classes
-        g = b + torch.randn(props, 4, generator=gen) * 4
-        g[:, 2:] = torch.maximum(g[:, 2:], g[:, :2] + 2)
+        b, objs = synth_proposals(props, H_IMG, W_IMG, gen, n_obj=n_obj)
+        objs = objs.clone()
+        objs[:, 2:] = torch.maximum(objs[:, 2:], objs[:, :2] + 2)
         boxes.append(b)
-        gt_cls.append(c)
-        gt_boxes.append(g)
+        gt_boxes.append(objs)
+        gt_cls.append(torch.randint(0, num_classes, (n_obj,), generator=gen))
     return feat, boxes, gt_cls, gt_boxes
 
 
-def build_head(num_classes, device, train=False, distill=False):
+def build_head(num_classes, device, train=False, distill=False, props=512):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
     from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
     cfg = config.get_cfg()
@@ -92,6 +93,8 @@ def build_head(num_classes, device, train=False, distill=False):
         cfg.MODEL.ROI_HEADS.ENABLE_DECOUPLE = True
         cfg.MODEL.ROI_HEADS.BACKWARD_SCALE = GDL_LAMBDA
         cfg.MODEL.ROI_HEADS.FREEZE_FEAT = True
+        cfg.MODEL.ROI_HEADS.BATCH_SIZE_PER_IMAGE = props
+        cfg.MODEL.B200.STATIC_SAMPLING = True      # no host read inside forward(): the step is captured in one CUDA graph
     torch.manual_seed(0)
     head = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=C4, stride=16)})
     head = head.train() if train else head.eval()
@@ -146,11 +149,13 @@ class CpuArm:
     def __init__(self, args):
         torch.set_num_threads(os.cpu_count() or 1)
         self.args, self.train = args, args.mode == "train"
-        _, head, aff = build_head(args.classes, "cpu", train=self.train)
+        _, head, aff = build_head(args.classes, "cpu", train=self.train, props=args.props)
         self.params = {k: v.detach().float().clone() for k, v in head.state_dict().items()}
         self.text = torch.cat([head.attention.embed, head.attention.bg_feature], 0).float()
         self.aff_w, self.aff_b = aff.weight.detach().clone(), aff.bias.detach().clone()
-        self.feat, self.boxes, self.gt_cls, self.gt_boxes = synth_inputs(1, args.props, num_classes=args.classes)
+        n_in = args.rpn_props if self.train else args.props
+        self.feat, self.boxes, self.gt_cls, self.gt_boxes = synth_inputs(1, n_in, num_classes=args.classes, n_obj=args.gt_per_image)
+        self.gen = torch.Generator().manual_seed(5)
         if self.train:
             self.trainable = [v for k, v in self.params.items() if k.startswith(("attention.", "box_predictor."))]
             self.trainable += [self.aff_w, self.aff_b]
@@ -166,14 +171,20 @@ class CpuArm:
                 return O.head_forward(self.feat * self.aff_w + self.aff_b, self.boxes, [(H_IMG, W_IMG)], self.text, self.params,
                                       stages=stages)
         self.opt.zero_grad(set_to_none=True)
-        out = O.head_train_step(self.feat, self.boxes, self.gt_cls[0], self.gt_boxes[0], self.text, self.params, self.aff_w,
-                                self.aff_b, GDL_LAMBDA, a.classes, DROP_P, stages=stages)
+        t0 = time.perf_counter()
+        with torch.no_grad():        # S1: roi_heads.py:157-250
+            b, c, g = O.label_and_sample(self.boxes[0], self.gt_boxes[0], self.gt_cls[0], a.classes, batch=a.props, gen=self.gen)
+        if stages is not None:
+            stages["label_sample"] = stages.get("label_sample", 0.0) + time.perf_counter() - t0
+        out = O.head_train_step(self.feat, [b], c, g, self.text, self.params, self.aff_w, self.aff_b, GDL_LAMBDA, a.classes,
+                                DROP_P, stages=stages)
         self.opt.step()
         return out
 
     def describe(self, n):
-        return "%d image(s) x %d proposals, %s step, fp32, torch %d threads" % (
-            n, self.args.props, "fine-tune (fwd + bwd + SGD)" if self.train else "inference", torch.get_num_threads())
+        return "%d image(s) x %d proposals%s, %s step, fp32, torch %d threads" % (
+            n, self.args.props, " sampled from %d" % self.args.rpn_props if self.train else "",
+            "fine-tune (label+sample, fwd, bwd, SGD)" if self.train else "inference", torch.get_num_threads())
 
 
 def run_cpu_baseline(args, warm=1):
@@ -206,25 +217,356 @@ def main_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1), "cpu_baseline": cb,
+        "config": workload_config(args, args.mode, args.classes, args.distill, 1), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, images_per_gpu):
-    if args.mode == "train" and getattr(args, "distill", False):
-        what = ("distillation fine-tune step (BASELINE configs[3]): the configs[1] step + frozen LV_attention_VKV teacher forward "
-                "(GT-conditioned, GloVe 300-d) + loss_kl (T = 5) on the student's logits")
-    elif args.mode == "train":
-        what = ("fine-tune step (BASELINE configs[1]): GDL+affine_rcnn -> ROIAlign 7x7 -> res5 (frozen) -> text fusion -> "
-                "cls_score(dropout 0.8)/bbox_pred -> loss_cls+loss_box_reg+loss_attentive -> backward to the res4 map "
-                "and all trained parameters -> (grad all-reduce) -> SGD+momentum; proposals arrive sampled and labelled")
+def workload_config(args, mode, classes, distill, images_per_gpu):
+    if mode == "train":
+        what = ("fine-tune step through the public API (BASELINE configs[%d]): affine_rcnn(decouple_layer(res4)) -> "
+                "SematicRes5ROIHeads%s.forward(images, features, proposals, targets) [label_and_sample_proposals %d+%d -> %d rows/image, "
+                "ROIAlign 7x7, res5 (frozen), text fusion, cls_score(dropout 0.8)/bbox_pred, loss_cls+loss_box_reg+loss_attentive%s] "
+                "-> backward to the res4 map and all trained parameters -> (grad all-reduce) -> SGD+momentum"
+                % (3 if distill else 1, "Distill" if distill else "", args.rpn_props, args.gt_per_image, args.props,
+                   "+loss_kl vs the frozen LV_attention_VKV teacher" if distill else ""))
     else:
-        what = "inference step: affine_rcnn -> ROIAlign 7x7 -> res5 -> text fusion -> decode/NMS top-100"
-    return {"workload": "DeFRCN R-101 C4 text-fused ROI head (SematicRes5ROIHeads, CLIP 512-d, K=%d), %s" % (args.classes, what),
-            "mode": args.mode, "classes": args.classes,
-            "roi_align_bins": "all 49" if getattr(args, "full_bins", False) else "16 live of 49 (stride-2 consumer)",
-            "images_per_gpu_per_step": images_per_gpu, "proposals_per_image": args.props, "image_px": [H_IMG, W_IMG],
+        what = ("inference step through the public API: affine_rcnn(res4) -> SematicRes5ROIHeads.forward(images, features, proposals) "
+                "[ROIAlign 7x7, res5, text fusion, softmax/decode/threshold/per-class NMS/top-100] -> Instances")
+    return {"workload": "DeFRCN R-101 C4 text-fused ROI head (CLIP 512-d, K=%d), %s" % (classes, what),
+            "mode": mode, "classes": classes, "api": "forward()",
+            "roi_align_bins": "16 live of 49 (stride-2 consumer)",
+            "images_per_gpu_per_step": images_per_gpu, "proposals_per_image": args.props,
+            "rpn_proposals_per_image": args.rpn_props if mode == "train" else None, "image_px": [H_IMG, W_IMG],
             "res4_map": [C4, HF, WF], "l2": "flushed between timed steps (256 MiB write)", "parallelism": "image-sharded dp%d" % args.gpus}
+
+
+TRAIN_STAGES = ["gdl_affine", "label_sample", "roi_align", "res5_mean", "text_fusion_losses", "bwd_text_fusion", "bwd_res5",
+                "bwd_roi_align", "bwd_gdl_affine", "allreduce_sgd"]
+INFER_STAGES = ["affine", "roi_align", "res5_mean", "text_fusion_predictor", "decode_nms"]
+
+
+class Workload:
+    """One configuration of the head on this rank's GPU: synthetic inputs (pinned host + device-resident copies), the
+    step function through `forward()`, CUDA-graph capture of the fine-tune step, device-timed and end-to-end loops."""
+
+    def __init__(self, args, mode, classes, distill, dev, rank, world, graph=True):
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+        self.args, self.mode, self.K, self.distill, self.dev, self.rank, self.world = args, mode, classes, distill, dev, rank, world
+        self.train = mode == "train"
+        self.B, self.P = args.images_per_gpu, args.props
+        self.cfg, self.head, self.aff = build_head(classes, dev, train=self.train, distill=distill, props=self.P)
+        n_in = args.rpn_props if self.train else self.P
+        feat_h, boxes_h, cls_h, gtb_h = synth_inputs(self.B, n_in, seed0=1234 + 1000 * rank, num_classes=classes, n_obj=args.gt_per_image)
+        self.host = {"feat": feat_h.pin_memory(), "boxes": torch.stack(boxes_h).pin_memory()}
+        if self.train:
+            self.host["gt_cls"] = torch.stack(cls_h).pin_memory()
+            self.host["gt_boxes"] = torch.stack(gtb_h).pin_memory()
+        self.names = list(self.host)
+        self.resident = {k: v.to(dev) for k, v in self.host.items()}
+        self.sizes = [(H_IMG, W_IMG)] * self.B
+        self.opt = None
+        if self.train:
+            self.opt = train_ops.FlatSGD(list(self.head.attention.parameters()) + list(self.head.box_predictor.parameters()) +
+                                         list(self.aff.parameters()), lr=LR, momentum=MOMENTUM, weight_decay=WD, direct_grads=True)
+        self.stage_names = TRAIN_STAGES if self.train else INFER_STAGES
+        self.n_marks = len(self.stage_names) + 1
+        self.graph, self.graph_note, self.in_graph = None, "off (--no-graph)" if self.train else "n/a (forward() returns Instances: one host read)", False
+        self.want_graph = graph and self.train and not args.no_graph
+
+    # -- inputs in the reference's containers ---------------------------------------------------------------------
+    def batch(self, d):
+        from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+        props, targets = [], ([] if self.train else None)
+        for i in range(self.B):
+            inst = Instances(self.sizes[i])
+            inst.proposal_boxes = Boxes(d["boxes"][i])
+            inst.objectness_logits = torch.zeros(d["boxes"].shape[1], device=d["boxes"].device)
+            props.append(inst)
+            if self.train:
+                t = Instances(self.sizes[i])
+                t.gt_boxes = Boxes(d["gt_boxes"][i])
+                t.gt_classes = d["gt_cls"][i]
+                targets.append(t)
+        return props, targets
+
+    # -- one step through the public API --------------------------------------------------------------------------
+    def step(self, d, ev=None, exchange=True):
+        import torch.distributed as dist
+        head, aff, opt = self.head, self.aff, self.opt
+        idx = {n: i + 1 for i, n in enumerate(self.stage_names)}
+
+        def mark(i):
+            if ev is not None:
+                ev[i].record()
+
+        def cb(name, tensor):
+            if name in idx:
+                mark(idx[name])
+            if self.train and ev is not None and tensor is not None and tensor.requires_grad:
+                if name == "res5_mean":
+                    tensor.register_hook(lambda g: ev[idx["bwd_text_fusion"]].record())
+                elif name == "roi_align":
+                    tensor.register_hook(lambda g: ev[idx["bwd_res5"]].record())
+        head._stage_cb = cb if ev is not None else None
+        props, targets = self.batch(d)
+        mark(0)
+        if not self.train:
+            f = aff(d["feat"], None, True, torch.bfloat16)                                # G2 (+ layout / dtype for the gather)
+            mark(1)
+            pred, _ = head(None, {"res4": f}, props, None)                                # forward(): P1, P2, T/A/C, D1-D3
+            return pred
+        opt.zero_grad()
+        x = d["feat"].detach().requires_grad_(True)
+        f = aff(x, GDL_LAMBDA, True, torch.bfloat16)                                      # G1 + G2 (rcnn.py:94-97)
+        mark(1)
+        if ev is not None:
+            f.register_hook(lambda g: ev[idx["bwd_roi_align"]].record())
+        _, losses = head(None, {"res4": f}, props, targets)                               # forward(): S1, P1, P2, T/A/C, L1
+        total = losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]
+        if self.distill:
+            total = total + losses["loss_kl"]
+        total.backward()                                                                  # L1, A*, P2, P1b, G1/G2 backward
+        mark(idx["bwd_gdl_affine"])
+        res = {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
+               "grad_feat": x.grad}
+        if not exchange:
+            opt.sync_grads()         # join the parameter-gradient streams (a captured region must end on one stream)
+            return res
+        if self.world > 1:
+            # the one real exchange step: head gradients on a communication stream behind the parameter-gradient streams
+            # (under the res5 / ROIAlign backward still queued on the GPU), affine_rcnn's two vectors at the end
+            opt.all_reduce_grads(n_late_params=len(list(aff.parameters())))
+        opt.step()
+        mark(idx["allreduce_sgd"])
+        return res
+
+    def prepare(self, warm):
+        """Warm-up steps, then (fine-tune) capture of the whole step into one CUDA graph."""
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+        with (torch.enable_grad() if self.train else torch.no_grad()):
+            for _ in range(max(warm, 3)):
+                self.out = self.step(self.resident)
+            torch.cuda.synchronize()
+            if self.train:
+                self.head.flush_deferred_logs()          # raises if static sampling did not hold on this batch
+            if self.want_graph:
+                try:
+                    self.head.use_device_dropout_counter(True)
+                    # world > 1: the NCCL gradient all-reduce is captured too (on the communication stream, behind the
+                    # parameter-gradient streams and under res5's backward); BENCH_GRAPH_ALLREDUCE=0 keeps it and SGD outside
+                    self.in_graph = self.world == 1 or os.environ.get("BENCH_GRAPH_ALLREDUCE", "1") == "1"
+                    self.graph = train_ops.GraphedStep(lambda d: self.step(d, exchange=self.in_graph), self.resident)
+                    self.graph_note = "whole step" if self.in_graph else "forward + backward (all-reduce and SGD outside)"
+                except Exception as e:  # noqa: BLE001
+                    self.graph, self.graph_note = None, "capture failed, running eagerly: %s" % str(e).splitlines()[0][:200]
+                    self.head.use_device_dropout_counter(False)
+                    torch.cuda.synchronize()
+
+    def run_step(self, d, ev=None):
+        import torch.distributed as dist
+        if self.graph is None:
+            with (torch.enable_grad() if self.train else torch.no_grad()):
+                return self.step(d, ev)
+        if ev is not None:
+            ev[0].record()
+        static_out = self.graph(d)
+        if self.world > 1 and not self.in_graph:
+            dist.all_reduce(self.opt.grad, op=dist.ReduceOp.AVG)
+            self.opt.step()
+        if ev is not None:
+            ev[self.n_marks - 1].record()
+        return static_out
+
+    def timed(self, steps, flush):
+        """Device-timed loop: `steps` steps, L2 flushed before each, one event pair per step (first mark .. last mark);
+        returns (total ms max over ranks, per-step list, kernel launches per step, host enqueue ms per step)."""
+        import torch.distributed as dist
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(self.n_marks)] for _ in range(steps)]
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.LAUNCHES
+        t0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            self.out = self.run_step(self.resident, evs[i])
+            if not self.train:
+                evs[i][self.n_marks - 1].record()
+        host_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)
+        torch.cuda.synchronize()
+        launches = (_lib.LAUNCHES - l0) // max(steps, 1)
+        if self.graph is not None:       # replays bypass the Python entry points: count the kernels recorded into the graph
+            launches = self.graph.kernel_launches
+        if self.world > 1:
+            dist.barrier()
+        per_step = [evs[i][0].elapsed_time(evs[i][self.n_marks - 1]) for i in range(steps)]
+        total = torch.tensor([float(sum(per_step))], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        if self.train:
+            self.head.flush_deferred_logs()
+        return float(total), per_step, int(launches), host_ms, evs
+
+    def stage_split(self, flush, evs=None, n=5):
+        """Per-stage times from eager steps with marks at the stage boundaries inside forward() / the backward."""
+        if evs is None or self.graph is not None:
+            with (torch.enable_grad() if self.train else torch.no_grad()):
+                for _ in range(4):           # the eager path's allocations settle again after the capture
+                    self.step(self.resident)
+                evs = [[torch.cuda.Event(enable_timing=True) for _ in range(self.n_marks)] for _ in range(n)]
+                for i in range(n):
+                    flush.fill_(i)
+                    self.step(self.resident, evs[i])
+                    if not self.train:
+                        evs[i][self.n_marks - 1].record()
+            torch.cuda.synchronize()
+            self.head._stage_cb = None
+        return dict(zip(self.stage_names, [float(np.median([e[s].elapsed_time(e[s + 1]) for e in evs])) for s in range(self.n_marks - 1)]))
+
+    # -- end to end: pinned host inputs -> device, result -> host, every step --------------------------------------
+    def result_tensors(self, out):
+        if self.train:
+            return {"losses": out["losses"]}
+        return {"boxes": torch.cat([r.pred_boxes.tensor for r in out], 0), "scores": torch.cat([r.scores for r in out], 0),
+                "classes": torch.cat([r.pred_classes for r in out], 0)}
+
+    def e2e(self, steps):
+        import torch.distributed as dist
+        dev, host, names = self.dev, self.host, self.names
+        cap = {"losses": (3,), "boxes": (self.B * 100, 4), "scores": (self.B * 100,), "classes": (self.B * 100,)}
+        ex = self.result_tensors(self.out)
+        res_host = {k: torch.empty(cap[k], dtype=v.dtype).pin_memory() for k, v in ex.items()}
+        cur = torch.cuda.current_stream()
+        cpy = torch.cuda.Stream()
+        dbuf = [{k: torch.empty_like(self.resident[k]) for k in names} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+        d2h = [0]
+
+        def upload(i):
+            b = i & 1
+            with torch.cuda.stream(cpy):
+                cpy.wait_event(free[b])
+                for k in names:
+                    dbuf[b][k].copy_(host[k], non_blocking=True)
+                ready[b].record(cpy)
+
+        def run(n, overlap):
+            for e in free:
+                e.record(cur)
+            if overlap:
+                upload(0)
+            for i in range(n):
+                b = i & 1
+                if overlap:
+                    if i + 1 < n:
+                        upload(i + 1)
+                    cur.wait_event(ready[b])
+                    o = self.run_step(dbuf[b])
+                    free[b].record(cur)
+                else:
+                    o = self.run_step({k: host[k].to(dev, non_blocking=True) for k in names})
+                r = self.result_tensors(o)
+                d2h[0] = 0
+                for k, v in r.items():
+                    res_host[k][: v.shape[0]].copy_(v, non_blocking=True)
+                    d2h[0] += v.numel() * v.element_size()
+                if not overlap:
+                    cur.synchronize()
+            cur.synchronize()
+
+        out = {}
+        for name, overlap in (("serial", False), ("overlap", True)):
+            run(3, overlap)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if self.world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            run(steps, overlap)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if self.world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            out[name] = float(ms)
+        return out, int(sum(v.numel() * v.element_size() for v in host.values())), int(d2h[0])
+
+    def close(self):
+        self.graph = None
+        self.head._stage_cb = None
+
+
+def replay_gemms(cases, dev, flush):
+    """Every tensor-core GEMM launch of one step (same shapes, operand layouts and epilogues; fresh operands) re-issued
+    back to back on the launching stream inside ONE CUDA event pair, L2 flushed before the sequence: the sum of the
+    kernels' durations without the cross-stream SM sharing of the step and without per-launch host latency."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops, train_ops
+    calls, flop = [], 0.0
+    rnd0 = lambda *s, sc=0.5: (torch.randn(*s, device=dev) * sc).to(torch.bfloat16)
+    rnd = lambda r, c_, sc=0.5: rnd0(r, (c_ + 7) // 8 * 8, sc=sc)[:, :c_]          # row pitch a multiple of 8 elements (TMA)
+    for c in cases:
+        if isinstance(c, dict):                      # b200_gemm2
+            M, N, K, K2 = c["M"], c["N"], c["K"], c["K2"]
+            if c["conv_c"]:
+                a = rnd(M, c["conv_c"])
+            else:
+                a = rnd(K, M) if c["a_mn"] else rnd(M, K)
+            b = rnd(K, N, sc=0.05) if c["b_mn"] else rnd(N, K + K2, sc=0.05)
+            kw = dict(a_mn=c["a_mn"], b_mn=c["b_mn"], conv_c=c["conv_c"], relu=c["relu"], accumulate=c["acc"], want_out=c["out"])
+            if K2:
+                kw["a2"] = rnd(M, K2)
+            if c["bias"]:
+                kw["bias"] = torch.randn(N, device=dev)
+            if c["res"]:
+                kw["residual"] = rnd(M, N)
+            if c["mbits"]:
+                kw["mask_bits"] = torch.randint(-2 ** 31, 2 ** 31 - 1, (M, (N + 31) // 32), dtype=torch.int32, device=dev)
+            if c["mact"]:
+                kw["mask_act"] = rnd(M, N)
+            if c["out"]:
+                kw["out"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            if c["out2"]:
+                kw["out2"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+            if c["f32"]:
+                kw["out_f32"] = torch.zeros(M, N, device=dev)
+            if c["bout"]:
+                kw["bits_out"] = torch.empty(M, N // 32, dtype=torch.int32, device=dev)
+            if c["mean"]:
+                kw["rowmean_out"] = torch.empty(M // 16, N, device=dev)
+            calls.append((ops.gemm2, (a, b), kw))
+            flop += 2.0 * M * N * (K + K2)
+        else:                                        # b200_gemm_bf16(_ex), single-CTA kernel
+            (M, N, K, obf, d2, relu, acc, msk, bias) = c
+            ld = (N + 7) // 8 * 8
+            kw = dict(relu=relu, accumulate=acc,
+                      out=torch.zeros(M, ld, device=dev, dtype=torch.bfloat16 if obf else torch.float32)[:, :N],
+                      out2=torch.empty(M, ld, device=dev, dtype=torch.bfloat16)[:, :N] if d2 else None,
+                      mask=rnd(M, ld)[:, :N] if msk else None)
+            calls.append((train_ops.gemm_ex, (rnd(M, K), rnd(N, K, sc=0.05), torch.randn(N, device=dev) if bias else None), kw))
+            flop += 2.0 * M * N * K
+    ts = []
+    for it in range(6):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for fn, a, kw in calls:
+            fn(*a, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts[2:])) if calls else float("nan"), flop, len(calls)
+
+
+def traffic_from_profiles(key):
+    """DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` summary of
+    this exact configuration (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py); None when not captured."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))).get(key)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def main():
@@ -236,386 +578,167 @@ def main():
         return main_reference(args, rank, world)
 
     import torch.distributed as dist
-    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, ops, train_ops
-    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
-    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, distributed as bdist, ops
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         # NB the GPU box exports NCCL_DEBUG=VERSION: NCCL itself prints one "NCCL version ..." line to stdout before the JSON line
         dist.init_process_group("nccl", device_id=dev)
-    train = args.mode == "train"
-    B, P, K = args.images_per_gpu, args.props, args.classes
-    distill = train and getattr(args, "distill", False)
-    cfg, head, aff = build_head(K, dev, train=train, distill=distill)
-    feat_h, boxes_h, cls_h, gtb_h = synth_inputs(B, P, seed0=1234 + 1000 * rank, num_classes=K)
-    host = {"feat": feat_h.pin_memory(), "boxes": torch.stack(boxes_h).pin_memory()}
-    if train:
-        host["gt_cls"] = torch.stack(cls_h).pin_memory()
-        host["gt_boxes"] = torch.stack(gtb_h).pin_memory()
-    names = list(host)
-    resident = {k: v.to(dev) for k, v in host.items()}
-    sizes = [(H_IMG, W_IMG)] * B
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # res5's first block reads the pooled 7x7 map through 1x1 stride-2 convs: only bins [::2, ::2] are live
-    skip = head.skip_dead_bins and head.res5[0].reads_strided_1x1() and not args.full_bins
-    bin_step = head.res5[0].stride if skip else 1
-    nb = -(-7 // bin_step)
-    opt = None
-    if train:
-        opt = train_ops.FlatSGD(list(head.attention.parameters()) + list(head.box_predictor.parameters()) + list(aff.parameters()),
-                                lr=LR, momentum=MOMENTUM, weight_decay=WD, direct_grads=True)
+    B, P, K = args.images_per_gpu, args.props, args.classes
+    train = args.mode == "train"
 
-    def make_props(d):
-        props = []
-        for i in range(B):
-            inst = Instances(sizes[i])
-            inst.proposal_boxes = Boxes(d["boxes"][i])
-            if train:
-                inst.gt_boxes = Boxes(d["gt_boxes"][i])
-                inst.gt_classes = d["gt_cls"][i]
-            props.append(inst)
-        return props
+    wl = Workload(args, args.mode, K, train and args.distill, dev, rank, world)
+    wl.prepare(args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, per_step, launches, host_ms, evs = wl.timed(args.steps, flush)
+    sampler.stop_flag = True
+    stage_ms = wl.stage_split(flush, evs)
 
-    if train:
-        stage_names = ["gdl_affine", "roi_align", "res5_mean", "text_fusion_losses", "bwd_text_fusion", "bwd_res5",
-                       "bwd_roi_align", "bwd_gdl_affine", "allreduce_sgd"]
-    else:
-        stage_names = ["affine", "roi_align", "res5_mean", "text_fusion_predictor", "decode_nms"]
-    n_marks = len(stage_names) + 1
-
-    def step(d, ev=None, exchange=True):
-        def mark(i):
-            if ev is not None:
-                ev[i].record()
-        props = make_props(d)
-        if not train:
-            mark(0)
-            f = aff(d["feat"], None, True, torch.bfloat16)                                    # G2 (+layout/dtype for the gather)
-            mark(1)
-            pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)   # P1
-            mark(2)
-            fp = head._res5_mean(pooled, prestrided=bin_step > 1)                               # P2 (cuDNN + own mean)
-            mark(3)
-            att, _ = head.forward_att(fp)                                                     # T1, A1-A6, C1
-            mark(4)
-            outs = FastRCNNOutputs(head.box2box_transform, att["pred_logits"], att["pred_bbox"], props, 0.0)
-            out = outs.inference_device(head.test_score_thresh, head.test_nms_thresh, head.test_detections_per_img)  # D1-D3
-            mark(5)
-            return out
-        mark(0)
-        opt.zero_grad()
-        begin = torch.cuda.Event()
-        begin.record()                                                                        # parameters hold this step's values
-        x = d["feat"].detach().requires_grad_(True)
-        f = aff(x, GDL_LAMBDA, True, torch.bfloat16)                                          # G1 + G2
-        mark(1)
-        pooled = head.pooler([f], [p.proposal_boxes for p in props], bin_step=bin_step)       # P1
-        mark(2)
-        fp = head._res5_mean(pooled, prestrided=bin_step > 1)                                 # P2 (frozen: one node)
-        head.prefetch_text_side(after=begin)                                                  # T1 (+ text half of A1/A2): side stream, under res5
-        mark(3)
-        gt = d["gt_cls"].reshape(-1)
-        if distill:            # frozen teacher forward (fused, no autograd) + KL as the fourth loss of the fused node
-            losses, _ = head.fused_train_losses(fp, props, gt, head._teacher_logits(fp, gt), head._kd_params())
-        else:
-            losses, _ = head.fused_train_losses(fp, props, gt)                                # T1, A1-A6, C1, L1
-        mark(4)
-        if ev is not None:     # events inside the backward pass: recorded when the gradient of that tensor is ready
-            fp.register_hook(lambda g: ev[5].record())
-            pooled.register_hook(lambda g: ev[6].record())
-            f.register_hook(lambda g: ev[7].record())
-        total = losses["loss_cls"] + losses["loss_box_reg"] + losses["loss_attentive"]
-        if distill:
-            total = total + losses["loss_kl"]
-        total.backward()                                                                      # L1, A*, P2, P1b, G1/G2 bwd
-        mark(8)
-        res = {"losses": torch.stack([losses["loss_cls"], losses["loss_box_reg"], losses["loss_attentive"]]).detach(),
-               "grad_feat": x.grad}
-        if not exchange:
-            opt.sync_grads()         # join the parameter-gradient streams (a captured region must end on one stream)
-            return res
-        if world > 1:
-            # the one real exchange step: head gradients on a communication stream behind the parameter-gradient streams
-            # (under the res5 / ROIAlign backward still queued on the GPU), affine_rcnn's two vectors at the end
-            opt.all_reduce_grads(n_late_params=len(list(aff.parameters())))
-        opt.step()
-        mark(9)
-        return res
-
-    grad_ctx = torch.enable_grad() if train else torch.no_grad()
-    with grad_ctx:
-        for _ in range(max(args.warmup, 3)):
-            out = step(resident)
-        torch.cuda.synchronize()
-        # ---- fine-tune step as one CUDA graph ------------------------------------------------------------
-        # ~200 launches on five streams per step cost the host about as long to enqueue as the GPU takes to run them;
-        # a busy host then stalls the GPU.  The whole step (zero_grad .. backward [.. SGD at world 1]) is captured once
-        # and replayed; inputs are copied into the graph's static buffers, the classifier-dropout step counter lives
-        # in device memory so every replay draws a new mask.  World > 1: the gradient all-reduce and SGD stay outside.
-        graph, in_graph, graph_note = None, False, "off (--no-graph)" if train else "n/a"
-        if train and not args.no_graph:
-            try:
-                head.use_device_dropout_counter(True)
-                # world > 1: the NCCL gradient all-reduce is captured too (on the communication stream, behind the
-                # parameter-gradient streams and under res5's backward); BENCH_GRAPH_ALLREDUCE=0 keeps it and SGD outside
-                in_graph = world == 1 or os.environ.get("BENCH_GRAPH_ALLREDUCE", "1") == "1"
-                graph = train_ops.GraphedStep(lambda d: step(d, exchange=in_graph), resident)
-                graph_note = "whole step" if in_graph else "forward + backward (all-reduce and SGD outside)"
-            except Exception as e:  # noqa: BLE001
-                graph, graph_note = None, "capture failed, running eagerly: %s" % str(e).splitlines()[0][:200]
-                head.use_device_dropout_counter(False)
-                torch.cuda.synchronize()
-
-        def run_step(d, ev=None):
-            if graph is None:
-                return step(d, ev)
-            if ev is not None:
-                ev[0].record()
-            static_out = graph(d)
-            if world > 1 and not in_graph:
-                dist.all_reduce(opt.grad, op=dist.ReduceOp.AVG)
-                opt.step()
-            if ev is not None:
-                ev[n_marks - 1].record()
-            return static_out
-        # ---- device-resident timing --------------------------------------------------------------------
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(args.steps)]
-        sampler = ClockSampler(local)
-        sampler.start()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        l0 = _lib.LAUNCHES
-        host_prof = None
-        if os.environ.get("BENCH_HOST_PROFILE"):        # where the host time of a step goes (cProfile, stderr)
-            import cProfile
-            host_prof = cProfile.Profile()
-            host_prof.enable()
-        t_cpu0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.fill_(i & 0xff)
-            out = run_step(resident, evs[i])
-        if host_prof is not None:
-            import pstats
-            host_prof.disable()
-            pstats.Stats(host_prof, stream=sys.stderr).sort_stats("tottime").print_stats(45)
-        cpu_enqueue_ms = (time.perf_counter() - t_cpu0) * 1e3 / max(args.steps, 1)    # host time to enqueue one step (no sync)
-        if world > 1 and not train:
-            insts = [Instances(sizes[0], pred_boxes=Boxes(out["boxes"][i]), scores=out["scores"][i], pred_classes=out["classes"][i]) for i in range(B)]
-            cnt, dets = bdist.pack_detections(insts)
-            bdist.all_gather_detections(out["counts"], dets, B * world)
-        torch.cuda.synchronize()
-        launches = (_lib.LAUNCHES - l0) // max(args.steps, 1)
-        if graph is not None:        # replays bypass the Python entry points: count the kernels recorded into the graph
-            launches = graph.kernel_launches
-        sampler.stop_flag = True
-        if world > 1:
-            dist.barrier()
-        per_step = [evs[i][0].elapsed_time(evs[i][n_marks - 1]) for i in range(args.steps)]
-        if graph is not None:        # stage marks cannot sit inside the graph: a few eager steps give the stage split
-            for _ in range(6):           # the eager path's allocations settle again after the capture
-                step(resident)
-            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(n_marks)] for _ in range(5)]
-            for i in range(5):
-                flush.fill_(i)
-                step(resident, evs[i])
-            torch.cuda.synchronize()
-        stage_ms = [float(np.median([e[s].elapsed_time(e[s + 1]) for e in evs])) for s in range(n_marks - 1)]
-        total_ms = torch.tensor([float(sum(per_step))], device=dev)
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        total_ms = float(total_ms)
-        # ---- per-entry-point profile (separate pass: an event pair around every C-ABI call) ---------------------
-        _lib.PROFILE = {}
-        prof_steps = 5
+    # ---- per-entry-point profile (separate eager pass: an event pair around every C-ABI call) ---------------------
+    _lib.PROFILE = {}
+    prof_steps = 5
+    with (torch.enable_grad() if train else torch.no_grad()):
         for i in range(prof_steps):
             flush.fill_(i)
-            step(resident)
-        torch.cuda.synchronize()
-        prof = {}
-        fl_of = lambda t: (t[0] if isinstance(t, tuple) else t) or 0.0
-        if os.environ.get("BENCH_DUMP_CALLS"):
-            for name, rows in _lib.PROFILE.items():
-                for a, b, t in rows[: len(rows) // prof_steps]:
-                    ms = a.elapsed_time(b)
-                    print("CALL %-34s %8.4f ms %s" % (name, ms, ("%.1f GF  %.0f TF/s %s" % (fl_of(t) / 1e9, fl_of(t) / ms / 1e9, t[1] if isinstance(t, tuple) else "")) if t else ""), file=sys.stderr)
-        # the step's GEMM launches, each shape / epilogue re-issued ALONE on the launching stream (fresh operands of the
-        # same shape, L2-warm as inside the step): inside the step the side-stream GEMMs share the SMs with res5's
-        # kernels by design, so their event-bracketed times there do not measure the kernel
-        gemm_cases = [t[1] for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex") for _, _, t in _lib.PROFILE.get(name, [])[: len(_lib.PROFILE.get(name, [])) // prof_steps]
-                      if isinstance(t, tuple)]
+            wl.step(wl.resident)
+    torch.cuda.synchronize()
+    prof, gemm_cases = {}, []
+    fl_of = lambda t: (t[0] if isinstance(t, tuple) else t) or 0.0
+    for name, rows in _lib.PROFILE.items():
+        per = max(len(rows) // prof_steps, 1)            # the same calls every step: median over the profiled steps
+        ms = float(np.median([sum(a.elapsed_time(b) for a, b, _ in rows[i * per:(i + 1) * per]) for i in range(prof_steps)]))
+        fl = sum(fl_of(t) for _, _, t in rows if t) / prof_steps
+        prof[name] = {"ms_per_step": ms, "calls_per_step": len(rows) / prof_steps}
+        if fl:
+            prof[name]["tflops"] = fl / (ms * 1e-3) / 1e12
+            prof[name]["flop_per_step"] = fl
+        if name in ("b200_gemm_bf16", "b200_gemm_bf16_ex", "b200_gemm2"):
+            gemm_cases += [t[1] for _, _, t in rows[:per] if isinstance(t, tuple)]
+    if os.environ.get("BENCH_DUMP_CALLS"):
         for name, rows in _lib.PROFILE.items():
-            per = max(len(rows) // prof_steps, 1)            # the same calls every step: median over the profiled steps
-            ms = float(np.median([sum(a.elapsed_time(b) for a, b, _ in rows[i * per:(i + 1) * per]) for i in range(prof_steps)]))
-            fl = sum(fl_of(t) for _, _, t in rows if t) / prof_steps
-            prof[name] = {"ms_per_step": ms, "calls_per_step": len(rows) / prof_steps}
-            if fl:
-                prof[name]["tflops"] = fl / (ms * 1e-3) / 1e12
-                prof[name]["flop_per_step"] = fl
-        _lib.PROFILE = None
-        # the stand-alone ROIAlign operator (all 49 bins, what torchvision.ops.roi_align computes) on the same maps / ROIs, and
-        # its backward (lists planned ahead, as in the step), L2 flushed before every launch
-        roi_op = {}
-        with torch.enable_grad():
-            fmap = resident["feat"].to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-            rois_l = [resident["boxes"][i] for i in range(B)]
-            rr, oo = ops.boxes_to_rois(rois_l)
-            tf, tb = [], []
-            for i in range(5):
-                flush.fill_(i)
-                e0_, e1_, e2_, e3_ = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-                e0_.record()
-                pooled_full = ops.roi_align(fmap, rr, 7, 1.0 / 16, 0, True, channels_last_out=True, roi_batch_offsets=oo, bin_step=1)
-                e1_.record()
-                gfull = torch.ones_like(pooled_full)
-                flush.fill_(i + 1)
-                e2_.record()
-                pooled_full.backward(gfull)
-                e3_.record()
-                torch.cuda.synchronize()
-                fmap.grad = None
-                if i >= 2:
-                    tf.append(e0_.elapsed_time(e1_))
-                    tb.append(e2_.elapsed_time(e3_))
-            full_bytes = B * C4 * HF * WF * 2 + B * P * 20 + B * P * C4 * 49 * 2
-            roi_op = {"bins": "7x7", "algorithmic_bytes": full_bytes,
-                      "fwd_ms": float(np.median(tf)), "fwd_gbs": full_bytes / float(np.median(tf)) / 1e6,
-                      "bwd_ms": float(np.median(tb)), "bwd_gbs": full_bytes / float(np.median(tb)) / 1e6,
-                      "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
-            del pooled_full, gfull, fmap
-        # the post-processing operator (BASELINE metric "NMS us"): softmax + decode + threshold compaction, per-class NMS,
-        # top-100 gather on this batch's proposals with SURVEY 8(d)'s logits (30 % of the ROIs peaked on a random foreground
-        # class, the rest on background), L2 flushed before every call
-        nms_op = {}
-        with torch.no_grad():
-            gen_ = torch.Generator().manual_seed(99)
-            lg_ = torch.randn(B * P, K + 1, generator=gen_)
-            peak_ = torch.rand(B * P, generator=gen_) < 0.3
-            cls_ = torch.randint(0, K, (B * P,), generator=gen_)
-            lg_[torch.arange(B * P)[peak_], cls_[peak_]] += 4.0
-            lg_[~peak_, K] += 4.0
-            lg_, dl_ = lg_.to(dev), (torch.randn(B * P, 4 * K, generator=gen_) * 0.5).to(dev)
-            pb_ = torch.cat([resident["boxes"][i] for i in range(B)], 0).float().contiguous()
-            offs_ = torch.arange(0, B * P + 1, P, dtype=torch.int32, device=dev)
-            hw_ = ops.image_hw_tensor([(H_IMG, W_IMG)] * B, dev)
-            tn_, tt_ = [], []
-            for i in range(6):
-                flush.fill_(i)
-                _lib.PROFILE = {}
-                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0_.record()
-                det_ = ops.fast_rcnn_inference_device(lg_, dl_, pb_, offs_, hw_, 0.05, 0.5, 100)
-                e1_.record()
-                torch.cuda.synchronize()
-                if i >= 2:
-                    tt_.append(e0_.elapsed_time(e1_))
-                    tn_.append(sum(a.elapsed_time(b) for a, b, _ in _lib.PROFILE.get("b200_batched_nms", [])))
-                _lib.PROFILE = None
-            nms_op = {"nms_us_per_image": 1e3 * float(np.median(tn_)) / B, "postprocess_us_per_image": 1e3 * float(np.median(tt_)) / B,
-                      "candidates_per_image": float(det_["n_candidates"].float().mean()),
-                      "detections_per_image": float(det_["counts"].float().mean()), "images": B, "classes": K,
-                      "note": "b200_batched_nms (3 kernels: class sort, per-class NMS, merge) / whole fast_rcnn_inference on the device, "
-                              "CUDA events, median of 4, bit-exact keep indices (tests/test_gpu_detect_post.py)"}
-            del lg_, dl_, det_
-        gemm_alone = {"ms": 0.0, "flop": 0.0, "calls": len(gemm_cases)}
-        gemm_ops = []
-        for (M_, N_, K_, obf, d2_, relu_, acc_, msk_, bias_) in gemm_cases:
-            ld = (N_ + 7) // 8 * 8
-            a_ = torch.randn(M_, K_, device=dev).to(torch.bfloat16)
-            b_ = (torch.randn(N_, K_, device=dev) * 0.05).to(torch.bfloat16)
-            o_ = torch.zeros(M_, ld, device=dev, dtype=torch.bfloat16 if obf else torch.float32)[:, :N_]
-            o2_ = torch.empty(M_, ld, device=dev, dtype=torch.bfloat16)[:, :N_] if d2_ else None
-            m_ = torch.randn(M_, ld, device=dev).to(torch.bfloat16)[:, :N_] if msk_ else None
-            bi_ = torch.randn(N_, device=dev) if bias_ else None
-            gemm_ops.append((a_, b_, bi_, relu_, o_, o2_, acc_, m_))
-            ts_ = []
-            for _ in range(4):
-                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0_.record()
-                train_ops.gemm_ex(a_, b_, bi_, relu=relu_, out=o_, out2=o2_, accumulate=acc_, mask=m_)
-                e1_.record()
-                torch.cuda.synchronize()
-                ts_.append(e0_.elapsed_time(e1_))
-            gemm_alone["ms"] += float(np.median(ts_[1:]))
-            gemm_alone["flop"] += 2.0 * M_ * N_ * K_
-        # the same launches BACK TO BACK on the launching stream, one event pair around the whole sequence, L2 flushed
-        # before it: the sum of the kernels' durations without the cross-stream SM sharing of the step (where the
-        # weight-gradient GEMMs run under res5's kernels by design) and without per-launch host latency
-        gemm_b2b = {"ms": float("nan"), "flop": gemm_alone["flop"]}
-        if gemm_ops:
-            ts_ = []
-            for it in range(6):
-                flush.fill_(it)
-                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0_.record()
-                for (a_, b_, bi_, relu_, o_, o2_, acc_, m_) in gemm_ops:
-                    train_ops.gemm_ex(a_, b_, bi_, relu=relu_, out=o_, out2=o2_, accumulate=acc_, mask=m_)
-                e1_.record()
-                torch.cuda.synchronize()
-                ts_.append(e0_.elapsed_time(e1_))
-            gemm_b2b["ms"] = float(np.median(ts_[2:]))
-        del gemm_ops
-        # ---- end to end: pinned host inputs -> device, result -> host, every step ------------------------------
-        # The public call with HOST buffers.  Two device input buffers: the upload of step i+1 (copy stream) overlaps
-        # the compute of step i; every step's inputs are copied from pinned memory and every step's result (losses /
-        # detections) is read back, all inside the timed region.  `serial` is the same loop without the overlap.
-        res_keys = ["losses"] if train else ["boxes", "scores", "classes", "counts"]
-        res_host = {k: torch.empty_like(out[k], device="cpu").pin_memory() for k in res_keys}
-        e2e_steps = max(3, min(args.steps, 10))
-        cur = torch.cuda.current_stream()
-        cpy = torch.cuda.Stream()
-        dbuf = [{k: torch.empty_like(resident[k]) for k in names} for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
+            for a, b, t in rows[: len(rows) // prof_steps]:
+                ms = a.elapsed_time(b)
+                print("CALL %-34s %8.4f ms %s" % (name, ms, ("%.1f GF  %.0f TF/s %s" % (fl_of(t) / 1e9, fl_of(t) / ms / 1e9, t[1] if isinstance(t, tuple) else "")) if t else ""), file=sys.stderr)
+    _lib.PROFILE = None
+    b2b_ms, gemm_flop, gemm_calls = replay_gemms(gemm_cases, dev, flush)
 
-        def upload(i):
-            b = i & 1
-            with torch.cuda.stream(cpy):
-                cpy.wait_event(free[b])
-                for k in names:
-                    dbuf[b][k].copy_(host[k], non_blocking=True)
-                ready[b].record(cpy)
+    # ---- the stand-alone ROIAlign operator (all 49 bins, what torchvision.ops.roi_align computes) on the same maps, and
+    # its backward (lists planned ahead, as in the step), L2 flushed before every launch
+    with torch.enable_grad():
+        fmap = wl.resident["feat"].to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        rois_l = [wl.resident["boxes"][i][:P] for i in range(B)]
+        rr, oo = ops.boxes_to_rois(rois_l)
+        tf, tb, ts16 = [], [], []
+        for i in range(5):
+            flush.fill_(i)
+            e0_, e1_, e2_, e3_ = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0_.record()
+            pooled_full = ops.roi_align(fmap, rr, 7, 1.0 / 16, 0, True, channels_last_out=True, roi_batch_offsets=oo, bin_step=1)
+            e1_.record()
+            gfull = torch.ones_like(pooled_full)
+            flush.fill_(i + 1)
+            e2_.record()
+            pooled_full.backward(gfull)
+            e3_.record()
+            flush.fill_(i + 2)
+            e4_, e5_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e4_.record()
+            with torch.no_grad():
+                ops.roi_align(fmap, rr, 7, 1.0 / 16, 0, True, channels_last_out=True, roi_batch_offsets=oo, bin_step=2)
+            e5_.record()
+            torch.cuda.synchronize()
+            fmap.grad = None
+            if i >= 2:
+                tf.append(e0_.elapsed_time(e1_))
+                tb.append(e2_.elapsed_time(e3_))
+                ts16.append(e4_.elapsed_time(e5_))
+        full_bytes = B * C4 * HF * WF * 2 + B * P * 20 + B * P * C4 * 49 * 2
+        live_bytes = B * C4 * HF * WF * 2 + B * P * 20 + B * P * C4 * 16 * 2
+        roi_op = {"bins": "7x7", "algorithmic_bytes": full_bytes,
+                  "fwd_ms": float(np.median(tf)), "fwd_gbs": full_bytes / float(np.median(tf)) / 1e6,
+                  "bwd_ms": float(np.median(tb)), "bwd_gbs": full_bytes / float(np.median(tb)) / 1e6,
+                  "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
+        roi16_ms = float(np.median(ts16))
+        del pooled_full, gfull, fmap
+    # ---- the post-processing operator (BASELINE metric "NMS us"): softmax + decode + threshold compaction, per-class NMS,
+    # top-100 gather on this batch's proposals with SURVEY 8(d)'s logits, L2 flushed before every call
+    with torch.no_grad():
+        gen_ = torch.Generator().manual_seed(99)
+        lg_ = torch.randn(B * P, K + 1, generator=gen_)
+        peak_ = torch.rand(B * P, generator=gen_) < 0.3
+        cls_ = torch.randint(0, K, (B * P,), generator=gen_)
+        lg_[torch.arange(B * P)[peak_], cls_[peak_]] += 4.0
+        lg_[~peak_, K] += 4.0
+        lg_, dl_ = lg_.to(dev), (torch.randn(B * P, 4 * K, generator=gen_) * 0.5).to(dev)
+        pb_ = torch.cat([wl.resident["boxes"][i][:P] for i in range(B)], 0).float().contiguous()
+        offs_ = torch.arange(0, B * P + 1, P, dtype=torch.int32, device=dev)
+        hw_ = ops.image_hw_tensor([(H_IMG, W_IMG)] * B, dev)
+        tn_, tt_ = [], []
+        for i in range(6):
+            flush.fill_(i)
+            _lib.PROFILE = {}
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record()
+            det_ = ops.fast_rcnn_inference_device(lg_, dl_, pb_, offs_, hw_, 0.05, 0.5, 100)
+            e1_.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                tt_.append(e0_.elapsed_time(e1_))
+                tn_.append(sum(a.elapsed_time(b) for a, b, _ in _lib.PROFILE.get("b200_batched_nms", [])))
+            _lib.PROFILE = None
+        nms_op = {"nms_us_per_image": 1e3 * float(np.median(tn_)) / B, "postprocess_us_per_image": 1e3 * float(np.median(tt_)) / B,
+                  "candidates_per_image": float(det_["n_candidates"].float().mean()),
+                  "detections_per_image": float(det_["counts"].float().mean()), "images": B, "classes": K,
+                  "note": "b200_batched_nms (3 kernels: class sort, per-class NMS, merge) / whole fast_rcnn_inference on the device, "
+                          "CUDA events, median of 4, bit-exact keep indices (tests/test_gpu_detect_post.py)"}
+        del lg_, dl_, det_
 
-        def run_e2e(n, overlap):
-            for ev in free:
-                ev.record(cur)
-            if overlap:
-                upload(0)
-            for i in range(n):
-                b = i & 1
-                if overlap:
-                    if i + 1 < n:
-                        upload(i + 1)
-                    cur.wait_event(ready[b])
-                    o = run_step(dbuf[b])
-                    free[b].record(cur)
-                else:
-                    o = run_step({k: host[k].to(dev, non_blocking=True) for k in names})
-                for k in res_host:
-                    res_host[k].copy_(o[k], non_blocking=True)
-                if not overlap:
-                    cur.synchronize()
-            cur.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e, h2d_bytes, d2h_bytes = wl.e2e(e2e_steps)
+    losses_last = [float(v) for v in wl.out["losses"].tolist()] if train else None
+    n_det = float(np.mean([len(r) for r in wl.out])) if not train else None
+    wl.close()
 
-        e2e = {}
-        for name, overlap in (("serial", False), ("overlap", True)):
-            run_e2e(3, overlap)
+    # ---- the other BASELINE configurations, briefly, in the same process ---------------------------------------------
+    extra = {}
+    if not args.no_extras:
+        plan = [("infer_voc20", "infer", 20, False), ("infer_coco80", "infer", 80, False), ("distill_voc20", "train", 20, True)]
+        if not train:
+            plan = [("train_voc20", "train", 20, False)] + plan[1:]
+        for name, mode, k, distill in plan:
+            try:
+                w2 = Workload(args, mode, k, distill, dev, rank, world)
+                w2.prepare(3)
+                n2 = 10
+                tot2, _, l2, _, ev2 = w2.timed(n2, flush)
+                st2 = w2.stage_split(flush, ev2, n=3)
+                ent = {"images_per_sec": world * B * n2 / (tot2 * 1e-3), "ms_per_step": tot2 / n2, "stage_ms": st2, "gpu_launches": l2,
+                       "config": workload_config(args, mode, k, distill, B)["workload"], "steps": n2, "warmup": 3,
+                       "cuda_graph": w2.graph_note}
+                if mode == "infer":
+                    ent["nms_us_per_image"] = 1e3 * st2["decode_nms"] / B
+                    ent["detections_per_image"] = float(np.mean([len(r) for r in w2.out]))
+                    if world > 1:        # the evaluation exchange (pascal_voc_evaluation.py:84): padded all-gather over NCCL
+                        cnt, dets = bdist.pack_detections(w2.out)
+                        tg = []
+                        for _ in range(4):
+                            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0_.record()
+                            allc, alld = bdist.all_gather_detections(cnt, dets, B * world)
+                            e1_.record()
+                            torch.cuda.synchronize()
+                            tg.append(e0_.elapsed_time(e1_))
+                        ent["all_gather_detections_ms"] = float(np.median(tg[1:]))
+                        ent["all_gather_detections_images"] = int(allc.shape[0])
+                extra[name] = ent
+                w2.close()
+                del w2
+            except Exception as ex:  # noqa: BLE001
+                extra[name] = {"error": repr(ex)[:300]}
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0.record()
-            run_e2e(e2e_steps, overlap)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            e2e[name] = float(ms)
-        e2e_ms = e2e["overlap"]
 
     if rank == 0:
         peaks = {}
@@ -624,79 +747,75 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tc_peak = float(peaks.get("bf16_tflops_sustained", 1366.0))
+        tc_burst = float(peaks.get("bf16_tflops", 1590.0))
+        tc_sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
         R = B * P
-        e = 2
-        roi_bytes = B * C4 * HF * WF * e + R * 20 + R * C4 * nb * nb * e
+        cfg_key = "%s_b%d_p%d_k%d" % (args.mode + ("_distill" if args.distill else ""), B, P, K)
         roi_ms = prof.get("b200_roi_align_fwd", {}).get("ms_per_step", float("nan"))
-        roi_gbs = roi_bytes / (roi_ms * 1e-3) / 1e9
-        # DRAM traffic per launch from the committed `ncu --set full` capture of exactly this configuration
-        # (profiles/r01_ncu_full_step_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: not captured
-        default_cfg = train and (B, P, K, bin_step) == (8, 512, 20, 2)
-        roi_traffic = 143825920 if default_cfg else None
-        gemm_traffic = 652731904 if default_cfg else None           # sum over the step's 26 GEMM launches
-        roi_roof = {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<%d,%d,%d> (bf16, rank 0)" % (nb, nb, bin_step),
-                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak, "traffic": roi_traffic,
+        roi_gbs = live_bytes / (roi_ms * 1e-3) / 1e9
+        traffic = traffic_from_profiles(cfg_key) or {}
+        roi_roof = {"kernel": "roi_slice_prepare_kernel + roi_align_fwd_slice_kernel<4,4,2> (bf16, rank 0)",
+                    "bound": "hbm", "achieved": roi_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": roi_gbs / hbm_peak,
+                    "traffic": traffic.get("roi_align_fwd"),
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                    "algorithmic_bytes_per_launch": roi_bytes, "avg_launch_ms": roi_ms,
-                    "bins_pooled": "%dx%d of 7x7%s" % (nb, nb, " (dead bins skipped: res5 block 0 reads [::2, ::2] only)" if bin_step > 1 else ""),
+                    "algorithmic_bytes_per_launch": live_bytes, "avg_launch_ms": roi_ms,
+                    "bins_pooled": "4x4 of 7x7 (dead bins skipped: res5 block 0 reads [::2, ::2] only)",
                     "timing": "CUDA events recorded around the entry point on the launching stream, median over %d profiled steps" % prof_steps,
-                    "standalone_op": dict(roi_op, fwd_frac=roi_op["fwd_gbs"] / hbm_peak, bwd_frac=roi_op["bwd_gbs"] / hbm_peak) if roi_op else None}
-        # dominant hand-written kernel of the step = the tcgen05 GEMM (all launches of the step together)
+                    "launched_alone_ms": roi16_ms,
+                    "standalone_op": dict(roi_op, fwd_frac=roi_op["fwd_gbs"] / hbm_peak, bwd_frac=roi_op["bwd_gbs"] / hbm_peak)}
+        # dominant hand-written kernel of the step = the tcgen05 GEMMs (res5 convolutions + text-fusion chain)
         gem = {"ms": 0.0, "flop": 0.0, "calls": 0.0}
-        for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex"):
+        for name in ("b200_gemm_bf16", "b200_gemm_bf16_ex", "b200_gemm2"):
             if name in prof:
                 gem["ms"] += prof[name]["ms_per_step"]
                 gem["flop"] += prof[name].get("flop_per_step", 0.0)
                 gem["calls"] += prof[name]["calls_per_step"]
         gemm_tf = gem["flop"] / (gem["ms"] * 1e-3) / 1e12 if gem["ms"] else float("nan")
-        alone_tf = gemm_alone["flop"] / (gemm_alone["ms"] * 1e-3) / 1e12 if gemm_alone["ms"] else float("nan")
-        b2b_ok = gemm_b2b["ms"] == gemm_b2b["ms"] and gemm_b2b["ms"] > 0
-        b2b_tf = gemm_b2b["flop"] / (gemm_b2b["ms"] * 1e-3) / 1e12 if b2b_ok else gemm_tf
-        gemm_roof = {"kernel": "gemm_bf16_tcgen05_kernel<BN> (all %d launches of the step, rank 0)" % round(gem["calls"]),
-                     "bound": "tensor", "achieved": b2b_tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": b2b_tf / tc_peak, "traffic": gemm_traffic,
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long sequence)" if peaks else "fallback",
-                     "algorithmic_flop_per_step": gem["flop"], "ms_per_step": gemm_b2b["ms"] if b2b_ok else gem["ms"],
-                     "timing": "every GEMM launch of one step (same shapes / epilogues, fresh operands) issued back to back on the launching "
-                               "stream, ONE CUDA event pair around the sequence, L2 flushed before it, median of 4: the sum of the kernels' "
-                               "durations.  Inside the step the weight-gradient GEMMs run on a side stream under res5's kernels by design, so "
-                               "per-call event pairs there also measure that sharing: see in_step",
-                     "in_step": {"achieved": gemm_tf, "ms_per_step": gem["ms"], "frac": gemm_tf / tc_peak,
+        b2b_ok = b2b_ms == b2b_ms and b2b_ms > 0
+        b2b_tf = gemm_flop / (b2b_ms * 1e-3) / 1e12 if b2b_ok else gemm_tf
+        g2 = prof.get("b200_gemm2", {})
+        gemm_roof = {"kernel": "gemm2_pair_kernel<BN,F> (tcgen05.mma.cta_group::2: res5 convolutions fwd + dgrad) + gemm_bf16_tcgen05_kernel<BN> "
+                               "(text-fusion chain): all %d tensor-core launches of the step, rank 0" % round(gem["calls"]),
+                     "bound": "tensor", "achieved": b2b_tf, "peak": tc_burst, "unit": "TFLOP/s", "frac": b2b_tf / tc_burst,
+                     "frac_of_sustained_peak": b2b_tf / tc_sust,
+                     "traffic": traffic.get("gemm"),
+                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; bf16_tflops_sustained = %.0f beside it)" % tc_sust) if peaks else "fallback",
+                     "algorithmic_flop_per_step": gem["flop"], "ms_per_step": b2b_ms if b2b_ok else gem["ms"],
+                     "timing": "every tensor-core GEMM launch of one step (same shapes / layouts / epilogues, fresh operands) issued back to back on "
+                               "the launching stream, ONE CUDA event pair around the sequence, L2 flushed before it, median of 4: the sum of the "
+                               "kernels' durations.  Inside the step the weight-gradient GEMMs run on a side stream by design: see in_step",
+                     "in_step": {"achieved": gemm_tf, "ms_per_step": gem["ms"], "frac": gemm_tf / tc_burst,
                                  "note": "CUDA events around every GEMM entry-point call on its launching stream, summed per step, median over "
                                          "%d profiled eager steps (SMs shared with the other streams' kernels)" % prof_steps},
-                     "launched_alone": {"achieved": alone_tf, "ms_per_step": gemm_alone["ms"],
-                                        "note": "every GEMM shape / epilogue of the step re-issued alone with a synchronize between launches: "
-                                                "includes the launch latency that back-to-back launches hide"}}
+                     "res5_convolutions": {"ms_per_step": g2.get("ms_per_step"), "tflops": g2.get("tflops"), "calls_per_step": g2.get("calls_per_step")}}
         ours_ms = sum(v["ms_per_step"] for v in prof.values())
-        dominant_is_gemm = gem["ms"] >= roi_ms
         line = {
             "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(args, B), cuda_graph=graph_note),
-            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
-                    "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in res_host.values())),
+            "config": dict(workload_config(args, args.mode, K, train and args.distill, B), cuda_graph=wl.graph_note),
+            "e2e": {"value": world * B * e2e_steps / (e2e["overlap"] * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "pipeline": "double-buffered device inputs: upload of step i+1 on a copy stream overlaps compute of step i",
                     "serial_value": world * B * e2e_steps / (e2e["serial"] * 1e-3)},
             "gpu_launches": int(launches),
+            "library_kernels": "none on the timed path (res5 runs on gemm2_pair_kernel; RES5_IMPL=cudnn restores the library convolutions)",
             "clocks": sampler.summary(),
-            "roofline": gemm_roof if dominant_is_gemm else roi_roof,
-            "roofline_other": roi_roof if dominant_is_gemm else gemm_roof,
-            "stage_ms": dict(zip(stage_names, stage_ms)),
-            "stage_ms_note": "eager steps (the timed steps replay one CUDA graph)" if graph is not None else "timed steps",
-            "roi_align_gbs": {"in_step_%dx%d_bins" % (nb, nb): roi_gbs, "operator_7x7_fwd": roi_op.get("fwd_gbs"), "operator_7x7_bwd": roi_op.get("bwd_gbs")},
+            "roofline": gemm_roof, "roofline_other": roi_roof,
+            "stage_ms": stage_ms,
+            "stage_ms_note": "eager steps with CUDA events at the stage boundaries inside forward() (the timed steps replay one CUDA graph)" if wl.graph_note.startswith(("whole", "forward")) else "timed steps",
+            "roi_align_gbs": {"in_step_4x4_bins": roi_gbs, "operator_7x7_fwd": roi_op.get("fwd_gbs"), "operator_7x7_bwd": roi_op.get("bwd_gbs")},
             "nms": nms_op,
-            "own_kernels_ms_per_step": ours_ms, "host_enqueue_ms_per_step": cpu_enqueue_ms,
+            "own_kernels_ms_per_step": ours_ms, "host_enqueue_ms_per_step": host_ms,
             "own_kernels_profile": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "flop_per_step"}
                                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+            "extra": extra,
         }
         if train:
-            line["losses_last_step"] = [float(v) for v in out["losses"].tolist()]
+            line["losses_last_step"] = losses_last
         else:
-            line["nms_us_per_image"] = 1e3 * stage_ms[4] / B
-            line["candidates_per_image"] = out["n_candidates"].float().mean().item()
-            line["detections_per_image"] = out["counts"].float().mean().item()
+            line["nms_us_per_image"] = 1e3 * stage_ms["decode_nms"] / B
+            line["detections_per_image"] = n_det
         if not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = run_cpu_baseline(args)
@@ -704,8 +823,7 @@ def main():
                 line["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(line))
     if world > 1:
-        # drop the captured graph (it may hold NCCL work) before the communicator goes away
-        graph = None
+        # drop the captured graphs (they may hold NCCL work) before the communicator goes away
         import gc
         gc.collect()
         torch.cuda.synchronize()

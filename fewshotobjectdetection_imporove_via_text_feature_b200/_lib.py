@@ -79,7 +79,7 @@ SIGNATURES = {
     "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
     "b200_cast_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "b200_label_sample_proposals": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.c_ulonglong] + [c_void_p] * 7 + [c_void_p]),
+    "b200_label_sample_proposals": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.c_ulonglong] + [c_void_p] * 8 + [c_void_p]),
     "b200_rpn_select_workspace_bytes": (c_size_t, [c_int] * 4),
     "b200_rpn_select_proposals": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float] * 2 + [c_void_p] * 4 + [c_void_p, c_size_t, c_void_p]),
     "b200_detector_postprocess": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p]),

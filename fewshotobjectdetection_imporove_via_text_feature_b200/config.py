@@ -48,7 +48,7 @@ def get_cfg():
             ADDITION=C(NAME=None, INFERENCE_WITH_GT=False, TEACHER_TRAINING=False, STUDENT_TRAINING=False,
                        DISTIL_MODE=False, FREEZEATTENTION=False),
             # b200roi extensions (absent keys fall back to these defaults when a reference cfg is passed)
-            B200=C(CHANNELS_LAST=True, RES5_DTYPE="bfloat16", RES5_IMPL="tcgen05", EMBED_DIR="datasets", SKIP_DEAD_BINS=True, FUSED_TRAINING=True, COSINE_LOGITS=False,
+            B200=C(CHANNELS_LAST=True, RES5_DTYPE="bfloat16", RES5_IMPL="tcgen05", STATIC_SAMPLING=False, EMBED_DIR="datasets", SKIP_DEAD_BINS=True, FUSED_TRAINING=True, COSINE_LOGITS=False,
                    COSINE_TAU=20.0),
         ),
         TEST=C(DETECTIONS_PER_IMAGE=100, PCB_ENABLE=False, PCB_MODELTYPE="resnet", PCB_MODELPATH="", PCB_ALPHA=0.50,

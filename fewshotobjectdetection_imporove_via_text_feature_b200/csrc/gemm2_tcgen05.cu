@@ -566,8 +566,9 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
     B200_CHECK_ARG(d->conv_c % kG2BK == 0 && d->M % 16 == 0 && !d->A2 && !d->a_mn && d->K == 9 * d->conv_c,
                    "gemm2: conv3x3 mode needs C %% 64 == 0, M = 16 R, K = 9 C, a K-major 4x4 NHWC activation");
   } else {
-    B200_CHECK_ARG(d->K % 8 == 0, "gemm2: K must be a multiple of 8");
-    B200_CHECK_ARG(!d->A2 || (d->K % kG2BK == 0 && d->K2 > 0 && d->K2 % 8 == 0 && !d->a_mn && !d->b_mn),
+    // K itself is free (TMA zero-fills the tail of the last 64-wide K block on both operands); only the row pitches of the
+    // bf16 tensors are constrained (multiples of 8 elements, checked above)
+    B200_CHECK_ARG(!d->A2 || (d->K % kG2BK == 0 && d->K2 > 0 && !d->a_mn && !d->b_mn),
                    "gemm2: K-concat needs K %% 64 == 0 and K-major operands");
   }
   B200_CHECK_ARG(!d->bits_out || (d->N % 32 == 0), "gemm2: bits_out needs N %% 32 == 0");

@@ -42,7 +42,8 @@ __device__ __forceinline__ void best_match(const float4 p, const float4* __restr
 __global__ void __launch_bounds__(kLsThreads)
 label_sample_kernel(const float4* __restrict__ props, const int32_t* __restrict__ prop_offsets, const float4* __restrict__ gt,
                     const int64_t* __restrict__ gt_classes, const int32_t* __restrict__ gt_offsets, int num_classes,
-                    float iou_thresh, int batch, int max_pos, unsigned long long seed, int32_t* __restrict__ matched_idx,
+                    float iou_thresh, int batch, int max_pos, unsigned long long seed,
+                    const long long* __restrict__ seed_salt, int32_t* __restrict__ matched_idx,
                     int32_t* __restrict__ matched_label, int32_t* __restrict__ sampled_idx, float4* __restrict__ out_props,
                     int64_t* __restrict__ out_classes, float4* __restrict__ out_gt, int32_t* __restrict__ counts) {
   __shared__ unsigned long long s_key[kLsMaxProps];
@@ -51,6 +52,14 @@ label_sample_kernel(const float4* __restrict__ props, const int32_t* __restrict_
   const int n = blockIdx.x;
   const int p0 = prop_offsets[n], P = prop_offsets[n + 1] - p0;
   const int g0 = gt_offsets[n], M = gt_offsets[n + 1] - g0;
+  if (P > kLsMaxProps || M > kLsMaxGt || P < 0 || M < 0) {
+    // the offsets on the device exceed what the host was told (max_props_per_image / max_gt_per_image): the shared
+    // arrays are sized for the limits, so refuse the image (no rows) instead of overrunning them
+    if (threadIdx.x == 0) { counts[2 * n] = 0; counts[2 * n + 1] = 0; }
+    for (int i = threadIdx.x; i < batch; i += kLsThreads) { sampled_idx[(size_t)n * batch + i] = -1; out_classes[(size_t)n * batch + i] = -1; }
+    return;
+  }
+  if (seed_salt) seed += (unsigned long long)*seed_salt;      // device-resident step counter (CUDA-graph replays)
   for (int g = threadIdx.x; g < M; g += kLsThreads) s_gt[g] = gt[g0 + g];
   if (threadIdx.x == 0) s_nfg = 0;
   __syncthreads();
@@ -123,7 +132,7 @@ extern "C" int b200_label_sample_proposals(const float* proposals, const int32_t
                                            const int64_t* gt_classes, const int32_t* gt_offsets, int num_images,
                                            int max_props_per_image, int max_gt_per_image, int num_classes, float iou_thresh,
                                            int batch_per_image, int max_positive, unsigned long long seed,
-                                           int32_t* matched_idx, int32_t* matched_label, int32_t* sampled_idx,
+                                           const int64_t* seed_salt, int32_t* matched_idx, int32_t* matched_label, int32_t* sampled_idx,
                                            float* out_proposals, int64_t* out_classes, float* out_gt_boxes, int32_t* counts,
                                            b200_stream_t stream) {
   B200_CHECK_ARG(prop_offsets && gt_offsets && sampled_idx && out_proposals && out_classes && out_gt_boxes && counts,
@@ -139,7 +148,7 @@ extern "C" int b200_label_sample_proposals(const float* proposals, const int32_t
   if (num_images == 0) return B200_OK;
   label_sample_kernel<<<num_images, kLsThreads, 0, (cudaStream_t)stream>>>(
       (const float4*)proposals, prop_offsets, (const float4*)gt_boxes, gt_classes, gt_offsets, num_classes, iou_thresh,
-      batch_per_image, max_positive, seed, matched_idx, matched_label, sampled_idx, (float4*)out_proposals, out_classes,
+      batch_per_image, max_positive, seed, (const long long*)seed_salt, matched_idx, matched_label, sampled_idx, (float4*)out_proposals, out_classes,
       (float4*)out_gt_boxes, counts);
   B200_CUDA_LAUNCH_CHECK("label_sample_proposals");
   return B200_OK;

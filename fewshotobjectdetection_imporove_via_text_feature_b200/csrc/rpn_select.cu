@@ -139,7 +139,9 @@ rpn_topk_filter_kernel(const float* __restrict__ proposals, const float* __restr
       }
       int total;
       const int ex = block_exclusive_scan_1024(keepf, s_warp, &total);
-      if (keepf) {
+      // the segment holds `cap` candidates: a raw ABI caller that passes less than sum_l min(pre_nms_topk, A_l) must not
+      // make this image overrun its neighbour's segment / the workspace — the excess is dropped and reported
+      if (keepf && running + ex < cap) {
         const size_t o = out0 + running + ex;
         *reinterpret_cast<float4*>(cand_boxes + 4 * o) = b;
         cand_scores[o] = s;
@@ -150,7 +152,10 @@ rpn_topk_filter_kernel(const float* __restrict__ proposals, const float* __restr
     __syncthreads();
   }
   __syncthreads();
-  if (threadIdx.x == 0) { cand_count[img] = running; n_invalid[img] = s_bad; }
+  if (threadIdx.x == 0) {
+    cand_count[img] = min(running, cap);
+    n_invalid[img] = running > cap ? -(running - cap) : s_bad;        // negative: candidates dropped for lack of capacity
+  }
 }
 
 __global__ void rpn_gather_kernel(const float* __restrict__ cand_boxes, const float* __restrict__ cand_scores,

@@ -93,11 +93,18 @@ class FastRCNNOutputs(object):
         self.Guided_gt_classes = Guided_gt_classes
 
     # ---- training ---------------------------------------------------------------------------------
-    def _log_accuracy(self):
+    def _log_accuracy(self, defer=None):
+        """fast_rcnn.py:191-220.  defer(key, tensor): hand the counts over without a host read (static-shape masks instead
+        of boolean indexing, asynchronous copy; `ROIHeads.flush_deferred_logs` logs them one step later)."""
         n = self.gt_classes.numel()
         pred = self.pred_class_logits.argmax(dim=1)
         bg = self.pred_class_logits.shape[1] - 1
         fg = (self.gt_classes >= 0) & (self.gt_classes < bg)
+        if defer is not None:
+            hit = pred == self.gt_classes
+            defer("accuracy", torch.stack([hit.sum(), fg.sum(), (hit & fg).sum(), ((pred == bg) & fg).sum(),
+                                           torch.full_like(fg.sum(), n)]))
+            return
         stats = torch.stack([(pred == self.gt_classes).sum(), fg.sum(), (pred[fg] == self.gt_classes[fg]).sum(),
                              (pred[fg] == bg).sum()]).tolist()   # one sync instead of four
         acc, n_fg, fg_acc, fn = stats

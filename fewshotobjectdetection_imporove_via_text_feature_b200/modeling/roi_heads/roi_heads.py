@@ -63,6 +63,21 @@ class ROIHeads(nn.Module):
         self.smooth_l1_beta = bh.SMOOTH_L1_BETA
         self.proposal_matcher = Matcher(rh.IOU_THRESHOLDS, rh.IOU_LABELS, allow_low_quality_matches=False)
         self.box2box_transform = Box2BoxTransform(weights=bh.BBOX_REG_WEIGHTS)
+        # STATIC_SAMPLING: the training forward makes no host read at all (CUDA-graph capturable): every image contributes
+        # exactly BATCH_SIZE_PER_IMAGE sampled rows (true whenever an image has that many background candidates, i.e.
+        # always with RPN's 2000 proposals; a device flag records a violation), and the logging scalars the reference
+        # reads back synchronously (roi_heads.py:236-248, fast_rcnn.py:191-220) are copied to pinned host memory
+        # asynchronously and handed to the event storage by `flush_deferred_logs()` one step later.
+        self.static_sampling = bool(b200_opt(cfg, "STATIC_SAMPLING", False))
+        self._deferred = {}
+
+    def _mark(self, name, tensor=None):
+        """Instrumentation hook (bench.py sets `_stage_cb`): called at the stage boundaries inside `forward` with the
+        tensor the stage produced, so that a caller can record CUDA events / gradient hooks without reaching into the
+        forward's internals.  No-op otherwise."""
+        cb = getattr(self, "_stage_cb", None)
+        if cb is not None:
+            cb(name, tensor)
 
     def _assign_labels(self, matched_idxs, matched_labels, gt_classes):
         if gt_classes.numel() > 0:
@@ -86,7 +101,10 @@ class ROIHeads(nn.Module):
         has its distribution but not torch's RNG stream."""
         r = ops.label_and_sample_proposals([p.proposal_boxes.tensor for p in proposals], [t.gt_boxes.tensor for t in targets],
                                            [t.gt_classes for t in targets], self.num_classes, self.proposal_matcher.thresholds[1],
-                                           self.batch_size_per_image, self.positive_sample_fraction)
+                                           self.batch_size_per_image, self.positive_sample_fraction,
+                                           seed_salt=getattr(self, "_drop_salt", None) if self.static_sampling else None)
+        if self.static_sampling:
+            return self._static_samples(r, proposals), None, None
         counts = r["counts"].cpu().tolist()
         out = []
         for i, (p, t) in enumerate(zip(proposals, targets)):
@@ -101,6 +119,52 @@ class ROIHeads(nn.Module):
         n_bg = [c[1] - c[0] for c in counts]
         return out, n_fg, n_bg
 
+    def _static_samples(self, r, proposals):
+        """Fixed-shape form of the sampled batch: B rows per image, no host read.  Padding rows (none, unless an image has
+        fewer than B candidates — flagged) are relabelled background."""
+        B = self.batch_size_per_image
+        counts = r["counts"]
+        classes = torch.where(r["classes"] < 0, torch.full_like(r["classes"], self.num_classes), r["classes"])
+        out = []
+        for i, p in enumerate(proposals):
+            q = p[r["sampled_idx"][i].long().clamp_(0, len(p) - 1)]
+            q.proposal_boxes = Boxes(r["boxes"][i])
+            q.gt_classes = classes[i]
+            q.gt_boxes = Boxes(r["gt_boxes"][i])
+            out.append(q)
+        fg = counts[:, 0].float().mean()
+        stats = torch.stack([fg, counts[:, 1].float().mean() - fg, (counts[:, 1] != B).any().float()])
+        self._defer("sample", stats)
+        return out
+
+    def _defer(self, key, dev_tensor):
+        """Asynchronous device -> pinned-host copy of a few logging scalars (a memcpy node when captured in a graph)."""
+        buf = self._deferred.get(key)
+        if buf is None or buf.numel() != dev_tensor.numel():
+            buf = torch.zeros(dev_tensor.numel(), dtype=torch.float32).pin_memory()
+            self._deferred[key] = buf
+        buf.copy_(dev_tensor.detach().float().reshape(-1), non_blocking=True)
+
+    def flush_deferred_logs(self):
+        """Hand the scalars of the most recently completed step to the event storage (reference keys); raises if a
+        static-sampling step did not have BATCH_SIZE_PER_IMAGE rows for every image."""
+        st = get_event_storage()
+        s = self._deferred.get("sample")
+        if s is not None:
+            n_fg, n_bg, bad = s.tolist()
+            if bad:
+                raise RuntimeError("STATIC_SAMPLING: an image had fewer than BATCH_SIZE_PER_IMAGE sampled proposals; "
+                                   "run this batch with MODEL.B200.STATIC_SAMPLING = False")
+            st.put_scalar("roi_head/num_fg_samples", n_fg)
+            st.put_scalar("roi_head/num_bg_samples", n_bg)
+        a = self._deferred.get("accuracy")
+        if a is not None:
+            acc, n_fg, fg_acc, fn, n = a.tolist()
+            st.put_scalar("fast_rcnn/cls_accuracy", acc / max(n, 1))
+            if n_fg > 0:
+                st.put_scalar("fast_rcnn/fg_cls_accuracy", fg_acc / n_fg)
+                st.put_scalar("fast_rcnn/false_negative", fn / n_fg)
+
     @torch.no_grad()
     def label_and_sample_proposals(self, proposals, targets):
         if self.proposal_append_gt:
@@ -110,6 +174,8 @@ class ROIHeads(nn.Module):
         if (proposals and all(p.proposal_boxes.tensor.is_cuda for p in proposals) and len(th) == 3 and list(lb) == [0, 1] and
                 not extra_gt and max(len(p) for p in proposals) <= 4096 and max(len(t) for t in targets) <= 256):
             out, n_fg, n_bg = self._label_and_sample_device(proposals, targets)
+            if n_fg is None:             # static sampling: the scalars are logged by flush_deferred_logs
+                return out
             st = get_event_storage()
             st.put_scalar("roi_head/num_fg_samples", np.mean(n_fg))
             st.put_scalar("roi_head/num_bg_samples", np.mean(n_bg))
@@ -220,8 +286,10 @@ class Res5ROIHeads(ROIHeads):
         skip = self.skip_dead_bins and not self._res5_trainable() and blk0.reads_strided_1x1()
         x = self.pooler([features[f] for f in self.in_features], [p.proposal_boxes for p in proposals],
                         bin_step=blk0.stride if skip else 1)
+        self._mark("roi_align", x)
         pooled = self._res5_mean(x, prestrided=skip)
         self._after_res5_enqueued()
+        self._mark("res5_mean", pooled)
         return pooled
 
     def _after_res5_enqueued(self):
@@ -377,6 +445,7 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         if self.training:
             proposals = self.label_and_sample_proposals(proposals, targets)
             gt_classes = cat([p.gt_classes for p in proposals], dim=0)
+            self._mark("label_sample")
         elif test_with_gt:
             proposals = self.label_proposals(proposals, targets)
         feature_pooled = self._pooled(features, proposals)
@@ -384,9 +453,12 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         if feature_pooled.is_cuda and self._fused_train_path():
             losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes, teacher_logits,
                                                      self._kd_params() if teacher_logits is not None else None)
-            FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy()
+            FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy(
+                self._defer if self.static_sampling else None)
+            self._mark("text_fusion_losses")
             return [], losses
         att_output, att_loss = self.forward_att(feature_pooled, gt_classes)
+        self._mark("text_fusion_predictor")
         outputs = FastRCNNOutputs(self.box2box_transform, att_output["pred_logits"], att_output["pred_bbox"], proposals,
                                   self.smooth_l1_beta)
         if self.training:
@@ -399,8 +471,8 @@ class SematicRes5ROIHeads(Res5ROIHeads):
                                                     {"alpha": alpha, "temperature": T})
             return [], losses
         pred, _ = outputs.inference(self.test_score_thresh, self.test_nms_thresh, self.test_detections_per_img)
+        self._mark("decode_nms")
         return pred, {}
-
 
     def _teacher_logits(self, feature_pooled, gt_classes):
         """Hook of the distillation head: logits of a frozen teacher for this batch, or None."""

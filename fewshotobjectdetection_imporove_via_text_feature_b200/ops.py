@@ -552,7 +552,11 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
     d.tile_n, d.max_clusters, d.epilogue_variant = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0], GEMM2_GENERIC_EPILOGUE[0]
     import ctypes
     _lib.call("b200_gemm2", ctypes.byref(d), _stream(),
-              tag=(2.0 * M * N * (K + K2), ("gemm2", M, N, K + K2, int(conv_c), int(a_mn), int(b_mn))))
+              tag=(2.0 * M * N * (K + K2),
+                   dict(M=M, N=N, K=K, K2=K2, conv_c=int(conv_c), a_mn=bool(a_mn), b_mn=bool(b_mn), relu=bool(relu),
+                        acc=bool(accumulate), out=out is not None, out2=out2 is not None, f32=out_f32 is not None,
+                        bias=bias is not None, res=residual is not None, mbits=mask_bits is not None,
+                        mact=mask_act is not None, bout=bits_out is not None, mean=rowmean_out is not None)))
     return out
 
 
@@ -591,7 +595,7 @@ _LS_CALLS = [0]
 
 
 def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, iou_thresh=0.5, batch_per_image=512,
-                               positive_fraction=0.25, seed=None, want_labels=False):
+                               positive_fraction=0.25, seed=None, want_labels=False, seed_salt=None):
     """S1 on the device, one launch for the batch (csrc/label_sample.cu; reference roi_heads.py:157-250).
     prop_boxes / gt_boxes / gt_classes: per-image lists of (P_i,4) fp32, (M_i,4) fp32, (M_i,) int64 CUDA tensors.
     Returns dict: sampled_idx (N,B) int32, boxes (N,B,4), classes (N,B) int64, gt_boxes (N,B,4), counts (N,2) int32
@@ -615,11 +619,13 @@ def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, io
     mi = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
     ml = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
     if seed is None:
-        _LS_CALLS[0] += 1
-        seed = (torch.initial_seed() * 2654435761 + _LS_CALLS[0]) & 0x7FFFFFFFFFFFFFFF
+        if seed_salt is None:
+            _LS_CALLS[0] += 1
+        seed = (torch.initial_seed() * 2654435761 + (_LS_CALLS[0] if seed_salt is None else 0)) & 0x7FFFFFFFFFFFFFFF
     _lib.call("b200_label_sample_proposals", props.data_ptr(), poff.data_ptr(), _ptr(gts) if gts.numel() else 0,
               _ptr(gcl) if gcl.numel() else 0, goff.data_ptr(), N, max(pc) if pc else 0, max(gc) if gc else 0, int(num_classes),
-              float(iou_thresh), B, int(B * positive_fraction), int(seed), _ptr(mi), _ptr(ml), out["sampled_idx"].data_ptr(),
+              float(iou_thresh), B, int(B * positive_fraction), int(seed), _ptr(seed_salt), _ptr(mi), _ptr(ml),
+              out["sampled_idx"].data_ptr(),
               out["boxes"].data_ptr(), out["classes"].data_ptr(), out["gt_boxes"].data_ptr(), out["counts"].data_ptr(),
               _stream())
     if want_labels:

@@ -60,16 +60,16 @@ def transpose_bf16(src, pad_rows_to=None):
     return dst
 
 
-def colsum(src, n=None, out=None):
-    """Column sums of `src` (rows, cols) -> fp32 (cols,) [or into `out`], two-pass and ordered (bias gradients)."""
+def colsum(src, n=None, out=None, accumulate=False):
+    """Column sums of `src` (rows, cols) -> fp32 (cols,) [or (+)= into `out`], two-pass and ordered (bias gradients)."""
     rows, cols = src.shape
     if out is None:
         out = torch.empty(cols, dtype=torch.float32, device=src.device)
     assert out.dtype == torch.float32 and out.numel() == cols and out.is_contiguous()
     nbytes = _lib.lib().b200_colsum_workspace_bytes(cols)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
-    _lib.call("b200_colsum", src.data_ptr(), _dt(src), src.stride(0), rows, cols, out.data_ptr(), 0, ws.data_ptr(), nbytes,
-              _stream())
+    _lib.call("b200_colsum", src.data_ptr(), _dt(src), src.stride(0), rows, cols, out.data_ptr(), int(accumulate), ws.data_ptr(),
+              nbytes, _stream())
     return out if n is None else out[:n]
 
 
@@ -226,6 +226,20 @@ def skinny(mode, A, B, bias=None, relu=False, scale=1.0, relu_ref=None, out_bias
     return (out, ob) if (out_bias and mode == "tn") else out
 
 
+def _claim_sinks(owners):
+    """Deferred parameter gradients are written (not accumulated) into the optimizer's flat gradient buffer: a parameter that
+    reaches a fused backward twice between two `zero_grad` calls (used twice in the graph, or micro-batch accumulation)
+    would silently lose the first contribution — refuse instead."""
+    for p in owners or ():
+        opt = getattr(p, "_b200_opt", None)
+        if opt is None:
+            continue
+        if getattr(p, "_b200_claim", -1) == opt.epoch:
+            raise RuntimeError("FlatSGD(direct_grads=True): a parameter received a second fused gradient write in one step; "
+                               "use direct_grads=False for gradient accumulation / shared parameters")
+        p._b200_claim = opt.epoch
+
+
 class _TextSide(torch.autograd.Function):
     """(T, key_projection, value_projection, w_k, w_v, dummy, w_q) -> (Kq (L,d) = [w_k(relu(key_proj T)); dummy] Wq / sqrt(d),
     Vp (L,d) = [w_v(relu(value_proj T)); 0]) — attentive_modules.py:274-277,125-135 plus the folded query operand."""
@@ -237,6 +251,7 @@ class _TextSide(torch.autograd.Function):
         sinks = [getattr(p, "_b200_grad_sink", None) for p in params]        # see _FusedHeadTrain.forward
         ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
                                  s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
+        ctx.sink_owners = params if ctx.sinks is not None else None
         f = lambda t: t.detach().float().contiguous()
         T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq = map(f, (T, Wkp, bkp, Wvp, bvp, Wk, Wv, Wq))
         d = Wq.shape[0]
@@ -259,6 +274,7 @@ class _TextSide(torch.autograd.Function):
             if ev is not None:
                 cur.wait_event(ev)
                 g.record_stream(cur)
+        _claim_sinks(ctx.sink_owners)
         sk = dict(zip(("Wkp", "bkp", "Wvp", "bvp", "Wk", "Wv", "dummy", "Wq"), ctx.sinks or [None] * 8))
         dkq = (dkq.float() * s).contiguous()
         dvp = dvp.float().contiguous()
@@ -336,22 +352,27 @@ class _FusedHeadTrain(torch.autograd.Function):
         gt = gt_classes.detach().to(torch.int64).contiguous()
         props, gtb = f32(proposals), f32(gt_boxes)
 
+        g2 = ops_mod.gemm2
+        f32e = lambda n: torch.empty((R, n), dtype=torch.float32, device=dev)
         xcat = torch.empty((R, 2 * d), dtype=torch.bfloat16, device=dev)          # [o1 | o2 | x]
         xb = cast_bf16_into(x, xcat[:, d:])
-        S = gemm_bf16(xb, W["kq"])                                                 # scaled scores (R, L)
+        S = f32e(W["kq"].shape[0])
+        g2(xb, W["kq"], out_f32=S, want_out=False)                                 # scaled scores (R, L)
         p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         attn = text_attention(None, x, None, vpf, p1, p2, scores=S)
-        gemm_bf16(p1, W["W1"], b1, relu=True, out=xcat[:, :h])
-        gemm_bf16(p2, W["W2"], b2, relu=True, out=xcat[:, h:d])
-        yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-        y = gemm_bf16(xcat, W["W3"], b3, out2=yb)
-        hdn = gemm_bf16(yb, W["Wf1"], bf1, relu=True, out_dtype=torch.bfloat16)
-        y2 = gemm_bf16(hdn, W["Wf2"], bf2)
+        g2(p1, W["W1"], bias=b1, relu=True, out=xcat[:, :h])
+        g2(p2, W["W2"], bias=b2, relu=True, out=xcat[:, h:d])
+        y = f32e(d)
+        yb = g2(xcat, W["W3"], bias=b3, out_f32=y)
+        hdn = g2(yb, W["Wf1"], bias=bf1, relu=True)
+        y2 = f32e(d)
+        g2(hdn, W["Wf2"], bias=bf2, out_f32=y2, want_out=False)
         z, _ = residual_layernorm(y, y2, gam, bet, 1e-5, relu=True, want_f32=True, want_bf16=False)
         zd = dropout_bf16(z, drop_p, seed, salt)
-        logits = gemm_bf16(zd, W["Wc"], bc)
-        deltas = gemm_bf16(xb, W["Wb"], bb)
+        logits, deltas = f32e(W["Wc"].shape[0]), f32e(W["Wb"].shape[0])
+        g2(zd, W["Wc"], bias=bc, out_f32=logits, want_out=False)
+        g2(xb, W["Wb"], bias=bb, out_f32=deltas, want_out=False)
         losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
         # distillation (BASELINE configs[3]): a fourth loss, KL against the frozen teacher's logits (my_module.py:409-437)
         tl = None
@@ -363,17 +384,10 @@ class _FusedHeadTrain(torch.autograd.Function):
                       float(kd[1]), kl.data_ptr(), _stream())
             losses = torch.cat([losses, kl])
         ctx.kd = (tl, kd)
-        # K-contiguous transposes of the weights, the B operands of the backward's dX = dY W products: they depend on
-        # nothing but the weights, so they run now on the side stream, under the forward chain / losses, instead of on the
-        # backward's critical path
-        main, side = torch.cuda.current_stream(), _side_stream(dev)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            WT = [transpose_bf16(W[k]) for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")]
-            ctx.wt_ready = torch.cuda.Event()
-            ctx.wt_ready.record(side)
+        # no transposed copies anywhere: the backward's dX = dY W reads W as an N-major B operand, dW = dY^T X reads dY and
+        # X as M- / N-major operands (tcgen05 smem descriptors, csrc/gemm2_tcgen05.cu)
         ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")], *WT)
+                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
         ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
         ctx.salt = salt
         # Deferred weight gradients (FlatSGD(direct_grads=True)): every parameter carries a view of the optimizer's flat
@@ -383,14 +397,15 @@ class _FusedHeadTrain(torch.autograd.Function):
         sinks = [getattr(p, "_b200_grad_sink", None) for p in params]
         ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
                                  s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
+        ctx.sink_owners = params if ctx.sinks is not None else None
         ctx.mark_non_differentiable(logits)
         return losses, logits
 
     @staticmethod
     def backward(ctx, g_losses, _g_logits):
         (x, xcat, p1, p2, attn, vp, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq, W1T, W2T, W3T, Wf1T, Wf2T, WcT, WbT, kqT) = ctx.saved_tensors
-        torch.cuda.current_stream().wait_event(ctx.wt_ready)
+         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors
+        g2 = ops_mod.gemm2
         K, box_w, l1_beta, drop_p, seed, want_attn = ctx.meta
         R, d = x.shape
         h = d // 2
@@ -422,6 +437,7 @@ class _FusedHeadTrain(torch.autograd.Function):
         side = _side_stream(dev)
         sinks = ctx.sinks
         deferred = sinks is not None
+        _claim_sinks(ctx.sink_owners)
         sk = dict(zip(("W1", "b1", "W2", "b2", "W3", "b3", "Wf1", "bf1", "Wf2", "bf2", "gamma", "beta", "Wc", "bc", "Wb", "bb"),
                       sinks if deferred else [None] * 16))
         out = {}
@@ -436,21 +452,22 @@ class _FusedHeadTrain(torch.autograd.Function):
             with torch.cuda.stream(stream):
                 fn()
 
-        def side_acts():     # transposes of saved forward activations: no dependence on any gradient
-            out["xcatT"] = transpose_bf16(xcat)             # (2d, Rp): rows [d, 2d) are x^T
-            out["zdT"], out["hdnT"], out["ybT"] = transpose_bf16(zd), transpose_bf16(hdn), transpose_bf16(yb)
-            out["p1T"], out["p2T"] = transpose_bf16(p1), transpose_bf16(p2)
-        fork(side_acts, xcat, zd, hdn, yb, p1, p2)
+        def dW(dy, xin, sink):           # dW = dY^T X, fp32, both operands read in place ([K = R][M] / [K = R][N])
+            out_ = sink if sink is not None else torch.empty((dy.shape[1], xin.shape[1]), dtype=torch.float32, device=dev)
+            g2(dy, xin, a_mn=True, b_mn=True, out_f32=out_, want_out=False)
+            return out_
 
+        xb = xcat[:, d:]
         # ---- C1: logits = zd Wc^T + bc ; deltas = xb Wb^T + bb -------------------------------------------------
         def side_c1():
-            out["dWc"] = gemm_ex(transpose_bf16(dlogits)[:C1], out["zdT"], out=sk["Wc"])
+            out["dWc"] = dW(dlogits[:, :C1], zd, sk["Wc"])
             out["dbc"] = colsum(dlogits[:, :C1], out=sk["bc"])
-            out["dWb"] = gemm_ex(transpose_bf16(ddeltas)[:C4], out["xcatT"][d:], out=sk["Wb"])
+            out["dWb"] = dW(ddeltas[:, :C4], xb, sk["Wb"])
             out["dbb"] = colsum(ddeltas[:, :C4], out=sk["bb"])
-        fork(side_c1, dlogits, ddeltas)
-        dzd = gemm_ex(dlogits, WcT, out_dtype=torch.bfloat16)
-        dx = gemm_ex(ddeltas, WbT)                                        # first producer of dL/dx (fp32)
+        fork(side_c1, dlogits, ddeltas, zd, xcat)
+        dzd = g2(dlogits[:, :C1], Wc, b_mn=True)                          # (R, d) bf16
+        dx = torch.empty((R, d), dtype=torch.float32, device=dev)
+        g2(ddeltas[:, :C4], Wb, b_mn=True, out_f32=dx, want_out=False)    # first producer of dL/dx (fp32)
         # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
         du = torch.empty((R, d), dtype=torch.float32, device=dev)
         dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
@@ -469,34 +486,32 @@ class _FusedHeadTrain(torch.autograd.Function):
         fork(side_ln, dzd, y, y2, gam, bet, ws)
         # ---- FFN: y2 = relu(yb Wf1^T + bf1) Wf2^T + bf2 -------------------------------------------------------
         def side_ffn2():
-            out["dWf2"] = gemm_ex(transpose_bf16(dub), out["hdnT"], out=sk["Wf2"])
+            out["dWf2"] = dW(dub, hdn, sk["Wf2"])
             out["dbf2"] = colsum(dub, out=sk["bf2"])   # the bf16 copy: `du` is overwritten in place by the dy GEMM below
-        fork(side_ffn2, dub)
-        dhdn = gemm_ex(dub, Wf2T, out_dtype=torch.bfloat16, mask=hdn)       # (R, h), ReLU backward fused
+        fork(side_ffn2, dub, hdn)
+        dhdn = g2(dub, Wf2, b_mn=True, mask_act=hdn)                       # (R, h), ReLU backward fused
 
         def side_ffn1():
-            out["dWf1"] = gemm_ex(transpose_bf16(dhdn), out["ybT"], out=sk["Wf1"])
+            out["dWf1"] = dW(dhdn, yb, sk["Wf1"])
             out["dbf1"] = colsum(dhdn, out=sk["bf1"])
-        fork(side_ffn1, dhdn)
-        dyb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-        gemm_ex(dhdn, Wf1T, out=du, out2=dyb, accumulate=True)   # dy = du + dhdn Wf1 (in place)
+        fork(side_ffn1, dhdn, yb)
+        dyb = g2(dhdn, Wf1, b_mn=True, out_f32=du, accumulate=True)        # dy = du + dhdn Wf1 (in place), bf16 copy
         # ---- linear3: y = [o1 | o2 | xb] W3^T + b3 -----------------------------------------------------------
         def side_l3():
-            out["dW3"] = gemm_ex(transpose_bf16(dyb), out["xcatT"], out=sk["W3"])
+            out["dW3"] = dW(dyb, xcat, sk["W3"])
             out["db3"] = colsum(du, out=sk["b3"])      # du now holds dy (fp32)
-        fork(side_l3, dyb, du)
-        do12 = gemm_ex(dyb, W3T[:d], out_dtype=torch.bfloat16, mask=xcat[:, :d])   # [do1 | do2], ReLU backward fused
-        gemm_ex(dyb, W3T[d:], out=dx, accumulate=True)
+        fork(side_l3, dyb, du, xcat)
+        do12 = g2(dyb, W3[:, :d], b_mn=True, mask_act=xcat[:, :d])          # [do1 | do2], ReLU backward fused
+        g2(dyb, W3[:, d:], b_mn=True, out_f32=dx, accumulate=True, want_out=False)
         # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
         def side_l12():
-            do12T = transpose_bf16(do12)
-            out["dW1"] = gemm_ex(do12T[:h], out["p1T"], out=sk["W1"])
-            out["dW2"] = gemm_ex(do12T[h:], out["p2T"], out=sk["W2"])
+            out["dW1"] = dW(do12[:, :h], p1, sk["W1"])
+            out["dW2"] = dW(do12[:, h:], p2, sk["W2"])
             out["db1"] = colsum(do12[:, :h], out=sk["b1"])
             out["db2"] = colsum(do12[:, h:], out=sk["b2"])
-        fork(side_l12, do12)
-        dp1 = gemm_ex(do12[:, :h], W1T, out_dtype=torch.bfloat16)
-        dp2 = gemm_ex(do12[:, h:], W2T, out_dtype=torch.bfloat16)
+        fork(side_l12, do12, p1, p2)
+        dp1 = g2(do12[:, :h], W1, b_mn=True)
+        dp2 = g2(do12[:, h:], W2, b_mn=True)
         # ---- A3 core: P1 = O * x, P2 = x - O, O = softmax(S) Vp ------------------------------------------------
         dO = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
         dS = torch.empty((R, Lp), dtype=torch.bfloat16, device=dev)
@@ -506,11 +521,13 @@ class _FusedHeadTrain(torch.autograd.Function):
         text = _TEXT_STREAMS.get((dev.type, dev.index), side)
 
         def side_att():
-            out["dvp"] = gemm_ex(transpose_bf16(attn), transpose_bf16(dO))         # (L, d)
-            out["dkq"] = gemm_ex(transpose_bf16(dS), transpose_bf16(xcat[:, d:]))[:L]
+            attn_b = torch.empty((R, Lp), dtype=torch.bfloat16, device=dev)[:, :L]
+            attn_b.copy_(attn)                                                # (R, L) probabilities as a bf16 operand
+            out["dvp"] = dW(attn_b, dO, None)                                 # (L, d)
+            out["dkq"] = dW(dS[:, :L], xb, None)
         fork(side_att, attn, dO, dS, xcat, stream=text)
         # ---- scores: S = xb Kq^T ----------------------------------------------------------------------------------
-        gemm_ex(dS, kqT, out=dx, accumulate=True)
+        g2(dS[:, :L], kq, b_mn=True, out_f32=dx, accumulate=True, want_out=False)
         done = torch.cuda.Event()
         done.record(side)
         tdone = torch.cuda.Event()
@@ -583,10 +600,32 @@ class FlatSGD:
             p.grad = self.grad[off:off + k].view_as(p.data)
             if direct_grads:
                 p._b200_grad_sink = p.grad
+                p._b200_opt = self
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
         self._zeroed = None
+        self.epoch = 0             # bumped by zero_grad; `_claim_sinks` refuses two fused writes to one sink per epoch
+        self._ranges = None        # [(begin, end)] of the flat buffer that receive gradients (decided at the first step)
+
+    def _active_ranges(self):
+        """torch.optim.SGD skips parameters whose `.grad` is None (no weight decay, no momentum) — the reference's solver
+        (defrcn/solver/build.py) relies on that for parameters the live head never uses (attention.query_projection,
+        attention.output_projection, ...).  With one flat gradient buffer "None" is "never written": parameters whose gradient
+        slice is still all-zero after the first backward are left out of every update."""
+        used = torch.stack([self.grad[o:o + p.numel()].abs().max() > 0 for p, o in zip(self.params, self.offsets)]).tolist()
+        ranges = []
+        for p, o, u in zip(self.params, self.offsets, used):
+            if not u:
+                continue
+            e = (o + p.numel() + 63) // 64 * 64
+            if ranges and ranges[-1][1] == o:
+                ranges[-1][1] = e
+            else:
+                ranges.append([o, e])
+        self.unused = [i for i, u in enumerate(used) if not u]
+        return [tuple(r) for r in ranges]
 
     def zero_grad(self):
+        self.epoch += 1
         self.grad.zero_()
         self._zeroed = torch.cuda.Event()
         self._zeroed.record()
@@ -633,8 +672,11 @@ class FlatSGD:
 
     def step(self):
         self.sync_grads()
-        _lib.call("b200_sgd_momentum", self.flat.data_ptr(), self.grad.data_ptr(), self.mom.data_ptr(), self.flat.numel(),
-                  float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
+        if self._ranges is None:
+            self._ranges = self._active_ranges()             # one host read, at the first step only
+        for b, e in self._ranges:
+            _lib.call("b200_sgd_momentum", self.flat[b:e].data_ptr(), self.grad[b:e].data_ptr(), self.mom[b:e].data_ptr(), e - b,
+                      float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
         ops_mod.PARAM_GENERATION[0] += 1     # the bf16 weight caches key on this (in-place kernel updates bypass _version)
 
 

@@ -353,12 +353,14 @@ B200_API int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src, 
  *   (counter-based hash of (seed, image, proposal): the reference's distribution, not torch's RNG stream),
  *   foreground rows first.  Outputs have batch_per_image rows per image: sampled_idx (index within the image, -1 =
  *   padding), the sampled boxes, their class (num_classes = background, -1 = padding), the matched ground-truth box;
- *   counts (num_images, 2) = (#foreground rows, #valid rows).
+ *   counts (num_images, 2) = (#foreground rows, #valid rows).  seed_salt (optional device scalar) is added to seed
+ *   on the device: a step counter that survives CUDA-graph replay.  An image whose offsets exceed the limits gets no
+ *   rows (counts 0) instead of being processed.
  * ------------------------------------------------------------------------------------------------- */
 B200_API int b200_label_sample_proposals(const float* proposals, const int32_t* prop_offsets, const float* gt_boxes,
                                 const int64_t* gt_classes, const int32_t* gt_offsets, int num_images,
                                 int max_props_per_image, int max_gt_per_image, int num_classes, float iou_thresh,
-                                int batch_per_image, int max_positive, unsigned long long seed, int32_t* matched_idx,
+                                int batch_per_image, int max_positive, unsigned long long seed, const int64_t* seed_salt, int32_t* matched_idx,
                                 int32_t* matched_label, int32_t* sampled_idx, float* out_proposals, int64_t* out_classes,
                                 float* out_gt_boxes, int32_t* counts, b200_stream_t stream);
 
@@ -373,7 +375,8 @@ B200_API int b200_label_sample_proposals(const float* proposals, const int32_t* 
  *   clip to image_hw (N,2) = (h, w), drop boxes whose width or height is not > min_box_size,
  *   batched_nms by level (coordinate-offset trick below 40000 candidates) at nms_thresh, keep the first
  *   post_nms_topk.  out_boxes (N, post_nms_topk, 4), out_logits (N, post_nms_topk) zero padded, out_count (N).
- *   cap_per_image = sum_l min(pre_nms_topk, A_l) (the caller knows the level sizes); pre_nms_topk <= 16384.
+ *   cap_per_image = sum_l min(pre_nms_topk, A_l) (the caller knows the level sizes); pre_nms_topk <= 16384.  A smaller
+ *   cap_per_image never overruns the workspace: candidates beyond it are dropped and n_invalid[image] = -(number dropped).
  *   Keep indices / counts are bit-exact with the reference's CPU path.  No host synchronisation.
  * ------------------------------------------------------------------------------------------------- */
 B200_API size_t b200_rpn_select_workspace_bytes(int N, int cap_per_image, int L, int post_nms_topk);

@@ -475,6 +475,25 @@ def sample_counts(n_fg, n_bg, batch=512, positive_fraction=0.25):
     return num_pos, min(n_bg, batch - num_pos)
 
 
+def label_and_sample(props, gt_boxes, gt_classes, K, batch=512, positive_fraction=0.25, iou_thresh=0.5, append_gt=True,
+                     gen=None):
+    """`ROIHeads.label_and_sample_proposals` for one image (roi_heads.py:157-250): ground truth appended to the proposals
+    (PROPOSAL_APPEND_GT), argmax-IoU labelling, random subsample of <= batch * positive_fraction foreground and the
+    rest background rows (torch.randperm, like detectron2's subsample_labels).  Returns (boxes, classes, matched gt boxes)."""
+    p = torch.as_tensor(props).float()
+    g = torch.as_tensor(gt_boxes).float().reshape(-1, 4)
+    if append_gt:
+        p = torch.cat([p, g], 0)
+    idx, lab, _ = label_proposals(p, g, iou_thresh)
+    cls = torch.as_tensor(gt_classes).to(torch.int64)[idx].clone() if g.shape[0] else torch.full((p.shape[0],), K, dtype=torch.int64)
+    cls[lab == 0] = K
+    pos, neg = torch.nonzero(cls != K).squeeze(1), torch.nonzero(cls == K).squeeze(1)
+    n_pos, n_neg = sample_counts(pos.numel(), neg.numel(), batch, positive_fraction)
+    sel = torch.cat([pos[torch.randperm(pos.numel(), generator=gen)[:n_pos]], neg[torch.randperm(neg.numel(), generator=gen)[:n_neg]]])
+    gtb = g[idx[sel]] if g.shape[0] else torch.zeros((sel.numel(), 4))
+    return p[sel], cls[sel], gtb
+
+
 # ------------------------------------------------------------------ SURVEY 8f-3: RPN proposal selection
 def find_top_rpn_proposals(proposals, pred_objectness_logits, image_sizes, nms_thresh, pre_nms_topk, post_nms_topk,
                            min_box_size=0.0):

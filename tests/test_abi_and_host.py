@@ -224,14 +224,16 @@ def test_bench_cli_contract(monkeypatch):
     spec.loader.exec_module(b)
     a = b.parse()
     assert (a.gpus, a.impl, a.mode) == (1, "b200", "train") and a.warmup >= 3 and a.steps > 0
-    cfg = b.workload_config(a, a.images_per_gpu)
+    cfg = b.workload_config(a, a.mode, a.classes, a.distill, a.images_per_gpu)
     assert "configs[1]" in cfg["workload"] and cfg["proposals_per_image"] == 512 and "model" not in cfg
+    assert "forward(" in cfg["workload"] and cfg["api"] == "forward()" and cfg["rpn_proposals_per_image"] == 2000
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "8", "--steps", "7", "--warmup", "4", "--impl", "reference"])
     a = b.parse()
     assert (a.gpus, a.steps, a.warmup, a.impl) == (8, 7, 4, "reference")
     monkeypatch.setattr(sys, "argv", ["bench.py", "--distill"])
-    assert "configs[3]" in b.workload_config(b.parse(), 8)["workload"]
+    a = b.parse()
+    assert "configs[3]" in b.workload_config(a, a.mode, a.classes, a.distill, 8)["workload"]
     monkeypatch.setattr(sys, "argv", ["bench.py", "--mode", "infer", "--classes", "80"])
     a = b.parse()
-    assert "inference step" in b.workload_config(a, 8)["workload"] and a.classes == 80
+    assert "inference step" in b.workload_config(a, a.mode, a.classes, a.distill, 8)["workload"] and a.classes == 80
     assert b.METRIC == "roi_head_images_per_sec" and b.UNIT == "images/s"

@@ -179,7 +179,7 @@ def test_gemm2_rejects_bad_arguments():
     ops = _ops()
     a = torch.zeros(64, 64, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(_lib.B200Error):
-        ops.gemm2(a[:, :60], a[:, :60])                               # K % 8 != 0
+        ops.gemm2(a[:, :60].contiguous(), a[:, :60].contiguous())     # row pitch not a multiple of 8 elements
     with pytest.raises(_lib.B200Error):
         ops.gemm2(a, a, want_out=False)                               # no output
     with pytest.raises(_lib.B200Error):

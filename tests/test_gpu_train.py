@@ -193,6 +193,31 @@ def test_flat_sgd_matches_torch_sgd():
         torch.testing.assert_close(p.data, q.data, rtol=1e-6, atol=1e-6)
 
 
+def test_flat_sgd_leaves_parameters_without_gradient_alone():
+    """torch.optim.SGD (the reference's solver, defrcn/solver/build.py) skips parameters whose grad is None: no weight
+    decay, no momentum.  The live head never uses e.g. attention.query_projection; with one flat gradient buffer those are
+    the parameters whose slice was never written — they must not decay either."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(40, 9, device="cuda")), torch.nn.Parameter(torch.randn(77, device="cuda")),
+          torch.nn.Parameter(torch.randn(65, 3, device="cuda"))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.SGD(qs, lr=0.05, momentum=0.9, weight_decay=1e-2)
+    opt = train_ops.FlatSGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-2)
+    for step in range(3):
+        opt.zero_grad()
+        for i in (0, 2):                    # parameter 1 never receives a gradient
+            gr = torch.randn_like(qs[i])
+            qs[i].grad = gr.clone()
+            ps[i].grad.add_(gr)
+        ref.step()
+        opt.step()
+    assert opt.unused == [1]
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.data, q.data, rtol=1e-6, atol=1e-6)
+    assert torch.equal(ps[1].data, qs[1].data)
+
+
 @pytest.mark.parametrize("rows,cols,dt", [(100, 24, torch.float32), (4096, 2048, torch.bfloat16), (70, 130, torch.bfloat16)])
 def test_transpose_and_colsum(rows, cols, dt):
     from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops

@@ -1,8 +1,8 @@
 #!/bin/bash
 # all gpu tests + smoke
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short --durations=5 > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --tb=short --durations=8 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke.log
-tail -n 25 gpurun_out/pytest_gpu.log; tail -n 3 gpurun_out/smoke.log
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | cut -c1-250 | tail -n 30; tail -n 4 gpurun_out/smoke.log
