@@ -261,6 +261,7 @@ class Workload:
         if self.train:
             self.host["gt_cls"] = torch.stack(cls_h).pin_memory()
             self.host["gt_boxes"] = torch.stack(gtb_h).pin_memory()
+        self.host["objectness"] = torch.zeros(self.B, n_in).pin_memory()          # RPN objectness logits travel with the boxes
         self.names = list(self.host)
         self.resident = {k: v.to(dev) for k, v in self.host.items()}
         self.sizes = [(H_IMG, W_IMG)] * self.B
@@ -280,7 +281,7 @@ class Workload:
         for i in range(self.B):
             inst = Instances(self.sizes[i])
             inst.proposal_boxes = Boxes(d["boxes"][i])
-            inst.objectness_logits = torch.zeros(d["boxes"].shape[1], device=d["boxes"].device)
+            inst.objectness_logits = d["objectness"][i]
             props.append(inst)
             if self.train:
                 t = Instances(self.sizes[i])

@@ -61,7 +61,7 @@ SIGNATURES = {
     "b200_layernorm_relu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_float, c_float, ctypes.c_ulonglong] + [c_void_p] * 5 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_layernorm_param_grads": (c_int, [c_void_p] * 5 + [c_float, ctypes.c_ulonglong] + [c_void_p] * 3 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_text_attention_bwd": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
-    "b200_head_losses": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float] * 5 + [c_void_p, c_void_p]),
+    "b200_head_losses": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float] * 5 + [c_void_p, c_void_p, c_void_p]),
     "b200_head_losses_bwd": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_float] * 5 + [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "b200_kd_loss": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_float] * 2 + [c_void_p, c_void_p]),
     "b200_kd_loss_bwd": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float] * 2 + [c_void_p, c_int, c_void_p]),
@@ -75,11 +75,11 @@ SIGNATURES = {
     "b200_pack_relu_bits": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_mean_bwd_relu_bits": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_add_relu_bits": (c_int, [c_void_p] * 4 + [c_size_t, c_void_p]),
-    "b200_sgd_momentum": (c_int, [c_void_p] * 3 + [c_size_t] + [c_float] * 3 + [c_void_p]),
+    "b200_sgd_momentum": (c_int, [c_void_p] * 3 + [c_size_t] + [c_float] * 3 + [c_void_p, c_void_p]),
     "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "b200_residual_layernorm": (c_int, [c_void_p] * 4 + [c_float, c_int] + [c_void_p] * 2 + [c_int] * 2 + [c_void_p]),
     "b200_cast_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "b200_label_sample_proposals": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.c_ulonglong] + [c_void_p] * 8 + [c_void_p]),
+    "b200_label_sample_proposals": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_void_p]),
     "b200_rpn_select_workspace_bytes": (c_size_t, [c_int] * 4),
     "b200_rpn_select_proposals": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float] * 2 + [c_void_p] * 4 + [c_void_p, c_size_t, c_void_p]),
     "b200_detector_postprocess": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p]),

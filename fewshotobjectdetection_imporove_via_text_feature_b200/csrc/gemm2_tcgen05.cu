@@ -577,10 +577,10 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int bn = d->tile_n;
   if (bn == 0) {
-    // 256-wide tiles unless that leaves SM pairs idle for most of the launch
+    // A 128-wide tile moves 3/4 of a 256-wide tile's operand bytes for half of its flops (the mainloop is L2-bound), so
+    // 256 wins unless the 128-wide tiling still fits one wave of CTA pairs (or N itself is narrow)
     const int mt = ceil_div(d->M, 256);
-    bn = (d->N > 128 && mt * ceil_div(d->N, 256) >= kNumSMs / 2) ? 256 : 128;
-    if (d->N <= 128) bn = 128;
+    bn = (d->N <= 128 || mt * ceil_div(d->N, 128) <= kNumSMs / 2) ? 128 : 256;
   }
   B200_CHECK_ARG(bn == 128 || bn == 256, "gemm2: tile_n must be 0, 128 or 256");
   // smallest instantiation whose compiled-in epilogue features cover the descriptor

@@ -43,16 +43,19 @@ __global__ void __launch_bounds__(kLsThreads)
 label_sample_kernel(const float4* __restrict__ props, const int32_t* __restrict__ prop_offsets, const float4* __restrict__ gt,
                     const int64_t* __restrict__ gt_classes, const int32_t* __restrict__ gt_offsets, int num_classes,
                     float iou_thresh, int batch, int max_pos, unsigned long long seed,
-                    const long long* __restrict__ seed_salt, int32_t* __restrict__ matched_idx,
+                    const long long* __restrict__ seed_salt, int append_gt, int pad_background,
+                    int32_t* __restrict__ matched_idx,
                     int32_t* __restrict__ matched_label, int32_t* __restrict__ sampled_idx, float4* __restrict__ out_props,
                     int64_t* __restrict__ out_classes, float4* __restrict__ out_gt, int32_t* __restrict__ counts) {
   __shared__ unsigned long long s_key[kLsMaxProps];
   __shared__ float4 s_gt[kLsMaxGt];
   __shared__ int s_nfg;
   const int n = blockIdx.x;
-  const int p0 = prop_offsets[n], P = prop_offsets[n + 1] - p0;
+  const int p0 = prop_offsets[n], Pn = prop_offsets[n + 1] - p0;
   const int g0 = gt_offsets[n], M = gt_offsets[n + 1] - g0;
-  if (P > kLsMaxProps || M > kLsMaxGt || P < 0 || M < 0) {
+  const int P = Pn + (append_gt ? M : 0);                   // candidates: the proposals, then (optionally) the gt boxes
+  const int m0 = p0 + (append_gt ? g0 : 0);                 // first entry of this image in matched_idx / matched_label
+  if (P > kLsMaxProps || M > kLsMaxGt || Pn < 0 || M < 0) {
     // the offsets on the device exceed what the host was told (max_props_per_image / max_gt_per_image): the shared
     // arrays are sized for the limits, so refuse the image (no rows) instead of overrunning them
     if (threadIdx.x == 0) { counts[2 * n] = 0; counts[2 * n + 1] = 0; }
@@ -71,10 +74,10 @@ label_sample_kernel(const float4* __restrict__ props, const int32_t* __restrict_
     if (i < P) {
       float best;
       int arg;
-      best_match(props[p0 + i], s_gt, M, best, arg);
+      best_match(i < Pn ? props[p0 + i] : s_gt[i - Pn], s_gt, M, best, arg);
       const bool fg = M > 0 && best >= iou_thresh;
-      if (matched_idx) matched_idx[p0 + i] = arg;
-      if (matched_label) matched_label[p0 + i] = fg ? 1 : 0;
+      if (matched_idx) matched_idx[m0 + i] = arg;
+      if (matched_label) matched_label[m0 + i] = fg ? 1 : 0;
       local_fg += fg;
       // [63] background flag, [62:31] random key, [30:0] proposal index: foreground first, random order within each class
       key = ((unsigned long long)(fg ? 0 : 1) << 63) | ((unsigned long long)ls_hash(seed, n, i) << 31) | (unsigned long long)i;
@@ -107,12 +110,12 @@ label_sample_kernel(const float4* __restrict__ props, const int32_t* __restrict_
       sampled_idx[o] = -1;
       out_props[o] = make_float4(0.f, 0.f, 0.f, 0.f);
       out_gt[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-      out_classes[o] = -1;
+      out_classes[o] = pad_background ? (int64_t)num_classes : -1;
       continue;
     }
     const unsigned long long key = s_key[j < num_pos ? j : nfg + (j - num_pos)];
     const int i = (int)(key & 0x7fffffffull);
-    const float4 p = props[p0 + i];
+    const float4 p = i < Pn ? props[p0 + i] : s_gt[i - Pn];
     float best;
     int arg;
     best_match(p, s_gt, M, best, arg);
@@ -132,14 +135,14 @@ extern "C" int b200_label_sample_proposals(const float* proposals, const int32_t
                                            const int64_t* gt_classes, const int32_t* gt_offsets, int num_images,
                                            int max_props_per_image, int max_gt_per_image, int num_classes, float iou_thresh,
                                            int batch_per_image, int max_positive, unsigned long long seed,
-                                           const int64_t* seed_salt, int32_t* matched_idx, int32_t* matched_label, int32_t* sampled_idx,
+                                           const int64_t* seed_salt, int append_gt, int pad_background, int32_t* matched_idx, int32_t* matched_label, int32_t* sampled_idx,
                                            float* out_proposals, int64_t* out_classes, float* out_gt_boxes, int32_t* counts,
                                            b200_stream_t stream) {
   B200_CHECK_ARG(prop_offsets && gt_offsets && sampled_idx && out_proposals && out_classes && out_gt_boxes && counts,
                  "label_sample_proposals: null tensor");
   B200_CHECK_ARG(num_images >= 0 && batch_per_image > 0 && max_positive >= 0 && max_positive <= batch_per_image,
                  "label_sample_proposals: bad sizes");
-  if (max_props_per_image > kLsMaxProps || max_gt_per_image > kLsMaxGt) {
+  if (max_props_per_image + (append_gt ? max_gt_per_image : 0) > kLsMaxProps || max_gt_per_image > kLsMaxGt) {
     set_error("label_sample_proposals: at most %d proposals and %d ground-truth boxes per image", kLsMaxProps, kLsMaxGt);
     return B200_ERR_UNSUPPORTED;
   }
@@ -148,7 +151,7 @@ extern "C" int b200_label_sample_proposals(const float* proposals, const int32_t
   if (num_images == 0) return B200_OK;
   label_sample_kernel<<<num_images, kLsThreads, 0, (cudaStream_t)stream>>>(
       (const float4*)proposals, prop_offsets, (const float4*)gt_boxes, gt_classes, gt_offsets, num_classes, iou_thresh,
-      batch_per_image, max_positive, seed, (const long long*)seed_salt, matched_idx, matched_label, sampled_idx, (float4*)out_proposals, out_classes,
+      batch_per_image, max_positive, seed, (const long long*)seed_salt, append_gt, pad_background, matched_idx, matched_label, sampled_idx, (float4*)out_proposals, out_classes,
       (float4*)out_gt_boxes, counts);
   B200_CUDA_LAUNCH_CHECK("label_sample_proposals");
   return B200_OK;

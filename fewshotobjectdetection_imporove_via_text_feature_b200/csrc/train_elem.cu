@@ -443,13 +443,27 @@ __global__ void __launch_bounds__(1024)
 head_losses_kernel(const float* __restrict__ logits, const float* __restrict__ deltas, const float* __restrict__ attn,
                    const int64_t* __restrict__ gt, const float* __restrict__ props, const float* __restrict__ gt_boxes,
                    int R, int K, int L, int agnostic, float wx, float wy, float ww, float wh, float beta,
-                   float* __restrict__ out) {
+                   float* __restrict__ out, float* __restrict__ acc_stats) {
   __shared__ float s_red[3][1024];
+  __shared__ int s_acc[4];
   float lc = 0.f, lb = 0.f, la = 0.f;
+  int n_hit = 0, n_fg = 0, n_fg_hit = 0, n_fg_bg = 0;
   const int C1 = K + 1, C4 = agnostic ? 4 : 4 * K;
+  if (threadIdx.x < 4) s_acc[threadIdx.x] = 0;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     const int g = (int)gt[r];
     lc += row_lse(logits + (size_t)r * C1, C1) - logits[(size_t)r * C1 + g];
+    if (acc_stats) {        // FastRCNNOutputs._log_accuracy (fast_rcnn.py:191-220): argmax = first maximum, like torch
+      const float* v = logits + (size_t)r * C1;
+      int am = 0;
+      float best = v[0];
+      for (int c = 1; c < C1; ++c) if (v[c] > best) { best = v[c]; am = c; }
+      const bool fg = g >= 0 && g < K;
+      n_hit += am == g;
+      n_fg += fg;
+      n_fg_hit += fg && am == g;
+      n_fg_bg += fg && am == K;
+    }
     if (attn) la += row_lse(attn + (size_t)r * L, L) - attn[(size_t)r * L + g];
     if (g >= 0 && g < K) {
       float t[4];
@@ -471,8 +485,20 @@ head_losses_kernel(const float* __restrict__ logits, const float* __restrict__ d
     }
     __syncthreads();
   }
+  if (acc_stats) {          // integer counts: the order of the atomic adds does not matter
+    __syncthreads();
+    if (n_hit) atomicAdd(&s_acc[0], n_hit);
+    if (n_fg) atomicAdd(&s_acc[1], n_fg);
+    if (n_fg_hit) atomicAdd(&s_acc[2], n_fg_hit);
+    if (n_fg_bg) atomicAdd(&s_acc[3], n_fg_bg);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     out[0] = s_red[0][0] / (float)R; out[1] = s_red[1][0] / (float)R; out[2] = s_red[2][0] / (float)R;
+    if (acc_stats) {
+      acc_stats[0] = (float)s_acc[0]; acc_stats[1] = (float)s_acc[1]; acc_stats[2] = (float)s_acc[2];
+      acc_stats[3] = (float)s_acc[3]; acc_stats[4] = (float)R;
+    }
   }
 }
 
@@ -581,13 +607,17 @@ kd_loss_bwd_kernel(const float* __restrict__ student, const float* __restrict__ 
 }
 
 // SGD with momentum over one flat fp32 buffer (torch.optim.SGD: g += wd * p; m = mu * m + g; p -= lr * m)
+// `shadow` (optional): the bf16 copy of the updated parameters the tensor-core GEMMs read as operands, written in the
+// same pass instead of by one cast kernel per weight matrix at the top of the next step.
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
-                                    float lr, float mu, float wd) {
+                                    float lr, float mu, float wd, __nv_bfloat16* __restrict__ shadow) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] + wd * p[i];
     const float mi = mu * m[i] + gi;
     m[i] = mi;
-    p[i] -= lr * mi;
+    const float pi = p[i] - lr * mi;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
   }
 }
 
@@ -717,12 +747,12 @@ extern "C" int b200_text_attention_bwd(const void* dp1, const void* dp2, int ldp
 
 extern "C" int b200_head_losses(const float* logits, const float* deltas, const float* attn, const int64_t* gt_classes,
                                 const float* proposals, const float* gt_boxes, int R, int K, int L, int cls_agnostic,
-                                float wx, float wy, float ww, float wh, float smooth_l1_beta, float* out3,
+                                float wx, float wy, float ww, float wh, float smooth_l1_beta, float* out3, float* acc_stats5,
                                 b200_stream_t stream) {
   B200_CHECK_ARG(logits && deltas && gt_classes && proposals && gt_boxes && out3, "head_losses: null tensor");
   B200_CHECK_ARG(R > 0 && K > 0 && (!attn || L > K), "head_losses: bad shape");
   head_losses_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, deltas, attn, gt_classes, proposals, gt_boxes, R, K, L,
-                                                           cls_agnostic, wx, wy, ww, wh, smooth_l1_beta, out3);
+                                                           cls_agnostic, wx, wy, ww, wh, smooth_l1_beta, out3, acc_stats5);
   B200_CUDA_LAUNCH_CHECK("head_losses");
   return B200_OK;
 }
@@ -743,11 +773,12 @@ extern "C" int b200_head_losses_bwd(const float* logits, const float* deltas, co
 }
 
 extern "C" int b200_sgd_momentum(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
-                                 float weight_decay, b200_stream_t stream) {
+                                 float weight_decay, void* bf16_shadow, b200_stream_t stream) {
   if (n == 0) return B200_OK;
   B200_CHECK_ARG(params && grads && momentum_buf, "sgd_momentum: null tensor");
   const int blocks = (int)min((size_t)kNumSMs * 8, (n + 255) / 256);
-  sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay);
+  sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay,
+                                                                (__nv_bfloat16*)bf16_shadow);
   B200_CUDA_LAUNCH_CHECK("sgd_momentum");
   return B200_OK;
 }

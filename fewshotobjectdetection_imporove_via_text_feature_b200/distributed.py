@@ -66,9 +66,15 @@ def allreduce_gradients(params, bucket_bytes=64 << 20, average=True):
     """Bucketed gradient all-reduce (flat fp32 buckets; NVSwitch makes cost launch-latency-, not link-bound, so
     buckets are sized for overlap rather than link count).  Returns the number of buckets reduced."""
     rank, W = world()
-    grads = [p.grad for p in params if p.grad is not None]
-    if W == 1 or not grads:
+    # buckets are laid out over the FIXED parameter list (a rank whose batch left a parameter without a gradient still
+    # contributes zeros), so every rank issues the same collectives with the same sizes
+    params = [p for p in params if p.requires_grad]
+    if W == 1 or not params:
         return 0
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     buckets, cur, size = [], [], 0
     for g in grads:
         nb = g.numel() * g.element_size()

@@ -315,7 +315,15 @@ class BottleneckBlock(nn.Module):
                     res = F.conv2d(x, sc[0], None, ssc)
                     bias3 = b3 if sc[1] is None else b3 + sc[1]
                 return torch.cudnn_convolution_add_relu(out, w3, res, 1.0, bias3, (1, 1), (0, 0), (1, 1), 1)
-            except RuntimeError:
+            except RuntimeError as e:
+                # only "this cuDNN build has no runtime-fused conv+bias+ReLU for this configuration" selects the unfused
+                # path; out-of-memory and asynchronous CUDA faults are real errors and must surface
+                msg = str(e).lower()
+                if "out of memory" in msg or "cuda error" in msg or "illegal" in msg or "launch failure" in msg:
+                    raise
+                import warnings
+                warnings.warn("b200roi: cuDNN fused conv+bias+ReLU unavailable (%s); using the unfused library path" %
+                              str(e).splitlines()[0][:160])
                 _FUSED_CONV["ok"] = False
         out = F.relu_(F.conv2d(x, w1, b1, s1))
         out = F.relu_(F.conv2d(out, w2, b2, self.conv2.stride, self.conv2.padding, self.conv2.dilation, self.conv2.groups))

@@ -94,15 +94,17 @@ class ROIHeads(nn.Module):
         idx = torch.cat([fg, bg], dim=0)
         return idx, gt_classes[idx]
 
-    def _label_and_sample_device(self, proposals, targets):
+    def _label_and_sample_device(self, proposals, targets, append_gt=False):
         """One kernel for the whole batch (ops.label_and_sample_proposals) and one small device->host read (the per-image
         row counts, which the reference's logging needs on the host anyway) instead of a Python loop of torch ops with
         several synchronisations per image.  Labels / matches are the reference's bit for bit; the random subsample
-        has its distribution but not torch's RNG stream."""
+        has its distribution but not torch's RNG stream.  append_gt: the kernel takes the ground-truth boxes as extra
+        candidates itself (static sampling only; otherwise the caller appended them to `proposals`)."""
         r = ops.label_and_sample_proposals([p.proposal_boxes.tensor for p in proposals], [t.gt_boxes.tensor for t in targets],
                                            [t.gt_classes for t in targets], self.num_classes, self.proposal_matcher.thresholds[1],
                                            self.batch_size_per_image, self.positive_sample_fraction,
-                                           seed_salt=getattr(self, "_drop_salt", None) if self.static_sampling else None)
+                                           seed_salt=getattr(self, "_drop_salt", None) if self.static_sampling else None,
+                                           append_gt=append_gt, pad_background=self.static_sampling)
         if self.static_sampling:
             return self._static_samples(r, proposals), None, None
         counts = r["counts"].cpu().tolist()
@@ -120,21 +122,18 @@ class ROIHeads(nn.Module):
         return out, n_fg, n_bg
 
     def _static_samples(self, r, proposals):
-        """Fixed-shape form of the sampled batch: B rows per image, no host read.  Padding rows (none, unless an image has
-        fewer than B candidates — flagged) are relabelled background."""
-        B = self.batch_size_per_image
-        counts = r["counts"]
-        classes = torch.where(r["classes"] < 0, torch.full_like(r["classes"], self.num_classes), r["classes"])
+        """Fixed-shape form of the sampled batch: B rows per image, no host read and no per-image kernels — the sampled
+        Instances are views of the kernel's padded outputs (they carry proposal_boxes, gt_classes, gt_boxes; the
+        objectness logits, which nothing downstream of the sampler reads, are not gathered).  Padding rows (none, unless
+        an image has fewer than B candidates — flagged) are labelled background by the kernel."""
         out = []
         for i, p in enumerate(proposals):
-            q = p[r["sampled_idx"][i].long().clamp_(0, len(p) - 1)]
+            q = Instances(p.image_size)
             q.proposal_boxes = Boxes(r["boxes"][i])
-            q.gt_classes = classes[i]
+            q.gt_classes = r["classes"][i]
             q.gt_boxes = Boxes(r["gt_boxes"][i])
             out.append(q)
-        fg = counts[:, 0].float().mean()
-        stats = torch.stack([fg, counts[:, 1].float().mean() - fg, (counts[:, 1] != B).any().float()])
-        self._defer("sample", stats)
+        self._defer("sample", r["counts"])
         return out
 
     def _defer(self, key, dev_tensor):
@@ -151,7 +150,9 @@ class ROIHeads(nn.Module):
         st = get_event_storage()
         s = self._deferred.get("sample")
         if s is not None:
-            n_fg, n_bg, bad = s.tolist()
+            c = s.reshape(-1, 2)
+            n_fg, n_bg = float(c[:, 0].mean()), float((c[:, 1] - c[:, 0]).mean())
+            bad = bool((c[:, 1] != self.batch_size_per_image).any())
             if bad:
                 raise RuntimeError("STATIC_SAMPLING: an image had fewer than BATCH_SIZE_PER_IMAGE sampled proposals; "
                                    "run this batch with MODEL.B200.STATIC_SAMPLING = False")
@@ -167,13 +168,16 @@ class ROIHeads(nn.Module):
 
     @torch.no_grad()
     def label_and_sample_proposals(self, proposals, targets):
-        if self.proposal_append_gt:
-            proposals = add_ground_truth_to_proposals([t.gt_boxes for t in targets], proposals)
         th, lb = self.proposal_matcher.thresholds, self.proposal_matcher.labels
         extra_gt = any(name.startswith("gt_") and name not in ("gt_boxes", "gt_classes") for t in targets for name in t.get_fields())
-        if (proposals and all(p.proposal_boxes.tensor.is_cuda for p in proposals) and len(th) == 3 and list(lb) == [0, 1] and
-                not extra_gt and max(len(p) for p in proposals) <= 4096 and max(len(t) for t in targets) <= 256):
-            out, n_fg, n_bg = self._label_and_sample_device(proposals, targets)
+        on_device = (proposals and all(p.proposal_boxes.tensor.is_cuda for p in proposals) and len(th) == 3 and list(lb) == [0, 1] and
+                     not extra_gt and max(len(p) + len(t) for p, t in zip(proposals, targets)) <= 4096 and
+                     max(len(t) for t in targets) <= 256)
+        in_kernel_append = self.proposal_append_gt and on_device and self.static_sampling
+        if self.proposal_append_gt and not in_kernel_append:
+            proposals = add_ground_truth_to_proposals([t.gt_boxes for t in targets], proposals)
+        if on_device:
+            out, n_fg, n_bg = self._label_and_sample_device(proposals, targets, append_gt=in_kernel_append)
             if n_fg is None:             # static sampling: the scalars are logged by flush_deferred_logs
                 return out
             st = get_event_storage()
@@ -402,9 +406,9 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         else:              # device-resident step counter (graph capture): the host part of the seed stays constant
             salt.add_(1)
             seed = (torch.initial_seed() * 1000003) & 0x7FFFFFFFFFFFFFFF
-        losses, logits = train_ops.fused_head_train(feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb,
-                                                    self.num_classes, self.box2box_transform.weights, self.smooth_l1_beta,
-                                                    drop, seed, True, salt, teacher_logits, kd)
+        losses, logits, self._acc_stats = train_ops.fused_head_train(
+            feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb, self.num_classes, self.box2box_transform.weights,
+            self.smooth_l1_beta, drop, seed, True, salt, teacher_logits, kd)
         out = {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}
         if teacher_logits is not None:
             out["loss_kl"] = losses[3]
@@ -453,8 +457,16 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         if feature_pooled.is_cuda and self._fused_train_path():
             losses, logits = self.fused_train_losses(feature_pooled, proposals, gt_classes, teacher_logits,
                                                      self._kd_params() if teacher_logits is not None else None)
-            FastRCNNOutputs(self.box2box_transform, logits, None, proposals, self.smooth_l1_beta)._log_accuracy(
-                self._defer if self.static_sampling else None)
+            # FastRCNNOutputs._log_accuracy (fast_rcnn.py:191-220): the counts come out of the loss kernel's pass
+            if self.static_sampling:
+                self._defer("accuracy", self._acc_stats)
+            else:
+                acc, n_fg, fg_acc, fn, n = self._acc_stats.tolist()
+                st = get_event_storage()
+                st.put_scalar("fast_rcnn/cls_accuracy", acc / max(n, 1))
+                if n_fg > 0:
+                    st.put_scalar("fast_rcnn/fg_cls_accuracy", fg_acc / n_fg)
+                    st.put_scalar("fast_rcnn/false_negative", fn / n_fg)
             self._mark("text_fusion_losses")
             return [], losses
         att_output, att_loss = self.forward_att(feature_pooled, gt_classes)

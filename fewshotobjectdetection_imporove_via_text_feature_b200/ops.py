@@ -594,8 +594,34 @@ def cast_bf16_into(src, dst):
 _LS_CALLS = [0]
 
 
+def cat_adjacent(ts):
+    """torch.cat(ts, 0) — as a VIEW (no kernel) when the tensors already sit back to back in one allocation, which is how
+    per-image slices of a batched tensor arrive."""
+    if len(ts) == 1:
+        return ts[0].contiguous()
+    t0 = ts[0]
+    ok = all(t.is_contiguous() and t.dtype == t0.dtype and t.shape[1:] == t0.shape[1:] and t.device == t0.device for t in ts)
+    if ok and t0.numel():
+        try:
+            same = all(t.untyped_storage().data_ptr() == t0.untyped_storage().data_ptr() for t in ts)
+        except Exception:  # noqa: BLE001
+            same = False
+        if same:
+            ptr, adj = t0.data_ptr(), True
+            for t in ts:
+                if t.data_ptr() != ptr:
+                    adj = False
+                    break
+                ptr += t.numel() * t.element_size()
+            if adj:
+                n = sum(t.shape[0] for t in ts)
+                return torch.as_strided(t0, (n,) + tuple(t0.shape[1:]), t0.stride())
+    return torch.cat(ts, 0).contiguous()
+
+
 def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, iou_thresh=0.5, batch_per_image=512,
-                               positive_fraction=0.25, seed=None, want_labels=False, seed_salt=None):
+                               positive_fraction=0.25, seed=None, want_labels=False, seed_salt=None, append_gt=False,
+                               pad_background=False):
     """S1 on the device, one launch for the batch (csrc/label_sample.cu; reference roi_heads.py:157-250).
     prop_boxes / gt_boxes / gt_classes: per-image lists of (P_i,4) fp32, (M_i,4) fp32, (M_i,) int64 CUDA tensors.
     Returns dict: sampled_idx (N,B) int32, boxes (N,B,4), classes (N,B) int64, gt_boxes (N,B,4), counts (N,2) int32
@@ -605,9 +631,9 @@ def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, io
     dev = prop_boxes[0].device
     _require_cuda(*prop_boxes)
     pc, gc = [int(b.shape[0]) for b in prop_boxes], [int(b.shape[0]) for b in gt_boxes]
-    props = torch.cat([b.detach().float().reshape(-1, 4) for b in prop_boxes], 0).contiguous()
-    gts = torch.cat([b.detach().float().reshape(-1, 4) for b in gt_boxes], 0).contiguous() if sum(gc) else torch.zeros((0, 4), device=dev)
-    gcl = torch.cat([c.detach().to(torch.int64).reshape(-1) for c in gt_classes], 0).contiguous() if sum(gc) else torch.zeros(0, dtype=torch.int64, device=dev)
+    props = cat_adjacent([b.detach().float().reshape(-1, 4) for b in prop_boxes])
+    gts = cat_adjacent([b.detach().float().reshape(-1, 4) for b in gt_boxes]) if sum(gc) else torch.zeros((0, 4), device=dev)
+    gcl = cat_adjacent([c.detach().to(torch.int64).reshape(-1) for c in gt_classes]) if sum(gc) else torch.zeros(0, dtype=torch.int64, device=dev)
     _, poff = _roi_index(tuple(pc), dev)
     _, goff = _roi_index(tuple(gc), dev)
     B = int(batch_per_image)
@@ -616,15 +642,17 @@ def label_and_sample_proposals(prop_boxes, gt_boxes, gt_classes, num_classes, io
            "classes": torch.empty((N, B), dtype=torch.int64, device=dev),
            "gt_boxes": torch.empty((N, B, 4), dtype=torch.float32, device=dev),
            "counts": torch.empty((N, 2), dtype=torch.int32, device=dev)}
-    mi = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
-    ml = torch.empty(sum(pc), dtype=torch.int32, device=dev) if want_labels else None
+    n_cand = sum(pc) + (sum(gc) if append_gt else 0)
+    mi = torch.empty(n_cand, dtype=torch.int32, device=dev) if want_labels else None
+    ml = torch.empty(n_cand, dtype=torch.int32, device=dev) if want_labels else None
     if seed is None:
         if seed_salt is None:
             _LS_CALLS[0] += 1
         seed = (torch.initial_seed() * 2654435761 + (_LS_CALLS[0] if seed_salt is None else 0)) & 0x7FFFFFFFFFFFFFFF
     _lib.call("b200_label_sample_proposals", props.data_ptr(), poff.data_ptr(), _ptr(gts) if gts.numel() else 0,
               _ptr(gcl) if gcl.numel() else 0, goff.data_ptr(), N, max(pc) if pc else 0, max(gc) if gc else 0, int(num_classes),
-              float(iou_thresh), B, int(B * positive_fraction), int(seed), _ptr(seed_salt), _ptr(mi), _ptr(ml),
+              float(iou_thresh), B, int(B * positive_fraction), int(seed), _ptr(seed_salt), int(append_gt), int(pad_background),
+              _ptr(mi), _ptr(ml),
               out["sampled_idx"].data_ptr(),
               out["boxes"].data_ptr(), out["classes"].data_ptr(), out["gt_boxes"].data_ptr(), out["counts"].data_ptr(),
               _stream())

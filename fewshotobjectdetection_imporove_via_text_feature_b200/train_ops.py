@@ -81,13 +81,14 @@ def dropout_bf16(x, p, seed, salt=None):
     return y
 
 
-def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weights, beta):
+def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weights, beta, acc_stats=None):
+    """acc_stats (5,) fp32, optional: the counts of FastRCNNOutputs._log_accuracy from the same pass over the logits."""
     R = logits.shape[0]
     out = torch.empty(3, dtype=torch.float32, device=logits.device)
     agnostic = deltas.shape[1] == 4 and K != 1
     _lib.call("b200_head_losses", logits.data_ptr(), deltas.data_ptr(), _ptr(attn), gt_classes.data_ptr(),
               proposals.data_ptr(), gt_boxes.data_ptr(), R, K, 0 if attn is None else attn.shape[1], int(agnostic),
-              *map(float, weights), float(beta), out.data_ptr(), _stream())
+              *map(float, weights), float(beta), out.data_ptr(), _ptr(acc_stats), _stream())
     return out
 
 
@@ -270,7 +271,7 @@ class _TextSide(torch.autograd.Function):
         s = 1.0 / float(d) ** 0.5
         cur = torch.cuda.current_stream()
         for g in (dkq, dvp):           # produced on another stream by _FusedHeadTrain.backward (deferred mode)
-            ev = _READY_EVENTS.pop(g.data_ptr(), None)
+            ev = _take_ready_event(g)
             if ev is not None:
                 cur.wait_event(ev)
                 g.record_stream(cur)
@@ -334,7 +335,8 @@ def text_side_async(att, after=None):
 
 
 class _FusedHeadTrain(torch.autograd.Function):
-    """(x, kq, vp, weights..., labels) -> (losses (3,), logits (R,K+1) [non-differentiable, for logging])."""
+    """(x, kq, vp, weights..., labels) -> (losses (3,), logits (R,K+1), accuracy counts (5,) [both non-differentiable,
+    for logging])."""
 
     @staticmethod
     def forward(ctx, x, kq, vp, W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb,
@@ -345,7 +347,11 @@ class _FusedHeadTrain(torch.autograd.Function):
         R, d = x.shape
         h = d // 2
         dev = x.device
-        bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+        def bf(t):          # the optimizer's bf16 shadow of the parameter when it keeps one (FlatSGD), else a cast
+            sh = getattr(t, "_b200_bf16", None)
+            if sh is not None and sh.shape == t.shape and sh.device == t.device:
+                return sh
+            return t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().float().contiguous()
         W = dict(W1=bf(W1), W2=bf(W2), W3=bf(W3), Wf1=bf(Wf1), Wf2=bf(Wf2), Wc=bf(Wc), Wb=bf(Wb), kq=bf(kq))
         vpf, gam, bet = f32(vp), f32(gamma), f32(beta)
@@ -373,7 +379,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         logits, deltas = f32e(W["Wc"].shape[0]), f32e(W["Wb"].shape[0])
         g2(zd, W["Wc"], bias=bc, out_f32=logits, want_out=False)
         g2(xb, W["Wb"], bias=bb, out_f32=deltas, want_out=False)
-        losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta)
+        acc = torch.empty(5, dtype=torch.float32, device=dev)
+        losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta, acc)
         # distillation (BASELINE configs[3]): a fourth loss, KL against the frozen teacher's logits (my_module.py:409-437)
         tl = None
         if teacher_logits is not None:
@@ -398,11 +405,11 @@ class _FusedHeadTrain(torch.autograd.Function):
         ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
                                  s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
         ctx.sink_owners = params if ctx.sinks is not None else None
-        ctx.mark_non_differentiable(logits)
-        return losses, logits
+        ctx.mark_non_differentiable(logits, acc)
+        return losses, logits, acc
 
     @staticmethod
-    def backward(ctx, g_losses, _g_logits):
+    def backward(ctx, g_losses, _g_logits, _g_acc):
         (x, xcat, p1, p2, attn, vp, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
          W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors
         g2 = ops_mod.gemm2
@@ -540,7 +547,7 @@ class _FusedHeadTrain(torch.autograd.Function):
             # uses make the caching allocator cudaMalloc afresh when the next step asks for the same sizes.
             PENDING_GRAD_EVENTS.append((done, keep))
             for g in (out["dkq"], out["dvp"]):
-                _READY_EVENTS[g.data_ptr()] = tdone
+                _set_ready_event(g, tdone)
             return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 12
         main.wait_event(done)
         main.wait_event(tdone)
@@ -550,7 +557,21 @@ class _FusedHeadTrain(torch.autograd.Function):
 
 
 _COMM_STREAMS = {}
-_READY_EVENTS = {}           # gradient address -> event after which it may be read (producer on another stream)
+_READY_EVENTS = {}           # (storage address, version-free) -> (weakref to the gradient, event): see _set_ready_event
+
+
+def _set_ready_event(g, ev):
+    """Attach "readable after `ev`" to a gradient produced on another stream.  The event rides on the tensor object
+    (autograd hands the same object to the consumer node when nothing accumulates into it); the address-keyed table is the
+    fall-back for the case where autograd re-wraps the storage, and it is cleared every step (FlatSGD.sync_grads)."""
+    g._b200_ready = ev
+    _READY_EVENTS[g.data_ptr()] = ev
+
+
+def _take_ready_event(g):
+    ev = getattr(g, "_b200_ready", None)
+    ev2 = _READY_EVENTS.pop(g.data_ptr(), None)
+    return ev if ev is not None else ev2
 PENDING_GRAD_EVENTS = []     # side-stream completion events of deferred parameter gradients (drained by FlatSGD.sync_grads)
 _SIDE = {}
 
@@ -582,7 +603,10 @@ class FlatSGD:
     gradients there itself, from its side stream, and `sync_grads` (called by `step`, and by the caller before a
     gradient all-reduce) is where that stream is joined.  Requires every such parameter to be used once per step."""
 
-    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0, direct_grads=False):
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0, direct_grads=False, bf16_shadow=None):
+        """bf16_shadow (default: on with direct_grads): keep a flat bf16 copy of the parameters, refreshed by the update
+        kernel itself; every parameter carries its slice as `_b200_bf16` and the fused head reads its GEMM operands from
+        there instead of casting the fp32 weights at the top of every step."""
         self.params = [p for p in params if p.requires_grad]
         offs, n = [], 0
         for p in self.params:
@@ -593,11 +617,15 @@ class FlatSGD:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.mom = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=dev) if (direct_grads if bf16_shadow is None else bf16_shadow) else None
         for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p.data)
             p.grad = self.grad[off:off + k].view_as(p.data)
+            if self.shadow is not None:
+                self.shadow[off:off + k].copy_(self.flat[off:off + k])
+                p._b200_bf16 = self.shadow[off:off + k].view_as(p.data)
             if direct_grads:
                 p._b200_grad_sink = p.grad
                 p._b200_opt = self
@@ -636,6 +664,9 @@ class FlatSGD:
         while PENDING_GRAD_EVENTS:
             ev, _keepalive = PENDING_GRAD_EVENTS.pop()
             cur.wait_event(ev)
+        for ev in _READY_EVENTS.values():        # text side frozen: nobody consumed dKq / dVp — still join their stream
+            cur.wait_event(ev)
+        _READY_EVENTS.clear()
 
     def all_reduce_grads(self, n_late_params=0, group=None):
         """Gradient all-reduce (replaces DDP at engine/defaults.py:252-258) for one process per GPU.  The gradients of all
@@ -644,6 +675,14 @@ class FlatSGD:
         all-reduce goes on a communication stream behind those events and runs under the res5 / ROIAlign backward that
         the current stream still has queued; only the late tail is reduced on the current stream."""
         import torch.distributed as dist
+        avg = dist.get_backend(group) == "nccl"          # ReduceOp.AVG exists on NCCL only: SUM then scale elsewhere
+
+        def reduce_(t):
+            if avg:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                t.div_(dist.get_world_size(group))
         cur = torch.cuda.current_stream()
         dev = self.grad.device
         key = (dev.type, dev.index)
@@ -653,7 +692,7 @@ class FlatSGD:
         split = self.offsets[len(self.params) - n_late_params] if n_late_params else self.grad.numel()
         if not PENDING_GRAD_EVENTS or n_late_params == 0:
             self.sync_grads()
-            dist.all_reduce(self.grad, op=dist.ReduceOp.AVG, group=group)
+            reduce_(self.grad)
             return
         if self._zeroed is not None:
             comm.wait_event(self._zeroed)            # not before this step's zero_grad
@@ -663,10 +702,10 @@ class FlatSGD:
             comm.wait_event(ev)
             held.append(keepalive)
         with torch.cuda.stream(comm):
-            dist.all_reduce(self.grad[:split], op=dist.ReduceOp.AVG, group=group)
+            reduce_(self.grad[:split])
             done = torch.cuda.Event()
             done.record(comm)
-        dist.all_reduce(self.grad[split:], op=dist.ReduceOp.AVG, group=group)
+        reduce_(self.grad[split:])
         cur.wait_event(done)
         del held                                     # the current stream is now behind every stream that read them
 
@@ -676,7 +715,8 @@ class FlatSGD:
             self._ranges = self._active_ranges()             # one host read, at the first step only
         for b, e in self._ranges:
             _lib.call("b200_sgd_momentum", self.flat[b:e].data_ptr(), self.grad[b:e].data_ptr(), self.mom[b:e].data_ptr(), e - b,
-                      float(self.lr), float(self.momentum), float(self.weight_decay), _stream())
+                      float(self.lr), float(self.momentum), float(self.weight_decay),
+                      0 if self.shadow is None else self.shadow[b:e].data_ptr(), _stream())
         ops_mod.PARAM_GENERATION[0] += 1     # the bf16 weight caches key on this (in-place kernel updates bypass _version)
 
 

@@ -262,10 +262,12 @@ B200_API int b200_text_attention_bwd(const void* dp1, const void* dp2, int ldp, 
                             const float* vp, const float* dattn_ext, float* dx, int accumulate_dx, void* d_o, void* ds,
                             int ldds, int R, int d, int L, b200_stream_t stream);
 /* L1: out3 = {loss_cls, loss_box_reg, loss_attentive} (fast_rcnn.py:222-304, roi_heads.py:1079-1081); attn may be
- * NULL (no attentive loss).  gt_classes int64 in [0, K] (K = background); proposals / gt_boxes (R,4). */
+ * NULL (no attentive loss).  gt_classes int64 in [0, K] (K = background); proposals / gt_boxes (R,4).
+ * acc_stats5 (optional): the counts FastRCNNOutputs._log_accuracy reads back (fast_rcnn.py:191-220) as floats:
+ * {#(argmax == gt), #fg, #(fg and argmax == gt), #(fg and argmax == K), R}. */
 B200_API int b200_head_losses(const float* logits, const float* deltas, const float* attn, const int64_t* gt_classes,
                      const float* proposals, const float* gt_boxes, int R, int K, int L, int cls_agnostic, float wx,
-                     float wy, float ww, float wh, float smooth_l1_beta, float* out3, b200_stream_t stream);
+                     float wy, float ww, float wh, float smooth_l1_beta, float* out3, float* acc_stats5, b200_stream_t stream);
 /* gradients of the three losses scaled by grad_scale3[0..2] (device): dlogits (R,ldl) bf16, ddeltas (R,ldd) bf16
  * (both zero padded to their row stride), dattn (R,L) fp32 (may be NULL). */
 B200_API int b200_head_losses_bwd(const float* logits, const float* deltas, const float* attn, const int64_t* gt_classes,
@@ -290,9 +292,10 @@ B200_API size_t b200_skinny_gemm_workspace_bytes(int M, int cols);   /* cols = N
 B200_API int b200_skinny_gemm(int mode, const float* A, int lda, const float* relu_ref, int ldref, const float* B, int ldb,
                      const float* bias, int relu, float scale, float* out, int ldo, float* out_bias, int M, int N, int K,
                      int accumulate, void* workspace, size_t workspace_bytes, b200_stream_t stream);
-/* torch.optim.SGD step over one flat fp32 buffer: g += wd*p; m = mu*m + g; p -= lr*m (defrcn/solver/build.py) */
+/* torch.optim.SGD step over one flat fp32 buffer: g += wd*p; m = mu*m + g; p -= lr*m (defrcn/solver/build.py).
+ * bf16_shadow (optional, n elements): receives bf16(p) — the operand copy the tensor-core GEMMs of the next step read. */
 B200_API int b200_sgd_momentum(float* params, const float* grads, float* momentum_buf, size_t n, float lr, float momentum,
-                      float weight_decay, b200_stream_t stream);
+                      float weight_decay, void* bf16_shadow, b200_stream_t stream);
 
 /* A3 + A4 prologue: S = Q Kp^T / sqrt(d), softmax over the K+2 keys, O = attn Vp, then the two gate
  * operands P1 = O*x and P2 = x - O written as bf16 (attentive_modules.py:45-55,166,170).
@@ -353,14 +356,17 @@ B200_API int b200_l2_normalize_rows(const void* src, int src_dtype, int ld_src, 
  *   (counter-based hash of (seed, image, proposal): the reference's distribution, not torch's RNG stream),
  *   foreground rows first.  Outputs have batch_per_image rows per image: sampled_idx (index within the image, -1 =
  *   padding), the sampled boxes, their class (num_classes = background, -1 = padding), the matched ground-truth box;
- *   counts (num_images, 2) = (#foreground rows, #valid rows).  seed_salt (optional device scalar) is added to seed
+ *   counts (num_images, 2) = (#foreground rows, #valid rows).  append_gt != 0: the image's ground-truth boxes are
+ *   candidates too, after its proposals (PROPOSAL_APPEND_GT, roi_heads.py:185-186; candidate index P_i + j = gt box j;
+ *   matched_idx / matched_label then cover P_i + M_i entries per image), without a concatenated copy.  pad_background
+ *   != 0: padding rows get class num_classes instead of -1 (fixed-shape consumers).  seed_salt (optional device scalar) is added to seed
  *   on the device: a step counter that survives CUDA-graph replay.  An image whose offsets exceed the limits gets no
  *   rows (counts 0) instead of being processed.
  * ------------------------------------------------------------------------------------------------- */
 B200_API int b200_label_sample_proposals(const float* proposals, const int32_t* prop_offsets, const float* gt_boxes,
                                 const int64_t* gt_classes, const int32_t* gt_offsets, int num_images,
                                 int max_props_per_image, int max_gt_per_image, int num_classes, float iou_thresh,
-                                int batch_per_image, int max_positive, unsigned long long seed, const int64_t* seed_salt, int32_t* matched_idx,
+                                int batch_per_image, int max_positive, unsigned long long seed, const int64_t* seed_salt, int append_gt, int pad_background, int32_t* matched_idx,
                                 int32_t* matched_label, int32_t* sampled_idx, float* out_proposals, int64_t* out_classes,
                                 float* out_gt_boxes, int32_t* counts, b200_stream_t stream);
 

@@ -47,8 +47,11 @@ def _worker(rank, world, port, n_images):
     ps = [torch.nn.Parameter(torch.zeros(1000)), torch.nn.Parameter(torch.zeros(37, 3)), torch.nn.Parameter(torch.zeros(5))]
     for p in ps[:2]:
         p.grad = torch.full_like(p, float(rank + 1))
+    if rank == 1:                      # a parameter that received a gradient on ONE rank only: the bucket layout is over the
+        ps[2].grad = torch.full_like(ps[2], 2.0)     # fixed parameter list, the other rank contributes zeros (no hang)
     nb = D.allreduce_gradients(ps, bucket_bytes=2048)
-    assert nb >= 2 and all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in ps[:2]) and ps[2].grad is None
+    assert nb >= 2 and all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in ps[:2])
+    assert torch.allclose(ps[2].grad, torch.full_like(ps[2], 1.0))
     dist.barrier()
     dist.destroy_process_group()
 
