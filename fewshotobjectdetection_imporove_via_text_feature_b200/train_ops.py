@@ -475,6 +475,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         dzd = g2(dlogits[:, :C1], Wc, b_mn=True)                          # (R, d) bf16
         dx = torch.empty((R, d), dtype=torch.float32, device=dev)
         g2(ddeltas[:, :C4], Wb, b_mn=True, out_f32=dx, want_out=False)    # first producer of dL/dx (fp32)
+        if _DEBUG is not None:
+            _DEBUG.update(dx_box=dx.clone(), dzd=dzd.clone(), dlogits=dlogits.clone())
         # ---- A5/A6 + dropout: zd = dropout(relu(LN(y + y2))) ---------------------------------------------------
         du = torch.empty((R, d), dtype=torch.float32, device=dev)
         dub = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
@@ -510,6 +512,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         fork(side_l3, dyb, du, xcat)
         do12 = g2(dyb, W3[:, :d], b_mn=True, mask_act=xcat[:, :d])          # [do1 | do2], ReLU backward fused
         g2(dyb, W3[:, d:], b_mn=True, out_f32=dx, accumulate=True, want_out=False)
+        if _DEBUG is not None:
+            _DEBUG.update(dx_l3=dx.clone(), dyb=dyb.clone(), do12=do12.clone(), dub=dub.clone(), dhdn=dhdn.clone(), du=du.clone())
         # ---- linear1 / linear2: o1 = relu(P1 W1^T + b1), o2 = relu(P2 W2^T + b2) --------------------------------
         def side_l12():
             out["dW1"] = dW(do12[:, :h], p1, sk["W1"])
@@ -525,6 +529,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         _lib.call("b200_text_attention_bwd", dp1.data_ptr(), dp2.data_ptr(), dp1.stride(0), x.data_ptr(), attn.data_ptr(),
                   vp.data_ptr(), _ptr(dattn), dx.data_ptr(), 1, dO.data_ptr(), dS.data_ptr(), Lp, R, d, L, st)
 
+        if _DEBUG is not None:
+            _DEBUG.update(dx_att=dx.clone(), dp1=dp1.clone(), dp2=dp2.clone(), dO=dO.clone(), dS=dS.clone())
         text = _TEXT_STREAMS.get((dev.type, dev.index), side)
 
         def side_att():
@@ -556,6 +562,7 @@ class _FusedHeadTrain(torch.autograd.Function):
                 dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 12
 
 
+_DEBUG = None                # tests / tools: a dict that receives clones of intermediate tensors of the fused backward
 _COMM_STREAMS = {}
 _READY_EVENTS = {}           # (storage address, version-free) -> (weakref to the gradient, event): see _set_ready_event
 

@@ -165,7 +165,9 @@ def test_chain_vs_oracle(R, K, fold):
     torch.testing.assert_close(attn[0].sum(1).cpu(), torch.ones(R), rtol=1e-4, atol=1e-4)
     assert rel_err(attn[0].cpu(), attn_ref) < 2e-2
     assert rel_err(out["sim2stext"].cpu(), sim_ref) < 2e-2
-    assert float((out["sim2stext"].cpu() - sim_ref).abs().max()) < 2e-2 * float(sim_ref.abs().max()) * 4
+    # elementwise, north_star's bf16 bar: |got - ref| <= 2e-2 |ref| + 2e-2 max |ref|
+    torch.testing.assert_close(out["sim2stext"].cpu().float(), sim_ref, rtol=2e-2, atol=2e-2 * float(sim_ref.abs().max()))
+    torch.testing.assert_close(attn[0].cpu().float(), attn_ref, rtol=2e-2, atol=2e-2 * float(attn_ref.abs().max()))
 
 
 def test_chain_golden_small(golden):

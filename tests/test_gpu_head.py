@@ -59,8 +59,10 @@ def test_head_tiny_golden(golden, tag, head, layer):
         att, _ = m.forward_att(fp)
         ref_l, got_l = T(g["logits"]), att["pred_logits"].float().cpu()
         assert float((got_l - ref_l).norm() / ref_l.norm()) < 2e-2
+        torch.testing.assert_close(got_l, ref_l, rtol=2e-2, atol=2e-2 * float(ref_l.abs().max()))
         ref_d, got_d = T(g["deltas"]), att["pred_bbox"].float().cpu()
         assert float((got_d - ref_d).norm() / ref_d.norm()) < 2e-2
+        torch.testing.assert_close(got_d, ref_d, rtol=2e-2, atol=2e-2 * float(ref_d.abs().max()))
         res, losses = m(None, {"res4": feat}, props, None)
     assert losses == {}
     for i, r in enumerate(res):
@@ -129,8 +131,55 @@ def test_head_full_width_vs_oracle():
     torch.testing.assert_close(fp.cpu(), mid["feature_pooled"], rtol=2e-3, atol=2e-3)
     rl = mid["logits"]
     assert float((att["pred_logits"].cpu() - rl).norm() / rl.norm()) < 2e-2
+    torch.testing.assert_close(att["pred_logits"].cpu().float(), rl, rtol=2e-2, atol=2e-2 * float(rl.abs().max()))
     rd = mid["deltas"]
     assert float((att["pred_bbox"].cpu() - rd).norm() / rd.norm()) < 2e-2
+    torch.testing.assert_close(att["pred_bbox"].cpu().float(), rd, rtol=2e-2, atol=2e-2 * float(rd.abs().max()))
+    torch.testing.assert_close(att["sim2stext"].cpu().float(), mid["sim2stext"], rtol=2e-2, atol=2e-2 * float(mid["sim2stext"].abs().max()))
+    assert len(res) == 2 and all(len(r) <= 100 for r in res)
+
+
+def test_head_full_width_bf16_res5_vs_oracle():
+    """The BENCH path at real channel widths: bf16 res5 on the own tcgen05 kernels (the default), R = 2 x 48, against the
+    fp32 CPU oracle — pooled feature, fused feature, logits and deltas elementwise within north_star's bf16 bar
+    (|got - ref| <= 2e-2 |ref| + 2e-2 max |ref|) and in relative L2."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, ShapeSpec
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeads"
+    cfg.MODEL.ADDITION.NAME = "clip"
+    assert cfg.MODEL.B200.RES5_DTYPE == "bfloat16" and cfg.MODEL.B200.RES5_IMPL == "tcgen05"
+    torch.manual_seed(0)
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)}).eval()
+    with torch.no_grad():
+        m.box_predictor.cls_score.weight.mul_(30.0)
+        m.box_predictor.bbox_pred.weight.mul_(50.0)
+    gen = torch.Generator().manual_seed(4)
+    feat = torch.relu(torch.randn(2, 1024, 25, 32, generator=gen)) * 0.5
+    sizes = [(400, 512), (384, 500)]
+    boxes = [synth_proposals(48, h, w, gen)[0] for (h, w) in sizes]
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    text = torch.cat([m.attention.embed, m.attention.bg_feature], 0)
+    _, mid = O.head_forward(feat, boxes, sizes, text, p)
+    m = m.cuda()
+    props = []
+    for b, s in zip(boxes, sizes):
+        inst = Instances(s)
+        inst.proposal_boxes = Boxes(b.cuda())
+        props.append(inst)
+    with torch.no_grad():
+        fp = m._pooled({"res4": feat.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)}, props)
+        att, _ = m.forward_att(fp)
+        res, _ = m(None, {"res4": feat.cuda()}, props, None)
+
+    def close(got, ref):
+        got, ref = got.float().cpu(), ref.float()
+        assert float((got - ref).norm() / ref.norm()) < 2e-2
+        torch.testing.assert_close(got, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+    close(fp, mid["feature_pooled"])
+    close(att["sim2stext"], mid["sim2stext"])
+    close(att["pred_logits"], mid["logits"])
+    close(att["pred_bbox"], mid["deltas"])
     assert len(res) == 2 and all(len(r) <= 100 for r in res)
 
 
