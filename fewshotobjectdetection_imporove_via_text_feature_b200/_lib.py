@@ -27,12 +27,14 @@ class Gemm2Desc(ctypes.Structure):
                 ("out_bf16", c_void_p), ("ld_out", c_int), ("out2_bf16", c_void_p), ("ld_out2", c_int),
                 ("out_f32", c_void_p), ("ld_out_f32", c_int), ("accumulate", c_int),
                 ("bits_out", c_void_p), ("ld_bits_out", c_int), ("rowmean_out", c_void_p), ("ld_rowmean", c_int),
-                ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int)]
+                ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int),
+                ("split_k", c_int), ("splitk_workspace", c_void_p), ("splitk_workspace_bytes", c_size_t)]
 
 
 # name -> (restype, argtypes); mirrors include/b200roi.h declaration by declaration
 SIGNATURES = {
     "b200_gemm2": (c_int, [ctypes.POINTER(Gemm2Desc), c_void_p]),
+    "b200_gemm2_splitk_workspace_bytes": (c_size_t, [c_int] * 4),
     "b200_abi_version": (c_int, []),
     "b200_last_error": (ctypes.c_char_p, []),
     "b200_set_option": (c_int, [ctypes.c_char_p, c_int]),
@@ -73,7 +75,7 @@ SIGNATURES = {
     "b200_add_relu_mask": (c_int, [c_void_p] * 4 + [c_size_t, c_void_p]),
     "b200_spatial_mean_bits": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200_pack_relu_bits": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
-    "b200_mean_bwd_relu_bits": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b200_mean_bwd_relu_bits": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200_add_relu_bits": (c_int, [c_void_p] * 4 + [c_size_t, c_void_p]),
     "b200_sgd_momentum": (c_int, [c_void_p] * 3 + [c_size_t] + [c_float] * 3 + [c_void_p, c_void_p]),
     "b200_text_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),

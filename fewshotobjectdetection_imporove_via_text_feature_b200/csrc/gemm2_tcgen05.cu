@@ -34,10 +34,12 @@ namespace b200 {
 constexpr int kG2BK = 64;            // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int kG2Threads = 320;      // warp 0: TMA producer, warp 1: TMEM alloc + MMA issue, warps 2..9: epilogue
 constexpr int kG2EpiWarps = 8;
+constexpr size_t kG2SplitCounterBytes = 65536;   // head of the split-K workspace: arrival counters (zero between launches)
 constexpr int kG2BoxBytes = 4096;    // epilogue box: 32 rows x 64 bf16 (128-byte rows, 128B swizzle)
 // epilogue features an instantiation carries (dead code for the others is compiled out)
 constexpr uint32_t kFRes = 1, kFMaskBits = 2, kFMaskAct = 4, kFF32 = 8, kFBitsOut = 16, kFRowMean = 32, kFOut2 = 64;
-constexpr uint32_t kFFwd = kFRes | kFBitsOut | kFRowMean;      // res5 forward: bias, residual, ReLU, mask out, mean
+constexpr uint32_t kFFwd = kFRes | kFBitsOut;                  // res5 forward: bias, residual, ReLU, mask out (packed bf16x2 tail)
+constexpr uint32_t kFFwdMean = kFRes | kFBitsOut | kFRowMean;  // ... last block: + mean over the 16 pixels
 constexpr uint32_t kFBwd = kFRes | kFMaskBits;                 // res5 backward: mask in, residual
 constexpr uint32_t kFAll = 127;
 
@@ -60,6 +62,11 @@ struct Gemm2Args {
   int a_mn, b_mn;                    // operand stored M- / N-contiguous
   int relu;
   int has_out, has_out2, has_res;    // map_d / map_d2 / map_res are valid
+  int split_k;                       // > 1: the K blocks of a tile are shared by split_k work items (no residual then)
+  float* ws;                         // split-K partial accumulators [split][Mp][Np] fp32
+  int* counters;                     // split-K arrival counters [tile][rank][epilogue warp], zero between launches
+  int ws_ld;                         // Np
+  long long ws_split_stride;         // Mp * Np
 };
 
 template <int BN> struct G2Cfg {
@@ -97,6 +104,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int m_tiles = (p.M + 255) / 256, n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.conv_cb ? 9 * p.conv_cb : p.kb1 + p.kb2;
+  // split-K: work item w = (tile w / S, K slice w % S); the S slices of a tile run on S different CTA pairs at once
+  const int S_k = p.split_k > 1 ? p.split_k : 1;
+  const int kb_per = (num_kb + S_k - 1) / S_k;
+  const int num_work = num_tiles * S_k;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -123,10 +134,11 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ---- TMA producer (both CTAs): own A rows, own half of B; the bytes of both CTAs complete on the LEADER's barrier
     if (lane == 0) {
       int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int t = w / S_k, kb_lo = (w % S_k) * kb_per, kb_hi = min(num_kb, kb_lo + kb_per);
         const int m0 = (t / n_tiles) * 256 + (int)rank * 128;
         const int n0 = (t % n_tiles) * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -163,12 +175,13 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint64_t a_step = p.a_mn ? (2048 >> 4) : (32 >> 4), b_step = p.b_mn ? (2048 >> 4) : (32 >> 4);
       const uint32_t a_lbo = p.a_mn ? 8192 : 0, b_lbo = p.b_mn ? 8192 : 0;
       int it = 0, lt = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++lt) {
+        const int kb_lo = (w % S_k) * kb_per, kb_hi = min(num_kb, kb_lo + kb_per);
         const int buf = lt & 1;
         mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);     // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -179,9 +192,9 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo), bdesc = make_smem_desc_sw128(sb, b_lbo);
 #pragma unroll
             for (int k = 0; k < kG2BK / 16; ++k)
-              umma_bf16_pair(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0);
+              umma_bf16_pair(tmem_d, adesc + a_step * k, bdesc + b_step * k, idesc, (kb > kb_lo) || (k > 0));
             umma_commit_pair(&empty_bar[s], 3);                        // both CTAs' stage s is reusable
-            if (kb == num_kb - 1) umma_commit_pair(&acc_full[buf], 3); // both CTAs' accumulator halves are complete
+            if (kb == kb_hi - 1) umma_commit_pair(&acc_full[buf], 3);  // both CTAs' accumulator halves are complete
           }
           __syncwarp();
         }
@@ -196,7 +209,7 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     constexpr int kChunks = kCw / 64;                        // 2 (BN = 256) or 1 (BN = 128)
     const int cbeg = half * kCw;
     unsigned char* my = epi + ew * Cfg::kEpiBytesPerWarp;
-    const uint32_t s_out = smem_u32(my), s_res = s_out + kG2BoxBytes;     // output staging x1, residual boxes x2
+    const uint32_t s_out = smem_u32(my), s_res = s_out + 2 * kG2BoxBytes;     // output staging x2, residual box x1
     uint64_t* rbar = res_bar + 2 * ew;
     const int swz = lane & 7;                                // 128B swizzle: 16-byte chunk j of row r lives at j ^ (r & 7)
     const uint32_t row_off = (uint32_t)lane * 128;
@@ -213,15 +226,17 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool vecm = f_mact && (p.ldmask % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_act) & 15) == 0);
     int lt = 0;
     uint32_t gc = 0;                                         // running chunk counter of this warp (residual buffer parity)
-    auto issue_res = [&](int t, int ci, uint32_t g) {        // lane 0: residual box of tile t, chunk ci -> buffer g & 1
+    auto issue_res = [&](int t, int ci, uint32_t g) {        // lane 0: residual box of tile t, chunk ci (chunk counter g)
       const int m0 = (t / n_tiles) * 256 + (int)rank * 128 + q * 32;
       const int n0 = (t % n_tiles) * BN + cbeg + ci * 64;
-      mbar_expect_tx(&rbar[g & 1], kG2BoxBytes);
-      tma_load_2d_u32(s_res + (g & 1) * kG2BoxBytes, &map_res, &rbar[g & 1], n0, m0);
+      mbar_expect_tx(&rbar[0], kG2BoxBytes);
+      tma_load_2d_u32(s_res, &map_res, &rbar[0], n0, m0);
     };
-    // residual boxes run one chunk ahead in shared memory and one whole tile ahead in L2
+    // one residual box per warp: the box of chunk g + 1 is requested as soon as chunk g's has been read into registers,
+    // i.e. a whole chunk's processing ahead of its use, and it comes out of L2 (prefetched a tile ahead)
     if (f_res && lane == 0 && cluster_id < num_tiles) issue_res(cluster_id, 0, 0);
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++lt) {
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++lt) {
+      const int t = w / S_k;
       const int m0 = (t / n_tiles) * 256 + (int)rank * 128, n0 = (t % n_tiles) * BN;
       const int buf = lt & 1;
       const int row = m0 + q * 32 + lane;
@@ -245,33 +260,95 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
       mbar_wait(&acc_full[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
+      if (S_k > 1) {
+        // split-K: every slice leaves its fp32 partial tile in the workspace; the slice that arrives LAST at the tile's
+        // counter (per epilogue warp: the warps' regions are disjoint) sums the S partials in slice order 0..S-1 —
+        // the same order whoever arrives last, so the result is bitwise reproducible — and runs the epilogue
+        float* wrow = p.ws + (long long)(w % S_k) * p.ws_split_stride + (long long)row * p.ws_ld + n0 + cbeg;
+#pragma unroll 1
+        for (int ci = 0; ci < kChunks; ++ci) {
+          uint32_t r[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cbeg + ci * 64);
+          tmem_ld_32x32_nowait(taddr, r);
+          tmem_ld_32x32_nowait(taddr + 32, r + 32);
+          tmem_ld_wait();
+          if (row_ok && n0 + cbeg + ci * 64 < p.N) {
+            float4* dst = reinterpret_cast<float4*>(wrow + ci * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+        __threadfence();
+        __syncwarp();
+        int* cnt = p.counters + ((t * 2 + (int)rank) * kG2EpiWarps + ew);
+        int prev = 0;
+        if (lane == 0) prev = atomicAdd(cnt, 1);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev != S_k - 1) continue;                       // another slice finishes this tile
+        if (lane == 0) *cnt = 0;                             // ready for the next launch
+        __threadfence();
+      }
 #pragma unroll 1
       for (int ci = 0; ci < kChunks; ++ci, ++gc) {
         const int c0 = cbeg + ci * 64;
         const int col0 = n0 + c0;
-        // the residual box one chunk ahead (this tile or the next one) goes in flight now; its buffer was last read, by
-        // every lane, in the previous chunk
+        uint32_t r[64];
+        if (S_k > 1) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) r[i] = 0u;
+          if (row_ok && col0 < p.N) {
+            const float* src = p.ws + (long long)row * p.ws_ld + n0 + c0;
+            for (int sl = 0; sl < S_k; ++sl, src += p.ws_split_stride) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src) + i);
+                r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + v4.x);
+                r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + v4.y);
+                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + v4.z);
+                r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + v4.w);
+              }
+            }
+          }
+        } else {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
+          tmem_ld_32x32_nowait(taddr, r);
+          tmem_ld_32x32_nowait(taddr + 32, r + 32);
+          tmem_ld_wait();
+          if (ci == kChunks - 1) {                           // last read of this accumulator: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+          }
+        }
         if (f_res) {
-          __syncwarp();
+          // residual (bf16, 128B-swizzled rows of the TMA box) added straight into the accumulator registers, so that the
+          // box is free again — and the next one requested — before the rest of the chunk is processed
+          mbar_wait(&rbar[0], gc & 1);
+          const uint32_t base = s_res + row_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + ((j ^ swz) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              r[8 * j + 2 * k] = __float_as_uint(__uint_as_float(r[8 * j + 2 * k]) + __uint_as_float(w[k] << 16));
+              r[8 * j + 2 * k + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * k + 1]) + __uint_as_float(w[k] & 0xffff0000u));
+            }
+          }
+          __syncwarp();                                      // every lane has read its row: the box can be refilled
           if (lane == 0) {
             if (ci + 1 < kChunks) issue_res(t, ci + 1, gc + 1);
             else if (t + num_clusters < num_tiles) issue_res(t + num_clusters, 0, gc + 1);
           }
         }
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
-        tmem_ld_32x32_nowait(taddr, r);
-        tmem_ld_32x32_nowait(taddr + 32, r + 32);
-        tmem_ld_wait();
-        if (ci == kChunks - 1) {                             // last read of this accumulator: hand it back to the MMA warp
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
-        }
-        if (f_res) mbar_wait(&rbar[gc & 1], (gc >> 1) & 1);
         if (col0 >= p.N) continue;                           // warp-uniform: chunk entirely beyond N
-        if (f_store) {                                       // the staging buffer was last read by the previous chunk's store
-          if (lane == 0) tma_store_wait_read<0>();
+        if (f_store) {                                       // staging buffer gc & 1 was last read by the store of chunk gc - 2
+          if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
         }
 #pragma unroll
@@ -298,28 +375,18 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[32 * h + i]);
           }
-          if (f_res) {                                       // residual tile (bf16, 128B-swizzled rows) from shared memory
-            const uint32_t base = s_res + (gc & 1) * kG2BoxBytes + row_off;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + (((4 * h + j) ^ swz) << 4)));
-              const uint32_t w[4] = {w0, w1, w2, w3};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
-                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
-              }
-            }
-          }
-          if (p.relu) {
+          // When nothing after the activation needs fp32 values (no gate, no fp32 / mean output), ReLU and the output's
+          // mask run on the packed bf16x2 words instead: max.bf16x2 and set.ne.bf16x2 handle two columns per instruction
+          // (ReLU commutes with the rounding; after it a stored value is positive iff it is not zero).
+          constexpr bool packed_tail = (F & (kFMaskBits | kFMaskAct | kFF32 | kFRowMean)) == 0;   // such instantiations always store
+          if (p.relu && !packed_tail) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
-          if (f_mbits) {
+          if (f_mbits) {      // packed mask word: bit j <-> column 2j, bit 16 + j <-> column 2j + 1
             const uint32_t pbits = (kChunks == 2 && ci) ? mw[2 + h] : mw[h];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (!(pbits & (1u << i))) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) if (!(pbits & (1u << ((i >> 1) | ((i & 1) << 4))))) v[i] = 0.f;
           }
           if (f_mact) {
             if (vecm && full && row_ok) {
@@ -361,10 +428,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             }
           }
-          if (f_bout) {
+          if (f_bout && !packed_tail) {
             uint32_t w = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (v[i] > 0.f) w |= 1u << i;
+            for (int i = 0; i < 32; ++i) if (v[i] > 0.f) w |= 1u << ((i >> 1) | ((i & 1) << 4));
             if (kChunks == 2 && ci) bw[2 + h] = w; else bw[h] = w;
           }
           if (f_mean) {
@@ -413,24 +480,49 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
           }
           if (f_store) {
-            const uint32_t base = s_out + row_off;
+            const uint32_t base = s_out + (gc & 1) * kG2BoxBytes + row_off;
+            uint32_t hw[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((4 * h + j) ^ swz) << 4)),
-                           "r"(*reinterpret_cast<const uint32_t*>(&h0)), "r"(*reinterpret_cast<const uint32_t*>(&h1)),
-                           "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(*reinterpret_cast<const uint32_t*>(&h3))
-                           : "memory");
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&hh);
             }
+            if (packed_tail) {
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) asm("max.bf16x2 %0, %1, %2;" : "=r"(hw[j]) : "r"(hw[j]), "r"(0u));
+              }
+              if (f_bout) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  uint32_t ne;                               // 0xffff per half that is not zero
+                  asm("set.ne.u32.bf16x2 %0, %1, %2;" : "=r"(ne) : "r"(hw[j]), "r"(0u));
+                  w |= ne & ((1u << j) | (1u << (16 + j)));
+                }
+                // without ReLU a stored value may be negative: positive = not zero and sign clear
+                if (!p.relu) {
+                  uint32_t neg = 0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) neg |= ((hw[j] >> 15) & 1u) << j | ((hw[j] >> 31) & 1u) << (16 + j);
+                  w &= ~neg;
+                }
+                if (kChunks == 2 && ci) bw[2 + h] = w; else bw[h] = w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((4 * h + j) ^ swz) << 4)),
+                           "r"(hw[4 * j]), "r"(hw[4 * j + 1]), "r"(hw[4 * j + 2]), "r"(hw[4 * j + 3])
+                           : "memory");
           }
         }
         if (f_store) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.has_out) tma_store_2d(&map_d, s_out, col0, m0 + q * 32);
-            if (f_out2) tma_store_2d(&map_d2, s_out, col0, m0 + q * 32);
+            if (p.has_out) tma_store_2d(&map_d, s_out + (gc & 1) * kG2BoxBytes, col0, m0 + q * 32);
+            if (f_out2) tma_store_2d(&map_d2, s_out + (gc & 1) * kG2BoxBytes, col0, m0 + q * 32);
             tma_store_commit();
           }
         }
@@ -526,10 +618,33 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   a.conv_cb = d->conv_c / kG2BK;
   a.a_mn = d->a_mn; a.b_mn = d->b_mn; a.relu = d->relu;
   a.has_out = d->out_bf16 != nullptr; a.has_out2 = d->out2_bf16 != nullptr; a.has_res = d->residual != nullptr;
+  a.split_k = d->split_k > 1 ? d->split_k : 1;
+  if (a.split_k > 1) {
+    const int mt = ceil_div(d->M, 256), nt = ceil_div(d->N, BN);
+    const size_t part = (size_t)a.split_k * mt * 256 * nt * BN * 4, need = kG2SplitCounterBytes + part;
+    if ((size_t)mt * nt * 2 * kG2EpiWarps * 4 > kG2SplitCounterBytes) {
+      set_error("gemm2: split-K is meant for products with few output tiles (%d x %d tiles)", mt, nt);
+      return B200_ERR_UNSUPPORTED;
+    }
+    const int nkb = d->conv_c ? 9 * (d->conv_c / kG2BK) : a.kb1 + a.kb2;
+    if (!d->splitk_workspace || d->splitk_workspace_bytes < need || (reinterpret_cast<uintptr_t>(d->splitk_workspace) & 15)) {
+      set_error("gemm2: split-K needs a 16-byte aligned workspace of %zu bytes (b200_gemm2_splitk_workspace_bytes)", need);
+      return B200_ERR_WORKSPACE;
+    }
+    if (d->residual || ceil_div(nkb, a.split_k) * (a.split_k - 1) >= nkb) {
+      set_error("gemm2: split-K excludes a residual operand and needs every K slice non-empty (K blocks %d, split %d)", nkb, a.split_k);
+      return B200_ERR_INVALID;
+    }
+    // counters first, at a fixed place: a workspace shared by launches of different shapes (one stream) keeps them zero
+    a.counters = (int*)d->splitk_workspace;
+    a.ws = (float*)((unsigned char*)d->splitk_workspace + kG2SplitCounterBytes);
+    a.ws_ld = nt * BN;
+    a.ws_split_stride = (long long)mt * 256 * nt * BN;
+  }
 
   auto kern = gemm2_pair_kernel<BN, F>;
   B200_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<BN>::kSmemBytes));
-  const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, BN);
+  const int tiles = ceil_div(d->M, 256) * ceil_div(d->N, BN) * a.split_k;
   int clusters = min(tiles, kNumSMs / 2);
   if (d->max_clusters > 0) clusters = min(clusters, d->max_clusters);
   cudaLaunchConfig_t cfg = {};
@@ -544,6 +659,12 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" size_t b200_gemm2_splitk_workspace_bytes(int M, int N, int tile_n, int split_k) {
+  if (split_k <= 1 || M <= 0 || N <= 0 || (tile_n != 128 && tile_n != 256)) return 0;
+  const size_t mt = (size_t)ceil_div(M, 256), nt = (size_t)ceil_div(N, tile_n);
+  return kG2SplitCounterBytes + (size_t)split_k * mt * 256 * nt * tile_n * 4;
+}
 
 extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
   B200_CHECK_ARG(d, "gemm2: null descriptor");
@@ -583,6 +704,7 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
     bn = (d->N <= 128 || mt * ceil_div(d->N, 128) <= kNumSMs / 2) ? 128 : 256;
   }
   B200_CHECK_ARG(bn == 128 || bn == 256, "gemm2: tile_n must be 0, 128 or 256");
+  B200_CHECK_ARG(d->split_k <= 1 || d->tile_n == bn, "gemm2: split-K needs an explicit tile_n (the workspace is sized for it)");
   // smallest instantiation whose compiled-in epilogue features cover the descriptor
   uint32_t need = 0;
   if (d->residual) need |= kFRes;
@@ -594,6 +716,7 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
   if (d->out2_bf16) need |= kFOut2;
   if (d->epilogue_variant == 1) need = kFAll;          // tests: force the generic instantiation
   if ((need & ~kFFwd) == 0) return bn == 256 ? launch_gemm2<256, kFFwd>(d, st) : launch_gemm2<128, kFFwd>(d, st);
+  if ((need & ~kFFwdMean) == 0) return bn == 256 ? launch_gemm2<256, kFFwdMean>(d, st) : launch_gemm2<128, kFFwdMean>(d, st);
   if ((need & ~kFBwd) == 0) return bn == 256 ? launch_gemm2<256, kFBwd>(d, st) : launch_gemm2<128, kFBwd>(d, st);
   return bn == 256 ? launch_gemm2<256, kFAll>(d, st) : launch_gemm2<128, kFAll>(d, st);
 }

@@ -82,7 +82,8 @@ spatial_mean_kernel(const uint4* __restrict__ x, float* __restrict__ pooled, int
 
 __global__ void __launch_bounds__(256)
 mean_bwd_relu_mask_kernel(const float* __restrict__ gpooled, int ld_g, const uint4* __restrict__ out,
-                          const uint8_t* __restrict__ bits, uint4* __restrict__ g, int R, int HW, int C8, float inv) {
+                          const uint8_t* __restrict__ bits, uint4* __restrict__ g, int R, int HW, int C8, float inv,
+                          int interleaved) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)R * C8) return;
   const int r = (int)(i / C8), c8 = (int)(i - (size_t)r * C8);
@@ -92,6 +93,24 @@ mean_bwd_relu_mask_kernel(const float* __restrict__ gpooled, int ld_g, const uin
   v.x = pack2(a.x * inv, a.y * inv); v.y = pack2(a.z * inv, a.w * inv);
   v.z = pack2(b.x * inv, b.y * inv); v.w = pack2(b.z * inv, b.w * inv);
   uint4* dst = g + (size_t)r * HW * C8 + c8;
+  if (bits && interleaved) {
+    // masks written by the GEMM epilogue (csrc/gemm2_tcgen05.cu): per 32 columns one word, bit j <-> column 2j, bit 16 + j
+    // <-> column 2j + 1; this thread's 8 columns are nibble k = c8 % 4 of each half
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(bits) + (size_t)r * HW * (C8 / 4) + (c8 >> 2);
+    const int sh = 4 * (c8 & 3);
+#pragma unroll 4
+    for (int p = 0; p < HW; ++p) {
+      const uint32_t word = __ldg(mw + (size_t)p * (C8 / 4));
+      const uint32_t lo = word >> sh, hi = word >> (16 + sh);
+      uint4 w;
+      w.x = v.x & (((lo & 1u) ? 0xffffu : 0u) | ((hi & 1u) ? 0xffff0000u : 0u));
+      w.y = v.y & (((lo & 2u) ? 0xffffu : 0u) | ((hi & 2u) ? 0xffff0000u : 0u));
+      w.z = v.z & (((lo & 4u) ? 0xffffu : 0u) | ((hi & 4u) ? 0xffff0000u : 0u));
+      w.w = v.w & (((lo & 8u) ? 0xffffu : 0u) | ((hi & 8u) ? 0xffff0000u : 0u));
+      dst[(size_t)p * C8] = w;
+    }
+    return;
+  }
   if (bits) {
     const uint8_t* mb = bits + (size_t)r * HW * C8 + c8;
 #pragma unroll 4
@@ -187,16 +206,18 @@ extern "C" int b200_pack_relu_bits(const void* x_bf16, void* relu_bits, size_t n
   return B200_OK;
 }
 
-extern "C" int b200_mean_bwd_relu_bits(const float* gpooled, int ld_g, const void* relu_bits, void* g_bf16, int R, int HW, int C,
+extern "C" int b200_mean_bwd_relu_bits(const float* gpooled, int ld_g, const void* relu_bits, void* g_bf16, int R, int HW, int C, int bit_layout,
                                        b200_stream_t stream) {
   B200_CHECK_ARG(gpooled && relu_bits && g_bf16, "mean_bwd_relu_bits: null tensor");
   B200_CHECK_ARG(R >= 0 && HW > 0 && C > 0 && C % 8 == 0 && ld_g % 4 == 0 && ld_g >= C,
                  "mean_bwd_relu_bits: need C %% 8 == 0 and ld_g %% 4 == 0");
+  B200_CHECK_ARG(bit_layout == 0 || (bit_layout == 1 && C % 32 == 0 && ((uintptr_t)relu_bits & 3) == 0),
+                 "mean_bwd_relu_bits: bit_layout 1 (GEMM epilogue words) needs C %% 32 == 0");
   B200_CHECK_ARG((((uintptr_t)gpooled | (uintptr_t)g_bf16) & 15) == 0, "mean_bwd_relu_bits: pointers must be 16-byte aligned");
   if (R == 0) return B200_OK;
   const size_t n = (size_t)R * (C / 8);
   mean_bwd_relu_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      gpooled, ld_g, nullptr, (const uint8_t*)relu_bits, (uint4*)g_bf16, R, HW, C / 8, 1.0f / (float)HW);
+      gpooled, ld_g, nullptr, (const uint8_t*)relu_bits, (uint4*)g_bf16, R, HW, C / 8, 1.0f / (float)HW, bit_layout);
   B200_CUDA_LAUNCH_CHECK("mean_bwd_relu_bits");
   return B200_OK;
 }
@@ -226,7 +247,7 @@ extern "C" int b200_mean_bwd_relu_mask(const float* gpooled, int ld_g, const voi
   if (R == 0) return B200_OK;
   const size_t n = (size_t)R * (C / 8);
   mean_bwd_relu_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      gpooled, ld_g, (const uint4*)out_bf16, nullptr, (uint4*)g_bf16, R, HW, C / 8, 1.0f / (float)HW);
+      gpooled, ld_g, (const uint4*)out_bf16, nullptr, (uint4*)g_bf16, R, HW, C / 8, 1.0f / (float)HW, 0);
   B200_CUDA_LAUNCH_CHECK("mean_bwd_relu_mask");
   return B200_OK;
 }

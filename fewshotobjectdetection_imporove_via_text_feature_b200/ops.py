@@ -485,6 +485,42 @@ def gemm_bf16(a, b, bias=None, relu=False, out=None, out_dtype=torch.float32, ou
 GEMM2_TILE_N = [0]          # tests / microbenchmarks force 128 or 256
 GEMM2_MAX_CLUSTERS = [0]    # tests lower it to force several tiles per CTA pair on small shapes
 GEMM2_GENERIC_EPILOGUE = [0]   # tests: 1 = always the generic epilogue instantiation
+import os as _os
+GEMM2_SPLIT_K = [int(_os.environ.get("B200_GEMM2_SPLIT_K", "0"))]   # 0 = choose per shape, 1 = never split, n > 1 = force (tests)
+_SPLITK_WS = {}                # (device, stream) -> workspace: split-K launches on one stream are ordered, streams do not share
+
+
+def _splitk_plan(M, N, nkb, has_res):
+    """(tile_n, split_k) for a product with few output tiles and a long K: enough K slices to give every SM pair work."""
+    forced = GEMM2_SPLIT_K[0]
+    if has_res or forced == 1:
+        return 0, 1
+    mt = -(-M // 256)
+    bn = 128 if (N <= 128 or mt * -(-N // 128) <= 74) else 256
+    bn = GEMM2_TILE_N[0] or bn
+    tiles = mt * -(-N // bn)
+    if forced > 1:
+        s = forced
+    else:
+        # only products with a short M (weight gradients of cls_score / bbox_pred, the (K+2)-row text operands): their
+        # partial tiles are a few rows; a tall skinny-N product would write whole 64-column chunks per slice
+        if tiles > 18 or nkb < 16 or M > 128:
+            return 0, 1
+        s = min(8, 74 // tiles, nkb // 4)
+    while s > 1 and -(-nkb // s) * (s - 1) >= nkb:      # every slice needs at least one K block
+        s -= 1
+    return (bn, s) if s > 1 else (0, 1)
+
+
+def _splitk_workspace(dev, nbytes):
+    key = (dev.index, _stream())
+    ws = _SPLITK_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        # zero-filled once: the arrival counters at the tail must start at zero; the kernel leaves them zero
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _SPLITK_WS[key] = ws
+    return ws
+
 
 
 def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residual=None, relu=False, mask_act=None,
@@ -550,6 +586,13 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
         assert rowmean_out.dtype == torch.float32 and tuple(rowmean_out.shape) == (M // 16, N) and rowmean_out.stride(1) == 1
         d.rowmean_out, d.ld_rowmean = rowmean_out.data_ptr(), rowmean_out.stride(0)
     d.tile_n, d.max_clusters, d.epilogue_variant = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0], GEMM2_GENERIC_EPILOGUE[0]
+    nkb = 9 * (conv_c // 64) if conv_c else -(-K // 64) + -(-K2 // 64)
+    bn_, sk = _splitk_plan(M, N, nkb, residual is not None)
+    if sk > 1:
+        nbytes = _lib.lib().b200_gemm2_splitk_workspace_bytes(M, N, bn_, sk)
+        ws = _splitk_workspace(dev, nbytes)
+        # the arrival counters sit at the head of the workspace and every launch leaves them zero
+        d.tile_n, d.split_k, d.splitk_workspace, d.splitk_workspace_bytes = bn_, sk, ws.data_ptr(), ws.numel()
     import ctypes
     _lib.call("b200_gemm2", ctypes.byref(d), _stream(),
               tag=(2.0 * M * N * (K + K2),

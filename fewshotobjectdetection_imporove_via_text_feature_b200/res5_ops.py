@@ -132,7 +132,7 @@ def res5_mean_backward(ws, masks, gp, R):
     c_out = ws[-1].c_out
     g = torch.empty((M, c_out), dtype=torch.bfloat16, device=dev)
     _lib.call("b200_mean_bwd_relu_bits", gp.data_ptr(), gp.stride(0), masks[-1][2].data_ptr(), g.data_ptr(), R, 16, c_out,
-              ops._stream())
+              1, ops._stream())          # bit_layout 1: the GEMM epilogue's interleaved mask words
     for i in reversed(range(len(ws))):
         w = ws[i]
         m1, m2, _ = masks[i]

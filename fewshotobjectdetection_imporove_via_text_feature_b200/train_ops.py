@@ -170,7 +170,7 @@ def mean_bwd_relu_bits(gpooled, bits, like):
     if gp.stride(1) != 1 or gp.stride(0) % 4 or gp.data_ptr() % 16:
         gp = gp.contiguous()
     g = torch.empty_like(like)
-    _lib.call("b200_mean_bwd_relu_bits", gp.data_ptr(), gp.stride(0), bits.data_ptr(), g.data_ptr(), R, h * w, C, _stream())
+    _lib.call("b200_mean_bwd_relu_bits", gp.data_ptr(), gp.stride(0), bits.data_ptr(), g.data_ptr(), R, h * w, C, 0, _stream())
     return g
 
 

@@ -191,14 +191,22 @@ B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, c
  *   A2, K2    optional second K segment (K-major, [M][lda2]); requires K % 64 == 0
  *   B         bf16.  b_mn = 0: [N][ldb] (K contiguous, K + K2 columns);  b_mn = 1: [K][ldb] (N contiguous)
  *   epilogue  v = acc + bias[n] (fp32, optional) + residual[m][n] (bf16, optional);  relu != 0: v = max(v, 0);
- *             mask_bits (packed, bit n%32 of word [m][n/32]) or mask_act (bf16 activation): v = 0 where the bit is clear /
+ *             mask_bits (packed words [m][n/32], layout below) or mask_act (bf16 activation): v = 0 where the bit is clear /
  *             the activation is <= 0  (ReLU backward)
  *   outputs   out_bf16 / out2_bf16 [M][ld] (TMA stores), out_f32 [M][ld_out_f32] (accumulate != 0: +=),
- *             bits_out: packed (v > 0) [M][ld_bits_out] words (needs N % 32 == 0),
+ *             bits_out: packed (v > 0) [M][ld_bits_out] words (needs N % 32 == 0); word w covers columns 32w .. 32w+31 with
+ *             bit j <-> column 32w + 2j and bit 16 + j <-> column 32w + 2j + 1 (the order in which the epilogue's packed
+ *             bf16x2 compare produces them); mask_bits uses the same layout,
  *             rowmean_out [M/16][ld_rowmean] fp32: mean of v over each group of 16 consecutive rows (the 4x4 pixels of a ROI)
  *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it);
  *             epilogue_variant: 0 = the smallest compiled epilogue that covers the requested features, 1 = the generic one
  *             (same results; tests compare them)
+ *   split_k   > 1: the K blocks of every output tile are shared by split_k CTA pairs (products with few output tiles and a
+ *             long K: the (K+2)-row text operands, cls_score / bbox_pred and their weight gradients).  Each slice leaves its
+ *             fp32 partial tile in splitk_workspace (b200_gemm2_splitk_workspace_bytes; its first 64 KiB hold the arrival
+ *             counters, which must be zero on entry and are left zero, so one zero-initialised workspace serves any
+ *             sequence of launches on one stream); the slice arriving last sums the partials in slice order — bitwise
+ *             reproducible, no floating-point atomics — and runs the epilogue.  Needs an explicit tile_n, no residual.
  * Alignment: bf16 tensors 16-byte aligned, their leading dimensions multiples of 8 elements.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct b200_gemm2_desc {
@@ -219,8 +227,10 @@ typedef struct b200_gemm2_desc {
   float* rowmean_out; int ld_rowmean;
   int tile_n, max_clusters;
   int epilogue_variant;
+  int split_k; void* splitk_workspace; size_t splitk_workspace_bytes;
 } b200_gemm2_desc;
 B200_API int b200_gemm2(const b200_gemm2_desc* desc, b200_stream_t stream);
+B200_API size_t b200_gemm2_splitk_workspace_bytes(int M, int N, int tile_n, int split_k);
 
 /* ---------------------------------------------------------------------------------------------------
  * Fine-tuning direction (BASELINE configs[1]): what autograd does for the reference's torch modules.
@@ -331,11 +341,13 @@ B200_API int b200_add_relu_mask(const void* a_bf16, const void* b_bf16, const vo
  * <-> element 8 i + k passes the ReLU backward), 1/16 of the activation's bytes.  b200_spatial_mean_bits = b200_spatial_mean
  * that also writes the mask of the tensor it averages; b200_pack_relu_bits writes the mask of any bf16 tensor (n elements,
  * n % 8 == 0); b200_mean_bwd_relu_bits / b200_add_relu_bits = the _mask entry points reading the mask instead of the
- * activation (add_relu_bits with a == the gradient, b == NULL is the in-place-capable ReLU backward y = a where kept). */
+ * activation (add_relu_bits with a == the gradient, b == NULL is the in-place-capable ReLU backward y = a where kept).
+ * b200_mean_bwd_relu_bits, bit_layout 1: the mask words b200_gemm2 writes (bits_out; C % 32 == 0): per 32 consecutive
+ * channels one 32-bit word, bit j <-> channel 2j, bit 16 + j <-> channel 2j + 1. */
 B200_API int b200_spatial_mean_bits(const void* x_bf16, float* pooled, int ld_pooled, void* relu_bits, int R, int HW, int C,
                            b200_stream_t stream);
 B200_API int b200_pack_relu_bits(const void* x_bf16, void* relu_bits, size_t n, b200_stream_t stream);
-B200_API int b200_mean_bwd_relu_bits(const float* gpooled, int ld_g, const void* relu_bits, void* g_bf16, int R, int HW, int C,
+B200_API int b200_mean_bwd_relu_bits(const float* gpooled, int ld_g, const void* relu_bits, void* g_bf16, int R, int HW, int C, int bit_layout,
                             b200_stream_t stream);
 B200_API int b200_add_relu_bits(const void* a_bf16, const void* b_bf16, const void* relu_bits, void* y_bf16, size_t n,
                        b200_stream_t stream);

@@ -18,17 +18,21 @@ def _rand(gen, *shape, scale=1.0):
     return (torch.randn(*shape, generator=gen) * scale).to(torch.bfloat16)
 
 
+_POS = torch.tensor([(i >> 1) | ((i & 1) << 4) for i in range(32)], dtype=torch.int64)   # column i of a word -> its bit
+
+
 def _bits_of(t):
-    """packed (t > 0) words of a (M, N) tensor, bit n % 32 of word n / 32."""
+    """packed (t > 0) words of a (M, N) tensor in b200_gemm2's layout: word n / 32, bit j <-> column 2j, bit 16 + j <->
+    column 2j + 1."""
     M, N = t.shape
     b = (t > 0).reshape(M, N // 32, 32).to(torch.int64)
-    w = (b << torch.arange(32, dtype=torch.int64)).sum(-1)
+    w = (b << _POS).sum(-1)
     return torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
 
 
 def _unpack(words, N):
     w = words.cpu().to(torch.int64) & 0xffffffff
-    return ((w[:, :, None] >> torch.arange(32, dtype=torch.int64)) & 1).reshape(w.shape[0], -1)[:, :N].bool()
+    return ((w[:, :, None] >> _POS) & 1).reshape(w.shape[0], -1)[:, :N].bool()
 
 
 @pytest.mark.parametrize("tile_n", [128, 256])
@@ -94,6 +98,55 @@ def test_gemm2_many_tiles_per_pair(clusters, tile_n):
     torch.testing.assert_close(o2.double(), (prod + res.cpu().double()) * gate, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(o3.double(), prod * gate, rtol=1e-2, atol=1e-2)
     assert bool((o2[~gate] == 0).all()) and bool((o3[~gate] == 0).all())
+
+
+@pytest.mark.parametrize("split", [2, 3, 8])
+@pytest.mark.parametrize("case", ["dW_skinny", "fwd_skinny_n", "plain_bf16_mask", "conv"])
+def test_gemm2_split_k(case, split):
+    """split-K: the K blocks of a tile shared by several CTA pairs, partials summed in slice order by whoever arrives last.
+    Same epilogues, bitwise reproducible run to run, equal (to fp32 summation order) to the unsplit launch."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(split)
+    dev = "cuda"
+
+    def run():
+        if case == "dW_skinny":        # dW = dY^T X: M = 21 (K + 1 classes), K = R
+            dy, xx = _rand(gen, 1024, 24, scale=0.5).cuda()[:, :21], _rand(gen, 1024, 2048, scale=0.5).cuda()
+            of = torch.full((21, 2048), 3.0, device=dev)
+            ops.gemm2(dy, xx, a_mn=True, b_mn=True, out_f32=of, accumulate=True, want_out=False)
+            return of, 3.0 + dy.double().t() @ xx.double()
+        if case == "fwd_skinny_n":     # logits = zd Wc^T + bc: N = 21
+            a, b = _rand(gen, 700, 2048, scale=0.5).cuda(), _rand(gen, 21, 2048, scale=0.05).cuda()
+            bias = torch.randn(21, generator=gen).cuda()
+            of = torch.empty(700, 21, device=dev)
+            ops.gemm2(a, b, bias=bias, out_f32=of, want_out=False)
+            return of, a.double() @ b.double().t() + bias.double()
+        if case == "plain_bf16_mask":
+            a, b = _rand(gen, 300, 1024, scale=0.5).cuda(), _rand(gen, 200, 1024, scale=0.05).cuda()
+            act = _rand(gen, 300, 200).cuda()
+            bo = torch.zeros(300, 200 // 32 + 1, dtype=torch.int32, device=dev)
+            o = ops.gemm2(a, b, relu=True, mask_act=act, out2=torch.empty(300, 208, dtype=torch.bfloat16, device=dev)[:, :200])
+            return o, (a.double() @ b.double().t()).clamp_min(0) * (act > 0)
+        x = _rand(gen, 16 * 20, 128, scale=0.5).cuda()
+        wgt = _rand(gen, 128, 9 * 128, scale=0.05).cuda()
+        o = ops.gemm2(x, wgt, conv_c=128, relu=True)
+        ref = F.conv2d(x.double().reshape(20, 4, 4, 128).permute(0, 3, 1, 2), wgt.double().reshape(128, 3, 3, 128).permute(0, 3, 1, 2), padding=1)
+        return o, ref.clamp_min(0).permute(0, 2, 3, 1).reshape(320, 128)
+    gen.manual_seed(split)
+    ops.GEMM2_SPLIT_K[0] = 1
+    try:
+        base, ref = run()
+        ops.GEMM2_SPLIT_K[0] = split
+        gen.manual_seed(split)
+        a1, _ = run()
+        gen.manual_seed(split)
+        a2, _ = run()
+    finally:
+        ops.GEMM2_SPLIT_K[0] = 0
+    assert torch.equal(a1, a2)
+    tol = 1e-3 if a1.dtype == torch.float32 else 1e-2
+    torch.testing.assert_close(a1.double(), ref, rtol=tol, atol=tol)
+    torch.testing.assert_close(a1.double(), base.double(), rtol=tol, atol=tol)
 
 
 def test_gemm2_k_concat():

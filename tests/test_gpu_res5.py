@@ -53,7 +53,8 @@ def _rb(t):
 def _unpack(words, R, C):
     """packed mask words (16 R, C / 32) int32 -> (R, C, 4, 4) bool."""
     w = words.to(torch.int64) & 0xffffffff
-    b = ((w[:, :, None] >> torch.arange(32, dtype=torch.int64, device=w.device)) & 1).reshape(16 * R, C).bool()
+    pos = torch.tensor([(i >> 1) | ((i & 1) << 4) for i in range(32)], dtype=torch.int64, device=w.device)   # b200_gemm2's layout
+    b = ((w[:, :, None] >> pos) & 1).reshape(16 * R, C).bool()
     return b.reshape(R, 4, 4, C).permute(0, 3, 1, 2)
 
 

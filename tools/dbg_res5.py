@@ -17,7 +17,8 @@ def nhwc(t):  # (R,C,4,4) fp64 -> (M,C)
     return t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])
 def unpack(words, N):
     w = words.to(torch.int64) & 0xffffffff
-    return ((w[:, :, None] >> torch.arange(32, dtype=torch.int64, device=w.device)) & 1).reshape(w.shape[0], -1)[:, :N].bool()
+    pos = torch.tensor([(i >> 1) | ((i & 1) << 4) for i in range(32)], dtype=torch.int64, device=w.device)
+    return ((w[:, :, None] >> pos) & 1).reshape(w.shape[0], -1)[:, :N].bool()
 def cmp(name, got, ref):
     got, ref = got.double(), ref.double()
     d = (got - ref).abs()
