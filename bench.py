@@ -683,7 +683,7 @@ def main():
             _lib.PROFILE = {}
             e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0_.record()
-            det_ = ops.fast_rcnn_inference_device(lg_, dl_, pb_, offs_, hw_, 0.05, 0.5, 100)
+            det_ = ops.fast_rcnn_inference_device(lg_, dl_, pb_, offs_, hw_, 0.05, 0.5, 100, max_rois_per_image=P)
             e1_.record()
             torch.cuda.synchronize()
             if i >= 2:

@@ -48,7 +48,8 @@ SIGNATURES = {
     "b200_roi_align_bwd_plan_bytes": (c_size_t, [c_int] * 8),
     "b200_roi_align_bwd_plan": (c_int, [c_void_p] * 2 + [c_int] * 8 + [c_float] + [c_int] * 2 + [c_void_p, c_size_t, c_void_p]),
     "b200_roi_align_bwd_planned": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p] + [c_int] * 8 + [c_void_p]),
-    "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_void_p]),
+    "b200_softmax_decode_compact_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_int, c_void_p, c_size_t, c_void_p]),
     "b200_batched_nms_workspace_bytes": (c_size_t, [c_int] * 3),
     "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "b200_gather_detections": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 4 + [c_void_p]),
@@ -100,7 +101,7 @@ class B200Error(RuntimeError):
 # happens); used by bench.py to report `gpu_launches`
 KERNELS_PER_CALL = {
     "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 3, "b200_roi_align_bwd_planned": 1,
-    "b200_softmax_decode_compact": 1, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
+    "b200_softmax_decode_compact": 2, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm2": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_layernorm_param_grads": 3, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
     "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1, "b200_label_sample_proposals": 1,

@@ -111,6 +111,93 @@ softmax_decode_compact_kernel(const float* __restrict__ scores_in, int input_is_
   if (threadIdx.x == 0) cand_count[img] = running;
 }
 
+// Many-CTA form (large proposal counts: BASELINE configs[4] sweeps up to 8192 proposals per image): 256 rows per CTA, two
+// launches.  COUNT: every row's number of candidates -> per-CTA totals (and the probabilities, if asked for).  WRITE: a
+// CTA's base offset is the sum of the totals of the CTAs before it in the image (<= a few dozen), the rows' offsets an
+// exclusive scan inside the CTA; the candidates are recomputed with the same operations (same bits) and written in the
+// torch.nonzero() order.  No host synchronisation, no atomics.
+constexpr int kMcRows = 256;
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp /*[9]*/, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < kMcRows / 32; ++w) { const int t = s_warp[w]; s_warp[w] = run; run += t; }
+    s_warp[8] = run;
+  }
+  __syncthreads();
+  const int res = s_warp[warp] + inc - v;
+  *total = s_warp[8];
+  __syncthreads();
+  return res;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kMcRows)
+softmax_decode_compact_mc_kernel(const float* __restrict__ scores_in, int input_is_prob, const float* __restrict__ deltas,
+                                 const float* __restrict__ proposals, const int32_t* __restrict__ roi_offsets,
+                                 const float* __restrict__ image_hw, int K, int cls_agnostic, float wx, float wy,
+                                 float ww, float wh, float thresh, float* __restrict__ probs_out,
+                                 float* __restrict__ cand_boxes, float* __restrict__ cand_scores,
+                                 int32_t* __restrict__ cand_roi, int32_t* __restrict__ cand_cls,
+                                 int32_t* __restrict__ cand_count, int32_t* __restrict__ block_tot, int nblk) {
+  __shared__ int s_warp[9];
+  __shared__ int s_base;
+  const int img = blockIdx.y, blk = blockIdx.x;
+  const int r0 = roi_offsets[img], r1 = roi_offsets[img + 1];
+  const int r = r0 + blk * kMcRows + (int)threadIdx.x;
+  const bool live = r < r1;
+  const int ncol = K + 1;
+  const float* row = scores_in + (size_t)r * ncol;
+  float mx = 0.f, sum = 1.f;
+  int cnt = 0;
+  if (live) {
+    if (!input_is_prob) row_stats(row, ncol, &mx, &sum);
+    for (int k = 0; k < ncol; ++k) {
+      const float p = row_prob(row, k, input_is_prob, mx, sum);
+      if (!WRITE && probs_out) probs_out[(size_t)r * ncol + k] = p;
+      cnt += (k < K && p > thresh);
+    }
+  }
+  int total;
+  const int ex = block_exclusive_scan_256(cnt, s_warp, &total);
+  if (!WRITE) {
+    if (threadIdx.x == 0) block_tot[(size_t)img * nblk + blk] = total;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    int base = 0;
+    for (int b = 0; b < blk; ++b) base += block_tot[(size_t)img * nblk + b];
+    s_base = base;
+    if (blk == nblk - 1) cand_count[img] = base + total;
+  }
+  __syncthreads();
+  if (live && cnt) {
+    const float img_h = image_hw[2 * img], img_w = image_hw[2 * img + 1];
+    size_t o = (size_t)r0 * K + s_base + ex;
+    const float4 pb = *reinterpret_cast<const float4*>(proposals + 4 * (size_t)r);
+    for (int k = 0; k < K; ++k) {
+      const float p = row_prob(row, k, input_is_prob, mx, sum);   // same ops, same bits as the counting pass
+      if (p > thresh) {
+        const float* d = deltas + (cls_agnostic ? (size_t)r * 4 : ((size_t)r * K + k) * 4);
+        *reinterpret_cast<float4*>(cand_boxes + 4 * o) = decode_clip(d, pb, wx, wy, ww, wh, img_h, img_w);
+        cand_scores[o] = p;
+        cand_roi[o] = r - r0;
+        cand_cls[o] = k;
+        ++o;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // NMS
 // ------------------------------------------------------------------------------------------------
@@ -583,17 +670,40 @@ static NmsWorkspace carve(void* ws, int N, int total_capacity, int num_classes) 
 
 using namespace b200;
 
+extern "C" size_t b200_softmax_decode_compact_workspace_bytes(int N, int max_rois_per_image) {
+  if (N <= 0 || max_rois_per_image <= 0) return 0;
+  return (size_t)N * ceil_div(max_rois_per_image, kMcRows) * sizeof(int32_t);
+}
+
 extern "C" int b200_softmax_decode_compact(const float* scores_in, int input_is_prob, const float* deltas,
                                            const float* proposals, const int32_t* roi_offsets, const float* image_hw,
                                            int N, int R, int K, int cls_agnostic, float wx, float wy, float ww,
                                            float wh, float score_thresh, float* probs_out, float* cand_boxes,
                                            float* cand_scores, int32_t* cand_roi, int32_t* cand_cls,
-                                           int32_t* cand_count, b200_stream_t stream) {
+                                           int32_t* cand_count, int max_rois_per_image, void* workspace,
+                                           size_t workspace_bytes, b200_stream_t stream) {
   B200_CHECK_ARG(N >= 0 && R >= 0 && K > 0, "softmax_decode_compact: bad shape");
   B200_CHECK_ARG(roi_offsets && image_hw && cand_count, "softmax_decode_compact: null index tensors");
   B200_CHECK_ARG(R == 0 || (scores_in && deltas && proposals && cand_boxes && cand_scores && cand_roi && cand_cls),
                  "softmax_decode_compact: null tensor");
   if (N == 0) return B200_OK;
+  if (workspace && max_rois_per_image > 0) {
+    // many CTAs per image (count, then write); max_rois_per_image bounds roi_offsets[i + 1] - roi_offsets[i]
+    const int nblk = ceil_div(max_rois_per_image, kMcRows);
+    if (workspace_bytes < b200_softmax_decode_compact_workspace_bytes(N, max_rois_per_image)) {
+      set_error("softmax_decode_compact: workspace too small");
+      return B200_ERR_WORKSPACE;
+    }
+    dim3 grid(nblk, N);
+    softmax_decode_compact_mc_kernel<false><<<grid, kMcRows, 0, (cudaStream_t)stream>>>(
+        scores_in, input_is_prob, deltas, proposals, roi_offsets, image_hw, K, cls_agnostic, wx, wy, ww, wh, score_thresh,
+        probs_out, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count, (int32_t*)workspace, nblk);
+    softmax_decode_compact_mc_kernel<true><<<grid, kMcRows, 0, (cudaStream_t)stream>>>(
+        scores_in, input_is_prob, deltas, proposals, roi_offsets, image_hw, K, cls_agnostic, wx, wy, ww, wh, score_thresh,
+        probs_out, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count, (int32_t*)workspace, nblk);
+    B200_CUDA_LAUNCH_CHECK("softmax_decode_compact (many-CTA)");
+    return B200_OK;
+  }
   softmax_decode_compact_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(
       scores_in, input_is_prob, deltas, proposals, roi_offsets, image_hw, K, cls_agnostic, wx, wy, ww, wh,
       score_thresh, probs_out, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count);

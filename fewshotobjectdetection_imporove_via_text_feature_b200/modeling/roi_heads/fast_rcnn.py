@@ -150,7 +150,8 @@ class FastRCNNOutputs(object):
         hw = ops.image_hw_tensor(self.image_shapes, dev)
         return ops.fast_rcnn_inference_device(self.pred_class_logits, self.pred_proposal_deltas, self.proposals.tensor,
                                               offs, hw, score_thresh, nms_thresh, topk_per_image,
-                                              weights=self.box2box_transform.weights)
+                                              weights=self.box2box_transform.weights,
+                                              max_rois_per_image=max(self.num_preds_per_image) if self.num_preds_per_image else None)
 
     def inference(self, score_thresh, nms_thresh, topk_per_image):
         out = self.inference_device(score_thresh, nms_thresh, topk_per_image)

@@ -297,7 +297,7 @@ def image_hw_tensor(image_shapes, device):
 # D1..D3  (fast_rcnn.py:46-134, :306-334)
 # ---------------------------------------------------------------------------------------------------
 def softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, weights=(10.0, 10.0, 5.0, 5.0),
-                           input_is_prob=False, want_probs=True):
+                           input_is_prob=False, want_probs=True, max_rois_per_image=None):
     """Returns dict(probs, cand_boxes, cand_scores, cand_roi, cand_cls, cand_count, seg_offsets)."""
     _require_cuda(scores, deltas, proposals)
     scores, deltas, proposals = scores.float().contiguous(), deltas.float().contiguous(), proposals.float().contiguous()
@@ -312,10 +312,14 @@ def softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, sco
     cr = torch.empty(cap, dtype=torch.int32, device=dev)
     cc = torch.empty(cap, dtype=torch.int32, device=dev)
     cnt = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
+    # an upper bound of the per-image ROI count without a host read: the caller's, else the total; many CTAs per image
+    mx = int(max_rois_per_image) if max_rois_per_image else R
+    nb = _lib.lib().b200_softmax_decode_compact_workspace_bytes(N, mx) if (N and mx) else 0
+    ws = torch.empty(max(nb, 4), dtype=torch.uint8, device=dev)
     _lib.call("b200_softmax_decode_compact", scores.data_ptr(), int(input_is_prob), deltas.data_ptr(), proposals.data_ptr(),
               roi_offsets.data_ptr(), image_hw.data_ptr(), N, R, K, int(agnostic), *map(float, weights),
               float(score_thresh), _ptr(probs), cb.data_ptr(), cs.data_ptr(), cr.data_ptr(), cc.data_ptr(),
-              cnt.data_ptr(), _stream())
+              cnt.data_ptr(), mx if nb else 0, ws.data_ptr() if nb else 0, nb, _stream())
     return dict(probs=probs, cand_boxes=cb, cand_scores=cs, cand_roi=cr, cand_cls=cc, cand_count=cnt[:N],
                 seg_offsets=(roi_offsets * K).to(torch.int32), capacity=cap)
 
@@ -353,12 +357,13 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
 
 
 def fast_rcnn_inference_device(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, nms_thresh, topk,
-                               weights=(10.0, 10.0, 5.0, 5.0), input_is_prob=False, want_probs=False):
+                               weights=(10.0, 10.0, 5.0, 5.0), input_is_prob=False, want_probs=False,
+                               max_rois_per_image=None):
     """Whole post-processing on the device, no host synchronisation.  Returns padded tensors:
     boxes (N,topk,4), scores (N,topk), classes (N,topk) int64, roi_inds (N,topk) int64, counts (N) int32,
-    n_candidates (N) int32."""
+    n_candidates (N) int32.  max_rois_per_image: host-side bound of an image's ROI count (default: the total)."""
     c = softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, score_thresh, weights, input_is_prob,
-                               want_probs)
+                               want_probs, max_rois_per_image)
     N = roi_offsets.numel() - 1
     K = scores.shape[1] - 1
     dev = scores.device

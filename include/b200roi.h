@@ -113,12 +113,17 @@ B200_API int b200_roi_align_bwd_planned(const void* grad_out, const void* plan, 
  *   probs_out (R,K+1) may be NULL.  Candidates of image i are written, in torch.nonzero() order
  *   (roi-major, class-minor), at [roi_offsets[i]*K, roi_offsets[i]*K + cand_count[i]) of
  *   cand_boxes (R*K,4) / cand_scores / cand_roi (index within the image) / cand_cls.
- * ------------------------------------------------------------------------------------------------- */
+ * -------------------------------------------------------------------------------------------------  *   workspace (optional, b200_softmax_decode_compact_workspace_bytes; max_rois_per_image >= every image's ROI count):
+ *   spreads an image over ceil(max_rois_per_image / 256) CTAs in two launches (count, write) — same output order and
+ *   bits; without it one CTA walks an image's rows (fine up to ~1000 proposals per image).
+ */
+B200_API size_t b200_softmax_decode_compact_workspace_bytes(int N, int max_rois_per_image);
 B200_API int b200_softmax_decode_compact(const float* scores_in, int input_is_prob, const float* deltas,
                                 const float* proposals, const int32_t* roi_offsets, const float* image_hw,
                                 int N, int R, int K, int cls_agnostic, float wx, float wy, float ww, float wh,
                                 float score_thresh, float* probs_out, float* cand_boxes, float* cand_scores,
-                                int32_t* cand_roi, int32_t* cand_cls, int32_t* cand_count,
+                                int32_t* cand_roi, int32_t* cand_cls, int32_t* cand_count, int max_rois_per_image, void* workspace,
+                                size_t workspace_bytes,
                                 b200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -237,3 +237,33 @@ def test_bench_cli_contract(monkeypatch):
     a = b.parse()
     assert "inference step" in b.workload_config(a, a.mode, a.classes, a.distill, 8)["workload"] and a.classes == 80
     assert b.METRIC == "roi_head_images_per_sec" and b.UNIT == "images/s"
+
+
+def test_pcb_constructs_like_the_reference_and_preprocesses_like_it():
+    """`PrototypicalCalibrationBlock(cfg)` — the reference's one-argument call (evaluator.py:90): ImageNet ResNet-101 with
+    torchvision's parameter names (so cfg.TEST.PCB_MODELPATH loads), the reference's preprocessing (calibration_layer.py:
+    91-98) and the reference's dataset-dict support format; no GPU needed up to the pooling."""
+    import torchvision
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    from fewshotobjectdetection_imporove_via_text_feature_b200.evaluation.calibration_layer import PrototypicalCalibrationBlock
+    cfg = config.get_cfg()
+    cfg.MODEL.DEVICE = "cpu"
+    torch.manual_seed(0)
+    pcb = PrototypicalCalibrationBlock(cfg)
+    ref = torchvision.models.resnet101()
+    assert list(pcb.imagenet_model.state_dict().keys()) == list(ref.state_dict().keys())
+    assert all(a.shape == b.shape for a, b in zip(pcb.imagenet_model.state_dict().values(), ref.state_dict().values()))
+    assert pcb.fc is pcb.imagenet_model.fc and pcb.exclude_cls == list(range(15))      # voc test_all: base classes excluded
+    # same network as torchvision's, fed the reference's preprocessing
+    ref.load_state_dict(pcb.imagenet_model.state_dict())
+    ref.eval()
+    img = np.random.RandomState(0).randint(0, 256, (96, 128, 3)).astype(np.uint8)       # BGR, as cv2.imread returns it
+    with torch.no_grad():
+        got = pcb.feature_extractor(img)
+        mean = torch.tensor([0.406, 0.456, 0.485]).reshape(3, 1, 1)
+        std = torch.tensor([0.225, 0.224, 0.229]).reshape(3, 1, 1)
+        x = ((torch.from_numpy(img.transpose(2, 0, 1)) / 255.0 - mean) / std)[None][:, [2, 1, 0]]
+        r = ref
+        want = r.layer4(r.layer3(r.layer2(r.layer1(r.maxpool(r.relu(r.bn1(r.conv1(x))))))))
+    assert got.shape == (1, 2048, 3, 4)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)

@@ -181,3 +181,43 @@ def test_adversarial_grid_cases_bit_exact():
         assert torch.equal(out["classes"][0, :k].cpu(), r["classes"]), case
         assert torch.equal(out["scores"][0, :k].cpu(), r["scores"]), case
         assert torch.equal(out["boxes"][0, :k].cpu(), r["boxes"]), case
+
+
+@pytest.mark.parametrize("K", [20, 80])
+def test_many_cta_compaction_equals_single_cta_bitwise(K):
+    """The many-CTA softmax + decode + threshold compaction (large proposal counts, BASELINE configs[4]) writes the same
+    candidate list, in the same torch.nonzero() order and with the same bits, as the one-CTA-per-image kernel: ragged
+    images (0, 1, 255, 256, 257, 3000, 8192 ROIs), every count checked against the probabilities' own nonzero()."""
+    import ctypes
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+    sizes = [0, 1, 255, 256, 257, 3000, 8192]
+    gen = torch.Generator().manual_seed(K)
+    R = sum(sizes)
+    lg = torch.randn(R, K + 1, generator=gen)
+    peak = torch.rand(R, generator=gen) < 0.3
+    lg[torch.arange(R)[peak], torch.randint(0, K, (R,), generator=gen)[peak]] += 4.0
+    lg[~peak, K] += 4.0
+    dl = torch.randn(R, 4 * K, generator=gen) * 0.5
+    pb = torch.cat([synth_proposals(max(s, 1), 600, 800, gen)[0][:s] for s in sizes], 0)
+    offs = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int32, device="cuda")
+    hw = torch.tensor([[600.0, 800.0]] * len(sizes), device="cuda")
+    lg, dl, pb = lg.cuda(), dl.cuda(), pb.cuda()
+    many = ops.softmax_decode_compact(lg, dl, pb, offs, hw, 0.05, max_rois_per_image=max(sizes))
+    # the single-CTA kernel through the raw C ABI (no workspace)
+    cap = R * K
+    one = dict(probs=torch.empty_like(lg), cand_boxes=torch.zeros(cap, 4, device="cuda"), cand_scores=torch.zeros(cap, device="cuda"),
+               cand_roi=torch.zeros(cap, dtype=torch.int32, device="cuda"), cand_cls=torch.zeros(cap, dtype=torch.int32, device="cuda"),
+               cand_count=torch.zeros(len(sizes), dtype=torch.int32, device="cuda"))
+    _lib.call("b200_softmax_decode_compact", lg.data_ptr(), 0, dl.data_ptr(), pb.data_ptr(), offs.data_ptr(), hw.data_ptr(),
+              len(sizes), R, K, 0, 10.0, 10.0, 5.0, 5.0, 0.05, one["probs"].data_ptr(), one["cand_boxes"].data_ptr(),
+              one["cand_scores"].data_ptr(), one["cand_roi"].data_ptr(), one["cand_cls"].data_ptr(), one["cand_count"].data_ptr(),
+              0, 0, 0, ops._stream())
+    assert torch.equal(many["cand_count"], one["cand_count"]) and torch.equal(many["probs"], one["probs"])
+    ref_cnt = [(int((many["probs"][int(offs[i]):int(offs[i + 1]), :K] > 0.05).sum())) for i in range(len(sizes))]
+    assert many["cand_count"].tolist() == ref_cnt
+    for i, s in enumerate(sizes):
+        a, n = int(offs[i]) * K, ref_cnt[i]
+        for key in ("cand_boxes", "cand_scores", "cand_roi", "cand_cls"):
+            assert torch.equal(many[key][a:a + n], one[key][a:a + n]), (i, key)
+        idx = (many["probs"][int(offs[i]):int(offs[i + 1]), :K] > 0.05).nonzero()
+        assert torch.equal(many["cand_roi"][a:a + n].long(), idx[:, 0]) and torch.equal(many["cand_cls"][a:a + n].long(), idx[:, 1])

@@ -94,3 +94,45 @@ def test_pcb_random_vs_oracle():
     mask[list(excl)] = 1
     out = ops.pcb_cosine_blend_(s.clone().cuda(), f.cuda(), p.cuda(), c.cuda(), mask.cuda(), 0.5, 0.05, 1.0)
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_pcb_one_argument_construction_end_to_end():
+    """The reference's call pattern (evaluator.py:88-110): PrototypicalCalibrationBlock(cfg) builds the ImageNet extractor
+    itself, prototypes come from the reference's dataset dicts (image file + gt Instances in the resized frame), then
+    execute_calibration(inputs, dts) on file-name inputs.  Checked against the oracle's restatement of the blend fed with
+    the block's own ROI features."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, evaluation
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances
+    cfg = config.get_cfg()
+    cfg.MODEL.DEVICE = "cuda"
+    cfg.DATASETS.TEST = ("voc_2007_test_novel1",)             # no excluded classes
+    rs = np.random.RandomState(5)
+    images = {"img%d.jpg" % i: rs.randint(0, 256, (160, 224, 3)).astype(np.uint8) for i in range(4)}
+    torch.manual_seed(0)
+    pcb = evaluation.PrototypicalCalibrationBlock(cfg, image_reader=lambda f: images[f])
+    assert pcb.imagenet_model is not None and not pcb.imagenet_model.training
+    support = []
+    for i in range(3):
+        inst = Instances((80, 112))                           # annotations live in a frame half the file's size
+        inst.gt_boxes = Boxes(torch.tensor([[4.0, 6.0, 60.0, 70.0], [30.0, 10.0, 100.0, 64.0]]))
+        inst.gt_classes = torch.tensor([i % 2, 2])
+        support.append({"file_name": "img%d.jpg" % i, "instances": inst})
+    protos = pcb.build_prototypes(support)
+    assert sorted(protos) == [0, 1, 2] and protos[2].shape == (1, 1000)
+    det = Instances((160, 224))
+    gen = torch.Generator().manual_seed(1)
+    n = 12
+    b = torch.rand(n, 4, generator=gen) * 80
+    b[:, 2:] += torch.tensor([100.0, 60.0])
+    det.pred_boxes = Boxes(b.cuda())
+    s = torch.sort(torch.rand(n, generator=gen), descending=True).values
+    s[0], s[-1] = 1.2, 0.01                                   # one above the upper, one below the lower threshold
+    det.scores = s.clone().cuda()
+    det.pred_classes = torch.randint(0, 3, (n,), generator=gen).cuda()
+    feats = pcb.extract_roi_features(images["img3.jpg"], [det.pred_boxes]).float().cpu()
+    out = pcb.execute_calibration([{"file_name": "img3.jpg"}], [{"instances": det}])
+    il, ir = int((s > cfg.TEST.PCB_UPPER).sum()), int((s > cfg.TEST.PCB_LOWER).sum())
+    pm = torch.cat([protos[c] for c in range(3)], 0)
+    ref = O.pcb_calibrate(s, feats[il:ir], pm, det.pred_classes.cpu(), cfg.TEST.PCB_ALPHA, set())
+    torch.testing.assert_close(out[0]["instances"].scores.cpu(), ref, rtol=1e-4, atol=1e-5)
+    assert float(out[0]["instances"].scores[0]) == pytest.approx(1.2) and float(out[0]["instances"].scores[-1]) == pytest.approx(0.01)
