@@ -406,10 +406,13 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         else:              # device-resident step counter (graph capture): the host part of the seed stays constant
             salt.add_(1)
             seed = (torch.initial_seed() * 1000003) & 0x7FFFFFFFFFFFFFFF
+        cross = self._fused_cross_operands()
         losses, logits, self._acc_stats = train_ops.fused_head_train(
             feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb, self.num_classes, self.box2box_transform.weights,
-            self.smooth_l1_beta, drop, seed, True, salt, teacher_logits, kd)
-        out = {"loss_cls": losses[0], "loss_box_reg": losses[1], "loss_attentive": losses[2]}
+            self.smooth_l1_beta, drop, seed, cross is None, salt, teacher_logits, kd, cross)
+        out = {"loss_cls": losses[0], "loss_box_reg": losses[1]}
+        if cross is None:
+            out["loss_attentive"] = losses[2]
         if teacher_logits is not None:
             out["loss_kl"] = losses[3]
         return out, logits
@@ -420,10 +423,19 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         dev = self.attention.attention.w_q.weight.device
         self._drop_salt = torch.zeros(1, dtype=torch.int64, device=dev) if enable else None
 
+    def _fused_cross_operands(self):
+        """None for the plain text-fused head; (output_projection, text prototypes) for the CrossOutput head."""
+        return None
+
     def _fused_train_path(self):
-        return (self.training and torch.is_grad_enabled() and self.fused_training and
-                type(self).forward_att is SematicRes5ROIHeads.forward_att and
-                type(self.box_predictor).__name__ == "FastRCNNOutputLayers")
+        if not (self.training and torch.is_grad_enabled() and self.fused_training):
+            return False
+        if type(self).forward_att is SematicRes5ROIHeads.forward_att:
+            return type(self.box_predictor).__name__ == "FastRCNNOutputLayers"
+        # CrossOutput: prototype logits without the cosine option and without dropout on the logits
+        return (type(self).forward_att is SematicRes5ROIHeadsCrossOutput.forward_att and not self.cosine_logits and
+                type(self.box_predictor).__name__ == "FastRCNNAttentionOutputLayers" and
+                not self.box_predictor._do_cls_dropout)
 
     def prefetch_text_side(self, after=None):
         """Start this step's text-side projections on a side stream (train_ops.text_side_async); `fused_train_losses`
@@ -537,6 +549,9 @@ class SematicRes5ROIHeadsDistill(SematicRes5ROIHeads):
 class SematicRes5ROIHeadsCrossOutput(SematicRes5ROIHeads):
     """Logits are dot products of the projected fused feature with the text prototypes (roi_heads.py:1154-1171);
     used with OUTPUT_LAYER = FastRCNNAttentionOutputLayers."""
+
+    def _fused_cross_operands(self):
+        return self.output_projection, self.attention.forward_language_model()["text_feat"]
 
     def forward_att(self, feature_pooled, gt_classes=0):
         if self.training and torch.is_grad_enabled():

@@ -341,7 +341,9 @@ class _FusedHeadTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kq, vp, W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb,
                 gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt=None,
-                teacher_logits=None, kd=None):
+                teacher_logits=None, kd=None, Wo=None, bo=None, text=None):
+        """Wo, bo, text given = the CrossOutput classifier (roi_heads.py:1154-1171 + fast_rcnn.py:462-476): logits =
+        relu(output_projection(z)) . text^T against the (K+1, D) text prototypes instead of cls_score(dropout(z))."""
         _require_cuda(x, kq, vp, W1, W3, Wc, Wb, gt_classes, proposals, gt_boxes)
         x = x.detach().float().contiguous()
         R, d = x.shape
@@ -354,6 +356,10 @@ class _FusedHeadTrain(torch.autograd.Function):
             return t.detach().to(torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().float().contiguous()
         W = dict(W1=bf(W1), W2=bf(W2), W3=bf(W3), Wf1=bf(Wf1), Wf2=bf(Wf2), Wc=bf(Wc), Wb=bf(Wb), kq=bf(kq))
+        cross = Wo is not None
+        if cross:
+            assert drop_p == 0.0, "the fused CrossOutput classifier has no dropout on the logits"
+            W["Wo"], W["T"] = bf(Wo), bf(text)
         vpf, gam, bet = f32(vp), f32(gamma), f32(beta)
         gt = gt_classes.detach().to(torch.int64).contiguous()
         props, gtb = f32(proposals), f32(gt_boxes)
@@ -376,8 +382,15 @@ class _FusedHeadTrain(torch.autograd.Function):
         g2(hdn, W["Wf2"], bias=bf2, out_f32=y2, want_out=False)
         z, _ = residual_layernorm(y, y2, gam, bet, 1e-5, relu=True, want_f32=True, want_bf16=False)
         zd = dropout_bf16(z, drop_p, seed, salt)
-        logits, deltas = f32e(W["Wc"].shape[0]), f32e(W["Wb"].shape[0])
-        g2(zd, W["Wc"], bias=bc, out_f32=logits, want_out=False)
+        deltas = f32e(W["Wb"].shape[0])
+        if cross:
+            av = g2(zd, W["Wo"], bias=bo, relu=True)                               # relu(output_projection(sim2stext)), bf16
+            logits = f32e(W["T"].shape[0])
+            g2(av, W["T"], out_f32=logits, want_out=False)                         # dot products with the text prototypes
+        else:
+            av = zd
+            logits = f32e(W["Wc"].shape[0])
+            g2(zd, W["Wc"], bias=bc, out_f32=logits, want_out=False)
         g2(xb, W["Wb"], bias=bb, out_f32=deltas, want_out=False)
         acc = torch.empty(5, dtype=torch.float32, device=dev)
         losses = head_losses(logits, deltas, attn if want_attn_loss else None, gt, props, gtb, K, box_weights, l1_beta, acc)
@@ -394,13 +407,15 @@ class _FusedHeadTrain(torch.autograd.Function):
         # no transposed copies anywhere: the backward's dX = dY W reads W as an N-major B operand, dW = dY^T X reads dY and
         # X as M- / N-major operands (tcgen05 smem descriptors, csrc/gemm2_tcgen05.cu)
         ctx.save_for_backward(x, xcat, p1, p2, attn, vpf, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")])
+                              *[W[k] for k in ("W1", "W2", "W3", "Wf1", "Wf2", "Wc", "Wb", "kq")],
+                              *([av, W["Wo"], W["T"]] if cross else []))
+        ctx.cross = cross
         ctx.meta = (K, tuple(box_weights), float(l1_beta), float(drop_p), int(seed), bool(want_attn_loss))
         ctx.salt = salt
         # Deferred weight gradients (FlatSGD(direct_grads=True)): every parameter carries a view of the optimizer's flat
         # gradient buffer; the backward then writes dW / db straight into it from the side stream and does not join that
         # stream — the optimizer does, so the parameter-gradient work overlaps the res5 / ROIAlign backward.
-        params = (W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb)
+        params = (W1, b1, W2, b2, W3, b3, Wf1, bf1, Wf2, bf2, gamma, beta, Wc, bc, Wb, bb) + ((Wo, bo) if cross else ())
         sinks = [getattr(p, "_b200_grad_sink", None) for p in params]
         ctx.sinks = sinks if all(s is not None and s.dtype == torch.float32 and s.is_contiguous() and s.shape == p.shape and
                                  s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
@@ -411,7 +426,10 @@ class _FusedHeadTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_losses, _g_logits, _g_acc):
         (x, xcat, p1, p2, attn, vp, yb, y, y2, hdn, zd, logits, deltas, gam, bet, gt, props, gtb,
-         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors
+         W1, W2, W3, Wf1, Wf2, Wc, Wb, kq) = ctx.saved_tensors[:26]
+        cross = ctx.cross
+        if cross:
+            av, Wo, Tb = ctx.saved_tensors[26:]
         g2 = ops_mod.gemm2
         K, box_w, l1_beta, drop_p, seed, want_attn = ctx.meta
         R, d = x.shape
@@ -445,8 +463,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         sinks = ctx.sinks
         deferred = sinks is not None
         _claim_sinks(ctx.sink_owners)
-        sk = dict(zip(("W1", "b1", "W2", "b2", "W3", "b3", "Wf1", "bf1", "Wf2", "bf2", "gamma", "beta", "Wc", "bc", "Wb", "bb"),
-                      sinks if deferred else [None] * 16))
+        sk = dict(zip(("W1", "b1", "W2", "b2", "W3", "b3", "Wf1", "bf1", "Wf2", "bf2", "gamma", "beta", "Wc", "bc", "Wb", "bb",
+                       "Wo", "bo"), sinks if deferred else [None] * 18))
         out = {}
 
         keep = []                       # current-stream tensors read on the other streams after this call returns
@@ -466,13 +484,21 @@ class _FusedHeadTrain(torch.autograd.Function):
 
         xb = xcat[:, d:]
         # ---- C1: logits = zd Wc^T + bc ; deltas = xb Wb^T + bb -------------------------------------------------
+        if cross:     # logits = relu(zd Wo^T + bo) T^T: through the prototypes and the ReLU, then like cls_score
+            da = g2(dlogits[:, :C1], Tb, b_mn=True, mask_act=av)             # (R, D) bf16
+
         def side_c1():
-            out["dWc"] = dW(dlogits[:, :C1], zd, sk["Wc"])
-            out["dbc"] = colsum(dlogits[:, :C1], out=sk["bc"])
+            if cross:
+                out["dWo"] = dW(da, zd, sk.get("Wo"))
+                out["dbo"] = colsum(da, out=sk.get("bo"))
+                out["dWc"] = out["dbc"] = None                              # cls_score is not part of this head's graph
+            else:
+                out["dWc"] = dW(dlogits[:, :C1], zd, sk["Wc"])
+                out["dbc"] = colsum(dlogits[:, :C1], out=sk["bc"])
             out["dWb"] = dW(ddeltas[:, :C4], xb, sk["Wb"])
             out["dbb"] = colsum(ddeltas[:, :C4], out=sk["bb"])
-        fork(side_c1, dlogits, ddeltas, zd, xcat)
-        dzd = g2(dlogits[:, :C1], Wc, b_mn=True)                          # (R, d) bf16
+        fork(side_c1, dlogits, ddeltas, zd, xcat, *([da] if cross else []))
+        dzd = g2(da, Wo, b_mn=True) if cross else g2(dlogits[:, :C1], Wc, b_mn=True)      # (R, d) bf16
         dx = torch.empty((R, d), dtype=torch.float32, device=dev)
         g2(ddeltas[:, :C4], Wb, b_mn=True, out_f32=dx, want_out=False)    # first producer of dL/dx (fp32)
         if _DEBUG is not None:
@@ -554,12 +580,12 @@ class _FusedHeadTrain(torch.autograd.Function):
             PENDING_GRAD_EVENTS.append((done, keep))
             for g in (out["dkq"], out["dvp"]):
                 _set_ready_event(g, tdone)
-            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 12
+            return (dx, out["dkq"], out["dvp"]) + (None,) * 16 + (None,) * 15
         main.wait_event(done)
         main.wait_event(tdone)
         dkq, dvp, dW1, dW2, dW3, dWf1, dWf2, dWc, dWb = (out[k] for k in ("dkq", "dvp", "dW1", "dW2", "dW3", "dWf1", "dWf2", "dWc", "dWb"))
         return (dx, dkq, dvp, dW1, out["db1"], dW2, out["db2"], dW3, out["db3"], dWf1, out["dbf1"], dWf2, out["dbf2"], dgamma,
-                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 12
+                dbeta, dWc, out["dbc"], dWb, out["dbb"]) + (None,) * 12 + (out.get("dWo"), out.get("dbo"), None)
 
 
 _DEBUG = None                # tests / tools: a dict that receives clones of intermediate tensors of the fused backward
@@ -591,15 +617,17 @@ def _side_stream(dev):
 
 
 def fused_head_train(x, kq, vp, att, predictor, gt_classes, proposals, gt_boxes, K, box_weights, l1_beta, drop_p, seed,
-                     want_attn_loss=True, salt=None, teacher_logits=None, kd=None):
+                     want_attn_loss=True, salt=None, teacher_logits=None, kd=None, cross=None):
     """att: SingleHeadSiameseAttention (parameters linear1/2/3, ffn.*), predictor: FastRCNNOutputLayers.
-    teacher_logits (R, K+1) + kd = (temperature, alpha): adds the distillation loss as a fourth entry of `losses`."""
+    teacher_logits (R, K+1) + kd = (temperature, alpha): adds the distillation loss as a fourth entry of `losses`.
+    cross = (output_projection module, text prototypes (K+1, D)): the CrossOutput classifier instead of cls_score."""
     return _FusedHeadTrain.apply(
         x, kq, vp, att.linear1[0].weight, att.linear1[0].bias, att.linear2[0].weight, att.linear2[0].bias,
         att.linear3.weight, att.linear3.bias, att.ffn.linear1.weight, att.ffn.linear1.bias, att.ffn.linear2.weight,
         att.ffn.linear2.bias, att.ffn.norm3.weight, att.ffn.norm3.bias, predictor.cls_score.weight,
         predictor.cls_score.bias, predictor.bbox_pred.weight, predictor.bbox_pred.bias, gt_classes, proposals, gt_boxes,
-        K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt, teacher_logits, kd)
+        K, box_weights, l1_beta, drop_p, seed, want_attn_loss, salt, teacher_logits, kd,
+        *((cross[0].weight, cross[0].bias, cross[1]) if cross is not None else (None, None, None)))
 
 
 class FlatSGD:

@@ -25,10 +25,15 @@ def box_deltas(src, dst, w):
 def emulate(P, x, kq, vp, gt, props, gtb, K, box_w=(10.0, 10.0, 5.0, 5.0), beta=0.0, eps=1e-5, wts=(1.0, 1.0, 1.0)):
     """P: dict of fp32 parameters (W1,b1,W2,b2,W3,b3,Wf1,bf1,Wf2,bf2,gamma,beta,Wc,bc,Wb,bb); x (R,d) fp32 pooled feature;
     kq (L,d), vp (L,d) the text-side operands; gt (R,) int64; props / gtb (R,4).  No dropout.
+    P with "Wo", "bo" and "T" (text prototypes (K+1, D)): the CrossOutput classifier, logits = relu(zd Wo^T + bo) T^T
+    (roi_heads.py:1154-1171) instead of cls_score, and no attentive loss.
     Returns (losses dict, grads dict) for sum(losses)."""
     f = lambda t: t.detach().to(D)
-    W = {k: rb(f(v)) for k, v in P.items() if k.startswith("W")}             # bf16 GEMM operands
-    b = {k: f(v) for k, v in P.items() if not k.startswith("W")}
+    cross = "Wo" in P
+    W = {k: rb(f(v)) for k, v in P.items() if k.startswith("W") or k == "T"}   # bf16 GEMM operands
+    b = {k: f(v) for k, v in P.items() if not (k.startswith("W") or k == "T")}
+    if cross:
+        wts = (wts[0], wts[1], 0.0)
     x, vp = f(x), f(vp)
     kqb = rb(f(kq))
     R, d = x.shape
@@ -53,7 +58,11 @@ def emulate(P, x, kq, vp, gt, props, gtb, K, box_w=(10.0, 10.0, 5.0, 5.0), beta=
     zpre = xh * b["gamma"] + b["beta"]
     z = torch.relu(zpre)
     zd = rb(z)
-    logits = zd @ W["Wc"].t() + b["bc"]
+    if cross:
+        av = rb(torch.relu(zd @ W["Wo"].t() + b["bo"]))
+        logits = av @ W["T"].t()
+    else:
+        logits = zd @ W["Wc"].t() + b["bc"]
     deltas = xb @ W["Wb"].t() + b["bb"]
     C1 = K + 1
     gt = gt.to(torch.int64)
@@ -69,6 +78,8 @@ def emulate(P, x, kq, vp, gt, props, gtb, K, box_w=(10.0, 10.0, 5.0, 5.0), beta=
     lb = n if beta < 1e-5 else torch.where(n < beta, 0.5 * n * n / beta, n - 0.5 * beta)
     loss_box = (lb * fg[:, None]).sum() / R
     losses = {"loss_cls": loss_cls, "loss_box_reg": loss_box, "loss_attentive": loss_att}
+    if cross:
+        losses.pop("loss_attentive")
     # ---- backward of sum(losses) -----------------------------------------------------------------------------------
     onehot = torch.zeros(R, C1, dtype=D, device=x.device)
     onehot[ar, gt] = 1
@@ -81,9 +92,14 @@ def emulate(P, x, kq, vp, gt, props, gtb, K, box_w=(10.0, 10.0, 5.0, 5.0), beta=
     oh_att[ar, gt] = 1
     dattn_ext = wts[2] * (torch.softmax(attn, 1) - oh_att) / R
     G = {}
-    G["Wc"], G["bc"] = dlogits.t() @ zd, dlogits.sum(0)
+    if cross:
+        da = rb((dlogits @ W["T"]) * (av > 0))
+        G["Wo"], G["bo"] = da.t() @ zd, da.sum(0)
+        dzd = rb(da @ W["Wo"])
+    else:
+        G["Wc"], G["bc"] = dlogits.t() @ zd, dlogits.sum(0)
+        dzd = rb(dlogits @ W["Wc"])
     G["Wb"], G["bb"] = ddeltas.t() @ xb, ddeltas.sum(0)
-    dzd = rb(dlogits @ W["Wc"])
     dx = ddeltas @ W["Wb"]
     dz = dzd * (zpre > 0)
     G["gamma"], G["beta"] = (dz * xh).sum(0), dz.sum(0)

@@ -142,6 +142,22 @@ def batched_nms(boxes, scores, idxs, thr):
     return torch.from_numpy(keep[:nk].copy())
 
 
+def batched_nms_detectron2(boxes, scores, idxs, thr):
+    """detectron2 v0.3 `layers.nms.batched_nms` as called from fast_rcnn.py:125: the coordinate-offset trick below 40 000
+    boxes (`batched_nms` above), and from 40 000 boxes on per-class NMS on the un-offset boxes, survivors ordered by score
+    (descending; the reference's argsort is unstable, so ties between survivors are only defined here: lower index first)."""
+    n = int(torch.as_tensor(boxes).shape[0])
+    if n < 40000:
+        return batched_nms(boxes, scores, idxs, thr)
+    b, s, c = torch.as_tensor(boxes).float(), torch.as_tensor(scores).float(), torch.as_tensor(idxs).long()
+    kept = []
+    for k in torch.unique(c).tolist():
+        m = torch.nonzero(c == k).view(-1)
+        kept.append(m[nms(b[m], s[m], thr)])
+    keep = torch.sort(torch.cat(kept)).values
+    return keep[torch.sort(s[keep], descending=True, stable=True).indices]
+
+
 def fast_rcnn_inference_single_image(boxes, probs, image_shape, score_thresh=0.05, nms_thresh=0.5,
                                      topk=100):
     """boxes (R,4K) decoded/unclipped, probs (R,K+1).  Returns dict(boxes, scores, classes, roi_inds,

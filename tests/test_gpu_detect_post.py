@@ -88,6 +88,22 @@ def test_batched_nms_vs_oracle(n, ncls, seed):
     assert torch.equal(keep.cpu(), ref)
 
 
+@pytest.mark.parametrize("n,ncls,seed", [(39999, 80, 11), (40000, 80, 12), (45000, 20, 13)])
+def test_batched_nms_around_the_40000_box_rule(n, ncls, seed):
+    """detectron2 v0.3's batched_nms changes algorithm at 40 000 boxes (fast_rcnn.py:125 -> layers/nms.py): coordinate
+    trick below, per-class NMS on the un-offset boxes from there on.  Keep indices bit-exact on both sides of the rule,
+    at 80 classes (BASELINE configs[2] / [4])."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(seed)
+    boxes, _ = synth_proposals(n, 600, 800, gen, n_obj=12)
+    scores = torch.rand(n, generator=gen)
+    boxes[300:340] = boxes[200:240]              # identical boxes
+    idxs = torch.randint(0, ncls, (n,), generator=gen)
+    ref = O.batched_nms_detectron2(boxes, scores, idxs, 0.5)
+    keep = ops.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.5)
+    assert torch.equal(keep.cpu(), ref)
+
+
 def test_batched_nms_empty_and_multi_segment():
     from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
     assert ops.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), 0.5).numel() == 0

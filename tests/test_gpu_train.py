@@ -164,6 +164,77 @@ def test_fused_train_step_gradients_vs_bf16_operand_restatement(golden):
     assert a[4] == R and a[1] == int(((gt >= 0) & (gt < K)).sum()) and 0 <= a[2] <= a[0] <= R
 
 
+def test_cross_output_head_trains_on_the_fused_node():
+    """SematicRes5ROIHeadsCrossOutput in train mode (SURVEY row C1': logits = relu(output_projection(sim2stext)) . T^T,
+    roi_heads.py:1154-1171 + fast_rcnn.py:462-476) through the Detectron2-style forward on the fused kernels: losses
+    against the differentiable torch expression of the same head, every gradient (dL/dx, dKq, dVp, the 14 attention / box
+    parameters and output_projection) against the bf16-operand restatement at 2e-2."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling, train_ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import Boxes, Instances, ShapeSpec
+    from oracle.emulate_head import emulate
+    from oracle.gen_golden import synth_proposals
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME, cfg.MODEL.ROI_HEADS.OUTPUT_LAYER = "SematicRes5ROIHeadsCrossOutput", "FastRCNNAttentionOutputLayers"
+    cfg.MODEL.ADDITION.NAME = "clip"
+    cfg.MODEL.ROI_BOX_HEAD.SMOOTH_L1_BETA = 0.5
+    torch.manual_seed(5)
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=1024, stride=16)}).cuda().train()
+    with torch.no_grad():
+        m.output_projection.weight.mul_(30.0)
+        m.box_predictor.bbox_pred.weight.mul_(50.0)
+    assert m._fused_train_path()
+    gen = torch.Generator().manual_seed(6)
+    R, K = 512, 20
+    b, _ = synth_proposals(R, 600, 800, gen)
+    inst = Instances((600, 800))
+    inst.proposal_boxes = Boxes(b.cuda())
+    gtb = b + torch.randn(R, 4, generator=gen) * 4
+    gtb[:, 2:] = torch.maximum(gtb[:, 2:], gtb[:, :2] + 2)
+    inst.gt_boxes = Boxes(gtb.cuda())
+    gt = torch.randint(0, K + 1, (R,), generator=gen)
+    gt[R // 4:] = K
+    inst.gt_classes = gt.cuda()
+    x0 = torch.relu(torch.randn(R, 2048, generator=gen)).cuda()
+    # fused node
+    sa, pred = m.attention.attention, m.box_predictor
+    kq, vp = train_ops.text_side(m.attention)
+    kq.retain_grad()
+    vp.retain_grad()
+    x = x0.clone().requires_grad_(True)
+    text = m.attention.forward_language_model()["text_feat"]
+    losses, logits, acc = train_ops.fused_head_train(x, kq, vp, sa, pred, inst.gt_classes, inst.proposal_boxes.tensor, inst.gt_boxes.tensor,
+                                                     K, m.box2box_transform.weights, 0.5, 0.0, 1, False, None, None, None,
+                                                     (m.output_projection, text))
+    m.zero_grad(set_to_none=True)
+    (losses[0] + losses[1]).backward()
+    assert pred.cls_score.weight.grad is None                      # not part of this head's graph
+    P = dict(W1=sa.linear1[0].weight, b1=sa.linear1[0].bias, W2=sa.linear2[0].weight, b2=sa.linear2[0].bias,
+             W3=sa.linear3.weight, b3=sa.linear3.bias, Wf1=sa.ffn.linear1.weight, bf1=sa.ffn.linear1.bias,
+             Wf2=sa.ffn.linear2.weight, bf2=sa.ffn.linear2.bias, gamma=sa.ffn.norm3.weight, beta=sa.ffn.norm3.bias,
+             Wb=pred.bbox_pred.weight, bb=pred.bbox_pred.bias, Wo=m.output_projection.weight, bo=m.output_projection.bias, T=text)
+    L, G = emulate(P, x0, kq, vp, inst.gt_classes, inst.proposal_boxes.tensor, inst.gt_boxes.tensor, K, m.box2box_transform.weights, 0.5)
+    assert set(L) == {"loss_cls", "loss_box_reg"}
+    assert abs(float(losses[0]) - float(L["loss_cls"])) <= 2e-3 * abs(float(L["loss_cls"])) + 1e-6
+    assert abs(float(losses[1]) - float(L["loss_box_reg"])) <= 2e-3 * abs(float(L["loss_box_reg"])) + 1e-6
+    got = dict(x=x.grad, kq=kq.grad, vp=vp.grad, **{k: v.grad for k, v in P.items() if k != "T"})
+    errs = {k: float((got[k].double().reshape(ref.shape) - ref).norm() / ref.norm().clamp_min(1e-30)) for k, ref in G.items() if not k.startswith("_")}
+    # dL/dx sits behind the LayerNorm backward, which amplifies the bf16-level differences of its input about tenfold
+    # (see _fused_vs_restatement): measured 2.4e-2 here, every other tensor <= 6e-3
+    assert len(errs) == 19 and max(v for k, v in errs.items() if k != "x") <= 2e-2 and errs["x"] <= 3e-2, errs
+    # through the Detectron2-style forward, against the torch expression of the same head
+    m.zero_grad(set_to_none=True)
+    xf = x0.clone().requires_grad_(True)
+    with torch.enable_grad():
+        out_f, _ = m.fused_train_losses(xf, [inst], inst.gt_classes)
+    m.fused_training = False
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads.fast_rcnn import FastRCNNOutputs
+    att_out, _ = m.forward_att(x0.clone().requires_grad_(True), inst.gt_classes)
+    ref_l = FastRCNNOutputs(m.box2box_transform, att_out["pred_logits"], att_out["pred_bbox"], [inst], 0.5).losses()
+    assert set(out_f) == {"loss_cls", "loss_box_reg"}
+    for k in ref_l:
+        assert abs(float(out_f[k]) - float(ref_l[k])) <= 2e-2 * abs(float(ref_l[k])) + 1e-4, (k, float(out_f[k]), float(ref_l[k]))
+
+
 def test_fused_train_step_is_deterministic_and_matches_torch_path(golden):
     """Bitwise run-to-run reproducibility (ordered reductions, no atomics) and agreement with the differentiable torch
     expression of the same head (fp32 library GEMMs) on the same device."""
