@@ -8,9 +8,11 @@ These modules are *teachers*: they consume ground-truth labels (the text key of 
 class), so they only run while training or in the reference's test-with-GT mode, and their key set is per-ROI: the
 attention matrix is (R, R+1) over the ROIs of the local batch.  With autograd on (the teacher itself is being trained)
 they run as differentiable torch expressions on the GPU, sharing `SingleHeadSiameseAttention` with the student path.
-Without autograd — the frozen teacher of student training, test-with-GT — `LV_attention` / `LV_attention_VKV` take the
-fused path `ops.teacher_attention_forward`: ROIs of one class share their key, so the dense attention collapses to a
-(K+2)-key attention (logit + log n_c, per-class mean values) and runs on the student's tcgen05 / fused kernels.
+Without autograd — the frozen teacher of student training, test-with-GT — all four variants take a fused path
+(`ops.teacher_attention_forward`, `ops.text_domination_forward`): ROIs of one class share their key, so the dense
+attention collapses to a (K+2)-key attention (logit + log n_c, per-class mean values) and runs on the tcgen05 GEMM /
+fused kernels; the 300-d `textDomination` variants keep their operands in 304-wide buffers (TMA row pitch), the products
+still contract over exactly 300 columns.
 
 Where the checked-in reference is broken (`LV_attention_VKV.forward` calls
 `forward_language_model(visual_feat, text)` against a one-argument signature and concatenates a 2-d with a 3-d
@@ -53,7 +55,7 @@ class LV_attention(nn.Module):
             _init_parameters(self.attention, 0.02)
 
     def _apply(self, fn, *a, **k):
-        super()._apply(fn, *a, **k)
+        nn.Module._apply(self, fn, *a, **k)          # explicit base: LV_attention_textDomination borrows this method
         self.embed = fn(self.embed)
         return self
 
@@ -138,14 +140,32 @@ class LV_attention_textDomination(nn.Module):
         value = F.relu(self.proj_value(torch.cat([v300[None, :], t], dim=2)))
         return loss, output, v300[None, :], F.relu(t), value
 
+    _vkv = False
+
+    def _frozen_forward(self, visual_feat, text):
+        """Forward without autograd (frozen teacher while the student trains, test-with-GT): the class-collapsed path on the
+        tensor-core GEMM, ops.text_domination_forward."""
+        if not hasattr(self, "_plan"):
+            self._plan = ops.TextDominationWeights()
+        named = {k: v for k, v in self.named_parameters() if not k.startswith(("mlp_adapter", "proj_k"))}
+        w = self._plan.refresh(named, (self.embed,))
+        out = ops.text_domination_forward(visual_feat, text, w, self._vkv)
+        return {}, {"text_feat": w["table"][text][None, :], "sim2stext": out[None, :]}
+
     def forward(self, visual_feat, text, num_preds_per_image=None):
+        if visual_feat.is_cuda and not torch.is_grad_enabled():
+            return self._frozen_forward(visual_feat, text)
         loss, output, q, k, v = self._qkv(visual_feat, text)
         output["sim2stext"] = self.proj2(F.relu(self.attention(q=q, k=k, v=v)[0]))
         return loss, output
 
 
 class LV_attention_textDomination_VKV(LV_attention_textDomination):
+    _vkv = True
+
     def forward(self, visual_feat, text, num_preds_per_image=None):
+        if visual_feat.is_cuda and not torch.is_grad_enabled():
+            return self._frozen_forward(visual_feat, text)
         loss, output, q, k, v = self._qkv(visual_feat, text)
         output["sim2stext"] = self.proj2(F.relu(self.attention(q=v, k=k, v=v)[0]))
         return loss, output

@@ -894,3 +894,116 @@ def teacher_attention_forward(x, labels, w, vkv):
     wt["vp"] = vp
     z, zb, _, _ = text_fusion_forward(val if vkv else x, wt, True, score_bias=bias)
     return z, zb
+
+
+# ---------------------------------------------------------------------------------------------------
+# A7: LV_attention_textDomination(_VKV), forward direction — attentive_modules.py:490-687
+# ---------------------------------------------------------------------------------------------------
+def _pad_cols(t, ld):
+    """(rows, cols) -> bf16 buffer with row pitch ld (zeros in the pitch padding), viewed as (rows, cols)."""
+    out = torch.zeros((t.shape[0], ld), dtype=torch.bfloat16, device=t.device)
+    out[:, : t.shape[1]].copy_(t.detach())
+    return out[:, : t.shape[1]]
+
+
+class TextDominationWeights:
+    """bf16 operand copies of an LV_attention_textDomination(_VKV) module for the CTA-pair GEMM.  The attention runs in the
+    300-d GloVe space: 300 and its half 150 are not multiples of 8 elements, which TMA needs for a row pitch, so every
+    300-wide operand lives in a buffer of pitch 304 and the [o1 | o2 | q] concatenation in one of pitch 608 with the three
+    blocks at columns 0, 152, 304 — the GEMMs still contract over exactly 300 / 150 columns (or over 604 with zero weight
+    columns under the two-column gaps), so nothing is approximated.  Cached like TextFusionWeights."""
+
+    def __init__(self):
+        self.key, self.w = None, {}
+
+    def refresh(self, named, text_parts):
+        params = [named[k] for k in sorted(named)] + list(text_parts)
+        key = TextFusionWeights._version(params)
+        if key == self.key:
+            return self.w
+        f32 = lambda t: t.detach().float().contiguous()
+        a = lambda n: named["attention." + n]
+        d = a("w_q.weight").shape[0]                      # 300
+        h = d // 2
+        dp, hp = (d + 7) // 8 * 8, (h + 7) // 8 * 8
+        w = dict(d=d, h=h, dp=dp, hp=hp)
+        w["proj_visual.weight"], w["proj_visual.bias"] = named["proj_visual.weight"].detach().to(torch.bfloat16).contiguous(), f32(named["proj_visual.bias"])
+        w["proj2.weight"], w["proj2.bias"] = _pad_cols(named["proj2.weight"], dp), f32(named["proj2.bias"])
+        pv = named["proj_value.weight"].detach()                                   # (d, 2d): [v300 | t]
+        pvp = torch.zeros((d, 2 * dp), dtype=torch.bfloat16, device=pv.device)
+        pvp[:, :d].copy_(pv[:, :d])
+        pvp[:, dp:dp + d].copy_(pv[:, d:])
+        w["proj_value.weight"], w["proj_value.bias"] = pvp[:, : dp + d], f32(named["proj_value.bias"])
+        w["linear1.weight"], w["linear1.bias"] = _pad_cols(a("linear1.0.weight"), dp), f32(a("linear1.0.bias"))
+        w["linear2.weight"], w["linear2.bias"] = _pad_cols(a("linear2.0.weight"), dp), f32(a("linear2.0.bias"))
+        l3 = a("linear3.weight").detach()                                          # (d, 2d): [o1 | o2 | q]
+        l3p = torch.zeros((d, 2 * dp), dtype=torch.bfloat16, device=l3.device)
+        l3p[:, :h].copy_(l3[:, :h])
+        l3p[:, hp:hp + h].copy_(l3[:, h:d])
+        l3p[:, 2 * hp:2 * hp + d].copy_(l3[:, d:])
+        w["linear3.weight"], w["linear3.bias"] = l3p[:, : 2 * hp + d], f32(a("linear3.bias"))
+        w["ffn1.weight"], w["ffn1.bias"] = _pad_cols(a("ffn.linear1.weight"), dp), f32(a("ffn.linear1.bias"))
+        f = a("ffn.linear2.weight").shape[1]                                       # d_ffn = 1024
+        w["ffn2.weight"], w["ffn2.bias"] = _pad_cols(a("ffn.linear2.weight"), (f + 7) // 8 * 8), f32(a("ffn.linear2.bias"))
+        w["gamma"], w["beta"] = f32(a("ffn.norm3.weight")), f32(a("ffn.norm3.bias"))
+        w["w_v"] = f32(a("w_v.weight"))
+        # label-independent text side: K+1 class rows (raw GloVe rows + w_bg), keys through w_k, dummy key, folded query
+        table = torch.cat([f32(text_parts[0]), f32(named["w_bg"])], 0).contiguous()
+        w["table"] = table
+        kp = torch.cat([torch.relu(table) @ f32(a("w_k.weight")).t(), f32(a("dummy")).reshape(1, -1)], 0)
+        w["kq"] = _pad_cols((kp @ f32(a("w_q.weight"))) / math.sqrt(d), dp)
+        self.key, self.w = key, w
+        return w
+
+
+def text_domination_forward(x, labels, w, vkv):
+    """LV_attention_textDomination (vkv=False) / ..._VKV (vkv=True) forward on the device, no autograd
+    (attentive_modules.py:597-634, :650-687): the visual feature is projected into the 300-d text space, attends there
+    over one key / value per ROI of the batch, and is projected back (proj2).  The same class-collapse identity as
+    `teacher_attention_forward` turns the (R, R+1) attention into a (K+2)-key one; every product runs on `b200_gemm2`.
+    x (R, C) fp32 pooled features, labels (R,) int64 in [0, K].  Returns sim2stext (R, C) fp32."""
+    _require_cuda(x, labels)
+    x = x.float().contiguous()
+    labels = labels.to(torch.int64).contiguous()
+    R, C = x.shape
+    d, h, dp, hp = w["d"], w["h"], w["dp"], w["hp"]
+    dev = x.device
+    f32z = lambda n: torch.zeros((R, n), dtype=torch.float32, device=dev)
+    bf16z = lambda n: torch.zeros((R, n), dtype=torch.bfloat16, device=dev)
+    xb = torch.empty((R, C), dtype=torch.bfloat16, device=dev)
+    cast_bf16_into(x, xb)
+    # v300 = proj_visual(x): fp32 (query / residual operand of the attention kernel, pitch dp) + bf16 into [v300 | t]
+    cat = bf16z(2 * dp)
+    v300 = f32z(dp)
+    gemm2(xb, w["proj_visual.weight"], bias=w["proj_visual.bias"], out=cat[:, :d], out_f32=v300[:, :d])
+    gather_rows_bf16(w["table"], labels, cat[:, dp:dp + d])
+    val = f32z(dp)
+    valb = gemm2(cat[:, : dp + d], w["proj_value.weight"], bias=w["proj_value.bias"], relu=True, out=bf16z(dp)[:, :d], out_f32=val[:, :d])
+    ncls = w["table"].shape[0]
+    vmean, counts = class_mean_rows(val[:, :d].contiguous(), labels, ncls)
+    vp = torch.zeros((ncls + 1, dp), dtype=torch.float32, device=dev)
+    vp[:ncls, :d] = vmean @ w["w_v"].t()
+    bias = torch.cat([torch.where(counts > 0, torch.log(counts.clamp(min=1.0)), counts.new_full((), -1e30)),
+                      counts.new_zeros(1)]).contiguous()
+    q32, qb = (val, valb) if vkv else (v300, cat[:, :d])
+    L = ncls + 1
+    S = torch.empty((R, L), dtype=torch.float32, device=dev)
+    gemm2(qb, w["kq"], bias=bias, out_f32=S, want_out=False)                     # scores + log n_c
+    p1, p2 = bf16z(dp), bf16z(dp)
+    text_attention(None, q32, None, vp, p1, p2, scores=S)                         # d = dp: the pitch padding stays zero
+    xcat = bf16z(2 * dp)
+    gemm2(p1[:, :d], w["linear1.weight"], bias=w["linear1.bias"], relu=True, out=xcat[:, :h])
+    gemm2(p2[:, :d], w["linear2.weight"], bias=w["linear2.bias"], relu=True, out=xcat[:, hp:hp + h])
+    xcat[:, 2 * hp:2 * hp + d].copy_(qb)
+    y = torch.empty((R, d), dtype=torch.float32, device=dev)
+    yb = gemm2(xcat[:, : 2 * hp + d], w["linear3.weight"], bias=w["linear3.bias"], out=bf16z(dp)[:, :d], out_f32=y)
+    f = w["ffn2.weight"].shape[1]
+    hdn = gemm2(yb, w["ffn1.weight"], bias=w["ffn1.bias"], relu=True, out=bf16z((f + 7) // 8 * 8)[:, :f])
+    y2 = torch.empty((R, d), dtype=torch.float32, device=dev)
+    gemm2(hdn, w["ffn2.weight"], bias=w["ffn2.bias"], out_f32=y2, want_out=False)
+    z, _ = residual_layernorm(y, y2, w["gamma"], w["beta"], 1e-5, relu=True, want_f32=True, want_bf16=False)
+    zb = bf16z(dp)[:, :d]
+    cast_bf16_into(z, zb)
+    out = torch.empty((R, C), dtype=torch.float32, device=dev)
+    gemm2(zb, w["proj2.weight"], bias=w["proj2.bias"], out_f32=out, want_out=False)
+    return out

@@ -190,6 +190,7 @@ def test_teacher_vkv_variants_run_and_differ():
         torch.manual_seed(1)
         b = getattr(RH, vkv)(32, cfg=cfg)
         b.load_state_dict(a.state_dict())
+        assert a.float() is a and a.embed.dtype == torch.float32         # Module._apply reaches the embedding table too
         ya, yb = a(x, lab)[1]["sim2stext"], b(x, lab)[1]["sim2stext"]
         assert ya.shape == yb.shape == (1, 10, 32) and not torch.allclose(ya, yb)
         yb.sum().backward()

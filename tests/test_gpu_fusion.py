@@ -258,6 +258,63 @@ def test_teacher_attention_fused_forward_vs_dense_torch(cls_name, R, d, K):
     torch.testing.assert_close(out["text_feat"], ref["text_feat"].detach(), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("cls_name", ["LV_attention_textDomination", "LV_attention_textDomination_VKV"])
+@pytest.mark.parametrize("R,d,K", [(1024, 2048, 20), (203, 256, 7), (640, 512, 80)])
+def test_text_domination_fused_forward_vs_dense_torch(cls_name, R, d, K):
+    """A7: the 300-d text-space teachers on the CTA-pair GEMM (operands in pitch-304 / 608 buffers, contraction over
+    exactly 300 / 150 columns) vs the module's dense fp32 torch expression (attentive_modules.py:597-634 / :650-687),
+    bf16 bar 2e-2, sharpened softmax, one class absent."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling.roi_heads import teacher_modules as tm
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    torch.manual_seed(4)
+    gen = torch.Generator().manual_seed(6)
+    embed = torch.randn(K, 300, generator=gen)
+    cfg = config.get_cfg()
+    cfg.MODEL.ADDITION.NAME = "glove"
+    m = getattr(tm, cls_name)(d, cfg=cfg, class_embed=embed).cuda().eval()
+    with torch.no_grad():
+        m.attention.w_q.weight.mul_(10.0)
+        m.attention.w_k.weight.mul_(10.0)
+    x = torch.relu(torch.randn(R, d, generator=gen)).cuda()
+    labels = torch.randint(0, K, (R,), generator=gen)
+    labels[torch.rand(R, generator=gen) < 0.6] = K
+    labels[labels == 2] = 3
+    labels = labels.cuda()
+    with torch.enable_grad():
+        _, ref = m(x, labels)
+    with torch.no_grad():
+        _, out = m(x, labels)
+    got, want = out["sim2stext"], ref["sim2stext"].detach()
+    assert got.shape == want.shape == (1, R, d)
+    want0 = ref["sim2stext"].detach()
+    assert float((want0 - want0.mean(1, keepdim=True)).abs().max()) > 1e-3   # rows differ: the attention matters
+    rel = float((got - want).norm() / want.norm())
+    assert rel < 2e-2, rel
+    torch.testing.assert_close(out["text_feat"], ref["text_feat"].detach(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,name", [("lv", "LV_attention"), ("td", "LV_attention_textDomination")])
+def test_teacher_fused_forward_matches_reference_golden(golden, tag, name):
+    """The frozen-teacher kernel path against the REFERENCE's own forward (tests/golden/teacher.npz, generated by importing
+    the reference; weights replayed by seed), bf16 bar 2e-2."""
+    import numpy as np
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling import roi_heads as RH
+    from oracle.gen_golden import seeded_fill
+    g = golden("teacher")
+    cfg = config.get_cfg()
+    cfg.MODEL.ADDITION.NAME = "glove"
+    m = getattr(RH, name)(32, cfg=cfg, class_embed=torch.from_numpy(g[tag + "_embed"])).eval()
+    seeded_fill(m, 77)
+    m = m.cuda()
+    with torch.no_grad():
+        _, out = m(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["lab"]).cuda())
+    want = torch.from_numpy(np.asarray(g[tag + "_sim2stext"])).cuda()
+    got = out["sim2stext"].reshape(want.shape)
+    rel = float((got - want).norm() / want.norm())
+    assert rel < 2e-2, rel
+
+
 def test_class_mean_rows_and_gather_rows():
     from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
     gen = torch.Generator().manual_seed(8)
