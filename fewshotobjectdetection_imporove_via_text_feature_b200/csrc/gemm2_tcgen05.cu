@@ -348,7 +348,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         if (col0 >= p.N) continue;                           // warp-uniform: chunk entirely beyond N
         if (f_store) {                                       // staging buffer gc & 1 was last read by the store of chunk gc - 2
-          if (lane == 0) tma_store_wait_read<1>();
+          if (lane == 0) {
+            if (f_mean) tma_store_wait_read<0>();            // the mean's scratch is the other buffer
+            else tma_store_wait_read<1>();
+          }
           __syncwarp();
         }
 #pragma unroll
@@ -435,48 +438,34 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (kChunks == 2 && ci) bw[2 + h] = w; else bw[h] = w;
           }
           if (f_mean) {
-            // mean over the 16 rows (the 4x4 pixels) of each ROI: lanes 0-15 hold one ROI, lanes 16-31 the next.  Butterfly
-            // reduce-scatter: at distance 8, 4, 2, 1 a lane keeps one half of its columns and adds the partner's copy of
-            // them, so 30 shuffles leave lane l (of 16) with the sums of columns 2l and 2l + 1.
-            float u[16];
-            {
-              const bool up = lane & 8;
+            // mean over the 16 rows (the 4x4 pixels) of each ROI: lanes 0-15 hold one ROI, lanes 16-31 the next.  The warp's
+            // 32 x 32 fp32 block goes through an output staging box (box h when nothing is stored; with a store, the box the
+            // store of this chunk does not use — the chunk then starts by waiting for every earlier store's read), 16-byte
+            // units XOR-swizzled by the row so that both the row writes and the column reads are conflict-free; lane l then
+            // sums columns 2l', 2l'+1 (l' = l & 15) over its ROI's 16 rows in row order — 8 STS.128 + 16 LDS.64 + 32 FADD per
+            // lane instead of a 30-shuffle butterfly.
+            const uint32_t mbase = s_out + (f_store ? ((gc & 1) ^ 1) : h) * kG2BoxBytes;
+            __syncwarp();                                     // the previous use of this box (chunk gc - 1) has been read
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-            }
-            {
-              const bool up = lane & 4;
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mbase + row_off + ((j ^ swz) << 4)),
+                           "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+            __syncwarp();
+            const int l15 = lane & 15;
+            const uint32_t rbase = mbase + (uint32_t)(lane & 16) * 128 + (uint32_t)(lane & 1) * 8;
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float send = up ? u[i] : u[i + 8], keep = up ? u[i + 8] : u[i];
-                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-            }
-            {
-              const bool up = lane & 2;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float send = up ? u[i] : u[i + 4], keep = up ? u[i + 4] : u[i];
-                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-              }
-            }
-            {
-              const bool up = lane & 1;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const float send = up ? u[i] : u[i + 2], keep = up ? u[i + 2] : u[i];
-                u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-              }
+            for (int rr = 0; rr < 16; ++rr) {
+              float a0, a1;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0), "=f"(a1) : "r"(rbase + rr * 128 + ((((l15 >> 1) ^ (rr & 7))) << 4)));
+              s0 += a0; s1 += a1;
             }
             const int roi = ((m0 + q * 32) >> 4) + (lane >> 4);
-            const int cc = col + 2 * (lane & 15);
+            const int cc = col + 2 * l15;
             if (roi * 16 < p.M) {
               float* dst = p.rowmean_out + (size_t)roi * p.ld_rowmean + cc;
-              if (cc < p.N) dst[0] = u[0] * (1.f / 16.f);
-              if (cc + 1 < p.N) dst[1] = u[1] * (1.f / 16.f);
+              if (cc < p.N) dst[0] = s0 * (1.f / 16.f);
+              if (cc + 1 < p.N) dst[1] = s1 * (1.f / 16.f);
             }
           }
           if (f_store) {
