@@ -817,7 +817,7 @@ def main():
         else:
             line["nms_us_per_image"] = 1e3 * stage_ms["decode_nms"] / B
             line["detections_per_image"] = n_det
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only: at N > 1 the other ranks would spin on the barrier meanwhile
             try:
                 line["cpu_baseline"] = run_cpu_baseline(args)
             except Exception as ex:  # noqa: BLE001

@@ -51,7 +51,7 @@ SIGNATURES = {
     "b200_softmax_decode_compact_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b200_softmax_decode_compact": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_void_p] * 6 + [c_int, c_void_p, c_size_t, c_void_p]),
     "b200_batched_nms_workspace_bytes": (c_size_t, [c_int] * 3),
-    "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
+    "b200_batched_nms": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int, c_int] + [c_void_p] * 2 + [c_void_p, c_size_t, c_void_p]),
     "b200_gather_detections": (c_int, [c_void_p] * 7 + [c_int] * 2 + [c_void_p] * 4 + [c_void_p]),
     "b200_pcb_cosine_blend": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float] * 3 + [c_void_p]),
     "b200_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int] + [c_int] * 4 + [c_void_p]),

@@ -291,7 +291,12 @@ nms_prepare_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ 
 }
 
 constexpr int kNmsThreads = 256;
-constexpr int kNmsSmemBoxes = 4096;  // per (class, image) handled fully in shared memory; larger -> global path
+constexpr int kNmsSmemBoxes = 4096;  // per (class, image) handled fully in shared memory by the 256-thread kernel
+// Larger slices (one class taking most of an image's 4096-8192 proposals: the BASELINE configs[4] sweep with an untrained
+// classifier) go to a second instantiation: 1024 threads, 8192 boxes x 24 B + bitmap = 197 KB of shared memory, so the
+// bitonic sort and the sweep stay on chip; beyond that the global-memory path of the same kernel.
+constexpr int kNmsBigBoxes = 8192;
+constexpr int kNmsBigThreads = 1024;
 // PRESORTED variant (RPN proposal selection, rpn_select.cu): the candidates of a class already arrive in
 // (score desc, index asc) order, so no keys are built or sorted and shared memory holds boxes + bitmap only:
 // 12288 boxes x 16 B + 1.5 KB = 198 KB, one 1024-thread CTA per (level, image).
@@ -299,13 +304,13 @@ constexpr int kNmsPresortedBoxes = 12288;
 constexpr int kNmsPresortedThreads = 1024;
 constexpr int kNmsCluster = 8;       // portable cluster size
 
-template <int THREADS, bool PRESORTED>
+template <int THREADS, bool PRESORTED, int CAP>
 __global__ void __launch_bounds__(THREADS)
 nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
                  const int32_t* __restrict__ seg_offsets, int num_classes, float thr,
                  const float* __restrict__ max1, const int32_t* __restrict__ class_start,
                  const int32_t* __restrict__ order, unsigned long long* __restrict__ kept,
-                 unsigned long long* __restrict__ scratch, int max_keep, int skip_upto) {
+                 unsigned long long* __restrict__ scratch, int max_keep, int skip_upto, int skip_above) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keep64;
@@ -313,7 +318,8 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   const int base = seg_offsets[img];
   const int cs = class_start[(size_t)img * (num_classes + 1) + c];
   const int m = class_start[(size_t)img * (num_classes + 1) + c + 1] - cs;
-  if (m == 0 || m <= skip_upto) return;                     // slices up to skip_upto belong to the cluster kernel
+  // slices up to skip_upto / above skip_above (> 0) belong to another launch of this call
+  if (m == 0 || m <= skip_upto || (skip_above > 0 && m > skip_above)) return;
   const float off = __fmul_rn((float)c, max1[img]);
   const int32_t* ord = order + base + cs;
   unsigned long long* kept_out = kept + base + cs;
@@ -323,7 +329,7 @@ nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     return;
   }
   const int m2 = next_pow2(m);
-  constexpr int kCap = PRESORTED ? kNmsPresortedBoxes : kNmsSmemBoxes;
+  constexpr int kCap = CAP;
   const bool in_smem = m <= kCap;
   unsigned long long* gslice = scratch + 4 * (size_t)(base + cs);  // 4*m u64 per class slice (host sizes scratch 4x)
   unsigned long long* keys = PRESORTED ? nullptr : (in_smem ? reinterpret_cast<unsigned long long*>(s_raw) : gslice);
@@ -742,7 +748,7 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
     // (not reachable from b200_rpn_select_proposals with pre_nms_topk <= 12288) on the single-CTA kernel's global path
     const size_t cls_smem = (size_t)kNmsPresortedBoxes * 16 + kNmsPresortedBoxes / 8;
     auto kc = nms_presorted_cluster_kernel<kNmsCluster>;
-    auto k = nms_class_kernel<kNmsPresortedThreads, true>;
+    auto k = nms_class_kernel<kNmsPresortedThreads, true, kNmsPresortedBoxes>;
     // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
     B200_CUDA_CALL(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
     B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
@@ -763,15 +769,28 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
     if ((max_slice_hint > 0 ? max_slice_hint : total_capacity) > kNmsPresortedBoxes)
       k<<<dim3(num_classes, N), kNmsPresortedThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh,
                                                                      w.max1, w.class_start, w.order, w.kept, w.scratch,
-                                                                     max_keep, kNmsPresortedBoxes);
+                                                                     max_keep, kNmsPresortedBoxes, 0);
   } else {
-    // keys (8 B) + shifted boxes (16 B) + removed bitmap
+    // keys (8 B) + shifted boxes (16 B) + removed bitmap.  A class slice cannot exceed max_slice_hint boxes (the image's ROI
+    // count, when the caller knows it): only then-possible large slices cost the second launch.
+    const int bound = max_slice_hint > 0 ? min(max_slice_hint, total_capacity) : total_capacity;
+    const bool big = bound > kNmsSmemBoxes;
     const size_t cls_smem = (size_t)kNmsSmemBoxes * 24 + kNmsSmemBoxes / 8;
-    auto k = nms_class_kernel<kNmsThreads, false>;
+    auto k = nms_class_kernel<kNmsThreads, false, kNmsSmemBoxes>;
     // set on every call: the attribute is per device and the call is cheap (no process-wide flag to race on)
     B200_CUDA_CALL(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cls_smem));
     k<<<dim3(num_classes, N), kNmsThreads, cls_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1,
-                                                          w.class_start, w.order, w.kept, w.scratch, max_keep, 0);
+                                                          w.class_start, w.order, w.kept, w.scratch, max_keep, 0,
+                                                          big ? kNmsSmemBoxes : 0);
+    if (big) {
+      B200_CUDA_LAUNCH_CHECK("nms_class");
+      const size_t big_smem = (size_t)kNmsBigBoxes * 24 + kNmsBigBoxes / 8;
+      auto kb = nms_class_kernel<kNmsBigThreads, false, kNmsBigBoxes>;
+      B200_CUDA_CALL(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
+      kb<<<dim3(num_classes, N), kNmsBigThreads, big_smem, st>>>(boxes, scores, seg_offsets, num_classes, iou_thresh, w.max1,
+                                                                w.class_start, w.order, w.kept, w.scratch, max_keep,
+                                                                kNmsSmemBoxes, 0);
+    }
   }
   B200_CUDA_LAUNCH_CHECK("nms_class");
   nms_finalize_kernel<<<N, 1024, 0, st>>>(seg_offsets, seg_count, w.kept, w.scratch, max_keep, keep, keep_count);
@@ -782,14 +801,15 @@ int run_batched_nms(const float* boxes, const float* scores, const int32_t* clas
 
 extern "C" int b200_batched_nms(const float* boxes, const float* scores, const int32_t* classes,
                                 const int32_t* seg_offsets, const int32_t* seg_count, int N, int total_capacity,
-                                int num_classes, float iou_thresh, int max_keep, int32_t* keep, int32_t* keep_count,
-                                void* workspace, size_t workspace_bytes, b200_stream_t stream) {
-  B200_CHECK_ARG(N >= 0 && total_capacity >= 0 && num_classes > 0 && num_classes <= kMaxClasses, "batched_nms: bad shape");
+                                int num_classes, float iou_thresh, int max_keep, int max_class_slice, int32_t* keep,
+                                int32_t* keep_count, void* workspace, size_t workspace_bytes, b200_stream_t stream) {
+  B200_CHECK_ARG(N >= 0 && total_capacity >= 0 && num_classes > 0 && num_classes <= kMaxClasses && max_class_slice >= 0,
+                 "batched_nms: bad shape");
   B200_CHECK_ARG(max_keep >= 0, "batched_nms: max_keep must be >= 0 (pass the capacity for 'all')");
   B200_CHECK_ARG(seg_offsets && seg_count && keep_count && (keep || max_keep == 0), "batched_nms: null tensor");
   if (N == 0) return B200_OK;
   return run_batched_nms(boxes, scores, classes, seg_offsets, seg_count, N, total_capacity, num_classes, iou_thresh,
-                         max_keep, keep, keep_count, workspace, workspace_bytes, false, 0, (cudaStream_t)stream);
+                         max_keep, keep, keep_count, workspace, workspace_bytes, false, max_class_slice, (cudaStream_t)stream);
 }
 
 extern "C" int b200_gather_detections(const float* cand_boxes, const float* cand_scores, const int32_t* cand_roi,

@@ -324,8 +324,9 @@ def softmax_decode_compact(scores, deltas, proposals, roi_offsets, image_hw, sco
                 seg_offsets=(roi_offsets * K).to(torch.int32), capacity=cap)
 
 
-def batched_nms_segments(boxes, scores, classes, seg_offsets, seg_count, num_classes, iou_thresh, max_keep):
-    """Device-side batched NMS over N segments; returns (keep (N,max_keep) int32 segment-relative, keep_count (N))."""
+def batched_nms_segments(boxes, scores, classes, seg_offsets, seg_count, num_classes, iou_thresh, max_keep, max_class_slice=0):
+    """Device-side batched NMS over N segments; returns (keep (N,max_keep) int32 segment-relative, keep_count (N)).
+    max_class_slice: host-side bound of one class's boxes in one segment (0 = unknown), see include/b200roi.h."""
     _require_cuda(boxes, scores, classes)
     N = seg_count.numel()
     cap = boxes.shape[0]
@@ -335,8 +336,8 @@ def batched_nms_segments(boxes, scores, classes, seg_offsets, seg_count, num_cla
     nbytes = _lib.lib().b200_batched_nms_workspace_bytes(N, cap, num_classes)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     _lib.call("b200_batched_nms", boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), seg_offsets.data_ptr(),
-              seg_count.data_ptr(), N, cap, num_classes, float(iou_thresh), int(max_keep), keep.data_ptr(), kc.data_ptr(),
-              ws.data_ptr(), nbytes, _stream())
+              seg_count.data_ptr(), N, cap, num_classes, float(iou_thresh), int(max_keep), int(max_class_slice),
+              keep.data_ptr(), kc.data_ptr(), ws.data_ptr(), nbytes, _stream())
     return keep[:N, :max_keep], kc[:N]
 
 
@@ -368,8 +369,10 @@ def fast_rcnn_inference_device(scores, deltas, proposals, roi_offsets, image_hw,
     K = scores.shape[1] - 1
     dev = scores.device
     topk = int(topk) if topk >= 0 else c["capacity"]
+    # a ROI yields at most one candidate per class: a class slice is bounded by the image's ROI count
+    slice_bound = int(max_rois_per_image) if max_rois_per_image else int(scores.shape[0])
     keep, kc = batched_nms_segments(c["cand_boxes"], c["cand_scores"], c["cand_cls"], c["seg_offsets"], c["cand_count"],
-                                    K, nms_thresh, topk)
+                                    K, nms_thresh, topk, max_class_slice=slice_bound)
     keep = keep.contiguous()
     ob = torch.empty((N, topk, 4), dtype=torch.float32, device=dev)
     os_ = torch.empty((N, topk), dtype=torch.float32, device=dev)

@@ -134,12 +134,15 @@ B200_API int b200_softmax_decode_compact(const float* scores_in, int input_is_pr
  *   segment start, ordered by descending score (ties: ascending index); keep_count (N).
  *   Bit-exact against the reference path for segments below 40000 boxes (above that detectron2 0.3
  *   switches to an un-offset per-class loop, which this kernel follows as well).
+ *   max_class_slice: an upper bound the caller knows for the boxes of ONE class in ONE segment (e.g. the image's ROI
+ *   count: a ROI yields at most one candidate per class), 0 = unknown (total_capacity is assumed).  It only decides
+ *   whether the launch for class slices above 4096 boxes (1024 threads, 197 KB shared memory) is issued at all.
  * ------------------------------------------------------------------------------------------------- */
 B200_API size_t b200_batched_nms_workspace_bytes(int N, int total_capacity, int num_classes);
 B200_API int b200_batched_nms(const float* boxes, const float* scores, const int32_t* classes,
                      const int32_t* seg_offsets, const int32_t* seg_count, int N, int total_capacity,
-                     int num_classes, float iou_thresh, int max_keep, int32_t* keep, int32_t* keep_count,
-                     void* workspace, size_t workspace_bytes, b200_stream_t stream);
+                     int num_classes, float iou_thresh, int max_keep, int max_class_slice, int32_t* keep,
+                     int32_t* keep_count, void* workspace, size_t workspace_bytes, b200_stream_t stream);
 
 /* gather kept candidates into padded detection tensors: boxes (N,max_keep,4), scores (N,max_keep),
  * classes / roi_inds (N,max_keep) int64 — fast_rcnn.py:128-134 */

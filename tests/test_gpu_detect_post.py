@@ -72,8 +72,11 @@ def test_golden_single_image_entry(golden, tag):
     assert torch.equal(res.pred_boxes.tensor.cpu(), T(g[tag + "_boxes"]))
 
 
-@pytest.mark.parametrize("n,ncls,seed", [(1, 1, 0), (2, 1, 1), (257, 5, 2), (3000, 20, 3), (9000, 80, 4), (6000, 1, 5)])
+@pytest.mark.parametrize("n,ncls,seed", [(1, 1, 0), (2, 1, 1), (257, 5, 2), (3000, 20, 3), (9000, 80, 4), (6000, 1, 5),
+                                         (4096, 1, 6), (4097, 1, 7), (8192, 1, 8), (8193, 1, 9), (20000, 3, 10)])
 def test_batched_nms_vs_oracle(n, ncls, seed):
+    """Class slices of every size class of the kernel: <= 4096 boxes (256-thread CTA, shared memory), 4097-8192 (1024-thread
+    CTA, 197 KB shared memory), above (global-memory path)."""
     from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
     gen = torch.Generator().manual_seed(seed)
     boxes, _ = synth_proposals(max(n, 8), 600, 800, gen, n_obj=6)
@@ -102,6 +105,37 @@ def test_batched_nms_around_the_40000_box_rule(n, ncls, seed):
     ref = O.batched_nms_detectron2(boxes, scores, idxs, 0.5)
     keep = ops.batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.5)
     assert torch.equal(keep.cpu(), ref)
+
+
+def test_one_class_takes_every_proposal_large_image():
+    """BASELINE configs[4] with an untrained classifier: one class passes the threshold on (nearly) all 8192 proposals of an
+    image, i.e. a single 8192-box class slice per image (the 1024-thread / 197 KB instantiation of the per-class kernel).
+    NMS bit-exact against the oracle on the kernel's own candidates, same result with and without the ROI-count hint."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    P, K, N = 8192, 20, 2
+    boxes = torch.cat([synth_proposals(P, 600, 800, gen, n_obj=8)[0] for _ in range(N)])
+    logits = torch.randn(N * P, K + 1, generator=gen) * 0.3
+    logits[:, 3] += 5.0                                   # class 3 wins everywhere
+    logits[::7, 11] += 4.5                                # a second class on every 7th proposal
+    deltas = torch.randn(N * P, 4 * K, generator=gen) * 0.3
+    offs = torch.arange(0, N * P + 1, P, dtype=torch.int32)
+    hw = torch.tensor([[600.0, 800.0]] * N)
+    outs = []
+    for hint in (P, None):
+        outs.append(ops.fast_rcnn_inference_device(logits.cuda(), deltas.cuda(), boxes.cuda(), offs.cuda(), hw.cuda(), 0.05, 0.5, 100,
+                                                   want_probs=True, max_rois_per_image=hint))
+    for k in ("boxes", "scores", "classes", "roi_inds", "counts", "keep"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    out, c = outs[0], outs[0]["cand"]
+    for i in range(N):
+        n = int(out["n_candidates"][i])
+        s0 = i * P * K
+        cc = c["cand_cls"][s0:s0 + n].cpu().long()
+        assert int((cc == 3).sum()) == P                   # the whole image in one class slice
+        ref = O.batched_nms(c["cand_boxes"][s0:s0 + n].cpu(), c["cand_scores"][s0:s0 + n].cpu(), cc, 0.5)[:100]
+        k = int(out["counts"][i])
+        assert k == len(ref) == 100 and torch.equal(out["keep"][i, :k].cpu().long(), ref)
 
 
 def test_batched_nms_empty_and_multi_segment():
