@@ -528,15 +528,23 @@ def replay_gemms(cases, dev, flush):
             if c["mact"]:
                 kw["mask_act"] = rnd(M, N)
             if c["out"]:
-                kw["out"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                kw["out"] = torch.empty(M, (N + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)[:, :N]
             if c["out2"]:
-                kw["out2"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+                kw["out2"] = torch.empty(M, (N + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)[:, :N]
             if c["f32"]:
                 kw["out_f32"] = torch.zeros(M, N, device=dev)
             if c["bout"]:
                 kw["bits_out"] = torch.empty(M, N // 32, dtype=torch.int32, device=dev)
             if c["mean"]:
                 kw["rowmean_out"] = torch.empty(M // 16, N, device=dev)
+            if c.get("ssq"):
+                kw["rowsumsq_out"] = torch.empty(M, (N + 63) // 64, device=dev)
+            if c.get("rscale"):
+                kw["row_scale_sumsq"] = torch.rand(M, c["rscale"], device=dev) + 0.5
+            if c.get("softmax"):
+                kw["softmax"] = True
+            if c.get("gate"):
+                kw["gate"] = True
             calls.append((ops.gemm2, (a, b), kw))
             flop += 2.0 * M * N * (K + K2)
         else:                                        # b200_gemm_bf16(_ex), single-CTA kernel

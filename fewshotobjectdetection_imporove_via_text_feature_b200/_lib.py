@@ -27,6 +27,9 @@ class Gemm2Desc(ctypes.Structure):
                 ("out_bf16", c_void_p), ("ld_out", c_int), ("out2_bf16", c_void_p), ("ld_out2", c_int),
                 ("out_f32", c_void_p), ("ld_out_f32", c_int), ("accumulate", c_int),
                 ("bits_out", c_void_p), ("ld_bits_out", c_int), ("rowmean_out", c_void_p), ("ld_rowmean", c_int),
+                ("rowsumsq_out", c_void_p), ("ld_rowsumsq", c_int),
+                ("row_scale_sumsq", c_void_p), ("ld_row_scale_sumsq", c_int), ("row_scale_parts", c_int), ("row_scale_eps", c_float),
+                ("softmax", c_int), ("gate", c_int),
                 ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int),
                 ("split_k", c_int), ("splitk_workspace", c_void_p), ("splitk_workspace_bytes", c_size_t)]
 

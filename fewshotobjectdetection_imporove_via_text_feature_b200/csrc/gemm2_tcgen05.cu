@@ -42,6 +42,12 @@ constexpr uint32_t kFFwd = kFRes | kFBitsOut;                  // res5 forward: 
 constexpr uint32_t kFFwdMean = kFRes | kFBitsOut | kFRowMean;  // ... last block: + mean over the 16 pixels
 constexpr uint32_t kFBwd = kFRes | kFMaskBits;                 // res5 backward: mask in, residual
 constexpr uint32_t kFAll = 127;
+// row-wise epilogues (one lane owns one output row, so these need no cross-lane traffic): sum of squares of a row's outputs,
+// a per-row scale from such sums (cosine logits: attentive / my_module.py:449-469 as the epilogue of the two products), softmax
+// over the row (attentive_modules.py:45-55 as the epilogue of the score product), gate operands O*x and x-O
+// (attentive_modules.py:166,170 as the epilogue of the probabilities x values product).  Their own instantiation.
+constexpr uint32_t kFRowSumSq = 128, kFRowScale = 256, kFSoftmax = 512, kFGate = 1024;
+constexpr uint32_t kFRow = kFRes | kFF32 | kFOut2 | kFRowSumSq | kFRowScale | kFSoftmax | kFGate;
 
 struct Gemm2Args {
   const float* bias;
@@ -56,6 +62,13 @@ struct Gemm2Args {
   int accumulate;
   float* rowmean_out;                // optional: mean over each group of 16 consecutive rows -> [M/16][ld_rowmean] fp32
   int ld_rowmean;
+  float* rowsumsq_out;               // optional: sum over each 64-column chunk of a row of the output's squares [M][ld_rowsumsq]
+  int ld_rowsumsq;
+  const float* row_sumsq_in;         // optional: per-row scale 1 / max(sqrt(sum of the row's row_parts entries), row_eps)
+  int ld_row_sumsq_in, row_parts;
+  float row_eps;
+  int softmax;                       // out = softmax over the row's N <= 128 columns of (acc + bias)
+  int gate;                          // residual operand is x: out = acc * x, out2 = x - acc
   int M, N;
   int kb1, kb2;                      // K blocks taken from A (map_a) and from A2 (map_a2)
   int conv_cb;                       // conv3x3 mode: K blocks per tap (C / 64); 0 = plain
@@ -221,6 +234,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool f_mean = (F & kFRowMean) && p.rowmean_out;
     const bool f_out2 = (F & kFOut2) && p.has_out2;
     const bool f_store = p.has_out || f_out2;
+    const bool f_ssq = (F & kFRowSumSq) && p.rowsumsq_out;
+    const bool f_rscale = (F & kFRowScale) && p.row_sumsq_in;
+    const bool f_softmax = (F & kFSoftmax) && p.softmax;
+    const bool f_gate = (F & kFGate) && p.gate;
     const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     const bool vec32 = f_f32 && (p.ldd32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.d_f32) & 15) == 0);
     const bool vecm = f_mact && (p.ldmask % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_act) & 15) == 0);
@@ -241,6 +258,12 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int buf = lt & 1;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
+      float rscale = 1.f;
+      if (f_rscale && row_ok) {
+        float ss = 0.f;
+        for (int j = 0; j < p.row_parts; ++j) ss += __ldg(p.row_sumsq_in + (size_t)row * p.ld_row_sumsq_in + j);
+        rscale = 1.f / fmaxf(sqrtf(ss), p.row_eps);
+      }
       if (f_res && lane == 0 && t + num_clusters < num_tiles) {      // next tile's residual boxes -> L2
         const int tn = t + num_clusters;
         const int pm0 = (tn / n_tiles) * 256 + (int)rank * 128 + q * 32, pn0 = (tn % n_tiles) * BN + cbeg;
@@ -324,6 +347,110 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
           }
         }
+        if (f_rscale) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rscale);
+        }
+        if (f_gate) {
+          // gate operands of the attention output O (this accumulator) and the query feature x (the residual operand's box):
+          // out = O * x, out2 = x - O, both through the two staging boxes
+          mbar_wait(&rbar[0], gc & 1);
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          const uint32_t xbase = s_res + row_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(xbase + ((j ^ swz) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+            uint32_t g1[4], g2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float x0 = __uint_as_float(w[k] << 16), x1 = __uint_as_float(w[k] & 0xffff0000u);
+              const float o0 = __uint_as_float(r[8 * j + 2 * k]), o1 = __uint_as_float(r[8 * j + 2 * k + 1]);
+              const __nv_bfloat162 a = __floats2bfloat162_rn(o0 * x0, o1 * x1), b = __floats2bfloat162_rn(x0 - o0, x1 - o1);
+              g1[k] = *reinterpret_cast<const uint32_t*>(&a);
+              g2[k] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_out + row_off + ((j ^ swz) << 4)), "r"(g1[0]), "r"(g1[1]), "r"(g1[2]), "r"(g1[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_out + kG2BoxBytes + row_off + ((j ^ swz) << 4)), "r"(g2[0]), "r"(g2[1]), "r"(g2[2]), "r"(g2[3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();                                      // every lane has read its x row and written both boxes
+          if (lane == 0) {
+            if (ci + 1 < kChunks) issue_res(t, ci + 1, gc + 1);
+            else if (t + num_clusters < num_tiles) issue_res(t + num_clusters, 0, gc + 1);
+            if (col0 < p.N) {
+              tma_store_2d(&map_d, s_out, col0, m0 + q * 32);
+              tma_store_2d(&map_d2, s_out + kG2BoxBytes, col0, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
+          continue;
+        }
+        if (f_softmax) {
+          // softmax over the row: N <= 64 is local to this lane; 64 < N <= 128 (BN = 128: the other column half belongs to
+          // warp ew ^ 4) merges the two halves' (max, sum) through this warp's otherwise unused residual box
+          float mx = -3.0e38f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const bool ok = col0 + i < p.N;
+            const float vv = ok ? __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + col0 + i) : 0.f) : -3.0e38f;
+            r[i] = __float_as_uint(vv);
+            mx = fmaxf(mx, vv);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float e = (col0 + i < p.N) ? __expf(__uint_as_float(r[i]) - mx) : 0.f;
+            r[i] = __float_as_uint(e);
+            sum += e;
+          }
+          float scale = 1.f / sum;
+          if (p.N > 64) {
+            float2* mine = reinterpret_cast<float2*>(my + 2 * kG2BoxBytes) + (lt & 1) * 32;
+            const float2* theirs = reinterpret_cast<const float2*>(epi + (ew ^ 4) * Cfg::kEpiBytesPerWarp + 2 * kG2BoxBytes) + (lt & 1) * 32;
+            mine[lane] = make_float2(mx, sum);
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            const float2 o = theirs[lane];
+            const float m2 = fmaxf(mx, o.x);
+            const float tot = sum * __expf(mx - m2) + o.y * __expf(o.x - m2);
+            scale = __expf(mx - m2) / tot;
+          }
+          if (f_store) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          const uint32_t sbase = s_out + (gc & 1) * kG2BoxBytes + row_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t hw4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a0 = __uint_as_float(r[8 * j + 2 * k]) * scale, a1 = __uint_as_float(r[8 * j + 2 * k + 1]) * scale;
+              r[8 * j + 2 * k] = __float_as_uint(a0);
+              r[8 * j + 2 * k + 1] = __float_as_uint(a1);
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(a0, a1);
+              hw4[k] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            if (f_store)
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + ((j ^ swz) << 4)), "r"(hw4[0]), "r"(hw4[1]), "r"(hw4[2]), "r"(hw4[3]) : "memory");
+          }
+          if (f_f32 && row_ok) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (col0 + i < p.N) p.d_f32[(size_t)row * p.ldd32 + col0 + i] = __uint_as_float(r[i]);
+          }
+          if (f_store) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && col0 < p.N) {
+              if (p.has_out) tma_store_2d(&map_d, s_out + (gc & 1) * kG2BoxBytes, col0, m0 + q * 32);
+              tma_store_commit();
+            }
+          }
+          continue;
+        }
         if (f_res) {
           // residual (bf16, 128B-swizzled rows of the TMA box) added straight into the accumulator registers, so that the
           // box is free again — and the next one requested — before the rest of the chunk is processed
@@ -354,6 +481,7 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           __syncwarp();
         }
+        float ssq = 0.f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = col0 + 32 * h;
@@ -431,6 +559,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               }
             }
           }
+          if (f_ssq) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (col + i < p.N) ssq += v[i] * v[i];
+          }
           if (f_bout && !packed_tail) {
             uint32_t w = 0;
 #pragma unroll
@@ -506,6 +638,7 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                            : "memory");
           }
         }
+        if (f_ssq && row_ok) p.rowsumsq_out[(size_t)row * p.ld_rowsumsq + (col0 >> 6)] = ssq;
         if (f_store) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -602,6 +735,10 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   a.bits_out = (uint32_t*)d->bits_out; a.ldbits_out = d->ld_bits_out;
   a.d_f32 = d->out_f32; a.ldd32 = d->ld_out_f32; a.accumulate = d->accumulate;
   a.rowmean_out = d->rowmean_out; a.ld_rowmean = d->ld_rowmean;
+  a.rowsumsq_out = d->rowsumsq_out; a.ld_rowsumsq = d->ld_rowsumsq;
+  a.row_sumsq_in = d->row_scale_sumsq; a.ld_row_sumsq_in = d->ld_row_scale_sumsq; a.row_parts = d->row_scale_parts;
+  a.row_eps = d->row_scale_eps;
+  a.softmax = d->softmax; a.gate = d->gate;
   a.M = d->M; a.N = d->N;
   a.kb1 = ceil_div(K1, kG2BK); a.kb2 = ceil_div(K2, kG2BK);
   a.conv_cb = d->conv_c / kG2BK;
@@ -659,6 +796,18 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
   B200_CHECK_ARG(d, "gemm2: null descriptor");
   B200_CHECK_ARG(d->A && d->B, "gemm2: null operand");
   B200_CHECK_ARG(d->out_bf16 || d->out2_bf16 || d->out_f32 || d->rowmean_out, "gemm2: no output");
+  const bool row_ops = d->rowsumsq_out || d->row_scale_sumsq || d->softmax || d->gate;
+  if (row_ops) {
+    B200_CHECK_ARG(!d->mask_act && !d->mask_bits && !d->bits_out && !d->rowmean_out && d->split_k <= 1 && !d->accumulate,
+                   "gemm2: row-wise epilogues exclude gates, mask / mean outputs, split-K and accumulate");
+    B200_CHECK_ARG(!d->row_scale_sumsq || (d->row_scale_parts > 0 && d->ld_row_scale_sumsq >= d->row_scale_parts),
+                   "gemm2: row_scale_sumsq needs row_scale_parts > 0 entries per row");
+    B200_CHECK_ARG(!d->softmax || (d->N <= 128 && !d->residual && !d->relu && !d->out2_bf16 && !d->rowsumsq_out),
+                   "gemm2: softmax epilogue needs N <= 128 and excludes residual / ReLU / out2 / rowsumsq");
+    B200_CHECK_ARG(!d->gate || (d->residual && d->out_bf16 && d->out2_bf16 && !d->bias && !d->relu && !d->out_f32 && !d->softmax &&
+                                !d->rowsumsq_out),
+                   "gemm2: gate epilogue takes x as the residual operand and writes out (O*x) and out2 (x-O) only");
+  }
   B200_CHECK_ARG(d->M >= 0 && d->N > 0 && d->K > 0, "gemm2: bad shape");
   B200_CHECK_ARG(!d->accumulate || d->out_f32, "gemm2: accumulate needs an fp32 output");
   B200_CHECK_ARG(!(d->mask_act && d->mask_bits), "gemm2: one ReLU-backward gate at most");
@@ -692,6 +841,7 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
     const int mt = ceil_div(d->M, 256);
     bn = (d->N <= 128 || mt * ceil_div(d->N, 128) <= kNumSMs / 2) ? 128 : 256;
   }
+  if (d->softmax) bn = 128;                               // the row's two 64-column halves sit in the two warps of a lane quarter
   B200_CHECK_ARG(bn == 128 || bn == 256, "gemm2: tile_n must be 0, 128 or 256");
   B200_CHECK_ARG(d->split_k <= 1 || d->tile_n == bn, "gemm2: split-K needs an explicit tile_n (the workspace is sized for it)");
   // smallest instantiation whose compiled-in epilogue features cover the descriptor
@@ -703,6 +853,7 @@ extern "C" int b200_gemm2(const b200_gemm2_desc* d, b200_stream_t stream) {
   if (d->bits_out) need |= kFBitsOut;
   if (d->rowmean_out) need |= kFRowMean;
   if (d->out2_bf16) need |= kFOut2;
+  if (row_ops) return bn == 256 ? launch_gemm2<256, kFRow>(d, st) : launch_gemm2<128, kFRow>(d, st);
   if (d->epilogue_variant == 1) need = kFAll;          // tests: force the generic instantiation
   if ((need & ~kFFwd) == 0) return bn == 256 ? launch_gemm2<256, kFFwd>(d, st) : launch_gemm2<128, kFFwd>(d, st);
   if ((need & ~kFFwdMean) == 0) return bn == 256 ? launch_gemm2<256, kFFwdMean>(d, st) : launch_gemm2<128, kFFwdMean>(d, st);

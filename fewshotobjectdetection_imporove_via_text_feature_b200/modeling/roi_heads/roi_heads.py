@@ -567,14 +567,19 @@ class SematicRes5ROIHeadsCrossOutput(SematicRes5ROIHeads):
             extra = {"output_projection.weight": self.output_projection.weight, "output_projection.bias": self.output_projection.bias}
             _, output_att = self.attention(feature_pooled, extra=extra)
             w = output_att["fused_w"]
-            a = ops.gemm_bf16(output_att["sim2stext_bf16"], w["extra.output_projection.weight"],
-                              w["extra.output_projection.bias"], relu=True, out_dtype=torch.bfloat16)
-            if self.cosine_logits:         # unit rows on both sides, temperature folded into the (K+1)-row text operand
-                a = ops.l2_normalize_rows(a)
+            zb, wo, bo = output_att["sim2stext_bf16"], w["extra.output_projection.weight"], w["extra.output_projection.bias"]
+            if self.cosine_logits:
+                # my_module.py:449-469: x.t / (|x| |t|) x temperature.  |x|^2 is a by-product of the projection's epilogue, the
+                # logits' epilogue divides by it; 1/|t| and the temperature sit in the (K+1)-row text operand — the
+                # activations never take a normalisation pass
+                ssq = torch.empty((zb.shape[0], -(-wo.shape[0] // 64)), dtype=torch.float32, device=zb.device)
+                a = ops.gemm2(zb, wo, bias=bo, relu=True, rowsumsq_out=ssq)
                 tb = ops.l2_normalize_rows(output_att["text_feat"].float().contiguous(), scale=self.cosine_tau)
+                score = torch.empty((zb.shape[0], tb.shape[0]), dtype=torch.float32, device=zb.device)
+                ops.gemm2(a, tb, row_scale_sumsq=ssq, out_f32=score, want_out=False)
             else:
-                tb = output_att["text_feat"].to(torch.bfloat16).contiguous()
-            score = ops.gemm_bf16(a, tb)
+                a = ops.gemm_bf16(zb, wo, bo, relu=True, out_dtype=torch.bfloat16)
+                score = ops.gemm_bf16(a, output_att["text_feat"].to(torch.bfloat16).contiguous())
             xb = output_att.get("x_bf16")
         logits, deltas = self.box_predictor(feature_pooled, score, xb, None)
         output_att["pred_logits"], output_att["pred_bbox"] = logits, deltas

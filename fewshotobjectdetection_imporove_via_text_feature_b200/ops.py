@@ -533,6 +533,7 @@ def _splitk_workspace(dev, nbytes):
 
 def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residual=None, relu=False, mask_act=None,
           mask_bits=None, out=None, out2=None, out_f32=None, accumulate=False, bits_out=None, rowmean_out=None,
+          rowsumsq_out=None, row_scale_sumsq=None, row_scale_eps=1e-12, softmax=False, gate=False,
           want_out=True, M=None):
     """CTA-pair tcgen05 GEMM / implicit 3x3 convolution (csrc/gemm2_tcgen05.cu, `b200_gemm2`).
 
@@ -593,9 +594,18 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
     if rowmean_out is not None:
         assert rowmean_out.dtype == torch.float32 and tuple(rowmean_out.shape) == (M // 16, N) and rowmean_out.stride(1) == 1
         d.rowmean_out, d.ld_rowmean = rowmean_out.data_ptr(), rowmean_out.stride(0)
+    row_ops = rowsumsq_out is not None or row_scale_sumsq is not None or softmax or gate
+    if rowsumsq_out is not None:       # (M, ceil(N/64)) fp32: squared norm of each output row, one entry per 64-column chunk
+        assert rowsumsq_out.dtype == torch.float32 and tuple(rowsumsq_out.shape) == (M, -(-N // 64)) and rowsumsq_out.stride(1) == 1
+        d.rowsumsq_out, d.ld_rowsumsq = rowsumsq_out.data_ptr(), rowsumsq_out.stride(0)
+    if row_scale_sumsq is not None:    # acc * 1 / max(sqrt(sum of the row's entries), eps)
+        assert row_scale_sumsq.dtype == torch.float32 and row_scale_sumsq.shape[0] == M and row_scale_sumsq.stride(1) == 1
+        d.row_scale_sumsq, d.ld_row_scale_sumsq = row_scale_sumsq.data_ptr(), row_scale_sumsq.stride(0)
+        d.row_scale_parts, d.row_scale_eps = row_scale_sumsq.shape[1], float(row_scale_eps)
+    d.softmax, d.gate = int(softmax), int(gate)
     d.tile_n, d.max_clusters, d.epilogue_variant = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0], GEMM2_GENERIC_EPILOGUE[0]
     nkb = 9 * (conv_c // 64) if conv_c else -(-K // 64) + -(-K2 // 64)
-    bn_, sk = _splitk_plan(M, N, nkb, residual is not None)
+    bn_, sk = (0, 1) if row_ops else _splitk_plan(M, N, nkb, residual is not None)
     if sk > 1:
         nbytes = _lib.lib().b200_gemm2_splitk_workspace_bytes(M, N, bn_, sk)
         ws = _splitk_workspace(dev, nbytes)
@@ -607,7 +617,9 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
                    dict(M=M, N=N, K=K, K2=K2, conv_c=int(conv_c), a_mn=bool(a_mn), b_mn=bool(b_mn), relu=bool(relu),
                         acc=bool(accumulate), out=out is not None, out2=out2 is not None, f32=out_f32 is not None,
                         bias=bias is not None, res=residual is not None, mbits=mask_bits is not None,
-                        mact=mask_act is not None, bout=bits_out is not None, mean=rowmean_out is not None)))
+                        mact=mask_act is not None, bout=bits_out is not None, mean=rowmean_out is not None,
+                        ssq=rowsumsq_out is not None, rscale=None if row_scale_sumsq is None else row_scale_sumsq.shape[1],
+                        softmax=bool(softmax), gate=bool(gate))))
     return out
 
 
@@ -764,6 +776,7 @@ class TextFusionWeights:
         vp = torch.nn.functional.linear(vt, named["attention.w_v.weight"].detach().float())
         w["kp"] = torch.cat([kp, named["attention.dummy"].detach().float().reshape(1, -1)], 0).contiguous()
         w["vp"] = torch.cat([vp, torch.zeros(1, vp.shape[1], device=vp.device)], 0).contiguous()
+        w["vp_bf16"] = w["vp"].to(torch.bfloat16)
         # folded query/key operand: S = (x Wq^T) Kp^T / sqrt(d) = x (Kp Wq)^T / sqrt(d); constant while weights are
         d = w["kp"].shape[1]
         w["kq"] = bf((w["kp"] @ named["attention.w_q.weight"].detach().float()) / math.sqrt(d))
@@ -773,6 +786,11 @@ class TextFusionWeights:
                 w[k] = bf(t) if (t.dim() == 2) else f32(t)
         self.key, self.w = key, w
         return w
+
+
+# inference chain: attention probabilities and gate operands as GEMM epilogues (False / B200_ATTN_EPILOGUES=0: the separate
+# fp32 attention kernel of round 1, kept for A/B runs and used by the training direction, which needs its fp32 operands)
+ATTENTION_AS_EPILOGUES = [_os.environ.get("B200_ATTN_EPILOGUES", "1") != "0"]
 
 
 def text_fusion_forward(x, w, fold_query=True, score_bias=None):
@@ -789,8 +807,19 @@ def text_fusion_forward(x, w, fold_query=True, score_bias=None):
     xb = cast_bf16_into(x, xcat[:, d:])
     p1 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
     p2 = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-    if fold_query:
-        s = gemm_bf16(xb, w["kq"], score_bias)       # score_bias (L,): per-key logit offset (teacher attention: log n_c)
+    if fold_query and ATTENTION_AS_EPILOGUES[0]:
+        # softmax as the epilogue of the (folded) score product, gate operands as the epilogue of probabilities x values:
+        # no separate attention kernel (north_star: "fused softmax GEMM epilogues")
+        L = w["kq"].shape[0]
+        pb = torch.empty((R, (L + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+        attn = torch.empty((R, L), dtype=torch.float32, device=dev)
+        gemm2(xb, w["kq"], bias=score_bias, softmax=True, out=pb[:, :L], out_f32=attn)    # score_bias (L,): teacher's log n_c
+        vpb = w.get("vp_bf16")
+        if vpb is None or vpb.shape != w["vp"].shape:
+            vpb = w["vp"].to(torch.bfloat16).contiguous()
+        gemm2(pb[:, :L], vpb, b_mn=True, residual=xb, gate=True, out=p1, out2=p2)
+    elif fold_query:
+        s = gemm_bf16(xb, w["kq"], score_bias)
         attn = text_attention(None, x, None, w["vp"], p1, p2, scores=s)
     else:
         q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)

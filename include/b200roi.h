@@ -206,6 +206,18 @@ B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, c
  *             bit j <-> column 32w + 2j and bit 16 + j <-> column 32w + 2j + 1 (the order in which the epilogue's packed
  *             bf16x2 compare produces them); mask_bits uses the same layout,
  *             rowmean_out [M/16][ld_rowmean] fp32: mean of v over each group of 16 consecutive rows (the 4x4 pixels of a ROI)
+ *   row-wise  (an epilogue lane owns one output row, so these cost no cross-lane traffic; they exclude the gates, bits_out,
+ *   epilogues  rowmean_out, accumulate and split-K):
+ *             rowsumsq_out [M][ld_rowsumsq] fp32: entry j of a row = sum of v^2 over columns 64j .. 64j+63 — the squared
+ *             norm of an output row as a by-product (ceil(N/64) entries);
+ *             row_scale_sumsq [M][ld] + row_scale_parts + row_scale_eps: acc is multiplied by
+ *             1 / max(sqrt(sum of the row's first row_scale_parts entries), eps) before the bias — with the previous
+ *             product's rowsumsq_out this is the cosine logit x.t / (|x| temperature) of my_module.py:449-469 without a
+ *             normalisation pass (the temperature and 1/|t| are folded into B's rows);
+ *             softmax != 0 (N <= 128): out_bf16 / out_f32 = softmax over the row of acc + bias — the attention
+ *             probabilities of attentive_modules.py:45-55 as the epilogue of the (folded) score product;
+ *             gate != 0: the residual operand is x and the outputs are out_bf16 = acc * x, out2_bf16 = x - acc — the gate
+ *             operands of attentive_modules.py:166,170 as the epilogue of the probabilities x values product
  *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it);
  *             epilogue_variant: 0 = the smallest compiled epilogue that covers the requested features, 1 = the generic one
  *             (same results; tests compare them)
@@ -215,7 +227,10 @@ B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, c
  *             counters, which must be zero on entry and are left zero, so one zero-initialised workspace serves any
  *             sequence of launches on one stream); the slice arriving last sums the partials in slice order — bitwise
  *             reproducible, no floating-point atomics — and runs the epilogue.  Needs an explicit tile_n, no residual.
- * Alignment: bf16 tensors 16-byte aligned, their leading dimensions multiples of 8 elements.
+ * Alignment: bf16 tensors 16-byte aligned, their leading dimensions multiples of 8 elements.  bf16 outputs leave through TMA
+ * stores, which are 16-byte granular: when N is not a multiple of 8, the up to 7 elements that complete the last 16-byte unit
+ * of a row (inside the row pitch, never in the next row) are written as well — with the epilogue's value for a column >= N
+ * (bias-free zero accumulator: 0 after ReLU / softmax / gate).  fp32 outputs are exact-width.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct b200_gemm2_desc {
   const void* A; int lda;
@@ -233,6 +248,11 @@ typedef struct b200_gemm2_desc {
   float* out_f32; int ld_out_f32; int accumulate;
   void* bits_out; int ld_bits_out;
   float* rowmean_out; int ld_rowmean;
+  float* rowsumsq_out; int ld_rowsumsq;                 /* [M][ld]: sum of squares of the row's outputs per 64-column chunk */
+  const float* row_scale_sumsq; int ld_row_scale_sumsq, row_scale_parts; float row_scale_eps;
+                                                        /* acc *= 1 / max(sqrt(sum of the row's parts), eps), before the bias */
+  int softmax;                                          /* out = softmax over the row (N <= 128) of acc + bias: bf16 and / or fp32 */
+  int gate;                                             /* residual = x: out = acc * x, out2 = x - acc */
   int tile_n, max_clusters;
   int epilogue_variant;
   int split_k; void* splitk_workspace; size_t splitk_workspace_bytes;

@@ -170,6 +170,30 @@ def test_chain_vs_oracle(R, K, fold):
     torch.testing.assert_close(attn[0].cpu().float(), attn_ref, rtol=2e-2, atol=2e-2 * float(attn_ref.abs().max()))
 
 
+def test_inference_chain_has_no_attention_or_normalisation_kernel():
+    """north_star / VERDICT r1 item 10: softmax and the gate operands leave as epilogues of the two products around them, so the
+    inference chain's launch list holds GEMMs, one cast and one LayerNorm — and both forms agree to the bf16 bar."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+    m = _build_attention(20, 2048).cuda()
+    x = torch.relu(torch.randn(640, 2048, generator=torch.Generator().manual_seed(5))).cuda()
+    outs = {}
+    for flag in (True, False):
+        ops.ATTENTION_AS_EPILOGUES[0] = flag
+        try:
+            with torch.no_grad():
+                m(x)
+                _lib.PROFILE = {}
+                attn, out = m(x)
+                names = set(_lib.PROFILE)
+        finally:
+            _lib.PROFILE = None
+            ops.ATTENTION_AS_EPILOGUES[0] = True
+        outs[flag] = (attn[0].float(), out["sim2stext"].float(), names)
+    assert "b200_text_attention" in outs[False][2] and "b200_text_attention" not in outs[True][2]
+    assert outs[True][2] <= {"b200_gemm2", "b200_gemm_bf16", "b200_gemm_bf16_ex", "b200_cast_bf16", "b200_residual_layernorm"}, outs[True][2]
+    assert rel_err(outs[True][0], outs[False][0]) < 2e-3 and rel_err(outs[True][1], outs[False][1]) < 2e-2
+
+
 def test_chain_golden_small(golden):
     """d_model = 32 golden produced by the reference's own SematicProposalAttention."""
     g = golden("attention_small")

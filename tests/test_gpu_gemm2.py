@@ -237,3 +237,94 @@ def test_gemm2_rejects_bad_arguments():
         ops.gemm2(a, a, want_out=False)                               # no output
     with pytest.raises(_lib.B200Error):
         ops.gemm2(a[:, 1:57], a[:, 1:57])                             # operand not 16-byte aligned
+
+
+# ---- row-wise epilogues (one lane owns one output row): VERDICT r1 item 10 ------------------------------------------------
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("M,N,K,N2", [(1000, 512, 2048, 21), (4096, 200, 512, 81), (77, 64, 72, 5)])
+def test_gemm2_cosine_logits_as_two_epilogues(M, N, K, N2, tile_n):
+    """relu(x W^T + b) with the squared row norms as a by-product (rowsumsq_out), then the product with the unit-norm,
+    temperature-scaled text rows scaled per row by 1 / |a| (row_scale_sumsq): the cosine logits of my_module.py:449-469 with no
+    normalisation pass over the activations."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(M + N)
+    x, w = _rand(gen, M, K, scale=0.5), _rand(gen, N, K, scale=0.05)
+    bias = torch.randn(N, generator=gen) * 0.1
+    t = torch.randn(N2, N, generator=gen)
+    tb = (t / t.norm(dim=1, keepdim=True) * 20.0).to(torch.bfloat16)
+    ops.GEMM2_TILE_N[0] = tile_n
+    try:
+        ssq = torch.full((M, (N + 63) // 64), -1.0, device="cuda")
+        a = ops.gemm2(x.cuda(), w.cuda(), bias=bias.cuda(), relu=True, rowsumsq_out=ssq)
+        v = (x.double() @ w.double().t() + bias.double()).clamp_min(0)
+        torch.testing.assert_close(a.cpu().double(), v, rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(ssq.sum(1).cpu().double(), (v * v).sum(1), rtol=2e-3, atol=1e-6)
+        for j in range(ssq.shape[1]):
+            torch.testing.assert_close(ssq[:, j].cpu().double(), (v[:, 64 * j:64 * j + 64] ** 2).sum(1), rtol=2e-3, atol=1e-6)
+        logits = torch.empty(M, N2, device="cuda")
+        ops.gemm2(a, tb.cuda(), row_scale_sumsq=ssq, out_f32=logits, want_out=False)
+        ad = a.cpu().double()
+        ref = (ad @ tb.double().t()) / ssq.sum(1).cpu().double().sqrt().clamp_min(1e-12)[:, None]
+        torch.testing.assert_close(logits.cpu().double(), ref, rtol=1e-3, atol=1e-3)
+        # and against the plain cosine expression (bf16 bar)
+        cos = torch.nn.functional.normalize(v, dim=1) @ torch.nn.functional.normalize(t.double(), dim=1).t() * 20.0
+        assert float((logits.cpu().double() - cos).norm() / cos.norm()) < 2e-2
+    finally:
+        ops.GEMM2_TILE_N[0] = 0
+
+
+@pytest.mark.parametrize("M,L,K", [(4096, 22, 2048), (1000, 82, 512), (333, 64, 256), (200, 128, 128), (96, 65, 64), (50, 1, 64)])
+def test_gemm2_softmax_epilogue(M, L, K):
+    """softmax over the row as the epilogue of the score product (attentive_modules.py:45-55): one lane owns a row, rows wider
+    than 64 columns merge the two column halves' (max, sum) between the two warps of the lane quarter."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(M + L)
+    x, kq = _rand(gen, M, K, scale=0.5), _rand(gen, L, K, scale=0.3)
+    bias = torch.randn(L, generator=gen)
+    Lp = (L + 7) // 8 * 8 + 8
+    pb = torch.full((M, Lp), 9.0, dtype=torch.bfloat16, device="cuda")
+    attn = torch.full((M, L), -1.0, device="cuda")
+    ops.gemm2(x.cuda(), kq.cuda(), bias=bias.cuda(), softmax=True, out=pb[:, :L], out_f32=attn)
+    ref = torch.softmax(x.double() @ kq.double().t() + bias.double(), dim=1)
+    torch.testing.assert_close(attn.cpu().double(), ref, rtol=2e-4, atol=1e-6)
+    torch.testing.assert_close(attn.sum(1).cpu(), torch.ones(M), rtol=1e-5, atol=1e-5)
+    assert torch.equal(pb[:, :L].float(), attn.to(torch.bfloat16).float())
+    # TMA stores are 16-byte granular: the columns that complete the row's last 16-byte unit receive the epilogue's value for
+    # columns >= N (zero probability here, which is what the next product's K padding needs); nothing beyond is touched
+    assert bool((pb[:, L:(L + 7) // 8 * 8] == 0.0).all()) and bool((pb[:, (L + 7) // 8 * 8:] == 9.0).all())
+    only = torch.full((M, L), -1.0, device="cuda")
+    ops.gemm2(x.cuda(), kq.cuda(), bias=bias.cuda(), softmax=True, out_f32=only, want_out=False)
+    assert torch.equal(only, attn)
+
+
+@pytest.mark.parametrize("M,L,d", [(4096, 22, 2048), (1000, 82, 512), (77, 6, 200)])
+def test_gemm2_gate_epilogue(M, L, d):
+    """O = P Vp with the gate operands O * x and x - O (attentive_modules.py:166,170) as its epilogue: P (M, L) bf16 with a
+    padded pitch, Vp (L, d) read N-major (no transposed copy), x the residual operand."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(M + L + d)
+    p = torch.softmax(torch.randn(M, L, generator=gen) * 2, dim=1).to(torch.bfloat16)
+    Lp = (L + 7) // 8 * 8
+    pp = torch.zeros(M, Lp, dtype=torch.bfloat16)
+    pp[:, :L] = p
+    dp = (d + 7) // 8 * 8
+    vp = _rand(gen, L, dp)[:, :d]
+    x = _rand(gen, M, dp)[:, :d]
+    p1 = torch.empty(M, dp, dtype=torch.bfloat16, device="cuda")[:, :d]
+    p2 = torch.empty(M, dp, dtype=torch.bfloat16, device="cuda")[:, :d]
+    ops.gemm2(pp.cuda()[:, :L], vp.cuda(), b_mn=True, residual=x.cuda(), gate=True, out=p1, out2=p2)
+    o = p.double() @ vp.double()
+    torch.testing.assert_close(p1.cpu().double(), o * x.double(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(p2.cpu().double(), x.double() - o, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm2_row_epilogues_reject_bad_combinations():
+    ops = _ops()
+    from fewshotobjectdetection_imporove_via_text_feature_b200._lib import B200Error
+    a, b = torch.zeros(64, 64, dtype=torch.bfloat16, device="cuda"), torch.zeros(256, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(B200Error):
+        ops.gemm2(a, b, softmax=True)                                      # N > 128
+    with pytest.raises(B200Error):
+        ops.gemm2(a, b[:64], gate=True)                                    # no x / second output
+    with pytest.raises(B200Error):
+        ops.gemm2(a, b[:64], softmax=True, relu=True)
