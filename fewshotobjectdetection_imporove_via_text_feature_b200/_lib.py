@@ -30,7 +30,7 @@ class Gemm2Desc(ctypes.Structure):
                 ("rowsumsq_out", c_void_p), ("ld_rowsumsq", c_int),
                 ("row_scale_sumsq", c_void_p), ("ld_row_scale_sumsq", c_int), ("row_scale_parts", c_int), ("row_scale_eps", c_float),
                 ("softmax", c_int), ("gate", c_int),
-                ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int),
+                ("tile_n", c_int), ("max_clusters", c_int), ("epilogue_variant", c_int), ("no_pdl", c_int),
                 ("split_k", c_int), ("splitk_workspace", c_void_p), ("splitk_workspace_bytes", c_size_t)]
 
 

@@ -142,6 +142,10 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   cluster_sync_all();                                     // both CTAs' barriers are initialised, both TMEM allocations done
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the next launch of the stream may take this SM as soon as this CTA leaves it and set itself up under our tail; our own
+  // operands may still be in flight from the previous launch: nothing above touched global memory
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ---- TMA producer (both CTAs): own A rows, own half of B; the bytes of both CTAs complete on the LEADER's barrier
@@ -778,6 +782,13 @@ static int launch_gemm2(const b200_gemm2_desc* d, cudaStream_t st) {
   cfg.blockDim = dim3(kG2Threads);
   cfg.dynamicSmemBytes = G2Cfg<BN>::kSmemBytes;
   cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (!d->no_pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
   B200_CUDA_CALL(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, md, md2, mr, a));
   return B200_OK;
 }

@@ -28,6 +28,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// Programmatic dependent launch: a grid launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident
+// while its predecessor in the stream is still running (as soon as that grid has called launch_dependents in every CTA and
+// resources free up), runs its prologue — barrier init, TMEM allocation, descriptor prefetch — and blocks in pdl_wait() until
+// the predecessor has completed and its memory is visible.  Everything that touches global memory comes after pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));

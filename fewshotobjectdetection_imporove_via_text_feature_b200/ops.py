@@ -494,6 +494,7 @@ GEMM2_TILE_N = [0]          # tests / microbenchmarks force 128 or 256
 GEMM2_MAX_CLUSTERS = [0]    # tests lower it to force several tiles per CTA pair on small shapes
 GEMM2_GENERIC_EPILOGUE = [0]   # tests: 1 = always the generic epilogue instantiation
 import os as _os
+GEMM2_NO_PDL = [int(_os.environ.get("B200_GEMM2_NO_PDL", "0"))]      # 1: no programmatic dependent launch (A/B runs)
 GEMM2_SPLIT_K = [int(_os.environ.get("B200_GEMM2_SPLIT_K", "0"))]   # 0 = choose per shape, 1 = never split, n > 1 = force (tests)
 _SPLITK_WS = {}                # (device, stream) -> workspace: split-K launches on one stream are ordered, streams do not share
 
@@ -604,6 +605,7 @@ def gemm2(a, b, *, a2=None, a_mn=False, b_mn=False, conv_c=0, bias=None, residua
         d.row_scale_parts, d.row_scale_eps = row_scale_sumsq.shape[1], float(row_scale_eps)
     d.softmax, d.gate = int(softmax), int(gate)
     d.tile_n, d.max_clusters, d.epilogue_variant = GEMM2_TILE_N[0], GEMM2_MAX_CLUSTERS[0], GEMM2_GENERIC_EPILOGUE[0]
+    d.no_pdl = GEMM2_NO_PDL[0]
     nkb = 9 * (conv_c // 64) if conv_c else -(-K // 64) + -(-K2 // 64)
     bn_, sk = (0, 1) if row_ops else _splitk_plan(M, N, nkb, residual is not None)
     if sk > 1:

@@ -221,6 +221,9 @@ B200_API int b200_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, c
  *   tile_n    0 = choose, 128 or 256;  max_clusters: 0 = one CTA pair per SM pair (tests lower it);
  *             epilogue_variant: 0 = the smallest compiled epilogue that covers the requested features, 1 = the generic one
  *             (same results; tests compare them)
+ *   no_pdl    0: the kernel is launched with programmatic stream serialisation — its CTAs may become resident and set themselves
+ *             up (barriers, TMEM) while the previous kernel of the stream drains, and wait (griddepcontrol.wait) for that
+ *             kernel's completion before touching global memory; results are identical either way
  *   split_k   > 1: the K blocks of every output tile are shared by split_k CTA pairs (products with few output tiles and a
  *             long K: the (K+2)-row text operands, cls_score / bbox_pred and their weight gradients).  Each slice leaves its
  *             fp32 partial tile in splitk_workspace (b200_gemm2_splitk_workspace_bytes; its first 64 KiB hold the arrival
@@ -255,6 +258,7 @@ typedef struct b200_gemm2_desc {
   int gate;                                             /* residual = x: out = acc * x, out2 = x - acc */
   int tile_n, max_clusters;
   int epilogue_variant;
+  int no_pdl;                                           /* != 0: plain stream serialisation instead of a programmatic dependent launch */
   int split_k; void* splitk_workspace; size_t splitk_workspace_bytes;
 } b200_gemm2_desc;
 B200_API int b200_gemm2(const b200_gemm2_desc* desc, b200_stream_t stream);
