@@ -5,6 +5,7 @@ All arithmetic on the ROI-head hot path is done by the kernels in csrc/ through 
 Reference call sites are cited per op.
 """
 import math
+import os as _os
 
 import torch
 
@@ -156,6 +157,9 @@ class _PlanBuffer:
             pass
 
 
+PLAN_EARLY = [_os.environ.get("B200_PLAN_EARLY", "1") != "0"]
+
+
 class _ROIAlign(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, rois, roi_batch_offsets, output_size, spatial_scale, sampling_ratio, aligned,
@@ -169,6 +173,31 @@ class _ROIAlign(torch.autograd.Function):
         out = _empty4(R, C, -(-PH // bin_step), -(-PW // bin_step), feat.dtype, feat.device, channels_last_out)
         nbytes = _lib.lib().b200_roi_align_fwd_workspace_bytes(N, C, H, W, R, _dt(feat), in_layout)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=feat.device) if nbytes else None
+        ctx.plan = None
+        plan_ok = (PLAN_AHEAD[0] and ctx.needs_input_grad[0] and R > 0 and roi_batch_offsets is not None and
+                   feat.dtype == torch.bfloat16 and channels_last_out and in_layout == NHWC)
+
+        def launch_plan():
+            # The backward's per-pixel gather lists depend only on the ROIs: build them now on a side stream so that the
+            # backward pass is a single gather launch.  Forked BEFORE the forward kernel (PLAN_EARLY): the list builders can
+            # share the SMs with the pooling kernel, not with res5's persistent GEMMs (227 KB of shared memory per CTA:
+            # a kernel of another stream only gets an SM between two of their launches, i.e. on the critical path).
+            pbytes = _lib.lib().b200_roi_align_bwd_plan_bytes(N, C, H, W, R, PH, PW, int(bin_step))
+            if pbytes:
+                main, side = torch.cuda.current_stream(), _plan_stream(feat.device)
+                side.wait_stream(main)
+                holder = _PlanBuffer(feat.device, pbytes)
+                with torch.cuda.stream(side):
+                    _lib.call("b200_roi_align_bwd_plan", rois.data_ptr(), roi_batch_offsets.data_ptr(), N, C, H, W, R, PH, PW,
+                              int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
+                              holder.buf.data_ptr(), pbytes, side.cuda_stream)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                # `rois` / offsets stay referenced by ctx until the backward, which waits on `done` first
+                ctx.plan = (holder, done)
+
+        if plan_ok and PLAN_EARLY[0]:
+            launch_plan()
         ev = KERNEL_EVENTS.get("roi_align_fwd") if KERNEL_EVENTS else None
         if ev is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -183,24 +212,8 @@ class _ROIAlign(torch.autograd.Function):
         ctx.save_for_backward(rois, roi_batch_offsets)
         ctx.meta = (feat.shape, feat.dtype, in_layout, output_size, spatial_scale, sampling_ratio, aligned,
                     channels_last_out, bin_step)
-        ctx.plan = None
-        if (PLAN_AHEAD[0] and ctx.needs_input_grad[0] and R > 0 and roi_batch_offsets is not None and
-                feat.dtype == torch.bfloat16 and channels_last_out and in_layout == NHWC):
-            # The backward's per-pixel gather lists depend only on the ROIs: build them now on a side stream, under the
-            # forward / res5 kernels, so that the backward pass is a single gather launch.
-            pbytes = _lib.lib().b200_roi_align_bwd_plan_bytes(N, C, H, W, R, PH, PW, int(bin_step))
-            if pbytes:
-                main, side = torch.cuda.current_stream(), _plan_stream(feat.device)
-                side.wait_stream(main)
-                holder = _PlanBuffer(feat.device, pbytes)
-                with torch.cuda.stream(side):
-                    _lib.call("b200_roi_align_bwd_plan", rois.data_ptr(), roi_batch_offsets.data_ptr(), N, C, H, W, R, PH, PW,
-                              int(bin_step), float(spatial_scale), int(sampling_ratio), int(bool(aligned)),
-                              holder.buf.data_ptr(), pbytes, side.cuda_stream)
-                    done = torch.cuda.Event()
-                    done.record(side)
-                # `rois` / offsets stay referenced by ctx until the backward, which waits on `done` first
-                ctx.plan = (holder, done)
+        if plan_ok and not PLAN_EARLY[0]:
+            launch_plan()
         return out
 
     @staticmethod
