@@ -328,3 +328,38 @@ def test_gemm2_row_epilogues_reject_bad_combinations():
         ops.gemm2(a, b[:64], gate=True)                                    # no x / second output
     with pytest.raises(B200Error):
         ops.gemm2(a, b[:64], softmax=True, relu=True)
+
+
+def test_gemm2_programmatic_dependent_launch_chain():
+    """Launched with programmatic stream serialisation, a GEMM's CTAs may become resident while the previous kernel of the stream
+    still runs; they must not touch global memory before griddepcontrol.wait.  A chain in which every product consumes the
+    previous one's output (read-after-write through the early launch) and overwrites a buffer the previous one read
+    (write-after-read), repeated, must equal the plainly serialised chain bit for bit."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(77)
+    M, D = 4096, 1024
+    x0 = _rand(gen, M, D, scale=0.5).cuda()
+    ws = [_rand(gen, D, D, scale=0.03).cuda() for _ in range(6)]
+    bs = [torch.randn(D, generator=gen).cuda() * 0.1 for _ in range(6)]
+
+    def chain():
+        a, b = x0.clone(), torch.empty_like(x0)
+        for rep in range(4):
+            for w, bias in zip(ws, bs):
+                ops.gemm2(a, w, bias=bias, relu=True, out=b)       # b <- f(a); the next product reads b and overwrites a
+                a, b = b, a
+        return a.clone()
+
+    outs = {}
+    for no_pdl in (1, 0, 0):
+        ops.GEMM2_NO_PDL[0] = no_pdl
+        try:
+            outs.setdefault(no_pdl, []).append(chain())
+        finally:
+            ops.GEMM2_NO_PDL[0] = 0
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[0][1])
+    ref = x0.double()
+    for rep in range(4):
+        for w, bias in zip(ws, bs):
+            ref = (ref @ w.double().t() + bias.double()).clamp_min(0).to(torch.bfloat16).double()
+    assert float((outs[0][0].double() - ref).norm() / ref.norm()) < 3e-2      # 24 chained bf16 roundings
