@@ -268,3 +268,30 @@ def test_pcb_constructs_like_the_reference_and_preprocesses_like_it():
         want = r.layer4(r.layer3(r.layer2(r.layer1(r.maxpool(r.relu(r.bn1(r.conv1(x))))))))
     assert got.shape == (1, 2048, 3, 4)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm2_descriptor_fields_agree_everywhere():
+    """struct b200_gemm2_desc: the header's field list == the package's ctypes mirror == the binding INTEGRATION.md shows a
+    maintainer (names, order and size; a silent mismatch would shift every later field)."""
+    import ctypes
+    import re
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "b200roi.h")).read()
+    body = hdr[hdr.index("typedef struct b200_gemm2_desc {"):hdr.index("} b200_gemm2_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).split("{", 1)[1]
+    names = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if stmt:
+            parts = stmt.split(",")
+            names.append(parts[0].split()[-1].lstrip("*"))
+            names += [q.strip().lstrip("*") for q in parts[1:]]
+    mirror = [n for n, _ in _lib.Gemm2Desc._fields_]
+    assert names == mirror, (names, mirror)
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", md, re.S) if "ctypes.CDLL" in b)
+    ns = {"ctypes": ctypes}
+    exec(block[block.index("class Gemm2Desc"):block.index("def linear_relu")], ns)
+    assert [n for n, _ in ns["Gemm2Desc"]._fields_] == mirror
+    assert ctypes.sizeof(ns["Gemm2Desc"]) == ctypes.sizeof(_lib.Gemm2Desc)

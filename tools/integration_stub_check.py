@@ -32,4 +32,15 @@ hw = ops.image_hw_tensor([(600, 800)] * 2, "cuda")
 bx, lg, cnt, bad = ns["rpn_select"](props[0].cuda().contiguous(), logits[0].cuda().contiguous(), hw, 0.7, 1000, 300)
 ref = ops.rpn_select_proposals(props[0].cuda(), logits[0].cuda(), [3000], hw, 0.7, 1000, 300)
 assert torch.equal(bx, ref["boxes"]) and torch.equal(lg, ref["logits"]) and torch.equal(cnt, ref["counts"]), "rpn_select stub"
-print("INTEGRATION.md stubs ok:", a.shape, int(cnt.sum()))
+x = (torch.randn(1000, 512, generator=gen) * 0.5).to(torch.bfloat16).cuda()
+wgt = (torch.randn(384, 512, generator=gen) * 0.05).to(torch.bfloat16).cuda()
+bias = torch.randn(384, generator=gen).cuda()
+res = torch.randn(1000, 384, generator=gen).to(torch.bfloat16).cuda()
+y = ns["linear_relu"](x, wgt, bias, res)
+assert torch.equal(y, ops.gemm2(x, wgt, bias=bias, residual=res, relu=True)), "gemm2 stub"
+ref_y = torch.relu(x.double() @ wgt.double().t() + bias.double() + res.double())
+torch.testing.assert_close(y.double(), ref_y, rtol=1e-2, atol=1e-2)
+import ctypes  # noqa: E402
+from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib  # noqa: E402
+assert ctypes.sizeof(ns["Gemm2Desc"]) == ctypes.sizeof(_lib.Gemm2Desc), "Gemm2Desc layout"
+print("INTEGRATION.md stubs ok:", a.shape, int(cnt.sum()), tuple(y.shape))
