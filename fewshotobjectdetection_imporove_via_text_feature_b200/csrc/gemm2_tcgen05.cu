@@ -49,6 +49,16 @@ constexpr uint32_t kFAll = 127;
 constexpr uint32_t kFRowSumSq = 128, kFRowScale = 256, kFSoftmax = 512, kFGate = 1024;
 constexpr uint32_t kFRow = kFRes | kFF32 | kFOut2 | kFRowSumSq | kFRowScale | kFSoftmax | kFGate;
 
+// packed fp32 add (sm_100: FADD2 adds two fp32 lanes of a 64-bit register pair per issue slot; the accumulator registers that
+// tcgen05.ld fills are consecutive, so (r[2i], r[2i+1]) are natural pairs)
+__device__ __forceinline__ void add_f32x2(uint32_t& a0, uint32_t& a1, uint32_t b0, uint32_t b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(a));
+}
+
 struct Gemm2Args {
   const float* bias;
   const __nv_bfloat16* mask_act;     // ReLU backward gate from a bf16 activation [M][ldmask] (zero where <= 0)
@@ -466,10 +476,7 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(base + ((j ^ swz) << 4)));
             const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              r[8 * j + 2 * k] = __float_as_uint(__uint_as_float(r[8 * j + 2 * k]) + __uint_as_float(w[k] << 16));
-              r[8 * j + 2 * k + 1] = __float_as_uint(__uint_as_float(r[8 * j + 2 * k + 1]) + __uint_as_float(w[k] & 0xffff0000u));
-            }
+            for (int k = 0; k < 4; ++k) add_f32x2(r[8 * j + 2 * k], r[8 * j + 2 * k + 1], w[k] << 16, w[k] & 0xffff0000u);
           }
           __syncwarp();                                      // every lane has read its row: the box can be refilled
           if (lane == 0) {
@@ -497,10 +504,11 @@ gemm2_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + i);
-                v[4 * i] = __uint_as_float(r[32 * h + 4 * i]) + b4.x;
-                v[4 * i + 1] = __uint_as_float(r[32 * h + 4 * i + 1]) + b4.y;
-                v[4 * i + 2] = __uint_as_float(r[32 * h + 4 * i + 2]) + b4.z;
-                v[4 * i + 3] = __uint_as_float(r[32 * h + 4 * i + 3]) + b4.w;
+                uint32_t t0 = r[32 * h + 4 * i], t1 = r[32 * h + 4 * i + 1], t2 = r[32 * h + 4 * i + 2], t3 = r[32 * h + 4 * i + 3];
+                add_f32x2(t0, t1, __float_as_uint(b4.x), __float_as_uint(b4.y));
+                add_f32x2(t2, t3, __float_as_uint(b4.z), __float_as_uint(b4.w));
+                v[4 * i] = __uint_as_float(t0); v[4 * i + 1] = __uint_as_float(t1);
+                v[4 * i + 2] = __uint_as_float(t2); v[4 * i + 3] = __uint_as_float(t3);
               }
             } else {
 #pragma unroll
