@@ -63,6 +63,8 @@ SIGNATURES = {
     "b200_colsum_workspace_bytes": (c_size_t, [c_int]),
     "b200_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_dropout_fwd": (c_int, [c_void_p, c_void_p, c_size_t, c_float, ctypes.c_ulonglong, c_void_p, c_void_p]),
+    "b200_residual_layernorm_dropout": (c_int, [c_void_p] * 4 + [c_float, c_int, c_float, ctypes.c_ulonglong, c_void_p, c_void_p,
+                                                                  c_int, c_int, c_void_p]),
     "b200_layernorm_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "b200_layernorm_relu_dropout_bwd": (c_int, [c_void_p] * 5 + [c_float, c_float, ctypes.c_ulonglong] + [c_void_p] * 5 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_layernorm_param_grads": (c_int, [c_void_p] * 5 + [c_float, ctypes.c_ulonglong] + [c_void_p] * 3 + [c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -105,7 +107,7 @@ class B200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 3, "b200_roi_align_bwd_planned": 1,
     "b200_softmax_decode_compact": 2, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
-    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm2": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1,
+    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm2": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1, "b200_residual_layernorm_dropout": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_layernorm_param_grads": 3, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
     "b200_sgd_momentum": 1, "b200_spatial_mean": 1, "b200_mean_bwd_relu_mask": 1, "b200_add_relu_mask": 1, "b200_skinny_gemm": 1, "b200_text_attention": 1, "b200_residual_layernorm": 1, "b200_cast_bf16": 1, "b200_l2_normalize_rows": 1, "b200_label_sample_proposals": 1,
     "b200_rpn_select_proposals": 5, "b200_gather_rows_bf16": 1, "b200_kd_loss": 1, "b200_kd_loss_bwd": 1, "b200_spatial_mean_bits": 1, "b200_pack_relu_bits": 1, "b200_mean_bwd_relu_bits": 1, "b200_add_relu_bits": 1, "b200_class_mean_rows": 2, "b200_detector_postprocess": 1,

@@ -134,6 +134,58 @@ __global__ void dropout_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* _
   }
 }
 
+// zd = dropout(relu(LayerNorm(y + y2) * gamma + beta)) as bf16 in one pass (attentive_modules.py:73-74,285 followed by the
+// classifier dropout of fast_rcnn.py:412-414): the fp32 z of the two-kernel form is never written or re-read (66 MB per step at
+// R = 4096).  Statistics, affine map and dropout decision are those of residual_layernorm_kernel / dropout_fwd_kernel,
+// expression for expression, so the result equals the two-kernel form bit for bit and the backward's recomputation matches.
+__global__ void __launch_bounds__(256)
+residual_layernorm_dropout_kernel(const float* __restrict__ y, const float* __restrict__ y2, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float eps, int relu, float p, unsigned long long seed,
+                                  const unsigned long long* __restrict__ salt, __nv_bfloat16* __restrict__ out, int R, int d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  if (salt) seed += *salt;
+  const uint32_t th = dropout_thresh(p);
+  const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  const float4* a = reinterpret_cast<const float4*>(y + (size_t)row * d);
+  const float4* b = y2 ? reinterpret_cast<const float4*>(y2 + (size_t)row * d) : nullptr;
+  const int n4 = d / 4;
+  float s = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    float4 v = a[i];
+    if (b) { const float4 w = b[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+  for (int i = lane; i < n4; i += 32) {
+    float4 v = a[i];
+    if (b) { const float4 w = b[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  for (int i = lane; i < n4; i += 32) {
+    float4 v = a[i];
+    if (b) { const float4 w = b[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + i);
+    float o[4];
+    o[0] = (v.x - mean) * rstd * g.x + be.x; o[1] = (v.y - mean) * rstd * g.y + be.y;
+    o[2] = (v.z - mean) * rstd * g.z + be.z; o[3] = (v.w - mean) * rstd * g.w + be.w;
+    const size_t idx = (size_t)row * d + 4 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (relu) o[k] = fmaxf(o[k], 0.f);
+      o[k] = (p > 0.f && !dropout_keep(seed, idx + k, th)) ? 0.f : o[k] * (p > 0.f ? scale : 1.f);
+    }
+    uint2 w;
+    w.x = t_pack(o[0], o[1]); w.y = t_pack(o[2], o[3]);
+    reinterpret_cast<uint2*>(out + (size_t)row * d)[i] = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward of  z = relu(LayerNorm(y + y2) * gamma + beta), zd = dropout(z):
 //   dz = dzd * keep/(1-p) * (z > 0);  du = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)),  dxh = dz * gamma
@@ -665,6 +717,23 @@ extern "C" int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p,
   const int blocks = (int)min((size_t)kNumSMs * 8, (n / 2 + 255) / 256 + 1);
   dropout_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y_bf16, n, p, seed, seed_salt);
   B200_CUDA_LAUNCH_CHECK("dropout_fwd");
+  return B200_OK;
+}
+
+extern "C" int b200_residual_layernorm_dropout(const float* y, const float* y2, const float* gamma, const float* beta, float eps,
+                                               int relu, float p, unsigned long long seed, const unsigned long long* seed_salt,
+                                               void* out_bf16, int R, int d, b200_stream_t stream) {
+  B200_CHECK_ARG(y && gamma && beta && out_bf16, "residual_layernorm_dropout: null tensor");
+  B200_CHECK_ARG(R >= 0 && d > 0 && d % 4 == 0, "residual_layernorm_dropout: d must be a multiple of 4");
+  B200_CHECK_ARG(p >= 0.f && p <= 1.f, "residual_layernorm_dropout: p must be in [0, 1]");
+  if ((((uintptr_t)y | (uintptr_t)y2 | (uintptr_t)gamma | (uintptr_t)beta) & 15) || ((uintptr_t)out_bf16 & 7)) {
+    set_error("residual_layernorm_dropout: fp32 operands must be 16-byte, the bf16 output 8-byte aligned");
+    return B200_ERR_UNSUPPORTED;
+  }
+  if (R == 0) return B200_OK;
+  residual_layernorm_dropout_kernel<<<ceil_div(R, 8), 256, 0, (cudaStream_t)stream>>>(y, y2, gamma, beta, eps, relu, p, seed, seed_salt,
+                                                                                      (__nv_bfloat16*)out_bf16, R, d);
+  B200_CUDA_LAUNCH_CHECK("residual_layernorm_dropout");
   return B200_OK;
 }
 

@@ -81,6 +81,15 @@ def dropout_bf16(x, p, seed, salt=None):
     return y
 
 
+def layernorm_relu_dropout_bf16(y, y2, gamma, beta, eps, p, seed, salt=None):
+    """bf16(dropout(relu(LayerNorm(y + y2) * gamma + beta))) in one pass — residual_layernorm + dropout_bf16 bit for bit."""
+    R, d = y.shape
+    out = torch.empty((R, d), dtype=torch.bfloat16, device=y.device)
+    _lib.call("b200_residual_layernorm_dropout", y.data_ptr(), _ptr(y2), gamma.data_ptr(), beta.data_ptr(), float(eps), 1,
+              float(p), int(seed), _ptr(salt), out.data_ptr(), R, d, _stream())
+    return out
+
+
 def head_losses(logits, deltas, attn, gt_classes, proposals, gt_boxes, K, weights, beta, acc_stats=None):
     """acc_stats (5,) fp32, optional: the counts of FastRCNNOutputs._log_accuracy from the same pass over the logits."""
     R = logits.shape[0]
@@ -380,8 +389,7 @@ class _FusedHeadTrain(torch.autograd.Function):
         hdn = g2(yb, W["Wf1"], bias=bf1, relu=True)
         y2 = f32e(d)
         g2(hdn, W["Wf2"], bias=bf2, out_f32=y2, want_out=False)
-        z, _ = residual_layernorm(y, y2, gam, bet, 1e-5, relu=True, want_f32=True, want_bf16=False)
-        zd = dropout_bf16(z, drop_p, seed, salt)
+        zd = layernorm_relu_dropout_bf16(y, y2, gam, bet, 1e-5, drop_p, seed, salt)   # sim2stext -> classifier input, one pass
         deltas = f32e(W["Wb"].shape[0])
         if cross:
             av = g2(zd, W["Wo"], bias=bo, relu=True)                               # relu(output_projection(sim2stext)), bf16

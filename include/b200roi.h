@@ -282,6 +282,12 @@ B200_API int b200_colsum(const void* src, int src_dtype, int ld, int rows, int c
  * mask on every replay. */
 B200_API int b200_dropout_fwd(const float* x, void* y_bf16, size_t n, float p, unsigned long long seed,
                      const unsigned long long* seed_salt, b200_stream_t stream);
+/* zd = bf16(dropout(relu?(LayerNorm(y + y2) * gamma + beta))): b200_residual_layernorm followed by b200_dropout_fwd in one pass,
+ * bit for bit (same statistics, same counter-based keep decision hash(seed + *seed_salt, row * d + col)); the fp32 intermediate
+ * is never written.  attentive_modules.py:73-74,285 + fast_rcnn.py:412-414. */
+B200_API int b200_residual_layernorm_dropout(const float* y, const float* y2, const float* gamma, const float* beta, float eps,
+                                    int relu, float p, unsigned long long seed, const unsigned long long* seed_salt,
+                                    void* out_bf16, int R, int d, b200_stream_t stream);
 /* backward of zd = dropout(relu(LayerNorm(y + y2))) (attentive_modules.py:73-74,285): du = dL/d(y + y2) as fp32
  * and/or bf16, dgamma / dbeta (may be NULL). */
 B200_API size_t b200_layernorm_bwd_workspace_bytes(int R, int d);

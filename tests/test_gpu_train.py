@@ -332,6 +332,25 @@ def test_dropout_statistics_and_backward_mask():
     assert torch.equal(train_ops.dropout_bf16(x, 0.8, 1231, salt=salt), train_ops.dropout_bf16(x, 0.8, 1234))
 
 
+@pytest.mark.parametrize("R,d,p", [(1000, 2048, 0.8), (77, 64, 0.5), (256, 512, 0.0), (33, 2048, 1.0)])
+def test_fused_layernorm_relu_dropout_equals_the_two_kernels(R, d, p):
+    """b200_residual_layernorm_dropout == b200_residual_layernorm (fp32 out) followed by b200_dropout_fwd, bit for bit: same
+    statistics, same keep decisions (the backward re-derives them from the same hash), no fp32 intermediate in memory."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops, train_ops
+    gen = torch.Generator().manual_seed(R + d)
+    y, y2 = torch.randn(R, d, generator=gen).cuda(), torch.randn(R, d, generator=gen).cuda()
+    gamma, beta = (torch.rand(d, generator=gen) + 0.5).cuda(), torch.randn(d, generator=gen).cuda()
+    salt = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    for s_ in (None, salt):
+        z, _ = ops.residual_layernorm(y, y2, gamma, beta, 1e-5, relu=True, want_f32=True, want_bf16=False)
+        ref = train_ops.dropout_bf16(z, p, 99, s_)
+        got = train_ops.layernorm_relu_dropout_bf16(y, y2, gamma, beta, 1e-5, p, 99, s_)
+        assert torch.equal(got, ref)
+    if 0.0 < p < 1.0:
+        keep = float((got != 0).float().mean()) / max(float((z > 0).float().mean()), 1e-9)
+        assert abs(keep - (1.0 - p)) < 0.02
+
+
 def test_flat_sgd_matches_torch_sgd():
     from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
     torch.manual_seed(0)
