@@ -410,11 +410,12 @@ class SematicRes5ROIHeads(Res5ROIHeads):
         losses, logits, self._acc_stats = train_ops.fused_head_train(
             feature_pooled, kq, vp, sa, pred, gt_classes, props, gtb, self.num_classes, self.box2box_transform.weights,
             self.smooth_l1_beta, drop, seed, cross is None, salt, teacher_logits, kd, cross)
-        out = {"loss_cls": losses[0], "loss_box_reg": losses[1]}
+        parts = train_ops.split_losses(losses)
+        out = {"loss_cls": parts[0], "loss_box_reg": parts[1]}
         if cross is None:
-            out["loss_attentive"] = losses[2]
+            out["loss_attentive"] = parts[2]
         if teacher_logits is not None:
-            out["loss_kl"] = losses[3]
+            out["loss_kl"] = parts[3]
         return out, logits
 
     def use_device_dropout_counter(self, enable=True):
