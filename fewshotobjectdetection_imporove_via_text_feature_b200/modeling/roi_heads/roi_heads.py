@@ -395,8 +395,9 @@ class SematicRes5ROIHeads(Res5ROIHeads):
             cur.wait_event(done)
             kq.record_stream(cur)
             vp.record_stream(cur)
-        props = cat([p.proposal_boxes.tensor for p in proposals], dim=0)
-        gtb = cat([p.gt_boxes.tensor for p in proposals], dim=0)
+        # per-image views of the sampler's batched outputs sit back to back: no copy kernel then
+        props = ops.cat_adjacent([p.proposal_boxes.tensor for p in proposals])
+        gtb = ops.cat_adjacent([p.gt_boxes.tensor for p in proposals])
         pred = self.box_predictor
         drop = pred._dropout_ratio if pred._do_cls_dropout else 0.0
         salt = getattr(self, "_drop_salt", None)
@@ -461,7 +462,7 @@ class SematicRes5ROIHeads(Res5ROIHeads):
             self._step_begin.record()
         if self.training:
             proposals = self.label_and_sample_proposals(proposals, targets)
-            gt_classes = cat([p.gt_classes for p in proposals], dim=0)
+            gt_classes = ops.cat_adjacent([p.gt_classes for p in proposals])
             self._mark("label_sample")
         elif test_with_gt:
             proposals = self.label_proposals(proposals, targets)

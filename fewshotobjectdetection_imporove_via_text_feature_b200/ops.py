@@ -288,7 +288,7 @@ def boxes_to_rois(box_tensors):
     """detectron2 convert_boxes_to_pooler_format: list[(Ri,4)] -> (rois (R,5), int32 offsets (N+1))."""
     dev = box_tensors[0].device
     idx, offs = _roi_index(tuple(int(b.shape[0]) for b in box_tensors), dev)
-    boxes = box_tensors[0] if len(box_tensors) == 1 else torch.cat(box_tensors, 0)
+    boxes = box_tensors[0] if len(box_tensors) == 1 else cat_adjacent(list(box_tensors))
     return torch.cat([idx, boxes.float()], dim=1), offs
 
 

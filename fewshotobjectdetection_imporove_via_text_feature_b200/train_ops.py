@@ -429,6 +429,7 @@ class _FusedHeadTrain(torch.autograd.Function):
                                  s.data_ptr() % 16 == 0 for s, p in zip(sinks, params)) else None
         ctx.sink_owners = params if ctx.sinks is not None else None
         ctx.mark_non_differentiable(logits, acc)
+        ctx.set_materialize_grads(False)             # no zero-filled gradients for the two non-differentiable outputs
         return losses, logits, acc
 
     @staticmethod
@@ -447,6 +448,8 @@ class _FusedHeadTrain(torch.autograd.Function):
         C1p, C4p, Lp = _rup(C1), _rup(C4), _rup(L)
         dev = x.device
         st = _stream()
+        if g_losses is None:                                 # nothing downstream used the losses
+            g_losses = torch.zeros(4 if ctx.kd[0] is not None else 3, device=x.device)
         g3 = g_losses.detach().float().contiguous()          # (3,) or, with the distillation loss, (4,)
 
         # ---- L1 backward ------------------------------------------------------------------------------------
