@@ -295,3 +295,58 @@ def test_gemm2_descriptor_fields_agree_everywhere():
     exec(block[block.index("class Gemm2Desc"):block.index("def linear_relu")], ns)
     assert [n for n, _ in ns["Gemm2Desc"]._fields_] == mirror
     assert ctypes.sizeof(ns["Gemm2Desc"]) == ctypes.sizeof(_lib.Gemm2Desc)
+
+
+def test_cat_adjacent_is_a_view_only_when_the_pieces_sit_back_to_back():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    base = torch.arange(24.0).reshape(6, 4)
+    parts = [base[0:2], base[2:5], base[5:6]]
+    v = ops.cat_adjacent(parts)
+    assert torch.equal(v, base) and v.data_ptr() == base.data_ptr()                     # view: no copy
+    gap = [base[0:2], base[3:5]]
+    c = ops.cat_adjacent(gap)
+    assert torch.equal(c, torch.cat(gap)) and c.data_ptr() != base.data_ptr()            # hole -> real concatenation
+    other = [base[0:2], torch.ones(3, 4)]
+    assert torch.equal(ops.cat_adjacent(other), torch.cat(other))
+    assert torch.equal(ops.cat_adjacent([base[1:3]]), base[1:3])
+
+
+def test_split_losses_backward_equals_indexing():
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import train_ops
+    w = torch.tensor([0.5, 2.0, -1.0, 3.0])
+    x1 = torch.tensor([1.0, 2.0, 3.0, 4.0], requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    a = train_ops.split_losses(x1 * w)
+    (a[0] + 3 * a[2] + a[3]).backward()                     # a[1] unused: its gradient arrives as None
+    y = x2 * w
+    (y[0] + 3 * y[2] + y[3]).backward()
+    assert torch.equal(x1.grad, x2.grad)
+
+
+def test_text_domination_operand_layout():
+    """300-d operands of LV_attention_textDomination in pitch-304 / 608 buffers: the padded weights reproduce linear3 / proj_value
+    on the padded concatenations exactly (zero weight columns under the gaps)."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, ops
+    from fewshotobjectdetection_imporove_via_text_feature_b200.modeling import roi_heads as RH
+    cfg = config.get_cfg()
+    cfg.MODEL.ADDITION.NAME = "glove"
+    torch.manual_seed(0)
+    m = RH.LV_attention_textDomination(64, cfg=cfg, class_embed=torch.randn(5, 300)).eval()
+    named = {k: v for k, v in m.named_parameters() if not k.startswith(("mlp_adapter", "proj_k"))}
+    w = ops.TextDominationWeights().refresh(named, (m.embed,))
+    d, h, dp, hp = w["d"], w["h"], w["dp"], w["hp"]
+    assert (d, h, dp, hp) == (300, 150, 304, 152)
+    o1, o2, q = torch.randn(7, h), torch.randn(7, h), torch.randn(7, d)
+    xcat = torch.zeros(7, 2 * dp)
+    xcat[:, :h], xcat[:, hp:hp + h], xcat[:, 2 * hp:2 * hp + d] = o1, o2, q
+    assert w["linear3.weight"].shape == (d, 2 * hp + d) and w["linear3.weight"].stride(0) == 2 * dp
+    W3 = w["linear3.weight"].float()
+    ref = torch.cat([o1, o2, q], 1) @ m.attention.linear3.weight.detach().to(torch.bfloat16).float().t()
+    torch.testing.assert_close(xcat[:, :2 * hp + d] @ W3.t(), ref, rtol=1e-5, atol=1e-5)
+    v300, t = torch.randn(7, d), torch.randn(7, d)
+    cat = torch.zeros(7, 2 * dp)
+    cat[:, :d], cat[:, dp:dp + d] = v300, t
+    ref = torch.cat([v300, t], 1) @ m.proj_value.weight.detach().to(torch.bfloat16).float().t()
+    torch.testing.assert_close(cat[:, :dp + d] @ w["proj_value.weight"].float().t(), ref, rtol=1e-5, atol=1e-5)
+    for k in ("linear1.weight", "linear2.weight", "ffn1.weight", "proj2.weight", "kq"):
+        assert w[k].stride(0) % 8 == 0 and w[k].stride(1) == 1, k
