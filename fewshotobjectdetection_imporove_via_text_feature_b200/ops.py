@@ -806,6 +806,7 @@ class TextFusionWeights:
 # inference chain: attention probabilities and gate operands as GEMM epilogues (False / B200_ATTN_EPILOGUES=0: the separate
 # fp32 attention kernel of round 1, kept for A/B runs and used by the training direction, which needs its fp32 operands)
 ATTENTION_AS_EPILOGUES = [_os.environ.get("B200_ATTN_EPILOGUES", "1") != "0"]
+GEMM2_INFERENCE_CHAIN = [_os.environ.get("B200_GEMM2_INFER", "1") != "0"]     # 0: the round-1 single-CTA GEMM for linear1-3 / FFN
 
 
 def text_fusion_forward(x, w, fold_query=True, score_bias=None):
@@ -839,12 +840,22 @@ def text_fusion_forward(x, w, fold_query=True, score_bias=None):
     else:
         q = gemm_bf16(xb, w["w_q.weight"], out_dtype=torch.bfloat16)
         attn = text_attention(q, x, w["kp"], w["vp"], p1, p2)
-    gemm_bf16(p1, w["linear1.0.weight"], w["linear1.0.bias"], relu=True, out=xcat[:, :h])
-    gemm_bf16(p2, w["linear2.0.weight"], w["linear2.0.bias"], relu=True, out=xcat[:, h:d])
-    yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
-    y = gemm_bf16(xcat, w["linear3.weight"], w["linear3.bias"], out2=yb)
-    hdn = gemm_bf16(yb, w["ffn.linear1.weight"], w["ffn.linear1.bias"], relu=True, out_dtype=torch.bfloat16)
-    y2 = gemm_bf16(hdn, w["ffn.linear2.weight"], w["ffn.linear2.bias"])
+    if GEMM2_INFERENCE_CHAIN[0] and d % 8 == 0 and h % 8 == 0:
+        # the CTA-pair kernel of the training direction (256-wide tiles, TMA-store epilogue, programmatic dependent launch)
+        gemm2(p1, w["linear1.0.weight"], bias=w["linear1.0.bias"], relu=True, out=xcat[:, :h])
+        gemm2(p2, w["linear2.0.weight"], bias=w["linear2.0.bias"], relu=True, out=xcat[:, h:d])
+        y = torch.empty((R, d), dtype=torch.float32, device=dev)
+        yb = gemm2(xcat, w["linear3.weight"], bias=w["linear3.bias"], out_f32=y)
+        hdn = gemm2(yb, w["ffn.linear1.weight"], bias=w["ffn.linear1.bias"], relu=True)
+        y2 = torch.empty((R, d), dtype=torch.float32, device=dev)
+        gemm2(hdn, w["ffn.linear2.weight"], bias=w["ffn.linear2.bias"], out_f32=y2, want_out=False)
+    else:
+        gemm_bf16(p1, w["linear1.0.weight"], w["linear1.0.bias"], relu=True, out=xcat[:, :h])
+        gemm_bf16(p2, w["linear2.0.weight"], w["linear2.0.bias"], relu=True, out=xcat[:, h:d])
+        yb = torch.empty((R, d), dtype=torch.bfloat16, device=dev)
+        y = gemm_bf16(xcat, w["linear3.weight"], w["linear3.bias"], out2=yb)
+        hdn = gemm_bf16(yb, w["ffn.linear1.weight"], w["ffn.linear1.bias"], relu=True, out_dtype=torch.bfloat16)
+        y2 = gemm_bf16(hdn, w["ffn.linear2.weight"], w["ffn.linear2.bias"])
     z, zb = residual_layernorm(y, y2, w["ffn.norm3.weight"], w["ffn.norm3.bias"], 1e-5, relu=True)
     return z, zb, attn, xb
 
