@@ -358,6 +358,8 @@ class Workload:
                     self.in_graph = self.world == 1 or os.environ.get("BENCH_GRAPH_ALLREDUCE", "1") == "1"
                     self.graph = train_ops.GraphedStep(lambda d: self.step(d, exchange=self.in_graph), self.resident)
                     self.graph_note = "whole step" if self.in_graph else "forward + backward (all-reduce and SGD outside)"
+                    # the resident inputs of the device-timed loop ARE the graph's static buffers: no per-step device copy
+                    self.resident = dict(self.graph.static_in)
                 except Exception as e:  # noqa: BLE001
                     self.graph, self.graph_note = None, "capture failed, running eagerly: %s" % str(e).splitlines()[0][:200]
                     self.head.use_device_dropout_counter(False)

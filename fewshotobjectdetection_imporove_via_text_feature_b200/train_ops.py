@@ -821,7 +821,11 @@ class GraphedStep:
         torch.cuda.synchronize()
 
     def __call__(self, inputs):
+        """Copy `inputs` into the graph's static buffers and replay.  An input that already IS its static buffer
+        (`step.static_in[k]`, e.g. the target of the caller's own host-to-device upload) is not copied."""
         for k, v in inputs.items():
-            self.static_in[k].copy_(v, non_blocking=True)
+            dst = self.static_in[k]
+            if v is not dst and (v.data_ptr() != dst.data_ptr() or v.shape != dst.shape):
+                dst.copy_(v, non_blocking=True)
         self.graph.replay()
         return self.static_out
