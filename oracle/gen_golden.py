@@ -362,6 +362,60 @@ def gen_train_step():
     np.savez_compressed(os.path.join(OUT, "train_step.npz"), **out)
 
 
+def gen_train_step_cross():
+    """C1' in the fine-tune direction, pinned on the reference's own modules: SematicRes5ROIHeadsCrossOutput.forward_att
+    (roi_heads.py:1154-1171: relu(output_projection(sim2stext)) . T^T as the class logits) + FastRCNNOutputs.losses
+    (fast_rcnn.py:222-304) in train mode and their autograd.  The head's own `forward` cannot run in training as checked in
+    (it calls `.items()` on the attention tensor forward_att returns in place of a loss dict), so the fixture stops where the
+    reference still runs: the two losses of the predictor."""
+    emb = lambda names, model, include_bg=False: rs.synthetic_class_embed(names, model, include_bg)
+    rs.install(class_embed_fn=emb)
+    am = rs.load("defrcn.modeling.roi_heads.attentive_modules")
+    am.get_class_embed = emb
+    rh = rs.load("defrcn.modeling.roi_heads.roi_heads")
+    fr = rs.load("defrcn.modeling.roi_heads.fast_rcnn")
+    K, R = 20, 96
+    cfg = rs.default_cfg(num_classes=K, addition="clip", output_layer="FastRCNNAttentionOutputLayers",
+                         roi_head="SematicRes5ROIHeadsCrossOutput")
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS = 8      # res5 out = 64
+    cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 1
+    cfg.MODEL.ROI_HEADS.CLS_DROPOUT = False
+    torch.manual_seed(21)
+    with cuda_as_cpu():
+        m = rh.build_roi_heads(cfg, {"res4": rs.ShapeSpec(channels=32, stride=16)}).train()
+        with torch.no_grad():
+            m.box_predictor.bbox_pred.weight.mul_(100.0)
+            m.output_projection.weight.mul_(6.0)
+            for p_ in m.attention.parameters():     # the 0.02-std init gives near-zero gradients: widen it
+                p_.mul_(4.0)
+        gen = torch.Generator().manual_seed(22)
+        d = m.out_channels
+        x = torch.relu(torch.randn(R, d, generator=gen)).requires_grad_(True)
+        h, w = 600, 800
+        props, _ = synth_proposals(R, h, w, gen)
+        gt_classes = torch.randint(0, K + 1, (R,), generator=gen)
+        gt_classes[R // 3:] = K
+        gt_boxes = props + torch.randn(R, 4, generator=gen) * 4
+        gt_boxes[:, 2:] = torch.maximum(gt_boxes[:, 2:], gt_boxes[:, :2] + 2)
+        inst = rs.Instances((h, w))
+        inst.proposal_boxes = rs.Boxes(props)
+        inst.gt_boxes = rs.Boxes(gt_boxes)
+        inst.gt_classes = gt_classes
+        att_output, _attn = m.forward_att(x, gt_classes)
+        o = fr.FastRCNNOutputs(m.box2box_transform, att_output["pred_logits"], att_output["pred_bbox"], [inst], m.smooth_l1_beta)
+        L = dict(o.losses())
+        sum(L.values()).backward()
+    out = {k: v for k, v in sd_to_np(m.state_dict()).items() if not k.startswith("res5.")}
+    out.update(x=x.detach().numpy(), props=props.numpy(), gt_boxes=gt_boxes.numpy(), gt_classes=gt_classes.numpy(),
+               embed=m.attention.embed.numpy(), bg_feature=m.attention.bg_feature.numpy(), grad_x=x.grad.numpy(),
+               text_feat=att_output["text_feat"].detach().numpy(), pred_logits=att_output["pred_logits"].detach().numpy(),
+               **{"loss." + k: v.detach().numpy() for k, v in L.items()})
+    for k, p_ in m.named_parameters():
+        if p_.grad is not None:
+            out["grad." + k] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "train_step_cross.npz"), **out)
+
+
 def gen_known_answer():
     """test.py:80-92 fixture: CE(pred_logits.pt, gt_classes.pt)."""
     pl = torch.load(os.path.join(rs.REFERENCE_ROOT, "pred_logits.pt"), map_location="cpu").detach()
@@ -555,6 +609,7 @@ def main():
     gen_pcb()
     gen_teacher()
     gen_train_step()
+    gen_train_step_cross()
     gen_known_answer()
     gen_cosine()
     gen_label_sample()

@@ -235,6 +235,58 @@ def test_cross_output_head_trains_on_the_fused_node():
         assert abs(float(out_f[k]) - float(ref_l[k])) <= 2e-2 * abs(float(ref_l[k])) + 1e-4, (k, float(out_f[k]), float(ref_l[k]))
 
 
+def test_cross_output_train_step_matches_reference_autograd(golden):
+    """C1' fine-tune direction against the reference's own SematicRes5ROIHeadsCrossOutput.forward_att + FastRCNNOutputs.losses
+    and their autograd (tests/golden/train_step_cross.npz, oracle/gen_golden.py:gen_train_step_cross): losses 2e-2; gradients
+    at the bf16-operand distance of this small fixture (8e-2 and cosine > 0.997 down the chain, 1e-2 at the box regressor) —
+    the same bars as test_fused_train_step_matches_reference_autograd; the 2e-2 bar proper is held against the restatement,
+    which tests/test_restatement_cpu.py pins on this very fixture to 1e-5."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import config, modeling
+    from fewshotobjectdetection_imporove_via_text_feature_b200.structures import ShapeSpec
+    g = golden("train_step_cross")
+    cfg = config.get_cfg()
+    cfg.MODEL.ROI_HEADS.NAME = "SematicRes5ROIHeadsCrossOutput"
+    cfg.MODEL.ROI_HEADS.OUTPUT_LAYER = "FastRCNNAttentionOutputLayers"
+    cfg.MODEL.ROI_HEADS.NUM_CLASSES = 20
+    cfg.MODEL.ADDITION.NAME = "clip"
+    cfg.MODEL.RESNETS.RES2_OUT_CHANNELS, cfg.MODEL.RESNETS.WIDTH_PER_GROUP = 8, 1
+    m = modeling.build_roi_heads(cfg, {"res4": ShapeSpec(channels=32, stride=16)})
+    sd = {k: torch.from_numpy(np.asarray(g[k])) for k in g.files
+          if k.startswith(("attention.", "box_predictor.", "output_projection", "sematic_projection", "projection_matrix"))}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("res5.", "teacher")) for k in missing), (missing, unexpected)
+    m.attention.embed = torch.from_numpy(np.asarray(g["embed"]))
+    m.attention.class_embed = m.attention.embed
+    m.attention.bg_feature = torch.from_numpy(np.asarray(g["bg_feature"]))
+    m = m.cuda().train()
+    assert m._fused_train_path()
+    props = _proposals(g)
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    losses, logits = m.fused_train_losses(x, props, props[0].gt_classes)
+    assert set(losses) == {"loss_cls", "loss_box_reg"}
+    for k in losses:
+        ref = float(g["loss." + k])
+        assert abs(float(losses[k]) - ref) <= 2e-2 * abs(ref) + 1e-4, (k, float(losses[k]), ref)
+    ref_logits = torch.from_numpy(g["pred_logits"])
+    torch.testing.assert_close(logits.detach().float().cpu(), ref_logits, rtol=2e-2, atol=2e-2 * float(ref_logits.abs().max()))
+    sum(losses.values()).backward()
+    gx = torch.from_numpy(g["grad_x"])
+    assert _rel(x.grad.cpu(), gx) < 0.1 and _cos(x.grad.cpu(), gx) > 0.995
+    worst = {}
+    for name, p in m.named_parameters():
+        key = "grad." + name
+        if key not in g.files:
+            continue
+        assert p.grad is not None, name
+        ref = torch.from_numpy(g[key])
+        if float(ref.abs().max()) < 1e-3 * float(torch.from_numpy(g["grad.output_projection.weight"]).abs().max()):
+            continue                                   # text-side tensors whose gradient vanishes on this fixture (1e-4 .. 1e-5)
+        worst[name] = (_rel(p.grad.cpu(), ref), _cos(p.grad.cpu(), ref))
+    assert len(worst) >= 18 and "output_projection.weight" in worst
+    bad = {k: v for k, v in worst.items() if v[0] >= (1e-2 if k.startswith("box_predictor") else 8e-2) or v[1] <= 0.997}
+    assert not bad, bad
+
+
 def test_fused_train_step_is_deterministic_and_matches_torch_path(golden):
     """Bitwise run-to-run reproducibility (ordered reductions, no atomics) and agreement with the differentiable torch
     expression of the same head (fp32 library GEMMs) on the same device."""
