@@ -69,6 +69,24 @@ def test_batched_nms_trick_vs_torchvision_nms():
     assert float((iou * same).max()) <= 0.5 + 1e-4
 
 
+def test_batched_nms_detectron2_rule_vs_torchvision():
+    """detectron2 v0.3's batched_nms switches at 40 000 boxes from the coordinate trick to a per-class loop on the un-offset
+    boxes; torchvision 0.26's own batched_nms takes the same per-class ("vanilla") route for large inputs on the CPU.  The
+    restatement agrees with it on both sides of the rule (distinct scores: the reference's final sort is unstable on ties)."""
+    gen = torch.Generator().manual_seed(17)
+    for n in (39999, 40000, 41000):
+        boxes, _ = synth_proposals(n, 600, 800, gen, n_obj=12)
+        scores = torch.rand(n, generator=gen, dtype=torch.float64).float()
+        scores = scores + torch.arange(n) * 1e-9                      # break accidental ties
+        idxs = torch.randint(0, 10, (n,), generator=gen)
+        keep = O.batched_nms_detectron2(boxes, scores, idxs, 0.5)
+        ref = torchvision.ops.batched_nms(boxes, scores, idxs, 0.5)
+        assert torch.equal(torch.sort(keep).values, torch.sort(ref).values), n
+        assert bool((scores[keep][:-1] >= scores[keep][1:]).all())
+        if len(torch.unique(scores[keep])) == len(keep):
+            assert torch.equal(keep, ref), n
+
+
 def test_voc_ap_sanity():
     gts = {0: np.array([[10, 10, 50, 50.0]]), 1: np.array([[20, 20, 80, 90.0], [100, 100, 150, 160.0]])}
     dets = [(0, 0.9, 11, 9, 50, 51), (1, 0.8, 21, 22, 79, 88), (1, 0.7, 0, 0, 10, 10), (1, 0.6, 101, 99, 149, 161)]
