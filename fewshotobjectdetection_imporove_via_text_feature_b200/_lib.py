@@ -113,6 +113,9 @@ KERNELS_PER_CALL = {
     "b200_rpn_select_proposals": 5, "b200_gather_rows_bf16": 1, "b200_kd_loss": 1, "b200_kd_loss_bwd": 1, "b200_spatial_mean_bits": 1, "b200_pack_relu_bits": 1, "b200_mean_bwd_relu_bits": 1, "b200_add_relu_bits": 1, "b200_class_mean_rows": 2, "b200_detector_postprocess": 1,
 }
 LAUNCHES = 0
+# mirror of `g_roi_bwd_impl`'s initial value in csrc/roi_align_bwd.cu (tests restore the option to it;
+# tests/test_abi_and_host.py checks the two agree)
+ROI_BWD_IMPL_DEFAULT = 1
 # bench.py sets PROFILE = {} to have a CUDA event pair recorded around every entry-point call (name -> [(e0, e1, tag)]);
 # None (the default) costs nothing
 PROFILE = None

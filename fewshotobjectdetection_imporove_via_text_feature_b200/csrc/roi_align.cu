@@ -550,7 +550,8 @@ extern "C" int b200_set_option(const char* key, int value) {
     return B200_OK;
   }
   if (strcmp(key, "roi_align_bwd_impl") == 0) {
-    B200_CHECK_ARG(value == 0 || value == 1, "set_option: roi_align_bwd_impl must be 0 (fp32 tables) or 1 (per-pixel CSR gather)");
+    B200_CHECK_ARG(value >= 0 && value <= 2,
+                   "set_option: roi_align_bwd_impl must be 0 (fp32 tables), 1 (per-pixel CSR gather) or 2 (pixel-tile tensor-core gather)");
     g_roi_bwd_impl = value;
     return B200_OK;
   }

@@ -18,8 +18,15 @@ int dispatch_affine(const void* x, const float* w, const float* b, float mult, v
 
 constexpr int kMaxP = 8;  // pooled size supported by the backward (the head uses 7)
 
-// 1 (default): per-pixel CSR gather (roi_align_bwd_slice.cu) for bf16 channels-last 7x7; 0: the table kernel below
+// bf16 channels-last 7x7 path — 2: pixel-tile gather on the tensor cores (roi_align_bwd_tile.cu; C % 64 == 0, else 1),
+// 1: per-pixel CSR gather (roi_align_bwd_slice.cu), 0: the table kernel below
 int g_roi_bwd_impl = 1;
+bool roi_bwd_tile_eligible(int C, int H, int W, int PH, int PW, int bin_step);
+size_t roi_bwd_tile_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step);
+int launch_roi_bwd_tile_plan(const float* rois, const int32_t* roi_offsets, int N, int H, int W, int R, int PH, int PW,
+                             int bin_step, float scale, int sr, int aligned, void* workspace, cudaStream_t st);
+int launch_roi_bwd_tile_gather(const __nv_bfloat16* g, const void* workspace, __nv_bfloat16* grad_feat, int N, int C, int H,
+                               int W, int R, int PH, int PW, int bin_step, cudaStream_t st);
 bool roi_bwd_slice_eligible(int C, int H, int W, int PH, int PW, int bin_step);
 size_t roi_bwd_slice_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step);
 int launch_roi_bwd_plan(const float* rois, const int32_t* roi_offsets, int N, int H, int W, int R, int PH, int PW,
@@ -201,6 +208,8 @@ extern "C" size_t b200_roi_align_bwd_workspace_bytes(int N, int C, int H, int W,
   if (grad_in_layout == B200_NCHW) b += align_up((size_t)N * C * H * W * e, 256);
   if (dtype == B200_BF16 && roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step))
     b = max(b, roi_bwd_slice_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step));
+  if (dtype == B200_BF16 && roi_bwd_tile_eligible(C, H, W, pooled_h, pooled_w, bin_step))
+    b = max(b, roi_bwd_tile_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step));
   return b;
 }
 
@@ -222,8 +231,16 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
     return B200_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (R > 0 && g_roi_bwd_impl == 1 && dtype == B200_BF16 && grad_out_layout == B200_NHWC && grad_in_layout == B200_NHWC &&
-      roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step) && (((uintptr_t)grad_out | (uintptr_t)grad_feat) & 15) == 0)
+  const bool cl16 = R > 0 && dtype == B200_BF16 && grad_out_layout == B200_NHWC && grad_in_layout == B200_NHWC &&
+                    (((uintptr_t)grad_out | (uintptr_t)grad_feat) & 15) == 0;
+  if (cl16 && g_roi_bwd_impl == 2 && roi_bwd_tile_eligible(C, H, W, pooled_h, pooled_w, bin_step)) {
+    int rc = launch_roi_bwd_tile_plan(rois, roi_batch_offsets, N, H, W, R, pooled_h, pooled_w, bin_step, spatial_scale,
+                                      sampling_ratio, aligned, workspace, st);
+    if (rc != B200_OK) return rc;
+    return launch_roi_bwd_tile_gather((const __nv_bfloat16*)grad_out, workspace, (__nv_bfloat16*)grad_feat, N, C, H, W, R,
+                                      pooled_h, pooled_w, bin_step, st);
+  }
+  if (cl16 && g_roi_bwd_impl >= 1 && roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step))
     return launch_roi_bwd_slice((const __nv_bfloat16*)grad_out, rois, roi_batch_offsets, (__nv_bfloat16*)grad_feat, N, C, H, W,
                                 R, pooled_h, pooled_w, bin_step, spatial_scale, sampling_ratio, aligned, workspace, st);
   unsigned char* p = (unsigned char*)workspace;
@@ -270,7 +287,11 @@ extern "C" int b200_roi_align_bwd(const void* grad_out, const float* rois, const
 extern "C" size_t b200_roi_align_bwd_plan_bytes(int N, int C, int H, int W, int R, int pooled_h, int pooled_w, int bin_step) {
   bin_step = max(bin_step, 1);
   if (N <= 0 || H <= 0 || W <= 0 || R < 0 || !roi_bwd_slice_eligible(C, H, W, pooled_h, pooled_w, bin_step)) return 0;
-  return roi_bwd_slice_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step);
+  // one size for both list formats, so that a plan buffer stays valid whichever "roi_align_bwd_impl" is selected
+  size_t b = roi_bwd_slice_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step);
+  if (roi_bwd_tile_eligible(C, H, W, pooled_h, pooled_w, bin_step))
+    b = max(b, roi_bwd_tile_workspace_bytes(N, H, W, R, pooled_h, pooled_w, bin_step));
+  return b;
 }
 
 extern "C" int b200_roi_align_bwd_plan(const float* rois, const int32_t* roi_batch_offsets, int N, int C, int H, int W, int R,
@@ -287,6 +308,10 @@ extern "C" int b200_roi_align_bwd_plan(const float* rois, const int32_t* roi_bat
     set_error("roi_align_bwd_plan: plan buffer too small (%zu < %zu)", plan_bytes, need);
     return B200_ERR_WORKSPACE;
   }
+  // the plan's format follows "roi_align_bwd_impl" at the time of the call; b200_roi_align_bwd_planned must see the same
+  if (g_roi_bwd_impl == 2 && roi_bwd_tile_eligible(C, H, W, pooled_h, pooled_w, bin_step))
+    return launch_roi_bwd_tile_plan(rois, roi_batch_offsets, N, H, W, R, pooled_h, pooled_w, bin_step, spatial_scale,
+                                    sampling_ratio, aligned, plan, (cudaStream_t)stream);
   return launch_roi_bwd_plan(rois, roi_batch_offsets, N, H, W, R, pooled_h, pooled_w, bin_step, spatial_scale, sampling_ratio,
                              aligned, plan, (cudaStream_t)stream);
 }
@@ -300,6 +325,9 @@ extern "C" int b200_roi_align_bwd_planned(const void* grad_out, const void* plan
     set_error("roi_align_bwd_planned: plan buffer does not match the shape (%zu < %zu)", plan_bytes, need);
     return B200_ERR_WORKSPACE;
   }
+  if (g_roi_bwd_impl == 2 && roi_bwd_tile_eligible(C, H, W, pooled_h, pooled_w, bin_step))
+    return launch_roi_bwd_tile_gather((const __nv_bfloat16*)grad_out, plan, (__nv_bfloat16*)grad_feat, N, C, H, W, R, pooled_h,
+                                      pooled_w, bin_step, (cudaStream_t)stream);
   return launch_roi_bwd_gather((const __nv_bfloat16*)grad_out, plan, (__nv_bfloat16*)grad_feat, N, C, H, W, R, pooled_h,
                                pooled_w, bin_step, (cudaStream_t)stream);
 }

@@ -350,3 +350,12 @@ def test_text_domination_operand_layout():
     torch.testing.assert_close(cat[:, :dp + d] @ w["proj_value.weight"].float().t(), ref, rtol=1e-5, atol=1e-5)
     for k in ("linear1.weight", "linear2.weight", "ffn1.weight", "proj2.weight", "kq"):
         assert w[k].stride(0) % 8 == 0 and w[k].stride(1) == 1, k
+
+
+def test_roi_bwd_impl_default_mirror():
+    """_lib.ROI_BWD_IMPL_DEFAULT (what tests restore "roi_align_bwd_impl" to) == the initial value in the CUDA source."""
+    import re
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+    src = open(os.path.join(os.path.dirname(_lib.__file__), "csrc", "roi_align_bwd.cu")).read()
+    m = re.search(r"^int g_roi_bwd_impl = (\d+);", src, re.M)
+    assert m and int(m.group(1)) == _lib.ROI_BWD_IMPL_DEFAULT

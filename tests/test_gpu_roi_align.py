@@ -177,7 +177,7 @@ def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
         _lib.set_option("roi_align_bwd_impl", 0)
         base = run()
     finally:
-        _lib.set_option("roi_align_bwd_impl", 1)
+        _lib.set_option("roi_align_bwd_impl", _lib.ROI_BWD_IMPL_DEFAULT)
         ops.PLAN_AHEAD[0] = True
     assert float((got.float() - base.float()).norm() / base.float().norm()) < 8e-3
 
@@ -297,3 +297,130 @@ def test_bwd_bf16_large_map_and_table_less_rois():
     assert float((gf - ref).norm() / ref.norm()) < 8e-3
     torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
     assert torch.equal(got, run())
+
+
+# ---- pixel-tile tensor-core gather (roi_align_bwd_tile.cu, "roi_align_bwd_impl" = 2) ------------------------------------
+class _bwd_impl:
+    def __init__(self, impl):
+        self.impl = impl
+
+    def __enter__(self):
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+        _lib.set_option("roi_align_bwd_impl", self.impl)
+
+    def __exit__(self, *exc):
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib, ops
+        _lib.set_option("roi_align_bwd_impl", _lib.ROI_BWD_IMPL_DEFAULT)
+        ops.PLAN_AHEAD[0] = True
+
+
+@pytest.mark.parametrize("N,C,H,W,R", [(2, 64, 38, 50, 90), (3, 128, 25, 31, 61), (1, 1024, 38, 50, 40), (2, 64, 7, 5, 300)])
+@pytest.mark.parametrize("bin_step", [1, 2])
+def test_bwd_bf16_tile_gather(N, C, H, W, R, bin_step):
+    """Pixel-tile gather backward (4 x 4-pixel tiles, mma.sync tf32; roi_align_bwd_tile.cu) vs the CPU oracle at the same
+    bars as the per-pixel CSR gather, vs that gather itself, bitwise run to run and plan-ahead == plan-inside-the-call
+    (the plan's blocks are placed by an integer atomic; their content is ordered).  Map sizes that are not multiples of
+    the tile, a map smaller than two tiles with more ROIs than one builder round."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    scale = 1 / 16
+    x, rois, offs = _inputs(N, C, H, W, R, scale, 29)
+    nb = -(-7 // bin_step)
+    g = torch.randn(R, C, nb, nb, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16)
+    gfull = torch.zeros(R, C, 7, 7)
+    gfull[:, :, ::bin_step, ::bin_step] = g.float()
+    ref = O.roi_align_bwd(gfull, rois, x.shape, scale, 0, True)
+    xd = x.to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    gd = g.cuda().contiguous(memory_format=torch.channels_last)
+
+    def run():
+        xin = xd.clone().requires_grad_(True)
+        out = ops.roi_align(xin, rois.cuda(), 7, scale, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda(),
+                            bin_step=bin_step)
+        out.backward(gd)
+        return xin.grad
+    with _bwd_impl(2):
+        got = run()
+        assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+        gf = got.float().cpu().contiguous()
+        assert float((gf - ref).norm() / ref.norm()) < 8e-3
+        torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+        assert torch.equal(got, run())
+        ops.PLAN_AHEAD[0] = False
+        assert torch.equal(got, run())
+    with _bwd_impl(1):
+        base = run()
+    assert float((got.float() - base.float()).norm() / base.float().norm()) < 6e-3
+
+
+def test_bwd_bf16_tile_gather_empty_image_fixed_grid_and_table_less_rois():
+    """impl 2 on the edge cases of the CSR gather's tests: an image without ROIs in the middle of the batch (zeros
+    written), sparse fixed sampling grids and ROIs wider than 8 samples per bin (per-sample path of the plan builder),
+    boxes partly outside the map, a 50 x 84 map."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    gen = torch.Generator().manual_seed(6)
+    x = torch.relu(torch.randn(3, 64, 20, 24, generator=gen)).to(torch.bfloat16)
+    b0 = synth_proposals(17, 320, 384, gen)[0]
+    b2 = synth_proposals(9, 320, 384, gen)[0]
+    b2[0] = torch.tensor([-40.0, -30.0, 500.0, 400.0])
+    rois = O.boxes_to_rois([b0, b0[:0], b2])
+    offs = torch.tensor([0, 17, 17, 26], dtype=torch.int32)
+    g = torch.randn(26, 64, 7, 7, generator=gen).to(torch.bfloat16)
+    with _bwd_impl(2):
+        for sr in (0, 1, 2):
+            ref = O.roi_align_bwd(g.float(), rois, x.shape, 1 / 16, sr, True)
+            xin = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, sr, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+            out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+            gf = xin.grad.float().cpu().contiguous()
+            assert float(gf[1].abs().max()) == 0.0
+            assert float((gf - ref).norm() / ref.norm()) < 8e-3, sr
+            torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+        N, C, H, W = 2, 64, 50, 84
+        x = torch.relu(torch.randn(N, C, H, W, generator=gen)).to(torch.bfloat16)
+        boxes = []
+        for n in range(N):
+            b = synth_proposals(40, 800, 1333, gen)[0]
+            b[0] = torch.tensor([3.0, 5.0, 1330.0, 795.0])
+            b[1] = torch.tensor([100.0, 20.0, 1300.0, 400.0])
+            boxes.append(b)
+        rois = O.boxes_to_rois(boxes)
+        offs = torch.tensor([0, 40, 80], dtype=torch.int32)
+        g = torch.randn(80, C, 7, 7, generator=gen).to(torch.bfloat16)
+        ref = O.roi_align_bwd(g.float(), rois, x.shape, 1 / 16, 0, True)
+
+        def run():
+            xin = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+            out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+            return xin.grad
+        got = run()
+        gf = got.float().cpu().contiguous()
+        assert float((gf - ref).norm() / ref.norm()) < 8e-3
+        torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+        assert torch.equal(got, run())
+
+
+def test_bwd_bf16_tile_gather_full_size_adjoint():
+    """BASELINE size (8 x 512 ROIs, C = 1024, 38 x 50, the 16 live bins): <roi_align(x), g> == <x, backward(g)> through
+    impl 2, and impl 2 against the per-pixel gather elementwise."""
+    from fewshotobjectdetection_imporove_via_text_feature_b200 import ops
+    N, C, H, W, P = 8, 1024, 38, 50, 512
+    gen = torch.Generator().manual_seed(12)
+    x = torch.relu(torch.randn(N, C, H, W, generator=gen)).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    boxes = [synth_proposals(P, 600, 800, gen, n_obj=8)[0].cuda() for _ in range(N)]
+    rois, offs = ops.boxes_to_rois(boxes)
+    g = torch.randn(N * P, C, 4, 4, generator=gen).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+
+    def run():
+        xin = x.clone().requires_grad_(True)
+        out = ops.roi_align(xin, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs, bin_step=2)
+        out.backward(g)
+        return out.detach(), xin.grad
+    with _bwd_impl(2):
+        out, got = run()
+    with _bwd_impl(1):
+        _, base = run()
+    lhs, rhs = (out.double() * g.double()).sum(), (x.double() * got.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-2 * abs(float(lhs))      # bf16 weights forward, tf32 backward, bf16 outputs
+    torch.testing.assert_close(got.float(), base.float(), rtol=2e-2, atol=2e-2 * float(base.float().abs().max()))
+    assert float((got.float() - base.float()).norm() / base.float().norm()) < 6e-3

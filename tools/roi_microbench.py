@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--impls", default="0,2")
     ap.add_argument("--steps", default="1,2")
+    ap.add_argument("--variants", default="0,1,2,3,4", help="backward variants to time (see bench_bwd)")
     ap.add_argument("--bwd", action="store_true", help="time the backward (b200_roi_align_bwd entry point) instead")
     a = ap.parse_args()
     B, P, C, H, W = a.images, a.props, 1024, 38, 50
@@ -68,9 +69,12 @@ def bench_bwd(a, feat, rois, offs, flush):
         nbytes = B * C * H * W * 2 + B * P * 20 + B * P * C * nb * nb * 2
         g = torch.randn(B * P, C, nb, nb, device=feat.device).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         res = {}
-        for impl in (0, 1, 2):          # 0: fp32-table kernel, 1: CSR lists built inside the call, 2: lists planned ahead
-            _lib.set_option("roi_align_bwd_impl", min(impl, 1))
-            ops.PLAN_AHEAD[0] = impl == 2
+        # 0: fp32-table kernel, 1: CSR lists built inside the call, 2: CSR lists planned ahead,
+        # 3: pixel-tile tensor-core gather with the plan built inside the call, 4: tile plan built ahead
+        variants = [int(v) for v in a.variants.split(",")]
+        for impl in variants:
+            _lib.set_option("roi_align_bwd_impl", {0: 0, 1: 1, 2: 1, 3: 2, 4: 2}[impl])
+            ops.PLAN_AHEAD[0] = impl in (2, 4)
             x = feat.clone().requires_grad_(True)
             out = ops.roi_align(x, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs, bin_step=step)
             ts = []
@@ -88,9 +92,14 @@ def bench_bwd(a, feat, rois, offs, flush):
             res[impl] = x.grad.float()
             print("bwd bin_step=%d impl=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
                   (step, impl, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
+        if len(variants) < 5:
+            continue
         d = (res[1] - res[0]).norm() / res[0].norm()
-        print("   rel |impl 1 - impl 0| = %.3g, impl 2 == impl 1: %s" % (d.item(), torch.equal(res[1], res[2])))
-    _lib.set_option("roi_align_bwd_impl", 1)
+        d3 = (res[3] - res[0]).norm() / res[0].norm()
+        print("   rel |impl 1 - impl 0| = %.3g, impl 2 == impl 1: %s; rel |impl 3 - impl 0| = %.3g, impl 4 == impl 3: %s" %
+              (d.item(), torch.equal(res[1], res[2]), d3.item(), torch.equal(res[3], res[4])))
+    _lib.set_option("roi_align_bwd_impl", _lib.ROI_BWD_IMPL_DEFAULT)
+    ops.PLAN_AHEAD[0] = True
 
 
 if __name__ == "__main__":
