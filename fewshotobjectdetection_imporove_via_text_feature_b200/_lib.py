@@ -105,7 +105,7 @@ class B200Error(RuntimeError):
 # kernels launched per entry point (upper bound for the optional layout-conversion launches is counted where it
 # happens); used by bench.py to report `gpu_launches`
 KERNELS_PER_CALL = {
-    "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 3, "b200_roi_align_bwd_planned": 1,
+    "b200_gdl_affine_fwd": 1, "b200_gdl_affine_bwd": 3, "b200_roi_align_fwd": 1, "b200_roi_align_bwd": 2, "b200_roi_align_bwd_plan": 2, "b200_roi_align_bwd_planned": 1,
     "b200_softmax_decode_compact": 2, "b200_batched_nms": 3, "b200_gather_detections": 1, "b200_pcb_cosine_blend": 1,
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm2": 1, "b200_transpose_bf16": 1, "b200_colsum": 2, "b200_dropout_fwd": 1, "b200_residual_layernorm_dropout": 1,
     "b200_layernorm_relu_dropout_bwd": 4, "b200_layernorm_param_grads": 3, "b200_text_attention_bwd": 1, "b200_head_losses": 1, "b200_head_losses_bwd": 1,
@@ -115,7 +115,7 @@ KERNELS_PER_CALL = {
 LAUNCHES = 0
 # mirror of `g_roi_bwd_impl`'s initial value in csrc/roi_align_bwd.cu (tests restore the option to it;
 # tests/test_abi_and_host.py checks the two agree)
-ROI_BWD_IMPL_DEFAULT = 1
+ROI_BWD_IMPL_DEFAULT = 2
 # bench.py sets PROFILE = {} to have a CUDA event pair recorded around every entry-point call (name -> [(e0, e1, tag)]);
 # None (the default) costs nothing
 PROFILE = None

@@ -539,7 +539,7 @@ static int make_feature_map(CUtensorMap* m, const void* ptr, int N, int C, int H
 
 }  // namespace b200
 
-namespace b200 { extern int g_gemm_ctas; extern int g_gemm_generic_epilogue; }
+namespace b200 { extern int g_gemm_ctas; extern int g_gemm_generic_epilogue; extern int g_roi_bwd_tile_variant; }
 using namespace b200;
 
 extern "C" int b200_set_option(const char* key, int value) {
@@ -553,6 +553,11 @@ extern "C" int b200_set_option(const char* key, int value) {
     B200_CHECK_ARG(value >= 0 && value <= 2,
                    "set_option: roi_align_bwd_impl must be 0 (fp32 tables), 1 (per-pixel CSR gather) or 2 (pixel-tile tensor-core gather)");
     g_roi_bwd_impl = value;
+    return B200_OK;
+  }
+  if (strcmp(key, "roi_bwd_tile_variant") == 0) {
+    B200_CHECK_ARG(value >= 0 && value <= 2, "set_option: roi_bwd_tile_variant must be in [0, 2]");
+    g_roi_bwd_tile_variant = value;
     return B200_OK;
   }
   if (strcmp(key, "gemm_generic_epilogue") == 0) {

@@ -20,7 +20,7 @@ constexpr int kMaxP = 8;  // pooled size supported by the backward (the head use
 
 // bf16 channels-last 7x7 path — 2: pixel-tile gather on the tensor cores (roi_align_bwd_tile.cu; C % 64 == 0, else 1),
 // 1: per-pixel CSR gather (roi_align_bwd_slice.cu), 0: the table kernel below
-int g_roi_bwd_impl = 1;
+int g_roi_bwd_impl = 2;
 bool roi_bwd_tile_eligible(int C, int H, int W, int PH, int PW, int bin_step);
 size_t roi_bwd_tile_workspace_bytes(int N, int H, int W, int R, int PH, int PW, int bin_step);
 int launch_roi_bwd_tile_plan(const float* rois, const int32_t* roi_offsets, int N, int H, int W, int R, int PH, int PW,

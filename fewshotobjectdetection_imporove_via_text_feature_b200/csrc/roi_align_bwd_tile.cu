@@ -36,7 +36,6 @@ constexpr int kBlkABytes = 32 * 16;           // uint4 per lane: A fragment {a0,
 constexpr int kBlkBytes = kBlkABytes + kBlkEntries * 4;   // + the gradient row of each entry
 constexpr int kTileChunk = 64;                // channels per warp of the gather kernel
 constexpr int kTileWarps = 8;
-constexpr int kTileUnroll = 2;                // plan blocks in flight per warp
 constexpr int kBuildThreads = 256;
 
 __device__ __forceinline__ void mma_bf16_16816(float* d, const uint4 a, uint32_t b0, uint32_t b1) {
@@ -224,13 +223,38 @@ roi_bwd_tile_build_kernel(const unsigned char* __restrict__ recs, const float* _
   for (int e = total + (int)threadIdx.x; e < padded; e += kBuildThreads) tile_write_entry(blocks, base, e, 0, zero, zero, 0.f);
 }
 
-// grid ceil(tiles * (C / 64) / kTileWarps), block kTileWarps warps; warp = (tile, 64 channels)
-__global__ void __launch_bounds__(kTileWarps * 32, 2)
+// 16 bytes (NT = 8) or 8 bytes (NT = 4) of one gradient row
+template <int NT> struct RowSeg;
+template <> struct RowSeg<8> {
+  uint32_t w[4];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  }
+};
+template <> struct RowSeg<4> {
+  uint32_t w[2];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    w[0] = v.x; w[1] = v.y;
+  }
+};
+
+// grid ceil(tiles * (C / (8 NT)) / kTileWarps), block kTileWarps warps; warp = (tile, 8 NT channels): NT n-tiles, lane
+// (g, t) loads channels NT g .. NT g + NT - 1 of its four entries and feeds channel NT g + j to n-tile j, so that its
+// accumulators are the 2 NT consecutive channels [2 NT t, 2 NT t + 2 NT) of tile pixels g and g + 8.
+// kUnroll plan blocks per iteration, optionally double-buffered in registers, kMinCtas CTAs per SM.  Measured
+// (profiles/r02_roi_bwd_tile_variants.txt): one block per iteration beats two (0.072 vs 0.094 ms), register double
+// buffering and a per-warp cp.async ring in shared memory (2 x the L2 sectors: 16-byte LDGSTS requests do not coalesce
+// into sectors across lanes; MIO throttle) were slower than the plain loop.
+template <int kUnroll, bool kDouble, int kMinCtas, int NT>
+__global__ void __launch_bounds__(kTileWarps * 32, kMinCtas)
 roi_bwd_tile_gather_kernel(const __nv_bfloat16* __restrict__ g, const int2* __restrict__ tiles,
                            const unsigned char* __restrict__ blocks, __nv_bfloat16* __restrict__ grad_feat, int ntiles, int H,
                            int W, int TYn, int TXn, int C) {
+  constexpr int kChunk = 8 * NT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = C / kTileChunk;
+  const int chunks = C / kChunk;
   const long long wi = (long long)blockIdx.x * kTileWarps + warp;
   if (wi >= (long long)ntiles * chunks) return;
   const int tile = (int)(wi / chunks), chunk = (int)(wi - (long long)tile * chunks);
@@ -238,17 +262,17 @@ roi_bwd_tile_gather_kernel(const __nv_bfloat16* __restrict__ g, const int2* __re
   const int2 td = __ldg(tiles + tile);
   const unsigned char* bp = blocks + (size_t)(unsigned)td.x * kBlkBytes;
   const int nblk = td.y;
-  const __nv_bfloat16* gc = g + chunk * kTileChunk + gq * 8;
+  const __nv_bfloat16* gc = g + chunk * kChunk + gq * NT;
 
-  float acc[8][4];
+  float acc[NT][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
   // rows of the entries this lane loads, one iteration ahead of the gradient loads that need them
-  int2 rlo[kTileUnroll], rhi[kTileUnroll];
+  int2 rlo[kUnroll], rhi[kUnroll];
   auto load_rows = [&](int b) {
 #pragma unroll
-    for (int u = 0; u < kTileUnroll; ++u) {
+    for (int u = 0; u < kUnroll; ++u) {
       rlo[u] = rhi[u] = make_int2(0, 0);
       if (b + u < nblk) {
         const int2* rows = reinterpret_cast<const int2*>(bp + (size_t)(b + u) * kBlkBytes + kBlkABytes);
@@ -257,68 +281,92 @@ roi_bwd_tile_gather_kernel(const __nv_bfloat16* __restrict__ g, const int2* __re
       }
     }
   };
-  load_rows(0);
-  for (int b = 0; b < nblk; b += kTileUnroll) {
-    uint4 af[kTileUnroll];
-    uint4 d[kTileUnroll][4];
+  struct Buf {
+    RowSeg<NT> d[kUnroll][4];
+  };
+  auto issue = [&](Buf& q, int b) {                    // rlo / rhi hold the rows of blocks [b, b + kUnroll)
 #pragma unroll
-    for (int u = 0; u < kTileUnroll; ++u) {
+    for (int u = 0; u < kUnroll; ++u) {
       if (b + u < nblk) {
-        d[u][0] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)rlo[u].x * C));
-        d[u][1] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)rlo[u].y * C));
-        d[u][2] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)rhi[u].x * C));
-        d[u][3] = __ldg(reinterpret_cast<const uint4*>(gc + (size_t)rhi[u].y * C));
-        af[u] = __ldg(reinterpret_cast<const uint4*>(bp + (size_t)(b + u) * kBlkBytes) + lane);
-      } else {
-        d[u][0] = d[u][1] = d[u][2] = d[u][3] = af[u] = make_uint4(0u, 0u, 0u, 0u);
+        q.d[u][0].load(gc + (size_t)rlo[u].x * C);
+        q.d[u][1].load(gc + (size_t)rlo[u].y * C);
+        q.d[u][2].load(gc + (size_t)rhi[u].x * C);
+        q.d[u][3].load(gc + (size_t)rhi[u].y * C);
       }
     }
-    load_rows(b + kTileUnroll);
+  };
+  auto compute = [&](const Buf& q, int b) {
+    // the A fragments share their plan block (and cache lines) with the row indices fetched earlier
+    uint4 af[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kTileUnroll; ++u) {
+    for (int u = 0; u < kUnroll; ++u)
+      if (b + u < nblk) af[u] = __ldg(reinterpret_cast<const uint4*>(bp + (size_t)(b + u) * kBlkBytes) + lane);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
       if (b + u < nblk) {                               // warp-uniform
-        const uint32_t e0[4] = {d[u][0].x, d[u][0].y, d[u][0].z, d[u][0].w};
-        const uint32_t e1[4] = {d[u][1].x, d[u][1].y, d[u][1].z, d[u][1].w};
-        const uint32_t e8[4] = {d[u][2].x, d[u][2].y, d[u][2].z, d[u][2].w};
-        const uint32_t e9[4] = {d[u][3].x, d[u][3].y, d[u][3].z, d[u][3].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // channel 8 * gq + j of entries (2t, 2t + 1) and (2t + 8, 2t + 9): the lower half-word is the lower K index
+        for (int j = 0; j < NT; ++j) {
+          // channel NT * gq + j of entries (2t, 2t + 1) and (2t + 8, 2t + 9): the lower half-word is the lower K index
           const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
-          const uint32_t b0 = __byte_perm(e0[j >> 1], e1[j >> 1], sel);
-          const uint32_t b1 = __byte_perm(e8[j >> 1], e9[j >> 1], sel);
+          const uint32_t b0 = __byte_perm(q.d[u][0].w[j >> 1], q.d[u][1].w[j >> 1], sel);
+          const uint32_t b1 = __byte_perm(q.d[u][2].w[j >> 1], q.d[u][3].w[j >> 1], sel);
           mma_bf16_16816(acc[j], af[u], b0, b1);
         }
       }
     }
+  };
+  load_rows(0);
+  if (kDouble) {
+    Buf qa, qb;
+    issue(qa, 0);
+    load_rows(kUnroll);
+    for (int b = 0; b < nblk; b += 2 * kUnroll) {
+      issue(qb, b + kUnroll);
+      load_rows(b + 2 * kUnroll);
+      compute(qa, b);
+      issue(qa, b + 2 * kUnroll);
+      load_rows(b + 3 * kUnroll);
+      compute(qb, b + kUnroll);
+    }
+  } else {
+    Buf q;
+    for (int b = 0; b < nblk; b += kUnroll) {
+      issue(q, b);
+      load_rows(b + kUnroll);
+      compute(q, b);
+    }
   }
 
-  // lane (gq, t): channels [16 t, 16 t + 16) of the chunk for tile pixels gq (c0: +j, c1: +8 + j) and gq + 8 (c2, c3)
   const int tpi = TYn * TXn;
   const int n = tile / tpi, tl = tile - n * tpi;
   const int ty0 = (tl / TXn) * kTileSide, tx0 = (tl % TXn) * kTileSide;
   const int x = tx0 + (gq & 3);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const int y = ty0 + (gq >> 2) + 2 * half;
+    const int y = ty0 + (gq >> 2) + 2 * half;                 // tile pixel gq (c0, c1) / gq + 8 (c2, c3)
     if (y < H && x < W) {
-      uint4 o0, o1;
-      uint32_t p[8];
+      uint32_t p[NT];                                           // channels 2 NT t + [0, NT) from c0 / c2, + [NT, 2 NT) from c1 / c3
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
+      for (int j = 0; j < NT; j += 2) {
         const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[j][2 * half], acc[j + 1][2 * half]);
         const __nv_bfloat162 hi = __floats2bfloat162_rn(acc[j][2 * half + 1], acc[j + 1][2 * half + 1]);
         p[j >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
-        p[4 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hi);
+        p[NT / 2 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hi);
       }
-      o0 = make_uint4(p[0], p[1], p[2], p[3]);
-      o1 = make_uint4(p[4], p[5], p[6], p[7]);
-      uint4* dst = reinterpret_cast<uint4*>(grad_feat + ((size_t)(n * H + y) * W + x) * C + chunk * kTileChunk + 16 * t);
-      dst[0] = o0;
-      dst[1] = o1;
+      __nv_bfloat16* dst = grad_feat + ((size_t)(n * H + y) * W + x) * C + chunk * kChunk + 2 * NT * t;
+      if (NT == 8) {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(p[NT - 4], p[NT - 3], p[NT - 2], p[NT - 1]);
+      } else {
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(p[0], p[1], p[2], p[3]);
+      }
     }
   }
 }
+
+// pipelining variant of the gather kernel ("roi_bwd_tile_variant" option: A/B measurement aid, every variant gives the
+// same bits; profiles/r02_roi_bwd_tile_variants.txt)
+int g_roi_bwd_tile_variant = 0;
 
 bool roi_bwd_tile_eligible(int C, int H, int W, int PH, int PW, int bin_step) {
   return PH <= 7 && PW <= 7 && bin_step >= 1 && C % kTileChunk == 0 && H <= 256 && W <= 256;
@@ -386,9 +434,18 @@ int launch_roi_bwd_tile_gather(const __nv_bfloat16* g, const void* workspace, __
   const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
   const TilePlan pl = carve_tile_plan(const_cast<void*>(workspace), N, H, W, R, PHO, PWO);
   const int ntiles = N * pl.TYn * pl.TXn;
-  const long long warps = (long long)ntiles * (C / kTileChunk);
-  roi_bwd_tile_gather_kernel<<<(unsigned)((warps + kTileWarps - 1) / kTileWarps), kTileWarps * 32, 0, st>>>(
-      g, pl.tiles, pl.blocks, grad_feat, ntiles, H, W, pl.TYn, pl.TXn, C);
+#define B200_TILE_GATHER(U, DB, MINB, NT)                                                                            \
+  do {                                                                                                                 \
+    const long long warps = (long long)ntiles * (C / (8 * NT));                                                        \
+    roi_bwd_tile_gather_kernel<U, DB, MINB, NT><<<(unsigned)((warps + kTileWarps - 1) / kTileWarps), kTileWarps * 32, 0, st>>>( \
+        g, pl.tiles, pl.blocks, grad_feat, ntiles, H, W, pl.TYn, pl.TXn, C);                                            \
+  } while (0)
+  switch (g_roi_bwd_tile_variant) {
+    case 1: B200_TILE_GATHER(2, false, 2, 8); break;    // two plan blocks per iteration, 16 warps / SM: 0.094 ms (16 bins)
+    case 2: B200_TILE_GATHER(1, false, 4, 4); break;    // 32-channel warps, 32 warps / SM: 0.083 ms
+    default: B200_TILE_GATHER(1, false, 3, 8); break;   // one block per iteration, 24 warps / SM: 0.072 ms
+  }
+#undef B200_TILE_GATHER
   B200_CUDA_LAUNCH_CHECK("roi_bwd_tile_gather");
   return B200_OK;
 }

@@ -239,8 +239,9 @@ class _ROIAlign(torch.autograd.Function):
         _lib.call("b200_roi_align_bwd", g.data_ptr(), rois.data_ptr(), offs.data_ptr(), gin.data_ptr(), N, C, H, W, R,
                   PH, PW, int(bin_step), float(scale), int(sr), int(bool(aligned)), _dt(g), g_layout, in_layout,
                   ws.data_ptr(), nbytes, _stream(),
-                  launches=4 if (g.dtype == torch.bfloat16 and cl_out and in_layout == NHWC and PH <= 7 and PW <= 7 and
-                                 C % 8 == 0 and H <= 256 and W <= 256) else 2)   # CSR path: prepare, count, fill, gather
+                  launches=(3 if C % 64 == 0 else 4) if (g.dtype == torch.bfloat16 and cl_out and in_layout == NHWC and PH <= 7 and
+                                                         PW <= 7 and C % 8 == 0 and H <= 256 and W <= 256) else 2)
+        # tile path: prepare, build, gather; per-pixel CSR path (C % 64 != 0): prepare, count, fill, gather
         return gin, None, None, None, None, None, None, None, None
 
 

@@ -46,7 +46,11 @@ B200_API const char* b200_last_error(void);
 /* process-wide implementation switches (for A/B measurement; results are parity-tested under every setting):
  *   "roi_align_bf16_impl": 0 = CUDA-core per-bin-window kernel, 1 = per-ROI TMA + ldmatrix + mma.sync kernel,
  *                          2 = slice-resident TMA + ldmatrix + mma.sync kernel (default; needs roi_batch_offsets)
- *   "roi_align_bwd_impl":  0 = per-pixel gather kernel, 1 = slice-resident row-owner kernel (default, bf16 NHWC 7x7) */
+ *   "roi_align_bwd_impl":  bf16 NHWC 7x7 path — 0 = fp32 weight-table row kernel, 1 = per-pixel CSR gather,
+ *                          2 = 4x4-pixel-tile gather on mma.sync (default; C % 64 == 0, else 1).  The format of a
+ *                          b200_roi_align_bwd_plan buffer follows the setting at plan time; b200_roi_align_bwd_planned
+ *                          must be called under the same setting
+ *   "roi_bwd_tile_variant": 0 (default) / 1 / 2 = pipelining variants of the tile gather, same bits */
 B200_API int b200_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------

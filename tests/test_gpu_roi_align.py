@@ -165,6 +165,7 @@ def test_bwd_bf16_slice_resident(N, C, H, W, R, bin_step):
                             bin_step=bin_step)
         out.backward(gd)
         return xin.grad
+    _lib.set_option("roi_align_bwd_impl", 1)
     got = run()
     assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
     gf = got.float().cpu().contiguous()
@@ -198,8 +199,9 @@ def test_bwd_bf16_csr_empty_image_and_fixed_grid():
     for sr in (0, 1, 2):
         ref = O.roi_align_bwd(g.float(), rois, x.shape, 1 / 16, sr, True)
         xin = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, sr, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
-        out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+        with _bwd_impl(1):
+            out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, sr, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
+            out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
         gf = xin.grad.float().cpu().contiguous()
         assert float(gf[1].abs().max()) == 0.0
         assert float((gf - ref).norm() / ref.norm()) < 8e-3, sr
@@ -292,11 +294,12 @@ def test_bwd_bf16_large_map_and_table_less_rois():
         out = ops.roi_align(xin, rois.cuda(), 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs.cuda())
         out.backward(g.cuda().contiguous(memory_format=torch.channels_last))
         return xin.grad
-    got = run()
-    gf = got.float().cpu().contiguous()
-    assert float((gf - ref).norm() / ref.norm()) < 8e-3
-    torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
-    assert torch.equal(got, run())
+    with _bwd_impl(1):
+        got = run()
+        gf = got.float().cpu().contiguous()
+        assert float((gf - ref).norm() / ref.norm()) < 8e-3
+        torch.testing.assert_close(gf, ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+        assert torch.equal(got, run())
 
 
 # ---- pixel-tile tensor-core gather (roi_align_bwd_tile.cu, "roi_align_bwd_impl" = 2) ------------------------------------
@@ -347,6 +350,13 @@ def test_bwd_bf16_tile_gather(N, C, H, W, R, bin_step):
         assert torch.equal(got, run())
         ops.PLAN_AHEAD[0] = False
         assert torch.equal(got, run())
+        from fewshotobjectdetection_imporove_via_text_feature_b200 import _lib
+        try:
+            for variant in (1, 2):                                  # pipelining variants of the gather: same bits
+                _lib.set_option("roi_bwd_tile_variant", variant)
+                assert torch.equal(got, run()), variant
+        finally:
+            _lib.set_option("roi_bwd_tile_variant", 0)
     with _bwd_impl(1):
         base = run()
     assert float((got.float() - base.float()).norm() / base.float().norm()) < 6e-3

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--impls", default="0,2")
     ap.add_argument("--steps", default="1,2")
     ap.add_argument("--variants", default="0,1,2,3,4", help="backward variants to time (see bench_bwd)")
+    ap.add_argument("--tile-variants", default="0", help="pipelining variants of the tile gather to time (roi_bwd_tile_variant)")
     ap.add_argument("--bwd", action="store_true", help="time the backward (b200_roi_align_bwd entry point) instead")
     a = ap.parse_args()
     B, P, C, H, W = a.images, a.props, 1024, 38, 50
@@ -72,8 +73,10 @@ def bench_bwd(a, feat, rois, offs, flush):
         # 0: fp32-table kernel, 1: CSR lists built inside the call, 2: CSR lists planned ahead,
         # 3: pixel-tile tensor-core gather with the plan built inside the call, 4: tile plan built ahead
         variants = [int(v) for v in a.variants.split(",")]
-        for impl in variants:
+        tvs = [int(v) for v in a.tile_variants.split(",")]
+        for impl, tv in [(i, 0) for i in variants if i != 4] + [(4, v) for v in tvs if 4 in variants]:
             _lib.set_option("roi_align_bwd_impl", {0: 0, 1: 1, 2: 1, 3: 2, 4: 2}[impl])
+            _lib.set_option("roi_bwd_tile_variant", tv)
             ops.PLAN_AHEAD[0] = impl in (2, 4)
             x = feat.clone().requires_grad_(True)
             out = ops.roi_align(x, rois, 7, 1 / 16, 0, True, channels_last_out=True, roi_batch_offsets=offs, bin_step=step)
@@ -89,9 +92,13 @@ def bench_bwd(a, feat, rois, offs, flush):
                 if i >= 3:
                     ts.append(e0.elapsed_time(e1))
             ms = float(np.median(ts))
-            res[impl] = x.grad.float()
-            print("bwd bin_step=%d impl=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
-                  (step, impl, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
+            if impl == 4 and tv != tvs[0]:
+                print("   tile variant %d == variant %d: %s" % (tv, tvs[0], torch.equal(res[4], x.grad.float())))
+            else:
+                res[impl] = x.grad.float()
+            print("bwd bin_step=%d impl=%d tv=%d  %.4f ms  %.1f GB/s (algorithmic %.1f MB)  min %.4f ms" %
+                  (step, impl, tv, ms, nbytes / ms / 1e6, nbytes / 1e6, min(ts)), flush=True)
+        _lib.set_option("roi_bwd_tile_variant", 0)
         if len(variants) < 5:
             continue
         d = (res[1] - res[0]).norm() / res[0].norm()
