@@ -217,7 +217,8 @@ def main_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.mode, args.classes, args.distill, 1), "cpu_baseline": cb,
+        # the own arm's workload; each timed step of this arm is the bounded sample `cpu_baseline.sample` names
+        "config": workload_config(args, args.mode, args.classes, args.distill, args.images_per_gpu), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -805,7 +806,8 @@ def main():
             "metric": METRIC, "value": world * B * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(args, args.mode, K, train and args.distill, B), cuda_graph=wl.graph_note),
+            # identical to the reference arm's `config` (same workload); how this arm executes it is beside it
+            "config": workload_config(args, args.mode, K, train and args.distill, B), "cuda_graph": wl.graph_note,
             "e2e": {"value": world * B * e2e_steps / (e2e["overlap"] * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "pipeline": "double-buffered device inputs: upload of step i+1 on a copy stream overlaps compute of step i",

@@ -8,7 +8,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads(open("gpurun_out/bench.log").read().strip().splitlines()[-1])
-    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"], d["config"]["cuda_graph"])
+    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"], d["cuda_graph"])
     print("stage", d["stage_ms"])
     r = d["roofline"]; print("roofline", r["achieved"], r["frac"], r["ms_per_step"], "in_step", r["in_step"]["achieved"], r["res5_convolutions"])
     print("roi", d["roofline_other"]["achieved"], d["roofline_other"]["standalone_op"]["fwd_frac"], d["roofline_other"]["standalone_op"]["bwd_frac"])
