@@ -673,6 +673,9 @@ def main():
         roi_op = {"bins": "7x7", "algorithmic_bytes": full_bytes,
                   "fwd_ms": float(np.median(tf)), "fwd_gbs": full_bytes / float(np.median(tf)) / 1e6,
                   "bwd_ms": float(np.median(tb)), "bwd_gbs": full_bytes / float(np.median(tb)) / 1e6,
+                  "bwd_kernel": "roi_bwd_tile_gather_kernel<1,false,3,8> (4x4-pixel tiles, mma.sync m16n8k16 bf16; plan = "
+                                "roi_slice_prepare_kernel + roi_bwd_tile_build_kernel, built ahead on the plan stream and complete "
+                                "before the timed launch)",
                   "note": "b200_roi_align_fwd / b200_roi_align_bwd_planned entry points, CUDA events, median of 3"}
         roi16_ms = float(np.median(ts16))
         del pooled_full, gfull, fmap

@@ -93,3 +93,86 @@ def test_plan_bytes_cover_the_tile_plan():
         assert L.b200_roi_align_bwd_plan_bytes(N, C + 8, H, W, R, 7, 7, bs) <= got
     assert L.b200_roi_align_bwd_plan_bytes(1, 1024, 300, 50, 10, 7, 7, 1) == 0        # map too tall for the byte-packed windows
     assert tile_plan_bytes(8, 38, 50, 4160, 7, 7, 2) < 200 << 20                       # bench shape: well under 200 MiB
+
+
+def _axis_windows(lo_px, hi_px, P, size, bin_step):
+    """Per computed bin: (first pixel, summed bilinear weights per pixel of the window) — roi_slice_prepare's tables
+    (adaptive sampling grid, aligned=True), fp32 step by step like roi_geom.cuh."""
+    start = f32(lo_px) - f32(0.5)
+    length = (f32(hi_px) - f32(0.5)) - start
+    bin_sz = length / f32(P)
+    g = max(int(math.ceil(float(length / f32(P)))), 0)
+    wins = []
+    for p in range(0, P, bin_step):
+        first, w = None, {}
+        for i in range(g):
+            c = (start + f32(p) * bin_sz) + (f32(i) + f32(0.5)) * bin_sz / f32(g)
+            if c < -1.0 or c > size:
+                continue
+            c = max(c, f32(0.0))
+            lo = int(c)
+            if lo >= size - 1:
+                lo = hi = size - 1
+                c = f32(lo)
+            else:
+                hi = lo + 1
+            l = f32(c) - f32(lo)
+            first = lo if first is None else first
+            w[lo] = w.get(lo, f32(0)) + (f32(1) - l)
+            w[hi] = w.get(hi, f32(0)) + l
+        wins.append((first, w))
+    return wins, max(g, 1)
+
+
+@pytest.mark.parametrize("bin_step", [1, 2])
+def test_tile_gather_restatement_vs_oracle(bin_step):
+    """numpy restatement of the pixel-tile backward (4 x 4 tiles; entries = (ROI, bin) pairs whose window meets the tile, in
+    ROI then bin order; weight bf16(bf16(a / count) * b); fp32 accumulation; bf16 output) against the oracle's
+    roi_align_bwd (pinned on torchvision) at the GPU test's bars."""
+    import torch
+    from oracle import oracle as O
+    rng = np.random.default_rng(5 + bin_step)
+    N, C, H, W, R, P, scale = 1, 8, 13, 18, 14, 7, 1 / 16
+    boxes = []
+    for _ in range(R):
+        cy, cx = rng.uniform(0, H / scale), rng.uniform(0, W / scale)
+        h, w = np.exp(rng.uniform(np.log(12), np.log(H / scale))), np.exp(rng.uniform(np.log(12), np.log(W / scale)))
+        boxes.append([max(cx - w / 2, 0), max(cy - h / 2, 0), min(cx + w / 2, W / scale), min(cy + h / 2, H / scale)])
+    boxes = torch.tensor(boxes, dtype=torch.float32)
+    rois = O.boxes_to_rois([boxes])
+    nb = _ceil_div(P, bin_step)
+    g = torch.randn(R, C, nb, nb, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    gfull = torch.zeros(R, C, P, P)
+    gfull[:, :, ::bin_step, ::bin_step] = g.float()
+    ref = O.roi_align_bwd(gfull, rois, (N, C, H, W), scale, 0, True).numpy()
+
+    bf = lambda v: float(torch.tensor(float(v)).to(torch.bfloat16))
+    gn = g.float().numpy()
+    out = np.zeros((H, W, C), np.float32)
+    geo = []
+    for r in range(R):
+        x1, y1, x2, y2 = (f32(v) * f32(scale) for v in boxes[r].tolist())
+        wy, gy = _axis_windows(y1, y2, P, H, bin_step)
+        wx, gx = _axis_windows(x1, x2, P, W, bin_step)
+        geo.append((wy, wx, f32(1.0) / f32(gy * gx)))
+    for ty in range(0, H, TILE):
+        for tx in range(0, W, TILE):
+            acc = np.zeros((TILE, TILE, C), np.float32)
+            for r, (wy, wx, inv) in enumerate(geo):
+                for pho, (fy, ay) in enumerate(wy):
+                    if fy is None or max(ay) < ty or min(ay) >= ty + TILE:
+                        continue
+                    for pwo, (fx, bx) in enumerate(wx):
+                        if fx is None or max(bx) < tx or min(bx) >= tx + TILE:
+                            continue
+                        for i in range(TILE):
+                            for j in range(TILE):
+                                a, b = ay.get(ty + i), bx.get(tx + j)
+                                if a is None or b is None:
+                                    continue
+                                wgt = bf(f32(bf(a * inv)) * b)
+                                acc[i, j] += f32(wgt) * gn[r, :, pho, pwo]
+            out[ty:ty + TILE, tx:tx + TILE] = acc[: H - ty, : W - tx]
+    got = torch.tensor(out).to(torch.bfloat16).float().permute(2, 0, 1)[None].numpy()
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 8e-3
+    np.testing.assert_allclose(got, ref, rtol=2e-2, atol=2e-2 * np.abs(ref).max())
