@@ -556,7 +556,7 @@ extern "C" int b200_set_option(const char* key, int value) {
     return B200_OK;
   }
   if (strcmp(key, "roi_bwd_tile_variant") == 0) {
-    B200_CHECK_ARG(value >= 0 && value <= 2, "set_option: roi_bwd_tile_variant must be in [0, 2]");
+    B200_CHECK_ARG(value >= 0 && value <= 3, "set_option: roi_bwd_tile_variant must be in [0, 3]");
     g_roi_bwd_tile_variant = value;
     return B200_OK;
   }

@@ -37,6 +37,7 @@ constexpr int kBlkBytes = kBlkABytes + kBlkEntries * 4;   // + the gradient row 
 constexpr int kTileChunk = 64;                // channels per warp of the gather kernel
 constexpr int kTileWarps = 8;
 constexpr int kBuildThreads = 256;
+constexpr int kOrderBuckets = 32;             // heaviest-first launch order of the gather: tiles bucketed by block count
 
 __device__ __forceinline__ void mma_bf16_16816(float* d, const uint4 a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -148,7 +149,7 @@ __device__ __forceinline__ void tile_write_entry(unsigned char* __restrict__ blo
 __global__ void __launch_bounds__(kBuildThreads)
 roi_bwd_tile_build_kernel(const unsigned char* __restrict__ recs, const float* __restrict__ rois,
                           const int32_t* __restrict__ roi_offsets, int2* __restrict__ tiles, unsigned int* __restrict__ counter,
-                          unsigned char* __restrict__ blocks, unsigned int capacity_blocks, int H, int W, int TXn, int PH,
+                          int* __restrict__ order_lists, unsigned char* __restrict__ blocks, unsigned int capacity_blocks, int H, int W, int TXn, int PH,
                           int PW, int bin_step, float scale, int sampling_ratio, int aligned) {
   __shared__ int s_warp[kBuildThreads / 32];
   __shared__ unsigned int s_base;
@@ -178,6 +179,11 @@ roi_bwd_tile_build_kernel(const unsigned char* __restrict__ recs, const float* _
     // the capacity is the worst case (launch function), so this never fires; a tile that would not fit is left empty
     const bool fits = base + nblk <= capacity_blocks;
     tiles[(size_t)n * gridDim.x + tile] = make_int2((int)base, fits ? (int)nblk : 0);
+    // launch order of the gather (scheduling only, never the arithmetic): the tile joins the bucket of its block count;
+    // counter[1 + bucket] = tiles in the bucket, order_lists[bucket][.] = their indices in arrival order
+    const int bkt = min(kOrderBuckets - 1, (fits ? (int)nblk : 0) / 2);
+    const int ntiles = (int)(gridDim.x * gridDim.y);
+    order_lists[(size_t)bkt * ntiles + atomicAdd(counter + 1 + bkt, 1u)] = n * (int)gridDim.x + tile;
     s_base = base;
     s_total = fits ? total : 0;
   }
@@ -246,18 +252,36 @@ template <> struct RowSeg<4> {
 // kUnroll plan blocks per iteration, optionally double-buffered in registers, kMinCtas CTAs per SM.  Measured
 // (profiles/r02_roi_bwd_tile_variants.txt): one block per iteration beats two (0.072 vs 0.094 ms), register double
 // buffering and a per-warp cp.async ring in shared memory (2 x the L2 sectors: 16-byte LDGSTS requests do not coalesce
-// into sectors across lanes; MIO throttle) were slower than the plain loop.
+// into sectors across lanes; MIO throttle) were slower than the plain loop.  Launching the tiles heaviest first (the plan
+// builder buckets them by block count) takes the tail off the last wave: 0.184 -> 0.159 ms for all 49 bins.
 template <int kUnroll, bool kDouble, int kMinCtas, int NT>
 __global__ void __launch_bounds__(kTileWarps * 32, kMinCtas)
 roi_bwd_tile_gather_kernel(const __nv_bfloat16* __restrict__ g, const int2* __restrict__ tiles,
                            const unsigned char* __restrict__ blocks, __nv_bfloat16* __restrict__ grad_feat, int ntiles, int H,
-                           int W, int TYn, int TXn, int C) {
+                           int W, int TYn, int TXn, int C, const unsigned int* __restrict__ order_counts,
+                           const int* __restrict__ order_lists) {
   constexpr int kChunk = 8 * NT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = C / kChunk;
   const long long wi = (long long)blockIdx.x * kTileWarps + warp;
   if (wi >= (long long)ntiles * chunks) return;
-  const int tile = (int)(wi / chunks), chunk = (int)(wi - (long long)tile * chunks);
+  int tile = (int)(wi / chunks);
+  const int chunk = (int)(wi - (long long)tile * chunks);
+  if (order_counts != nullptr) {
+    // heaviest tiles first (longest-processing-time order against the tail of the last wave): rank -> bucket -> tile
+    const int rank = tile;
+    const int c = (int)__ldg(order_counts + 1 + (kOrderBuckets - 1 - lane));      // lane 0 <-> the heaviest bucket
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, incl > rank);               // the counts add up to ntiles > rank
+    const int l = __ffs(m) - 1;
+    const int before = __shfl_sync(0xffffffffu, incl - c, l);
+    tile = __ldg(order_lists + (size_t)(kOrderBuckets - 1 - l) * ntiles + (rank - before));
+  }
   const int gq = lane >> 2, t = lane & 3;
   const int2 td = __ldg(tiles + tile);
   const unsigned char* bp = blocks + (size_t)(unsigned)td.x * kBlkBytes;
@@ -375,7 +399,8 @@ bool roi_bwd_tile_eligible(int C, int H, int W, int PH, int PW, int bin_step) {
 struct TilePlan {
   unsigned char* recs;
   int2* tiles;
-  unsigned int* counter;
+  unsigned int* counter;      // [0]: blocks allocated, [1 .. kOrderBuckets]: tiles per order bucket
+  int* order_lists;           // [kOrderBuckets][ntiles]
   unsigned char* blocks;
   size_t capacity_blocks;
   int TYn, TXn;
@@ -393,7 +418,7 @@ size_t roi_bwd_tile_workspace_bytes(int N, int H, int W, int R, int PH, int PW, 
   const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
   const size_t ntiles = (size_t)N * ceil_div(H, kTileSide) * ceil_div(W, kTileSide);
   return align_up((size_t)max(R, 1) * kRecBytes, 256) + align_up(ntiles * sizeof(int2), 256) + 256 +
-         tile_capacity_blocks(N, H, W, R, PHO, PWO) * kBlkBytes;
+         align_up(ntiles * kOrderBuckets * sizeof(int), 256) + tile_capacity_blocks(N, H, W, R, PHO, PWO) * kBlkBytes;
 }
 
 static TilePlan carve_tile_plan(void* workspace, int N, int H, int W, int R, int PHO, int PWO) {
@@ -405,6 +430,7 @@ static TilePlan carve_tile_plan(void* workspace, int N, int H, int W, int R, int
   pl.recs = p;                       p += align_up((size_t)max(R, 1) * kRecBytes, 256);
   pl.tiles = (int2*)p;               p += align_up(ntiles * sizeof(int2), 256);
   pl.counter = (unsigned int*)p;     p += 256;
+  pl.order_lists = (int*)p;          p += align_up(ntiles * kOrderBuckets * sizeof(int), 256);
   pl.blocks = p;
   pl.capacity_blocks = tile_capacity_blocks(N, H, W, R, PHO, PWO);
   return pl;
@@ -421,9 +447,9 @@ int launch_roi_bwd_tile_plan(const float* rois, const int32_t* roi_offsets, int 
   }
   int rc = launch_roi_slice_prepare(rois, pl.recs, R, H, W, PH, PW, bin_step, scale, sr, aligned, st);
   if (rc != B200_OK) return rc;
-  B200_CUDA_CALL(cudaMemsetAsync(pl.counter, 0, sizeof(unsigned int), st));
+  B200_CUDA_CALL(cudaMemsetAsync(pl.counter, 0, 256, st));
   roi_bwd_tile_build_kernel<<<dim3(pl.TYn * pl.TXn, N), kBuildThreads, 0, st>>>(
-      pl.recs, rois, roi_offsets, pl.tiles, pl.counter, pl.blocks, (unsigned int)pl.capacity_blocks, H, W, pl.TXn, PH, PW,
+      pl.recs, rois, roi_offsets, pl.tiles, pl.counter, pl.order_lists, pl.blocks, (unsigned int)pl.capacity_blocks, H, W, pl.TXn, PH, PW,
       bin_step, scale, sr, aligned);
   B200_CUDA_LAUNCH_CHECK("roi_bwd_tile_build");
   return B200_OK;
@@ -434,16 +460,18 @@ int launch_roi_bwd_tile_gather(const __nv_bfloat16* g, const void* workspace, __
   const int PHO = ceil_div(PH, bin_step), PWO = ceil_div(PW, bin_step);
   const TilePlan pl = carve_tile_plan(const_cast<void*>(workspace), N, H, W, R, PHO, PWO);
   const int ntiles = N * pl.TYn * pl.TXn;
-#define B200_TILE_GATHER(U, DB, MINB, NT)                                                                            \
+#define B200_TILE_GATHER(U, DB, MINB, NT, ORDERED)                                                                   \
   do {                                                                                                                 \
     const long long warps = (long long)ntiles * (C / (8 * NT));                                                        \
     roi_bwd_tile_gather_kernel<U, DB, MINB, NT><<<(unsigned)((warps + kTileWarps - 1) / kTileWarps), kTileWarps * 32, 0, st>>>( \
-        g, pl.tiles, pl.blocks, grad_feat, ntiles, H, W, pl.TYn, pl.TXn, C);                                            \
+        g, pl.tiles, pl.blocks, grad_feat, ntiles, H, W, pl.TYn, pl.TXn, C, (ORDERED) ? pl.counter : nullptr,            \
+        pl.order_lists);                                                                                               \
   } while (0)
   switch (g_roi_bwd_tile_variant) {
-    case 1: B200_TILE_GATHER(2, false, 2, 8); break;    // two plan blocks per iteration, 16 warps / SM: 0.094 ms (16 bins)
-    case 2: B200_TILE_GATHER(1, false, 4, 4); break;    // 32-channel warps, 32 warps / SM: 0.083 ms
-    default: B200_TILE_GATHER(1, false, 3, 8); break;   // one block per iteration, 24 warps / SM: 0.072 ms
+    case 1: B200_TILE_GATHER(2, false, 2, 8, false); break;    // two plan blocks per iteration, 16 warps / SM: 0.094 ms (16 bins)
+    case 2: B200_TILE_GATHER(1, false, 4, 4, false); break;    // 32-channel warps, 32 warps / SM: 0.083 ms
+    case 3: B200_TILE_GATHER(1, false, 3, 8, false); break;    // the default's kernel, tiles in map order: 0.072 ms
+    default: B200_TILE_GATHER(1, false, 3, 8, true); break;    // one block per iteration, 24 warps / SM, heaviest tiles first: 0.067 ms
   }
 #undef B200_TILE_GATHER
   B200_CUDA_LAUNCH_CHECK("roi_bwd_tile_gather");

@@ -50,7 +50,8 @@ B200_API const char* b200_last_error(void);
  *                          2 = 4x4-pixel-tile gather on mma.sync (default; C % 64 == 0, else 1).  The format of a
  *                          b200_roi_align_bwd_plan buffer follows the setting at plan time; b200_roi_align_bwd_planned
  *                          must be called under the same setting
- *   "roi_bwd_tile_variant": 0 (default) / 1 / 2 = pipelining variants of the tile gather, same bits */
+ *   "roi_bwd_tile_variant": 0 (default: tiles launched heaviest first) / 1 / 2 (pipelining variants) / 3 (the default's
+ *                          kernel in map order) of the tile gather, same bits */
 B200_API int b200_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -25,7 +25,8 @@ def tile_plan_bytes(N, H, W, R, PH, PW, bin_step):
     per_roi = _ceil_div(H + 8 * pho + 2, TILE) * _ceil_div(W + 8 * pwo + 2, TILE)
     ntiles = N * _ceil_div(H, TILE) * _ceil_div(W, TILE)
     blocks = _ceil_div(max(R, 1) * per_roi, BLK_ENTRIES) + ntiles
-    return _align_up(max(R, 1) * REC_BYTES, 256) + _align_up(ntiles * 8, 256) + 256 + blocks * BLK_BYTES
+    return (_align_up(max(R, 1) * REC_BYTES, 256) + _align_up(ntiles * 8, 256) + 256 + _align_up(ntiles * 32 * 4, 256) +
+            blocks * BLK_BYTES)
 
 
 def axis_tile_bin_pairs(lo_px, hi_px, P, size, sampling_ratio, bin_step):

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--impls", default="0,2")
     ap.add_argument("--steps", default="1,2")
     ap.add_argument("--variants", default="0,1,2,3,4", help="backward variants to time (see bench_bwd)")
-    ap.add_argument("--tile-variants", default="0", help="pipelining variants of the tile gather to time (roi_bwd_tile_variant)")
+    ap.add_argument("--tile-variants", default="0", help="variants of the tile gather to time (roi_bwd_tile_variant: 0 default = heaviest tile first, 1 / 2 pipelining, 3 map order)")
     ap.add_argument("--bwd", action="store_true", help="time the backward (b200_roi_align_bwd entry point) instead")
     a = ap.parse_args()
     B, P, C, H, W = a.images, a.props, 1024, 38, 50
