@@ -1,5 +1,6 @@
-// P1b: ROIAlign backward, per-pixel CSR gather (bf16, channels-last) — atomic-free, deterministic, the fine-tune
-// path's default.  Reference: autograd of the roi_align call at defrcn/modeling/roi_heads/roi_heads.py:340
+// P1b: ROIAlign backward, per-pixel CSR gather (bf16, channels-last) — atomic-free, deterministic.  The fine-tune path's
+// default until the pixel-tile gather (roi_align_bwd_tile.cu) replaced it for C % 64 == 0; still "roi_align_bwd_impl" = 1
+// and the path of every other channel count.  Reference: autograd of the roi_align call at defrcn/modeling/roi_heads/roi_heads.py:340
 // (torchvision scatters with atomicAdd; fine-tuning reaches it with BACKWARD_SCALE = 0.001 through the GDL).
 //
 //   grad_feat[n,y,x,c] = sum over ROIs r of image n (index order), computed bins (ph,pw) whose pixel windows contain
